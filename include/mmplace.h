@@ -1,0 +1,229 @@
+/*
+ * mmplace.h — C ABI of libmmplace: a B200-native (sm_100a CUDA) placement / LRU-eviction solver that drops in
+ * behind ModelMesh's decision API.  Plain pointers and sizes only; no CUDA/torch types.  This is the boundary a
+ * JNI shim binds (see INTEGRATION.md for the Java side).  Reference = kserve/modelmesh @ ea13cdc5;
+ * MM = src/main/java/com/ibm/watson/modelmesh/ModelMesh.java, IR = InstanceRecord.java, MR = ModelRecord.java,
+ * TCM = TypeConstraintManager.java, UT = UpgradeTracker.java, CLHM = clhm/ConcurrentLinkedHashMap.java.
+ *
+ * Every function returns >= 0 on success or a negative MMP_E_* code; mmp_last_error() gives the message.
+ * The library never falls back to a CPU path: if no CUDA device is usable, mmp_fleet_create fails with MMP_E_CUDA.
+ *
+ * Threading: ingest calls (mmp_instance_*, mmp_model*, mmp_types_*, mmp_replicasets_set, mmp_fleet_commit) are
+ * single-writer (the reference serialises them on TypeConstraintManager.executor(), TCM:145-147, MM:1423-1427).
+ * mmp_place_* / mmp_stats / mmp_reaper_select may be called from any number of threads concurrently with each
+ * other and with ingest; they always see the last committed snapshot epoch.
+ */
+#ifndef MMPLACE_H
+#define MMPLACE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMP_ABI_VERSION 1
+
+enum {
+  MMP_OK = 0,
+  MMP_E_ARG = -1,    /* bad argument / out-of-range index / value outside the supported domain */
+  MMP_E_CUDA = -2,   /* CUDA runtime failure (including "no device") */
+  MMP_E_NCCL = -3,   /* collective failure in the instance-sharded path */
+  MMP_E_EPOCH = -4,  /* no committed snapshot yet */
+  MMP_E_NOMEM = -5,
+  MMP_E_STATE = -6
+};
+
+/* per-decision result codes in mmp_decision_out.target */
+enum {
+  MMP_TARGET_NONE = -1, /* getNext returned null        (MM:4796,4801,4872,4941) */
+  MMP_TARGET_SELF = -2  /* getNext returned ABORT_REQUEST (MM:4894,4932,4990)    */
+};
+
+typedef struct mmp_fleet mmp_fleet;
+
+/* Replaces the per-JVM constants ModelMesh derives in initialize() (MM:697, MM:767-771). */
+typedef struct {
+  int64_t min_space_units;           /* isFull threshold, MM:4640-4642 / MM:767-769 */
+  int64_t min_churn_age_ms;          /* MM:697 */
+  int32_t default_model_size_units;  /* MM:712 (runtime's default model size / 8 KiB) */
+  int32_t max_instances;             /* capacity of the instance index space (<= 65536) */
+  int32_t max_models;                /* capacity of the model index space */
+  int32_t device;                    /* CUDA device ordinal */
+  int32_t shard_rank;                /* instance-shard of this process (0 when not sharded) */
+  int32_t shard_count;               /* number of instance shards (1 when not sharded) */
+  uint32_t flags;                    /* reserved, 0 */
+  uint32_t reserved;
+} mmp_config;
+
+/* Numeric part of InstanceRecord (IR:37-73).  Strings travel beside it in mmp_instance_upsert. */
+typedef struct {
+  int64_t lru_time;      /* IR:37  "lruTime", Long.MAX_VALUE when the cache is empty */
+  int64_t capacity;      /* IR:41  "cap"  units of 8 KiB */
+  int64_t used;          /* IR:43  "used" */
+  int64_t start_time;    /* IR:60  "startTime" */
+  int64_t vers;          /* IR:62  "vers" */
+  int32_t count;         /* IR:39  "count" */
+  int32_t l_threads;     /* IR:45  "lThreads" */
+  int32_t l_in_prog;     /* IR:47  "lInProg" */
+  int32_t rpm;           /* IR:51  "rpm"; must be <= 500,000,000 */
+  int32_t shutting_down; /* IR:56  "shutdown": treated as a deletion, MM:1462-1464 */
+  int32_t active;        /* 1 if the instance is in litelinks' service-instance list (siMap, MM:4765,4778) */
+} mmp_instance_row;
+
+/* Per-model registry state needed on the path (MR:61-114): 24 bytes. */
+typedef struct {
+  int64_t last_used;     /* MR:105 "lu" */
+  int32_t size_units;    /* CacheEntry weight / KNOWN_SIZE (MM:5160-5178) */
+  int32_t rpm;           /* request rate, informational */
+  uint16_t type_id;      /* from mmp_type_id(); 0 = a type with no configured constraints */
+  uint8_t copy_count;    /* MR:69  instanceIds.size() (saturating at 255) */
+  uint8_t fail_count;    /* MR:73  loadFailedInstanceIds.size() */
+  uint32_t reserved;
+} mmp_model_row;
+
+/* One call of CacheMissForwardingLB.getNext (MM:4776-5004): 32 bytes.
+ * The model's exclusion set (loaded ∪ failed, MM:4735-4743) and type come from the model table. */
+#define MMP_DF_FAVOUR_SELF 1u        /* CacheMissExcludeSet.favourSelf (MM:4721) */
+#define MMP_DF_MODEL_LAST_USED 2u    /* take last_used from the model row instead of this struct */
+typedef struct {
+  int32_t model;        /* model index */
+  int32_t self;         /* instance index of the calling pod ("instanceId", MM:4780,4808) */
+  int64_t last_used;    /* CacheMissExcludeSet.lastUsedTime (MM:4730, 4949) */
+  uint32_t flags;       /* MMP_DF_* */
+  int32_t fresh;        /* index into the fresh[] rows of the call (getFreshInstanceRecord MM:5369), or -1:
+                           self's published row with rpm = 0 (the reference never sets rpm on the fresh record) */
+  int32_t extra_off;    /* offset into extra[] of this decision's additional excluded instance indices
+                           (tried-this-request ∪ explicit, MM:4706-4715) */
+  int32_t extra_n;      /* how many (<= 16) */
+} mmp_decision_in;
+
+typedef struct {
+  int32_t target;        /* instance index, MMP_TARGET_NONE or MMP_TARGET_SELF */
+  int32_t n_candidates;  /* candidates.size() at MM:4939 (0 if getNext returned before that) */
+} mmp_decision_out;
+
+/* Optional per-decision trace for parity checking (everything before and after the random draw). */
+#define MMP_TF_RS_RETRY 1       /* replicaset filter dropped and retried (MM:4798-4802) */
+#define MMP_TF_SIMPLE 2         /* reached the simple-case walk (MM:4889) */
+#define MMP_TF_BEST_FULL 4      /* bestIsFull (MM:4811) */
+#define MMP_TF_FAVOUR_EXIT 8    /* returned through a favourSelf short-circuit */
+#define MMP_TF_KEEP_BEST 16     /* best survived the rpm filter */
+#define MMP_TF_KEEP_OTHERS 32   /* non-self candidates survived the rpm filter (all share one recorded rpm, N2) */
+#define MMP_TF_KEEP_SELF 64     /* the self candidate survived the rpm filter */
+#define MMP_TF_PREF_B 128       /* non-simple case (b) with preferred candidates (MM:4866-4880) */
+typedef struct {
+  int32_t best;          /* bestIid after preferred handling (instance index), -1 if none */
+  int32_t n_remaining;   /* remainingCount (MM:4956) */
+  int32_t pick_index;    /* index of the chosen non-null candidate (MM:4981) */
+  int32_t flags;         /* MMP_TF_* */
+  int32_t cut_rank;      /* rank (position in PLACEMENT_ORDER) of the first violator, INT32_MAX if none */
+  int32_t best_rank;
+  int32_t reserved[2];
+} mmp_decision_trace;
+
+typedef struct {  /* ModelMesh.ClusterStats MM:1570-1591 */
+  int64_t total_capacity, total_free, global_lru;
+  int32_t instance_count, model_copy_count;
+} mmp_cluster_stats;
+
+/* ---- lifecycle ---- */
+int32_t mmp_abi_version(void);
+int32_t mmp_fleet_create(const mmp_config *cfg, mmp_fleet **out);
+void mmp_fleet_destroy(mmp_fleet *);
+const char *mmp_last_error(mmp_fleet *); /* thread-local message of the last failing call (fleet may be NULL) */
+
+/* ---- plug point 2: fleet-state ingest.  Replaces handleInstanceTableChange (MM:1455-1568) feeding
+ * clusterState, and ModelMesh.event(type,key,ModelRecord) (MM:2807-2854). ---- */
+/* id/loc/zone/labels are UTF-8; ordered as UTF-16 code units like String.compareTo (MM:4697-4700). loc/zone may be NULL. */
+int32_t mmp_instance_upsert(mmp_fleet *, int32_t idx, const mmp_instance_row *row, const char *id, const char *loc,
+                            const char *zone, const char *const *labels, int32_t n_labels);
+/* update only the numeric columns of an instance already present (the common KV update event) */
+int32_t mmp_instance_update(mmp_fleet *, int32_t idx, const mmp_instance_row *row);
+int32_t mmp_instance_remove(mmp_fleet *, int32_t idx);
+/* MM_TYPE_CONSTRAINTS json (TCM:79-98, 193-206; config/examples/type-constraints-example):
+ * {"type": {"required": ["l1",..], "preferred": ["l2",..]}, "_default": {...}}.  NULL/"" = typeConstraints == null. */
+int32_t mmp_types_set_json(mmp_fleet *, const char *json);
+/* type id for a model-type name: >= 1 for configured types, 0 for any other name (falls to "_default" if configured). */
+int32_t mmp_type_id(mmp_fleet *, const char *type_name);
+/* UpgradeTracker.getLikelyReplacedReplicaSets() keys (UT:78): 6-char replicaset prefixes to avoid (MM:4769-4770). */
+int32_t mmp_replicasets_set(mmp_fleet *, const char *const *prefixes, int32_t n);
+/* instance_ids = loaded ∪ failed instance indices of the model (MR:69,73): the CacheMissExcludeSet row (MM:4735-4743) */
+int32_t mmp_model_upsert(mmp_fleet *, int32_t model, const mmp_model_row *row, const int32_t *instance_ids, int32_t n_ids);
+/* bulk form: models [first, first+n); edge_off has n+1 entries indexing edge_inst */
+int32_t mmp_models_bulk(mmp_fleet *, int32_t first, int32_t n, const mmp_model_row *rows, const int64_t *edge_off,
+                        const int32_t *edge_inst);
+/* Publish everything ingested since the last commit as a new snapshot epoch: recomputes PLACEMENT_ORDER ranks
+ * (MM:4646-4703), type/preferred masks (TCM:680-747), stats columns and the rank-space exclusion bitmap in HBM.
+ * Returns the new epoch number (>= 1). */
+int32_t mmp_fleet_commit(mmp_fleet *);
+
+/* ---- plug point 1: placement.  Replaces CacheMissForwardingLB.getNext (MM:4776-5004). ---- */
+/* Host buffers in, host buffers out (copies included).  fresh[]/extra[] may be NULL when unused. */
+int32_t mmp_place_batch(mmp_fleet *, const mmp_decision_in *in, int32_t n, const mmp_instance_row *fresh, int32_t n_fresh,
+                        const int32_t *extra, int32_t n_extra, mmp_decision_out *out, int64_t now_ms, uint64_t seed);
+/* Same with the optional trace (trace may be NULL) and candidate masks: cand_mask (may be NULL) receives, per decision,
+ * mmp_row_words() 32-bit words whose bit r is set iff the instance at PLACEMENT_ORDER rank r is a candidate other than best. */
+int32_t mmp_place_batch_trace(mmp_fleet *, const mmp_decision_in *in, int32_t n, const mmp_instance_row *fresh,
+                              int32_t n_fresh, const int32_t *extra, int32_t n_extra, mmp_decision_out *out,
+                              mmp_decision_trace *trace, uint32_t *cand_mask, int64_t now_ms, uint64_t seed);
+/* Single decision (latency path, B = 1). */
+int32_t mmp_place_one(mmp_fleet *, const mmp_decision_in *in, const mmp_instance_row *fresh, const int32_t *extra,
+                      mmp_decision_out *out, int64_t now_ms, uint64_t seed);
+/* Device-resident variant used to time the kernel alone: d_in/d_out are device pointers obtained from
+ * mmp_device_alloc; returns after the kernel has been enqueued AND completed; *kernel_ms (may be NULL) receives the
+ * CUDA-event duration of the scoring kernel on its launch stream. */
+int32_t mmp_place_batch_device(mmp_fleet *, const void *d_in, int32_t n, void *d_out, int64_t now_ms, uint64_t seed,
+                               float *kernel_ms);
+int32_t mmp_device_alloc(mmp_fleet *, int64_t bytes, void **out);
+int32_t mmp_device_free(mmp_fleet *, void *p);
+int32_t mmp_device_upload(mmp_fleet *, void *dst, const void *src, int64_t bytes);
+int32_t mmp_device_download(mmp_fleet *, void *dst, const void *src, int64_t bytes);
+int32_t mmp_flush_l2(mmp_fleet *); /* writes a buffer larger than L2 (bench hygiene) */
+
+/* ---- snapshot introspection ---- */
+int32_t mmp_row_words(mmp_fleet *);                                   /* 32-bit words per exclusion-bitmap row */
+int32_t mmp_live_instances(mmp_fleet *);                              /* number of ranked instances in the snapshot */
+int32_t mmp_cluster_order(mmp_fleet *, int32_t *out_idx, int32_t cap); /* instance idx by ascending PLACEMENT_ORDER rank */
+/* candidate/preferred membership of a type id as computed at commit (TCM:242-251): 0/1 per instance idx;
+ * *preferred_null = 1 when getPreferredInstances would return null */
+int32_t mmp_type_sets(mmp_fleet *, int32_t type_id, int32_t n_idx, uint8_t *allowed, int32_t *allowed_null,
+                      uint8_t *preferred, int32_t *preferred_null);
+int64_t mmp_kernel_launches(mmp_fleet *);                             /* count of library kernels launched so far */
+
+/* ---- plug point 4: batch scans ---- */
+/* ClusterStats (MM:1570-1591, ISST:63-92) reduced on the device from the snapshot: out[0] = whole cluster, then one
+ * per prohibited-type-set partition (TCM:557-579) in TCM.getPartitionStats order (TCM:264-292). part_ids gets the
+ * partition id of each entry (-1 for the cluster). Returns the number of entries. */
+int32_t mmp_stats(mmp_fleet *, mmp_cluster_stats *out, int32_t *part_ids, int32_t cap);
+int32_t mmp_instance_partition(mmp_fleet *, int32_t idx);
+/* Reaper candidate scan + proactive-load selection (MM:6574-6577, 6616-6735) for one partition (-1: no type
+ * constraints).  taken[] (max_models bytes, in/out, may be NULL) mirrors allCandidates.set(i, null).
+ * Writes the selected model indices most-recently-used first; returns how many. */
+int32_t mmp_reaper_select(mmp_fleet *, int32_t partition, int64_t now_ms, uint8_t *taken, int32_t *out_models, int32_t cap);
+
+/* ---- plug point 3: per-instance time-ordered weighted LRU (CLHM:821-858, 590-652, 329-352; LD:243-288) ---- */
+enum { MMP_LRU_INSERT = 0, MMP_LRU_TOUCH = 1, MMP_LRU_RESIZE = 2, MMP_LRU_REMOVE = 3, MMP_LRU_SET_CAPACITY = 4 };
+typedef struct {
+  int32_t op;         /* MMP_LRU_* */
+  int32_t instance;   /* which instance's cache */
+  int32_t model;      /* key */
+  int32_t weight;     /* INSERT/RESIZE: entry weight; SET_CAPACITY: unused */
+  int64_t last_used;  /* INSERT/TOUCH: 0 = now;  SET_CAPACITY: the new capacity */
+} mmp_lru_event;
+typedef struct {
+  int32_t instance, model;
+  int64_t last_used;
+  int32_t weight;
+  int32_t event;      /* index of the event that triggered the eviction */
+} mmp_eviction;
+/* (re)initialise the LRU store: one cache per instance index with the given capacities (units) */
+int32_t mmp_lru_init(mmp_fleet *, int32_t n_instances, const int64_t *capacity, int32_t slots_per_instance);
+/* applies events in order per instance (instances are independent); evictions are returned grouped by event order
+ * within each instance, oldest first (CLHM:329-352).  Returns the number of evictions (<= cap written). */
+int32_t mmp_lru_apply(mmp_fleet *, const mmp_lru_event *ev, int32_t n, int64_t now_ms, mmp_eviction *out, int32_t cap);
+/* per-instance oldestTime() (CLHM:1125-1133, -1 if empty), weightedSize() and size() */
+int32_t mmp_lru_state(mmp_fleet *, int32_t n_instances, int64_t *oldest, int64_t *weighted, int32_t *count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

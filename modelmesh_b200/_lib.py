@@ -1,0 +1,135 @@
+"""ctypes binding of the libmmplace C ABI (include/mmplace.h).
+
+The shipped library is ``modelmesh_b200/csrc/libmmplace.so`` (built by ``__graft_entry__.build()`` /
+``python -m modelmesh_b200.build``).  There is no CPU implementation behind this package: ``load_product()`` raises if
+the CUDA library has not been built, and ``mmp_fleet_create`` fails with MMP_E_CUDA when no device is usable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PRODUCT_SO = os.path.join(HERE, "csrc", "libmmplace.so")
+
+# numpy mirrors of the C structs (include/mmplace.h); itemsize is asserted against the header's layout in tests
+INSTANCE_ROW = np.dtype(
+    [("lru_time", "<i8"), ("capacity", "<i8"), ("used", "<i8"), ("start_time", "<i8"), ("vers", "<i8"),
+     ("count", "<i4"), ("l_threads", "<i4"), ("l_in_prog", "<i4"), ("rpm", "<i4"), ("shutting_down", "<i4"),
+     ("active", "<i4")], align=True)
+MODEL_ROW = np.dtype(
+    [("last_used", "<i8"), ("size_units", "<i4"), ("rpm", "<i4"), ("type_id", "<u2"), ("copy_count", "u1"),
+     ("fail_count", "u1"), ("reserved", "<u4")], align=True)
+DECISION_IN = np.dtype(
+    [("model", "<i4"), ("self", "<i4"), ("last_used", "<i8"), ("flags", "<u4"), ("fresh", "<i4"),
+     ("extra_off", "<i4"), ("extra_n", "<i4")], align=True)
+DECISION_OUT = np.dtype([("target", "<i4"), ("n_candidates", "<i4")], align=True)
+DECISION_TRACE = np.dtype(
+    [("best", "<i4"), ("n_remaining", "<i4"), ("pick_index", "<i4"), ("flags", "<i4"), ("cut_rank", "<i4"),
+     ("best_rank", "<i4"), ("reserved", "<i4", (2,))], align=True)
+CLUSTER_STATS = np.dtype(
+    [("total_capacity", "<i8"), ("total_free", "<i8"), ("global_lru", "<i8"), ("instance_count", "<i4"),
+     ("model_copy_count", "<i4")], align=True)
+LRU_EVENT = np.dtype([("op", "<i4"), ("instance", "<i4"), ("model", "<i4"), ("weight", "<i4"), ("last_used", "<i8")],
+                     align=True)
+EVICTION = np.dtype([("instance", "<i4"), ("model", "<i4"), ("last_used", "<i8"), ("weight", "<i4"), ("event", "<i4")],
+                    align=True)
+assert INSTANCE_ROW.itemsize == 64 and MODEL_ROW.itemsize == 24 and DECISION_IN.itemsize == 32
+assert DECISION_OUT.itemsize == 8 and DECISION_TRACE.itemsize == 32 and CLUSTER_STATS.itemsize == 32
+assert LRU_EVENT.itemsize == 24 and EVICTION.itemsize == 24
+
+DF_FAVOUR_SELF = 1
+DF_MODEL_LAST_USED = 2
+TARGET_NONE = -1
+TARGET_SELF = -2
+TARGET_INVALID = -3
+TF_RS_RETRY, TF_SIMPLE, TF_BEST_FULL, TF_FAVOUR_EXIT = 1, 2, 4, 8
+TF_KEEP_BEST, TF_KEEP_OTHERS, TF_KEEP_SELF, TF_PREF_B = 16, 32, 64, 128
+
+E_ARG, E_CUDA, E_NCCL, E_EPOCH, E_NOMEM, E_STATE = -1, -2, -3, -4, -5, -6
+
+
+class MmpConfig(C.Structure):
+    _fields_ = [("min_space_units", C.c_int64), ("min_churn_age_ms", C.c_int64),
+                ("default_model_size_units", C.c_int32), ("max_instances", C.c_int32), ("max_models", C.c_int32),
+                ("device", C.c_int32), ("shard_rank", C.c_int32), ("shard_count", C.c_int32), ("flags", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+# every symbol include/mmplace.h declares: (name, restype, argtypes)
+_P = C.c_void_p
+_I32, _I64, _U64 = C.c_int32, C.c_int64, C.c_uint64
+_STRS = C.POINTER(C.c_char_p)
+SYMBOLS = [
+    ("mmp_abi_version", _I32, []),
+    ("mmp_fleet_create", _I32, [C.POINTER(MmpConfig), C.POINTER(_P)]),
+    ("mmp_fleet_destroy", None, [_P]),
+    ("mmp_last_error", C.c_char_p, [_P]),
+    ("mmp_instance_upsert", _I32, [_P, _I32, _P, C.c_char_p, C.c_char_p, C.c_char_p, _STRS, _I32]),
+    ("mmp_instance_update", _I32, [_P, _I32, _P]),
+    ("mmp_instance_remove", _I32, [_P, _I32]),
+    ("mmp_types_set_json", _I32, [_P, C.c_char_p]),
+    ("mmp_type_id", _I32, [_P, C.c_char_p]),
+    ("mmp_replicasets_set", _I32, [_P, _STRS, _I32]),
+    ("mmp_model_upsert", _I32, [_P, _I32, _P, _P, _I32]),
+    ("mmp_models_bulk", _I32, [_P, _I32, _I32, _P, _P, _P]),
+    ("mmp_fleet_commit", _I32, [_P]),
+    ("mmp_place_batch", _I32, [_P, _P, _I32, _P, _I32, _P, _I32, _P, _I64, _U64]),
+    ("mmp_place_batch_trace", _I32, [_P, _P, _I32, _P, _I32, _P, _I32, _P, _P, _P, _I64, _U64]),
+    ("mmp_place_one", _I32, [_P, _P, _P, _P, _P, _I64, _U64]),
+    ("mmp_place_batch_device", _I32, [_P, _P, _I32, _P, _I64, _U64, C.POINTER(C.c_float)]),
+    ("mmp_device_alloc", _I32, [_P, _I64, C.POINTER(_P)]),
+    ("mmp_device_free", _I32, [_P, _P]),
+    ("mmp_device_upload", _I32, [_P, _P, _P, _I64]),
+    ("mmp_device_download", _I32, [_P, _P, _P, _I64]),
+    ("mmp_host_alloc", _I32, [_P, _I64, C.POINTER(_P)]),
+    ("mmp_host_free", _I32, [_P, _P]),
+    ("mmp_flush_l2", _I32, [_P]),
+    ("mmp_row_words", _I32, [_P]),
+    ("mmp_live_instances", _I32, [_P]),
+    ("mmp_cluster_order", _I32, [_P, _P, _I32]),
+    ("mmp_type_sets", _I32, [_P, _I32, _I32, _P, C.POINTER(_I32), _P, C.POINTER(_I32)]),
+    ("mmp_kernel_launches", _I64, [_P]),
+    ("mmp_stats", _I32, [_P, _P, _P, _I32]),
+    ("mmp_instance_partition", _I32, [_P, _I32]),
+    ("mmp_reaper_select", _I32, [_P, _I32, _I64, _P, _P, _I32]),
+    ("mmp_lru_init", _I32, [_P, _I32, _P, _I32]),
+    ("mmp_lru_apply", _I32, [_P, _P, _I32, _I64, _P, _I32]),
+    ("mmp_lru_state", _I32, [_P, _I32, _P, _P, _P]),
+]
+
+
+def bind(lib: C.CDLL, require_all: bool = True) -> C.CDLL:
+    missing = []
+    for name, res, args in SYMBOLS:
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            missing.append(name)
+            continue
+        fn.restype = res
+        fn.argtypes = args
+    if missing and require_all:
+        raise ImportError(f"libmmplace is missing symbols declared in include/mmplace.h: {missing}")
+    lib._mmp_missing = missing
+    return lib
+
+
+def load(path: str, require_all: bool = True) -> C.CDLL:
+    if not os.path.exists(path):
+        raise ImportError(
+            f"{path} not found: the CUDA library has not been built. Run `python -c 'import __graft_entry__ as g; "
+            f"g.build()'` (needs nvcc). There is no CPU fallback.")
+    return bind(C.CDLL(path, mode=C.RTLD_GLOBAL), require_all)
+
+
+_product = None
+
+
+def load_product() -> C.CDLL:
+    global _product
+    if _product is None:
+        _product = load(PRODUCT_SO)
+    return _product

@@ -1,0 +1,632 @@
+// host_state.hpp — host side of libmmplace: ingest tables, PLACEMENT_ORDER ranking, type-constraint set algebra and
+// the rank-space snapshot that is uploaded to HBM at mmp_fleet_commit.  Pure C++17 (no CUDA) so that the same code is
+// compiled into libmmplace.so by nvcc and into the CPU-only test harness (tests/emul) by g++.
+//
+// Formulation: PLACEMENT_ORDER (MM:4646-4703) does not depend on the model being placed, so the
+// "scoring" of instances is done once per snapshot epoch: every live instance gets a dense rank, and every per-type /
+// per-snapshot instance set becomes a bitmask over ranks.  A placement decision is then bitmask algebra plus
+// find-first-set (= argmin under PLACEMENT_ORDER) over one row of the model x instance exclusion bitmap.
+//
+// Reference citations: MM = ModelMesh.java, IR = InstanceRecord.java, TCM = TypeConstraintManager.java,
+// UT = UpgradeTracker.java (kserve/modelmesh @ ea13cdc5).
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <set>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/mmplace.h"
+#include "place_core.cuh"
+
+namespace mmp {
+
+typedef std::u16string JStr;  // java.lang.String ordering = UTF-16 code units
+
+inline JStr utf8_to_utf16(const char *s) {
+  JStr out;
+  if (!s) return out;
+  const unsigned char *p = (const unsigned char *)s;
+  while (*p) {
+    uint32_t cp;
+    int len = (*p < 0x80) ? 1 : ((*p >> 5) == 6) ? 2 : ((*p >> 4) == 14) ? 3 : ((*p >> 3) == 30) ? 4 : 0;
+    bool ok = len > 0;
+    for (int i = 1; ok && i < len; i++) ok = (p[i] & 0xC0) == 0x80;
+    if (!ok) { out.push_back(0xFFFD); p++; continue; }
+    switch (len) {
+      case 1: cp = p[0]; break;
+      case 2: cp = ((p[0] & 0x1Fu) << 6) | (p[1] & 0x3Fu); break;
+      case 3: cp = ((p[0] & 0x0Fu) << 12) | ((p[1] & 0x3Fu) << 6) | (p[2] & 0x3Fu); break;
+      default: cp = ((p[0] & 0x07u) << 18) | ((p[1] & 0x3Fu) << 12) | ((p[2] & 0x3Fu) << 6) | (p[3] & 0x3Fu); break;
+    }
+    p += len;
+    if (cp >= 0x10000) { cp -= 0x10000; out.push_back((char16_t)(0xD800 + (cp >> 10))); out.push_back((char16_t)(0xDC00 + (cp & 0x3FF))); }
+    else out.push_back((char16_t)cp);
+  }
+  return out;
+}
+
+struct HostInstance {
+  bool present = false;
+  mmp_instance_row row{};
+  JStr id, loc, zone;
+  bool has_loc = false, has_zone = false;
+  std::vector<JStr> labels;  // sorted, as IR:90-91
+};
+
+struct TypeConfig {  // TCM.ConfigTypeConstraints (TCM:79-98), normalised: sorted, de-duplicated, disjoint
+  std::vector<JStr> required, preferred;
+};
+
+// Dense ranks of a set of strings under String.compareTo; absent (null) values rank last (Ordering.nullsLast, MM:4644)
+inline void dense_string_ranks(const std::vector<const JStr *> &vals, std::vector<uint32_t> &out) {
+  size_t n = vals.size();
+  std::vector<uint32_t> ord(n);
+  for (size_t i = 0; i < n; i++) ord[i] = (uint32_t)i;
+  auto less = [&](uint32_t a, uint32_t b) {
+    const JStr *x = vals[a], *y = vals[b];
+    if (!x || !y) return x && !y;  // non-null before null
+    return *x < *y;                // u16string operator< compares code units lexicographically, then length
+  };
+  std::sort(ord.begin(), ord.end(), less);
+  out.assign(n, 0);
+  uint32_t r = 0;
+  for (size_t i = 0; i < n; i++) {
+    if (i > 0 && (less(ord[i - 1], ord[i]))) r++;
+    out[ord[i]] = r;
+  }
+}
+
+// Everything mmp_fleet_commit derives on the host; plain vectors, uploaded verbatim.
+struct HostSnapshot {
+  int32_t n_ranks = 0, row_words = 0, n_slots = 0, any_rs = 0, order_not_total = 0;
+  int32_t tc_enabled = 0;
+  std::vector<RankRow> rows;          // [n_ranks]
+  std::vector<int32_t> rank_of;       // [max_instances]
+  std::vector<uint32_t> cand;         // [n_slots][row_words]
+  std::vector<uint32_t> pref;         // [n_slots][row_words]
+  std::vector<uint8_t> has_pref;      // [n_slots]
+  std::vector<uint8_t> allowed_null;  // [n_slots] (introspection only)
+  std::vector<uint16_t> type_slot;    // [n_type_ids] type id -> mask slot
+  std::vector<uint32_t> rs, full;     // [row_words]
+  std::vector<WordSumI> csum;         // [row_words]
+  std::vector<WordSumL> lsum;         // [row_words]
+  std::vector<int32_t> part_of_rank;  // [n_ranks] partition (PTS) id, 0 when no type constraints
+  std::vector<std::vector<std::string>> part_types;  // prohibited type names per partition id
+  // instance columns for the stats / reaper kernels, by rank
+  std::vector<int64_t> cap_col;
+  std::vector<int32_t> lthreads_col, linprog_col;
+};
+
+class HostState {
+ public:
+  mmp_config cfg{};
+  std::vector<HostInstance> inst;
+  bool tc_enabled = false;                       // typeConstraints != null (TCM.get returned non-null)
+  std::map<std::string, TypeConfig> tc_config;   // type name -> constraints; every mmp_types_set_json is a fresh load (all types "new", TCM:639-650)
+  std::unordered_map<std::string, int32_t> type_ids;  // interned model-type names; ids start at 1
+  std::vector<std::string> type_names;           // [id]
+  std::set<JStr> replaced_rs;                    // likelyReplacedReplicaSets keys (UT:71)
+  // model registry columns (MR:61-114).  Edges = loaded ∪ failed instance indices; 4 inline per model + overflow map.
+  static constexpr int EDGE_INL = 4;
+  std::vector<mmp_model_row> models;
+  std::vector<int32_t> edge_inl;
+  std::unordered_map<int32_t, std::vector<int32_t>> edge_ovf;
+  int32_t n_models_used = 0;
+  bool dirty_models = true;
+  std::string err;
+
+  void init(const mmp_config &c) {
+    cfg = c;
+    inst.assign((size_t)c.max_instances, HostInstance());
+    type_names.assign(1, std::string());
+    models.assign((size_t)c.max_models, mmp_model_row{});
+    edge_inl.assign((size_t)c.max_models * EDGE_INL, -1);
+  }
+
+  int32_t upsert_instance(int32_t idx, const mmp_instance_row *row, const char *id, const char *loc, const char *zone,
+                          const char *const *labels, int32_t n_labels) {
+    if (idx < 0 || idx >= cfg.max_instances || !row || !id || n_labels < 0) { err = "bad instance index or null argument"; return MMP_E_ARG; }
+    if (const char *m = validate_row(*row)) { err = m; return MMP_E_ARG; }
+    HostInstance &h = inst[idx];
+    h.present = true;
+    h.row = *row;
+    h.id = utf8_to_utf16(id);
+    h.has_loc = loc != nullptr; h.loc = utf8_to_utf16(loc);
+    h.has_zone = zone != nullptr; h.zone = utf8_to_utf16(zone);
+    h.labels.clear();
+    for (int32_t i = 0; i < n_labels; i++) h.labels.push_back(utf8_to_utf16(labels[i]));
+    std::sort(h.labels.begin(), h.labels.end());  // IR:90-91 Arrays.sort(labels)
+    return MMP_OK;
+  }
+  int32_t update_instance(int32_t idx, const mmp_instance_row *row) {
+    if (idx < 0 || idx >= cfg.max_instances || !row || !inst[idx].present) { err = "instance not present"; return MMP_E_ARG; }
+    if (const char *m = validate_row(*row)) { err = m; return MMP_E_ARG; }
+    inst[idx].row = *row;
+    return MMP_OK;
+  }
+  int32_t remove_instance(int32_t idx) {
+    if (idx < 0 || idx >= cfg.max_instances) { err = "bad instance index"; return MMP_E_ARG; }
+    inst[idx] = HostInstance();
+    return MMP_OK;
+  }
+  int32_t set_replicasets(const char *const *prefixes, int32_t n) {
+    if (n < 0 || (n > 0 && !prefixes)) { err = "bad replicaset list"; return MMP_E_ARG; }
+    replaced_rs.clear();
+    for (int32_t i = 0; i < n; i++) replaced_rs.insert(utf8_to_utf16(prefixes[i]));
+    return MMP_OK;
+  }
+  int32_t set_model(int32_t m, const mmp_model_row *row, const int32_t *ids, int32_t n_ids) {
+    if (m < 0 || m >= cfg.max_models || !row || n_ids < 0 || (n_ids > 0 && !ids)) { err = "bad model index or null argument"; return MMP_E_ARG; }
+    if (row->type_id >= type_names.size()) { err = "unknown type_id (use mmp_type_id)"; return MMP_E_ARG; }
+    for (int32_t i = 0; i < n_ids; i++)
+      if (ids[i] < 0 || ids[i] >= cfg.max_instances) { err = "model instance id out of range"; return MMP_E_ARG; }
+    models[m] = *row;
+    for (int i = 0; i < EDGE_INL; i++) edge_inl[(size_t)m * EDGE_INL + i] = i < n_ids ? ids[i] : -1;
+    if (n_ids > EDGE_INL) edge_ovf[m].assign(ids + EDGE_INL, ids + n_ids);
+    else if (!edge_ovf.empty()) edge_ovf.erase(m);
+    if (m + 1 > n_models_used) n_models_used = m + 1;
+    dirty_models = true;
+    return MMP_OK;
+  }
+  int32_t row_words() const { return ((cfg.max_instances + 31) / 32 + 31) / 32 * 32; }  // multiple of 32 words = 128 B
+
+  int32_t set_types_json(const char *json);  // defined after TcJson
+
+  static const char *validate_row(const mmp_instance_row &r) {
+    if (r.lru_time < 0) return "lru_time must be >= 0 (Long.MAX_VALUE when empty)";
+    if (r.rpm < 0 || r.rpm > 500000000) return "rpm outside [0, 5e8]";
+    if (r.count < 0 || r.count > 1000000000) return "count outside [0, 1e9]";
+    if (r.capacity < 0 || r.used < 0) return "capacity/used must be >= 0";
+    return nullptr;
+  }
+
+  int32_t intern_type(const std::string &name) {
+    auto it = type_ids.find(name);
+    if (it != type_ids.end()) return it->second;
+    if (type_names.size() >= 65535) return -1;
+    int32_t id = (int32_t)type_names.size();
+    type_names.push_back(name);
+    type_ids[name] = id;
+    return id;
+  }
+
+  // TCM.sortAndDeduplicate (TCM:100-113)
+  static std::vector<JStr> sort_dedupe(std::vector<JStr> v, const std::vector<JStr> *exclude) {
+    std::sort(v.begin(), v.end());
+    v.erase(std::unique(v.begin(), v.end()), v.end());
+    if (exclude) {
+      std::vector<JStr> o;
+      for (auto &l : v)
+        if (!std::binary_search(exclude->begin(), exclude->end(), l)) o.push_back(l);
+      return o;
+    }
+    return v;
+  }
+
+  // ---- PLACEMENT_ORDER as a comparator over numeric columns + dense string ranks ----
+  struct OrderKey {
+    int64_t vers, rem, lru, cap;
+    int32_t count, free_threads, lip, rpm;
+    uint32_t id_rank, loc_rank, zone_rank, labels_rank;
+    bool full, shutting_down;
+  };
+  // literal restatement of MM:4646-4703 on OrderKey (shutting-down records never reach here, MM:1462-1464)
+  static int compare_keys(const OrderKey &a, const OrderKey &b, int64_t churn2) {
+    if (a.shutting_down != b.shutting_down) return a.shutting_down ? 1 : -1;
+    if (a.vers != b.vers) {
+      if (a.vers > b.vers) { if (!a.full || a.lru > churn2) return -1; }
+      else if (!b.full || b.lru > churn2) return 1;
+    }
+    if (a.full != b.full) return a.full ? 1 : -1;
+    if (a.full && a.lru != b.lru) return a.lru < b.lru ? -1 : 1;
+    if (a.count != b.count) return a.count < b.count ? -1 : 1;  // counts validated to [0,1e9]: the int subtraction cannot wrap
+    if (a.rem != b.rem) return a.rem > b.rem ? -1 : 1;
+    if (!a.full && a.lru != b.lru) return a.lru < b.lru ? -1 : 1;
+    if (a.free_threads != b.free_threads) return a.free_threads > b.free_threads ? -1 : 1;
+    if (a.lip != b.lip) return a.lip < b.lip ? -1 : 1;
+    if (a.cap != b.cap) return a.cap > b.cap ? -1 : 1;
+    if (a.rpm != b.rpm) return a.rpm < b.rpm ? -1 : 1;
+    if (a.id_rank != b.id_rank) return a.id_rank < b.id_rank ? -1 : 1;
+    if (a.loc_rank != b.loc_rank) return a.loc_rank < b.loc_rank ? -1 : 1;
+    if (a.zone_rank != b.zone_rank) return a.zone_rank < b.zone_rank ? -1 : 1;
+    if (a.labels_rank != b.labels_rank) return a.labels_rank < b.labels_rank ? -1 : 1;
+    return 0;
+  }
+
+  template <class Cmp>
+  static void merge_sort(std::vector<int32_t> &v, Cmp less) {  // tolerant of a non-transitive comparator (N1)
+    std::vector<int32_t> tmp(v.size());
+    for (size_t w = 1; w < v.size(); w *= 2) {
+      for (size_t lo = 0; lo < v.size(); lo += 2 * w) {
+        size_t mid = std::min(lo + w, v.size()), hi = std::min(lo + 2 * w, v.size());
+        size_t i = lo, j = mid, k = lo;
+        while (i < mid && j < hi) tmp[k++] = less(v[j], v[i]) ? v[j++] : v[i++];
+        while (i < mid) tmp[k++] = v[i++];
+        while (j < hi) tmp[k++] = v[j++];
+      }
+      v.swap(tmp);
+    }
+  }
+
+  // Build the rank-space snapshot.  Returns nullptr on success or an error message.
+  const char *build_snapshot(HostSnapshot &s) const {
+    const int32_t NI = cfg.max_instances;
+    const int32_t RW = row_words();
+    s = HostSnapshot();
+    s.row_words = RW;
+    s.tc_enabled = tc_enabled ? 1 : 0;
+    // --- live set (present and not shutting down: MM:1462-1464 treats a shutting-down record as deleted) ---
+    std::vector<int32_t> live;
+    for (int32_t i = 0; i < NI; i++)
+      if (inst[i].present && !inst[i].row.shutting_down) live.push_back(i);
+    const int32_t n = (int32_t)live.size();
+    s.n_ranks = n;
+
+    // --- dense string ranks for the tie-break chain (MM:4697-4700) ---
+    std::vector<const JStr *> ids(n), locs(n), zones(n);
+    for (int32_t k = 0; k < n; k++) {
+      const HostInstance &h = inst[live[k]];
+      ids[k] = &h.id;
+      locs[k] = h.has_loc ? &h.loc : nullptr;
+      zones[k] = h.has_zone ? &h.zone : nullptr;
+    }
+    std::vector<uint32_t> id_r, loc_r, zone_r, lab_r(n);
+    dense_string_ranks(ids, id_r);
+    dense_string_ranks(locs, loc_r);
+    dense_string_ranks(zones, zone_r);
+    {  // labels under Utils.STRING_ARRAY_COMP (Utils.java:25-36): length first, then element-wise
+      std::vector<uint32_t> ord(n);
+      for (int32_t k = 0; k < n; k++) ord[k] = k;
+      auto cmp = [&](uint32_t a, uint32_t b) {
+        const auto &x = inst[live[a]].labels, &y = inst[live[b]].labels;
+        if (x.size() != y.size()) return x.size() < y.size();
+        for (size_t i = 0; i < x.size(); i++)
+          if (x[i] != y[i]) return x[i] < y[i];
+        return false;
+      };
+      std::sort(ord.begin(), ord.end(), cmp);
+      uint32_t r = 0;
+      for (int32_t k = 0; k < n; k++) {
+        if (k > 0 && cmp(ord[k - 1], ord[k])) r++;
+        lab_r[ord[k]] = r;
+      }
+    }
+    std::vector<OrderKey> keys(n);
+    bool any_saturated = false, mixed_vers = false;
+    const int64_t churn2 = (int64_t)((uint64_t)cfg.min_churn_age_ms * 2u);
+    for (int32_t k = 0; k < n; k++) {
+      const mmp_instance_row &r = inst[live[k]].row;
+      OrderKey &o = keys[k];
+      o.vers = r.vers;
+      o.rem = std::max<int64_t>(0, r.capacity - r.used);  // IR:203-205
+      o.lru = r.lru_time;
+      o.cap = r.capacity;
+      o.count = r.count;
+      o.free_threads = (int32_t)((uint32_t)r.l_threads - (uint32_t)r.l_in_prog);
+      o.lip = r.l_in_prog;
+      o.rpm = r.rpm;
+      o.id_rank = id_r[k]; o.loc_rank = loc_r[k]; o.zone_rank = zone_r[k]; o.labels_rank = lab_r[k];
+      o.full = o.rem < cfg.min_space_units;  // MM:4640-4642
+      o.shutting_down = false;
+      if (o.full && !(o.lru > churn2)) any_saturated = true;
+      if (r.vers != inst[live[0]].row.vers) mixed_vers = true;
+    }
+    s.order_not_total = (any_saturated && mixed_vers) ? 1 : 0;  // N1: comparator may be non-transitive
+    std::vector<int32_t> ord(n);
+    for (int32_t k = 0; k < n; k++) ord[k] = k;
+    merge_sort(ord, [&](int32_t a, int32_t b) { return compare_keys(keys[a], keys[b], churn2) < 0; });
+
+    s.rows.resize(n);
+    s.rank_of.assign(NI, -1);
+    s.cap_col.resize(n); s.lthreads_col.resize(n); s.linprog_col.resize(n);
+    s.rs.assign(RW, 0); s.full.assign(RW, 0);
+    s.csum.assign(RW, WordSumI{INT32_MAX, INT32_MIN});
+    s.lsum.assign(RW, WordSumL{INT64_MAX, INT64_MIN});
+    s.any_rs = replaced_rs.empty() ? 0 : 1;
+    for (int32_t r = 0; r < n; r++) {
+      int32_t k = ord[r];
+      int32_t idx = live[k];
+      const HostInstance &h = inst[idx];
+      RankRow &row = s.rows[r];
+      row.lru = keys[k].lru; row.rem = keys[k].rem; row.count = h.row.count; row.rpm = h.row.rpm; row.idx = idx;
+      row.flags = keys[k].full ? 1u : 0u;
+      s.rank_of[idx] = r;
+      s.cap_col[r] = h.row.capacity; s.lthreads_col[r] = h.row.l_threads; s.linprog_col[r] = h.row.l_in_prog;
+      if (keys[k].full) s.full[r >> 5] |= 1u << (r & 31);
+      // MM:4769-4770: iid.length() >= 7 and first six chars name a likely-replaced replicaset
+      if (!replaced_rs.empty() && h.id.size() >= 7 && replaced_rs.count(h.id.substr(0, 6))) s.rs[r >> 5] |= 1u << (r & 31);
+      WordSumI &ci = s.csum[r >> 5];
+      ci.lo = std::min(ci.lo, row.count); ci.hi = std::max(ci.hi, row.count);
+      WordSumL &li = s.lsum[r >> 5];
+      li.lo = std::min(li.lo, row.lru); li.hi = std::max(li.hi, row.lru);
+    }
+
+    // --- type-constraint set algebra (converged state of TCM.refreshPerTypeInstanceSets, TCM:680-747) ---
+    build_type_masks(s, live);
+    return nullptr;
+  }
+
+ private:
+  // instanceMatches TCM:478-486 over sorted label vectors
+  static bool instance_matches(const std::vector<JStr> &inst_labels, const std::vector<JStr> &type_labels, bool match_all) {
+    if (inst_labels.empty() || type_labels.empty()) return false;
+    for (auto &l : type_labels) {
+      bool has = std::binary_search(inst_labels.begin(), inst_labels.end(), l);
+      if (match_all && !has) return false;
+      if (!match_all && has) return true;
+    }
+    return match_all;
+  }
+
+  struct Resolved {  // per configured type name, over ranks
+    bool allowed_null = true, pref_null = true, cfg_pref_null = true;
+    std::vector<uint8_t> allowed, pref, cfg_pref;
+  };
+
+  // inferPreferredInstances TCM:727-747
+  static bool infer_preferred(const std::vector<int32_t> &scores, const std::vector<uint8_t> *include, std::vector<uint8_t> &out) {
+    int32_t mn = INT32_MAX, mx = 0;
+    out.assign(scores.size(), 0);
+    for (size_t r = 0; r < scores.size(); r++) {
+      if (include && !(*include)[r]) continue;
+      int32_t sc = scores[r];
+      if (sc < mn) mn = sc;
+      if (sc >= mx) {
+        if (sc > mx) { std::fill(out.begin(), out.end(), 0); mx = sc; }
+        out[r] = 1;
+      }
+    }
+    return mn < mx;  // false => null
+  }
+
+  void build_type_masks(HostSnapshot &s, const std::vector<int32_t> & /*live*/) const {
+    const int32_t n = s.n_ranks, RW = s.row_words;
+    const size_t n_type_ids = type_names.size();
+    s.type_slot.assign(n_type_ids, 0);
+    s.part_of_rank.assign(n, 0);
+    s.part_types.clear();
+
+    // active (siMap) mask applies to every slot (MM:4765)
+    std::vector<uint32_t> active(RW, 0);
+    for (int32_t r = 0; r < n; r++)
+      if (inst[s.rows[r].idx].row.active) active[r >> 5] |= 1u << (r & 31);
+
+    auto add_slot = [&](const std::vector<uint8_t> *allowed, const std::vector<uint8_t> *pref) -> uint16_t {
+      std::vector<uint32_t> c(RW, 0), p(RW, 0);
+      for (int32_t r = 0; r < n; r++) {
+        if (!allowed || (*allowed)[r]) c[r >> 5] |= 1u << (r & 31);
+        if (pref && (*pref)[r]) p[r >> 5] |= 1u << (r & 31);
+      }
+      for (int32_t w = 0; w < RW; w++) c[w] &= active[w];
+      // de-duplicate identical slots
+      for (int32_t sl = 0; sl < s.n_slots; sl++) {
+        if (s.has_pref[sl] == (pref ? 1 : 0) && s.allowed_null[sl] == (allowed ? 0 : 1) &&
+            !memcmp(&s.cand[(size_t)sl * RW], c.data(), RW * 4) && !memcmp(&s.pref[(size_t)sl * RW], p.data(), RW * 4))
+          return (uint16_t)sl;
+      }
+      s.cand.insert(s.cand.end(), c.begin(), c.end());
+      s.pref.insert(s.pref.end(), p.begin(), p.end());
+      s.has_pref.push_back(pref ? 1 : 0);
+      s.allowed_null.push_back(allowed ? 0 : 1);
+      return (uint16_t)(s.n_slots++);
+    };
+
+    if (!tc_enabled) {
+      uint16_t sl = add_slot(nullptr, nullptr);  // constrainTo == null, prefer == null (MM:4789, 4817)
+      for (size_t t = 0; t < n_type_ids; t++) s.type_slot[t] = sl;
+      s.part_types.push_back({});
+      return;
+    }
+    // per configured type: allowed / configured-preferred sets via updateInstance semantics (TCM:455-468)
+    std::map<std::string, Resolved> res;
+    for (auto &e : tc_config) {
+      Resolved R;
+      const TypeConfig &tc = e.second;
+      R.allowed_null = tc.required.empty();
+      R.allowed.assign(n, 0); R.cfg_pref.assign(n, 0);
+      bool any_pref = false;
+      for (int32_t r = 0; r < n; r++) {
+        const auto &labels = inst[s.rows[r].idx].labels;
+        if (!R.allowed_null && instance_matches(labels, tc.required, true)) R.allowed[r] = 1;
+        if (instance_matches(labels, tc.preferred, false)) { R.cfg_pref[r] = 1; any_pref = true; }
+      }
+      R.cfg_pref_null = !any_pref;
+      res[e.first] = std::move(R);
+    }
+    // prohibited type sets (TCM:557-579): types whose required labels the instance does not satisfy
+    std::map<std::vector<std::string>, int32_t> pts_ids;
+    std::vector<int32_t> scores(n, 0);
+    for (int32_t r = 0; r < n; r++) {
+      std::vector<std::string> pts;
+      for (auto &e : res)
+        if (!e.second.allowed_null && !e.second.allowed[r]) pts.push_back(e.first);  // std::map iterates sorted
+      auto it = pts_ids.find(pts);
+      int32_t id;
+      if (it == pts_ids.end()) { id = (int32_t)s.part_types.size(); pts_ids[pts] = id; s.part_types.push_back(pts); }
+      else id = it->second;
+      s.part_of_rank[r] = id;
+      scores[r] = (int32_t)pts.size() * 4;  // TCM:686-688
+    }
+    if (s.part_types.empty()) s.part_types.push_back({});
+    for (auto &e : res)
+      if (!e.second.cfg_pref_null)
+        for (int32_t r = 0; r < n; r++)
+          if (e.second.cfg_pref[r]) scores[r] -= 1;  // TCM:689-698
+    std::vector<uint8_t> def_pref;
+    bool def_pref_nonnull = infer_preferred(scores, nullptr, def_pref);
+    for (auto &e : res) {  // TCM:706-722
+      Resolved &R = e.second;
+      if (R.allowed_null) {
+        R.pref_null = !def_pref_nonnull; R.pref = def_pref;  // N11
+      } else {
+        bool allowed_empty = true;
+        for (int32_t r = 0; r < n; r++) if (R.allowed[r]) { allowed_empty = false; break; }
+        if (!R.cfg_pref_null || allowed_empty) { R.pref_null = R.cfg_pref_null; R.pref = R.cfg_pref; }
+        else { R.pref_null = !infer_preferred(scores, &R.allowed, R.pref); }
+      }
+    }
+    // slots: id 0 and every interned name resolve through getTypeConstraints (TCM:258-262): own entry, else "_default"
+    auto slot_for = [&](const std::string &name, bool named) -> uint16_t {
+      const Resolved *R = nullptr;
+      if (named) { auto it = res.find(name); if (it != res.end()) R = &it->second; }
+      if (!R) { auto it = res.find("_default"); if (it != res.end()) R = &it->second; }
+      if (R) return add_slot(R->allowed_null ? nullptr : &R->allowed, R->pref_null ? nullptr : &R->pref);
+      return add_slot(nullptr, def_pref_nonnull ? &def_pref : nullptr);  // TCM:250: defaultPreferredInstances
+    };
+    s.type_slot[0] = slot_for(std::string(), false);
+    for (size_t t = 1; t < n_type_ids; t++) s.type_slot[t] = slot_for(type_names[t], true);
+  }
+};
+
+// ---- minimal JSON reader for the MM_TYPE_CONSTRAINTS document (object of objects of string arrays) ----
+class TcJson {
+ public:
+  explicit TcJson(const char *s) : p_(s) {}
+  // returns false on malformed input; unknown properties are ignored like jackson's FAIL_ON_UNKNOWN_PROPERTIES=false (TCM:72)
+  bool parse(std::map<std::string, TypeConfig> &out, std::string &err) {
+    ws();
+    if (!eat('{')) { err = "expected '{'"; return false; }
+    ws();
+    if (eat('}')) return tail(err);
+    for (;;) {
+      std::string name;
+      ws();
+      if (!str(name)) { err = "expected type name"; return false; }
+      ws();
+      if (!eat(':')) { err = "expected ':'"; return false; }
+      std::vector<JStr> req, pref;
+      if (!type_obj(req, pref, err)) return false;
+      TypeConfig tc;
+      tc.required = HostState::sort_dedupe(req, nullptr);
+      tc.preferred = HostState::sort_dedupe(pref, &tc.required);
+      out[name] = tc;  // duplicate keys: last wins, as jackson
+      ws();
+      if (eat(',')) continue;
+      if (eat('}')) return tail(err);
+      err = "expected ',' or '}'";
+      return false;
+    }
+  }
+
+ private:
+  const char *p_;
+  void ws() { while (*p_ == ' ' || *p_ == '\t' || *p_ == '\n' || *p_ == '\r') p_++; }
+  bool eat(char c) { if (*p_ == c) { p_++; return true; } return false; }
+  bool tail(std::string &err) { ws(); if (*p_) { err = "trailing characters"; return false; } return true; }
+  static void put_utf8(std::string &o, uint32_t cp) {
+    if (cp < 0x80) o.push_back((char)cp);
+    else if (cp < 0x800) { o.push_back((char)(0xC0 | (cp >> 6))); o.push_back((char)(0x80 | (cp & 0x3F))); }
+    else if (cp < 0x10000) { o.push_back((char)(0xE0 | (cp >> 12))); o.push_back((char)(0x80 | ((cp >> 6) & 0x3F))); o.push_back((char)(0x80 | (cp & 0x3F))); }
+    else { o.push_back((char)(0xF0 | (cp >> 18))); o.push_back((char)(0x80 | ((cp >> 12) & 0x3F))); o.push_back((char)(0x80 | ((cp >> 6) & 0x3F))); o.push_back((char)(0x80 | (cp & 0x3F))); }
+  }
+  bool hex4(uint32_t &v) {
+    v = 0;
+    for (int i = 0; i < 4; i++) {
+      char c = *p_++;
+      v <<= 4;
+      if (c >= '0' && c <= '9') v |= c - '0'; else if (c >= 'a' && c <= 'f') v |= c - 'a' + 10; else if (c >= 'A' && c <= 'F') v |= c - 'A' + 10; else return false;
+    }
+    return true;
+  }
+  bool str(std::string &o) {
+    if (!eat('"')) return false;
+    while (*p_ && *p_ != '"') {
+      if (*p_ == '\\') {
+        p_++;
+        char c = *p_++;
+        switch (c) {
+          case '"': o.push_back('"'); break; case '\\': o.push_back('\\'); break; case '/': o.push_back('/'); break;
+          case 'b': o.push_back('\b'); break; case 'f': o.push_back('\f'); break; case 'n': o.push_back('\n'); break;
+          case 'r': o.push_back('\r'); break; case 't': o.push_back('\t'); break;
+          case 'u': {
+            uint32_t v;
+            if (!hex4(v)) return false;
+            if (v >= 0xD800 && v < 0xDC00 && p_[0] == '\\' && p_[1] == 'u') {
+              p_ += 2; uint32_t lo; if (!hex4(lo)) return false;
+              v = 0x10000 + ((v - 0xD800) << 10) + (lo - 0xDC00);
+            }
+            put_utf8(o, v);
+            break;
+          }
+          default: return false;
+        }
+      } else o.push_back(*p_++);
+    }
+    return eat('"');
+  }
+  bool skip_value() {  // skip any JSON value (for unknown properties)
+    ws();
+    if (*p_ == '"') { std::string d; return str(d); }
+    if (*p_ == '{' || *p_ == '[') {
+      char open = *p_, close = open == '{' ? '}' : ']';
+      p_++; ws();
+      if (eat(close)) return true;
+      for (;;) {
+        if (open == '{') { std::string k; ws(); if (!str(k)) return false; ws(); if (!eat(':')) return false; }
+        if (!skip_value()) return false;
+        ws();
+        if (eat(',')) continue;
+        return eat(close);
+      }
+    }
+    const char *q = p_;
+    while (*p_ && *p_ != ',' && *p_ != '}' && *p_ != ']' && *p_ != ' ' && *p_ != '\n' && *p_ != '\t' && *p_ != '\r') p_++;
+    return p_ != q;
+  }
+  bool str_array(std::vector<JStr> &out) {
+    ws();
+    if (!strncmp(p_, "null", 4)) { p_ += 4; return true; }
+    if (!eat('[')) return false;
+    ws();
+    if (eat(']')) return true;
+    for (;;) {
+      std::string s8;
+      ws();
+      if (!str(s8)) return false;
+      out.push_back(utf8_to_utf16(s8.c_str()));
+      ws();
+      if (eat(',')) continue;
+      return eat(']');
+    }
+  }
+  bool type_obj(std::vector<JStr> &req, std::vector<JStr> &pref, std::string &err) {
+    ws();
+    if (!eat('{')) { err = "expected '{' for type constraints"; return false; }
+    ws();
+    if (eat('}')) return true;
+    for (;;) {
+      std::string k;
+      ws();
+      if (!str(k)) { err = "expected property name"; return false; }
+      ws();
+      if (!eat(':')) { err = "expected ':'"; return false; }
+      bool ok;
+      if (k == "required") { req.clear(); ok = str_array(req); }
+      else if (k == "preferred") { pref.clear(); ok = str_array(pref); }
+      else ok = skip_value();
+      if (!ok) { err = "bad value for property " + k; return false; }
+      ws();
+      if (eat(',')) continue;
+      if (eat('}')) return true;
+      err = "expected ',' or '}' in type constraints";
+      return false;
+    }
+  }
+};
+
+inline int32_t HostState::set_types_json(const char *json) {
+  if (!json || !*json) { tc_enabled = false; tc_config.clear(); return MMP_OK; }
+  std::map<std::string, TypeConfig> cfgmap;
+  std::string e;
+  if (!TcJson(json).parse(cfgmap, e)) { err = "type constraints json: " + e; return MMP_E_ARG; }
+  tc_enabled = true;
+  tc_config.swap(cfgmap);
+  for (auto &t : tc_config) intern_type(t.first);
+  return MMP_OK;
+}
+
+}  // namespace mmp

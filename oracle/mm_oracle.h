@@ -1,0 +1,175 @@
+/*
+ * mm_oracle.h — C API of the CPU ORACLE for the ModelMesh placement / LRU hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is a line-by-line CPU restatement of the reference's
+ * Java (see mm_oracle.cpp header for the file:line map).  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load it.  The product library
+ * (modelmesh_b200/csrc, include/mmplace.h) never links, imports or calls anything in oracle/.
+ *
+ * Parity status: the reference's own tests hold no unit vectors for this path;
+ * the integration scenarios they do hold (EvictionsModelMeshTest, ModelMeshEvictionsTest,
+ * ModelMeshErrorPropagationTest) are restated as known-answer tests in tests/test_oracle_golden.py.
+ * The Java reference cannot be executed in this image (no JDK, un-vendored jars), so everything
+ * those scenarios do not pin is "parity unpinned by reference tests" — pinned only by the
+ * line-by-line correspondence documented in mm_oracle.cpp.
+ */
+#ifndef MM_ORACLE_H
+#define MM_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct orc_fleet orc_fleet;
+
+/* Numeric part of InstanceRecord (InstanceRecord.java:37-73). */
+typedef struct {
+  int64_t lru_time;   /* Long.MAX_VALUE when empty */
+  int64_t capacity;   /* units of 8 KiB */
+  int64_t used;
+  int64_t start_time;
+  int64_t vers;
+  int32_t count;
+  int32_t l_threads;
+  int32_t l_in_prog;
+  int32_t rpm;
+  int32_t shutting_down;
+  int32_t active;     /* present in litelinks' service-instance map (siMap, MM:4778) */
+} orc_inst_t;
+
+/* ModelMesh.ClusterStats (MM:1570-1591) */
+typedef struct {
+  int64_t total_capacity, total_free, global_lru;
+  int32_t instance_count, model_copy_count;
+} orc_stats_t;
+
+/* One placement decision = one call of CacheMissForwardingLB.getNext (MM:4776-5004). */
+typedef struct {
+  int32_t type_idx;     /* index into the type-name table passed to orc_get_next_batch; -1 = a type with no config */
+  int32_t self;         /* instance idx of the caller ("instanceId") */
+  int32_t fresh_idx;    /* index into fresh[] (getFreshInstanceRecord, MM:5369), -1 = use self's published row with rpm forced to 0 */
+  int32_t favour_self;  /* CacheMissExcludeSet.favourSelf */
+  int64_t last_used;    /* CacheMissExcludeSet.lastUsedTime */
+  uint64_t decision_id; /* feeds the replacement of ThreadLocalRandom (note N4) */
+} orc_decision_t;
+
+enum { ORC_NONE = -1, ORC_SELF = -2 };
+
+typedef struct {
+  int32_t target;        /* instance idx, ORC_NONE (null) or ORC_SELF (ABORT_REQUEST) */
+  int32_t n_candidates;  /* candidates.size() at MM:4939 (0 if returned earlier) */
+  int32_t n_remaining;   /* remainingCount after the rpm filter */
+  int32_t pick_index;    /* index-th non-null candidate */
+  int32_t best;          /* instance idx of bestIid after preferred handling, -1 if none */
+  int32_t flags;         /* bit0: replicaset filter retried (MM:4798); bit1: simpleCase at MM:4889;
+                            bit2: bestIsFull; bit3: returned via favourSelf short-circuit */
+} orc_result_t;
+
+orc_fleet *orc_create(int64_t min_space_units, int64_t min_churn_age_ms, int32_t default_model_size_units);
+void orc_destroy(orc_fleet *);
+
+/* handleInstanceTableChange (MM:1455-1568).  type: 0 ENTRY_ADDED, 1 ENTRY_UPDATED, 2 ENTRY_DELETED.
+ * idx is the caller's dense handle for instance id `id` (a bijection).  loc/zone may be NULL.
+ * Strings are UTF-8; they are compared as UTF-16 code units like java.lang.String.compareTo. */
+int orc_instance_event(orc_fleet *, int type, int32_t idx, const orc_inst_t *rec, const char *id,
+                       const char *loc, const char *zone, const char *const *labels, int32_t n_labels,
+                       int64_t now_ms);
+/* litelinks siMap membership (MM:4778) for an instance that is in the table */
+int orc_set_active(orc_fleet *, int32_t idx, int32_t active);
+
+/* TypeConstraintManager.typeMappingsUpdated (TCM:607-668).  The config is passed pre-parsed:
+ * n types; for type t, names[t], then req_off[t]..req_off[t+1] index into req_labels, same for pref.
+ * Passing n = -1 disables type constraints (typeConstraints == null). */
+int orc_types_set(orc_fleet *, int32_t n, const char *const *names, const int32_t *req_off,
+                  const char *const *req_labels, const int32_t *pref_off, const char *const *pref_labels);
+
+/* Runs TypeConstraintManager.refreshPerTypeInstanceSets (TCM:680-725) once more on the current map with every
+ * instance already in clusterState.  The reference reaches this state whenever a refresh happens after the fleet has
+ * stopped changing; calling it explicitly removes the arrival-order lag of quirk N10 so that a snapshot-based solver
+ * can be compared without replaying the exact event order.  No code other than the literal restatement runs. */
+int orc_tc_converge(orc_fleet *);
+
+/* Directly set UpgradeTracker.likelyReplacedReplicaSets keys (UT:71); the event-driven tracker
+ * (UT:120-187) also runs inside orc_instance_event. */
+int orc_set_replaced_replicasets(orc_fleet *, const char *const *prefixes, int32_t n);
+int orc_get_replaced_replicasets(orc_fleet *, char *buf, int32_t cap); /* comma-joined, returns count */
+
+/* Read back TCM state for a type name: fills allowed/preferred membership (0/1 per instance idx < n_idx);
+ * *allowed_null / *preferred_null tell whether the Java Set is null. */
+int orc_type_sets(orc_fleet *, const char *type, int32_t n_idx, uint8_t *allowed, int32_t *allowed_null,
+                  uint8_t *preferred, int32_t *preferred_null);
+
+/* Sorted fleet (clusterState iteration order under PLACEMENT_ORDER, MM:4646-4703): writes instance idx. */
+int orc_cluster_order(orc_fleet *, int32_t *out_idx, int32_t cap);
+/* PLACEMENT_ORDER.compare on two instances currently in clusterState */
+int orc_compare(orc_fleet *, int32_t idx1, int32_t idx2);
+
+/* clusterStats (global) and per-PTS partition stats in TCM.getPartitionStats order (TCM:264-292).
+ * part_pts_ids returns an opaque id per partition also reported by orc_instance_partition. */
+int orc_cluster_stats(orc_fleet *, orc_stats_t *out);
+int orc_partition_stats(orc_fleet *, orc_stats_t *out, int32_t *part_ids, int32_t cap);
+int orc_instance_partition(orc_fleet *, int32_t idx);
+int orc_type_stats(orc_fleet *, const char *type, orc_stats_t *out); /* ModelMesh.typeSetStats MM:1432-1438 */
+
+/* Batch of getNext calls against the current state.
+ * excl_off[n+1]/excl_idx: per decision the union of CacheMissExcludeSet members (tried ∪ loaded ∪ failed ∪ explicit).
+ * Optional outputs (may be NULL): cand_off[n+1] + cand_idx/cand_load/cand_keep[cap] = ordered candidates,
+ * instReqLoad and whether each survived the rpm filter. Returns number of candidate slots needed or <0. */
+int64_t orc_get_next_batch(orc_fleet *, int32_t n, const orc_decision_t *dec, const char *const *type_names,
+                           int32_t n_types, const orc_inst_t *fresh, int32_t n_fresh, const int64_t *excl_off,
+                           const int32_t *excl_idx, int64_t now_ms, uint64_t seed, int32_t threads,
+                           orc_result_t *out, int64_t *cand_off, int32_t *cand_idx, int32_t *cand_load,
+                           uint8_t *cand_keep, int64_t cand_cap);
+
+/* ---- time-ordered weighted LRU (clhm/ConcurrentLinkedHashMap + LinkedDeque) ---- */
+typedef struct orc_lru orc_lru;
+typedef struct {
+  int32_t op;       /* 0 INSERT (putIfAbsent k,v,lastUsed) 1 TOUCH (get k,lastUsed) 2 RESIZE (replace weight, quiet)
+                       3 REMOVE 4 SET_CAPACITY (weight = new capacity) 5 FORCE_TIME (forceSetLastUsedTime) */
+  int32_t key;
+  int64_t weight;
+  int64_t last_used; /* 0 = now */
+} orc_lru_event_t;
+typedef struct { int32_t key; int32_t event; int64_t last_used; int64_t weight; } orc_eviction_t;
+orc_lru *orc_lru_create(int64_t capacity);
+void orc_lru_destroy(orc_lru *);
+/* applies events in order; evictions appended in listener order. returns number of evictions (may exceed cap) */
+int64_t orc_lru_apply(orc_lru *, const orc_lru_event_t *ev, int64_t n, int64_t now_ms, orc_eviction_t *out, int64_t cap);
+int64_t orc_lru_oldest_time(orc_lru *);
+int64_t orc_lru_weighted_size(orc_lru *);
+int64_t orc_lru_size(orc_lru *);
+/* ascending (oldest first) dump: keys / lastUsed / weights */
+int64_t orc_lru_dump(orc_lru *, int32_t *keys, int64_t *last_used, int64_t *weights, int64_t cap);
+
+/* ---- capacity constants (MM:749-755, 767-769) ---- */
+int64_t orc_unload_reserve_units(int64_t cache_capacity_units, int32_t loading_threads, int32_t default_model_size_units);
+int64_t orc_min_space_units(int64_t cap_units, int32_t loading_threads, int32_t default_model_size_units, int32_t has_unload_manager);
+
+/* ---- loadLocal admission rules (MM:5145-5148, 5185-5197) and churn guard (MM:3872-3884) ---- */
+/* returns 1 if the load is rejected by the churn guard */
+int orc_churn_reject(int64_t capacity, int64_t weighted_size, int64_t oldest_time, int64_t min_space_units,
+                     int64_t min_churn_age_ms, int64_t now_ms);
+/* returns 1 if loadLocal aborts early at MM:5187 */
+int orc_early_reject(int64_t abs_size, int64_t capacity, int64_t weighted_size, int64_t oldest_time, int64_t last_used);
+
+/* ---- reaper proactive-load selection (MM:6574-6577, 6616-6735) over the current fleet state ---- */
+typedef struct {
+  int64_t last_used;
+  int32_t type_idx;    /* index into type_names, -1 none */
+  int32_t n_loaded;    /* insts.size() */
+  int32_t n_failed;    /* failInsts.size() */
+  int32_t pad;
+} orc_model_t;
+/* Runs candidate collection over all n models then triggerProactiveLoadsForInstanceSubset for the
+ * partition `part_id` (-1 = no type constraints / whole cluster).  Writes selected model idx MRU-first.
+ * `taken` (n bytes, in/out) mirrors allCandidates.set(i,null). */
+int64_t orc_reaper_select(orc_fleet *, int32_t n, const orc_model_t *models, const char *const *type_names,
+                          int32_t n_types, int32_t part_id, int64_t now_ms, uint8_t *taken, int32_t *out_models,
+                          int64_t cap);
+
+uint64_t orc_hash64(uint64_t seed, uint64_t decision_id);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

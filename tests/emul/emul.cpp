@@ -1,0 +1,153 @@
+// tests/emul/emul.cpp — CPU-ONLY TEST HARNESS.  Not part of the product and never loaded by modelmesh_b200/.
+//
+// It compiles the product's host-side snapshot builder (csrc/host_state.hpp) and the rank-space decision routine
+// (csrc/place_core.cuh, single-lane Coop1 shape) with g++ and exposes them under the same mmp_* entry points as
+// libmmplace.so, so that the `-m "not gpu"` tests can check the bitmask formulation, the PLACEMENT_ORDER ranking, the
+// type-constraint masks and the JSON reader against the oracle on a box with no GPU.  The CUDA library differs from
+// this harness only in the cooperative shape (Coop32: shuffles/ballots, vector loads) and in where the arrays live.
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../modelmesh_b200/csrc/host_state.hpp"
+
+using namespace mmp;
+
+struct mmp_fleet {
+  HostState hs;
+  HostSnapshot snap;
+  std::vector<uint32_t> excl;
+  std::vector<mmp_model_row> models;
+  int32_t epoch = 0;
+  int64_t launches = 0;
+};
+static thread_local std::string g_err;
+
+extern "C" {
+
+int32_t mmp_abi_version(void) { return MMP_ABI_VERSION; }
+const char *mmp_last_error(mmp_fleet *) { return g_err.c_str(); }
+
+int32_t mmp_fleet_create(const mmp_config *cfg, mmp_fleet **out) {
+  if (!cfg || !out || cfg->max_instances <= 0 || cfg->max_instances > 65536 || cfg->max_models <= 0) { g_err = "bad config"; return MMP_E_ARG; }
+  auto *f = new mmp_fleet();
+  f->hs.init(*cfg);
+  *out = f;
+  return MMP_OK;
+}
+void mmp_fleet_destroy(mmp_fleet *f) { delete f; }
+
+#define FWD(call) do { int32_t rc_ = (call); if (rc_ < 0) g_err = f->hs.err; return rc_; } while (0)
+int32_t mmp_instance_upsert(mmp_fleet *f, int32_t idx, const mmp_instance_row *row, const char *id, const char *loc,
+                            const char *zone, const char *const *labels, int32_t n_labels) {
+  FWD(f->hs.upsert_instance(idx, row, id, loc, zone, labels, n_labels));
+}
+int32_t mmp_instance_update(mmp_fleet *f, int32_t idx, const mmp_instance_row *row) { FWD(f->hs.update_instance(idx, row)); }
+int32_t mmp_instance_remove(mmp_fleet *f, int32_t idx) { FWD(f->hs.remove_instance(idx)); }
+int32_t mmp_types_set_json(mmp_fleet *f, const char *json) { FWD(f->hs.set_types_json(json)); }
+int32_t mmp_type_id(mmp_fleet *f, const char *name) {
+  if (!name) return MMP_E_ARG;
+  int32_t id = f->hs.intern_type(name);
+  if (id < 0) { g_err = "too many types"; return MMP_E_ARG; }
+  return id;
+}
+int32_t mmp_replicasets_set(mmp_fleet *f, const char *const *p, int32_t n) { FWD(f->hs.set_replicasets(p, n)); }
+int32_t mmp_model_upsert(mmp_fleet *f, int32_t m, const mmp_model_row *row, const int32_t *ids, int32_t n) { FWD(f->hs.set_model(m, row, ids, n)); }
+int32_t mmp_models_bulk(mmp_fleet *f, int32_t first, int32_t n, const mmp_model_row *rows, const int64_t *off, const int32_t *e) {
+  for (int32_t i = 0; i < n; i++) {
+    int32_t rc = f->hs.set_model(first + i, &rows[i], e + off[i], (int32_t)(off[i + 1] - off[i]));
+    if (rc < 0) { g_err = f->hs.err; return rc; }
+  }
+  return MMP_OK;
+}
+
+int32_t mmp_fleet_commit(mmp_fleet *f) {
+  if (const char *m = f->hs.build_snapshot(f->snap)) { g_err = m; return MMP_E_ARG; }
+  const int RW = f->snap.row_words;
+  const int32_t nm = f->hs.n_models_used;
+  f->models.assign(f->hs.models.begin(), f->hs.models.begin() + nm);
+  f->excl.assign((size_t)nm * RW, 0u);
+  auto setbit = [&](int32_t m, int32_t inst) {
+    int32_t r = f->snap.rank_of[inst];
+    if (r >= 0) f->excl[(size_t)m * RW + (r >> 5)] |= 1u << (r & 31);
+  };
+  for (int32_t m = 0; m < nm; m++)
+    for (int i = 0; i < HostState::EDGE_INL; i++) {
+      int32_t e = f->hs.edge_inl[(size_t)m * HostState::EDGE_INL + i];
+      if (e >= 0) setbit(m, e);
+    }
+  for (auto &kv : f->hs.edge_ovf)
+    for (int32_t e : kv.second) setbit(kv.first, e);
+  return ++f->epoch;
+}
+
+static SnapshotView make_view(mmp_fleet *f) {
+  SnapshotView v{};
+  const HostSnapshot &s = f->snap;
+  v.n_ranks = s.n_ranks; v.row_words = s.row_words; v.n_models = (int32_t)f->models.size(); v.max_instances = f->hs.cfg.max_instances;
+  v.any_rs = s.any_rs; v.n_type_ids = (int32_t)s.type_slot.size(); v.min_space = f->hs.cfg.min_space_units;
+  v.excl = f->excl.data(); v.cand = s.cand.data(); v.pref = s.pref.data(); v.has_pref = s.has_pref.data();
+  v.type_slot = s.type_slot.data(); v.rs = s.rs.data(); v.full = s.full.data(); v.rows = s.rows.data();
+  v.rank_of = s.rank_of.data(); v.csum = s.csum.data(); v.lsum = s.lsum.data(); v.models = f->models.data();
+  return v;
+}
+
+int32_t mmp_place_batch_trace(mmp_fleet *f, const mmp_decision_in *in, int32_t n, const mmp_instance_row *fresh, int32_t n_fresh,
+                              const int32_t *extra, int32_t /*n_extra*/, mmp_decision_out *out, mmp_decision_trace *trace,
+                              uint32_t *cand_mask, int64_t now_ms, uint64_t seed) {
+  if (f->epoch == 0) { g_err = "no committed snapshot"; return MMP_E_EPOCH; }
+  SnapshotView v = make_view(f);
+  std::vector<FreshRow> fr((size_t)(n_fresh > 0 ? n_fresh : 0));
+  for (int32_t i = 0; i < n_fresh; i++) {
+    if (const char *m = HostState::validate_row(fresh[i])) { g_err = m; return MMP_E_ARG; }
+    fr[i] = FreshRow{fresh[i].lru_time, std::max<int64_t>(0, fresh[i].capacity - fresh[i].used), fresh[i].count, fresh[i].rpm};
+  }
+  Coop1 co(v.row_words);
+  std::vector<uint32_t> fbuf(Coop1::NW_CAP);
+  for (int32_t i = 0; i < n; i++) {
+    DecideOut o;
+    decide<Coop1>(v, in[i], fr.data(), n_fresh, extra, now_ms, seed, (uint64_t)i, co, fbuf.data(), o,
+                  cand_mask ? cand_mask + (size_t)i * 2 * v.row_words : nullptr);
+    out[i].target = o.target; out[i].n_candidates = o.n_candidates;
+    if (trace) {
+      trace[i].best = o.best; trace[i].n_remaining = o.n_remaining; trace[i].pick_index = o.pick_index; trace[i].flags = o.flags;
+      trace[i].cut_rank = o.cut_rank; trace[i].best_rank = o.best_rank; trace[i].reserved[0] = trace[i].reserved[1] = 0;
+    }
+  }
+  f->launches++;
+  return MMP_OK;
+}
+int32_t mmp_place_batch(mmp_fleet *f, const mmp_decision_in *in, int32_t n, const mmp_instance_row *fresh, int32_t n_fresh,
+                        const int32_t *extra, int32_t n_extra, mmp_decision_out *out, int64_t now_ms, uint64_t seed) {
+  return mmp_place_batch_trace(f, in, n, fresh, n_fresh, extra, n_extra, out, nullptr, nullptr, now_ms, seed);
+}
+
+int32_t mmp_row_words(mmp_fleet *f) { return f->hs.row_words(); }
+int32_t mmp_live_instances(mmp_fleet *f) { return f->snap.n_ranks; }
+int32_t mmp_cluster_order(mmp_fleet *f, int32_t *out_idx, int32_t cap) {
+  for (int32_t r = 0; r < f->snap.n_ranks && r < cap; r++) out_idx[r] = f->snap.rows[r].idx;
+  return f->snap.n_ranks;
+}
+int32_t mmp_type_sets(mmp_fleet *f, int32_t type_id, int32_t n_idx, uint8_t *allowed, int32_t *allowed_null, uint8_t *preferred,
+                      int32_t *preferred_null) {
+  const HostSnapshot &s = f->snap;
+  if (type_id < 0 || type_id >= (int32_t)s.type_slot.size()) { g_err = "bad type id"; return MMP_E_ARG; }
+  int sl = s.type_slot[type_id];
+  *allowed_null = s.allowed_null[sl]; *preferred_null = !s.has_pref[sl];
+  for (int32_t i = 0; i < n_idx; i++) {
+    int32_t r = i < (int32_t)s.rank_of.size() ? s.rank_of[i] : -1;
+    // NB the candidate mask also folds in the siMap "active" bit (MM:4765)
+    allowed[i] = (r >= 0 && !s.allowed_null[sl]) ? (s.cand[(size_t)sl * s.row_words + (r >> 5)] >> (r & 31)) & 1u : 0;
+    preferred[i] = (r >= 0) ? (s.pref[(size_t)sl * s.row_words + (r >> 5)] >> (r & 31)) & 1u : 0;
+  }
+  return MMP_OK;
+}
+int32_t mmp_instance_partition(mmp_fleet *f, int32_t idx) {
+  if (idx < 0 || idx >= (int32_t)f->snap.rank_of.size() || f->snap.rank_of[idx] < 0) return -1;
+  return f->snap.part_of_rank[f->snap.rank_of[idx]];
+}
+int64_t mmp_kernel_launches(mmp_fleet *f) { return f->launches; }
+
+}  // extern "C"

@@ -1,0 +1,39 @@
+"""CPU checks of the rank-space formulation (product host code + single-lane decision routine) against the oracle.
+
+These do not touch a GPU: they exercise csrc/host_state.hpp and csrc/place_core.cuh through the tests/emul harness.
+Parity of everything here is "unpinned by reference tests" beyond the golden scenarios (see test_oracle_golden.py).
+"""
+import numpy as np
+import pytest
+
+from modelmesh_b200.synth import make_decisions, make_fleet
+
+from helpers import compare_decisions, oracle_from_synth, solver_from_synth
+
+
+@pytest.mark.parametrize("config,nm,ni,seed", [
+    ("C1", 200, 16, 1), ("C2", 3000, 200, 2), ("C2", 2000, 1000, 12), ("C3", 4000, 700, 3), ("C5", 4000, 500, 5),
+    ("C3", 1500, 1300, 33), ("C5", 1000, 33, 55),
+])
+def test_decisions_match_oracle(emul_lib, oracle_lib, config, nm, ni, seed):
+    fl = make_fleet(config, nm, ni, seed)
+    o = oracle_from_synth(fl)
+    s = solver_from_synth(fl, emul_lib)
+    assert np.array_equal(s.cluster_order(), o.cluster_order())
+    sd = make_decisions(fl, 3000, seed)
+    compare_decisions(fl, sd, o, s, seed=seed * 7919)
+    sd = make_decisions(fl, 1000, seed + 1, sweep=True, plain=True)
+    compare_decisions(fl, sd, o, s, seed=seed)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_mixed_regimes_match_oracle(emul_lib, oracle_lib, seed):
+    """Regime-randomised fleets (synth._make_mix) that reach the rare branches: filter retry, non-simple (a)/(b),
+    long full-case shortlists, equal keys down to the string tie-breaks."""
+    ni = [33, 64, 97, 160, 300][seed % 5]
+    fl = make_fleet("MIX", 600, ni, seed)
+    o = oracle_from_synth(fl)
+    s = solver_from_synth(fl, emul_lib)
+    assert np.array_equal(s.cluster_order(), o.cluster_order())
+    sd = make_decisions(fl, 1500, seed)
+    compare_decisions(fl, sd, o, s, seed=seed + 99)
