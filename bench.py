@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py — placement decisions/sec on the BASELINE.json headline workload (1M models x 10k instances, C3).
+
+One "step" = one pass of the hot path over one batch: a reaper-style sweep of B = n_models getNext decisions against one
+snapshot epoch.  Reported on one JSON line:
+  value     decisions/s with the batch already resident in HBM (CUDA events around the scoring kernel, max over ranks)
+  e2e       the same batch through mmp_place_batch with pinned HOST buffers (H2D + kernel + D2H inside the timed region)
+  roofline  algorithmic bytes (1312 B/decision + 80 B/instance) / measured kernel time vs the measured
+            HBM copy peak in MEASURED_PEAKS.json
+  cpu_baseline  the oracle (C++ restatement of the reference's Java path; the JVM cannot run here) on the host cores
+`--impl reference` times only that CPU path.  N > 1 (torchrun): the registry is sharded by model across ranks (each rank
+places its slice against a replicated instance table; no data-path collective), so total work is fixed: "strong".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_MODELS = int(os.environ.get("BENCH_MODELS", 1_000_000))
+N_INSTANCES = int(os.environ.get("BENCH_INSTANCES", 10_000))
+CONFIG = os.environ.get("BENCH_CONFIG", "C3")
+SEED = 3
+METRIC = "placement decisions/sec at 1M models x 10k instances"
+
+
+def bytes_per_decision(row_words: int) -> int:
+    """exclusion-bitmap row + 24 B model row + 8 B result (1312 B at 10k instances, 1280 B padded row)."""
+    return row_words * 4 + 24 + 8
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu_index = gpu_index
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag.is_set():
+                    break
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag.set()
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm, mx, reasons = [], [], set()
+        for p in self.samples:
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy kernel)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def build_oracle(fl):
+    """CPU baseline / checker only."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    return helpers, helpers.oracle_from_synth(fl)
+
+
+def cpu_leg(fl, sd_all, budget_s: float, chunk: int, threads: int):
+    """Time the oracle's getNext on chunks of the same workload for about budget_s seconds."""
+    helpers, oracle = build_oracle(fl)
+    from modelmesh_b200.synth import SynthDecisions
+    done, t_total, results = 0, 0.0, []
+    n = len(sd_all.dec)
+    pos = 0
+    while t_total < budget_s and pos < n:
+        hi = min(n, pos + chunk)
+        sd = SynthDecisions(sd_all.dec[pos:hi], sd_all.fresh, sd_all.extra)
+        od, off, idx = helpers.oracle_inputs_fast(fl, sd)
+        od["decision_id"] = np.arange(pos, hi, dtype=np.uint64)
+        t0 = time.perf_counter()
+        res = oracle.get_next_batch(od, fl.type_names, off, idx, fl.now_ms, SEED, threads=threads)
+        t_total += time.perf_counter() - t0
+        results.append((pos, hi, res))
+        done += hi - pos
+        pos = hi
+    return done, t_total, results
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    from modelmesh_b200.synth import make_decisions, make_fleet
+    fl = make_fleet(CONFIG, N_MODELS, N_INSTANCES, SEED)
+    sd = make_decisions(fl, N_MODELS, SEED, sweep=True, plain=True)
+    threads = host_threads()
+    chunk = min(len(sd.dec), int(os.environ.get("BENCH_REF_CHUNK", 250_000)))
+    helpers, oracle = build_oracle(fl)
+    from modelmesh_b200.synth import SynthDecisions
+    times = []
+    for step in range(args.warmup + args.steps):
+        lo = (step * chunk) % max(1, len(sd.dec) - chunk + 1)
+        s = SynthDecisions(sd.dec[lo:lo + chunk], sd.fresh, sd.extra)
+        od, off, idx = helpers.oracle_inputs_fast(fl, s)
+        t0 = time.perf_counter()
+        oracle.get_next_batch(od, fl.type_names, off, idx, fl.now_ms, SEED, threads=threads)
+        dt = time.perf_counter() - t0
+        if step >= args.warmup:
+            times.append(dt)
+    tot = sum(times)
+    value = chunk * len(times) / tot
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "decisions/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * tot / len(times), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": f"{CONFIG} {N_MODELS} models x {N_INSTANCES} instances, mixed type constraints, "
+                               f"reaper-style sweep; each step a {chunk}-decision sample on the host cores"},
+        "cpu_baseline": {"value": value, "unit": "decisions/s", "cores": threads, "kind": "port",
+                         "sample": f"{chunk} decisions/step x {len(times)} steps, C++ restatement of "
+                                   f"CacheMissForwardingLB.getNext (the Java reference cannot run: no JDK)"},
+        "e2e": {"value": value, "unit": "decisions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import ctypes as C
+    from modelmesh_b200 import _lib
+    from modelmesh_b200._lib import DECISION_IN, DECISION_OUT
+    from modelmesh_b200.fleet import Fleet
+    from modelmesh_b200.synth import SynthDecisions, load_into_fleet, make_decisions, make_fleet
+
+    lib = _lib.load_product()  # raises if libmmplace.so is missing: no CPU fallback
+    fl = make_fleet(CONFIG, N_MODELS, N_INSTANCES, SEED)
+    sd_all = make_decisions(fl, N_MODELS, SEED, sweep=True, plain=True)
+    # model-shard of this rank (whole registry when world == 1)
+    lo = rank * N_MODELS // world
+    hi = (rank + 1) * N_MODELS // world
+    B = hi - lo
+    solver = Fleet(fl.min_space_units, fl.min_churn_age_ms, fl.default_model_size_units, fl.n_instances, N_MODELS,
+                   device=local_rank, lib=lib)
+    load_into_fleet(fl, solver)
+    dec = np.ascontiguousarray(sd_all.dec[lo:hi])
+    row_words = solver.row_words()
+
+    # ---- device-resident timing (the `value`) ----
+    d_in, d_out = C.c_void_p(), C.c_void_p()
+    solver._ck(lib.mmp_device_alloc(solver.h, dec.nbytes, C.byref(d_in)))
+    solver._ck(lib.mmp_device_alloc(solver.h, B * DECISION_OUT.itemsize, C.byref(d_out)))
+    solver._ck(lib.mmp_device_upload(solver.h, d_in, dec.ctypes.data_as(C.c_void_p), dec.nbytes))
+    kms = C.c_float()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        solver._ck(lib.mmp_place_batch_device(solver.h, d_in, B, d_out, fl.now_ms, SEED, C.byref(kms)))
+    launches0 = solver.kernel_launches()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    kernel_ms = []
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        solver._ck(lib.mmp_place_batch_device(solver.h, d_in, B, d_out, fl.now_ms, SEED, C.byref(kms)))
+        kernel_ms.append(float(kms.value))
+    barrier()
+    wall_s = time.perf_counter() - t_wall0
+    dev_ms = float(np.sum(kernel_ms))
+    out_dev = np.zeros(B, dtype=DECISION_OUT)
+    solver._ck(lib.mmp_device_download(solver.h, out_dev.ctypes.data_as(C.c_void_p), d_out, out_dev.nbytes))
+
+    # ---- end to end through the C ABI with pinned host buffers ----
+    e2e_ms = []
+    e2e = None
+    if not args.no_e2e:
+        h_in, h_out = C.c_void_p(), C.c_void_p()
+        solver._ck(lib.mmp_host_alloc(solver.h, dec.nbytes, C.byref(h_in)))
+        solver._ck(lib.mmp_host_alloc(solver.h, B * DECISION_OUT.itemsize, C.byref(h_out)))
+        C.memmove(h_in, dec.ctypes.data_as(C.c_void_p), dec.nbytes)
+        for _ in range(args.warmup):
+            solver._ck(lib.mmp_place_batch(solver.h, h_in, B, None, 0, None, 0, h_out, fl.now_ms, SEED))
+        barrier()
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            solver._ck(lib.mmp_place_batch(solver.h, h_in, B, None, 0, None, 0, h_out, fl.now_ms, SEED))
+            e2e_ms.append(1000.0 * (time.perf_counter() - t0))
+        barrier()
+        out_e2e = np.frombuffer((C.c_char * (B * DECISION_OUT.itemsize)).from_address(h_out.value), dtype=DECISION_OUT).copy()
+        assert np.array_equal(out_e2e, out_dev), "e2e and device-resident paths disagree"
+    launches = solver.kernel_launches() - launches0
+    clocks = sampler.finish() if rank == 0 else None
+
+    # ---- B = 1 latency (p99 decision us) ----
+    lat = None
+    if rank == 0:
+        one = np.zeros(1, dtype=DECISION_OUT)
+        ts = []
+        for i in range(300 + 2000):
+            t0 = time.perf_counter()
+            lib.mmp_place_one(solver.h, dec[i % B:i % B + 1].ctypes.data_as(C.c_void_p), None, None,
+                              one.ctypes.data_as(C.c_void_p), fl.now_ms, SEED)
+            if i >= 300:
+                ts.append(1e6 * (time.perf_counter() - t0))
+        lat = {"p50_us": float(np.percentile(ts, 50)), "p99_us": float(np.percentile(ts, 99)), "n": len(ts)}
+
+    # ---- max over ranks ----
+    stats = torch.tensor([dev_ms, float(np.sum(e2e_ms)) if e2e_ms else 0.0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max = float(stats[0]), float(stats[1])
+    total_decisions = N_MODELS * args.steps
+    value = total_decisions / (dev_ms_max / 1000.0)
+    if e2e_ms:
+        e2e = {"value": total_decisions / (e2e_ms_max / 1000.0), "unit": "decisions/s",
+               "h2d_bytes_per_step": int(N_MODELS * DECISION_IN.itemsize), "d2h_bytes_per_step": int(N_MODELS * DECISION_OUT.itemsize),
+               "ms_per_step": e2e_ms_max / args.steps}
+
+    if rank == 0:
+        peak, peak_src = measured_hbm_peak()
+        alg_bytes = B * bytes_per_decision(row_words) + 80 * fl.n_instances
+        k_avg_s = float(np.mean(kernel_ms)) / 1000.0
+        achieved = alg_bytes / k_avg_s / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": peak_src, "kernel": "k_place",
+                    "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms_avg": 1000.0 * k_avg_s}
+        cpu = None
+        if not args.no_cpu:
+            threads = host_threads()
+            done, t_cpu, results = cpu_leg(fl, SynthDecisions(dec, sd_all.fresh, sd_all.extra), budget_s=12.0,
+                                           chunk=min(B, 250_000), threads=threads)
+            mism = 0
+            for a, b_, res in results:
+                mism += int(np.count_nonzero(res["target"] != out_dev["target"][a:b_]))
+                mism += int(np.count_nonzero(res["n_candidates"] != out_dev["n_candidates"][a:b_]))
+            cpu = {"value": done / t_cpu, "unit": "decisions/s", "cores": threads, "kind": "port",
+                   "sample": f"{done} decisions of the same sweep, {threads} threads, C++ restatement of the reference's "
+                             f"sorted-set walk (CacheMissForwardingLB.getNext); the Java reference cannot run here",
+                   "parity_mismatches_vs_gpu": mism}
+        line = {
+            "metric": METRIC, "value": value, "unit": "decisions/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": {"workload": f"{CONFIG} {N_MODELS} models x {N_INSTANCES} instances, mixed type constraints, one "
+                                   f"reaper-style sweep of {N_MODELS} getNext decisions per step",
+                       "batch": N_MODELS, "sharding": "registry sharded by model across ranks, instance table replicated"
+                       if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2 (exclusion bitmap %.2f GB per rank streamed every step)" % (B * row_words * 4 / 1e9)},
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "latency_b1": lat, "wall_s_timed_region": wall_s,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -177,6 +177,10 @@ int32_t mmp_device_alloc(mmp_fleet *, int64_t bytes, void **out);
 int32_t mmp_device_free(mmp_fleet *, void *p);
 int32_t mmp_device_upload(mmp_fleet *, void *dst, const void *src, int64_t bytes);
 int32_t mmp_device_download(mmp_fleet *, void *dst, const void *src, int64_t bytes);
+/* pinned (page-locked) host memory for decision/result buffers, so that the copies in mmp_place_batch are true DMA;
+ * a JNI shim wraps these in direct ByteBuffers */
+int32_t mmp_host_alloc(mmp_fleet *, int64_t bytes, void **out);
+int32_t mmp_host_free(mmp_fleet *, void *p);
 int32_t mmp_flush_l2(mmp_fleet *); /* writes a buffer larger than L2 (bench hygiene) */
 
 /* ---- snapshot introspection ---- */

@@ -122,7 +122,7 @@ def load(path: str, require_all: bool = True) -> C.CDLL:
         raise ImportError(
             f"{path} not found: the CUDA library has not been built. Run `python -c 'import __graft_entry__ as g; "
             f"g.build()'` (needs nvcc). There is no CPU fallback.")
-    return bind(C.CDLL(path, mode=C.RTLD_GLOBAL), require_all)
+    return bind(C.CDLL(path), require_all)  # RTLD_LOCAL: never interpose with another copy of the ABI
 
 
 _product = None

@@ -1,0 +1,547 @@
+// mmplace.cu — libmmplace: the sm_100a CUDA implementation behind include/mmplace.h.
+//
+// Data layout in HBM, per snapshot epoch (double-buffered, flipped atomically at commit):
+//   excl      [n_models][row_words] u32   model x instance exclusion bitmap (loaded ∪ failed, MR:69,73), bit = RANK of
+//                                         the instance under PLACEMENT_ORDER; row stride is a multiple of 128 B
+//   cand/pref [n_slots][row_words]  u32   per type-constraint slot: allowed ∧ active / preferred instances (TCM:242-251)
+//   rs, full  [row_words]           u32   likely-replaced replicaset members (MM:4769) / isFull instances (MM:4640)
+//   rows      [n_ranks] RankRow 32 B      per-rank instance columns the walk reads (lru, remaining, count, rpm, idx)
+//   csum/lsum [row_words]                 per-32-rank min/max of count / lruTime (threshold searches skip whole words)
+//   rank_of   [max_instances] i32, models [n_models] mmp_model_row 24 B, type_slot [n_type_ids] u16
+// Kernels: k_build_bitmap / k_build_bitmap_ovf (commit), k_place<V,NJ,TRACE> (one warp per decision, the hot path),
+//          k_stats, k_reaper_*, k_lru_apply (see below).
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <cstdio>
+#include <memory>
+#include <mutex>
+#include <shared_mutex>
+#include <string>
+#include <vector>
+
+#include "host_state.hpp"
+
+using namespace mmp;
+
+static thread_local std::string g_err;
+
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) {                                                                             \
+      g_err = std::string(#call) + ": " + cudaGetErrorString(e_);                                        \
+      return MMP_E_CUDA;                                                                                 \
+    }                                                                                                    \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------------------
+// One thread per model scatters its (<= 4) inline edges into its own bitmap row: no atomics needed.
+__global__ void k_build_bitmap(uint32_t *__restrict__ excl, const int4 *__restrict__ edge_inl,
+                               const int32_t *__restrict__ rank_of, int n_models, int row_words) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n_models) return;
+  int4 e = edge_inl[m];
+  uint32_t *row = excl + (size_t)m * row_words;
+  int es[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    if (es[i] >= 0) {
+      int r = rank_of[es[i]];
+      if (r >= 0) row[r >> 5] |= 1u << (r & 31);
+    }
+  }
+}
+__global__ void k_build_bitmap_ovf(uint32_t *__restrict__ excl, const int2 *__restrict__ pairs, int n_pairs,
+                                   const int32_t *__restrict__ rank_of, int row_words) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pairs) return;
+  int2 p = pairs[i];
+  int r = rank_of[p.y];
+  if (r >= 0) atomicOr(&excl[(size_t)p.x * row_words + (r >> 5)], 1u << (r & 31));
+}
+
+// The scoring kernel: one warp per decision, persistent grid-stride loop.  Each lane keeps NJ x V words of the
+// decision's exclusion row in registers (V = 4: 128-bit loads, a warp-load covers 512 contiguous bytes).
+template <int V, int NJ, bool TRACE>
+__global__ void __launch_bounds__(256) k_place(const SnapshotView s, const mmp_decision_in *__restrict__ in, int n,
+                                               const FreshRow *__restrict__ fresh, int n_fresh,
+                                               const int32_t *__restrict__ extra, mmp_decision_out *__restrict__ out,
+                                               mmp_decision_trace *__restrict__ tr, uint32_t *__restrict__ cand,
+                                               int64_t now, uint64_t seed, uint64_t id_base) {
+  Coop32<V, NJ> co;
+  const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+  uint32_t f[V * NJ];
+  for (int i = warp; i < n; i += nwarps) {
+    const int4 *dp = reinterpret_cast<const int4 *>(in + i);
+    int4 a = __ldg(dp), b = __ldg(dp + 1);
+    mmp_decision_in d;
+    d.model = a.x; d.self = a.y; d.last_used = (int64_t)(((uint64_t)(uint32_t)a.w << 32) | (uint32_t)a.z);
+    d.flags = (uint32_t)b.x; d.fresh = b.y; d.extra_off = b.z; d.extra_n = b.w;
+    DecideOut o;
+    decide(s, d, fresh, n_fresh, extra, now, seed, id_base + (uint64_t)i, co, f, o,
+           (TRACE && cand) ? cand + (size_t)i * 2 * s.row_words : nullptr);
+    if (co.lane() == 0) {
+      out[i] = mmp_decision_out{o.target, o.n_candidates};
+      if (TRACE && tr) {
+        mmp_decision_trace t;
+        t.best = o.best; t.n_remaining = o.n_remaining; t.pick_index = o.pick_index; t.flags = o.flags;
+        t.cut_rank = o.cut_rank; t.best_rank = o.best_rank; t.reserved[0] = t.reserved[1] = 0;
+        tr[i] = t;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// device-side containers
+// ---------------------------------------------------------------------------------------------------------------
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct DeviceSnapshot {
+  DevBuf excl, cand, pref, has_pref, type_slot, rs, full, rows, rank_of, csum, lsum, models;
+  DevBuf cap_col, lthreads_col, linprog_col, part_of_rank;
+  SnapshotView view{};
+  HostSnapshot host;  // kept for introspection and the small host-side parts of stats / reaper
+  int32_t n_models = 0;
+  void release() {
+    for (DevBuf *b : {&excl, &cand, &pref, &has_pref, &type_slot, &rs, &full, &rows, &rank_of, &csum, &lsum, &models,
+                      &cap_col, &lthreads_col, &linprog_col, &part_of_rank})
+      b->release();
+  }
+};
+
+struct PlaceCtx {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  DevBuf d_in, d_out, d_fresh, d_extra, d_trace, d_cand;
+  std::vector<FreshRow> fresh_host;
+};
+
+struct mmp_fleet {
+  HostState hs;
+  int device = 0;
+  int sm_count = 148;
+  std::mutex ingest_mu;         // single-writer ingest, but do not corrupt state if violated
+  std::shared_mutex snap_mu;    // readers: place/stats; writer: the epoch flip in commit
+  DeviceSnapshot snaps[2];
+  int cur = 0;
+  int32_t epoch = 0;
+  cudaStream_t commit_stream = nullptr;
+  DevBuf d_edge_inl, d_ovf_pairs, d_flush;
+  std::mutex ctx_mu;
+  std::vector<std::unique_ptr<PlaceCtx>> ctx_free;
+  std::atomic<int64_t> launches{0};
+  // LRU store (plug point 3)
+  DevBuf lru_ts, lru_seq, lru_weight, lru_model, lru_cap, lru_wsize, lru_count, lru_seqctr;
+  int32_t lru_n = 0, lru_slots = 0;
+};
+
+static int32_t set_device(mmp_fleet *f) {
+  CK(cudaSetDevice(f->device));
+  return MMP_OK;
+}
+
+template <class T>
+static cudaError_t upload_vec(DevBuf &b, const std::vector<T> &v, cudaStream_t st) {
+  size_t bytes = v.size() * sizeof(T);
+  cudaError_t e = b.ensure(bytes ? bytes : 16);
+  if (e != cudaSuccess) return e;
+  if (bytes) e = cudaMemcpyAsync(b.p, v.data(), bytes, cudaMemcpyHostToDevice, st);
+  return e;
+}
+
+static PlaceCtx *acquire_ctx(mmp_fleet *f) {
+  {
+    std::lock_guard<std::mutex> g(f->ctx_mu);
+    if (!f->ctx_free.empty()) {
+      PlaceCtx *c = f->ctx_free.back().release();
+      f->ctx_free.pop_back();
+      return c;
+    }
+  }
+  auto *c = new PlaceCtx();
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&c->e0) != cudaSuccess || cudaEventCreate(&c->e1) != cudaSuccess) {
+    delete c;
+    return nullptr;
+  }
+  return c;
+}
+static void release_ctx(mmp_fleet *f, PlaceCtx *c) {
+  std::lock_guard<std::mutex> g(f->ctx_mu);
+  f->ctx_free.emplace_back(c);
+}
+static void destroy_ctx(PlaceCtx *c) {
+  for (DevBuf *b : {&c->d_in, &c->d_out, &c->d_fresh, &c->d_extra, &c->d_trace, &c->d_cand}) b->release();
+  if (c->e0) cudaEventDestroy(c->e0);
+  if (c->e1) cudaEventDestroy(c->e1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// kernel dispatch on the row width
+// ---------------------------------------------------------------------------------------------------------------
+struct PlaceArgs {
+  SnapshotView s;
+  const mmp_decision_in *in;
+  int n;
+  const FreshRow *fresh;
+  int n_fresh;
+  const int32_t *extra;
+  mmp_decision_out *out;
+  mmp_decision_trace *tr;
+  uint32_t *cand;
+  int64_t now;
+  uint64_t seed, id_base;
+};
+
+template <int V, int NJ, bool TRACE>
+static cudaError_t launch_place_t(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st) {
+  static int blocks_per_sm = 0;
+  if (!blocks_per_sm) {
+    int b = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_place<V, NJ, TRACE>, 256, 0);
+    if (e != cudaSuccess) return e;
+    blocks_per_sm = b > 0 ? b : 1;
+  }
+  int want = (a.n + 7) / 8;
+  int grid = std::min(want, f->sm_count * blocks_per_sm);
+  if (grid < 1) grid = 1;
+  k_place<V, NJ, TRACE><<<grid, 256, 0, st>>>(a.s, a.in, a.n, a.fresh, a.n_fresh, a.extra, a.out, a.tr, a.cand, a.now,
+                                              a.seed, a.id_base);
+  f->launches++;
+  return cudaGetLastError();
+}
+
+template <bool TRACE>
+static cudaError_t launch_place(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st) {
+  const int rw = a.s.row_words;
+  if (rw <= 32) return launch_place_t<1, 1, TRACE>(f, a, st);
+  if (rw <= 64) return launch_place_t<2, 1, TRACE>(f, a, st);
+  if (rw <= 128) return launch_place_t<4, 1, TRACE>(f, a, st);
+  if (rw <= 256) return launch_place_t<4, 2, TRACE>(f, a, st);
+  if (rw <= 384) return launch_place_t<4, 3, TRACE>(f, a, st);
+  if (rw <= 512) return launch_place_t<4, 4, TRACE>(f, a, st);
+  if (rw <= 768) return launch_place_t<4, 6, TRACE>(f, a, st);
+  if (rw <= 1024) return launch_place_t<4, 8, TRACE>(f, a, st);
+  if (rw <= 1536) return launch_place_t<4, 12, TRACE>(f, a, st);
+  return launch_place_t<4, 16, TRACE>(f, a, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int32_t mmp_abi_version(void) { return MMP_ABI_VERSION; }
+const char *mmp_last_error(mmp_fleet *) { return g_err.c_str(); }
+
+int32_t mmp_fleet_create(const mmp_config *cfg, mmp_fleet **out) {
+  if (!cfg || !out) { g_err = "null argument"; return MMP_E_ARG; }
+  if (cfg->max_instances <= 0 || cfg->max_instances > 65536 || cfg->max_models <= 0) { g_err = "max_instances must be in [1, 65536] and max_models > 0"; return MMP_E_ARG; }
+  if (cfg->shard_count < 1 || cfg->shard_rank < 0 || cfg->shard_rank >= cfg->shard_count) { g_err = "bad shard_rank/shard_count"; return MMP_E_ARG; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    g_err = std::string("no usable CUDA device (libmmplace has no CPU path): ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    return MMP_E_CUDA;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) { g_err = "device ordinal out of range"; return MMP_E_ARG; }
+  auto f = std::make_unique<mmp_fleet>();
+  f->device = cfg->device;
+  CK(cudaSetDevice(f->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, f->device));
+  f->sm_count = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&f->commit_stream, cudaStreamNonBlocking));
+  f->hs.init(*cfg);
+  *out = f.release();
+  return MMP_OK;
+}
+
+void mmp_fleet_destroy(mmp_fleet *f) {
+  if (!f) return;
+  cudaSetDevice(f->device);
+  cudaDeviceSynchronize();
+  for (auto &c : f->ctx_free) { destroy_ctx(c.get()); }
+  f->ctx_free.clear();
+  f->snaps[0].release(); f->snaps[1].release();
+  for (DevBuf *b : {&f->d_edge_inl, &f->d_ovf_pairs, &f->d_flush, &f->lru_ts, &f->lru_seq, &f->lru_weight, &f->lru_model,
+                    &f->lru_cap, &f->lru_wsize, &f->lru_count, &f->lru_seqctr})
+    b->release();
+  if (f->commit_stream) cudaStreamDestroy(f->commit_stream);
+  delete f;
+}
+
+#define NEED(f) do { if (!(f)) { g_err = "null fleet"; return MMP_E_ARG; } } while (0)
+#define FWD(call) do { std::lock_guard<std::mutex> g_(f->ingest_mu); int32_t rc_ = (call); if (rc_ < 0) g_err = f->hs.err; return rc_; } while (0)
+
+int32_t mmp_instance_upsert(mmp_fleet *f, int32_t idx, const mmp_instance_row *row, const char *id, const char *loc,
+                            const char *zone, const char *const *labels, int32_t n_labels) {
+  NEED(f);
+  FWD(f->hs.upsert_instance(idx, row, id, loc, zone, labels, n_labels));
+}
+int32_t mmp_instance_update(mmp_fleet *f, int32_t idx, const mmp_instance_row *row) { NEED(f); FWD(f->hs.update_instance(idx, row)); }
+int32_t mmp_instance_remove(mmp_fleet *f, int32_t idx) { NEED(f); FWD(f->hs.remove_instance(idx)); }
+int32_t mmp_types_set_json(mmp_fleet *f, const char *json) { NEED(f); FWD(f->hs.set_types_json(json)); }
+int32_t mmp_type_id(mmp_fleet *f, const char *name) {
+  NEED(f);
+  if (!name) { g_err = "null type name"; return MMP_E_ARG; }
+  std::lock_guard<std::mutex> g(f->ingest_mu);
+  int32_t id = f->hs.intern_type(name);
+  if (id < 0) { g_err = "more than 65534 model types"; return MMP_E_ARG; }
+  return id;
+}
+int32_t mmp_replicasets_set(mmp_fleet *f, const char *const *p, int32_t n) { NEED(f); FWD(f->hs.set_replicasets(p, n)); }
+int32_t mmp_model_upsert(mmp_fleet *f, int32_t m, const mmp_model_row *row, const int32_t *ids, int32_t n) {
+  NEED(f);
+  FWD(f->hs.set_model(m, row, ids, n));
+}
+int32_t mmp_models_bulk(mmp_fleet *f, int32_t first, int32_t n, const mmp_model_row *rows, const int64_t *off, const int32_t *e) {
+  NEED(f);
+  if (n < 0 || !rows || !off || (off[n] > 0 && !e)) { g_err = "null argument"; return MMP_E_ARG; }
+  std::lock_guard<std::mutex> g(f->ingest_mu);
+  for (int32_t i = 0; i < n; i++) {
+    int64_t k = off[i + 1] - off[i];
+    if (k < 0 || k > 65536) { g_err = "bad edge offsets"; return MMP_E_ARG; }
+    int32_t rc = f->hs.set_model(first + i, &rows[i], e + off[i], (int32_t)k);
+    if (rc < 0) { g_err = f->hs.err; return rc; }
+  }
+  return MMP_OK;
+}
+
+int32_t mmp_fleet_commit(mmp_fleet *f) {
+  NEED(f);
+  std::lock_guard<std::mutex> g(f->ingest_mu);
+  int32_t rc = set_device(f);
+  if (rc < 0) return rc;
+  DeviceSnapshot &ds = f->snaps[1 - f->cur];
+  if (const char *m = f->hs.build_snapshot(ds.host)) { g_err = m; return MMP_E_ARG; }
+  const HostSnapshot &h = ds.host;
+  cudaStream_t st = f->commit_stream;
+  const int RW = h.row_words;
+  const int32_t nm = f->hs.n_models_used;
+  ds.n_models = nm;
+  CK(upload_vec(ds.cand, h.cand, st)); CK(upload_vec(ds.pref, h.pref, st)); CK(upload_vec(ds.has_pref, h.has_pref, st));
+  CK(upload_vec(ds.type_slot, h.type_slot, st)); CK(upload_vec(ds.rs, h.rs, st)); CK(upload_vec(ds.full, h.full, st));
+  CK(upload_vec(ds.rows, h.rows, st)); CK(upload_vec(ds.rank_of, h.rank_of, st)); CK(upload_vec(ds.csum, h.csum, st));
+  CK(upload_vec(ds.lsum, h.lsum, st)); CK(upload_vec(ds.cap_col, h.cap_col, st));
+  CK(upload_vec(ds.lthreads_col, h.lthreads_col, st)); CK(upload_vec(ds.linprog_col, h.linprog_col, st));
+  CK(upload_vec(ds.part_of_rank, h.part_of_rank, st));
+  // model rows (each snapshot keeps its own copy so in-flight readers of the other epoch are undisturbed)
+  CK(ds.models.ensure((size_t)std::max(nm, 1) * sizeof(mmp_model_row)));
+  if (nm) CK(cudaMemcpyAsync(ds.models.p, f->hs.models.data(), (size_t)nm * sizeof(mmp_model_row), cudaMemcpyHostToDevice, st));
+  // exclusion bitmap in rank space: zero, then scatter the sparse loaded/failed lists
+  CK(ds.excl.ensure((size_t)std::max(nm, 1) * RW * 4));
+  if (nm) {
+    CK(cudaMemsetAsync(ds.excl.p, 0, (size_t)nm * RW * 4, st));
+    CK(f->d_edge_inl.ensure((size_t)nm * HostState::EDGE_INL * 4));
+    CK(cudaMemcpyAsync(f->d_edge_inl.p, f->hs.edge_inl.data(), (size_t)nm * HostState::EDGE_INL * 4, cudaMemcpyHostToDevice, st));
+    k_build_bitmap<<<(nm + 255) / 256, 256, 0, st>>>(ds.excl.as<uint32_t>(), f->d_edge_inl.as<int4>(), ds.rank_of.as<int32_t>(), nm, RW);
+    f->launches++;
+    CK(cudaGetLastError());
+    std::vector<int2> pairs;
+    for (auto &kv : f->hs.edge_ovf)
+      for (int32_t e : kv.second) pairs.push_back(make_int2(kv.first, e));
+    if (!pairs.empty()) {
+      CK(upload_vec(f->d_ovf_pairs, pairs, st));
+      k_build_bitmap_ovf<<<((int)pairs.size() + 255) / 256, 256, 0, st>>>(ds.excl.as<uint32_t>(), f->d_ovf_pairs.as<int2>(),
+                                                                         (int)pairs.size(), ds.rank_of.as<int32_t>(), RW);
+      f->launches++;
+      CK(cudaGetLastError());
+    }
+  }
+  CK(cudaStreamSynchronize(st));
+  SnapshotView &v = ds.view;
+  v.n_ranks = h.n_ranks; v.row_words = RW; v.n_models = nm; v.max_instances = f->hs.cfg.max_instances;
+  v.any_rs = h.any_rs; v.n_type_ids = (int32_t)h.type_slot.size(); v.min_space = f->hs.cfg.min_space_units;
+  v.excl = ds.excl.as<uint32_t>(); v.cand = ds.cand.as<uint32_t>(); v.pref = ds.pref.as<uint32_t>();
+  v.has_pref = ds.has_pref.as<uint8_t>(); v.type_slot = ds.type_slot.as<uint16_t>(); v.rs = ds.rs.as<uint32_t>();
+  v.full = ds.full.as<uint32_t>(); v.rows = ds.rows.as<RankRow>(); v.rank_of = ds.rank_of.as<int32_t>();
+  v.csum = ds.csum.as<WordSumI>(); v.lsum = ds.lsum.as<WordSumL>(); v.models = ds.models.as<mmp_model_row>();
+  {
+    std::unique_lock<std::shared_mutex> w(f->snap_mu);  // waits for in-flight readers of the current epoch
+    f->cur = 1 - f->cur;
+    f->epoch++;
+  }
+  f->hs.dirty_models = false;
+  return f->epoch;
+}
+
+static int32_t place_impl(mmp_fleet *f, const mmp_decision_in *in, int32_t n, const mmp_instance_row *fresh, int32_t n_fresh,
+                          const int32_t *extra, int32_t n_extra, mmp_decision_out *out, mmp_decision_trace *trace,
+                          uint32_t *cand_mask, int64_t now_ms, uint64_t seed) {
+  NEED(f);
+  if (n < 0 || (n > 0 && (!in || !out)) || n_fresh < 0 || n_extra < 0 || (n_fresh > 0 && !fresh) || (n_extra > 0 && !extra)) {
+    g_err = "bad argument"; return MMP_E_ARG;
+  }
+  if (n == 0) return MMP_OK;
+  int32_t rc = set_device(f);
+  if (rc < 0) return rc;
+  std::shared_lock<std::shared_mutex> rd(f->snap_mu);
+  if (f->epoch == 0) { g_err = "no committed snapshot (call mmp_fleet_commit)"; return MMP_E_EPOCH; }
+  const DeviceSnapshot &ds = f->snaps[f->cur];
+  PlaceCtx *c = acquire_ctx(f);
+  if (!c) { g_err = "cannot create CUDA stream"; return MMP_E_CUDA; }
+  struct Rel { mmp_fleet *f; PlaceCtx *c; ~Rel() { release_ctx(f, c); } } rel{f, c};
+  c->fresh_host.resize((size_t)n_fresh);
+  for (int32_t i = 0; i < n_fresh; i++) {
+    if (const char *m = HostState::validate_row(fresh[i])) { g_err = std::string("fresh row: ") + m; return MMP_E_ARG; }
+    c->fresh_host[i] = FreshRow{fresh[i].lru_time, std::max<int64_t>(0, fresh[i].capacity - fresh[i].used), fresh[i].count, fresh[i].rpm};
+  }
+  const int RW = ds.view.row_words;
+  cudaStream_t st = c->stream;
+  CK(c->d_in.ensure((size_t)n * sizeof(mmp_decision_in)));
+  CK(c->d_out.ensure((size_t)n * sizeof(mmp_decision_out)));
+  CK(c->d_fresh.ensure((size_t)std::max(n_fresh, 1) * sizeof(FreshRow)));
+  CK(c->d_extra.ensure((size_t)std::max(n_extra, 1) * 4));
+  if (trace) CK(c->d_trace.ensure((size_t)n * sizeof(mmp_decision_trace)));
+  if (cand_mask) CK(c->d_cand.ensure((size_t)n * 2 * RW * 4));
+  CK(cudaMemcpyAsync(c->d_in.p, in, (size_t)n * sizeof(mmp_decision_in), cudaMemcpyHostToDevice, st));
+  if (n_fresh) CK(cudaMemcpyAsync(c->d_fresh.p, c->fresh_host.data(), (size_t)n_fresh * sizeof(FreshRow), cudaMemcpyHostToDevice, st));
+  if (n_extra) CK(cudaMemcpyAsync(c->d_extra.p, extra, (size_t)n_extra * 4, cudaMemcpyHostToDevice, st));
+  if (cand_mask) CK(cudaMemsetAsync(c->d_cand.p, 0, (size_t)n * 2 * RW * 4, st));
+  PlaceArgs a{ds.view, c->d_in.as<mmp_decision_in>(), n, c->d_fresh.as<FreshRow>(), n_fresh, c->d_extra.as<int32_t>(),
+              c->d_out.as<mmp_decision_out>(), trace ? c->d_trace.as<mmp_decision_trace>() : nullptr,
+              cand_mask ? c->d_cand.as<uint32_t>() : nullptr, now_ms, seed, 0};
+  if (trace || cand_mask) CK(launch_place<true>(f, a, st)); else CK(launch_place<false>(f, a, st));
+  CK(cudaMemcpyAsync(out, c->d_out.p, (size_t)n * sizeof(mmp_decision_out), cudaMemcpyDeviceToHost, st));
+  if (trace) CK(cudaMemcpyAsync(trace, c->d_trace.p, (size_t)n * sizeof(mmp_decision_trace), cudaMemcpyDeviceToHost, st));
+  if (cand_mask) CK(cudaMemcpyAsync(cand_mask, c->d_cand.p, (size_t)n * 2 * RW * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return MMP_OK;
+}
+
+int32_t mmp_place_batch(mmp_fleet *f, const mmp_decision_in *in, int32_t n, const mmp_instance_row *fresh, int32_t n_fresh,
+                        const int32_t *extra, int32_t n_extra, mmp_decision_out *out, int64_t now_ms, uint64_t seed) {
+  return place_impl(f, in, n, fresh, n_fresh, extra, n_extra, out, nullptr, nullptr, now_ms, seed);
+}
+int32_t mmp_place_batch_trace(mmp_fleet *f, const mmp_decision_in *in, int32_t n, const mmp_instance_row *fresh, int32_t n_fresh,
+                              const int32_t *extra, int32_t n_extra, mmp_decision_out *out, mmp_decision_trace *trace,
+                              uint32_t *cand_mask, int64_t now_ms, uint64_t seed) {
+  return place_impl(f, in, n, fresh, n_fresh, extra, n_extra, out, trace, cand_mask, now_ms, seed);
+}
+int32_t mmp_place_one(mmp_fleet *f, const mmp_decision_in *in, const mmp_instance_row *fresh, const int32_t *extra,
+                      mmp_decision_out *out, int64_t now_ms, uint64_t seed) {
+  if (!in) { g_err = "null decision"; return MMP_E_ARG; }
+  int32_t nf = (fresh && in->fresh >= 0) ? in->fresh + 1 : 0;
+  int32_t ne = (extra && in->extra_n > 0) ? in->extra_off + in->extra_n : 0;
+  return place_impl(f, in, 1, fresh, nf, extra, ne, out, nullptr, nullptr, now_ms, seed);
+}
+
+int32_t mmp_place_batch_device(mmp_fleet *f, const void *d_in, int32_t n, void *d_out, int64_t now_ms, uint64_t seed, float *kernel_ms) {
+  NEED(f);
+  if (n <= 0 || !d_in || !d_out) { g_err = "bad argument"; return MMP_E_ARG; }
+  int32_t rc = set_device(f);
+  if (rc < 0) return rc;
+  std::shared_lock<std::shared_mutex> rd(f->snap_mu);
+  if (f->epoch == 0) { g_err = "no committed snapshot"; return MMP_E_EPOCH; }
+  const DeviceSnapshot &ds = f->snaps[f->cur];
+  PlaceCtx *c = acquire_ctx(f);
+  if (!c) { g_err = "cannot create CUDA stream"; return MMP_E_CUDA; }
+  struct Rel { mmp_fleet *f; PlaceCtx *c; ~Rel() { release_ctx(f, c); } } rel{f, c};
+  CK(c->d_fresh.ensure(sizeof(FreshRow)));
+  CK(c->d_extra.ensure(4));
+  PlaceArgs a{ds.view, (const mmp_decision_in *)d_in, n, c->d_fresh.as<FreshRow>(), 0, c->d_extra.as<int32_t>(),
+              (mmp_decision_out *)d_out, nullptr, nullptr, now_ms, seed, 0};
+  CK(cudaEventRecord(c->e0, c->stream));
+  CK(launch_place<false>(f, a, c->stream));
+  CK(cudaEventRecord(c->e1, c->stream));
+  CK(cudaEventSynchronize(c->e1));
+  if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, c->e0, c->e1));
+  return MMP_OK;
+}
+
+int32_t mmp_device_alloc(mmp_fleet *f, int64_t bytes, void **out) {
+  NEED(f);
+  if (bytes <= 0 || !out) { g_err = "bad argument"; return MMP_E_ARG; }
+  int32_t rc = set_device(f); if (rc < 0) return rc;
+  CK(cudaMalloc(out, (size_t)bytes));
+  return MMP_OK;
+}
+int32_t mmp_device_free(mmp_fleet *f, void *p) { NEED(f); int32_t rc = set_device(f); if (rc < 0) return rc; CK(cudaFree(p)); return MMP_OK; }
+int32_t mmp_device_upload(mmp_fleet *f, void *dst, const void *src, int64_t bytes) {
+  NEED(f); int32_t rc = set_device(f); if (rc < 0) return rc;
+  CK(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyHostToDevice));
+  return MMP_OK;
+}
+int32_t mmp_device_download(mmp_fleet *f, void *dst, const void *src, int64_t bytes) {
+  NEED(f); int32_t rc = set_device(f); if (rc < 0) return rc;
+  CK(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost));
+  return MMP_OK;
+}
+int32_t mmp_host_alloc(mmp_fleet *f, int64_t bytes, void **out) {
+  NEED(f);
+  if (bytes <= 0 || !out) { g_err = "bad argument"; return MMP_E_ARG; }
+  int32_t rc = set_device(f); if (rc < 0) return rc;
+  CK(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault));
+  return MMP_OK;
+}
+int32_t mmp_host_free(mmp_fleet *f, void *p) { NEED(f); int32_t rc = set_device(f); if (rc < 0) return rc; CK(cudaFreeHost(p)); return MMP_OK; }
+int32_t mmp_flush_l2(mmp_fleet *f) {
+  NEED(f);
+  int32_t rc = set_device(f); if (rc < 0) return rc;
+  const size_t bytes = 256u << 20;  // > 126 MB L2
+  CK(f->d_flush.ensure(bytes));
+  CK(cudaMemsetAsync(f->d_flush.p, (int)(f->launches.load() & 0xff), bytes, 0));
+  CK(cudaStreamSynchronize(0));
+  return MMP_OK;
+}
+
+int32_t mmp_row_words(mmp_fleet *f) { NEED(f); return f->hs.row_words(); }
+int32_t mmp_live_instances(mmp_fleet *f) { NEED(f); std::shared_lock<std::shared_mutex> rd(f->snap_mu); return f->snaps[f->cur].host.n_ranks; }
+int32_t mmp_cluster_order(mmp_fleet *f, int32_t *out_idx, int32_t cap) {
+  NEED(f);
+  std::shared_lock<std::shared_mutex> rd(f->snap_mu);
+  const HostSnapshot &h = f->snaps[f->cur].host;
+  for (int32_t r = 0; r < h.n_ranks && r < cap; r++) out_idx[r] = h.rows[r].idx;
+  return h.n_ranks;
+}
+int32_t mmp_type_sets(mmp_fleet *f, int32_t type_id, int32_t n_idx, uint8_t *allowed, int32_t *allowed_null, uint8_t *preferred,
+                      int32_t *preferred_null) {
+  NEED(f);
+  std::shared_lock<std::shared_mutex> rd(f->snap_mu);
+  const HostSnapshot &s = f->snaps[f->cur].host;
+  if (f->epoch == 0) { g_err = "no committed snapshot"; return MMP_E_EPOCH; }
+  if (type_id < 0 || type_id > 65535) { g_err = "bad type id"; return MMP_E_ARG; }
+  // a name interned after this snapshot was committed had no configuration in it: it resolves like id 0
+  int sl = s.type_slot[type_id < (int32_t)s.type_slot.size() ? type_id : 0];
+  *allowed_null = s.allowed_null[sl]; *preferred_null = !s.has_pref[sl];
+  for (int32_t i = 0; i < n_idx; i++) {
+    int32_t r = i < (int32_t)s.rank_of.size() ? s.rank_of[i] : -1;
+    allowed[i] = (r >= 0 && !s.allowed_null[sl]) ? (s.cand[(size_t)sl * s.row_words + (r >> 5)] >> (r & 31)) & 1u : 0;
+    preferred[i] = (r >= 0) ? (s.pref[(size_t)sl * s.row_words + (r >> 5)] >> (r & 31)) & 1u : 0;
+  }
+  return MMP_OK;
+}
+int32_t mmp_instance_partition(mmp_fleet *f, int32_t idx) {
+  NEED(f);
+  std::shared_lock<std::shared_mutex> rd(f->snap_mu);
+  const HostSnapshot &s = f->snaps[f->cur].host;
+  if (idx < 0 || idx >= (int32_t)s.rank_of.size() || s.rank_of[idx] < 0) return -1;
+  return s.part_of_rank[s.rank_of[idx]];
+}
+int64_t mmp_kernel_launches(mmp_fleet *f) { return f ? f->launches.load() : 0; }
+
+}  // extern "C"
+
+#include "scan_kernels.cuh"

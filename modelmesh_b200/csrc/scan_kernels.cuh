@@ -1,0 +1,490 @@
+// scan_kernels.cuh — batch scans (plug points 3 and 4 of include/mmplace.h): ClusterStats reductions, the reaper's
+// registry sweep + top-K selection, and the per-instance time-ordered weighted LRU.  Included at the end of mmplace.cu.
+#pragma once
+
+// ---------------------------------------------------------------------------------------------------------------
+// ClusterStats (MM:1570-1591) per prohibited-type-set partition: InstanceSetStatsTracker.add (ISST:63-72) as a
+// segmented reduction over the rank-ordered instance columns.  acc layout per partition: [cap, free, count|copies]
+// ---------------------------------------------------------------------------------------------------------------
+struct StatsAcc { unsigned long long cap, free; int count, copies; };
+
+__global__ void k_stats(const RankRow *__restrict__ rows, const int64_t *__restrict__ cap_col,
+                        const int32_t *__restrict__ part_of_rank, int n_ranks, int64_t min_space, StatsAcc *acc,
+                        long long *min_lru) {
+  long long lmin = 0x7fffffffffffffffLL;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_ranks; r += gridDim.x * blockDim.x) {
+    RankRow row = rows[r];
+    int p = part_of_rank[r] + 1;  // slot 0 = whole cluster
+    unsigned long long cap = (unsigned long long)cap_col[r];
+    unsigned long long fr = row.rem < min_space ? 0ull : (unsigned long long)row.rem;  // only non-full instances (ISST:67-71)
+    atomicAdd(&acc[0].cap, cap); atomicAdd(&acc[0].free, fr); atomicAdd(&acc[0].count, 1); atomicAdd(&acc[0].copies, row.count);
+    atomicAdd(&acc[p].cap, cap); atomicAdd(&acc[p].free, fr); atomicAdd(&acc[p].count, 1); atomicAdd(&acc[p].copies, row.count);
+    if (row.lru > 0 && row.lru < lmin) lmin = row.lru;  // ISST.addLru (ISST:57-61)
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    long long t = __shfl_xor_sync(0xffffffffu, lmin, o);
+    if (t < lmin) lmin = t;
+  }
+  if ((threadIdx.x & 31) == 0) atomicMin(min_lru, lmin);
+}
+
+struct StatsResult {
+  std::vector<mmp_cluster_stats> parts;  // [0] cluster, [1+p] partition p
+};
+
+static int32_t run_stats(mmp_fleet *f, const DeviceSnapshot &ds, StatsResult &res) {
+  const HostSnapshot &h = ds.host;
+  const int np = (int)h.part_types.size();
+  PlaceCtx *c = acquire_ctx(f);
+  if (!c) { g_err = "cannot create CUDA stream"; return MMP_E_CUDA; }
+  struct Rel { mmp_fleet *f; PlaceCtx *c; ~Rel() { release_ctx(f, c); } } rel{f, c};
+  size_t bytes = (size_t)(np + 1) * sizeof(StatsAcc) + 8;
+  CK(c->d_trace.ensure(bytes));
+  CK(cudaMemsetAsync(c->d_trace.p, 0, bytes, c->stream));
+  long long *d_min = reinterpret_cast<long long *>(c->d_trace.as<char>() + (size_t)(np + 1) * sizeof(StatsAcc));
+  const long long init = 0x7fffffffffffffffLL;
+  CK(cudaMemcpyAsync(d_min, &init, 8, cudaMemcpyHostToDevice, c->stream));
+  if (h.n_ranks > 0) {
+    int grid = std::min(f->sm_count, (h.n_ranks + 255) / 256);
+    k_stats<<<grid, 256, 0, c->stream>>>(ds.rows.as<RankRow>(), ds.cap_col.as<int64_t>(), ds.part_of_rank.as<int32_t>(), h.n_ranks,
+                                        f->hs.cfg.min_space_units, c->d_trace.as<StatsAcc>(), d_min);
+    f->launches++;
+    CK(cudaGetLastError());
+  }
+  std::vector<StatsAcc> acc(np + 1);
+  long long mn = 0;
+  CK(cudaMemcpyAsync(acc.data(), c->d_trace.p, (size_t)(np + 1) * sizeof(StatsAcc), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(&mn, d_min, 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  res.parts.resize(np + 1);
+  for (int i = 0; i <= np; i++) {
+    mmp_cluster_stats &s = res.parts[i];
+    s.total_capacity = (int64_t)acc[i].cap; s.total_free = (int64_t)acc[i].free; s.instance_count = acc[i].count;
+    s.model_copy_count = acc[i].copies;
+    // quirk N10: every subset's LRU is recomputed over all cluster instances (MM:1519-1541)
+    s.global_lru = acc[i].count > 0 || i == 0 ? (int64_t)mn : INT64_MAX;
+  }
+  return MMP_OK;
+}
+
+// PARTITION_STATS_COMP (TCM:264-271): free desc, lru asc, capacity desc; partition id breaks remaining ties
+static std::vector<int> partition_order(const StatsResult &res) {
+  std::vector<int> ord;
+  for (int p = 1; p < (int)res.parts.size(); p++)
+    if (res.parts[p].instance_count > 0) ord.push_back(p - 1);
+  std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) {
+    const mmp_cluster_stats &x = res.parts[a + 1], &y = res.parts[b + 1];
+    if (x.total_free != y.total_free) return x.total_free > y.total_free;
+    if (x.global_lru != y.global_lru) return x.global_lru < y.global_lru;
+    if (x.total_capacity != y.total_capacity) return x.total_capacity > y.total_capacity;
+    return a < b;
+  });
+  return ord;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Reaper: registry sweep (MM:6536-6590 candidate rule MM:6574-6577) + bounded most-recently-used selection
+// (MM:6675-6698) as  flag/compact -> bitonic sort by (lastUsed desc, model asc) -> first-of-run.
+// ---------------------------------------------------------------------------------------------------------------
+struct SortRec { unsigned long long k; unsigned long long v; };  // k: ~biased(lastUsed) so ascending k = descending time; v: model
+
+__global__ void k_reaper_flag(const mmp_model_row *__restrict__ models, int n_models, const uint8_t *__restrict__ type_excluded,
+                              int n_type_ids, const uint8_t *__restrict__ taken, long long global_lru, int need_cutoff,
+                              long long cutoff, SortRec *out, int *out_n) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n_models) return;
+  mmp_model_row r = models[m];
+  bool ok = r.copy_count == 0 && r.fail_count < 2 && (global_lru == 0 || r.last_used > global_lru);  // MM:6574-6577
+  if (ok && taken && taken[m]) ok = false;                                                           // allCandidates.set(i, null)
+  if (ok && r.type_id < n_type_ids && type_excluded[r.type_id]) ok = false;                          // MM:6681-6683
+  if (ok && need_cutoff && !(r.last_used > cutoff)) ok = false;                                      // MM:6685-6687
+  if (ok) {
+    int pos = atomicAdd(out_n, 1);
+    unsigned long long biased = (unsigned long long)r.last_used ^ 0x8000000000000000ull;
+    out[pos] = SortRec{~biased, (unsigned long long)(unsigned)m};
+  }
+}
+__global__ void k_fill_pad(SortRec *a, int from, int to) {
+  int i = from + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < to) a[i] = SortRec{~0ull, ~0ull};
+}
+__device__ __forceinline__ bool rec_less(const SortRec &a, const SortRec &b) { return a.k < b.k || (a.k == b.k && a.v < b.v); }
+__global__ void k_bitonic_step(SortRec *a, int n, int j, int k) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int l = i ^ j;
+  if (l > i) {
+    SortRec x = a[i], y = a[l];
+    bool up = (i & k) == 0;
+    if (up ? rec_less(y, x) : rec_less(x, y)) { a[i] = y; a[l] = x; }
+  }
+}
+// keep the first record of every equal-lastUsed run (TreeSet<ModelToLoad> drops equal keys, MM:6405-6408), in order
+__global__ void k_unique_mark(const SortRec *a, int n, int *flags) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flags[i] = (i == 0 || a[i].k != a[i - 1].k) ? 1 : 0;
+}
+
+static int32_t reaper_impl(mmp_fleet *f, int32_t partition, int64_t now, uint8_t *taken, int32_t *out_models, int32_t cap) {
+  if (!out_models || cap < 0) { g_err = "bad argument"; return MMP_E_ARG; }
+  int32_t rc = set_device(f);
+  if (rc < 0) return rc;
+  std::shared_lock<std::shared_mutex> rd(f->snap_mu);
+  if (f->epoch == 0) { g_err = "no committed snapshot"; return MMP_E_EPOCH; }
+  const DeviceSnapshot &ds = f->snaps[f->cur];
+  const HostSnapshot &h = ds.host;
+  const int np = (int)h.part_types.size();
+  if (partition >= np || (partition >= 0 && !h.tc_enabled)) { g_err = "no such partition"; return MMP_E_ARG; }
+  StatsResult sr;
+  rc = run_stats(f, ds, sr);
+  if (rc < 0) return rc;
+  const mmp_cluster_stats &g = sr.parts[0];
+  if (!(g.total_capacity > 0)) return 0;                                   // MM:6456
+  const int64_t global_lru = g.total_free > 0 ? 0 : g.global_lru;          // MM:6460
+  const mmp_cluster_stats &st = partition < 0 ? g : sr.parts[partition + 1];
+  // triggerProactiveLoadsForInstanceSubset MM:6616-6664
+  int32_t free_count = 0, total_count = 0;
+  if (st.total_capacity > 0 && st.total_free > 0) {
+    int32_t size_est;
+    const int32_t def = f->hs.cfg.default_model_size_units;
+    if (st.model_copy_count < 3) size_est = def;
+    else {
+      int32_t avg = (int32_t)jsub(st.total_capacity, st.total_free) / st.model_copy_count;
+      size_est = st.model_copy_count > 10 ? avg : jaddi(avg, def) / 2;
+    }
+    if (size_est == 0) { g_err = "size estimate is zero (the reference would throw ArithmeticException)"; return MMP_E_ARG; }
+    int64_t space = 0;
+    for (int32_t r = 0; r < h.n_ranks; r++) {
+      if (partition >= 0 && h.part_of_rank[r] != partition) continue;
+      int32_t max_loads = (int32_t)((uint32_t)jmuli(h.lthreads_col[r], 50) - (uint32_t)h.linprog_col[r]);
+      if (max_loads <= 0) continue;
+      int64_t avail = jsub(h.rows[r].rem, h.cap_col[r] / 8);
+      if (avail > 0) space = (int64_t)((uint64_t)space + (uint64_t)std::min<int64_t>(avail, (int64_t)jmuli(max_loads, size_est)));
+    }
+    space /= 2;
+    free_count = (int32_t)(space / size_est);
+    int64_t d = (int64_t)((uint64_t)20 * (uint64_t)(int64_t)size_est);
+    total_count = std::max(free_count, d == 0 ? 0 : (int32_t)(d == -1 ? -st.total_capacity : st.total_capacity / d));
+  }
+  const int64_t cutoff = st.global_lru == INT64_MAX ? 0
+      : (int64_t)((uint64_t)st.global_lru + (uint64_t)std::max<int64_t>(age_of(st.global_lru, now) / 3, 1200000));
+  if (total_count <= 0) return 0;
+  // prohibited types of this partition -> per type id flag
+  std::vector<uint8_t> excl(h.type_slot.size(), 0);
+  if (partition >= 0)
+    for (const std::string &t : h.part_types[partition]) {
+      auto it = f->hs.type_ids.find(t);
+      if (it != f->hs.type_ids.end() && it->second < (int32_t)excl.size()) excl[it->second] = 1;
+    }
+  const int nm = ds.n_models;
+  if (nm == 0) return 0;
+  PlaceCtx *c = acquire_ctx(f);
+  if (!c) { g_err = "cannot create CUDA stream"; return MMP_E_CUDA; }
+  struct Rel { mmp_fleet *f; PlaceCtx *c; ~Rel() { release_ctx(f, c); } } rel{f, c};
+  cudaStream_t s = c->stream;
+  int npad = 1;
+  while (npad < nm) npad <<= 1;
+  CK(c->d_in.ensure((size_t)npad * sizeof(SortRec)));
+  CK(c->d_out.ensure((size_t)npad * 4 + 16));
+  CK(c->d_extra.ensure(excl.size() + 16));
+  CK(c->d_fresh.ensure((size_t)nm + 16));
+  CK(cudaMemcpyAsync(c->d_extra.p, excl.data(), excl.size(), cudaMemcpyHostToDevice, s));
+  if (taken) CK(cudaMemcpyAsync(c->d_fresh.p, taken, (size_t)nm, cudaMemcpyHostToDevice, s));
+  int *d_n = c->d_out.as<int>() + npad;
+  CK(cudaMemsetAsync(d_n, 0, 4, s));
+  k_reaper_flag<<<(nm + 255) / 256, 256, 0, s>>>(ds.models.as<mmp_model_row>(), nm, c->d_extra.as<uint8_t>(), (int)excl.size(),
+                                               taken ? c->d_fresh.as<uint8_t>() : nullptr, global_lru, free_count > 0 ? 0 : 1, cutoff,
+                                               c->d_in.as<SortRec>(), d_n);
+  f->launches++;
+  CK(cudaGetLastError());
+  int ncand = 0;
+  CK(cudaMemcpyAsync(&ncand, d_n, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (ncand == 0) return 0;
+  int n2 = 1;
+  while (n2 < ncand) n2 <<= 1;
+  if (n2 > ncand) { k_fill_pad<<<(n2 - ncand + 255) / 256, 256, 0, s>>>(c->d_in.as<SortRec>(), ncand, n2); f->launches++; }
+  for (int k = 2; k <= n2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) { k_bitonic_step<<<(n2 + 255) / 256, 256, 0, s>>>(c->d_in.as<SortRec>(), n2, j, k); f->launches++; }
+  CK(cudaGetLastError());
+  // distinct lastUsed values, first (lowest model index) of each: small enough to finish on the host once sorted
+  std::vector<SortRec> sorted((size_t)ncand);
+  CK(cudaMemcpyAsync(sorted.data(), c->d_in.p, (size_t)ncand * sizeof(SortRec), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  int64_t emitted = 0;
+  int32_t kept = 0, free_left = free_count;
+  unsigned long long prev_k = 0;
+  for (int i = 0; i < ncand && kept < total_count; i++) {
+    if (i > 0 && sorted[i].k == prev_k) continue;  // N12
+    prev_k = sorted[i].k;
+    kept++;
+    int64_t ts = (int64_t)((~sorted[i].k) ^ 0x8000000000000000ull);
+    if (free_left > 0) free_left--;          // MM:6713-6714
+    else if (ts < cutoff) break;             // MM:6715-6717
+    int32_t m = (int32_t)sorted[i].v;
+    if (taken) taken[m] = 1;
+    if (emitted < cap) out_models[emitted] = m;
+    emitted++;
+  }
+  return (int32_t)std::min<int64_t>(emitted, INT32_MAX);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Time-ordered weighted LRU (CLHM + LinkedDeque), one warp per instance, events applied in order.
+// An entry's position in the reference's deque is represented by the key (lastUsed, seq): LinkedDeque.insert (LD:258-288)
+// links after every element with lastUsed <= ts  ==  a fresh, larger seq; reposition (LD:243-255) keeps the node in
+// place when its successor's lastUsed >= the new time  ==  keep the position (seq just below the successor's when the
+// times tie).  Eviction (CLHM:329-352) pops the minimum key while weightedSize > capacity.
+// ---------------------------------------------------------------------------------------------------------------
+struct LruView {
+  long long *ts; long long *seq; int *weight; int *model;   // [n][slots]
+  long long *cap, *wsize, *seqctr; int *count;              // [n]
+  int n, slots;
+};
+
+__device__ __forceinline__ bool key_less(long long t1, long long s1, long long t2, long long s2) { return t1 < t2 || (t1 == t2 && s1 < s2); }
+
+// warp argmin of (ts, seq) over alive slots with key > (lo_t, lo_s) when bounded; returns slot or -1
+__device__ int lru_min_slot(const LruView &v, int inst, int lane, bool bounded, long long lo_t, long long lo_s, long long *out_t, long long *out_s) {
+  const size_t base = (size_t)inst * v.slots;
+  long long bt = 0x7fffffffffffffffLL, bs = 0x7fffffffffffffffLL;
+  int bi = -1;
+  for (int i = lane; i < v.slots; i += 32) {
+    if (v.model[base + i] < 0) continue;
+    long long t = v.ts[base + i], s = v.seq[base + i];
+    if (bounded && !key_less(lo_t, lo_s, t, s)) continue;
+    if (bi < 0 || key_less(t, s, bt, bs)) { bt = t; bs = s; bi = i; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    long long t2 = __shfl_xor_sync(0xffffffffu, bt, o), s2 = __shfl_xor_sync(0xffffffffu, bs, o);
+    int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (i2 >= 0 && (bi < 0 || key_less(t2, s2, bt, bs))) { bt = t2; bs = s2; bi = i2; }
+  }
+  *out_t = bt; *out_s = bs;
+  return bi;
+}
+__device__ int lru_find(const LruView &v, int inst, int lane, int model, int *free_slot) {
+  const size_t base = (size_t)inst * v.slots;
+  int found = -1, fr = -1;
+  for (int i = lane; i < v.slots; i += 32) {
+    int m = v.model[base + i];
+    if (m == model) found = i;
+    if (m < 0 && fr < 0) fr = i;
+  }
+  found = __reduce_max_sync(0xffffffffu, found);
+  unsigned ufr = fr < 0 ? 0x7fffffffu : (unsigned)fr;
+  ufr = __reduce_min_sync(0xffffffffu, ufr);
+  *free_slot = ufr == 0x7fffffffu ? -1 : (int)ufr;
+  return found;
+}
+
+__global__ void k_lru_apply(LruView v, const mmp_lru_event *__restrict__ ev, const int *__restrict__ ev_order,
+                            const int *__restrict__ inst_off, long long now, mmp_eviction *out, int out_cap, int *out_n, int *err) {
+  const int lane = threadIdx.x & 31;
+  const int inst = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (inst >= v.n) return;
+  const size_t base = (size_t)inst * v.slots;
+  long long wsize = v.wsize[inst], capacity = v.cap[inst], ctr = v.seqctr[inst];
+  int count = v.count[inst];
+  for (int p = inst_off[inst]; p < inst_off[inst + 1]; p++) {
+    const int ei = ev_order[p];
+    const mmp_lru_event e = ev[ei];
+    int free_slot;
+    int slot = (e.op == MMP_LRU_SET_CAPACITY) ? -1 : lru_find(v, inst, lane, e.model, &free_slot);
+    bool do_evict = false;
+    if (e.op == MMP_LRU_SET_CAPACITY) { capacity = e.last_used; do_evict = true; }
+    else if (e.op == MMP_LRU_INSERT && slot < 0) {
+      if (free_slot < 0) { if (lane == 0) atomicExch(err, 1); continue; }
+      if (lane == 0) {
+        v.model[base + free_slot] = e.model; v.weight[base + free_slot] = e.weight;
+        v.ts[base + free_slot] = e.last_used == 0 ? now : e.last_used;   // Node ctor: touch(time) (CLHM:1352-1360)
+        v.seq[base + free_slot] = ++ctr;
+      } else ++ctr;
+      __syncwarp();
+      wsize += e.weight; count++; do_evict = true;                       // AddTask (CLHM:601-610)
+    } else if ((e.op == MMP_LRU_INSERT || e.op == MMP_LRU_TOUCH) && slot >= 0) {
+      // afterRead -> touch + reposition (CLHM:383-388, 477-505; LD:243-255)
+      long long old_t = v.ts[base + slot], old_s = v.seq[base + slot];
+      long long lu = e.last_used > 0 ? (old_t > e.last_used ? old_t : e.last_used) : now;
+      if (lu != old_t) {
+        long long nt, ns;
+        // (times only move forward through max(); a smaller "now" than the entry's time can move it backwards)
+        bool moved_back = lu < old_t;
+        int nx = moved_back ? -1 : lru_min_slot(v, inst, lane, true, old_t, old_s, &nt, &ns);
+        bool stay = !moved_back && (nx < 0 || nt >= lu);
+        if (moved_back) {
+          // prev.lastUsed <= lu fails in general: unlink + insert (LD:253-254)
+          if (lane == 0) { v.ts[base + slot] = lu; v.seq[base + slot] = ctr + 1; }
+          ++ctr;
+        } else if (stay) {
+          if (lane == 0) { v.ts[base + slot] = lu; if (nx >= 0 && nt == lu) v.seq[base + slot] = ns - 1; }
+        } else {
+          if (lane == 0) { v.ts[base + slot] = lu; v.seq[base + slot] = ctr + 1; }
+          ++ctr;
+        }
+        __syncwarp();
+      }
+    } else if (e.op == MMP_LRU_RESIZE && slot >= 0) {
+      int oldw = v.weight[base + slot];
+      if (lane == 0) v.weight[base + slot] = e.weight;
+      __syncwarp();
+      wsize += (long long)e.weight - oldw; do_evict = true;              // UpdateTask (CLHM:643-651), quiet
+    } else if (e.op == MMP_LRU_REMOVE && slot >= 0) {
+      int w = v.weight[base + slot];
+      if (lane == 0) v.model[base + slot] = -1;
+      __syncwarp();
+      wsize -= (w < 0 ? -w : w); count--;                                // RemovalTask + makeDead (CLHM:614-628, 561-570)
+    }
+    if (do_evict) {
+      while (wsize > capacity) {                                          // evict() CLHM:329-352
+        long long t, s;
+        int victim = lru_min_slot(v, inst, lane, false, 0, 0, &t, &s);
+        if (victim < 0) break;
+        int w = v.weight[base + victim], m = v.model[base + victim];
+        __syncwarp();
+        if (lane == 0) {
+          v.model[base + victim] = -1;
+          int pos = atomicAdd(out_n, 1);
+          if (pos < out_cap) out[pos] = mmp_eviction{inst, m, t, w, ei};
+        }
+        __syncwarp();
+        wsize -= (w < 0 ? -w : w); count--;
+      }
+    }
+  }
+  if (lane == 0) { v.wsize[inst] = wsize; v.cap[inst] = capacity; v.seqctr[inst] = ctr; v.count[inst] = count; }
+}
+
+__global__ void k_lru_state(LruView v, long long *oldest, long long *weighted, int *count) {
+  const int lane = threadIdx.x & 31;
+  const int inst = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (inst >= v.n) return;
+  long long t, s;
+  int slot = lru_min_slot(v, inst, lane, false, 0, 0, &t, &s);
+  if (lane == 0) { oldest[inst] = slot < 0 ? -1 : t; weighted[inst] = v.wsize[inst]; count[inst] = v.count[inst]; }
+}
+
+static LruView lru_view(mmp_fleet *f) {
+  LruView v;
+  v.ts = f->lru_ts.as<long long>(); v.seq = f->lru_seq.as<long long>(); v.weight = f->lru_weight.as<int>(); v.model = f->lru_model.as<int>();
+  v.cap = f->lru_cap.as<long long>(); v.wsize = f->lru_wsize.as<long long>(); v.seqctr = f->lru_seqctr.as<long long>();
+  v.count = f->lru_count.as<int>(); v.n = f->lru_n; v.slots = f->lru_slots;
+  return v;
+}
+
+extern "C" {
+
+int32_t mmp_stats(mmp_fleet *f, mmp_cluster_stats *out, int32_t *part_ids, int32_t cap) {
+  NEED(f);
+  if (!out || !part_ids || cap < 1) { g_err = "bad argument"; return MMP_E_ARG; }
+  int32_t rc = set_device(f);
+  if (rc < 0) return rc;
+  std::shared_lock<std::shared_mutex> rd(f->snap_mu);
+  if (f->epoch == 0) { g_err = "no committed snapshot"; return MMP_E_EPOCH; }
+  const DeviceSnapshot &ds = f->snaps[f->cur];
+  StatsResult sr;
+  rc = run_stats(f, ds, sr);
+  if (rc < 0) return rc;
+  int n = 0;
+  out[n] = sr.parts[0]; part_ids[n] = -1; n++;
+  if (ds.host.tc_enabled)
+    for (int p : partition_order(sr)) {
+      if (n < cap) { out[n] = sr.parts[p + 1]; part_ids[n] = p; }
+      n++;
+    }
+  return n;
+}
+
+int32_t mmp_reaper_select(mmp_fleet *f, int32_t partition, int64_t now_ms, uint8_t *taken, int32_t *out_models, int32_t cap) {
+  NEED(f);
+  return reaper_impl(f, partition, now_ms, taken, out_models, cap);
+}
+
+int32_t mmp_lru_init(mmp_fleet *f, int32_t n, const int64_t *capacity, int32_t slots) {
+  NEED(f);
+  if (n <= 0 || !capacity || slots <= 0 || slots > (1 << 20)) { g_err = "bad argument"; return MMP_E_ARG; }
+  int32_t rc = set_device(f);
+  if (rc < 0) return rc;
+  std::lock_guard<std::mutex> g(f->ingest_mu);
+  size_t tot = (size_t)n * slots;
+  CK(f->lru_ts.ensure(tot * 8)); CK(f->lru_seq.ensure(tot * 8)); CK(f->lru_weight.ensure(tot * 4)); CK(f->lru_model.ensure(tot * 4));
+  CK(f->lru_cap.ensure((size_t)n * 8)); CK(f->lru_wsize.ensure((size_t)n * 8)); CK(f->lru_seqctr.ensure((size_t)n * 8)); CK(f->lru_count.ensure((size_t)n * 4));
+  CK(cudaMemset(f->lru_model.p, 0xff, tot * 4));
+  CK(cudaMemset(f->lru_wsize.p, 0, (size_t)n * 8)); CK(cudaMemset(f->lru_count.p, 0, (size_t)n * 4));
+  std::vector<long long> ctr((size_t)n, 1LL << 40);
+  CK(cudaMemcpy(f->lru_seqctr.p, ctr.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(f->lru_cap.p, capacity, (size_t)n * 8, cudaMemcpyHostToDevice));
+  f->lru_n = n; f->lru_slots = slots;
+  return MMP_OK;
+}
+
+int32_t mmp_lru_apply(mmp_fleet *f, const mmp_lru_event *ev, int32_t n, int64_t now_ms, mmp_eviction *out, int32_t cap) {
+  NEED(f);
+  if (n < 0 || (n > 0 && !ev) || cap < 0 || (cap > 0 && !out)) { g_err = "bad argument"; return MMP_E_ARG; }
+  if (f->lru_n == 0) { g_err = "mmp_lru_init not called"; return MMP_E_STATE; }
+  if (n == 0) return 0;
+  int32_t rc = set_device(f);
+  if (rc < 0) return rc;
+  std::lock_guard<std::mutex> g(f->ingest_mu);
+  // group events by instance, keeping their order (counting sort)
+  std::vector<int> off((size_t)f->lru_n + 1, 0), order((size_t)n);
+  for (int32_t i = 0; i < n; i++) {
+    if (ev[i].instance < 0 || ev[i].instance >= f->lru_n || ev[i].op < 0 || ev[i].op > MMP_LRU_SET_CAPACITY || ev[i].last_used < 0 ||
+        (ev[i].op != MMP_LRU_SET_CAPACITY && ev[i].model < 0)) { g_err = "bad LRU event"; return MMP_E_ARG; }
+    off[ev[i].instance + 1]++;
+  }
+  for (int i = 0; i < f->lru_n; i++) off[i + 1] += off[i];
+  { std::vector<int> pos(off.begin(), off.end() - 1); for (int32_t i = 0; i < n; i++) order[pos[ev[i].instance]++] = i; }
+  PlaceCtx *c = acquire_ctx(f);
+  if (!c) { g_err = "cannot create CUDA stream"; return MMP_E_CUDA; }
+  struct Rel { mmp_fleet *f; PlaceCtx *c; ~Rel() { release_ctx(f, c); } } rel{f, c};
+  cudaStream_t s = c->stream;
+  CK(c->d_in.ensure((size_t)n * sizeof(mmp_lru_event)));
+  CK(c->d_extra.ensure((size_t)n * 4));
+  CK(c->d_fresh.ensure(off.size() * 4));
+  CK(c->d_out.ensure((size_t)std::max(cap, 1) * sizeof(mmp_eviction)));
+  CK(c->d_trace.ensure(16));
+  CK(cudaMemcpyAsync(c->d_in.p, ev, (size_t)n * sizeof(mmp_lru_event), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(c->d_extra.p, order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(c->d_fresh.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(c->d_trace.p, 0, 16, s));
+  int warps_per_block = 4;
+  int grid = (f->lru_n + warps_per_block - 1) / warps_per_block;
+  k_lru_apply<<<grid, warps_per_block * 32, 0, s>>>(lru_view(f), c->d_in.as<mmp_lru_event>(), c->d_extra.as<int>(), c->d_fresh.as<int>(),
+                                                   now_ms, c->d_out.as<mmp_eviction>(), cap, c->d_trace.as<int>(), c->d_trace.as<int>() + 1);
+  f->launches++;
+  CK(cudaGetLastError());
+  int hdr[2] = {0, 0};
+  CK(cudaMemcpyAsync(hdr, c->d_trace.p, 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (hdr[1]) { g_err = "LRU slot capacity exceeded for some instance (raise slots_per_instance)"; return MMP_E_NOMEM; }
+  int got = std::min(hdr[0], cap);
+  std::vector<mmp_eviction> tmp((size_t)got);
+  if (got) CK(cudaMemcpy(tmp.data(), c->d_out.p, (size_t)got * sizeof(mmp_eviction), cudaMemcpyDeviceToHost));
+  // each instance's evictions were appended in its own order; group by instance keeping that order
+  std::stable_sort(tmp.begin(), tmp.end(), [](const mmp_eviction &a, const mmp_eviction &b) { return a.instance < b.instance; });
+  for (int i = 0; i < got; i++) out[i] = tmp[i];
+  return hdr[0];
+}
+
+int32_t mmp_lru_state(mmp_fleet *f, int32_t n, int64_t *oldest, int64_t *weighted, int32_t *count) {
+  NEED(f);
+  if (n != f->lru_n || !oldest || !weighted || !count) { g_err = "bad argument"; return MMP_E_ARG; }
+  int32_t rc = set_device(f);
+  if (rc < 0) return rc;
+  std::lock_guard<std::mutex> g(f->ingest_mu);
+  PlaceCtx *c = acquire_ctx(f);
+  if (!c) { g_err = "cannot create CUDA stream"; return MMP_E_CUDA; }
+  struct Rel { mmp_fleet *f; PlaceCtx *c; ~Rel() { release_ctx(f, c); } } rel{f, c};
+  CK(c->d_in.ensure((size_t)n * 8)); CK(c->d_out.ensure((size_t)n * 8)); CK(c->d_extra.ensure((size_t)n * 4));
+  k_lru_state<<<(n + 3) / 4, 128, 0, c->stream>>>(lru_view(f), c->d_in.as<long long>(), c->d_out.as<long long>(), c->d_extra.as<int>());
+  f->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(oldest, c->d_in.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(weighted, c->d_out.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(count, c->d_extra.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return MMP_OK;
+}
+
+}  // extern "C"

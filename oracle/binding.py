@@ -57,6 +57,7 @@ def lib() -> C.CDLL:
             "orc_set_active": (C.c_int, [P, I32, I32]),
             "orc_types_set": (C.c_int, [P, I32, STRS, P, STRS, P, STRS]),
             "orc_tc_converge": (C.c_int, [P]),
+            "orc_tc_defer_refresh": (C.c_int, [P, C.c_int]),
             "orc_set_replaced_replicasets": (C.c_int, [P, STRS, I32]),
             "orc_get_replaced_replicasets": (C.c_int, [P, C.c_char_p, I32]),
             "orc_type_sets": (C.c_int, [P, C.c_char_p, I32, P, C.POINTER(I32), P, C.POINTER(I32)]),
@@ -134,6 +135,9 @@ class OracleFleet:
             pref_off.append(len(pref))
         ro, po = np.asarray(req_off, dtype=np.int32), np.asarray(pref_off, dtype=np.int32)
         assert self.L.orc_types_set(self.h, len(names), _strs(names), _ptr(ro), _strs(req), _ptr(po), _strs(pref)) == 0
+
+    def tc_defer_refresh(self, defer: bool):
+        assert self.L.orc_tc_defer_refresh(self.h, int(defer)) == 0
 
     def tc_converge(self):
         assert self.L.orc_tc_converge(self.h) == 0

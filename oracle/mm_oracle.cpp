@@ -267,7 +267,30 @@ struct Isst {
   }
 };
 
-typedef std::optional<std::set<int32_t>> OptSet;  // Set<String> of instance ids or null (ids <-> idx bijection)
+// Set<String> of instance ids (ids <-> idx bijection): sorted vector for iteration/equality + dense byte map so that
+// contains() is O(1) like the reference's HashSet/ImmutableSet.
+struct IdSet {
+  std::vector<int32_t> v;
+  std::vector<uint8_t> m;
+  size_t count(int32_t i) const { return (i >= 0 && (size_t)i < m.size() && m[i]) ? 1 : 0; }
+  size_t size() const { return v.size(); }
+  bool empty() const { return v.empty(); }
+  void insert(int32_t i) {
+    if (count(i)) return;
+    if ((size_t)i >= m.size()) m.resize((size_t)i + 1, 0);
+    m[i] = 1;
+    v.insert(std::lower_bound(v.begin(), v.end(), i), i);
+  }
+  void erase(int32_t i) {
+    if (!count(i)) return;
+    m[i] = 0;
+    v.erase(std::lower_bound(v.begin(), v.end(), i));
+  }
+  void clear() { v.clear(); m.clear(); }
+  std::vector<int32_t>::const_iterator begin() const { return v.begin(); }
+  std::vector<int32_t>::const_iterator end() const { return v.end(); }
+};
+typedef std::optional<IdSet> OptSet;  // ... or null
 
 // ModelTypeConstraints TCM:337-506
 struct Mtc {
@@ -305,17 +328,17 @@ bool updateInstanceSet(int32_t iid, const std::vector<JStr> &instanceLabels, con
   bool curMatch = instanceSet && instanceSet->count(iid);
   if (instanceMatches(instanceLabels, typeLabels, matchAll)) {
     if (!curMatch) {
-      std::set<int32_t> s = instanceSet ? *instanceSet : std::set<int32_t>();
+      IdSet s = instanceSet ? *instanceSet : IdSet();
       s.insert(iid);
       out = std::move(s);
       return true;
     }
   } else if (curMatch) {
     if (instanceSet->size() == 1) {
-      if (matchAll) out = std::set<int32_t>(); else out = std::nullopt;
+      if (matchAll) out = IdSet(); else out = std::nullopt;
       return true;
     }
-    std::set<int32_t> s = *instanceSet;
+    IdSet s = *instanceSet;
     s.erase(iid);
     out = std::move(s);
     return true;
@@ -423,23 +446,25 @@ struct Tcm {
   Isst *localInstanceSetStats = nullptr;
   std::map<std::string, Mtcp> typeConstraintsMap;
   OptSet defaultPreferredInstances;
+  bool deferRefresh = false;  // test-harness switch for bulk loads, see orc_tc_defer_refresh
 
-  Mtcp getTypeConstraints(const std::string &type) const {  // TCM:258-262
+  // (raw pointers: the map is not mutated while decisions run, and a Java reference read costs no refcount traffic)
+  const Mtc *getTypeConstraints(const std::string &type) const {  // TCM:258-262
     auto it = typeConstraintsMap.find(type);
-    if (it != typeConstraintsMap.end()) return it->second;
+    if (it != typeConstraintsMap.end()) return it->second.get();
     it = typeConstraintsMap.find("_default");
-    return it != typeConstraintsMap.end() ? it->second : nullptr;
+    return it != typeConstraintsMap.end() ? it->second.get() : nullptr;
   }
   // TCM:242-245: null means all
-  const OptSet *getCandidateInstances(const std::string &type, Mtcp &hold) const {
-    hold = getTypeConstraints(type);
+  const OptSet *getCandidateInstances(const std::string &type) const {
+    const Mtc *m = getTypeConstraints(type);
     static const OptSet NULLSET;
-    return hold ? &hold->allowedInstances : &NULLSET;
+    return m ? &m->allowedInstances : &NULLSET;
   }
   // TCM:248-251
-  const OptSet *getPreferredInstances(const std::string &type, Mtcp &hold) const {
-    hold = getTypeConstraints(type);
-    return hold ? &hold->preferredInstances : &defaultPreferredInstances;
+  const OptSet *getPreferredInstances(const std::string &type) const {
+    const Mtc *m = getTypeConstraints(type);
+    return m ? &m->preferredInstances : &defaultPreferredInstances;
   }
   Isst *getStatsForLabels(const std::vector<JStr> &labels) {  // TCM:508-510
     auto it = labelsToInstanceSetStats.find(labels);
@@ -456,7 +481,7 @@ struct Tcm {
   void instanceRemoved(int32_t iid, const std::vector<JStr> &labels);
   void typeMappingsUpdated(std::map<std::string, ConfigTypeConstraints> newConfig);
   void refreshPerTypeInstanceSets(std::map<std::string, Mtcp> &mtcMap);
-  static OptSet inferPreferredInstances(const std::map<int32_t, int32_t> &instanceScores, const std::set<int32_t> *include);
+  static OptSet inferPreferredInstances(const std::map<int32_t, int32_t> &instanceScores, const IdSet *include);
 };
 
 struct Fleet {
@@ -491,14 +516,14 @@ struct Fleet {
 Mtcp Tcm::fromInstanceSet(const std::vector<JStr> &requiredLabels, const std::vector<JStr> &preferredLabels,
                           const ClusterState &instances, bool hasStats, const std::vector<Isst *> &stats) {  // TCM:418-446
   bool haveReq = !requiredLabels.empty();
-  std::set<int32_t> required;
+  IdSet required;
   OptSet preferred;
   for (const Entry &ent : instances) {
     const std::vector<JStr> &instanceLabels = ent.rec->labels;
     if (haveReq && instanceMatches(instanceLabels, requiredLabels, true)) {
       required.insert(ent.idx);
     } else if (instanceMatches(instanceLabels, preferredLabels, false)) {  // N11 else-if
-      if (!preferred) preferred = std::set<int32_t>();
+      if (!preferred) preferred = IdSet();
       preferred->insert(ent.idx);
     }
   }
@@ -583,7 +608,7 @@ Isst *Tcm::instanceAdded(int32_t iid, const std::vector<JStr> &labels, bool /*in
   bool changed = instanceUpdated(iid, labels, typeConstraintsMap, newMap);
   Isst *instanceSetStats = getInstanceSetStats(iid, labels, changed ? newMap : typeConstraintsMap);
   if (changed) {
-    refreshPerTypeInstanceSets(newMap);
+    if (!deferRefresh) refreshPerTypeInstanceSets(newMap);
     typeConstraintsMap = newMap;
   }
   return instanceSetStats;
@@ -688,8 +713,8 @@ void Tcm::refreshPerTypeInstanceSets(std::map<std::string, Mtcp> &mtcMap) {
 }
 
 // TCM:727-747
-OptSet Tcm::inferPreferredInstances(const std::map<int32_t, int32_t> &instanceScores, const std::set<int32_t> *include) {
-  std::set<int32_t> instanceIds;
+OptSet Tcm::inferPreferredInstances(const std::map<int32_t, int32_t> &instanceScores, const IdSet *include) {
+  IdSet instanceIds;
   int32_t min = INT32_MAX, max = 0;
   for (auto &ent : instanceScores) {
     if (include != nullptr && !include->count(ent.first)) continue;
@@ -825,9 +850,8 @@ inline int64_t age(int64_t t, int64_t now) { return t == 0 ? 0 : jsub(now, t); }
 void getNext(const Fleet &f, const std::string &modelType, int32_t self, const IR &fresh, bool favourSelf,
              int64_t lastUsedTime, const ExcludeSet &exclude, int64_t now, uint64_t rnd, GetNextOut &o) {
   const bool excludeSelf = exclude.isExcluded(self);
-  Mtcp hold1, hold2;
   static const OptSet NULLSET;
-  const OptSet *constrainTo = f.haveTc ? f.tcm.getCandidateInstances(modelType, hold1) : &NULLSET;
+  const OptSet *constrainTo = f.haveTc ? f.tcm.getCandidateInstances(modelType) : &NULLSET;
   const bool rsEmpty = f.upgradeTracker.likelyReplacedReplicaSets.empty();
 
   EntIter it{f.clusterState.begin(), f.clusterState.end(), nullptr, 0, &f, constrainTo, &exclude, true, nullptr};
@@ -847,7 +871,7 @@ void getNext(const Fleet &f, const std::string &modelType, int32_t self, const I
   std::vector<int32_t> &candidates = o.candidates, &instReqLoad = o.instReqLoad;
   candidates.clear(); instReqLoad.clear();
 
-  const OptSet *prefer = f.haveTc ? f.tcm.getPreferredInstances(modelType, hold2) : &NULLSET;
+  const OptSet *prefer = f.haveTc ? f.tcm.getPreferredInstances(modelType) : &NULLSET;
   auto preferContains = [&](int32_t iid) { return (*prefer)->count(iid) != 0; };
 
   bool simpleCase = !*prefer || preferContains(bestIid);
@@ -1145,6 +1169,12 @@ int orc_types_set(orc_fleet *h, int32_t n, const char *const *names, const int32
   return 0;
 }
 
+int orc_tc_defer_refresh(orc_fleet *h, int defer) {
+  if (!h) return -1;
+  h->f.tcm.deferRefresh = defer != 0;
+  return 0;
+}
+
 int orc_tc_converge(orc_fleet *h) {
   if (!h || !h->f.haveTc) return -1;
   std::map<std::string, Mtcp> m = h->f.tcm.typeConstraintsMap;
@@ -1172,10 +1202,9 @@ int orc_type_sets(orc_fleet *h, const char *type, int32_t n_idx, uint8_t *allowe
                   uint8_t *preferred, int32_t *preferred_null) {
   if (!h) return -1;
   Fleet &f = h->f;
-  Mtcp h1, h2;
   static const OptSet NULLSET;
-  const OptSet *a = f.haveTc ? f.tcm.getCandidateInstances(type, h1) : &NULLSET;
-  const OptSet *p = f.haveTc ? f.tcm.getPreferredInstances(type, h2) : &NULLSET;
+  const OptSet *a = f.haveTc ? f.tcm.getCandidateInstances(type) : &NULLSET;
+  const OptSet *p = f.haveTc ? f.tcm.getPreferredInstances(type) : &NULLSET;
   *allowed_null = !*a; *preferred_null = !*p;
   for (int i = 0; i < n_idx; i++) {
     allowed[i] = *a ? ((*a)->count(i) ? 1 : 0) : 0;

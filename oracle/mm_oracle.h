@@ -88,6 +88,10 @@ int orc_types_set(orc_fleet *, int32_t n, const char *const *names, const int32_
  * stopped changing; calling it explicitly removes the arrival-order lag of quirk N10 so that a snapshot-based solver
  * can be compared without replaying the exact event order.  No code other than the literal restatement runs. */
 int orc_tc_converge(orc_fleet *);
+/* Bulk-load switch: while set, TCM.instanceAdded (TCM:513-526) skips its refreshPerTypeInstanceSets call (an
+ * O(instances x types) pass per event, quadratic for a 10k-instance fleet).  The sets it would have produced are a
+ * pure function of the membership sets, so a following orc_tc_converge() yields the same state. */
+int orc_tc_defer_refresh(orc_fleet *, int defer);
 
 /* Directly set UpgradeTracker.likelyReplacedReplicaSets keys (UT:71); the event-driven tracker
  * (UT:120-187) also runs inside orc_instance_event. */

@@ -30,7 +30,7 @@ def emul_lib():
             os.path.join(ROOT, "modelmesh_b200", "csrc", "place_core.cuh"), os.path.join(ROOT, "include", "mmplace.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         os.makedirs(os.path.dirname(so), exist_ok=True)
-        subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-Wall", "-shared", "-o", so, srcs[0]])
+        subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-Wall", "-Wl,-Bsymbolic", "-shared", "-o", so, srcs[0]])
     return _lib.load(so, require_all=False)
 
 

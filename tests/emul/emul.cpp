@@ -133,8 +133,9 @@ int32_t mmp_cluster_order(mmp_fleet *f, int32_t *out_idx, int32_t cap) {
 int32_t mmp_type_sets(mmp_fleet *f, int32_t type_id, int32_t n_idx, uint8_t *allowed, int32_t *allowed_null, uint8_t *preferred,
                       int32_t *preferred_null) {
   const HostSnapshot &s = f->snap;
-  if (type_id < 0 || type_id >= (int32_t)s.type_slot.size()) { g_err = "bad type id"; return MMP_E_ARG; }
-  int sl = s.type_slot[type_id];
+  if (type_id < 0 || type_id > 65535) { g_err = "bad type id"; return MMP_E_ARG; }
+  // a name interned after this snapshot was committed had no configuration in it: it resolves like id 0
+  int sl = s.type_slot[type_id < (int32_t)s.type_slot.size() ? type_id : 0];
   *allowed_null = s.allowed_null[sl]; *preferred_null = !s.has_pref[sl];
   for (int32_t i = 0; i < n_idx; i++) {
     int32_t r = i < (int32_t)s.rank_of.size() ? s.rank_of[i] : -1;

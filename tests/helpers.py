@@ -13,6 +13,7 @@ def oracle_from_synth(fl: SynthFleet) -> ob.OracleFleet:
     """Config first (as a pod does at start-up, MM:777), instances as ADDED events, then one converged refresh."""
     o = ob.OracleFleet(fl.min_space_units, fl.min_churn_age_ms, fl.default_model_size_units)
     o.types_set(fl.type_config)
+    o.tc_defer_refresh(fl.n_instances > 2000)  # same final state after tc_converge(), without the quadratic refreshes
     for i in range(fl.n_instances):
         o.instance_event(ob.ADDED, i, fl.inst_rows[i], fl.inst_ids[i], fl.inst_locs[i], fl.inst_zones[i],
                          fl.inst_labels[i], fl.now_ms)
@@ -52,6 +53,37 @@ def oracle_inputs(fl: SynthFleet, sd: SynthDecisions):
         idx[off[i]:off[i] + k] = fl.edge_inst[a:b]
         e0 = dec["extra_off"][i]
         idx[off[i] + k:off[i + 1]] = sd.extra[e0:e0 + dec["extra_n"][i]]
+    return od, off, idx
+
+
+def oracle_inputs_fast(fl: SynthFleet, sd: SynthDecisions):
+    """Vectorised oracle_inputs for large batches."""
+    dec = sd.dec
+    n = len(dec)
+    od = np.zeros(n, dtype=ob.DECISION)
+    od["type_idx"] = fl.model_type[dec["model"]]
+    od["self"] = dec["self"]
+    od["fresh_idx"] = dec["fresh"]
+    od["favour_self"] = (dec["flags"] & L.DF_FAVOUR_SELF) != 0
+    use_model = (dec["flags"] & L.DF_MODEL_LAST_USED) != 0
+    od["last_used"] = np.where(use_model, fl.model_last_used[dec["model"]], dec["last_used"])
+    od["decision_id"] = np.arange(n, dtype=np.uint64)
+    m = dec["model"].astype(np.int64)
+    dm = (fl.edge_off[m + 1] - fl.edge_off[m]).astype(np.int64)
+    dx = dec["extra_n"].astype(np.int64)
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(dm + dx, out=off[1:])
+    idx = np.zeros(int(off[-1]), dtype=np.int32)
+    for deg, src_base, src, shift in ((dm, fl.edge_off[m], fl.edge_inst, np.zeros(n, dtype=np.int64)),
+                                      (dx, dec["extra_off"].astype(np.int64), sd.extra, dm)):
+        tot = int(deg.sum())
+        if tot == 0:
+            continue
+        owner = np.repeat(np.arange(n, dtype=np.int64), deg)
+        start = np.zeros(n, dtype=np.int64)
+        np.cumsum(deg[:-1], out=start[1:])
+        within = np.arange(tot, dtype=np.int64) - start[owner]
+        idx[off[owner] + shift[owner] + within] = src[src_base[owner] + within]
     return od, off, idx
 
 

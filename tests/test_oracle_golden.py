@@ -1,0 +1,194 @@
+"""Known-answer tests that pin the oracle to what the reference's own tests assert.
+
+The reference holds no unit vectors for this path; these are its integration scenarios restated as event traces.
+Everything the scenarios do not reach (tie-break chain, preferred cases (a)/(b), rpm filter, UpgradeTracker, inferred
+preferences, reaper selection) is "parity unpinned by reference tests" and is covered by brute-force cross-checks in
+test_oracle_properties.py instead.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+
+MIB = 1024 * 1024
+UNIT = 8192
+
+
+def ev(op, key, weight=0, last_used=0):
+    return (op, key, weight, last_used)
+
+
+def events(lst):
+    a = np.zeros(len(lst), dtype=ob.LRU_EVENT)
+    for i, e in enumerate(lst):
+        a[i] = e
+    return a
+
+
+INSERT, TOUCH, RESIZE, REMOVE, SETCAP = 0, 1, 2, 3, 4
+
+
+def load_model(key, size_units, t):
+    """loadLocal: 1-unit placeholder (INSERTION_WEIGHT, MM:5011,5061) then inflate to the predicted size (MM:2094-2100)."""
+    return [ev(INSERT, key, 1, t), ev(RESIZE, key, size_units)]
+
+
+def test_capacity_constants_evictions_model_mesh_test(oracle_lib):
+    # T/EvictionsModelMeshTest.java:30-33: 1024 MiB capacity, 50 MiB default size, 6 loading threads
+    #   => unload buffer 75 MiB, effective capacity 949 MiB
+    cap_units = 1024 * MIB // UNIT
+    default_units = 50 * MIB // UNIT
+    reserve = oracle_lib.orc_unload_reserve_units(cap_units, 6, default_units)
+    assert reserve == 75 * MIB // UNIT == 9600
+    assert (cap_units - reserve) * UNIT == 949 * MIB
+    # isFull threshold MM:767-769 with an unload manager: max(6400, min(6400*6, 131072/20)) = 6553
+    assert oracle_lib.orc_min_space_units(cap_units, 6, default_units, 1) == 6553
+    # DummyModelMesh (T/DummyModelMesh.java:39): 10 x 20 MiB, 20 MiB models, reserve clamps to cap/10 => 9 models fit
+    assert oracle_lib.orc_unload_reserve_units(25600, 8, 2560) == 2560
+
+
+def test_basic_eviction_test_trace(oracle_lib):
+    """T/EvictionsModelMeshTest.java:36-128 basicEvictionTest as an LRU event trace."""
+    cap = 949 * MIB // UNIT  # effective capacity once the unload buffer entry is set aside
+    m50, m160 = 50 * MIB // UNIT, 160 * MIB // UNIT
+    lru = ob.OracleLru(cap)
+    t = 1_000_000
+    trace = []
+    for i in range(18):  # :51-62 eighteen 50 MiB models fit
+        trace += load_model(i, m50, t + 10 * i)
+    assert len(lru.apply(events(trace), now_ms=t)) == 0 and lru.size() == 18
+    # :64-83 the 19th takes the total to 950 MiB > 949 and evicts exactly myModel0 (the oldest)
+    e = lru.apply(events(load_model(18, m50, t + 200)), now_ms=t)
+    assert [int(x["key"]) for x in e] == [0]
+    # :85-105 the 20th and 21st evict myModel1 then myModel2
+    e = lru.apply(events(load_model(19, m50, t + 210)), now_ms=t)
+    assert [int(x["key"]) for x in e] == [1]
+    e = lru.apply(events(load_model(20, m50, t + 220)), now_ms=t)
+    assert [int(x["key"]) for x in e] == [2]
+    # :107-109 re-ensureLoaded(myModel0) evicts myModel3
+    e = lru.apply(events(load_model(0, m50, t + 230)), now_ms=t)
+    assert [int(x["key"]) for x in e] == [3]
+    # :111-123 a 160 MiB model: predicted 50 MiB evicts myModel4, post-load sizing (UpdateTask) evicts 5 and 6, keeps 7
+    e = lru.apply(events(load_model(21, m50, t + 240)), now_ms=t)
+    assert [int(x["key"]) for x in e] == [4]
+    e = lru.apply(events([ev(RESIZE, 21, m160)]), now_ms=t)
+    assert [int(x["key"]) for x in e] == [5, 6]
+    keys, _, _ = lru.dump()
+    assert 7 in keys and 21 in keys and lru.weighted_size() <= cap
+    assert lru.oldest_time() == t + 70
+
+
+def test_concurrent_eviction_exactly_the_ten_oldest(oracle_lib):
+    """T/EvictionsModelMeshTest.java:136-200: ten inserts into a full cache evict exactly the ten oldest, no cascade."""
+    cap = 949 * MIB // UNIT
+    m50 = 50 * MIB // UNIT
+    lru = ob.OracleLru(cap)
+    t = 5_000_000
+    tr = []
+    for i in range(18):
+        tr += load_model(i, m50, t + i)
+    lru.apply(events(tr), now_ms=t)
+    tr = []
+    for i in range(18, 28):
+        tr += load_model(i, m50, t + 100 + i)
+    e = lru.apply(events(tr), now_ms=t)
+    assert sorted(int(x["key"]) for x in e) == list(range(10))
+    assert [int(x["key"]) for x in e] == list(range(10))  # oldest first
+
+
+def test_multi_load_with_eviction_standalone(oracle_lib):
+    """T/ModelMeshEvictionsTest.java:156-187: 10 x 2560-unit capacity, 0.9 factor => 9 fit; loading 9+3 keeps the last 9."""
+    lru = ob.OracleLru(25600 - 2560)
+    tr = []
+    for i in range(12):
+        tr += load_model(i, 2560, 1000 + i)
+    e = lru.apply(events(tr), now_ms=999)
+    assert [int(x["key"]) for x in e] == [0, 1, 2]
+    keys, _, _ = lru.dump()
+    assert sorted(keys.tolist()) == list(range(3, 12))
+
+
+def test_multi_load_with_big_eviction_standalone(oracle_lib):
+    """:190-228 one 4x-size model displaces four: survivors are ids[6..] of the twelve."""
+    lru = ob.OracleLru(25600 - 2560)
+    tr = []
+    for i in range(11):
+        tr += load_model(i, 2560, 1000 + i)
+    lru.apply(events(tr), now_ms=999)
+    lru.apply(events(load_model(11, 4 * 2560, 2000)), now_ms=999)  # size hint = 4x (KNOWN_SIZE, MM:5160-5163)
+    keys, _, _ = lru.dump()
+    assert sorted(keys.tolist()) == list(range(6, 12))
+
+
+def test_multi_load_with_eviction_standalone_reuse(oracle_lib):
+    """:240-281 touching the first three (internalOperation(load=true,lastUsed=0) -> now) protects them."""
+    lru = ob.OracleLru(25600 - 2560)
+    tr = []
+    for i in range(9):
+        tr += load_model(i, 2560, 1000 + i)
+    lru.apply(events(tr), now_ms=1500)
+    lru.apply(events([ev(TOUCH, 0, 0, 0), ev(TOUCH, 1, 0, 0), ev(TOUCH, 2, 0, 0)]), now_ms=2000)
+    tr = []
+    for i in range(9, 12):
+        tr += load_model(i, 2560, 3000 + i)
+    e = lru.apply(events(tr), now_ms=3000)
+    assert [int(x["key"]) for x in e] == [3, 4, 5]
+    keys, _, _ = lru.dump()
+    assert {0, 1, 2, 9, 10, 11} <= set(keys.tolist())
+
+
+def _row(**kw):
+    r = np.zeros(1, dtype=ob.INST)
+    r["capacity"], r["lru_time"], r["l_threads"], r["active"], r["vers"] = 131072, (1 << 63) - 1, 6, 1, 1
+    for k, v in kw.items():
+        r[k] = v
+    return r[0]
+
+
+def test_error_propagation_test_type_constraint(oracle_lib):
+    """T/ModelMeshErrorPropagationTest.java:52-62,89-121: type my-type-1 requires my-label-1; only pod 9000 carries it,
+    so the single copy always lands there, whichever pod the request enters through."""
+    o = ob.OracleFleet(6553, 600_000, 6400)
+    o.types_set({"my-type-1": {"required": ["my-label-1"]}})
+    o.instance_event(ob.ADDED, 0, _row(), "inst-9000", labels=["my-label-1"], now_ms=1)
+    o.instance_event(ob.ADDED, 1, _row(), "inst-9004", labels=[], now_ms=2)
+    allowed, pref = o.type_sets("my-type-1", 2)
+    assert allowed.tolist() == [True, False]
+    dec = np.zeros(4, dtype=ob.DECISION)
+    dec["type_idx"] = 0
+    dec["self"] = [0, 1, 0, 1]
+    dec["fresh_idx"] = -1
+    dec["favour_self"] = [0, 0, 1, 1]
+    dec["decision_id"] = np.arange(4)
+    off = np.zeros(5, dtype=np.int64)
+    res = o.get_next_batch(dec, ["my-type-1"], off, np.zeros(0, dtype=np.int32), 10, 1)
+    # entering at 9000: itself (ABORT_REQUEST); entering at 9004: forwarded to 9000
+    assert res["target"].tolist() == [ob.SELF, 0, ob.SELF, 0]
+    # once loaded there it is excluded, nothing else qualifies -> null ("Nowhere available to load")
+    off = np.asarray([0, 1, 2, 3, 4], dtype=np.int64)
+    res = o.get_next_batch(dec, ["my-type-1"], off, np.zeros(4, dtype=np.int32), 10, 1)
+    assert res["target"].tolist() == [ob.NONE] * 4
+
+
+def test_documented_constraint_shapes(oracle_lib):
+    """config/examples/type-constraints-example/README.md:21-39 — the only documented JSON shapes."""
+    cfg = {"type-name1": {"required": ["label1", "label2"]}, "type-name2": {"preferred": ["label2"]},
+           "type-name3": {"required": ["label1", "label3"], "preferred": ["label4"]},
+           "_default": {"required": ["_unrecognized"]}}
+    o = ob.OracleFleet(6553, 600_000, 6400)
+    o.types_set(cfg)
+    labels = [["label1", "label2"], ["label2"], ["label1", "label3", "label4"], ["label1", "label3"], []]
+    for i, l in enumerate(labels):
+        o.instance_event(ob.ADDED, i, _row(), f"pod-{i:04d}", labels=l, now_ms=i)
+    o.tc_converge()
+    a1, _ = o.type_sets("type-name1", 5)
+    a3, _ = o.type_sets("type-name3", 5)
+    ad, _ = o.type_sets("some-unknown-type", 5)
+    a2, p2 = o.type_sets("type-name2", 5)
+    assert a1.tolist() == [True, False, False, False, False]
+    assert a3.tolist() == [False, False, True, True, False]
+    assert ad.tolist() == [False] * 5  # _default: nowhere
+    assert a2 is None  # no required labels: all instances are candidates
