@@ -55,6 +55,7 @@ def lib() -> C.CDLL:
             "orc_create": (P, [I64, I64, I32]), "orc_destroy": (None, [P]),
             "orc_instance_event": (C.c_int, [P, C.c_int, I32, P, C.c_char_p, C.c_char_p, C.c_char_p, STRS, I32, I64]),
             "orc_set_active": (C.c_int, [P, I32, I32]),
+            "orc_bulk_add": (C.c_int, [P, I32, P, STRS, STRS, STRS, P, STRS]),
             "orc_types_set": (C.c_int, [P, I32, STRS, P, STRS, P, STRS]),
             "orc_tc_converge": (C.c_int, [P]),
             "orc_tc_defer_refresh": (C.c_int, [P, C.c_int]),
@@ -117,6 +118,22 @@ class OracleFleet:
         rc = self.L.orc_instance_event(self.h, etype, idx, _ptr(r), iid.encode(), None if loc is None else loc.encode(),
                                        None if zone is None else zone.encode(), _strs(labels), len(labels), now_ms)
         assert rc == 0
+
+    def bulk_add(self, rows: np.ndarray, ids, locs, zones, labels):
+        rows = np.ascontiguousarray(rows, dtype=INST)
+        n = len(rows)
+        off = np.zeros(n + 1, dtype=np.int32)
+        flat = []
+        for i, l in enumerate(labels):
+            flat += list(l)
+            off[i + 1] = len(flat)
+
+        def opt(items):
+            arr = (C.c_char_p * max(1, n))()
+            for i, s_ in enumerate(items):
+                arr[i] = None if s_ is None else s_.encode("utf-8")
+            return arr
+        assert self.L.orc_bulk_add(self.h, n, _ptr(rows), _strs(ids), opt(locs), opt(zones), _ptr(off), _strs(flat)) == 0
 
     def set_active(self, idx: int, active: bool):
         assert self.L.orc_set_active(self.h, idx, int(active)) == 0

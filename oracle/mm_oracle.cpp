@@ -507,6 +507,7 @@ struct Fleet {
   }
   bool isFull(int64_t r) const { return po.isFull(r); }
   void instanceEvent(int type, int32_t idx, const JStr &key, IRp record, int64_t now);
+  void bulkAdd(const std::vector<Entry> &ents);
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -792,6 +793,59 @@ void Fleet::instanceEvent(int type, int32_t idx, const JStr &key, IRp record, in
   if ((size_t)idx >= byIdx.size()) { byIdx.resize(idx + 1); keyByIdx.resize(idx + 1); siActive.resize(idx + 1, 0); }
   keyByIdx[idx] = key;
   if (type == ENTRY_DELETED) byIdx[idx] = nullptr; else byIdx[idx] = record;
+}
+
+// Test-harness shortcut: the state that ENTRY_ADDED events for `ents` (fresh keys, empty fleet, type config already
+// set, refresh deferred) followed by a converged refresh produce, computed without the per-event O(N) rescans of
+// MM:1522-1542 and the per-event immutable-set rebuilds of TCM:489-505.  tests/test_host_logic.py checks it against the
+// event-driven path; it exists only so that 40k-65k instance fleets can be set up in seconds.
+void Fleet::bulkAdd(const std::vector<Entry> &ents) {
+  if (haveTc) {
+    std::map<std::string, Mtcp> newMap;
+    for (auto &te : tcm.typeConstraintsMap) {
+      auto m = std::make_shared<Mtc>(*te.second);
+      if (!m->requiredLabels.empty() && !m->allowedInstances) m->allowedInstances = IdSet();
+      for (const Entry &e : ents) {
+        if (e.rec->shuttingDown) continue;  // MM:1462-1464: never reaches TypeConstraintManager.instanceAdded
+        if (m->allowedInstances && instanceMatches(e.rec->labels, m->requiredLabels, true)) m->allowedInstances->insert(e.idx);
+        if (instanceMatches(e.rec->labels, m->preferredLabels, false)) {
+          if (!m->configuredPreferredInstances) m->configuredPreferredInstances = IdSet();
+          m->configuredPreferredInstances->insert(e.idx);
+        }
+      }
+      m->preferredInstances = m->configuredPreferredInstances;
+      newMap[te.first] = m;
+    }
+    tcm.typeConstraintsMap = newMap;
+  }
+  int32_t maxIdx = -1;
+  for (const Entry &e : ents) maxIdx = std::max(maxIdx, e.idx);
+  if ((size_t)(maxIdx + 1) > byIdx.size()) { byIdx.resize(maxIdx + 1); keyByIdx.resize(maxIdx + 1); siActive.resize(maxIdx + 1, 0); }
+  for (const Entry &e : ents) {
+    if (e.rec->shuttingDown) { keyByIdx[e.idx] = e.key; continue; }  // treated as a deletion of an absent key: no-op
+    Isst *ss = nullptr;
+    if (haveTc) {
+      ss = tcm.getInstanceSetStats(e.idx, e.rec->labels, tcm.typeConstraintsMap);
+      e.rec->prohibitedTypes = ss->prohibitedTypesSet;
+      ss->add(*e.rec);
+    }
+    clusterState.insert(e);
+    clusterStatsTracker.add(*e.rec);
+    byIdx[e.idx] = e.rec; keyByIdx[e.idx] = e.key;
+  }
+  clusterStatsTracker.resetLru();
+  for (auto &ps : tcm.ptsToInstanceSetStats) ps.second->resetLru();
+  for (const Entry &e : clusterState) {
+    clusterStatsTracker.addLru(e.rec->lruTime);
+    for (auto &ps : tcm.ptsToInstanceSetStats) ps.second->addLru(e.rec->lruTime);  // N10
+  }
+  for (auto &ps : tcm.ptsToInstanceSetStats) ps.second->update();
+  clusterStats = clusterStatsTracker.update();
+  if (haveTc) {
+    std::map<std::string, Mtcp> m = tcm.typeConstraintsMap;
+    tcm.refreshPerTypeInstanceSets(m);
+    tcm.typeConstraintsMap = m;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1140,6 +1194,29 @@ int orc_instance_event(orc_fleet *h, int type, int32_t idx, const orc_inst_t *re
   }
   f.instanceEvent(type, idx, utf8to16(id), r, now_ms);
   if (rec && (size_t)idx < f.siActive.size()) f.siActive[idx] = rec->active ? 1 : 0;
+  return 0;
+}
+
+int orc_bulk_add(orc_fleet *h, int32_t n, const orc_inst_t *recs, const char *const *ids, const char *const *locs,
+                 const char *const *zones, const int32_t *label_off, const char *const *labels) {
+  if (!h || n < 0 || !h->f.clusterState.empty()) return -1;
+  Fleet &f = h->f;
+  std::vector<Entry> ents;
+  for (int32_t i = 0; i < n; i++) {
+    auto r = std::make_shared<IR>();
+    const orc_inst_t *rec = &recs[i];
+    r->lruTime = rec->lru_time; r->count = rec->count; r->capacity = rec->capacity; r->used = rec->used;
+    r->lThreads = rec->l_threads; r->lInProg = rec->l_in_prog; r->rpm = rec->rpm; r->shuttingDown = rec->shutting_down != 0;
+    r->startTime = rec->start_time; r->vers = rec->vers;
+    if (locs[i]) { r->hasLoc = true; r->loc = utf8to16(locs[i]); }
+    if (zones[i]) { r->hasZone = true; r->zone = utf8to16(zones[i]); }
+    for (int k = label_off[i]; k < label_off[i + 1]; k++) r->labels.push_back(utf8to16(labels[k]));
+    std::sort(r->labels.begin(), r->labels.end(), [](const JStr &a, const JStr &b) { return jcompare(a, b) < 0; });
+    r->labelsIdentity = r->labels.empty() ? 0 : f.nextLabelsIdentity++;
+    ents.push_back(Entry{utf8to16(ids[i]), i, r});
+  }
+  f.bulkAdd(ents);
+  for (int32_t i = 0; i < n; i++) f.siActive[i] = recs[i].active ? 1 : 0;
   return 0;
 }
 

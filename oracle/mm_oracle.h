@@ -74,6 +74,10 @@ void orc_destroy(orc_fleet *);
 int orc_instance_event(orc_fleet *, int type, int32_t idx, const orc_inst_t *rec, const char *id,
                        const char *loc, const char *zone, const char *const *labels, int32_t n_labels,
                        int64_t now_ms);
+/* Test-harness shortcut for big fleets: same final state as n ENTRY_ADDED events (instance idx = position) on an empty
+ * fleet followed by orc_tc_converge(), without the per-event O(N) work (see Fleet::bulkAdd). locs/zones entries may be NULL. */
+int orc_bulk_add(orc_fleet *, int32_t n, const orc_inst_t *recs, const char *const *ids, const char *const *locs,
+                 const char *const *zones, const int32_t *label_off, const char *const *labels);
 /* litelinks siMap membership (MM:4778) for an instance that is in the table */
 int orc_set_active(orc_fleet *, int32_t idx, int32_t active);
 

@@ -9,16 +9,20 @@ from modelmesh_b200.synth import SynthDecisions, SynthFleet, load_into_fleet
 from oracle import binding as ob
 
 
-def oracle_from_synth(fl: SynthFleet) -> ob.OracleFleet:
+def oracle_from_synth(fl: SynthFleet, bulk=None) -> ob.OracleFleet:
     """Config first (as a pod does at start-up, MM:777), instances as ADDED events, then one converged refresh."""
     o = ob.OracleFleet(fl.min_space_units, fl.min_churn_age_ms, fl.default_model_size_units)
     o.types_set(fl.type_config)
-    o.tc_defer_refresh(fl.n_instances > 2000)  # same final state after tc_converge(), without the quadratic refreshes
-    for i in range(fl.n_instances):
-        o.instance_event(ob.ADDED, i, fl.inst_rows[i], fl.inst_ids[i], fl.inst_locs[i], fl.inst_zones[i],
-                         fl.inst_labels[i], fl.now_ms)
-    if fl.type_config is not None:
-        o.tc_converge()
+    if bulk is None:
+        bulk = fl.n_instances > 3000
+    if bulk:  # same final state (checked in test_host_logic.py) without the per-event O(N) work
+        o.bulk_add(fl.inst_rows, fl.inst_ids, fl.inst_locs, fl.inst_zones, fl.inst_labels)
+    else:
+        for i in range(fl.n_instances):
+            o.instance_event(ob.ADDED, i, fl.inst_rows[i], fl.inst_ids[i], fl.inst_locs[i], fl.inst_zones[i],
+                             fl.inst_labels[i], fl.now_ms)
+        if fl.type_config is not None:
+            o.tc_converge()
     o.set_replaced_replicasets(fl.replaced_replicasets)
     return o
 

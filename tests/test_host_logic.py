@@ -234,3 +234,24 @@ def test_admission_rules(oracle_lib):
     assert L_.orc_early_reject(200, 1000, 900, 5000, 4000) == 1                # no room and older than everything
     assert L_.orc_early_reject(200, 1000, 900, 5000, 6000) == 0
     assert L_.orc_early_reject(200, 1000, 900, 5000, 0) == 0                   # lastUsed 0 = "now"
+
+
+@pytest.mark.parametrize("config,ni,seed", [("C3", 600, 3), ("C5", 500, 5), ("MIX", 300, 2), ("MIX", 160, 9), ("C2", 400, 2)])
+def test_oracle_bulk_load_equals_event_driven(oracle_lib, config, ni, seed):
+    """orc_bulk_add is a set-up shortcut for big fleets; it must reach exactly the event-driven state."""
+    fl = make_fleet(config, 10, ni, seed)
+    a = oracle_from_synth(fl, bulk=False)
+    b = oracle_from_synth(fl, bulk=True)
+    assert np.array_equal(a.cluster_order(), b.cluster_order())
+    for k in ("total_capacity", "total_free", "global_lru", "instance_count", "model_copy_count"):
+        assert int(a.cluster_stats()[k]) == int(b.cluster_stats()[k])
+    for t in fl.type_names + ["zzz"]:
+        (a1, p1), (a2, p2) = a.type_sets(t, ni), b.type_sets(t, ni)
+        assert (a1 is None) == (a2 is None) and (p1 is None) == (p2 is None)
+        assert a1 is None or np.array_equal(a1, a2)
+        assert p1 is None or np.array_equal(p1, p2)
+    if fl.type_config is not None:
+        sa, ia = a.partition_stats()
+        sb, ib = b.partition_stats()
+        key = lambda s_: sorted((int(x["total_capacity"]), int(x["total_free"]), int(x["instance_count"]), int(x["model_copy_count"])) for x in s_ if x["instance_count"] > 0)
+        assert key(sa) == key(sb)
