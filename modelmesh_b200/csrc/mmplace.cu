@@ -15,6 +15,8 @@
 #include <atomic>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <memory>
 #include <mutex>
 #include <shared_mutex>
@@ -97,6 +99,131 @@ __global__ void __launch_bounds__(256) k_place(const SnapshotView s, const mmp_d
   }
 }
 
+// ---- TMA 1-D bulk copy + mbarrier helpers (cp.async.bulk: SASS UBLKCP) ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+// The scoring kernel, TMA-staged: one warp per decision as in k_place, but every warp owns a ring of K exclusion-row
+// buffers in shared memory that one elected lane keeps filled K decisions ahead with cp.async.bulk (a row is one
+// contiguous, 128-byte-aligned run of row_words*4 bytes), so K rows per warp are in flight from HBM while the current
+// decision is being resolved.  Decisions are taken in batches of 32: lane j prepares the context of decision j (its
+// dependent gathers: decision -> model row, rank_of[self] -> rows[self]) one batch ahead, so those latencies overlap
+// across lanes and with the previous batch.
+template <int V, int NJ, int K, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_place_ring(const SnapshotView s, const mmp_decision_in *__restrict__ in, int n,
+                                                          const FreshRow *__restrict__ fresh, int n_fresh,
+                                                          const int32_t *__restrict__ extra, mmp_decision_out *__restrict__ out,
+                                                          int64_t now, uint64_t seed, uint64_t id_base) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int RW = s.row_words;
+  const uint32_t row_bytes = (uint32_t)RW * 4u;
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t per_warp = ((size_t)K * row_bytes + 32 * sizeof(DecisionCtx) + (size_t)K * 8 + 127) / 128 * 128;
+  unsigned char *base = smem_raw + (size_t)wib * per_warp;
+  uint32_t *rows_s = reinterpret_cast<uint32_t *>(base);
+  DecisionCtx *ctx_s = reinterpret_cast<DecisionCtx *>(base + (size_t)K * row_bytes);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(base + (size_t)K * row_bytes + 32 * sizeof(DecisionCtx));
+  if (lane == 0) {
+    for (int k = 0; k < K; k++) mbar_init(&bars[k], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const int nb = (n + 31) >> 5;
+  const int gw = blockIdx.x * WARPS + wib, nw = gridDim.x * WARPS;
+  Coop32<V, NJ> co;
+  uint32_t f[V * NJ];
+  uint32_t use = 0;  // ring position of the next row to consume (warp-uniform)
+  DecisionCtx cn;    // this lane's context for the upcoming batch
+  auto prep = [&](int batch) {
+    const int i = batch * 32 + lane;
+    cn.slot = -2;  // absent
+    cn.d.model = 0;
+    if (batch < nb && i < n) {
+      const int4 *dp = reinterpret_cast<const int4 *>(in + i);
+      int4 a = __ldg(dp), b = __ldg(dp + 1);
+      mmp_decision_in d;
+      d.model = a.x; d.self = a.y; d.last_used = (int64_t)(((uint64_t)(uint32_t)a.w << 32) | (uint32_t)a.z);
+      d.flags = (uint32_t)b.x; d.fresh = b.y; d.extra_off = b.z; d.extra_n = b.w;
+      prepare_ctx(s, d, fresh, n_fresh, cn);
+    }
+  };
+  auto issue = [&](int model, uint32_t pos) {  // lane 0 only
+    const int m = (model >= 0 && model < s.n_models) ? model : 0;
+    uint64_t *bar = &bars[pos % K];
+    mbar_expect_tx(bar, row_bytes);
+    bulk_g2s(rows_s + (size_t)(pos % K) * RW, s.excl + (size_t)m * RW, row_bytes, bar);
+  };
+  int b = gw;
+  prep(b);
+  if (b < nb) {
+    ctx_s[lane] = cn;
+    __syncwarp();
+    const int count = min(32, n - b * 32);
+    if (lane == 0)
+      for (int t = 0; t < K && t < count; t++) issue(ctx_s[t].d.model, (uint32_t)t);
+  }
+  while (b < nb) {
+    const int bn = b + nw;
+    prep(bn);  // next batch's decisions + contexts: loads stay in flight while this batch is resolved
+    const int count = min(32, n - b * 32);
+    mmp_decision_out mine{MMP_TARGET_NONE, 0};
+    for (int j = 0; j < count; j++) {
+      const uint32_t slot = use % K, parity = (use / K) & 1u;
+      while (!mbar_try_wait(&bars[slot], parity)) {}
+      co.load_smem(f, rows_s + (size_t)slot * RW, RW);
+      // refill this ring slot with the row of the decision K positions ahead (this batch, else the next one)
+      const int t = j + K;
+      int nm = 0;
+      bool have = false;
+      if (t < count) { nm = ctx_s[t].d.model; have = true; }
+      else {
+        const int src = (t - count) & 31;
+        const int m2 = __shfl_sync(0xffffffffu, cn.d.model, src);
+        const int s2 = __shfl_sync(0xffffffffu, cn.slot, src);
+        if (t - count < 32 && s2 != -2) { nm = m2; have = true; }
+      }
+      __syncwarp();
+      if (lane == 0 && have) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(nm, use + K);
+      }
+      use++;
+      DecideOut o;
+      decide_ctx(s, ctx_s[j], extra, now, seed, id_base + (uint64_t)(b * 32 + j), co, f,
+                 [&](uint32_t *ff, const uint32_t *cand_row) { co.combine_cand(ff, cand_row, RW); }, o, nullptr);
+      if (lane == j) { mine.target = o.target; mine.n_candidates = o.n_candidates; }
+    }
+    if (lane < count) out[b * 32 + lane] = mine;
+    b = bn;
+    __syncwarp();
+    if (b < nb) ctx_s[lane] = cn;
+    __syncwarp();
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // device-side containers
 // ---------------------------------------------------------------------------------------------------------------
@@ -131,9 +258,15 @@ struct DeviceSnapshot {
 
 struct PlaceCtx {
   cudaStream_t stream = nullptr;
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  static constexpr int NPIPE = 3;
+  cudaStream_t pipe[NPIPE] = {nullptr, nullptr, nullptr};  // H2D / kernel / D2H of consecutive chunks overlap across these
+  cudaEvent_t e0 = nullptr, e1 = nullptr, ready = nullptr;
   DevBuf d_in, d_out, d_fresh, d_extra, d_trace, d_cand;
   std::vector<FreshRow> fresh_host;
+  // pinned, device-mapped scratch for tiny batches: the kernel reads the decisions and writes the results straight
+  // through PCIe, so a B = 1 call is one launch + one synchronise (no copy calls)
+  unsigned char *mapped = nullptr;
+  static constexpr size_t MAPPED_BYTES = 16384;
 };
 
 struct mmp_fleet {
@@ -150,6 +283,7 @@ struct mmp_fleet {
   std::mutex ctx_mu;
   std::vector<std::unique_ptr<PlaceCtx>> ctx_free;
   std::atomic<int64_t> launches{0};
+  bool use_ring = true;         // k_place_ring (TMA-staged) for untraced batches; MMP_PLACE_KERNEL=warp selects k_place
   // LRU store (plug point 3)
   DevBuf lru_ts, lru_seq, lru_weight, lru_model, lru_cap, lru_wsize, lru_count, lru_seqctr;
   int32_t lru_n = 0, lru_slots = 0;
@@ -179,11 +313,12 @@ static PlaceCtx *acquire_ctx(mmp_fleet *f) {
     }
   }
   auto *c = new PlaceCtx();
-  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreate(&c->e0) != cudaSuccess || cudaEventCreate(&c->e1) != cudaSuccess) {
-    delete c;
-    return nullptr;
-  }
+  bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreate(&c->e0) == cudaSuccess && cudaEventCreate(&c->e1) == cudaSuccess &&
+            cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming) == cudaSuccess &&
+            cudaHostAlloc((void **)&c->mapped, PlaceCtx::MAPPED_BYTES, cudaHostAllocMapped) == cudaSuccess;
+  for (int i = 0; ok && i < PlaceCtx::NPIPE; i++) ok = cudaStreamCreateWithFlags(&c->pipe[i], cudaStreamNonBlocking) == cudaSuccess;
+  if (!ok) { delete c; return nullptr; }
   return c;
 }
 static void release_ctx(mmp_fleet *f, PlaceCtx *c) {
@@ -194,6 +329,9 @@ static void destroy_ctx(PlaceCtx *c) {
   for (DevBuf *b : {&c->d_in, &c->d_out, &c->d_fresh, &c->d_extra, &c->d_trace, &c->d_cand}) b->release();
   if (c->e0) cudaEventDestroy(c->e0);
   if (c->e1) cudaEventDestroy(c->e1);
+  if (c->ready) cudaEventDestroy(c->ready);
+  if (c->mapped) cudaFreeHost(c->mapped);
+  for (int i = 0; i < PlaceCtx::NPIPE; i++) if (c->pipe[i]) cudaStreamDestroy(c->pipe[i]);
   if (c->stream) cudaStreamDestroy(c->stream);
 }
 
@@ -232,9 +370,46 @@ static cudaError_t launch_place_t(mmp_fleet *f, const PlaceArgs &a, cudaStream_t
   return cudaGetLastError();
 }
 
+static constexpr int RING_K = 4, RING_WARPS = 8;
+template <int V, int NJ>
+static cudaError_t launch_ring_t(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st) {
+  static int blocks_per_sm = 0;
+  const size_t per_warp = ((size_t)RING_K * a.s.row_words * 4 + 32 * sizeof(DecisionCtx) + (size_t)RING_K * 8 + 127) / 128 * 128;
+  const size_t smem = per_warp * RING_WARPS;
+  auto kern = k_place_ring<V, NJ, RING_K, RING_WARPS>;
+  if (!blocks_per_sm) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024));
+    if (e != cudaSuccess) return e;
+    int b = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, RING_WARPS * 32, smem);
+    if (e != cudaSuccess) return e;
+    blocks_per_sm = b > 0 ? b : 1;
+  }
+  int want = (a.n + 32 * RING_WARPS - 1) / (32 * RING_WARPS);
+  int grid = std::min(want, f->sm_count * blocks_per_sm);
+  if (grid < 1) grid = 1;
+  kern<<<grid, RING_WARPS * 32, smem, st>>>(a.s, a.in, a.n, a.fresh, a.n_fresh, a.extra, a.out, a.now, a.seed, a.id_base);
+  f->launches++;
+  return cudaGetLastError();
+}
+// the TMA-staged kernel needs the ring to fit in shared memory: rows up to 4 KiB (32k instances)
+static bool ring_supported(int rw) { return rw >= 32 && rw <= 1024; }
+static cudaError_t launch_ring(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st) {
+  const int rw = a.s.row_words;
+  if (rw <= 32) return launch_ring_t<1, 1>(f, a, st);
+  if (rw <= 64) return launch_ring_t<2, 1>(f, a, st);
+  if (rw <= 128) return launch_ring_t<4, 1>(f, a, st);
+  if (rw <= 256) return launch_ring_t<4, 2>(f, a, st);
+  if (rw <= 384) return launch_ring_t<4, 3>(f, a, st);
+  if (rw <= 512) return launch_ring_t<4, 4>(f, a, st);
+  if (rw <= 768) return launch_ring_t<4, 6>(f, a, st);
+  return launch_ring_t<4, 8>(f, a, st);
+}
+
 template <bool TRACE>
 static cudaError_t launch_place(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st) {
   const int rw = a.s.row_words;
+  if (!TRACE && f->use_ring && ring_supported(rw)) return launch_ring(f, a, st);
   if (rw <= 32) return launch_place_t<1, 1, TRACE>(f, a, st);
   if (rw <= 64) return launch_place_t<2, 1, TRACE>(f, a, st);
   if (rw <= 128) return launch_place_t<4, 1, TRACE>(f, a, st);
@@ -274,6 +449,7 @@ int32_t mmp_fleet_create(const mmp_config *cfg, mmp_fleet **out) {
   f->sm_count = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&f->commit_stream, cudaStreamNonBlocking));
   f->hs.init(*cfg);
+  if (const char *k = getenv("MMP_PLACE_KERNEL")) f->use_ring = std::string(k) != "warp";
   *out = f.release();
   return MMP_OK;
 }
@@ -410,20 +586,59 @@ static int32_t place_impl(mmp_fleet *f, const mmp_decision_in *in, int32_t n, co
   }
   const int RW = ds.view.row_words;
   cudaStream_t st = c->stream;
+  const bool traced = trace || cand_mask;
+  // ---- tiny batches: zero-copy through pinned mapped memory (one launch + one synchronise) ----
+  {
+    const size_t need = (size_t)n * (sizeof(mmp_decision_in) + sizeof(mmp_decision_out)) + (size_t)n_fresh * sizeof(FreshRow) + (size_t)n_extra * 4 + 64;
+    if (!traced && need <= PlaceCtx::MAPPED_BYTES) {
+      unsigned char *h = c->mapped, *dbase = nullptr;
+      CK(cudaHostGetDevicePointer((void **)&dbase, h, 0));
+      size_t o_in = 0, o_out = o_in + (size_t)n * sizeof(mmp_decision_in), o_fr = o_out + (size_t)n * sizeof(mmp_decision_out);
+      size_t o_ex = (o_fr + (size_t)n_fresh * sizeof(FreshRow) + 15) / 16 * 16;
+      memcpy(h + o_in, in, (size_t)n * sizeof(mmp_decision_in));
+      if (n_fresh) memcpy(h + o_fr, c->fresh_host.data(), (size_t)n_fresh * sizeof(FreshRow));
+      if (n_extra) memcpy(h + o_ex, extra, (size_t)n_extra * 4);
+      PlaceArgs a{ds.view, (const mmp_decision_in *)(dbase + o_in), n, (const FreshRow *)(dbase + o_fr), n_fresh,
+                  (const int32_t *)(dbase + o_ex), (mmp_decision_out *)(dbase + o_out), nullptr, nullptr, now_ms, seed, 0};
+      CK(launch_place<false>(f, a, st));
+      CK(cudaStreamSynchronize(st));
+      memcpy(out, h + o_out, (size_t)n * sizeof(mmp_decision_out));
+      return MMP_OK;
+    }
+  }
   CK(c->d_in.ensure((size_t)n * sizeof(mmp_decision_in)));
   CK(c->d_out.ensure((size_t)n * sizeof(mmp_decision_out)));
   CK(c->d_fresh.ensure((size_t)std::max(n_fresh, 1) * sizeof(FreshRow)));
   CK(c->d_extra.ensure((size_t)std::max(n_extra, 1) * 4));
   if (trace) CK(c->d_trace.ensure((size_t)n * sizeof(mmp_decision_trace)));
   if (cand_mask) CK(c->d_cand.ensure((size_t)n * 2 * RW * 4));
-  CK(cudaMemcpyAsync(c->d_in.p, in, (size_t)n * sizeof(mmp_decision_in), cudaMemcpyHostToDevice, st));
   if (n_fresh) CK(cudaMemcpyAsync(c->d_fresh.p, c->fresh_host.data(), (size_t)n_fresh * sizeof(FreshRow), cudaMemcpyHostToDevice, st));
   if (n_extra) CK(cudaMemcpyAsync(c->d_extra.p, extra, (size_t)n_extra * 4, cudaMemcpyHostToDevice, st));
+  // ---- large untraced batches: chunks flow through NPIPE streams so that the H2D copy of chunk i+1, the kernel of
+  // chunk i and the D2H copy of chunk i-1 overlap (with pinned caller buffers these are true DMA) ----
+  const int32_t CHUNK = 1 << 17;
+  if (!traced && n > CHUNK) {
+    CK(cudaEventRecord(c->ready, st));  // fresh/extra tables uploaded
+    for (int i = 0; i < PlaceCtx::NPIPE; i++) CK(cudaStreamWaitEvent(c->pipe[i], c->ready, 0));
+    int ci = 0;
+    for (int32_t lo = 0; lo < n; lo += CHUNK, ci++) {
+      const int32_t cnt = std::min(CHUNK, n - lo);
+      cudaStream_t ps = c->pipe[ci % PlaceCtx::NPIPE];
+      CK(cudaMemcpyAsync(c->d_in.as<mmp_decision_in>() + lo, in + lo, (size_t)cnt * sizeof(mmp_decision_in), cudaMemcpyHostToDevice, ps));
+      PlaceArgs a{ds.view, c->d_in.as<mmp_decision_in>() + lo, cnt, c->d_fresh.as<FreshRow>(), n_fresh, c->d_extra.as<int32_t>(),
+                  c->d_out.as<mmp_decision_out>() + lo, nullptr, nullptr, now_ms, seed, (uint64_t)lo};
+      CK(launch_place<false>(f, a, ps));
+      CK(cudaMemcpyAsync(out + lo, c->d_out.as<mmp_decision_out>() + lo, (size_t)cnt * sizeof(mmp_decision_out), cudaMemcpyDeviceToHost, ps));
+    }
+    for (int i = 0; i < PlaceCtx::NPIPE; i++) CK(cudaStreamSynchronize(c->pipe[i]));
+    return MMP_OK;
+  }
+  CK(cudaMemcpyAsync(c->d_in.p, in, (size_t)n * sizeof(mmp_decision_in), cudaMemcpyHostToDevice, st));
   if (cand_mask) CK(cudaMemsetAsync(c->d_cand.p, 0, (size_t)n * 2 * RW * 4, st));
   PlaceArgs a{ds.view, c->d_in.as<mmp_decision_in>(), n, c->d_fresh.as<FreshRow>(), n_fresh, c->d_extra.as<int32_t>(),
               c->d_out.as<mmp_decision_out>(), trace ? c->d_trace.as<mmp_decision_trace>() : nullptr,
               cand_mask ? c->d_cand.as<uint32_t>() : nullptr, now_ms, seed, 0};
-  if (trace || cand_mask) CK(launch_place<true>(f, a, st)); else CK(launch_place<false>(f, a, st));
+  if (traced) CK(launch_place<true>(f, a, st)); else CK(launch_place<false>(f, a, st));
   CK(cudaMemcpyAsync(out, c->d_out.p, (size_t)n * sizeof(mmp_decision_out), cudaMemcpyDeviceToHost, st));
   if (trace) CK(cudaMemcpyAsync(trace, c->d_trace.p, (size_t)n * sizeof(mmp_decision_trace), cudaMemcpyDeviceToHost, st));
   if (cand_mask) CK(cudaMemcpyAsync(cand_mask, c->d_cand.p, (size_t)n * 2 * RW * 4, cudaMemcpyDeviceToHost, st));

@@ -212,6 +212,44 @@ struct Coop32 {
       }
     }
   }
+  // f = raw words of a row staged in shared memory (conflict-free: consecutive lanes read consecutive vectors)
+  MMP_D void load_smem(uint32_t *f, const uint32_t *row_s, int row_words) const {
+    const int nvec = row_words / V_;
+#pragma unroll
+    for (int j = 0; j < NJ_; j++) {
+      int q = j * 32 + lane_;
+      if (q < nvec) {
+        if constexpr (V_ == 4) {
+          uint4 e = reinterpret_cast<const uint4 *>(row_s)[q];
+          f[j * 4 + 0] = e.x; f[j * 4 + 1] = e.y; f[j * 4 + 2] = e.z; f[j * 4 + 3] = e.w;
+        } else {
+#pragma unroll
+          for (int v = 0; v < V_; v++) f[j * V_ + v] = row_s[q * V_ + v];
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < V_; v++) f[j * V_ + v] = 0;
+      }
+    }
+  }
+  // f = cand & ~f  (f pre-filled with the exclusion words)
+  MMP_D void combine_cand(uint32_t *f, const uint32_t *cand_row, int row_words) const {
+    const int nvec = row_words / V_;
+#pragma unroll
+    for (int j = 0; j < NJ_; j++) {
+      int q = j * 32 + lane_;
+      if (q < nvec) {
+        if constexpr (V_ == 4) {
+          uint4 c = __ldg(reinterpret_cast<const uint4 *>(cand_row) + q);
+          f[j * 4 + 0] = c.x & ~f[j * 4 + 0]; f[j * 4 + 1] = c.y & ~f[j * 4 + 1];
+          f[j * 4 + 2] = c.z & ~f[j * 4 + 2]; f[j * 4 + 3] = c.w & ~f[j * 4 + 3];
+        } else {
+#pragma unroll
+          for (int v = 0; v < V_; v++) f[j * V_ + v] = __ldg(cand_row + q * V_ + v) & ~f[j * V_ + v];
+        }
+      }
+    }
+  }
 };
 #endif
 
@@ -348,30 +386,50 @@ struct RpmFilter {
   }
 };
 
-// One getNext.  f is the caller-provided register/stack array of C::NW_CAP words.
+// Everything about one decision that does not need its bitmap row (72 bytes).  k_place_ring lets lane j prepare the
+// context of decision j of a 32-decision batch (the dependent gathers overlap across lanes) and stages it in shared memory.
+struct DecisionCtx {
+  mmp_decision_in d;
+  int64_t last_used;
+  FreshRow fr;         // the caller's fresh record (MM:5369), or its published row with rpm 0 (N7)
+  int32_t self_rank;
+  int32_t slot;        // type-constraint mask slot, -1 = malformed decision
+};
+
+MMP_HD void prepare_ctx(const SnapshotView &s, const mmp_decision_in &d, const FreshRow *fresh_tab, int32_t n_fresh,
+                        DecisionCtx &c) {
+  c.d = d; c.slot = -1; c.self_rank = -1; c.last_used = 0;
+  c.fr.lru = 0; c.fr.rem = 0; c.fr.count = 0; c.fr.rpm = 0;
+  if (d.model < 0 || d.model >= s.n_models || d.self < 0 || d.self >= s.max_instances) return;
+  const mmp_model_row mr = s.models[d.model];
+  const int tid = mr.type_id < s.n_type_ids ? mr.type_id : 0;
+  c.last_used = (d.flags & MMP_DF_MODEL_LAST_USED) ? mr.last_used : d.last_used;
+  c.self_rank = s.rank_of[d.self];
+  if (d.fresh >= 0 && d.fresh < n_fresh) c.fr = fresh_tab[d.fresh];
+  else if (c.self_rank >= 0) { const RankRow sr = s.rows[c.self_rank]; c.fr.lru = sr.lru; c.fr.rem = sr.rem; c.fr.count = sr.count; c.fr.rpm = 0; }
+  else return;
+  c.slot = s.type_slot[tid];
+}
+
+// One getNext.  f is the caller-provided register/stack array of C::NW_CAP words; load_row(f, cand_row) must fill it
+// with cand_row & ~(the decision's exclusion row).
 // cand_rows (optional): [2][row_words] receives the candidate mask (other than best) and the survivor mask.
-template <class C>
-MMP_HD void decide(const SnapshotView &s, const mmp_decision_in &d, const FreshRow *fresh_tab, int32_t n_fresh,
-                   const int32_t *extra, int64_t now, uint64_t seed, uint64_t decision_id, const C &co, uint32_t *f,
-                   DecideOut &o, uint32_t *cand_rows) {
+template <class C, class LOADER>
+MMP_HD void decide_ctx(const SnapshotView &s, const DecisionCtx &c, const int32_t *extra, int64_t now, uint64_t seed,
+                       uint64_t decision_id, const C &co, uint32_t *f, LOADER &&load_row, DecideOut &o, uint32_t *cand_rows) {
   o.target = MMP_TARGET_NONE; o.n_candidates = 0; o.best = -1; o.n_remaining = 0; o.pick_index = 0; o.flags = 0;
   o.cut_rank = (int32_t)NONE_RANK; o.best_rank = -1;
   const int RW = s.row_words;
-  if (d.model < 0 || d.model >= s.n_models || d.self < 0 || d.self >= s.max_instances) { o.target = TARGET_INVALID; return; }
-  const mmp_model_row mr = s.models[d.model];
-  const int tid = mr.type_id < s.n_type_ids ? mr.type_id : 0;
-  const int slot = s.type_slot[tid];
-  const int64_t last_used = (d.flags & MMP_DF_MODEL_LAST_USED) ? mr.last_used : d.last_used;
+  if (c.slot < 0) { o.target = TARGET_INVALID; return; }
+  const mmp_decision_in &d = c.d;
+  const int slot = c.slot;
+  const int64_t last_used = c.last_used;
   const bool favour_self = (d.flags & MMP_DF_FAVOUR_SELF) != 0;
-  const int32_t self_rank = s.rank_of[d.self];
-
-  FreshRow fr;
-  if (d.fresh >= 0 && d.fresh < n_fresh) fr = fresh_tab[d.fresh];
-  else if (self_rank >= 0) { const RankRow sr = s.rows[self_rank]; fr.lru = sr.lru; fr.rem = sr.rem; fr.count = sr.count; fr.rpm = 0; }  // N7
-  else { o.target = TARGET_INVALID; return; }
+  const int32_t self_rank = c.self_rank;
+  const FreshRow fr = c.fr;
 
   // ---- filter (MM:4760-4771) ----
-  co.load_andnot(f, s.cand + (size_t)slot * RW, s.excl + (size_t)d.model * RW, RW);
+  load_row(f, s.cand + (size_t)slot * RW);
   for (int e = 0; e < d.extra_n && e < 16; e++) {
     int32_t x = extra[d.extra_off + e];
     if (x >= 0 && x < s.max_instances) { int32_t r = s.rank_of[x]; if (r >= 0) clear_bit(co, f, (uint32_t)r); }
@@ -531,6 +589,18 @@ MMP_HD void decide(const SnapshotView &s, const mmp_decision_in &d, const FreshR
   else { if (keep_best) kth--; chosen_rank = select_kth(co, f, kth); }
   const int32_t cidx = chosen_rank == best_rank ? best_idx : s.rows[chosen_rank].idx;
   o.target = (!favour_self && cidx == d.self) ? MMP_TARGET_SELF : cidx;
+}
+
+// Convenience form: context prepared inline, exclusion row read from global memory.
+template <class C>
+MMP_HD void decide(const SnapshotView &s, const mmp_decision_in &d, const FreshRow *fresh_tab, int32_t n_fresh,
+                   const int32_t *extra, int64_t now, uint64_t seed, uint64_t decision_id, const C &co, uint32_t *f,
+                   DecideOut &o, uint32_t *cand_rows) {
+  DecisionCtx c;
+  prepare_ctx(s, d, fresh_tab, n_fresh, c);
+  const uint32_t *erow = s.excl + (size_t)(c.slot >= 0 ? d.model : 0) * s.row_words;
+  decide_ctx(s, c, extra, now, seed, decision_id, co, f,
+             [&](uint32_t *ff, const uint32_t *cand_row) { co.load_andnot(ff, cand_row, erow, s.row_words); }, o, cand_rows);
 }
 
 }  // namespace mmp

@@ -102,6 +102,9 @@ def compare_decisions(fl: SynthFleet, sd: SynthDecisions, oracle: ob.OracleFleet
     out, tr, cm = solver.place_batch(sd.dec, fl.now_ms, seed, fresh=fresh, extra=extra, trace=True, masks=True)
     order = solver.cluster_order()
     n = len(sd.dec)
+    # the untraced entry point runs the production kernel (k_place_ring on the GPU): same answers
+    out_fast = solver.place_batch(sd.dec, fl.now_ms, seed, fresh=fresh, extra=extra)
+    assert np.array_equal(out_fast, out), _first_diff(out_fast["target"], out["target"], sd, ores, out_fast, tr)
     assert np.array_equal(out["target"], ores["target"]), _first_diff(out["target"], ores["target"], sd, ores, out, tr)
     assert np.array_equal(out["n_candidates"], ores["n_candidates"]), _first_diff(out["n_candidates"], ores["n_candidates"], sd, ores, out, tr)
     has = ores["n_candidates"] > 0
