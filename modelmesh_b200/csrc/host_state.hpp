@@ -87,6 +87,7 @@ struct HostSnapshot {
   std::vector<RankRow> rows;          // [n_ranks]
   std::vector<int32_t> rank_of;       // [max_instances]
   std::vector<uint32_t> cand;         // [n_slots][row_words]
+  std::vector<uint32_t> candx;        // [n_slots][row_words] cand & ~rs
   std::vector<uint32_t> pref;         // [n_slots][row_words]
   std::vector<uint8_t> has_pref;      // [n_slots]
   std::vector<uint8_t> allowed_null;  // [n_slots] (introspection only)
@@ -172,7 +173,15 @@ class HostState {
     dirty_models = true;
     return MMP_OK;
   }
-  int32_t row_words() const { return ((cfg.max_instances + 31) / 32 + 31) / 32 * 32; }  // multiple of 32 words = 128 B
+  // Words per bitmap row = 32 lanes x NWL words per lane, NWL from the set the kernel is instantiated for
+  // (row stride is a multiple of 128 B; 10 000 instances -> NWL 10 -> 320 words = 1 280 B, no padding words).
+  static int32_t words_per_lane(int32_t max_instances) {
+    static const int32_t sup[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16, 20, 24, 32, 48, 64};
+    int32_t need = ((max_instances + 31) / 32 + 31) / 32;
+    for (int32_t v : sup) if (v >= need) return v;
+    return 64;
+  }
+  int32_t row_words() const { return 32 * words_per_lane(cfg.max_instances); }
 
   int32_t set_types_json(const char *json);  // defined after TcJson
 
@@ -347,6 +356,9 @@ class HostState {
 
     // --- type-constraint set algebra (converged state of TCM.refreshPerTypeInstanceSets, TCM:680-747) ---
     build_type_masks(s, live);
+    s.candx = s.cand;
+    for (int32_t sl = 0; sl < s.n_slots; sl++)
+      for (int32_t w = 0; w < RW; w++) s.candx[(size_t)sl * RW + w] &= ~s.rs[w];
     return nullptr;
   }
 

@@ -4,11 +4,12 @@
 //   excl      [n_models][row_words] u32   model x instance exclusion bitmap (loaded ∪ failed, MR:69,73), bit = RANK of
 //                                         the instance under PLACEMENT_ORDER; row stride is a multiple of 128 B
 //   cand/pref [n_slots][row_words]  u32   per type-constraint slot: allowed ∧ active / preferred instances (TCM:242-251)
-//   rs, full  [row_words]           u32   likely-replaced replicaset members (MM:4769) / isFull instances (MM:4640)
+//   candx     [n_slots][row_words]  u32   cand minus likely-replaced replicaset members (MM:4769-4770)
+//   full      [row_words]           u32   isFull instances (MM:4640)
 //   rows      [n_ranks] RankRow 32 B      per-rank instance columns the walk reads (lru, remaining, count, rpm, idx)
 //   csum/lsum [row_words]                 per-32-rank min/max of count / lruTime (threshold searches skip whole words)
 //   rank_of   [max_instances] i32, models [n_models] mmp_model_row 24 B, type_slot [n_type_ids] u16
-// Kernels: k_build_bitmap / k_build_bitmap_ovf (commit), k_place<V,NJ,TRACE> (one warp per decision, the hot path),
+// Kernels: k_build_bitmap / k_build_bitmap_ovf (commit), k_place<NWL,K,WARPS> (one warp per decision, TMA-staged rows),
 //          k_stats, k_reaper_*, k_lru_apply (see below).
 #include <cuda_runtime.h>
 
@@ -66,39 +67,6 @@ __global__ void k_build_bitmap_ovf(uint32_t *__restrict__ excl, const int2 *__re
   if (r >= 0) atomicOr(&excl[(size_t)p.x * row_words + (r >> 5)], 1u << (r & 31));
 }
 
-// The scoring kernel: one warp per decision, persistent grid-stride loop.  Each lane keeps NJ x V words of the
-// decision's exclusion row in registers (V = 4: 128-bit loads, a warp-load covers 512 contiguous bytes).
-template <int V, int NJ, bool TRACE>
-__global__ void __launch_bounds__(256) k_place(const SnapshotView s, const mmp_decision_in *__restrict__ in, int n,
-                                               const FreshRow *__restrict__ fresh, int n_fresh,
-                                               const int32_t *__restrict__ extra, mmp_decision_out *__restrict__ out,
-                                               mmp_decision_trace *__restrict__ tr, uint32_t *__restrict__ cand,
-                                               int64_t now, uint64_t seed, uint64_t id_base) {
-  Coop32<V, NJ> co;
-  const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
-  uint32_t f[V * NJ];
-  for (int i = warp; i < n; i += nwarps) {
-    const int4 *dp = reinterpret_cast<const int4 *>(in + i);
-    int4 a = __ldg(dp), b = __ldg(dp + 1);
-    mmp_decision_in d;
-    d.model = a.x; d.self = a.y; d.last_used = (int64_t)(((uint64_t)(uint32_t)a.w << 32) | (uint32_t)a.z);
-    d.flags = (uint32_t)b.x; d.fresh = b.y; d.extra_off = b.z; d.extra_n = b.w;
-    DecideOut o;
-    decide(s, d, fresh, n_fresh, extra, now, seed, id_base + (uint64_t)i, co, f, o,
-           (TRACE && cand) ? cand + (size_t)i * 2 * s.row_words : nullptr);
-    if (co.lane() == 0) {
-      out[i] = mmp_decision_out{o.target, o.n_candidates};
-      if (TRACE && tr) {
-        mmp_decision_trace t;
-        t.best = o.best; t.n_remaining = o.n_remaining; t.pick_index = o.pick_index; t.flags = o.flags;
-        t.cut_rank = o.cut_rank; t.best_rank = o.best_rank; t.reserved[0] = t.reserved[1] = 0;
-        tr[i] = t;
-      }
-    }
-  }
-}
-
 // ---- TMA 1-D bulk copy + mbarrier helpers (cp.async.bulk: SASS UBLKCP) ----
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
@@ -126,22 +94,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
   return ok != 0;
 }
 
-// The scoring kernel, TMA-staged: one warp per decision as in k_place, but every warp owns a ring of K exclusion-row
-// buffers in shared memory that one elected lane keeps filled K decisions ahead with cp.async.bulk (a row is one
-// contiguous, 128-byte-aligned run of row_words*4 bytes), so K rows per warp are in flight from HBM while the current
-// decision is being resolved.  Decisions are taken in batches of 32: lane j prepares the context of decision j (its
-// dependent gathers: decision -> model row, rank_of[self] -> rows[self]) one batch ahead, so those latencies overlap
-// across lanes and with the previous batch.
-template <int V, int NJ, int K, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) k_place_ring(const SnapshotView s, const mmp_decision_in *__restrict__ in, int n,
-                                                          const FreshRow *__restrict__ fresh, int n_fresh,
-                                                          const int32_t *__restrict__ extra, mmp_decision_out *__restrict__ out,
-                                                          int64_t now, uint64_t seed, uint64_t id_base) {
+// The scoring kernel (TMA-staged).  One warp per decision; every warp owns a ring of K exclusion-row buffers in shared
+// memory that one elected lane keeps filled ahead with cp.async.bulk (a row is one contiguous, 128-byte-aligned run of
+// row_words*4 bytes), so K-1 rows per warp are in flight from HBM while the current decision is resolved out of the
+// K-th.  Lane l then owns words [l*NWL, (l+1)*NWL) of the row in registers (mmp::Coop32).  Decisions are taken in
+// batches of 32: lane j prepares the context of decision j (its dependent gathers: decision -> model row,
+// rank_of[self] -> rows[self]) one batch ahead, so those latencies overlap across lanes and with the previous batch.
+template <int NWL, int K, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_place(const SnapshotView s, const mmp_decision_in *__restrict__ in, int n,
+                                                     const FreshRow *__restrict__ fresh, int n_fresh,
+                                                     const int32_t *__restrict__ extra, mmp_decision_out *__restrict__ out,
+                                                     mmp_decision_trace *__restrict__ tr, uint32_t *__restrict__ cand,
+                                                     int64_t now, uint64_t seed, uint64_t id_base) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int RW = s.row_words;
-  const uint32_t row_bytes = (uint32_t)RW * 4u;
+  constexpr int RW = NWL * 32;
+  constexpr uint32_t row_bytes = (uint32_t)RW * 4u;
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t per_warp = ((size_t)K * row_bytes + 32 * sizeof(DecisionCtx) + (size_t)K * 8 + 127) / 128 * 128;
+  constexpr size_t per_warp = ((size_t)K * row_bytes + 32 * sizeof(DecisionCtx) + (size_t)K * 8 + 127) / 128 * 128;
   unsigned char *base = smem_raw + (size_t)wib * per_warp;
   uint32_t *rows_s = reinterpret_cast<uint32_t *>(base);
   DecisionCtx *ctx_s = reinterpret_cast<DecisionCtx *>(base + (size_t)K * row_bytes);
@@ -153,8 +122,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_place_ring(const SnapshotView s,
   __syncwarp();
   const int nb = (n + 31) >> 5;
   const int gw = blockIdx.x * WARPS + wib, nw = gridDim.x * WARPS;
-  Coop32<V, NJ> co;
-  uint32_t f[V * NJ];
+  Coop32<NWL> co;
+  uint32_t f[NWL];
   uint32_t use = 0;  // ring position of the next row to consume (warp-uniform)
   DecisionCtx cn;    // this lane's context for the upcoming batch
   auto prep = [&](int batch) {
@@ -193,8 +162,18 @@ __global__ void __launch_bounds__(WARPS * 32) k_place_ring(const SnapshotView s,
     for (int j = 0; j < count; j++) {
       const uint32_t slot = use % K, parity = (use / K) & 1u;
       while (!mbar_try_wait(&bars[slot], parity)) {}
-      co.load_smem(f, rows_s + (size_t)slot * RW, RW);
-      // refill this ring slot with the row of the decision K positions ahead (this batch, else the next one)
+      const uint32_t *erow = rows_s + (size_t)slot * RW;
+      const int gi = b * 32 + j;
+      DecideOut o;
+      decide_ctx(s, ctx_s[j], erow, extra, now, seed, id_base + (uint64_t)gi, co, f, o, cand ? cand + (size_t)gi * 2 * RW : nullptr);
+      if (lane == j) { mine.target = o.target; mine.n_candidates = o.n_candidates; }
+      if (tr && lane == 0) {
+        mmp_decision_trace t;
+        t.best = o.best; t.n_remaining = o.n_remaining; t.pick_index = o.pick_index; t.flags = o.flags;
+        t.cut_rank = o.cut_rank; t.best_rank = o.best_rank; t.reserved[0] = t.reserved[1] = 0;
+        tr[gi] = t;
+      }
+      // the row has been consumed: refill this ring slot with the row of the decision K positions ahead
       const int t = j + K;
       int nm = 0;
       bool have = false;
@@ -211,10 +190,6 @@ __global__ void __launch_bounds__(WARPS * 32) k_place_ring(const SnapshotView s,
         issue(nm, use + K);
       }
       use++;
-      DecideOut o;
-      decide_ctx(s, ctx_s[j], extra, now, seed, id_base + (uint64_t)(b * 32 + j), co, f,
-                 [&](uint32_t *ff, const uint32_t *cand_row) { co.combine_cand(ff, cand_row, RW); }, o, nullptr);
-      if (lane == j) { mine.target = o.target; mine.n_candidates = o.n_candidates; }
     }
     if (lane < count) out[b * 32 + lane] = mine;
     b = bn;
@@ -244,13 +219,13 @@ struct DevBuf {
 };
 
 struct DeviceSnapshot {
-  DevBuf excl, cand, pref, has_pref, type_slot, rs, full, rows, rank_of, csum, lsum, models;
+  DevBuf excl, cand, candx, pref, has_pref, type_slot, full, rows, rank_of, csum, lsum, models;
   DevBuf cap_col, lthreads_col, linprog_col, part_of_rank;
   SnapshotView view{};
   HostSnapshot host;  // kept for introspection and the small host-side parts of stats / reaper
   int32_t n_models = 0;
   void release() {
-    for (DevBuf *b : {&excl, &cand, &pref, &has_pref, &type_slot, &rs, &full, &rows, &rank_of, &csum, &lsum, &models,
+    for (DevBuf *b : {&excl, &cand, &candx, &pref, &has_pref, &type_slot, &full, &rows, &rank_of, &csum, &lsum, &models,
                       &cap_col, &lthreads_col, &linprog_col, &part_of_rank})
       b->release();
   }
@@ -283,7 +258,6 @@ struct mmp_fleet {
   std::mutex ctx_mu;
   std::vector<std::unique_ptr<PlaceCtx>> ctx_free;
   std::atomic<int64_t> launches{0};
-  bool use_ring = true;         // k_place_ring (TMA-staged) for untraced batches; MMP_PLACE_KERNEL=warp selects k_place
   // LRU store (plug point 3)
   DevBuf lru_ts, lru_seq, lru_weight, lru_model, lru_cap, lru_wsize, lru_count, lru_seqctr;
   int32_t lru_n = 0, lru_slots = 0;
@@ -352,74 +326,48 @@ struct PlaceArgs {
   uint64_t seed, id_base;
 };
 
-template <int V, int NJ, bool TRACE>
+template <int NWL, int K, int WARPS>
 static cudaError_t launch_place_t(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st) {
   static int blocks_per_sm = 0;
+  constexpr size_t per_warp = ((size_t)K * NWL * 128 + 32 * sizeof(DecisionCtx) + (size_t)K * 8 + 127) / 128 * 128;
+  constexpr size_t smem = per_warp * WARPS;
+  auto kern = k_place<NWL, K, WARPS>;
   if (!blocks_per_sm) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     int b = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_place<V, NJ, TRACE>, 256, 0);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, WARPS * 32, smem);
     if (e != cudaSuccess) return e;
     blocks_per_sm = b > 0 ? b : 1;
   }
-  int want = (a.n + 7) / 8;
+  int want = (a.n + 32 * WARPS - 1) / (32 * WARPS);
   int grid = std::min(want, f->sm_count * blocks_per_sm);
   if (grid < 1) grid = 1;
-  k_place<V, NJ, TRACE><<<grid, 256, 0, st>>>(a.s, a.in, a.n, a.fresh, a.n_fresh, a.extra, a.out, a.tr, a.cand, a.now,
-                                              a.seed, a.id_base);
+  kern<<<grid, WARPS * 32, smem, st>>>(a.s, a.in, a.n, a.fresh, a.n_fresh, a.extra, a.out, a.tr, a.cand, a.now, a.seed, a.id_base);
   f->launches++;
   return cudaGetLastError();
 }
 
-static constexpr int RING_K = 4, RING_WARPS = 8;
-template <int V, int NJ>
-static cudaError_t launch_ring_t(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st) {
-  static int blocks_per_sm = 0;
-  const size_t per_warp = ((size_t)RING_K * a.s.row_words * 4 + 32 * sizeof(DecisionCtx) + (size_t)RING_K * 8 + 127) / 128 * 128;
-  const size_t smem = per_warp * RING_WARPS;
-  auto kern = k_place_ring<V, NJ, RING_K, RING_WARPS>;
-  if (!blocks_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024));
-    if (e != cudaSuccess) return e;
-    int b = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, RING_WARPS * 32, smem);
-    if (e != cudaSuccess) return e;
-    blocks_per_sm = b > 0 ? b : 1;
-  }
-  int want = (a.n + 32 * RING_WARPS - 1) / (32 * RING_WARPS);
-  int grid = std::min(want, f->sm_count * blocks_per_sm);
-  if (grid < 1) grid = 1;
-  kern<<<grid, RING_WARPS * 32, smem, st>>>(a.s, a.in, a.n, a.fresh, a.n_fresh, a.extra, a.out, a.now, a.seed, a.id_base);
-  f->launches++;
-  return cudaGetLastError();
-}
-// the TMA-staged kernel needs the ring to fit in shared memory: rows up to 4 KiB (32k instances)
-static bool ring_supported(int rw) { return rw >= 32 && rw <= 1024; }
-static cudaError_t launch_ring(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st) {
-  const int rw = a.s.row_words;
-  if (rw <= 32) return launch_ring_t<1, 1>(f, a, st);
-  if (rw <= 64) return launch_ring_t<2, 1>(f, a, st);
-  if (rw <= 128) return launch_ring_t<4, 1>(f, a, st);
-  if (rw <= 256) return launch_ring_t<4, 2>(f, a, st);
-  if (rw <= 384) return launch_ring_t<4, 3>(f, a, st);
-  if (rw <= 512) return launch_ring_t<4, 4>(f, a, st);
-  if (rw <= 768) return launch_ring_t<4, 6>(f, a, st);
-  return launch_ring_t<4, 8>(f, a, st);
-}
-
-template <bool TRACE>
+// dispatch on words per lane (row_words / 32); HostState::words_per_lane picks from the same set
 static cudaError_t launch_place(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st) {
-  const int rw = a.s.row_words;
-  if (!TRACE && f->use_ring && ring_supported(rw)) return launch_ring(f, a, st);
-  if (rw <= 32) return launch_place_t<1, 1, TRACE>(f, a, st);
-  if (rw <= 64) return launch_place_t<2, 1, TRACE>(f, a, st);
-  if (rw <= 128) return launch_place_t<4, 1, TRACE>(f, a, st);
-  if (rw <= 256) return launch_place_t<4, 2, TRACE>(f, a, st);
-  if (rw <= 384) return launch_place_t<4, 3, TRACE>(f, a, st);
-  if (rw <= 512) return launch_place_t<4, 4, TRACE>(f, a, st);
-  if (rw <= 768) return launch_place_t<4, 6, TRACE>(f, a, st);
-  if (rw <= 1024) return launch_place_t<4, 8, TRACE>(f, a, st);
-  if (rw <= 1536) return launch_place_t<4, 12, TRACE>(f, a, st);
-  return launch_place_t<4, 16, TRACE>(f, a, st);
+  switch (a.s.row_words / 32) {
+    case 1: return launch_place_t<1, 4, 8>(f, a, st);
+    case 2: return launch_place_t<2, 4, 8>(f, a, st);
+    case 3: return launch_place_t<3, 4, 8>(f, a, st);
+    case 4: return launch_place_t<4, 4, 8>(f, a, st);
+    case 5: return launch_place_t<5, 4, 8>(f, a, st);
+    case 6: return launch_place_t<6, 4, 8>(f, a, st);
+    case 8: return launch_place_t<8, 4, 8>(f, a, st);
+    case 10: return launch_place_t<10, 4, 8>(f, a, st);
+    case 12: return launch_place_t<12, 4, 8>(f, a, st);
+    case 16: return launch_place_t<16, 4, 8>(f, a, st);
+    case 20: return launch_place_t<20, 3, 8>(f, a, st);
+    case 24: return launch_place_t<24, 3, 8>(f, a, st);
+    case 32: return launch_place_t<32, 3, 8>(f, a, st);
+    case 48: return launch_place_t<48, 2, 4>(f, a, st);
+    case 64: return launch_place_t<64, 2, 4>(f, a, st);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -449,7 +397,6 @@ int32_t mmp_fleet_create(const mmp_config *cfg, mmp_fleet **out) {
   f->sm_count = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&f->commit_stream, cudaStreamNonBlocking));
   f->hs.init(*cfg);
-  if (const char *k = getenv("MMP_PLACE_KERNEL")) f->use_ring = std::string(k) != "warp";
   *out = f.release();
   return MMP_OK;
 }
@@ -518,7 +465,7 @@ int32_t mmp_fleet_commit(mmp_fleet *f) {
   const int32_t nm = f->hs.n_models_used;
   ds.n_models = nm;
   CK(upload_vec(ds.cand, h.cand, st)); CK(upload_vec(ds.pref, h.pref, st)); CK(upload_vec(ds.has_pref, h.has_pref, st));
-  CK(upload_vec(ds.type_slot, h.type_slot, st)); CK(upload_vec(ds.rs, h.rs, st)); CK(upload_vec(ds.full, h.full, st));
+  CK(upload_vec(ds.type_slot, h.type_slot, st)); CK(upload_vec(ds.candx, h.candx, st)); CK(upload_vec(ds.full, h.full, st));
   CK(upload_vec(ds.rows, h.rows, st)); CK(upload_vec(ds.rank_of, h.rank_of, st)); CK(upload_vec(ds.csum, h.csum, st));
   CK(upload_vec(ds.lsum, h.lsum, st)); CK(upload_vec(ds.cap_col, h.cap_col, st));
   CK(upload_vec(ds.lthreads_col, h.lthreads_col, st)); CK(upload_vec(ds.linprog_col, h.linprog_col, st));
@@ -551,7 +498,7 @@ int32_t mmp_fleet_commit(mmp_fleet *f) {
   v.n_ranks = h.n_ranks; v.row_words = RW; v.n_models = nm; v.max_instances = f->hs.cfg.max_instances;
   v.any_rs = h.any_rs; v.n_type_ids = (int32_t)h.type_slot.size(); v.min_space = f->hs.cfg.min_space_units;
   v.excl = ds.excl.as<uint32_t>(); v.cand = ds.cand.as<uint32_t>(); v.pref = ds.pref.as<uint32_t>();
-  v.has_pref = ds.has_pref.as<uint8_t>(); v.type_slot = ds.type_slot.as<uint16_t>(); v.rs = ds.rs.as<uint32_t>();
+  v.has_pref = ds.has_pref.as<uint8_t>(); v.type_slot = ds.type_slot.as<uint16_t>(); v.candx = ds.candx.as<uint32_t>();
   v.full = ds.full.as<uint32_t>(); v.rows = ds.rows.as<RankRow>(); v.rank_of = ds.rank_of.as<int32_t>();
   v.csum = ds.csum.as<WordSumI>(); v.lsum = ds.lsum.as<WordSumL>(); v.models = ds.models.as<mmp_model_row>();
   {
@@ -600,7 +547,7 @@ static int32_t place_impl(mmp_fleet *f, const mmp_decision_in *in, int32_t n, co
       if (n_extra) memcpy(h + o_ex, extra, (size_t)n_extra * 4);
       PlaceArgs a{ds.view, (const mmp_decision_in *)(dbase + o_in), n, (const FreshRow *)(dbase + o_fr), n_fresh,
                   (const int32_t *)(dbase + o_ex), (mmp_decision_out *)(dbase + o_out), nullptr, nullptr, now_ms, seed, 0};
-      CK(launch_place<false>(f, a, st));
+      CK(launch_place(f, a, st));
       CK(cudaStreamSynchronize(st));
       memcpy(out, h + o_out, (size_t)n * sizeof(mmp_decision_out));
       return MMP_OK;
@@ -627,7 +574,7 @@ static int32_t place_impl(mmp_fleet *f, const mmp_decision_in *in, int32_t n, co
       CK(cudaMemcpyAsync(c->d_in.as<mmp_decision_in>() + lo, in + lo, (size_t)cnt * sizeof(mmp_decision_in), cudaMemcpyHostToDevice, ps));
       PlaceArgs a{ds.view, c->d_in.as<mmp_decision_in>() + lo, cnt, c->d_fresh.as<FreshRow>(), n_fresh, c->d_extra.as<int32_t>(),
                   c->d_out.as<mmp_decision_out>() + lo, nullptr, nullptr, now_ms, seed, (uint64_t)lo};
-      CK(launch_place<false>(f, a, ps));
+      CK(launch_place(f, a, ps));
       CK(cudaMemcpyAsync(out + lo, c->d_out.as<mmp_decision_out>() + lo, (size_t)cnt * sizeof(mmp_decision_out), cudaMemcpyDeviceToHost, ps));
     }
     for (int i = 0; i < PlaceCtx::NPIPE; i++) CK(cudaStreamSynchronize(c->pipe[i]));
@@ -638,7 +585,7 @@ static int32_t place_impl(mmp_fleet *f, const mmp_decision_in *in, int32_t n, co
   PlaceArgs a{ds.view, c->d_in.as<mmp_decision_in>(), n, c->d_fresh.as<FreshRow>(), n_fresh, c->d_extra.as<int32_t>(),
               c->d_out.as<mmp_decision_out>(), trace ? c->d_trace.as<mmp_decision_trace>() : nullptr,
               cand_mask ? c->d_cand.as<uint32_t>() : nullptr, now_ms, seed, 0};
-  if (traced) CK(launch_place<true>(f, a, st)); else CK(launch_place<false>(f, a, st));
+  CK(launch_place(f, a, st));
   CK(cudaMemcpyAsync(out, c->d_out.p, (size_t)n * sizeof(mmp_decision_out), cudaMemcpyDeviceToHost, st));
   if (trace) CK(cudaMemcpyAsync(trace, c->d_trace.p, (size_t)n * sizeof(mmp_decision_trace), cudaMemcpyDeviceToHost, st));
   if (cand_mask) CK(cudaMemcpyAsync(cand_mask, c->d_cand.p, (size_t)n * 2 * RW * 4, cudaMemcpyDeviceToHost, st));
@@ -679,7 +626,7 @@ int32_t mmp_place_batch_device(mmp_fleet *f, const void *d_in, int32_t n, void *
   PlaceArgs a{ds.view, (const mmp_decision_in *)d_in, n, c->d_fresh.as<FreshRow>(), 0, c->d_extra.as<int32_t>(),
               (mmp_decision_out *)d_out, nullptr, nullptr, now_ms, seed, 0};
   CK(cudaEventRecord(c->e0, c->stream));
-  CK(launch_place<false>(f, a, c->stream));
+  CK(launch_place(f, a, c->stream));
   CK(cudaEventRecord(c->e1, c->stream));
   CK(cudaEventSynchronize(c->e1));
   if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, c->e0, c->e1));

@@ -88,8 +88,8 @@ static SnapshotView make_view(mmp_fleet *f) {
   const HostSnapshot &s = f->snap;
   v.n_ranks = s.n_ranks; v.row_words = s.row_words; v.n_models = (int32_t)f->models.size(); v.max_instances = f->hs.cfg.max_instances;
   v.any_rs = s.any_rs; v.n_type_ids = (int32_t)s.type_slot.size(); v.min_space = f->hs.cfg.min_space_units;
-  v.excl = f->excl.data(); v.cand = s.cand.data(); v.pref = s.pref.data(); v.has_pref = s.has_pref.data();
-  v.type_slot = s.type_slot.data(); v.rs = s.rs.data(); v.full = s.full.data(); v.rows = s.rows.data();
+  v.excl = f->excl.data(); v.cand = s.cand.data(); v.candx = s.candx.data(); v.pref = s.pref.data(); v.has_pref = s.has_pref.data();
+  v.type_slot = s.type_slot.data(); v.full = s.full.data(); v.rows = s.rows.data();
   v.rank_of = s.rank_of.data(); v.csum = s.csum.data(); v.lsum = s.lsum.data(); v.models = f->models.data();
   return v;
 }
@@ -108,8 +108,11 @@ int32_t mmp_place_batch_trace(mmp_fleet *f, const mmp_decision_in *in, int32_t n
   std::vector<uint32_t> fbuf(Coop1::NW_CAP);
   for (int32_t i = 0; i < n; i++) {
     DecideOut o;
-    decide<Coop1>(v, in[i], fr.data(), n_fresh, extra, now_ms, seed, (uint64_t)i, co, fbuf.data(), o,
-                  cand_mask ? cand_mask + (size_t)i * 2 * v.row_words : nullptr);
+    DecisionCtx cx;
+    prepare_ctx(v, in[i], fr.data(), n_fresh, cx);
+    const uint32_t *erow = v.excl + (size_t)(cx.slot >= 0 ? in[i].model : 0) * v.row_words;
+    decide_ctx<Coop1>(v, cx, erow, extra, now_ms, seed, (uint64_t)i, co, fbuf.data(), o,
+                      cand_mask ? cand_mask + (size_t)i * 2 * v.row_words : nullptr);
     out[i].target = o.target; out[i].n_candidates = o.n_candidates;
     if (trace) {
       trace[i].best = o.best; trace[i].n_remaining = o.n_remaining; trace[i].pick_index = o.pick_index; trace[i].flags = o.flags;
