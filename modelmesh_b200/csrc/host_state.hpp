@@ -173,15 +173,9 @@ class HostState {
     dirty_models = true;
     return MMP_OK;
   }
-  // Words per bitmap row = 32 lanes x NWL words per lane, NWL from the set the kernel is instantiated for
-  // (row stride is a multiple of 128 B; 10 000 instances -> NWL 10 -> 320 words = 1 280 B, no padding words).
-  static int32_t words_per_lane(int32_t max_instances) {
-    static const int32_t sup[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16, 20, 24, 32, 48, 64};
-    int32_t need = ((max_instances + 31) / 32 + 31) / 32;
-    for (int32_t v : sup) if (v >= need) return v;
-    return 64;
-  }
-  int32_t row_words() const { return 32 * words_per_lane(cfg.max_instances); }
+  // Words per bitmap row, rounded up to 32 words so that every row starts on a 128-byte line and is a whole number
+  // of 16-byte TMA units (10 000 instances -> 320 words = 1 280 B).
+  int32_t row_words() const { return ((cfg.max_instances + 31) / 32 + 31) / 32 * 32; }
 
   int32_t set_types_json(const char *json);  // defined after TcJson
 

@@ -97,24 +97,33 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 // The scoring kernel (TMA-staged).  One warp per decision; every warp owns a ring of K exclusion-row buffers in shared
 // memory that one elected lane keeps filled ahead with cp.async.bulk (a row is one contiguous, 128-byte-aligned run of
 // row_words*4 bytes), so K-1 rows per warp are in flight from HBM while the current decision is resolved out of the
-// K-th.  Lane l then owns words [l*NWL, (l+1)*NWL) of the row in registers (mmp::Coop32).  Decisions are taken in
+// K-th by window scans (mmp::decide_ctx: 32 words of the row at a time, one per lane).  Decisions are taken in
 // batches of 32: lane j prepares the context of decision j (its dependent gathers: decision -> model row,
-// rank_of[self] -> rows[self]) one batch ahead, so those latencies overlap across lanes and with the previous batch.
-template <int NWL, int K, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) k_place(const SnapshotView s, const mmp_decision_in *__restrict__ in, int n,
+// rank_of[self] -> rows[self]) one batch ahead into a double-buffered shared-memory table, so those latencies overlap
+// across lanes and with the previous batch.
+struct RingLayout {
+  uint32_t row_bytes, k;
+  size_t per_warp;
+  __host__ __device__ RingLayout(int row_words, int k_) : row_bytes((uint32_t)row_words * 4u), k((uint32_t)k_) {
+    per_warp = ((size_t)k * row_bytes + 2 * 32 * sizeof(DecisionCtx) + (size_t)k * 8 + 127) / 128 * 128;
+  }
+};
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_place(const SnapshotView s, const int K, const mmp_decision_in *__restrict__ in, int n,
                                                      const FreshRow *__restrict__ fresh, int n_fresh,
                                                      const int32_t *__restrict__ extra, mmp_decision_out *__restrict__ out,
                                                      mmp_decision_trace *__restrict__ tr, uint32_t *__restrict__ cand,
                                                      int64_t now, uint64_t seed, uint64_t id_base) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr int RW = NWL * 32;
-  constexpr uint32_t row_bytes = (uint32_t)RW * 4u;
+  const int RW = s.row_words;
+  const RingLayout lay(RW, K);
+  const uint32_t row_bytes = lay.row_bytes;
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr size_t per_warp = ((size_t)K * row_bytes + 32 * sizeof(DecisionCtx) + (size_t)K * 8 + 127) / 128 * 128;
-  unsigned char *base = smem_raw + (size_t)wib * per_warp;
+  unsigned char *base = smem_raw + (size_t)wib * lay.per_warp;
   uint32_t *rows_s = reinterpret_cast<uint32_t *>(base);
-  DecisionCtx *ctx_s = reinterpret_cast<DecisionCtx *>(base + (size_t)K * row_bytes);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(base + (size_t)K * row_bytes + 32 * sizeof(DecisionCtx));
+  DecisionCtx *ctx_s = reinterpret_cast<DecisionCtx *>(base + (size_t)K * row_bytes);  // [2][32]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(base + (size_t)K * row_bytes + 2 * 32 * sizeof(DecisionCtx));
   if (lane == 0) {
     for (int k = 0; k < K; k++) mbar_init(&bars[k], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -122,12 +131,11 @@ __global__ void __launch_bounds__(WARPS * 32) k_place(const SnapshotView s, cons
   __syncwarp();
   const int nb = (n + 31) >> 5;
   const int gw = blockIdx.x * WARPS + wib, nw = gridDim.x * WARPS;
-  Coop32<NWL> co;
-  uint32_t f[NWL];
+  Coop32 co;
   uint32_t use = 0;  // ring position of the next row to consume (warp-uniform)
-  DecisionCtx cn;    // this lane's context for the upcoming batch
-  auto prep = [&](int batch) {
+  auto prep = [&](int batch, DecisionCtx *dst) {  // lane j stages the context of decision j of `batch`
     const int i = batch * 32 + lane;
+    DecisionCtx cn;
     cn.slot = -2;  // absent
     cn.d.model = 0;
     if (batch < nb && i < n) {
@@ -138,34 +146,37 @@ __global__ void __launch_bounds__(WARPS * 32) k_place(const SnapshotView s, cons
       d.flags = (uint32_t)b.x; d.fresh = b.y; d.extra_off = b.z; d.extra_n = b.w;
       prepare_ctx(s, d, fresh, n_fresh, cn);
     }
+    dst[lane] = cn;
   };
   auto issue = [&](int model, uint32_t pos) {  // lane 0 only
     const int m = (model >= 0 && model < s.n_models) ? model : 0;
-    uint64_t *bar = &bars[pos % K];
-    mbar_expect_tx(bar, row_bytes);
-    bulk_g2s(rows_s + (size_t)(pos % K) * RW, s.excl + (size_t)m * RW, row_bytes, bar);
+    const uint32_t sl = pos % (uint32_t)K;
+    mbar_expect_tx(&bars[sl], row_bytes);
+    bulk_g2s(rows_s + (size_t)sl * RW, s.excl + (size_t)m * RW, row_bytes, &bars[sl]);
   };
-  int b = gw;
-  prep(b);
+  int b = gw, cur = 0;
+  prep(b, ctx_s);
+  __syncwarp();
   if (b < nb) {
-    ctx_s[lane] = cn;
-    __syncwarp();
     const int count = min(32, n - b * 32);
     if (lane == 0)
       for (int t = 0; t < K && t < count; t++) issue(ctx_s[t].d.model, (uint32_t)t);
   }
   while (b < nb) {
     const int bn = b + nw;
-    prep(bn);  // next batch's decisions + contexts: loads stay in flight while this batch is resolved
+    const DecisionCtx *cc = ctx_s + cur * 32;
+    DecisionCtx *cnext = ctx_s + (cur ^ 1) * 32;
+    prep(bn, cnext);  // next batch's contexts: their loads overlap this batch (the stores wait on them, nothing else does)
+    __syncwarp();
     const int count = min(32, n - b * 32);
     mmp_decision_out mine{MMP_TARGET_NONE, 0};
     for (int j = 0; j < count; j++) {
-      const uint32_t slot = use % K, parity = (use / K) & 1u;
+      const uint32_t slot = use % (uint32_t)K, parity = (use / (uint32_t)K) & 1u;
       while (!mbar_try_wait(&bars[slot], parity)) {}
       const uint32_t *erow = rows_s + (size_t)slot * RW;
       const int gi = b * 32 + j;
       DecideOut o;
-      decide_ctx(s, ctx_s[j], erow, extra, now, seed, id_base + (uint64_t)gi, co, f, o, cand ? cand + (size_t)gi * 2 * RW : nullptr);
+      decide_ctx(s, cc[j], erow, extra, now, seed, id_base + (uint64_t)gi, co, o, cand ? cand + (size_t)gi * 2 * RW : nullptr);
       if (lane == j) { mine.target = o.target; mine.n_candidates = o.n_candidates; }
       if (tr && lane == 0) {
         mmp_decision_trace t;
@@ -175,26 +186,22 @@ __global__ void __launch_bounds__(WARPS * 32) k_place(const SnapshotView s, cons
       }
       // the row has been consumed: refill this ring slot with the row of the decision K positions ahead
       const int t = j + K;
-      int nm = 0;
-      bool have = false;
-      if (t < count) { nm = ctx_s[t].d.model; have = true; }
-      else {
-        const int src = (t - count) & 31;
-        const int m2 = __shfl_sync(0xffffffffu, cn.d.model, src);
-        const int s2 = __shfl_sync(0xffffffffu, cn.slot, src);
-        if (t - count < 32 && s2 != -2) { nm = m2; have = true; }
-      }
       __syncwarp();
-      if (lane == 0 && have) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        issue(nm, use + K);
+      if (lane == 0) {
+        int nm = 0;
+        bool have = false;
+        if (t < count) { nm = cc[t].d.model; have = true; }
+        else if (t - count < 32 && cnext[t - count].slot != -2) { nm = cnext[t - count].d.model; have = true; }
+        if (have) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          issue(nm, use + (uint32_t)K);
+        }
       }
       use++;
     }
     if (lane < count) out[b * 32 + lane] = mine;
     b = bn;
-    __syncwarp();
-    if (b < nb) ctx_s[lane] = cn;
+    cur ^= 1;
     __syncwarp();
   }
 }
@@ -326,48 +333,35 @@ struct PlaceArgs {
   uint64_t seed, id_base;
 };
 
-template <int NWL, int K, int WARPS>
-static cudaError_t launch_place_t(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st) {
-  static int blocks_per_sm = 0;
-  constexpr size_t per_warp = ((size_t)K * NWL * 128 + 32 * sizeof(DecisionCtx) + (size_t)K * 8 + 127) / 128 * 128;
-  constexpr size_t smem = per_warp * WARPS;
-  auto kern = k_place<NWL, K, WARPS>;
-  if (!blocks_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+// ring depth / warps per block by row size: rows up to 2 KiB (16k instances) K=4 x 8 warps, up to 4 KiB K=3, beyond K=2 x 4 warps
+template <int WARPS>
+static cudaError_t launch_place_t(mmp_fleet *f, const PlaceArgs &a, int K, cudaStream_t st) {
+  static int attr_set = 0;
+  const RingLayout lay(a.s.row_words, K);
+  const size_t smem = lay.per_warp * WARPS;
+  auto kern = k_place<WARPS>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return e;
-    int b = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, WARPS * 32, smem);
-    if (e != cudaSuccess) return e;
-    blocks_per_sm = b > 0 ? b : 1;
+    attr_set = 1;
   }
+  int bps = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, WARPS * 32, smem);
+  if (e != cudaSuccess) return e;
+  if (bps < 1) bps = 1;
   int want = (a.n + 32 * WARPS - 1) / (32 * WARPS);
-  int grid = std::min(want, f->sm_count * blocks_per_sm);
+  int grid = std::min(want, f->sm_count * bps);
   if (grid < 1) grid = 1;
-  kern<<<grid, WARPS * 32, smem, st>>>(a.s, a.in, a.n, a.fresh, a.n_fresh, a.extra, a.out, a.tr, a.cand, a.now, a.seed, a.id_base);
+  kern<<<grid, WARPS * 32, smem, st>>>(a.s, K, a.in, a.n, a.fresh, a.n_fresh, a.extra, a.out, a.tr, a.cand, a.now, a.seed, a.id_base);
   f->launches++;
   return cudaGetLastError();
 }
 
-// dispatch on words per lane (row_words / 32); HostState::words_per_lane picks from the same set
 static cudaError_t launch_place(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st) {
-  switch (a.s.row_words / 32) {
-    case 1: return launch_place_t<1, 4, 8>(f, a, st);
-    case 2: return launch_place_t<2, 4, 8>(f, a, st);
-    case 3: return launch_place_t<3, 4, 8>(f, a, st);
-    case 4: return launch_place_t<4, 4, 8>(f, a, st);
-    case 5: return launch_place_t<5, 4, 8>(f, a, st);
-    case 6: return launch_place_t<6, 4, 8>(f, a, st);
-    case 8: return launch_place_t<8, 4, 8>(f, a, st);
-    case 10: return launch_place_t<10, 4, 8>(f, a, st);
-    case 12: return launch_place_t<12, 4, 8>(f, a, st);
-    case 16: return launch_place_t<16, 4, 8>(f, a, st);
-    case 20: return launch_place_t<20, 3, 8>(f, a, st);
-    case 24: return launch_place_t<24, 3, 8>(f, a, st);
-    case 32: return launch_place_t<32, 3, 8>(f, a, st);
-    case 48: return launch_place_t<48, 2, 4>(f, a, st);
-    case 64: return launch_place_t<64, 2, 4>(f, a, st);
-    default: return cudaErrorInvalidValue;
-  }
+  const int rw = a.s.row_words;
+  if (rw <= 512) return launch_place_t<8>(f, a, 4, st);
+  if (rw <= 1024) return launch_place_t<8>(f, a, 3, st);
+  return launch_place_t<4>(f, a, 2, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -1,8 +1,8 @@
 // place_core.cuh — the placement decision in rank space, written once for two cooperative shapes:
-//   * Coop32<NWL>: one 32-lane warp per decision on sm_100a.  The decision's exclusion-bitmap row has been staged in
-//     shared memory by a TMA bulk copy; lane l owns the NWL consecutive 32-bit words [l*NWL, (l+1)*NWL) of it in
-//     registers (a contiguous range of NWL*32 ranks), reductions are REDUX / SHFL / VOTE.
-//   * Coop1: a single "lane" holding the whole row; compiled by g++ into the CPU-only test harness (tests/emul) so the
+//   * Coop32: one 32-lane warp per decision on sm_100a.  The decision's exclusion-bitmap row has been staged in shared
+//     memory by a TMA bulk copy; the row is visited in windows of 32 consecutive words, one word per lane (1 024 ranks
+//     per step), reductions are REDUX / SHFL / VOTE.
+//   * Coop1: a single "lane", window = one word; compiled by g++ into the CPU-only test harness (tests/emul) so the
 //     bitmask formulation can be checked against the oracle without a GPU.  It is NOT part of the shipped library.
 //
 // What is computed (reference: CacheMissForwardingLB.getNext, ModelMesh.java:4776-5004; quirk labels N1.. are those of
@@ -13,9 +13,10 @@
 //   cut    = first rank in S whose walk test fails (MM:4913-4928, literal N2 semantics)               MM:4901-4937
 //   shortlist = {best} ∪ (S below cut); rpm filter (MM:4957-4980); hash-indexed pick (MM:4981-4986, N4)
 //
-// The routine is written to be issue-efficient on the GPU: every pass over the row costs NWL warp instructions per
-// operation, so passes are few (load, find-first, restrict, classify, count) and single-rank questions ("is self in the
-// filtered set?") are answered in O(1) from the staged row instead of by a pass.
+// The routine is written to be issue-efficient on the GPU: PLACEMENT_ORDER puts the answers near the front of the
+// order and near `best`, so every query ("first member", "first violator", "how many below the cut", "k-th survivor")
+// is a window scan that normally ends in its first window (~20 warp instructions), and single-rank questions ("is self
+// in the filtered set?") are answered in O(1) from the staged row.  No per-lane copy of the row is kept in registers.
 #pragma once
 #include <stdint.h>
 
@@ -130,20 +131,16 @@ MMP_HD uint32_t shl_ones(int32_t t) {
 MMP_HD uint32_t mask_above(uint32_t rank_base, uint32_t lo) { return shl_ones((int32_t)lo - (int32_t)rank_base + 1); }
 MMP_HD uint32_t mask_below(uint32_t rank_base, uint32_t hi) { return ~shl_ones((int32_t)hi - (int32_t)rank_base); }
 
-// ---- the single-lane cooperative shape (CPU harness) ----
+// ---- the single-lane cooperative shape (CPU harness): a "window" is one word ----
 struct Coop1 {
-  static constexpr int L = 1;
-  static constexpr int NW_CAP = 2048;  // 65536 instances
-  int nwl_;
-  explicit Coop1(int row_words) : nwl_(row_words) {}
-  MMP_HD int nwl() const { return nwl_; }
-  MMP_HD int lane() const { return 0; }
-  MMP_HD uint32_t wbase() const { return 0; }
+  static constexpr uint32_t L = 1;
+  MMP_HD uint32_t lane() const { return 0; }
   MMP_HD uint32_t rmin(uint32_t x) const { return x; }
   MMP_HD uint32_t rsum(uint32_t x) const { return x; }
   MMP_HD int32_t rmin_i(int32_t x) const { return x; }
   MMP_HD bool rany(bool p) const { return p; }
   MMP_HD uint32_t exscan(uint32_t) const { return 0; }
+  MMP_HD uint32_t shfl(uint32_t x, uint32_t) const { return x; }
   template <class F> MMP_HD uint32_t eval_word(uint32_t wi, int32_t n_ranks, F &&f) const {
     uint32_t m = 0;
     for (int b = 0; b < 32; b++) {
@@ -152,35 +149,26 @@ struct Coop1 {
     }
     return m;
   }
-  MMP_HD void load_andnot(uint32_t *f, const uint32_t *a, const uint32_t *b) const {
-    for (int k = 0; k < nwl_; k++) f[k] = a[k] & ~b[k];
-  }
-  MMP_HD void store_row(uint32_t *dst, const uint32_t *f) const {
-    for (int k = 0; k < nwl_; k++) dst[k] = f[k];
-  }
 };
 
 #if defined(__CUDACC__)
-// ---- the warp cooperative shape: lane l owns words [l*NWL, (l+1)*NWL) ----
-template <int NWL_>
+// ---- the warp cooperative shape: a window is 32 consecutive words of the row, one per lane ----
 struct Coop32 {
-  static constexpr int L = 32;
-  static constexpr int NW_CAP = NWL_;
-  int lane_;
+  static constexpr uint32_t L = 32;
+  uint32_t lane_;
   MMP_D Coop32() : lane_(threadIdx.x & 31) {}
-  MMP_D int nwl() const { return NWL_; }
-  MMP_D int lane() const { return lane_; }
-  MMP_D uint32_t wbase() const { return (uint32_t)lane_ * NWL_; }
+  MMP_D uint32_t lane() const { return lane_; }
   MMP_D uint32_t rmin(uint32_t x) const { return __reduce_min_sync(0xffffffffu, x); }
   MMP_D uint32_t rsum(uint32_t x) const { return __reduce_add_sync(0xffffffffu, x); }
   MMP_D int32_t rmin_i(int32_t x) const { return __reduce_min_sync(0xffffffffu, x); }
   MMP_D bool rany(bool p) const { return __any_sync(0xffffffffu, p) != 0; }
+  MMP_D uint32_t shfl(uint32_t x, uint32_t src) const { return __shfl_sync(0xffffffffu, x, (int)src); }
   MMP_D uint32_t exscan(uint32_t x) const {
     uint32_t v = x;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
-      if (lane_ >= o) v += t;
+      if (lane_ >= (uint32_t)o) v += t;
     }
     return v - x;
   }
@@ -189,113 +177,71 @@ struct Coop32 {
     bool p = (int32_t)r < n_ranks && f(r);
     return __ballot_sync(0xffffffffu, p);
   }
-  // f = a & ~b over this lane's words; a: type mask in global memory (L1/L2 resident), b: the staged exclusion row
-  // (shared memory).  Widest vector the lane's byte offset (lane*NWL*4) allows.
-  MMP_D void load_andnot(uint32_t *f, const uint32_t *a, const uint32_t *b) const {
-    const uint32_t w0 = wbase();
-    if constexpr (NWL_ % 4 == 0) {
-#pragma unroll
-      for (int k = 0; k < NWL_; k += 4) {
-        uint4 x = __ldg(reinterpret_cast<const uint4 *>(a + w0 + k));
-        uint4 y = *reinterpret_cast<const uint4 *>(b + w0 + k);
-        f[k] = x.x & ~y.x; f[k + 1] = x.y & ~y.y; f[k + 2] = x.z & ~y.z; f[k + 3] = x.w & ~y.w;
-      }
-    } else if constexpr (NWL_ % 2 == 0) {
-#pragma unroll
-      for (int k = 0; k < NWL_; k += 2) {
-        uint2 x = __ldg(reinterpret_cast<const uint2 *>(a + w0 + k));
-        uint2 y = *reinterpret_cast<const uint2 *>(b + w0 + k);
-        f[k] = x.x & ~y.x; f[k + 1] = x.y & ~y.y;
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < NWL_; k++) f[k] = __ldg(a + w0 + k) & ~b[w0 + k];
-    }
-  }
-  MMP_D void store_row(uint32_t *dst, const uint32_t *f) const {
-    const uint32_t w0 = wbase();
-#pragma unroll
-    for (int k = 0; k < NWL_; k++) dst[w0 + k] = f[k];
-  }
 };
 #endif
 
-#if defined(__CUDA_ARCH__)
-#define MMP_UNROLL _Pragma("unroll")
-#define MMP_FOR_K(co, k) _Pragma("unroll") for (int k = 0; k < C::NW_CAP; ++k)
-#define MMP_FOR_K_DESC(co, k) _Pragma("unroll") for (int k = C::NW_CAP - 1; k >= 0; --k)
-#else
-#define MMP_UNROLL
-#define MMP_FOR_K(co, k) for (int k = 0; k < (co).nwl(); ++k)
-#define MMP_FOR_K_DESC(co, k) for (int k = (co).nwl() - 1; k >= 0; --k)
-#endif
-
-// rank of the first set bit of f & m(k, rank_base) over the whole row, NONE_RANK if none
-template <class C, class M> MMP_HD uint32_t first_set_where(const C &co, const uint32_t *f, M &&m) {
-  const uint32_t rb0 = co.wbase() * 32u;
-  uint32_t w = 0, kk = 0;
-  MMP_FOR_K_DESC(co, k) {
-    uint32_t x = f[k] & m(k, rb0 + (uint32_t)k * 32u);
-    if (x) { w = x; kk = (uint32_t)k; }
+// ---- window scans.  A row is visited C::L words at a time starting at the word that holds the lower bound; `word(wi)`
+// returns word wi of the set being queried (range masks included).  Answers are almost always inside the first window
+// (the shortlist is a short prefix after best), so a query costs one window: ~20 warp instructions, not a row pass. ----
+template <class C, class W>
+MMP_HD uint32_t scan_first(const C &co, uint32_t from_word, uint32_t end_word, W &&word) {
+  for (uint32_t wb = from_word; wb < end_word; wb += C::L) {
+    const uint32_t wi = wb + co.lane();
+    const uint32_t x = wi < end_word ? word(wi) : 0u;
+    const uint32_t r = co.rmin(x ? wi * 32u + (uint32_t)ffs32(x) : NONE_RANK);
+    if (r != NONE_RANK) return r;
   }
-  uint32_t r = w ? rb0 + kk * 32u + (uint32_t)ffs32(w) : NONE_RANK;
-  return co.rmin(r);
+  return NONE_RANK;
 }
-template <class C> MMP_HD uint32_t first_set(const C &co, const uint32_t *f) {
-  return first_set_where(co, f, [](int, uint32_t) { return 0xffffffffu; });
-}
-template <class C> MMP_HD void clear_bit(const C &co, uint32_t *f, uint32_t rank) {
-  const uint32_t w = rank >> 5;
-  MMP_FOR_K(co, k) { if (co.wbase() + (uint32_t)k == w) f[k] &= ~(1u << (rank & 31)); }
-}
-// rank of the kth (0-based) set bit in ascending rank order; `mine` = popcount of this lane's words; kth < total
-template <class C> MMP_HD uint32_t select_kth(const C &co, const uint32_t *f, uint32_t mine, uint32_t kth) {
-  const uint32_t pre = co.exscan(mine);
-  uint32_t r = NONE_RANK;
-  if (kth >= pre && kth < pre + mine) {
-    uint32_t rem = kth - pre;
-    bool found = false;
-    MMP_FOR_K(co, k) {
-      uint32_t pc = (uint32_t)popc32(f[k]);
-      if (!found) {
-        if (rem < pc) { r = (co.wbase() + (uint32_t)k) * 32u + (uint32_t)nth_bit(f[k], rem); found = true; }
-        else rem -= pc;
-      }
+// First rank whose per-rank predicate holds.  `cls(wi)` classifies a 32-rank word from its min/max summary: 0 = no rank
+// violates, 1 = every rank violates, 2 = mixed; `eval(rank)` is the exact per-rank test.  Mixed words are resolved in
+// ascending order by a cooperative 32-rank evaluation; the scan stops at the first hit.
+template <class C, class W, class CLS, class EV>
+MMP_HD uint32_t scan_first_violator(const C &co, uint32_t from_word, uint32_t end_word, int32_t n_ranks, W &&word, CLS &&cls, EV &&eval) {
+  for (uint32_t wb = from_word; wb < end_word; wb += C::L) {
+    const uint32_t wi = wb + co.lane();
+    const uint32_t x = wi < end_word ? word(wi) : 0u;
+    uint32_t A = NONE_RANK, M = NONE_RANK;
+    if (x) {
+      const int c = cls(wi);
+      if (c == 1) A = wi * 32u + (uint32_t)ffs32(x);
+      else if (c == 2) M = wi;
     }
+    uint32_t Amin = co.rmin(A), Mmin = co.rmin(M);
+    while (Mmin != NONE_RANK && Mmin * 32u < Amin) {
+      const uint32_t xm = co.shfl(x, Mmin - wb);
+      const uint32_t vm = co.eval_word(Mmin, n_ranks, eval) & xm;
+      if (vm) { const uint32_t r = Mmin * 32u + (uint32_t)ffs32(vm); if (r < Amin) Amin = r; break; }
+      if (M == Mmin) M = NONE_RANK;
+      Mmin = co.rmin(M);
+    }
+    if (Amin != NONE_RANK) return Amin;
   }
-  return co.rmin(r);
+  return NONE_RANK;
 }
-
-// First rank in f whose per-rank predicate holds.  `cls(wi)` classifies a 32-rank word from its min/max summary:
-// 0 = no rank violates, 1 = every rank violates, 2 = mixed; `eval(rank)` is the exact per-rank test; `word(wi)` returns
-// word wi of f to every lane (recomputed from the staged row, so no register indexing).  Words are resolved in
-// ascending order and the search stops at the first hit, so the common case (a sorted fleet: one mixed word) costs
-// one cooperative word evaluation.
-template <class C, class CLS, class EV, class WORD>
-MMP_HD uint32_t first_violator(const C &co, const uint32_t *f, int32_t n_ranks, CLS &&cls, EV &&eval, WORD &&word) {
-  const uint32_t w0 = co.wbase();
-  uint32_t A = NONE_RANK, M = NONE_RANK;
-  MMP_FOR_K_DESC(co, k) {  // descending: the lowest class-1 hit and the lowest mixed word of this lane are what remain
-    if (f[k]) {
-      int c = cls(w0 + (uint32_t)k);
-      if (c == 1) A = (w0 + (uint32_t)k) * 32u + (uint32_t)ffs32(f[k]);
-      else if (c == 2) M = w0 + (uint32_t)k;
-    }
+template <class C, class W>
+MMP_HD uint32_t scan_count(const C &co, uint32_t from_word, uint32_t end_word, W &&word) {
+  uint32_t mine = 0;
+  for (uint32_t wb = from_word; wb < end_word; wb += C::L) {
+    const uint32_t wi = wb + co.lane();
+    if (wi < end_word) mine += (uint32_t)popc32(word(wi));
   }
-  uint32_t Amin = co.rmin(A), Mmin = co.rmin(M);
-  while (Mmin != NONE_RANK && Mmin * 32u < Amin) {
-    uint32_t vm = co.eval_word(Mmin, n_ranks, eval) & word(Mmin);
-    if (vm) { uint32_t r = Mmin * 32u + (uint32_t)ffs32(vm); if (r < Amin) Amin = r; break; }
-    if (M == Mmin) {  // this lane owned it: advance to its next mixed word
-      M = NONE_RANK;
-      MMP_FOR_K_DESC(co, k) {
-        uint32_t wi = w0 + (uint32_t)k;
-        if (wi > Mmin && f[k] && cls(wi) == 2) M = wi;
-      }
+  return co.rsum(mine);
+}
+// rank of the kth (0-based) set bit in ascending rank order
+template <class C, class W>
+MMP_HD uint32_t scan_select(const C &co, uint32_t from_word, uint32_t end_word, W &&word, uint32_t kth) {
+  for (uint32_t wb = from_word; wb < end_word; wb += C::L) {
+    const uint32_t wi = wb + co.lane();
+    const uint32_t x = wi < end_word ? word(wi) : 0u;
+    const uint32_t c = (uint32_t)popc32(x), tot = co.rsum(c);
+    if (kth < tot) {
+      const uint32_t pre = co.exscan(c);
+      return co.rmin((kth >= pre && kth < pre + c) ? wi * 32u + (uint32_t)nth_bit(x, kth - pre) : NONE_RANK);
     }
-    Mmin = co.rmin(M);
+    kth -= tot;
   }
-  return Amin;
+  return NONE_RANK;
 }
 
 struct DecideOut {
@@ -344,48 +290,40 @@ MMP_HD void prepare_ctx(const SnapshotView &s, const mmp_decision_in &d, const F
   c.slot = s.type_slot[tid];
 }
 
-// One getNext.  f: caller-provided array of C::NW_CAP words (registers on the GPU).  erow: this decision's exclusion
-// row, readable by every lane (shared memory on the GPU) until the routine returns.
-// cand_rows (optional): [2][row_words] receives the candidate mask (other than best) and the survivor mask.
+// One getNext.  erow: this decision's exclusion row, readable by every lane (shared memory on the GPU) until the
+// routine returns.  cand_rows (optional, trace): [2][row_words] receives the candidate mask (other than best) and the
+// survivor mask.
 template <class C>
 MMP_HD void decide_ctx(const SnapshotView &s, const DecisionCtx &c, const uint32_t *erow, const int32_t *extra, int64_t now,
-                       uint64_t seed, uint64_t decision_id, const C &co, uint32_t *f, DecideOut &o, uint32_t *cand_rows) {
+                       uint64_t seed, uint64_t decision_id, const C &co, DecideOut &o, uint32_t *cand_rows) {
   o.target = MMP_TARGET_NONE; o.n_candidates = 0; o.best = -1; o.n_remaining = 0; o.pick_index = 0; o.flags = 0;
   o.cut_rank = (int32_t)NONE_RANK; o.best_rank = -1;
-  const int RW = s.row_words;
+  const uint32_t NW = (uint32_t)s.row_words;
   if (c.slot < 0) { o.target = TARGET_INVALID; return; }
   const mmp_decision_in &d = c.d;
   const int slot = c.slot;
   const bool favour_self = (d.flags & MMP_DF_FAVOUR_SELF) != 0;
   const int32_t self_rank = c.self_rank;
   const FreshRow fr = c.fr;
-  const uint32_t *CAND = s.cand + (size_t)slot * RW;
-  const uint32_t *P = s.pref + (size_t)slot * RW;
+  const uint32_t *CAND = s.cand + (size_t)slot * NW;
+  const uint32_t *P = s.pref + (size_t)slot * NW;
   const int n_extra = d.extra_n < 16 ? d.extra_n : 16;
-  const uint32_t w0 = co.wbase();
-
-  // ---- filter (MM:4760-4771): candx already excludes likely-replaced replicaset members ----
-  const uint32_t *CX = s.any_rs ? s.candx + (size_t)slot * RW : CAND;
-  auto apply_extra = [&]() {
-    for (int e = 0; e < n_extra; e++) {
-      int32_t x = extra[d.extra_off + e];
-      if (x >= 0 && x < s.max_instances) { int32_t r = s.rank_of[x]; if (r >= 0) clear_bit(co, f, (uint32_t)r); }
+  auto end_for = [&](uint32_t hi_rank) -> uint32_t {  // one past the last word that can hold a rank < hi_rank
+    if (hi_rank == NONE_RANK) return NW;
+    uint32_t e = (hi_rank + 31u) >> 5;
+    return e < NW ? e : NW;
+  };
+  auto emit_rows = [&](auto &&w0f, auto &&w1f) {  // trace only
+    for (uint32_t wb = 0; wb < NW; wb += C::L) {
+      uint32_t wi = wb + co.lane();
+      if (wi < NW) { cand_rows[wi] = w0f(wi); cand_rows[NW + wi] = w1f(wi); }
     }
   };
-  co.load_andnot(f, CX, erow);
-  if (n_extra) apply_extra();
-  uint32_t b = first_set(co, f);
-  if (b == NONE_RANK && s.any_rs) {
-    // MM:4798-4802: nothing survives; run the filter again without the replicaset exclusion
-    o.flags |= MMP_TF_RS_RETRY;
-    CX = CAND;
-    co.load_andnot(f, CX, erow);
-    if (n_extra) apply_extra();
-    b = first_set(co, f);
-  }
-  if (b == NONE_RANK) return;  // null
-  // word wi of the filtered set F, recomputed from the staged row for every lane (uniform loads, no register indexing)
-  auto f_word = [&](uint32_t wi) -> uint32_t {
+
+  // ---- filter (MM:4760-4771): candx already excludes likely-replaced replicaset members ----
+  const uint32_t *CX = s.any_rs ? s.candx + (size_t)slot * NW : CAND;
+  // word wi of the filtered set F
+  auto Fw = [&](uint32_t wi) -> uint32_t {
     uint32_t m = CX[wi] & ~erow[wi];
     for (int e = 0; e < n_extra; e++) {
       int32_t x = extra[d.extra_off + e];
@@ -393,7 +331,15 @@ MMP_HD void decide_ctx(const SnapshotView &s, const DecisionCtx &c, const uint32
     }
     return m;
   };
-  auto in_filter = [&](uint32_t r) -> bool { return (f_word(r >> 5) >> (r & 31)) & 1u; };
+  uint32_t b = scan_first(co, 0, NW, Fw);
+  if (b == NONE_RANK && s.any_rs) {
+    // MM:4798-4802: nothing survives; run the filter again without the replicaset exclusion
+    o.flags |= MMP_TF_RS_RETRY;
+    CX = CAND;
+    b = scan_first(co, 0, NW, Fw);
+  }
+  if (b == NONE_RANK) return;  // null
+  auto in_filter = [&](uint32_t r) -> bool { return (Fw(r >> 5) >> (r & 31)) & 1u; };
   auto pref_bit = [&](uint32_t r) -> bool { return (P[r >> 5] >> (r & 31)) & 1u; };
 
   const RankRow rb = s.rows[b];  // bestEntry.getValue()
@@ -411,9 +357,20 @@ MMP_HD void decide_ctx(const SnapshotView &s, const DecisionCtx &c, const uint32
 
   if (!simple) {
     if (!best_full) {
-      // non-simple (a) MM:4828-4852: first later entry that is preferred, unless a full one comes first
-      uint32_t p1 = first_set_where(co, f, [&](int k, uint32_t rbk) { return P[w0 + k] & mask_above(rbk, b); });
-      uint32_t f1 = first_set_where(co, f, [&](int k, uint32_t rbk) { return s.full[w0 + k] & ~P[w0 + k] & mask_above(rbk, b); });
+      // non-simple (a) MM:4828-4852: first later entry that is preferred, unless a full one comes first.
+      // One fused scan: stop at the first window that holds either.
+      uint32_t p1 = NONE_RANK, f1 = NONE_RANK;
+      for (uint32_t wb = b >> 5; wb < NW; wb += C::L) {
+        const uint32_t wi = wb + co.lane();
+        uint32_t xp = 0, xf = 0;
+        if (wi < NW) {
+          const uint32_t x = Fw(wi) & mask_above(wi * 32u, b), pw = P[wi];
+          xp = x & pw; xf = x & s.full[wi] & ~pw;
+        }
+        p1 = co.rmin(xp ? wi * 32u + (uint32_t)ffs32(xp) : NONE_RANK);
+        f1 = co.rmin(xf ? wi * 32u + (uint32_t)ffs32(xf) : NONE_RANK);
+        if (p1 != NONE_RANK || f1 != NONE_RANK) break;
+      }
       if (p1 < f1) {
         const RankRow rp = s.rows[p1];
         best_rank = p1; best_idx = rp.idx; best_rem = rp.rem; best_lru = rp.lru; best_count = rp.count; best_rpm = rp.rpm;
@@ -426,47 +383,55 @@ MMP_HD void decide_ctx(const SnapshotView &s, const DecisionCtx &c, const uint32
       // non-simple (b) MM:4853-4887
       const int64_t oldest = best_lru, a4 = age_of(oldest, now) / 4;
       auto viol = [&](int64_t l) { int64_t diff = jsub(l, oldest); return diff > 120000 && diff > a4; };
-      MMP_FOR_K(co, k) { f[k] &= mask_above((w0 + (uint32_t)k) * 32u, b); }
-      const uint32_t kb = first_violator(co, f, s.n_ranks,
+      const uint32_t kb = scan_first_violator(co, b >> 5, NW, s.n_ranks,
+          [&](uint32_t wi) { return Fw(wi) & mask_above(wi * 32u, b); },
           [&](uint32_t wi) { WordSumL m = s.lsum[wi]; return !viol(m.hi) ? 0 : (viol(m.lo) ? 1 : 2); },
-          [&](uint32_t r) { return viol(s.rows[r].lru); },
-          [&](uint32_t wi) { return f_word(wi) & mask_above(wi * 32u, b); });
-      bool anyp = false;
-      MMP_FOR_K(co, k) { if (f[k] & P[w0 + k] & mask_below((w0 + (uint32_t)k) * 32u, kb)) anyp = true; }
-      if (co.rany(anyp)) {
+          [&](uint32_t r) { return viol(s.rows[r].lru); });
+      const uint32_t endb = end_for(kb);
+      auto Cw = [&](uint32_t wi) { return Fw(wi) & P[wi] & mask_above(wi * 32u, b) & mask_below(wi * 32u, kb); };
+      const uint32_t firstp = scan_first(co, b >> 5, endb, Cw);
+      if (firstp != NONE_RANK) {
         // only preferred instances within the age distance are candidates; each records its own published rpm
         o.flags |= MMP_TF_PREF_B;
-        MMP_FOR_K(co, k) { f[k] &= P[w0 + k] & mask_below((w0 + (uint32_t)k) * 32u, kb); }
-        if (cand_rows) co.store_row(cand_rows, f);
         const bool self_in = self_rank >= 0 && (uint32_t)self_rank > b && (uint32_t)self_rank < kb && pref_bit((uint32_t)self_rank) &&
                              in_filter((uint32_t)self_rank);
-        if (self_in && favour_self) { o.flags |= MMP_TF_FAVOUR_EXIT; return; }  // N8: returns null
-        uint32_t mine = 0;
-        MMP_FOR_K(co, k) { mine += (uint32_t)popc32(f[k]); }
-        const int32_t ccount = (int32_t)co.rsum(mine);
+        if (self_in && favour_self) {  // N8: returns null
+          o.flags |= MMP_TF_FAVOUR_EXIT;
+          if (cand_rows) emit_rows(Cw, [](uint32_t) { return 0u; });
+          return;
+        }
+        const int32_t ccount = (int32_t)scan_count(co, firstp >> 5, endb, Cw);
         o.n_candidates = ccount;
         uint32_t chosen;
-        if (ccount == 1) { chosen = first_set(co, f); o.n_remaining = 1; }
-        else {
+        if (ccount == 1) {
+          chosen = firstp; o.n_remaining = 1;
+          if (cand_rows) emit_rows(Cw, Cw);
+        } else {
           int32_t remaining = ccount;
           const int64_t ago = age_of(c.last_used, now);
-          if (ago < 432000000LL) {
+          const bool filter = ago < 432000000LL;
+          RpmFilter rf;
+          rf.init(100, ago);
+          if (filter) {
             int32_t mn = 2147483647;
-            MMP_FOR_K(co, k) { uint32_t w = f[k], wi = w0 + (uint32_t)k; while (w) { int bt = ffs32(w); w &= w - 1; int32_t v = s.rows[wi * 32 + bt].rpm; if (v < mn) mn = v; } }
-            RpmFilter rf; rf.init(co.rmin_i(mn), ago);
-            mine = 0;
-            MMP_FOR_K(co, k) {
-              uint32_t w = f[k], wi = w0 + (uint32_t)k;
-              while (w) { int bt = ffs32(w); w &= w - 1; if (rf.drop(s.rows[wi * 32 + bt].rpm)) f[k] &= ~(1u << bt); }
-              mine += (uint32_t)popc32(f[k]);
+            for (uint32_t wb = firstp >> 5; wb < endb; wb += C::L) {
+              const uint32_t wi = wb + co.lane();
+              uint32_t w = wi < endb ? Cw(wi) : 0u;
+              while (w) { int bt = ffs32(w); w &= w - 1; int32_t v = s.rows[wi * 32 + bt].rpm; if (v < mn) mn = v; }
             }
-            remaining = (int32_t)co.rsum(mine);
+            rf.init(co.rmin_i(mn), ago);
           }
+          auto Kw = [&](uint32_t wi) {  // candidates that survive the rpm filter
+            uint32_t w = Cw(wi), keep = w;
+            if (filter) while (w) { int bt = ffs32(w); w &= w - 1; if (rf.drop(s.rows[wi * 32 + bt].rpm)) keep &= ~(1u << bt); }
+            return keep;
+          };
+          if (filter) remaining = (int32_t)scan_count(co, firstp >> 5, endb, Kw);
           uint32_t index = remaining == 1 ? 0u : hash_index(seed, decision_id, (uint32_t)remaining);
-          chosen = select_kth(co, f, mine, index);
+          chosen = scan_select(co, firstp >> 5, endb, Kw, index);
           o.n_remaining = remaining; o.pick_index = (int32_t)index;
+          if (cand_rows) emit_rows(Cw, Kw);
         }
-        if (cand_rows) co.store_row(cand_rows + RW, f);
         int32_t cidx = s.rows[chosen].idx;
         o.target = (!favour_self && cidx == d.self) ? MMP_TARGET_SELF : cidx;
         return;
@@ -478,19 +443,14 @@ MMP_HD void decide_ctx(const SnapshotView &s, const DecisionCtx &c, const uint32
   o.flags |= MMP_TF_SIMPLE;
   if (us && favour_self) { o.flags |= MMP_TF_FAVOUR_EXIT; o.target = MMP_TARGET_SELF; return; }
   // S = F restricted to ranks in (lo, hi) and, when preference is binding, to preferred instances
-  MMP_FOR_K(co, k) {
-    const uint32_t rbk = (w0 + (uint32_t)k) * 32u;
-    uint32_t m = mask_above(rbk, lo) & mask_below(rbk, hi);
-    if (use_pref) m &= P[w0 + k];
-    f[k] &= m;
-  }
-  const bool self_in_s = self_rank >= 0 && (uint32_t)self_rank > lo && (uint32_t)self_rank < hi &&
-                         (!use_pref || pref_bit((uint32_t)self_rank)) && in_filter((uint32_t)self_rank);
-  auto s_word = [&](uint32_t wi) -> uint32_t {  // word wi of S for every lane
-    uint32_t m = f_word(wi) & mask_above(wi * 32u, lo) & mask_below(wi * 32u, hi);
+  const uint32_t from = lo >> 5, end = end_for(hi);
+  auto Sw = [&](uint32_t wi) -> uint32_t {
+    uint32_t m = Fw(wi) & mask_above(wi * 32u, lo) & mask_below(wi * 32u, hi);
     if (use_pref) m &= P[wi];
     return m;
   };
+  const bool self_in_s = self_rank >= 0 && (uint32_t)self_rank > lo && (uint32_t)self_rank < hi &&
+                         (!use_pref || pref_bit((uint32_t)self_rank)) && in_filter((uint32_t)self_rank);
   const int64_t oldest = best_lru;
   bool c_self, self_viol;
   uint32_t cut_others = NONE_RANK;
@@ -510,27 +470,26 @@ MMP_HD void decide_ctx(const SnapshotView &s, const DecisionCtx &c, const uint32
   if (!best_full && self_in_s && cv(s.rows[self_rank].count)) self_viol = true;
   if (c_self) {
     // every non-self candidate fails: the walk stops at the first member of S other than self
-    cut_others = first_set(co, f);
+    cut_others = scan_first(co, from, end, Sw);
     if (self_in_s && cut_others == (uint32_t)self_rank)
-      cut_others = first_set_where(co, f, [&](int, uint32_t rbk) { return mask_above(rbk, (uint32_t)self_rank); });
+      cut_others = scan_first(co, (uint32_t)self_rank >> 5, end, [&](uint32_t wi) { return Sw(wi) & mask_above(wi * 32u, (uint32_t)self_rank); });
   } else if (!best_full) {
     // a self member that fails the count test is reported here too; it then also sets self_viol: same cut
-    cut_others = first_violator(co, f, s.n_ranks,
+    cut_others = scan_first_violator(co, from, end, s.n_ranks, Sw,
         [&](uint32_t wi) { WordSumI m = s.csum[wi]; return !cv(m.hi) ? 0 : (cv(m.lo) ? 1 : 2); },
-        [&](uint32_t r) { return cv(s.rows[r].count); }, s_word);
+        [&](uint32_t r) { return cv(s.rows[r].count); });
   }
   const uint32_t cut_self = (self_in_s && self_viol) ? (uint32_t)self_rank : NONE_RANK;
   const uint32_t cut = cut_others < cut_self ? cut_others : cut_self;
   o.cut_rank = (int32_t)cut;
   const bool self_in_sl = self_in_s && (uint32_t)self_rank < cut;
   if (favour_self && self_in_sl) { o.flags |= MMP_TF_FAVOUR_EXIT; o.target = MMP_TARGET_SELF; return; }
-  uint32_t mine = 0;
-  MMP_FOR_K(co, k) { f[k] &= mask_below((w0 + (uint32_t)k) * 32u, cut); mine += (uint32_t)popc32(f[k]); }  // f = candidates other than best
-  const int32_t n_in = (int32_t)co.rsum(mine);
+  const uint32_t endc = cut == NONE_RANK ? end : (end_for(cut) < end ? end_for(cut) : end);
+  auto SLw = [&](uint32_t wi) -> uint32_t { return Sw(wi) & mask_below(wi * 32u, cut); };  // candidates other than best
+  const int32_t n_in = (int32_t)scan_count(co, from, endc, SLw);
   const int32_t n_others = n_in - (self_in_sl ? 1 : 0);
   const int32_t ccount = 1 + n_in;
   o.n_candidates = ccount;
-  if (cand_rows) co.store_row(cand_rows, f);
   bool keep_best = true, keep_others = true, keep_self = true;
   int32_t remaining = ccount;
   uint32_t index = 0;
@@ -549,30 +508,20 @@ MMP_HD void decide_ctx(const SnapshotView &s, const DecisionCtx &c, const uint32
   o.n_remaining = remaining; o.pick_index = (int32_t)index;
   o.flags |= (keep_best ? MMP_TF_KEEP_BEST : 0) | (keep_others ? MMP_TF_KEEP_OTHERS : 0) | (keep_self ? MMP_TF_KEEP_SELF : 0);
   // survivors in rank order: best first (its rank precedes all of S), then S below the cut
-  if (cand_rows) {  // trace only: materialise the survivor mask
-    const uint32_t sw = (uint32_t)self_rank >> 5, sb = 1u << (self_rank & 31);
-    MMP_FOR_K(co, k) {
-      uint32_t v = keep_others ? f[k] : 0u;
-      if (self_in_sl && w0 + (uint32_t)k == sw) v = keep_self ? (v | sb) : (v & ~sb);
-      cand_rows[RW + w0 + k] = v;
-    }
-  }
+  const uint32_t sw = self_rank >= 0 ? (uint32_t)self_rank >> 5 : NONE_RANK, sb = 1u << (self_rank & 31);
+  auto SVw = [&](uint32_t wi) -> uint32_t {
+    uint32_t v = keep_others ? SLw(wi) : 0u;
+    if (self_in_sl && wi == sw) v = keep_self ? (v | sb) : (v & ~sb);
+    return v;
+  };
+  if (cand_rows) emit_rows(SLw, SVw);
   uint32_t chosen_rank;
   uint32_t kth = index;
   if (keep_best && kth == 0) chosen_rank = best_rank;
   else {
     if (keep_best) kth--;
     if (!keep_others) chosen_rank = (uint32_t)self_rank;  // the only other survivor can be the self candidate
-    else {
-      if (self_in_sl && !keep_self) {
-        // skip the self candidate: it sits at position ps among the set bits of f
-        uint32_t below = 0;
-        MMP_FOR_K(co, k) { below += (uint32_t)popc32(f[k] & mask_below((w0 + (uint32_t)k) * 32u, (uint32_t)self_rank)); }
-        const uint32_t ps = co.rsum(below);
-        if (kth >= ps) kth++;
-      }
-      chosen_rank = select_kth(co, f, mine, kth);
-    }
+    else chosen_rank = scan_select(co, from, endc, SVw, kth);
   }
   const int32_t cidx = chosen_rank == best_rank ? best_idx : s.rows[chosen_rank].idx;
   o.target = (!favour_self && cidx == d.self) ? MMP_TARGET_SELF : cidx;

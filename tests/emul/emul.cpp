@@ -104,14 +104,13 @@ int32_t mmp_place_batch_trace(mmp_fleet *f, const mmp_decision_in *in, int32_t n
     if (const char *m = HostState::validate_row(fresh[i])) { g_err = m; return MMP_E_ARG; }
     fr[i] = FreshRow{fresh[i].lru_time, std::max<int64_t>(0, fresh[i].capacity - fresh[i].used), fresh[i].count, fresh[i].rpm};
   }
-  Coop1 co(v.row_words);
-  std::vector<uint32_t> fbuf(Coop1::NW_CAP);
+  Coop1 co;
   for (int32_t i = 0; i < n; i++) {
     DecideOut o;
     DecisionCtx cx;
     prepare_ctx(v, in[i], fr.data(), n_fresh, cx);
     const uint32_t *erow = v.excl + (size_t)(cx.slot >= 0 ? in[i].model : 0) * v.row_words;
-    decide_ctx<Coop1>(v, cx, erow, extra, now_ms, seed, (uint64_t)i, co, fbuf.data(), o,
+    decide_ctx<Coop1>(v, cx, erow, extra, now_ms, seed, (uint64_t)i, co, o,
                       cand_mask ? cand_mask + (size_t)i * 2 * v.row_words : nullptr);
     out[i].target = o.target; out[i].n_candidates = o.n_candidates;
     if (trace) {
