@@ -109,8 +109,8 @@ struct RingLayout {
   }
 };
 
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) k_place(const SnapshotView s, const int K, const mmp_decision_in *__restrict__ in, int n,
+template <int WARPS, int K>
+__global__ void __launch_bounds__(WARPS * 32) k_place(const SnapshotView s, const mmp_decision_in *__restrict__ in, int n,
                                                      const FreshRow *__restrict__ fresh, int n_fresh,
                                                      const int32_t *__restrict__ extra, mmp_decision_out *__restrict__ out,
                                                      mmp_decision_trace *__restrict__ tr, uint32_t *__restrict__ cand,
@@ -176,7 +176,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_place(const SnapshotView s, cons
       const uint32_t *erow = rows_s + (size_t)slot * RW;
       const int gi = b * 32 + j;
       DecideOut o;
-      decide_ctx(s, cc[j], erow, extra, now, seed, id_base + (uint64_t)gi, co, o, cand ? cand + (size_t)gi * 2 * RW : nullptr);
+      if (cand || !decide_fast(s, cc[j], erow, now, seed, id_base + (uint64_t)gi, co, o))
+        decide_ctx(s, cc[j], erow, extra, now, seed, id_base + (uint64_t)gi, co, o, cand ? cand + (size_t)gi * 2 * RW : nullptr);
       if (lane == j) { mine.target = o.target; mine.n_candidates = o.n_candidates; }
       if (tr && lane == 0) {
         mmp_decision_trace t;
@@ -333,13 +334,13 @@ struct PlaceArgs {
   uint64_t seed, id_base;
 };
 
-// ring depth / warps per block by row size: rows up to 2 KiB (16k instances) K=4 x 8 warps, up to 4 KiB K=3, beyond K=2 x 4 warps
-template <int WARPS>
-static cudaError_t launch_place_t(mmp_fleet *f, const PlaceArgs &a, int K, cudaStream_t st) {
+// ring depth (a power of two) / warps per block by row size: rows up to 2 KiB (16k instances) K=4 x 8 warps, up to 4 KiB K=2 x 8, beyond K=2 x 4
+template <int WARPS, int K>
+static cudaError_t launch_place_t(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st) {
   static int attr_set = 0;
   const RingLayout lay(a.s.row_words, K);
   const size_t smem = lay.per_warp * WARPS;
-  auto kern = k_place<WARPS>;
+  auto kern = k_place<WARPS, K>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return e;
@@ -352,16 +353,16 @@ static cudaError_t launch_place_t(mmp_fleet *f, const PlaceArgs &a, int K, cudaS
   int want = (a.n + 32 * WARPS - 1) / (32 * WARPS);
   int grid = std::min(want, f->sm_count * bps);
   if (grid < 1) grid = 1;
-  kern<<<grid, WARPS * 32, smem, st>>>(a.s, K, a.in, a.n, a.fresh, a.n_fresh, a.extra, a.out, a.tr, a.cand, a.now, a.seed, a.id_base);
+  kern<<<grid, WARPS * 32, smem, st>>>(a.s, a.in, a.n, a.fresh, a.n_fresh, a.extra, a.out, a.tr, a.cand, a.now, a.seed, a.id_base);
   f->launches++;
   return cudaGetLastError();
 }
 
 static cudaError_t launch_place(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st) {
   const int rw = a.s.row_words;
-  if (rw <= 512) return launch_place_t<8>(f, a, 4, st);
-  if (rw <= 1024) return launch_place_t<8>(f, a, 3, st);
-  return launch_place_t<4>(f, a, 2, st);
+  if (rw <= 512) return launch_place_t<8, 4>(f, a, st);
+  if (rw <= 1024) return launch_place_t<8, 2>(f, a, st);
+  return launch_place_t<4, 2>(f, a, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

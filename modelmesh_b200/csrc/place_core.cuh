@@ -108,13 +108,18 @@ MMP_HD int popc32(uint32_t x) {
 #endif
 }
 // position of the (n+1)-th set bit of w (n < popc(w))
-MMP_HD int nth_bit(uint32_t w, uint32_t n) {
-#if defined(__CUDA_ARCH__)
-  return (int)__fns(w, 0, (int)n + 1);
-#else
-  for (uint32_t i = 0; i < n; i++) w &= w - 1;
-  return __builtin_ctz(w);
-#endif
+MMP_HD int nth_bit(uint32_t w, uint32_t n) {  // halving search on popcounts (the __fns intrinsic is ~50 instructions)
+  int pos = 0;
+  uint32_t c = (uint32_t)popc32(w & 0xffffu);
+  if (n >= c) { n -= c; pos = 16; w >>= 16; }
+  c = (uint32_t)popc32(w & 0xffu);
+  if (n >= c) { n -= c; pos += 8; w >>= 8; }
+  c = (uint32_t)popc32(w & 0xfu);
+  if (n >= c) { n -= c; pos += 4; w >>= 4; }
+  c = (uint32_t)popc32(w & 0x3u);
+  if (n >= c) { n -= c; pos += 2; w >>= 2; }
+  if (n >= (w & 1u)) pos += 1;
+  return pos;
 }
 // 0xffffffff << t with t clamped to [0, 32] (32 -> 0).  PTX shl clamps the shift amount, C does not.
 MMP_HD uint32_t shl_ones(int32_t t) {
@@ -149,6 +154,42 @@ struct Coop1 {
     }
     return m;
   }
+  // ---- 32-word window values (the GPU keeps one word per lane; here the 32 words are an array) ----
+  struct W { uint32_t v[32]; };
+  template <class F> MMP_HD W wmap(uint32_t w0, uint32_t nw, F &&f) const {  // word wi = w0 + i, zero past the row
+    W r;
+    for (uint32_t i = 0; i < 32; i++) r.v[i] = (w0 + i < nw) ? f(w0 + i) : 0u;
+    return r;
+  }
+  template <class F> MMP_HD W wmap1(uint32_t w0, const W &a, F &&f) const {
+    W r;
+    for (uint32_t i = 0; i < 32; i++) r.v[i] = f(w0 + i, a.v[i]);
+    return r;
+  }
+  template <class F> MMP_HD W wmap2(uint32_t w0, const W &a, const W &b, F &&f) const {
+    W r;
+    for (uint32_t i = 0; i < 32; i++) r.v[i] = f(w0 + i, a.v[i], b.v[i]);
+    return r;
+  }
+  MMP_HD uint32_t wfirst(uint32_t w0, const W &x) const {  // rank of the first set bit in the window
+    for (uint32_t i = 0; i < 32; i++) if (x.v[i]) return (w0 + i) * 32u + (uint32_t)ffs32(x.v[i]);
+    return NONE_RANK;
+  }
+  template <class F> MMP_HD uint32_t wmin(uint32_t w0, const W &x, F &&f) const {  // min over words of f(wi, word)
+    uint32_t m = NONE_RANK;
+    for (uint32_t i = 0; i < 32; i++) { uint32_t t = f(w0 + i, x.v[i]); if (t < m) m = t; }
+    return m;
+  }
+  MMP_HD uint32_t wpopc(const W &x) const { uint32_t c = 0; for (uint32_t i = 0; i < 32; i++) c += (uint32_t)popc32(x.v[i]); return c; }
+  MMP_HD uint32_t wget(uint32_t w0, const W &x, uint32_t wi) const { return x.v[wi - w0]; }
+  MMP_HD uint32_t wselect(uint32_t w0, const W &x, uint32_t kth) const {  // rank of the kth set bit; kth < wpopc(x)
+    for (uint32_t i = 0; i < 32; i++) {
+      uint32_t c = (uint32_t)popc32(x.v[i]);
+      if (kth < c) return (w0 + i) * 32u + (uint32_t)nth_bit(x.v[i], kth);
+      kth -= c;
+    }
+    return NONE_RANK;
+  }
 };
 
 #if defined(__CUDACC__)
@@ -176,6 +217,19 @@ struct Coop32 {
     uint32_t r = wi * 32 + lane_;
     bool p = (int32_t)r < n_ranks && f(r);
     return __ballot_sync(0xffffffffu, p);
+  }
+  // ---- 32-word window values: one word per lane, in a register ----
+  typedef uint32_t W;
+  template <class F> MMP_D W wmap(uint32_t w0, uint32_t nw, F &&f) const { uint32_t wi = w0 + lane_; return wi < nw ? f(wi) : 0u; }
+  template <class F> MMP_D W wmap1(uint32_t w0, W a, F &&f) const { return f(w0 + lane_, a); }
+  template <class F> MMP_D W wmap2(uint32_t w0, W a, W b, F &&f) const { return f(w0 + lane_, a, b); }
+  MMP_D uint32_t wfirst(uint32_t w0, W x) const { return rmin(x ? (w0 + lane_) * 32u + (uint32_t)ffs32(x) : NONE_RANK); }
+  template <class F> MMP_D uint32_t wmin(uint32_t w0, W x, F &&f) const { return rmin(f(w0 + lane_, x)); }
+  MMP_D uint32_t wpopc(W x) const { return rsum((uint32_t)popc32(x)); }
+  MMP_D uint32_t wget(uint32_t w0, W x, uint32_t wi) const { return __shfl_sync(0xffffffffu, x, (int)(wi - w0)); }
+  MMP_D uint32_t wselect(uint32_t w0, W x, uint32_t kth) const {
+    const uint32_t c = (uint32_t)popc32(x), pre = exscan(c);
+    return rmin((kth >= pre && kth < pre + c) ? (w0 + lane_) * 32u + (uint32_t)nth_bit(x, kth - pre) : NONE_RANK);
   }
 };
 #endif
@@ -288,6 +342,161 @@ MMP_HD void prepare_ctx(const SnapshotView &s, const mmp_decision_in &d, const F
   else if (c.self_rank >= 0) { const RankRow sr = s.rows[c.self_rank]; c.fr.lru = sr.lru; c.fr.rem = sr.rem; c.fr.count = sr.count; c.fr.rpm = 0; }
   else return;
   c.slot = s.type_slot[tid];
+}
+
+#define MMP_TF_FAST 256  // trace flag (not part of the ABI): resolved by the one-window fast path
+
+// The common case of getNext resolved inside ONE 32-word window (1 024 ranks) whose words stay in registers: best, the
+// non-simple (a) probe, the cut, the shortlist count and the pick are all window reductions (~250 warp instructions).
+// Returns false -- nothing written -- whenever the answer is not provably inside the window or the decision takes a
+// path handled only by the general routine (extra excludes, replicaset retry, best full, trace masks); the caller then
+// runs decide_ctx.  Same semantics, same quirks; tests compare both against the oracle.
+template <class C>
+MMP_HD bool decide_fast(const SnapshotView &s, const DecisionCtx &c, const uint32_t *erow, int64_t now, uint64_t seed,
+                        uint64_t decision_id, const C &co, DecideOut &o) {
+  typedef typename C::W W;
+  if (c.slot < 0 || c.d.extra_n != 0) return false;
+  const uint32_t NW = (uint32_t)s.row_words;
+  const mmp_decision_in &d = c.d;
+  const uint32_t so = (uint32_t)c.slot * NW;
+  const uint32_t *CX = (s.any_rs ? s.candx : s.cand) + so;
+  const uint32_t *P = s.pref + so;
+  const bool favour_self = (d.flags & MMP_DF_FAVOUR_SELF) != 0;
+  const int32_t self_rank = c.self_rank;
+  uint32_t w0 = 0;
+  W fw = co.wmap(w0, NW, [&](uint32_t wi) { return CX[wi] & ~erow[wi]; });
+  const uint32_t b = co.wfirst(w0, fw);
+  if (b == NONE_RANK) return false;  // deeper in the row, or empty (replicaset retry): general routine
+  if ((b >> 5) >= 16) {              // re-centre so that the window starts at best's word
+    w0 = b >> 5;
+    fw = co.wmap(w0, NW, [&](uint32_t wi) { return CX[wi] & ~erow[wi]; });
+  }
+  const uint32_t wend = (w0 + 32u < NW ? w0 + 32u : NW) * 32u;  // ranks below wend are inside the window
+  const bool to_row_end = w0 + 32u >= NW;
+  const RankRow rb = s.rows[b];
+  bool us = rb.idx == d.self;
+  const FreshRow fr = c.fr;
+  int64_t best_rem = us ? fr.rem : rb.rem, best_lru = us ? fr.lru : rb.lru;
+  int32_t best_count = us ? fr.count : rb.count, best_rpm = us ? fr.rpm : rb.rpm, best_idx = rb.idx;
+  uint32_t best_rank = b;
+  if (best_rem < s.min_space) return false;  // best full: general routine
+  (void)best_lru;
+  const bool has_pref = s.has_pref[c.slot] != 0;
+  W pw = co.wmap(w0, NW, [&](uint32_t wi) { return has_pref ? P[wi] : 0u; });
+  bool simple = !has_pref || ((co.wget(w0, pw, b >> 5) >> (b & 31)) & 1u);
+  uint32_t lo = b, hi = NONE_RANK;
+  bool use_pref = has_pref && simple;
+  int32_t flags = 0;
+  if (!simple) {
+    // non-simple (a) MM:4828-4852
+    const W fullw = co.wmap(w0, NW, [&](uint32_t wi) { return s.full[wi]; });
+    const W fa = co.wmap1(w0, fw, [&](uint32_t wi, uint32_t f) { return f & mask_above(wi * 32u, b); });
+    const uint32_t p1 = co.wfirst(w0, co.wmap2(w0, fa, pw, [](uint32_t, uint32_t f, uint32_t p) { return f & p; }));
+    const uint32_t f1 = co.wfirst(w0, co.wmap2(w0, co.wmap2(w0, fa, pw, [](uint32_t, uint32_t f, uint32_t p) { return f & ~p; }), fullw,
+                                               [](uint32_t, uint32_t f, uint32_t fl) { return f & fl; }));
+    if (p1 == NONE_RANK && f1 == NONE_RANK && !to_row_end) return false;
+    if (p1 < f1) {
+      const RankRow rp = s.rows[p1];
+      best_rank = p1; best_idx = rp.idx; best_rem = rp.rem; best_count = rp.count; best_rpm = rp.rpm;
+      us = rp.idx == d.self;
+      lo = p1; use_pref = true;
+    } else hi = f1;
+    simple = true;
+  }
+  flags |= MMP_TF_SIMPLE | MMP_TF_FAST;
+  if (us && favour_self) {
+    o.target = MMP_TARGET_SELF; o.n_candidates = 0; o.best = best_idx; o.best_rank = (int32_t)best_rank; o.n_remaining = 0;
+    o.pick_index = 0; o.flags = flags | MMP_TF_FAVOUR_EXIT; o.cut_rank = (int32_t)NONE_RANK;
+    return true;
+  }
+  // S inside the window
+  const W sx = co.wmap2(w0, fw, pw, [&](uint32_t wi, uint32_t f, uint32_t p) {
+    uint32_t m = f & mask_above(wi * 32u, lo) & mask_below(wi * 32u, hi);
+    return use_pref ? (m & p) : m;
+  });
+  const bool s_in_window = hi != NONE_RANK ? hi <= wend : to_row_end;  // does the window hold all of S?
+  bool self_in_s = false;
+  if (self_rank >= 0 && (uint32_t)self_rank > lo && (uint32_t)self_rank < hi) {
+    const uint32_t sw_ = (uint32_t)self_rank >> 5, sb_ = 1u << (self_rank & 31);
+    self_in_s = (CX[sw_] & ~erow[sw_] & sb_) != 0 && (!use_pref || (P[sw_] & sb_) != 0);
+  }
+  const int64_t q = best_rem >> 2;
+  const bool c_self = fr.rem < s.min_space || fr.rem < q;
+  bool self_viol = rb.rem < s.min_space || rb.rem < q;
+  const int32_t thr = jaddi(best_count, best_count >> 2);
+  auto cv = [&](int32_t cnt) { return cnt >= 10 && cnt > thr; };
+  if (self_in_s && cv(s.rows[self_rank].count)) self_viol = true;
+  uint32_t cut_others;
+  if (c_self) {
+    const uint32_t sw_ = self_rank >= 0 ? (uint32_t)self_rank >> 5 : NONE_RANK, sb_ = 1u << (self_rank & 31);
+    cut_others = co.wfirst(w0, co.wmap1(w0, sx, [&](uint32_t wi, uint32_t x) { return (self_in_s && wi == sw_) ? (x & ~sb_) : x; }));
+  } else {
+    // classification of the window's words from the count summaries, then exact evaluation of mixed words in order
+    const W cls = co.wmap1(w0, sx, [&](uint32_t wi, uint32_t x) -> uint32_t {
+      if (!x) return 0u;
+      const WordSumI m = s.csum[wi];
+      return !cv(m.hi) ? 0u : (cv(m.lo) ? 1u : 2u);
+    });
+    uint32_t Amin = co.wfirst(w0, co.wmap2(w0, sx, cls, [](uint32_t, uint32_t x, uint32_t cl) { return cl == 1u ? x : 0u; }));
+    W mixed = co.wmap2(w0, sx, cls, [](uint32_t, uint32_t x, uint32_t cl) { return cl == 2u ? x : 0u; });
+    uint32_t Mmin = co.wfirst(w0, mixed);
+    while (Mmin != NONE_RANK && Mmin < Amin) {
+      const uint32_t mw = Mmin >> 5;
+      const uint32_t vm = co.eval_word(mw, s.n_ranks, [&](uint32_t r) { return cv(s.rows[r].count); }) & co.wget(w0, mixed, mw);
+      if (vm) { const uint32_t r = mw * 32u + (uint32_t)ffs32(vm); if (r < Amin) Amin = r; break; }
+      mixed = co.wmap1(w0, mixed, [&](uint32_t wi, uint32_t x) { return wi == mw ? 0u : x; });
+      Mmin = co.wfirst(w0, mixed);
+    }
+    cut_others = Amin;
+  }
+  if (cut_others == NONE_RANK && !s_in_window) return false;  // the walk continues past the window
+  const uint32_t cut_self = (self_in_s && self_viol) ? (uint32_t)self_rank : NONE_RANK;
+  if (cut_self != NONE_RANK && cut_self >= wend && cut_others == NONE_RANK && !s_in_window) return false;
+  const uint32_t cut = cut_others < cut_self ? cut_others : cut_self;
+  if (cut == NONE_RANK ? !s_in_window : cut > wend) return false;
+  const bool self_in_sl = self_in_s && (uint32_t)self_rank < cut;
+  if (favour_self && self_in_sl) {
+    o.target = MMP_TARGET_SELF; o.n_candidates = 0; o.best = best_idx; o.best_rank = (int32_t)best_rank; o.n_remaining = 0;
+    o.pick_index = 0; o.flags = flags | MMP_TF_FAVOUR_EXIT; o.cut_rank = (int32_t)cut;
+    return true;
+  }
+  const W sl = co.wmap1(w0, sx, [&](uint32_t wi, uint32_t x) { return x & mask_below(wi * 32u, cut); });
+  const int32_t n_in = (int32_t)co.wpopc(sl);
+  const int32_t n_others = n_in - (self_in_sl ? 1 : 0);
+  const int32_t ccount = 1 + n_in;
+  bool keep_best = true, keep_others = true, keep_self = true;
+  int32_t remaining = ccount;
+  uint32_t index = 0;
+  if (ccount > 1) {
+    const int64_t ago = age_of(c.last_used, now);
+    if (ago < 432000000LL) {
+      int32_t mn = best_rpm;
+      if (n_others > 0 && fr.rpm < mn) mn = fr.rpm;
+      if (self_in_sl && rb.rpm < mn) mn = rb.rpm;
+      RpmFilter rf; rf.init(mn, ago);
+      keep_best = !rf.drop(best_rpm); keep_others = !rf.drop(fr.rpm); keep_self = !rf.drop(rb.rpm);
+      remaining = (keep_best ? 1 : 0) + (keep_others ? n_others : 0) + ((self_in_sl && keep_self) ? 1 : 0);
+    }
+    index = remaining == 1 ? 0u : hash_index(seed, decision_id, (uint32_t)remaining);
+  }
+  flags |= (keep_best ? MMP_TF_KEEP_BEST : 0) | (keep_others ? MMP_TF_KEEP_OTHERS : 0) | (keep_self ? MMP_TF_KEEP_SELF : 0);
+  uint32_t chosen_rank;
+  uint32_t kth = index;
+  if (keep_best && kth == 0) chosen_rank = best_rank;
+  else {
+    if (keep_best) kth--;
+    if (!keep_others) chosen_rank = (uint32_t)self_rank;
+    else {
+      const uint32_t sw_ = self_rank >= 0 ? (uint32_t)self_rank >> 5 : NONE_RANK, sb_ = 1u << (self_rank & 31);
+      const bool drop_self = self_in_sl && !keep_self;
+      chosen_rank = co.wselect(w0, co.wmap1(w0, sl, [&](uint32_t wi, uint32_t x) { return (drop_self && wi == sw_) ? (x & ~sb_) : x; }), kth);
+    }
+  }
+  const int32_t cidx = chosen_rank == best_rank ? best_idx : s.rows[chosen_rank].idx;
+  o.target = (!favour_self && cidx == d.self) ? MMP_TARGET_SELF : cidx;
+  o.n_candidates = ccount; o.best = best_idx; o.best_rank = (int32_t)best_rank; o.n_remaining = remaining;
+  o.pick_index = (int32_t)index; o.flags = flags; o.cut_rank = (int32_t)cut;
+  return true;
 }
 
 // One getNext.  erow: this decision's exclusion row, readable by every lane (shared memory on the GPU) until the

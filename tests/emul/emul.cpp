@@ -110,8 +110,9 @@ int32_t mmp_place_batch_trace(mmp_fleet *f, const mmp_decision_in *in, int32_t n
     DecisionCtx cx;
     prepare_ctx(v, in[i], fr.data(), n_fresh, cx);
     const uint32_t *erow = v.excl + (size_t)(cx.slot >= 0 ? in[i].model : 0) * v.row_words;
-    decide_ctx<Coop1>(v, cx, erow, extra, now_ms, seed, (uint64_t)i, co, o,
-                      cand_mask ? cand_mask + (size_t)i * 2 * v.row_words : nullptr);
+    if (cand_mask || !decide_fast<Coop1>(v, cx, erow, now_ms, seed, (uint64_t)i, co, o))
+      decide_ctx<Coop1>(v, cx, erow, extra, now_ms, seed, (uint64_t)i, co, o,
+                        cand_mask ? cand_mask + (size_t)i * 2 * v.row_words : nullptr);
     out[i].target = o.target; out[i].n_candidates = o.n_candidates;
     if (trace) {
       trace[i].best = o.best; trace[i].n_remaining = o.n_remaining; trace[i].pick_index = o.pick_index; trace[i].flags = o.flags;

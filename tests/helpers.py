@@ -105,6 +105,13 @@ def compare_decisions(fl: SynthFleet, sd: SynthDecisions, oracle: ob.OracleFleet
     # the untraced entry point runs the production kernel (k_place_ring on the GPU): same answers
     out_fast = solver.place_batch(sd.dec, fl.now_ms, seed, fresh=fresh, extra=extra)
     assert np.array_equal(out_fast, out), _first_diff(out_fast["target"], out["target"], sd, ores, out_fast, tr)
+    # traced but without masks: the one-window fast path answers whatever it can resolve; same trace fields
+    out2, tr2, _ = solver.place_batch(sd.dec, fl.now_ms, seed, fresh=fresh, extra=extra, trace=True, masks=False)
+    assert np.array_equal(out2, out), _first_diff(out2["target"], out["target"], sd, ores, out2, tr2)
+    for k in ("best", "n_remaining", "pick_index", "cut_rank", "best_rank"):
+        assert np.array_equal(tr2[k], tr[k]), (k, _first_diff(tr2[k], tr[k], sd, ores, out2, tr2))
+    assert np.array_equal(tr2["flags"] & 255, tr["flags"] & 255), _first_diff(tr2["flags"] & 255, tr["flags"] & 255, sd, ores, out2, tr2)
+    compare_decisions.fast_fraction = float(np.mean((tr2["flags"] & 256) != 0))
     assert np.array_equal(out["target"], ores["target"]), _first_diff(out["target"], ores["target"], sd, ores, out, tr)
     assert np.array_equal(out["n_candidates"], ores["n_candidates"]), _first_diff(out["n_candidates"], ores["n_candidates"], sd, ores, out, tr)
     has = ores["n_candidates"] > 0
