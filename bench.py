@@ -202,8 +202,8 @@ def main():
     fl = make_fleet(CONFIG, N_MODELS, N_INSTANCES, SEED)
     sd_all = make_decisions(fl, N_MODELS, SEED, sweep=True, plain=True)
     # model-shard of this rank (whole registry when world == 1)
-    lo = rank * N_MODELS // world
-    hi = (rank + 1) * N_MODELS // world
+    from modelmesh_b200.sharding import shard_range
+    lo, hi = shard_range(rank, world, N_MODELS)
     B = hi - lo
     solver = Fleet(fl.min_space_units, fl.min_churn_age_ms, fl.default_model_size_units, fl.n_instances, N_MODELS,
                    device=local_rank, lib=lib)

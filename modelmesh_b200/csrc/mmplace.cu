@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_place(const SnapshotView s, cons
   const int nb = (n + 31) >> 5;
   const int gw = blockIdx.x * WARPS + wib, nw = gridDim.x * WARPS;
   Coop32 co;
+  CoopTile<16> co16;
   uint32_t use = 0;  // ring position of the next row to consume (warp-uniform)
   auto prep = [&](int batch, DecisionCtx *dst) {  // lane j stages the context of decision j of `batch`
     const int i = batch * 32 + lane;
@@ -170,35 +171,76 @@ __global__ void __launch_bounds__(WARPS * 32) k_place(const SnapshotView s, cons
     __syncwarp();
     const int count = min(32, n - b * 32);
     mmp_decision_out mine{MMP_TARGET_NONE, 0};
-    for (int j = 0; j < count; j++) {
-      const uint32_t slot = use % (uint32_t)K, parity = (use / (uint32_t)K) & 1u;
-      while (!mbar_try_wait(&bars[slot], parity)) {}
-      const uint32_t *erow = rows_s + (size_t)slot * RW;
-      const int gi = b * 32 + j;
-      DecideOut o;
-      if (cand || !decide_fast(s, cc[j], erow, now, seed, id_base + (uint64_t)gi, co, o))
-        decide_ctx(s, cc[j], erow, extra, now, seed, id_base + (uint64_t)gi, co, o, cand ? cand + (size_t)gi * 2 * RW : nullptr);
-      if (lane == j) { mine.target = o.target; mine.n_candidates = o.n_candidates; }
-      if (tr && lane == 0) {
-        mmp_decision_trace t;
-        t.best = o.best; t.n_remaining = o.n_remaining; t.pick_index = o.pick_index; t.flags = o.flags;
-        t.cut_rank = o.cut_rank; t.best_rank = o.best_rank; t.reserved[0] = t.reserved[1] = 0;
-        tr[gi] = t;
+    int jbase = 0;
+    auto refill = [&](int jdone) {  // lane 0: the row of decision jdone has been consumed; fetch the one K positions ahead
+      const int t = jdone + K;
+      int nm = 0;
+      bool have = false;
+      if (t < count) { nm = cc[t].d.model; have = true; }
+      else if (t - count < 32 && cnext[t - count].slot != -2) { nm = cnext[t - count].d.model; have = true; }
+      if (have) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(nm, use + (uint32_t)(jdone - jbase) + (uint32_t)K);
       }
-      // the row has been consumed: refill this ring slot with the row of the decision K positions ahead
-      const int t = j + K;
-      __syncwarp();
-      if (lane == 0) {
-        int nm = 0;
-        bool have = false;
-        if (t < count) { nm = cc[t].d.model; have = true; }
-        else if (t - count < 32 && cnext[t - count].slot != -2) { nm = cnext[t - count].d.model; have = true; }
-        if (have) {
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          issue(nm, use + (uint32_t)K);
+    };
+    if (!tr && !cand) {
+      // ---- two decisions per warp: each half-warp resolves one out of a 16-word window (CoopTile<16>); whatever
+      // a half cannot resolve inside its window is redone warp-wide by the general routine ----
+      const int half = lane >> 4;
+      for (int jp = 0; jp < count; jp += 2) {
+        jbase = jp;
+        const int j = jp + half;
+        const bool valid = j < count;
+        const uint32_t myuse = use + (uint32_t)half;
+        const uint32_t slot = myuse % (uint32_t)K, parity = (myuse / (uint32_t)K) & 1u;
+        if (valid) { while (!mbar_try_wait(&bars[slot], parity)) {} }
+        DecideOut o;
+        o.target = MMP_TARGET_NONE; o.n_candidates = 0;
+        bool resolved = false;
+        if (valid) resolved = decide_fast<false>(s, cc[j], rows_s + (size_t)slot * RW, now, seed, id_base + (uint64_t)(b * 32 + j), co16, o);
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int need = __shfl_sync(0xffffffffu, (valid && !resolved) ? 1 : 0, h * 16);
+          if (need) {
+            const int jj = jp + h;
+            const uint32_t sl2 = (use + (uint32_t)h) % (uint32_t)K;
+            DecideOut o2;
+            if (!decide_fast<false>(s, cc[jj], rows_s + (size_t)sl2 * RW, now, seed, id_base + (uint64_t)(b * 32 + jj), co, o2))
+              decide_ctx(s, cc[jj], rows_s + (size_t)sl2 * RW, extra, now, seed, id_base + (uint64_t)(b * 32 + jj), co, o2, nullptr);
+            if (half == h) { o.target = o2.target; o.n_candidates = o2.n_candidates; }
+          }
         }
+        const int t0 = __shfl_sync(0xffffffffu, o.target, 0), c0 = __shfl_sync(0xffffffffu, o.n_candidates, 0);
+        const int t1 = __shfl_sync(0xffffffffu, o.target, 16), c1 = __shfl_sync(0xffffffffu, o.n_candidates, 16);
+        if (lane == jp) { mine.target = t0; mine.n_candidates = c0; }
+        if (lane == jp + 1) { mine.target = t1; mine.n_candidates = c1; }
+        __syncwarp();
+        const int npair = (jp + 1 < count) ? 2 : 1;
+        if (lane == 0) { refill(jp); if (npair == 2) refill(jp + 1); }
+        use += (uint32_t)npair;
       }
-      use++;
+    } else {
+      for (int j = 0; j < count; j++) {
+        jbase = j;
+        const uint32_t slot = use % (uint32_t)K, parity = (use / (uint32_t)K) & 1u;
+        while (!mbar_try_wait(&bars[slot], parity)) {}
+        const uint32_t *erow = rows_s + (size_t)slot * RW;
+        const int gi = b * 32 + j;
+        DecideOut o;
+        if (cand || !decide_fast<true>(s, cc[j], erow, now, seed, id_base + (uint64_t)gi, co, o))
+          decide_ctx(s, cc[j], erow, extra, now, seed, id_base + (uint64_t)gi, co, o, cand ? cand + (size_t)gi * 2 * RW : nullptr);
+        if (lane == j) { mine.target = o.target; mine.n_candidates = o.n_candidates; }
+        if (tr && lane == 0) {
+          mmp_decision_trace t;
+          t.best = o.best; t.n_remaining = o.n_remaining; t.pick_index = o.pick_index; t.flags = o.flags;
+          t.cut_rank = o.cut_rank; t.best_rank = o.best_rank; t.reserved[0] = t.reserved[1] = 0;
+          tr[gi] = t;
+        }
+        __syncwarp();
+        if (lane == 0) refill(j);
+        use++;
+      }
     }
     if (lane < count) out[b * 32 + lane] = mine;
     b = bn;

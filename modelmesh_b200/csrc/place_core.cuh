@@ -136,9 +136,12 @@ MMP_HD uint32_t shl_ones(int32_t t) {
 MMP_HD uint32_t mask_above(uint32_t rank_base, uint32_t lo) { return shl_ones((int32_t)lo - (int32_t)rank_base + 1); }
 MMP_HD uint32_t mask_below(uint32_t rank_base, uint32_t hi) { return ~shl_ones((int32_t)hi - (int32_t)rank_base); }
 
-// ---- the single-lane cooperative shape (CPU harness): a "window" is one word ----
-struct Coop1 {
+// ---- the single-lane cooperative shape (CPU harness).  Scans step one word at a time (L = 1); the fast path's
+// window values are arrays of WN words (WN = 32 or 16, the two tile widths the GPU kernel uses). ----
+template <int WN_>
+struct CoopHost {
   static constexpr uint32_t L = 1;
+  static constexpr uint32_t WN = WN_;
   MMP_HD uint32_t lane() const { return 0; }
   MMP_HD uint32_t rmin(uint32_t x) const { return x; }
   MMP_HD uint32_t rsum(uint32_t x) const { return x; }
@@ -154,36 +157,36 @@ struct Coop1 {
     }
     return m;
   }
-  // ---- 32-word window values (the GPU keeps one word per lane; here the 32 words are an array) ----
-  struct W { uint32_t v[32]; };
+  // ---- window values (the GPU keeps one word per lane of the tile; here the WN words are an array) ----
+  struct W { uint32_t v[WN_]; };
   template <class F> MMP_HD W wmap(uint32_t w0, uint32_t nw, F &&f) const {  // word wi = w0 + i, zero past the row
     W r;
-    for (uint32_t i = 0; i < 32; i++) r.v[i] = (w0 + i < nw) ? f(w0 + i) : 0u;
+    for (uint32_t i = 0; i < WN; i++) r.v[i] = (w0 + i < nw) ? f(w0 + i) : 0u;
     return r;
   }
   template <class F> MMP_HD W wmap1(uint32_t w0, const W &a, F &&f) const {
     W r;
-    for (uint32_t i = 0; i < 32; i++) r.v[i] = f(w0 + i, a.v[i]);
+    for (uint32_t i = 0; i < WN; i++) r.v[i] = f(w0 + i, a.v[i]);
     return r;
   }
   template <class F> MMP_HD W wmap2(uint32_t w0, const W &a, const W &b, F &&f) const {
     W r;
-    for (uint32_t i = 0; i < 32; i++) r.v[i] = f(w0 + i, a.v[i], b.v[i]);
+    for (uint32_t i = 0; i < WN; i++) r.v[i] = f(w0 + i, a.v[i], b.v[i]);
     return r;
   }
   MMP_HD uint32_t wfirst(uint32_t w0, const W &x) const {  // rank of the first set bit in the window
-    for (uint32_t i = 0; i < 32; i++) if (x.v[i]) return (w0 + i) * 32u + (uint32_t)ffs32(x.v[i]);
+    for (uint32_t i = 0; i < WN; i++) if (x.v[i]) return (w0 + i) * 32u + (uint32_t)ffs32(x.v[i]);
     return NONE_RANK;
   }
   template <class F> MMP_HD uint32_t wmin(uint32_t w0, const W &x, F &&f) const {  // min over words of f(wi, word)
-    uint32_t m = NONE_RANK;
-    for (uint32_t i = 0; i < 32; i++) { uint32_t t = f(w0 + i, x.v[i]); if (t < m) m = t; }
+    uint32_t m = 0xffffffffu;
+    for (uint32_t i = 0; i < WN; i++) { uint32_t t = f(w0 + i, x.v[i]); if (t < m) m = t; }
     return m;
   }
-  MMP_HD uint32_t wpopc(const W &x) const { uint32_t c = 0; for (uint32_t i = 0; i < 32; i++) c += (uint32_t)popc32(x.v[i]); return c; }
+  MMP_HD uint32_t wpopc(const W &x) const { uint32_t c = 0; for (uint32_t i = 0; i < WN; i++) c += (uint32_t)popc32(x.v[i]); return c; }
   MMP_HD uint32_t wget(uint32_t w0, const W &x, uint32_t wi) const { return x.v[wi - w0]; }
   MMP_HD uint32_t wselect(uint32_t w0, const W &x, uint32_t kth) const {  // rank of the kth set bit; kth < wpopc(x)
-    for (uint32_t i = 0; i < 32; i++) {
+    for (uint32_t i = 0; i < WN; i++) {
       uint32_t c = (uint32_t)popc32(x.v[i]);
       if (kth < c) return (w0 + i) * 32u + (uint32_t)nth_bit(x.v[i], kth);
       kth -= c;
@@ -191,34 +194,51 @@ struct Coop1 {
     return NONE_RANK;
   }
 };
+typedef CoopHost<32> Coop1;
 
 #if defined(__CUDACC__)
-// ---- the warp cooperative shape: a window is 32 consecutive words of the row, one per lane ----
-struct Coop32 {
-  static constexpr uint32_t L = 32;
-  uint32_t lane_;
-  MMP_D Coop32() : lane_(threadIdx.x & 31) {}
+// ---- the cooperative shape on the GPU: a tile of T lanes (T = 32: one decision per warp; T = 16: two decisions per
+// warp, each half-warp with its own 16-word window).  A window is T consecutive words of the row, one per lane. ----
+template <int T>
+struct CoopTile {
+  static constexpr uint32_t L = T;
+  static constexpr uint32_t WN = T;
+  uint32_t lane_;  // lane within the tile
+  uint32_t mask_;  // member mask of the tile
+  uint32_t base_;  // first warp lane of the tile
+  MMP_D CoopTile() {
+    const uint32_t wl = threadIdx.x & 31;
+    lane_ = wl & (T - 1);
+    base_ = wl & ~(uint32_t)(T - 1);
+    mask_ = T == 32 ? 0xffffffffu : (((1u << T) - 1u) << base_);
+  }
   MMP_D uint32_t lane() const { return lane_; }
-  MMP_D uint32_t rmin(uint32_t x) const { return __reduce_min_sync(0xffffffffu, x); }
-  MMP_D uint32_t rsum(uint32_t x) const { return __reduce_add_sync(0xffffffffu, x); }
-  MMP_D int32_t rmin_i(int32_t x) const { return __reduce_min_sync(0xffffffffu, x); }
-  MMP_D bool rany(bool p) const { return __any_sync(0xffffffffu, p) != 0; }
-  MMP_D uint32_t shfl(uint32_t x, uint32_t src) const { return __shfl_sync(0xffffffffu, x, (int)src); }
+  MMP_D uint32_t rmin(uint32_t x) const { return __reduce_min_sync(mask_, x); }
+  MMP_D uint32_t rsum(uint32_t x) const { return __reduce_add_sync(mask_, x); }
+  MMP_D int32_t rmin_i(int32_t x) const { return __reduce_min_sync(mask_, x); }
+  MMP_D bool rany(bool p) const { return (__ballot_sync(mask_, p) & mask_) != 0; }
+  MMP_D uint32_t shfl(uint32_t x, uint32_t src) const { return __shfl_sync(mask_, x, (int)src, T); }
   MMP_D uint32_t exscan(uint32_t x) const {
     uint32_t v = x;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+    for (int o = 1; o < T; o <<= 1) {
+      uint32_t t = __shfl_up_sync(mask_, v, o, T);
       if (lane_ >= (uint32_t)o) v += t;
     }
     return v - x;
   }
+  // exact 32-rank evaluation of one word by the tile (T = 16: two ranks per lane)
   template <class F> MMP_D uint32_t eval_word(uint32_t wi, int32_t n_ranks, F &&f) const {
-    uint32_t r = wi * 32 + lane_;
-    bool p = (int32_t)r < n_ranks && f(r);
-    return __ballot_sync(0xffffffffu, p);
+    uint32_t m = 0;
+#pragma unroll
+    for (int h = 0; h < 32 / T; h++) {
+      const uint32_t r = wi * 32 + h * T + lane_;
+      const bool p = (int32_t)r < n_ranks && f(r);
+      m |= ((__ballot_sync(mask_, p) >> base_) & (T == 32 ? 0xffffffffu : ((1u << T) - 1u))) << (h * T);
+    }
+    return m;
   }
-  // ---- 32-word window values: one word per lane, in a register ----
+  // ---- window values: one word per lane, in a register ----
   typedef uint32_t W;
   template <class F> MMP_D W wmap(uint32_t w0, uint32_t nw, F &&f) const { uint32_t wi = w0 + lane_; return wi < nw ? f(wi) : 0u; }
   template <class F> MMP_D W wmap1(uint32_t w0, W a, F &&f) const { return f(w0 + lane_, a); }
@@ -226,12 +246,13 @@ struct Coop32 {
   MMP_D uint32_t wfirst(uint32_t w0, W x) const { return rmin(x ? (w0 + lane_) * 32u + (uint32_t)ffs32(x) : NONE_RANK); }
   template <class F> MMP_D uint32_t wmin(uint32_t w0, W x, F &&f) const { return rmin(f(w0 + lane_, x)); }
   MMP_D uint32_t wpopc(W x) const { return rsum((uint32_t)popc32(x)); }
-  MMP_D uint32_t wget(uint32_t w0, W x, uint32_t wi) const { return __shfl_sync(0xffffffffu, x, (int)(wi - w0)); }
+  MMP_D uint32_t wget(uint32_t w0, W x, uint32_t wi) const { return __shfl_sync(mask_, x, (int)(wi - w0), T); }
   MMP_D uint32_t wselect(uint32_t w0, W x, uint32_t kth) const {
     const uint32_t c = (uint32_t)popc32(x), pre = exscan(c);
     return rmin((kth >= pre && kth < pre + c) ? (w0 + lane_) * 32u + (uint32_t)nth_bit(x, kth - pre) : NONE_RANK);
   }
 };
+typedef CoopTile<32> Coop32;
 #endif
 
 // ---- window scans.  A row is visited C::L words at a time starting at the word that holds the lower bound; `word(wi)`
@@ -310,8 +331,10 @@ struct RpmFilter {
   MMP_HD void init(int32_t min_rpm, int64_t last_used_ago) {
     ago = last_used_ago;
     min_load = min_rpm > 100 ? min_rpm : 100;                       // Math.max(100, instReqLoad.min())
-    m11 = jd2i(jmul_d(1.1, (double)min_load));
-    m15 = jd2i(jmul_d(1.5, (double)min_load));
+    if (ago < 5000) {  // the 1.1x / 1.5x thresholds are only consulted for a model used in the last five seconds
+      m11 = jd2i(jmul_d(1.1, (double)min_load));
+      m15 = jd2i(jmul_d(1.5, (double)min_load));
+    } else m11 = m15 = 2147483647;
   }
   MMP_HD bool drop(int32_t rpm) const {
     return rpm >= 100 && ((ago < -1000 && rpm > m11) || (ago < 5000 && rpm > m15) ||
@@ -326,8 +349,10 @@ struct DecisionCtx {
   int64_t last_used;
   FreshRow fr;         // the caller's fresh record (MM:5369), or its published row with rpm 0 (N7)
   int32_t self_rank;
-  int32_t slot;        // type-constraint mask slot, -1 = malformed decision
+  int32_t slot;        // type-constraint mask slot | (has_pref << 16); -1 = malformed decision, -2 = absent
 };
+MMP_HD int ctx_slot(const DecisionCtx &c) { return c.slot & 0xffff; }
+MMP_HD bool ctx_has_pref(const DecisionCtx &c) { return (c.slot >> 16) & 1; }
 
 MMP_HD void prepare_ctx(const SnapshotView &s, const mmp_decision_in &d, const FreshRow *fresh_tab, int32_t n_fresh,
                         DecisionCtx &c) {
@@ -341,24 +366,26 @@ MMP_HD void prepare_ctx(const SnapshotView &s, const mmp_decision_in &d, const F
   if (d.fresh >= 0 && d.fresh < n_fresh) c.fr = fresh_tab[d.fresh];
   else if (c.self_rank >= 0) { const RankRow sr = s.rows[c.self_rank]; c.fr.lru = sr.lru; c.fr.rem = sr.rem; c.fr.count = sr.count; c.fr.rpm = 0; }
   else return;
-  c.slot = s.type_slot[tid];
+  const int sl = s.type_slot[tid];
+  c.slot = sl | ((s.has_pref[sl] ? 1 : 0) << 16);
 }
 
 #define MMP_TF_FAST 256  // trace flag (not part of the ABI): resolved by the one-window fast path
 
-// The common case of getNext resolved inside ONE 32-word window (1 024 ranks) whose words stay in registers: best, the
-// non-simple (a) probe, the cut, the shortlist count and the pick are all window reductions (~250 warp instructions).
-// Returns false -- nothing written -- whenever the answer is not provably inside the window or the decision takes a
-// path handled only by the general routine (extra excludes, replicaset retry, best full, trace masks); the caller then
-// runs decide_ctx.  Same semantics, same quirks; tests compare both against the oracle.
-template <class C>
+// The common case of getNext resolved inside ONE window of C::WN words (32 words = 1 024 ranks for a warp-wide tile,
+// 16 words for a half-warp tile) whose words stay in registers: best, the non-simple (a) probe, the cut, the shortlist
+// count and the pick are all window reductions.  Returns false -- nothing written -- whenever the answer is not
+// provably inside the window or the decision takes a path handled only by the general routine (extra excludes,
+// replicaset retry, best full); the caller then runs decide_ctx.  Same semantics, same quirks; the tests compare both
+// against the oracle.  TRACE = false skips the outputs only the trace needs.
+template <bool TRACE, class C>
 MMP_HD bool decide_fast(const SnapshotView &s, const DecisionCtx &c, const uint32_t *erow, int64_t now, uint64_t seed,
                         uint64_t decision_id, const C &co, DecideOut &o) {
   typedef typename C::W W;
   if (c.slot < 0 || c.d.extra_n != 0) return false;
   const uint32_t NW = (uint32_t)s.row_words;
   const mmp_decision_in &d = c.d;
-  const uint32_t so = (uint32_t)c.slot * NW;
+  const uint32_t so = (uint32_t)ctx_slot(c) * NW;
   const uint32_t *CX = (s.any_rs ? s.candx : s.cand) + so;
   const uint32_t *P = s.pref + so;
   const bool favour_self = (d.flags & MMP_DF_FAVOUR_SELF) != 0;
@@ -367,46 +394,41 @@ MMP_HD bool decide_fast(const SnapshotView &s, const DecisionCtx &c, const uint3
   W fw = co.wmap(w0, NW, [&](uint32_t wi) { return CX[wi] & ~erow[wi]; });
   const uint32_t b = co.wfirst(w0, fw);
   if (b == NONE_RANK) return false;  // deeper in the row, or empty (replicaset retry): general routine
-  if ((b >> 5) >= 16) {              // re-centre so that the window starts at best's word
+  if ((b >> 5) >= C::WN / 2) {       // re-centre so that the window starts at best's word
     w0 = b >> 5;
     fw = co.wmap(w0, NW, [&](uint32_t wi) { return CX[wi] & ~erow[wi]; });
   }
-  const uint32_t wend = (w0 + 32u < NW ? w0 + 32u : NW) * 32u;  // ranks below wend are inside the window
-  const bool to_row_end = w0 + 32u >= NW;
+  const uint32_t wend = (w0 + C::WN < NW ? w0 + C::WN : NW) * 32u;  // ranks below wend are inside the window
+  const bool to_row_end = w0 + C::WN >= NW;
   const RankRow rb = s.rows[b];
   bool us = rb.idx == d.self;
   const FreshRow fr = c.fr;
-  int64_t best_rem = us ? fr.rem : rb.rem, best_lru = us ? fr.lru : rb.lru;
+  int64_t best_rem = us ? fr.rem : rb.rem;
   int32_t best_count = us ? fr.count : rb.count, best_rpm = us ? fr.rpm : rb.rpm, best_idx = rb.idx;
   uint32_t best_rank = b;
   if (best_rem < s.min_space) return false;  // best full: general routine
-  (void)best_lru;
-  const bool has_pref = s.has_pref[c.slot] != 0;
+  const bool has_pref = ctx_has_pref(c);
   W pw = co.wmap(w0, NW, [&](uint32_t wi) { return has_pref ? P[wi] : 0u; });
   bool simple = !has_pref || ((co.wget(w0, pw, b >> 5) >> (b & 31)) & 1u);
   uint32_t lo = b, hi = NONE_RANK;
   bool use_pref = has_pref && simple;
-  int32_t flags = 0;
   if (!simple) {
-    // non-simple (a) MM:4828-4852
-    const W fullw = co.wmap(w0, NW, [&](uint32_t wi) { return s.full[wi]; });
-    const W fa = co.wmap1(w0, fw, [&](uint32_t wi, uint32_t f) { return f & mask_above(wi * 32u, b); });
-    const uint32_t p1 = co.wfirst(w0, co.wmap2(w0, fa, pw, [](uint32_t, uint32_t f, uint32_t p) { return f & p; }));
-    const uint32_t f1 = co.wfirst(w0, co.wmap2(w0, co.wmap2(w0, fa, pw, [](uint32_t, uint32_t f, uint32_t p) { return f & ~p; }), fullw,
-                                               [](uint32_t, uint32_t f, uint32_t fl) { return f & fl; }));
-    if (p1 == NONE_RANK && f1 == NONE_RANK && !to_row_end) return false;
-    if (p1 < f1) {
-      const RankRow rp = s.rows[p1];
-      best_rank = p1; best_idx = rp.idx; best_rem = rp.rem; best_count = rp.count; best_rpm = rp.rpm;
+    // non-simple (a) MM:4828-4852: the first later entry that is preferred or full decides: preferred -> new best
+    // (even when it is also full, the preference test comes first), full and not preferred -> the replay stops there
+    const W u = co.wmap2(w0, fw, pw, [&](uint32_t wi, uint32_t f, uint32_t p) { return f & mask_above(wi * 32u, b) & (p | s.full[wi]); });
+    const uint32_t r1 = co.wfirst(w0, u);
+    if (r1 == NONE_RANK) { if (!to_row_end) return false; }
+    else if ((co.wget(w0, pw, r1 >> 5) >> (r1 & 31)) & 1u) {
+      const RankRow rp = s.rows[r1];
+      best_rank = r1; best_idx = rp.idx; best_rem = rp.rem; best_count = rp.count; best_rpm = rp.rpm;
       us = rp.idx == d.self;
-      lo = p1; use_pref = true;
-    } else hi = f1;
-    simple = true;
+      lo = r1; use_pref = true;
+    } else hi = r1;
   }
-  flags |= MMP_TF_SIMPLE | MMP_TF_FAST;
   if (us && favour_self) {
-    o.target = MMP_TARGET_SELF; o.n_candidates = 0; o.best = best_idx; o.best_rank = (int32_t)best_rank; o.n_remaining = 0;
-    o.pick_index = 0; o.flags = flags | MMP_TF_FAVOUR_EXIT; o.cut_rank = (int32_t)NONE_RANK;
+    o.target = MMP_TARGET_SELF; o.n_candidates = 0;
+    if (TRACE) { o.best = best_idx; o.best_rank = (int32_t)best_rank; o.n_remaining = 0; o.pick_index = 0;
+                 o.flags = MMP_TF_SIMPLE | MMP_TF_FAST | MMP_TF_FAVOUR_EXIT; o.cut_rank = (int32_t)NONE_RANK; }
     return true;
   }
   // S inside the window
@@ -415,11 +437,10 @@ MMP_HD bool decide_fast(const SnapshotView &s, const DecisionCtx &c, const uint3
     return use_pref ? (m & p) : m;
   });
   const bool s_in_window = hi != NONE_RANK ? hi <= wend : to_row_end;  // does the window hold all of S?
+  const uint32_t sw_ = self_rank >= 0 ? (uint32_t)self_rank >> 5 : 0xffffffffu, sb_ = 1u << (self_rank & 31);
   bool self_in_s = false;
-  if (self_rank >= 0 && (uint32_t)self_rank > lo && (uint32_t)self_rank < hi) {
-    const uint32_t sw_ = (uint32_t)self_rank >> 5, sb_ = 1u << (self_rank & 31);
+  if (self_rank >= 0 && (uint32_t)self_rank > lo && (uint32_t)self_rank < hi)
     self_in_s = (CX[sw_] & ~erow[sw_] & sb_) != 0 && (!use_pref || (P[sw_] & sb_) != 0);
-  }
   const int64_t q = best_rem >> 2;
   const bool c_self = fr.rem < s.min_space || fr.rem < q;
   bool self_viol = rb.rem < s.min_space || rb.rem < q;
@@ -428,36 +449,37 @@ MMP_HD bool decide_fast(const SnapshotView &s, const DecisionCtx &c, const uint3
   if (self_in_s && cv(s.rows[self_rank].count)) self_viol = true;
   uint32_t cut_others;
   if (c_self) {
-    const uint32_t sw_ = self_rank >= 0 ? (uint32_t)self_rank >> 5 : NONE_RANK, sb_ = 1u << (self_rank & 31);
     cut_others = co.wfirst(w0, co.wmap1(w0, sx, [&](uint32_t wi, uint32_t x) { return (self_in_s && wi == sw_) ? (x & ~sb_) : x; }));
   } else {
-    // classification of the window's words from the count summaries, then exact evaluation of mixed words in order
-    const W cls = co.wmap1(w0, sx, [&](uint32_t wi, uint32_t x) -> uint32_t {
-      if (!x) return 0u;
+    // One key per word: (rank of its first member << 1) | mixed, for words whose count summary admits a violator.
+    // The minimum key is the earliest word that can hold the cut: class 1 -> that member is the cut; mixed -> evaluate
+    // the word's 32 ranks exactly, and on a miss drop the word and look again.
+    W pend = co.wmap1(w0, sx, [&](uint32_t wi, uint32_t x) -> uint32_t {
+      if (!x) return 0xffffffffu;
       const WordSumI m = s.csum[wi];
-      return !cv(m.hi) ? 0u : (cv(m.lo) ? 1u : 2u);
+      if (!cv(m.hi)) return 0xffffffffu;
+      return ((wi * 32u + (uint32_t)ffs32(x)) << 1) | (cv(m.lo) ? 0u : 1u);
     });
-    uint32_t Amin = co.wfirst(w0, co.wmap2(w0, sx, cls, [](uint32_t, uint32_t x, uint32_t cl) { return cl == 1u ? x : 0u; }));
-    W mixed = co.wmap2(w0, sx, cls, [](uint32_t, uint32_t x, uint32_t cl) { return cl == 2u ? x : 0u; });
-    uint32_t Mmin = co.wfirst(w0, mixed);
-    while (Mmin != NONE_RANK && Mmin < Amin) {
-      const uint32_t mw = Mmin >> 5;
-      const uint32_t vm = co.eval_word(mw, s.n_ranks, [&](uint32_t r) { return cv(s.rows[r].count); }) & co.wget(w0, mixed, mw);
-      if (vm) { const uint32_t r = mw * 32u + (uint32_t)ffs32(vm); if (r < Amin) Amin = r; break; }
-      mixed = co.wmap1(w0, mixed, [&](uint32_t wi, uint32_t x) { return wi == mw ? 0u : x; });
-      Mmin = co.wfirst(w0, mixed);
+    cut_others = NONE_RANK;
+    for (;;) {
+      const uint32_t key = co.wmin(w0, pend, [](uint32_t, uint32_t k) { return k; });
+      if (key == 0xffffffffu) break;
+      if (!(key & 1u)) { cut_others = key >> 1; break; }
+      const uint32_t mw = key >> 6;  // word index of the mixed word
+      const uint32_t vm = co.eval_word(mw, s.n_ranks, [&](uint32_t r) { return cv(s.rows[r].count); }) & co.wget(w0, sx, mw);
+      if (vm) { cut_others = mw * 32u + (uint32_t)ffs32(vm); break; }
+      pend = co.wmap1(w0, pend, [&](uint32_t wi, uint32_t k) { return wi == mw ? 0xffffffffu : k; });
     }
-    cut_others = Amin;
   }
-  if (cut_others == NONE_RANK && !s_in_window) return false;  // the walk continues past the window
   const uint32_t cut_self = (self_in_s && self_viol) ? (uint32_t)self_rank : NONE_RANK;
-  if (cut_self != NONE_RANK && cut_self >= wend && cut_others == NONE_RANK && !s_in_window) return false;
   const uint32_t cut = cut_others < cut_self ? cut_others : cut_self;
-  if (cut == NONE_RANK ? !s_in_window : cut > wend) return false;
+  if (cut == NONE_RANK ? !s_in_window : cut > wend) return false;  // the walk continues past the window
+  if (cut_others == NONE_RANK && !s_in_window) return false;       // an earlier violator may sit between wend and cut_self
   const bool self_in_sl = self_in_s && (uint32_t)self_rank < cut;
   if (favour_self && self_in_sl) {
-    o.target = MMP_TARGET_SELF; o.n_candidates = 0; o.best = best_idx; o.best_rank = (int32_t)best_rank; o.n_remaining = 0;
-    o.pick_index = 0; o.flags = flags | MMP_TF_FAVOUR_EXIT; o.cut_rank = (int32_t)cut;
+    o.target = MMP_TARGET_SELF; o.n_candidates = 0;
+    if (TRACE) { o.best = best_idx; o.best_rank = (int32_t)best_rank; o.n_remaining = 0; o.pick_index = 0;
+                 o.flags = MMP_TF_SIMPLE | MMP_TF_FAST | MMP_TF_FAVOUR_EXIT; o.cut_rank = (int32_t)cut; }
     return true;
   }
   const W sl = co.wmap1(w0, sx, [&](uint32_t wi, uint32_t x) { return x & mask_below(wi * 32u, cut); });
@@ -479,7 +501,6 @@ MMP_HD bool decide_fast(const SnapshotView &s, const DecisionCtx &c, const uint3
     }
     index = remaining == 1 ? 0u : hash_index(seed, decision_id, (uint32_t)remaining);
   }
-  flags |= (keep_best ? MMP_TF_KEEP_BEST : 0) | (keep_others ? MMP_TF_KEEP_OTHERS : 0) | (keep_self ? MMP_TF_KEEP_SELF : 0);
   uint32_t chosen_rank;
   uint32_t kth = index;
   if (keep_best && kth == 0) chosen_rank = best_rank;
@@ -487,15 +508,19 @@ MMP_HD bool decide_fast(const SnapshotView &s, const DecisionCtx &c, const uint3
     if (keep_best) kth--;
     if (!keep_others) chosen_rank = (uint32_t)self_rank;
     else {
-      const uint32_t sw_ = self_rank >= 0 ? (uint32_t)self_rank >> 5 : NONE_RANK, sb_ = 1u << (self_rank & 31);
       const bool drop_self = self_in_sl && !keep_self;
       chosen_rank = co.wselect(w0, co.wmap1(w0, sl, [&](uint32_t wi, uint32_t x) { return (drop_self && wi == sw_) ? (x & ~sb_) : x; }), kth);
     }
   }
   const int32_t cidx = chosen_rank == best_rank ? best_idx : s.rows[chosen_rank].idx;
   o.target = (!favour_self && cidx == d.self) ? MMP_TARGET_SELF : cidx;
-  o.n_candidates = ccount; o.best = best_idx; o.best_rank = (int32_t)best_rank; o.n_remaining = remaining;
-  o.pick_index = (int32_t)index; o.flags = flags; o.cut_rank = (int32_t)cut;
+  o.n_candidates = ccount;
+  if (TRACE) {
+    o.best = best_idx; o.best_rank = (int32_t)best_rank; o.n_remaining = remaining; o.pick_index = (int32_t)index;
+    o.flags = MMP_TF_SIMPLE | MMP_TF_FAST | (keep_best ? MMP_TF_KEEP_BEST : 0) | (keep_others ? MMP_TF_KEEP_OTHERS : 0) |
+              (keep_self ? MMP_TF_KEEP_SELF : 0);
+    o.cut_rank = (int32_t)cut;
+  }
   return true;
 }
 
@@ -510,7 +535,7 @@ MMP_HD void decide_ctx(const SnapshotView &s, const DecisionCtx &c, const uint32
   const uint32_t NW = (uint32_t)s.row_words;
   if (c.slot < 0) { o.target = TARGET_INVALID; return; }
   const mmp_decision_in &d = c.d;
-  const int slot = c.slot;
+  const int slot = ctx_slot(c);
   const bool favour_self = (d.flags & MMP_DF_FAVOUR_SELF) != 0;
   const int32_t self_rank = c.self_rank;
   const FreshRow fr = c.fr;
@@ -558,7 +583,7 @@ MMP_HD void decide_ctx(const SnapshotView &s, const DecisionCtx &c, const uint32
   uint32_t best_rank = b;
   const bool best_full = best_rem < s.min_space;
   if (best_full) o.flags |= MMP_TF_BEST_FULL;
-  const bool has_pref = s.has_pref[slot] != 0;
+  const bool has_pref = ctx_has_pref(c);
   bool simple = !has_pref || pref_bit(b);
   uint32_t lo = b, hi = NONE_RANK;
   bool use_pref = has_pref && simple;  // best is preferred: preference is treated as required (MM:4905-4907)

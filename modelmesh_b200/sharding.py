@@ -1,0 +1,38 @@
+"""Host-side sharding arithmetic for multi-GPU runs (one process per GPU, torch.distributed for the plumbing).
+
+Registry (model) sharding: rank r owns the contiguous model range shard_range(r, world, n_models); every rank holds the
+whole instance table, so a decision needs no data-path exchange — each rank resolves the decisions of its own models.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import numpy as np
+
+
+def shard_range(rank: int, world: int, n: int) -> Tuple[int, int]:
+    """Contiguous, balanced [lo, hi) slice of n items for `rank` of `world`."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    return rank * n // world, (rank + 1) * n // world
+
+
+def owner_of(item: np.ndarray, world: int, n: int) -> np.ndarray:
+    """Inverse of shard_range: which rank owns each item index."""
+    item = np.asarray(item, dtype=np.int64)
+    # rank r owns [r*n//w, (r+1)*n//w): the owner is the largest r with r*n//w <= item
+    r = (item * world + world - 1) // max(n, 1)
+    r = np.minimum(r, world - 1)
+    lo = r * n // world
+    r = np.where(lo > item, r - 1, r)
+    hi = (r + 1) * n // world
+    r = np.where(hi <= item, r + 1, r)
+    return r.astype(np.int64)
+
+
+def localize_decisions(dec: np.ndarray, lo: int, hi: int) -> np.ndarray:
+    """Decisions whose model lies in [lo, hi), with the model index rebased to the shard."""
+    sel = (dec["model"] >= lo) & (dec["model"] < hi)
+    out = dec[sel].copy()
+    out["model"] -= lo
+    return out

@@ -6,6 +6,7 @@
 // type-constraint masks and the JSON reader against the oracle on a box with no GPU.  The CUDA library differs from
 // this harness only in the cooperative shape (Coop32: shuffles/ballots, vector loads) and in where the arrays live.
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -24,10 +25,12 @@ struct mmp_fleet {
   int64_t launches = 0;
 };
 static thread_local std::string g_err;
+static int g_window = 32;  // fast-path window width under test (32: warp tile, 16: half-warp tile)
 
 extern "C" {
 
 int32_t mmp_abi_version(void) { return MMP_ABI_VERSION; }
+void mmp_emul_set_window(int w) { g_window = w == 16 ? 16 : 32; }  // harness-only entry point
 const char *mmp_last_error(mmp_fleet *) { return g_err.c_str(); }
 
 int32_t mmp_fleet_create(const mmp_config *cfg, mmp_fleet **out) {
@@ -105,12 +108,17 @@ int32_t mmp_place_batch_trace(mmp_fleet *f, const mmp_decision_in *in, int32_t n
     fr[i] = FreshRow{fresh[i].lru_time, std::max<int64_t>(0, fresh[i].capacity - fresh[i].used), fresh[i].count, fresh[i].rpm};
   }
   Coop1 co;
+  CoopHost<16> co16;
+  const bool win16 = g_window == 16;
   for (int32_t i = 0; i < n; i++) {
     DecideOut o;
     DecisionCtx cx;
     prepare_ctx(v, in[i], fr.data(), n_fresh, cx);
     const uint32_t *erow = v.excl + (size_t)(cx.slot >= 0 ? in[i].model : 0) * v.row_words;
-    if (cand_mask || !decide_fast<Coop1>(v, cx, erow, now_ms, seed, (uint64_t)i, co, o))
+    bool done = false;
+    if (!cand_mask) done = win16 ? decide_fast<true>(v, cx, erow, now_ms, seed, (uint64_t)i, co16, o)
+                                 : decide_fast<true>(v, cx, erow, now_ms, seed, (uint64_t)i, co, o);
+    if (!done)
       decide_ctx<Coop1>(v, cx, erow, extra, now_ms, seed, (uint64_t)i, co, o,
                         cand_mask ? cand_mask + (size_t)i * 2 * v.row_words : nullptr);
     out[i].target = o.target; out[i].n_candidates = o.n_candidates;

@@ -37,3 +37,20 @@ def test_mixed_regimes_match_oracle(emul_lib, oracle_lib, seed):
     assert np.array_equal(s.cluster_order(), o.cluster_order())
     sd = make_decisions(fl, 1500, seed)
     compare_decisions(fl, sd, o, s, seed=seed + 99)
+
+
+@pytest.mark.parametrize("config,nm,ni,seed", [("C2", 2000, 1000, 12), ("C3", 4000, 700, 3), ("C5", 3000, 500, 5), ("MIX", 600, 160, 8),
+                                               ("MIX", 600, 300, 14), ("C3", 1500, 1300, 33)])
+def test_half_warp_window_matches_oracle(emul_lib, oracle_lib, config, nm, ni, seed):
+    """The fast path with 16-word windows (the half-warp tile of the GPU kernel: two decisions per warp)."""
+    emul_lib.mmp_emul_set_window(16)
+    try:
+        fl = make_fleet(config, nm, ni, seed)
+        o = oracle_from_synth(fl)
+        s = solver_from_synth(fl, emul_lib)
+        sd = make_decisions(fl, 2500, seed)
+        compare_decisions(fl, sd, o, s, seed=seed * 31)
+        sd = make_decisions(fl, 1500, seed + 1, sweep=True, plain=True)
+        compare_decisions(fl, sd, o, s, seed=seed)
+    finally:
+        emul_lib.mmp_emul_set_window(32)
