@@ -105,12 +105,12 @@ struct RingLayout {
   uint32_t row_bytes, k;
   size_t per_warp;
   __host__ __device__ RingLayout(int row_words, int k_) : row_bytes((uint32_t)row_words * 4u), k((uint32_t)k_) {
-    per_warp = ((size_t)k * row_bytes + 2 * 32 * sizeof(DecisionCtx) + (size_t)k * 8 + 127) / 128 * 128;
+    per_warp = ((size_t)k * row_bytes + 32 * sizeof(DecisionCtx) + (size_t)k * 8 + 127) / 128 * 128;
   }
 };
 
-template <int WARPS, int K>
-__global__ void __launch_bounds__(WARPS * 32) k_place(const SnapshotView s, const mmp_decision_in *__restrict__ in, int n,
+template <int WARPS, int K, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) k_place(const SnapshotView s, const mmp_decision_in *__restrict__ in, int n,
                                                      const FreshRow *__restrict__ fresh, int n_fresh,
                                                      const int32_t *__restrict__ extra, mmp_decision_out *__restrict__ out,
                                                      mmp_decision_trace *__restrict__ tr, uint32_t *__restrict__ cand,
@@ -122,8 +122,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_place(const SnapshotView s, cons
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char *base = smem_raw + (size_t)wib * lay.per_warp;
   uint32_t *rows_s = reinterpret_cast<uint32_t *>(base);
-  DecisionCtx *ctx_s = reinterpret_cast<DecisionCtx *>(base + (size_t)K * row_bytes);  // [2][32]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(base + (size_t)K * row_bytes + 2 * 32 * sizeof(DecisionCtx));
+  DecisionCtx *ctx_s = reinterpret_cast<DecisionCtx *>(base + (size_t)K * row_bytes);  // [32]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(base + (size_t)K * row_bytes + 32 * sizeof(DecisionCtx));
   if (lane == 0) {
     for (int k = 0; k < K; k++) mbar_init(&bars[k], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_place(const SnapshotView s, cons
     mbar_expect_tx(&bars[sl], row_bytes);
     bulk_g2s(rows_s + (size_t)sl * RW, s.excl + (size_t)m * RW, row_bytes, &bars[sl]);
   };
-  int b = gw, cur = 0;
+  int b = gw;
   prep(b, ctx_s);
   __syncwarp();
   if (b < nb) {
@@ -165,19 +165,27 @@ __global__ void __launch_bounds__(WARPS * 32) k_place(const SnapshotView s, cons
   }
   while (b < nb) {
     const int bn = b + nw;
-    const DecisionCtx *cc = ctx_s + cur * 32;
-    DecisionCtx *cnext = ctx_s + (cur ^ 1) * 32;
-    prep(bn, cnext);  // next batch's contexts: their loads overlap this batch (the stores wait on them, nothing else does)
-    __syncwarp();
+    const DecisionCtx *cc = ctx_s;
+    // the next batch's contexts are staged when this batch is done (one buffer); only its model indices are fetched
+    // now, because the ring must start loading its first rows K positions before the batch boundary
+    int next_model = -1;
+    {
+      const int i = bn * 32 + lane;
+      if (bn < nb && i < n) next_model = __ldg(&in[i].model);
+    }
     const int count = min(32, n - b * 32);
     mmp_decision_out mine{MMP_TARGET_NONE, 0};
+    int nm_next[K];  // model indices of the next batch's first K decisions (held by every lane, used by lane 0)
+#pragma unroll
+    for (int t = 0; t < K; t++) nm_next[t] = -2;
+    bool nm_loaded = false;
     int jbase = 0;
     auto refill = [&](int jdone) {  // lane 0: the row of decision jdone has been consumed; fetch the one K positions ahead
       const int t = jdone + K;
       int nm = 0;
       bool have = false;
       if (t < count) { nm = cc[t].d.model; have = true; }
-      else if (t - count < 32 && cnext[t - count].slot != -2) { nm = cnext[t - count].d.model; have = true; }
+      else if (t - count < K && nm_next[t - count] != -1) { nm = nm_next[t - count]; have = true; }
       if (have) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         issue(nm, use + (uint32_t)(jdone - jbase) + (uint32_t)K);
@@ -189,6 +197,11 @@ __global__ void __launch_bounds__(WARPS * 32) k_place(const SnapshotView s, cons
       const int half = lane >> 4;
       for (int jp = 0; jp < count; jp += 2) {
         jbase = jp;
+        if (!nm_loaded && jp + 1 + K >= count) {
+#pragma unroll
+          for (int t = 0; t < K; t++) nm_next[t] = __shfl_sync(0xffffffffu, next_model, t);
+          nm_loaded = true;
+        }
         const int j = jp + half;
         const bool valid = j < count;
         const uint32_t myuse = use + (uint32_t)half;
@@ -223,6 +236,11 @@ __global__ void __launch_bounds__(WARPS * 32) k_place(const SnapshotView s, cons
     } else {
       for (int j = 0; j < count; j++) {
         jbase = j;
+        if (!nm_loaded && j + K >= count) {
+#pragma unroll
+          for (int t = 0; t < K; t++) nm_next[t] = __shfl_sync(0xffffffffu, next_model, t);
+          nm_loaded = true;
+        }
         const uint32_t slot = use % (uint32_t)K, parity = (use / (uint32_t)K) & 1u;
         while (!mbar_try_wait(&bars[slot], parity)) {}
         const uint32_t *erow = rows_s + (size_t)slot * RW;
@@ -244,7 +262,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_place(const SnapshotView s, cons
     }
     if (lane < count) out[b * 32 + lane] = mine;
     b = bn;
-    cur ^= 1;
+    __syncwarp();
+    prep(b, ctx_s);
     __syncwarp();
   }
 }
@@ -377,12 +396,12 @@ struct PlaceArgs {
 };
 
 // ring depth (a power of two) / warps per block by row size: rows up to 2 KiB (16k instances) K=4 x 8 warps, up to 4 KiB K=2 x 8, beyond K=2 x 4
-template <int WARPS, int K>
+template <int WARPS, int K, int MINB>
 static cudaError_t launch_place_t(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st) {
   static int attr_set = 0;
   const RingLayout lay(a.s.row_words, K);
   const size_t smem = lay.per_warp * WARPS;
-  auto kern = k_place<WARPS, K>;
+  auto kern = k_place<WARPS, K, MINB>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return e;
@@ -402,9 +421,9 @@ static cudaError_t launch_place_t(mmp_fleet *f, const PlaceArgs &a, cudaStream_t
 
 static cudaError_t launch_place(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st) {
   const int rw = a.s.row_words;
-  if (rw <= 512) return launch_place_t<8, 4>(f, a, st);
-  if (rw <= 1024) return launch_place_t<8, 2>(f, a, st);
-  return launch_place_t<4, 2>(f, a, st);
+  if (rw <= 512) return launch_place_t<4, 4, 7>(f, a, st);   // rows <= 2 KiB: 7 blocks x 4 warps per SM
+  if (rw <= 1024) return launch_place_t<4, 4, 3>(f, a, st);  // rows <= 4 KiB
+  return launch_place_t<4, 2, 2>(f, a, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
