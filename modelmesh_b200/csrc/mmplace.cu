@@ -101,6 +101,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 // batches of 32: lane j prepares the context of decision j (its dependent gathers: decision -> model row,
 // rank_of[self] -> rows[self]) one batch ahead into a double-buffered shared-memory table, so those latencies overlap
 // across lanes and with the previous batch.
+// The warp-wide redo of a decision its tile could not resolve inside its window: the 32-word fast path first, then the
+// general routine.  Kept out of line so the kernel's tile loop stays small.
+__device__ __noinline__ void decide_warp(const SnapshotView s, const DecisionCtx &c, const uint32_t *erow, const int32_t *extra,
+                                         int64_t now, uint64_t seed, uint64_t decision_id, int32_t *target, int32_t *n_candidates) {
+  Coop32 co;
+  DecideOut o;
+  if (!decide_fast<false>(s, c, erow, now, seed, decision_id, co, o)) decide_ctx(s, c, erow, extra, now, seed, decision_id, co, o, nullptr);
+  *target = o.target; *n_candidates = o.n_candidates;
+}
+
 struct RingLayout {
   uint32_t row_bytes, k;
   size_t per_warp;
@@ -109,7 +119,7 @@ struct RingLayout {
   }
 };
 
-template <int WARPS, int K, int MINB>
+template <int WARPS, int K, int MINB, int T>
 __global__ void __launch_bounds__(WARPS * 32, MINB) k_place(const SnapshotView s, const mmp_decision_in *__restrict__ in, int n,
                                                      const FreshRow *__restrict__ fresh, int n_fresh,
                                                      const int32_t *__restrict__ extra, mmp_decision_out *__restrict__ out,
@@ -132,7 +142,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_place(const SnapshotView s
   const int nb = (n + 31) >> 5;
   const int gw = blockIdx.x * WARPS + wib, nw = gridDim.x * WARPS;
   Coop32 co;
-  CoopTile<16> co16;
+  CoopTile<T> cot;
+  constexpr int G = 32 / T;  // decisions resolved per step by the tiles of one warp
   uint32_t use = 0;  // ring position of the next row to consume (warp-uniform)
   auto prep = [&](int batch, DecisionCtx *dst) {  // lane j stages the context of decision j of `batch`
     const int i = batch * 32 + lane;
@@ -192,46 +203,49 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_place(const SnapshotView s
       }
     };
     if (!tr && !cand) {
-      // ---- two decisions per warp: each half-warp resolves one out of a 16-word window (CoopTile<16>); whatever
-      // a half cannot resolve inside its window is redone warp-wide by the general routine ----
-      const int half = lane >> 4;
-      for (int jp = 0; jp < count; jp += 2) {
+      // ---- G decisions per warp step: each T-lane tile resolves one out of a T-word window (CoopTile<T>); whatever a
+      // tile cannot resolve inside its window is redone warp-wide by the general routine ----
+      const int tile = lane / T;
+      for (int jp = 0; jp < count; jp += G) {
         jbase = jp;
-        if (!nm_loaded && jp + 1 + K >= count) {
+        if (!nm_loaded && jp + G - 1 + K >= count) {
 #pragma unroll
           for (int t = 0; t < K; t++) nm_next[t] = __shfl_sync(0xffffffffu, next_model, t);
           nm_loaded = true;
         }
-        const int j = jp + half;
+        const int j = jp + tile;
         const bool valid = j < count;
-        const uint32_t myuse = use + (uint32_t)half;
+        const uint32_t myuse = use + (uint32_t)tile;
         const uint32_t slot = myuse % (uint32_t)K, parity = (myuse / (uint32_t)K) & 1u;
         if (valid) { while (!mbar_try_wait(&bars[slot], parity)) {} }
         DecideOut o;
         o.target = MMP_TARGET_NONE; o.n_candidates = 0;
         bool resolved = false;
-        if (valid) resolved = decide_fast<false>(s, cc[j], rows_s + (size_t)slot * RW, now, seed, id_base + (uint64_t)(b * 32 + j), co16, o);
+        if (valid) resolved = decide_fast<false>(s, cc[j], rows_s + (size_t)slot * RW, now, seed, id_base + (uint64_t)(b * 32 + j), cot, o);
         __syncwarp();
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-          const int need = __shfl_sync(0xffffffffu, (valid && !resolved) ? 1 : 0, h * 16);
-          if (need) {
-            const int jj = jp + h;
-            const uint32_t sl2 = (use + (uint32_t)h) % (uint32_t)K;
-            DecideOut o2;
-            if (!decide_fast<false>(s, cc[jj], rows_s + (size_t)sl2 * RW, now, seed, id_base + (uint64_t)(b * 32 + jj), co, o2))
-              decide_ctx(s, cc[jj], rows_s + (size_t)sl2 * RW, extra, now, seed, id_base + (uint64_t)(b * 32 + jj), co, o2, nullptr);
-            if (half == h) { o.target = o2.target; o.n_candidates = o2.n_candidates; }
+        {
+          const uint32_t pending = __ballot_sync(0xffffffffu, valid && !resolved);
+#pragma unroll 1
+          for (int h = 0; h < G; h++) {
+            if (pending & (1u << (h * T))) {
+              const int jj = jp + h;
+              const uint32_t sl2 = (use + (uint32_t)h) % (uint32_t)K;
+              int32_t t2, c2;
+              decide_warp(s, cc[jj], rows_s + (size_t)sl2 * RW, extra, now, seed, id_base + (uint64_t)(b * 32 + jj), &t2, &c2);
+              if (tile == h) { o.target = t2; o.n_candidates = c2; }
+            }
           }
         }
-        const int t0 = __shfl_sync(0xffffffffu, o.target, 0), c0 = __shfl_sync(0xffffffffu, o.n_candidates, 0);
-        const int t1 = __shfl_sync(0xffffffffu, o.target, 16), c1 = __shfl_sync(0xffffffffu, o.n_candidates, 16);
-        if (lane == jp) { mine.target = t0; mine.n_candidates = c0; }
-        if (lane == jp + 1) { mine.target = t1; mine.n_candidates = c1; }
+#pragma unroll
+        for (int h = 0; h < G; h++) {
+          const int th = __shfl_sync(0xffffffffu, o.target, h * T), ch = __shfl_sync(0xffffffffu, o.n_candidates, h * T);
+          if (lane == jp + h) { mine.target = th; mine.n_candidates = ch; }
+        }
         __syncwarp();
-        const int npair = (jp + 1 < count) ? 2 : 1;
-        if (lane == 0) { refill(jp); if (npair == 2) refill(jp + 1); }
-        use += (uint32_t)npair;
+        const int nstep = min(G, count - jp);
+        if (lane == 0)
+          for (int h = 0; h < nstep; h++) refill(jp + h);
+        use += (uint32_t)nstep;
       }
     } else {
       for (int j = 0; j < count; j++) {
@@ -327,6 +341,7 @@ struct mmp_fleet {
   std::mutex ctx_mu;
   std::vector<std::unique_ptr<PlaceCtx>> ctx_free;
   std::atomic<int64_t> launches{0};
+  int tile = 16;                // lanes per decision in k_place (MMP_TILE = 8 | 16 | 32)
   // LRU store (plug point 3)
   DevBuf lru_ts, lru_seq, lru_weight, lru_model, lru_cap, lru_wsize, lru_count, lru_seqctr;
   int32_t lru_n = 0, lru_slots = 0;
@@ -396,12 +411,12 @@ struct PlaceArgs {
 };
 
 // ring depth (a power of two) / warps per block by row size: rows up to 2 KiB (16k instances) K=4 x 8 warps, up to 4 KiB K=2 x 8, beyond K=2 x 4
-template <int WARPS, int K, int MINB>
+template <int WARPS, int K, int MINB, int T>
 static cudaError_t launch_place_t(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st) {
   static int attr_set = 0;
   const RingLayout lay(a.s.row_words, K);
   const size_t smem = lay.per_warp * WARPS;
-  auto kern = k_place<WARPS, K, MINB>;
+  auto kern = k_place<WARPS, K, MINB, T>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return e;
@@ -421,9 +436,14 @@ static cudaError_t launch_place_t(mmp_fleet *f, const PlaceArgs &a, cudaStream_t
 
 static cudaError_t launch_place(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st) {
   const int rw = a.s.row_words;
-  if (rw <= 512) return launch_place_t<4, 4, 7>(f, a, st);   // rows <= 2 KiB: 7 blocks x 4 warps per SM
-  if (rw <= 1024) return launch_place_t<4, 4, 3>(f, a, st);  // rows <= 4 KiB
-  return launch_place_t<4, 2, 2>(f, a, st);
+  // tile width: how many lanes (= window words) resolve one decision; 32/T decisions advance per warp step
+  if (rw <= 512) {  // rows <= 2 KiB (16k instances): 7 blocks x 4 warps per SM
+    if (f->tile == 8) return launch_place_t<4, 4, 7, 8>(f, a, st);
+    if (f->tile == 32) return launch_place_t<4, 4, 7, 32>(f, a, st);
+    return launch_place_t<4, 4, 7, 16>(f, a, st);
+  }
+  if (rw <= 1024) return launch_place_t<4, 4, 3, 16>(f, a, st);  // rows <= 4 KiB
+  return launch_place_t<4, 2, 2, 16>(f, a, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -453,6 +473,7 @@ int32_t mmp_fleet_create(const mmp_config *cfg, mmp_fleet **out) {
   f->sm_count = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&f->commit_stream, cudaStreamNonBlocking));
   f->hs.init(*cfg);
+  if (const char *t = getenv("MMP_TILE")) { int v = atoi(t); if (v == 8 || v == 16 || v == 32) f->tile = v; }
   *out = f.release();
   return MMP_OK;
 }
