@@ -119,7 +119,7 @@ struct RingLayout {
   }
 };
 
-template <int WARPS, int K, int MINB, int T>
+template <int WARPS, int K, int MINB, int T, bool TRACE>
 __global__ void __launch_bounds__(WARPS * 32, MINB) k_place(const SnapshotView s, const mmp_decision_in *__restrict__ in, int n,
                                                      const FreshRow *__restrict__ fresh, int n_fresh,
                                                      const int32_t *__restrict__ extra, mmp_decision_out *__restrict__ out,
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_place(const SnapshotView s
         issue(nm, use + (uint32_t)(jdone - jbase) + (uint32_t)K);
       }
     };
-    if (!tr && !cand) {
+    if constexpr (!TRACE) {
       // ---- G decisions per warp step: each T-lane tile resolves one out of a T-word window (CoopTile<T>); whatever a
       // tile cannot resolve inside its window is redone warp-wide by the general routine ----
       const int tile = lane / T;
@@ -411,12 +411,12 @@ struct PlaceArgs {
 };
 
 // ring depth (a power of two) / warps per block by row size: rows up to 2 KiB (16k instances) K=4 x 8 warps, up to 4 KiB K=2 x 8, beyond K=2 x 4
-template <int WARPS, int K, int MINB, int T>
+template <int WARPS, int K, int MINB, int T, bool TRACE>
 static cudaError_t launch_place_t(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st) {
   static int attr_set = 0;
   const RingLayout lay(a.s.row_words, K);
   const size_t smem = lay.per_warp * WARPS;
-  auto kern = k_place<WARPS, K, MINB, T>;
+  auto kern = k_place<WARPS, K, MINB, T, TRACE>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return e;
@@ -436,14 +436,18 @@ static cudaError_t launch_place_t(mmp_fleet *f, const PlaceArgs &a, cudaStream_t
 
 static cudaError_t launch_place(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st) {
   const int rw = a.s.row_words;
-  // tile width: how many lanes (= window words) resolve one decision; 32/T decisions advance per warp step
+  // tile width: how many lanes (= window words) resolve one decision; 32/T decisions advance per warp step.
+  // The traced variant (parity tests) is a separate, single-decision-per-warp kernel so that the production kernel's
+  // instruction footprint stays small.
+  const bool traced = a.tr || a.cand;
   if (rw <= 512) {  // rows <= 2 KiB (16k instances): 7 blocks x 4 warps per SM
-    if (f->tile == 8) return launch_place_t<4, 4, 7, 8>(f, a, st);
-    if (f->tile == 32) return launch_place_t<4, 4, 7, 32>(f, a, st);
-    return launch_place_t<4, 4, 7, 16>(f, a, st);
+    if (traced) return launch_place_t<4, 4, 4, 32, true>(f, a, st);
+    if (f->tile == 8) return launch_place_t<4, 4, 7, 8, false>(f, a, st);
+    if (f->tile == 32) return launch_place_t<4, 4, 7, 32, false>(f, a, st);
+    return launch_place_t<4, 4, 7, 16, false>(f, a, st);
   }
-  if (rw <= 1024) return launch_place_t<4, 4, 3, 16>(f, a, st);  // rows <= 4 KiB
-  return launch_place_t<4, 2, 2, 16>(f, a, st);
+  if (rw <= 1024) return traced ? launch_place_t<4, 4, 3, 32, true>(f, a, st) : launch_place_t<4, 4, 3, 16, false>(f, a, st);  // rows <= 4 KiB
+  return traced ? launch_place_t<4, 2, 2, 32, true>(f, a, st) : launch_place_t<4, 2, 2, 16, false>(f, a, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

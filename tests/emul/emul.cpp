@@ -30,7 +30,7 @@ static int g_window = 32;  // fast-path window width under test (32: warp tile, 
 extern "C" {
 
 int32_t mmp_abi_version(void) { return MMP_ABI_VERSION; }
-void mmp_emul_set_window(int w) { g_window = w == 16 ? 16 : 32; }  // harness-only entry point
+void mmp_emul_set_window(int w) { g_window = (w == 16 || w == 8) ? w : 32; }  // harness-only entry point
 const char *mmp_last_error(mmp_fleet *) { return g_err.c_str(); }
 
 int32_t mmp_fleet_create(const mmp_config *cfg, mmp_fleet **out) {
@@ -109,15 +109,17 @@ int32_t mmp_place_batch_trace(mmp_fleet *f, const mmp_decision_in *in, int32_t n
   }
   Coop1 co;
   CoopHost<16> co16;
-  const bool win16 = g_window == 16;
+  CoopHost<8> co8;
+  const int win = g_window;
   for (int32_t i = 0; i < n; i++) {
     DecideOut o;
     DecisionCtx cx;
     prepare_ctx(v, in[i], fr.data(), n_fresh, cx);
     const uint32_t *erow = v.excl + (size_t)(cx.slot >= 0 ? in[i].model : 0) * v.row_words;
     bool done = false;
-    if (!cand_mask) done = win16 ? decide_fast<true>(v, cx, erow, now_ms, seed, (uint64_t)i, co16, o)
-                                 : decide_fast<true>(v, cx, erow, now_ms, seed, (uint64_t)i, co, o);
+    if (!cand_mask) done = win == 16 ? decide_fast<true>(v, cx, erow, now_ms, seed, (uint64_t)i, co16, o)
+                         : win == 8 ? decide_fast<true>(v, cx, erow, now_ms, seed, (uint64_t)i, co8, o)
+                                    : decide_fast<true>(v, cx, erow, now_ms, seed, (uint64_t)i, co, o);
     if (!done)
       decide_ctx<Coop1>(v, cx, erow, extra, now_ms, seed, (uint64_t)i, co, o,
                         cand_mask ? cand_mask + (size_t)i * 2 * v.row_words : nullptr);
