@@ -342,6 +342,7 @@ struct mmp_fleet {
   std::vector<std::unique_ptr<PlaceCtx>> ctx_free;
   std::atomic<int64_t> launches{0};
   int tile = 16;                // lanes per decision in k_place (MMP_TILE = 8 | 16 | 32)
+  int ring_k = 4;               // ring depth for rows <= 2 KiB (MMP_RING_K = 2 | 4)
   // LRU store (plug point 3)
   DevBuf lru_ts, lru_seq, lru_weight, lru_model, lru_cap, lru_wsize, lru_count, lru_seqctr;
   int32_t lru_n = 0, lru_slots = 0;
@@ -444,6 +445,7 @@ static cudaError_t launch_place(mmp_fleet *f, const PlaceArgs &a, cudaStream_t s
     if (traced) return launch_place_t<4, 4, 4, 32, true>(f, a, st);
     if (f->tile == 8) return launch_place_t<4, 4, 7, 8, false>(f, a, st);
     if (f->tile == 32) return launch_place_t<4, 4, 7, 32, false>(f, a, st);
+    if (f->ring_k == 2) return launch_place_t<4, 2, 8, 16, false>(f, a, st);  // no look-ahead, smaller footprint: 8 blocks/SM
     return launch_place_t<4, 4, 7, 16, false>(f, a, st);
   }
   if (rw <= 1024) return traced ? launch_place_t<4, 4, 3, 32, true>(f, a, st) : launch_place_t<4, 4, 3, 16, false>(f, a, st);  // rows <= 4 KiB
@@ -477,6 +479,7 @@ int32_t mmp_fleet_create(const mmp_config *cfg, mmp_fleet **out) {
   f->sm_count = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&f->commit_stream, cudaStreamNonBlocking));
   f->hs.init(*cfg);
+  if (const char *t = getenv("MMP_RING_K")) { int v = atoi(t); if (v == 2 || v == 4) f->ring_k = v; }
   if (const char *t = getenv("MMP_TILE")) { int v = atoi(t); if (v == 8 || v == 16 || v == 32) f->tile = v; }
   *out = f.release();
   return MMP_OK;
