@@ -95,6 +95,10 @@ struct HostSnapshot {
   std::vector<uint32_t> rs, full;     // [row_words]
   std::vector<WordSumI> csum;         // [row_words]
   std::vector<WordSumL> lsum;         // [row_words]
+  std::vector<int32_t> count_col;     // [row_words*32] count by rank, 0 past the last rank
+  // instance sharding: the row words this process holds and the stride of a stored row
+  int32_t word_lo = 0, word_hi = 0, excl_stride = 0;
+  std::vector<int32_t> candx_before;  // [n_slots] members of candx at ranks below word_lo*32 (entries that beat this shard)
   std::vector<int32_t> part_of_rank;  // [n_ranks] partition (PTS) id, 0 when no type constraints
   std::vector<std::vector<std::string>> part_types;  // prohibited type names per partition id
   // instance columns for the stats / reaper kernels, by rank
@@ -329,6 +333,8 @@ class HostState {
     s.rs.assign(RW, 0); s.full.assign(RW, 0);
     s.csum.assign(RW, WordSumI{INT32_MAX, INT32_MIN});
     s.lsum.assign(RW, WordSumL{INT64_MAX, INT64_MIN});
+    s.count_col.assign((size_t)RW * 32, 0);
+    shard_words(RW, cfg.shard_rank, cfg.shard_count, s.word_lo, s.word_hi, s.excl_stride);
     s.any_rs = replaced_rs.empty() ? 0 : 1;
     for (int32_t r = 0; r < n; r++) {
       int32_t k = ord[r];
@@ -342,6 +348,7 @@ class HostState {
       if (keys[k].full) s.full[r >> 5] |= 1u << (r & 31);
       // MM:4769-4770: iid.length() >= 7 and first six chars name a likely-replaced replicaset
       if (!replaced_rs.empty() && h.id.size() >= 7 && replaced_rs.count(h.id.substr(0, 6))) s.rs[r >> 5] |= 1u << (r & 31);
+      s.count_col[r] = row.count;
       WordSumI &ci = s.csum[r >> 5];
       ci.lo = std::min(ci.lo, row.count); ci.hi = std::max(ci.hi, row.count);
       WordSumL &li = s.lsum[r >> 5];
@@ -353,7 +360,20 @@ class HostState {
     s.candx = s.cand;
     for (int32_t sl = 0; sl < s.n_slots; sl++)
       for (int32_t w = 0; w < RW; w++) s.candx[(size_t)sl * RW + w] &= ~s.rs[w];
+    s.candx_before.assign((size_t)s.n_slots, 0);
+    for (int32_t sl = 0; sl < s.n_slots; sl++)
+      for (int32_t w = 0; w < s.word_lo; w++) s.candx_before[sl] += __builtin_popcount(s.candx[(size_t)sl * RW + w]);
     return nullptr;
+  }
+
+  // Contiguous rank ranges per instance shard, in whole 16-byte granules (TMA bulk copies): shard k of n holds row words
+  // [lo, hi); a stored row is `stride` words (hi - lo rounded up to 4, at least 4).
+  static void shard_words(int32_t row_words, int32_t rank, int32_t count, int32_t &lo, int32_t &hi, int32_t &stride) {
+    if (count <= 1) { lo = 0; hi = row_words; stride = row_words; return; }
+    const int32_t block = ((row_words + count - 1) / count + 3) / 4 * 4;
+    lo = std::min(row_words, rank * block);
+    hi = std::min(row_words, lo + block);
+    stride = std::max(4, (hi - lo + 3) / 4 * 4);
   }
 
  private:

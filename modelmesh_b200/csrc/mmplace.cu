@@ -43,28 +43,30 @@ static thread_local std::string g_err;
 // kernels
 // ---------------------------------------------------------------------------------------------------------------
 // One thread per model scatters its (<= 4) inline edges into its own bitmap row: no atomics needed.
+// (instance-sharded: a stored row holds row words [word_lo, word_hi) at a stride of `stride` words)
 __global__ void k_build_bitmap(uint32_t *__restrict__ excl, const int4 *__restrict__ edge_inl,
-                               const int32_t *__restrict__ rank_of, int n_models, int row_words) {
+                               const int32_t *__restrict__ rank_of, int n_models, int stride, int word_lo, int word_hi) {
   int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= n_models) return;
   int4 e = edge_inl[m];
-  uint32_t *row = excl + (size_t)m * row_words;
+  uint32_t *row = excl + (size_t)m * stride;
   int es[4] = {e.x, e.y, e.z, e.w};
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     if (es[i] >= 0) {
       int r = rank_of[es[i]];
-      if (r >= 0) row[r >> 5] |= 1u << (r & 31);
+      if (r >= 0 && (r >> 5) >= word_lo && (r >> 5) < word_hi) row[(r >> 5) - word_lo] |= 1u << (r & 31);
     }
   }
 }
 __global__ void k_build_bitmap_ovf(uint32_t *__restrict__ excl, const int2 *__restrict__ pairs, int n_pairs,
-                                   const int32_t *__restrict__ rank_of, int row_words) {
+                                   const int32_t *__restrict__ rank_of, int stride, int word_lo, int word_hi) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_pairs) return;
   int2 p = pairs[i];
   int r = rank_of[p.y];
-  if (r >= 0) atomicOr(&excl[(size_t)p.x * row_words + (r >> 5)], 1u << (r & 31));
+  if (r >= 0 && (r >> 5) >= word_lo && (r >> 5) < word_hi)
+    atomicOr(&excl[(size_t)p.x * stride + ((r >> 5) - word_lo)], 1u << (r & 31));
 }
 
 // ---- TMA 1-D bulk copy + mbarrier helpers (cp.async.bulk: SASS UBLKCP) ----
@@ -107,7 +109,8 @@ __device__ __noinline__ void decide_warp(const SnapshotView s, const DecisionCtx
                                          int64_t now, uint64_t seed, uint64_t decision_id, int32_t *target, int32_t *n_candidates) {
   Coop32 co;
   DecideOut o;
-  if (!decide_fast<false>(s, c, erow, now, seed, decision_id, co, o)) decide_ctx(s, c, erow, extra, now, seed, decision_id, co, o, nullptr);
+  const bool whole_rows = s.word_lo == 0 && s.word_hi == s.row_words;  // decide_fast reads rows by absolute word index
+  if (!whole_rows || !decide_fast<false>(s, c, erow, now, seed, decision_id, co, o)) decide_ctx(s, c, erow, extra, now, seed, decision_id, co, o, nullptr);
   *target = o.target; *n_candidates = o.n_candidates;
 }
 
@@ -126,7 +129,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_place(const SnapshotView s
                                                      mmp_decision_trace *__restrict__ tr, uint32_t *__restrict__ cand,
                                                      int64_t now, uint64_t seed, uint64_t id_base) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int RW = s.row_words;
+  const int RW = s.excl_stride;  // words per stored row
+  const bool whole_rows = s.word_lo == 0 && s.word_hi == s.row_words;  // decide_fast needs whole rows (not instance-sharded)
   const RingLayout lay(RW, K);
   const uint32_t row_bytes = lay.row_bytes;
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -221,7 +225,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_place(const SnapshotView s
         DecideOut o;
         o.target = MMP_TARGET_NONE; o.n_candidates = 0;
         bool resolved = false;
-        if (valid) resolved = decide_fast<false>(s, cc[j], rows_s + (size_t)slot * RW, now, seed, id_base + (uint64_t)(b * 32 + j), cot, o);
+        if (valid && whole_rows) resolved = decide_fast<false>(s, cc[j], rows_s + (size_t)slot * RW, now, seed, id_base + (uint64_t)(b * 32 + j), cot, o);
         __syncwarp();
         {
           const uint32_t pending = __ballot_sync(0xffffffffu, valid && !resolved);
@@ -260,8 +264,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_place(const SnapshotView s
         const uint32_t *erow = rows_s + (size_t)slot * RW;
         const int gi = b * 32 + j;
         DecideOut o;
-        if (cand || !decide_fast<true>(s, cc[j], erow, now, seed, id_base + (uint64_t)gi, co, o))
-          decide_ctx(s, cc[j], erow, extra, now, seed, id_base + (uint64_t)gi, co, o, cand ? cand + (size_t)gi * 2 * RW : nullptr);
+        if (cand || !whole_rows || !decide_fast<true>(s, cc[j], erow, now, seed, id_base + (uint64_t)gi, co, o))
+          decide_ctx(s, cc[j], erow, extra, now, seed, id_base + (uint64_t)gi, co, o, cand ? cand + (size_t)gi * 2 * s.row_words : nullptr);
         if (lane == j) { mine.target = o.target; mine.n_candidates = o.n_candidates; }
         if (tr && lane == 0) {
           mmp_decision_trace t;
@@ -279,6 +283,107 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_place(const SnapshotView s
     __syncwarp();
     prep(b, ctx_s);
     __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_place_lanes — the production scoring kernel: ONE DECISION PER LANE.
+//
+// Each warp owns a stage of 32 exclusion rows in shared memory.  Per step every lane (1) reads its decision record,
+// (2) issues the TMA bulk copy of its model's bitmap row (cp.async.bulk, one mbarrier per warp: 32 arrivals + 32 x
+// row_bytes transaction bytes), (3) gathers its decision context (model row, rank_of[self], the caller's row, type slot)
+// while the 32 rows stream in from HBM, (4) resolves its decision out of its staged row with the single-lane walk
+// (mmp::decide_ctx<CoopLane>: the same routine the CPU harness checks against the oracle), (5) writes its 8-byte
+// result (coalesced).  Blocks are single warps, so an SM holds floor(227 KB / stage) independent warps (5 at 10k
+// instances) whose load and compute phases interleave: ~200 KB of rows in flight per SM keeps HBM saturated while the
+// per-decision instruction cost drops from ~450 warp instructions (cooperative tiles) to ~30.
+// A walk that exceeds its word budget (long shortlists: adversarial fleets) bails and is redone by the whole warp
+// (decide_warp: Coop32 fast path, then the general routine) from the same staged row.
+// Rows are staged at a stride of row_bytes + 16 so that lanes reading the same word of their own rows spread over
+// the banks (16-byte granules: 8 lanes cover the 32 banks).
+// ---------------------------------------------------------------------------------------------------------------
+struct LaneLayout {
+  uint32_t row_bytes, stride;
+  size_t per_warp;
+  __host__ __device__ explicit LaneLayout(int row_words) : row_bytes((uint32_t)row_words * 4u), stride((uint32_t)row_words * 4u + 16u) {
+    per_warp = ((size_t)32 * stride + sizeof(DecisionCtx) + 16 + 127) / 128 * 128;
+  }
+};
+static constexpr int LANE_BUDGET = 48;  // row words one lane may visit before handing its decision to the warp
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_place_lanes(const SnapshotView s, const mmp_decision_in *__restrict__ in, int n,
+                                                            const FreshRow *__restrict__ fresh, int n_fresh,
+                                                            const int32_t *__restrict__ extra, mmp_decision_out *__restrict__ out,
+                                                            int64_t now, uint64_t seed, uint64_t id_base) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int RW = s.excl_stride;  // words per stored row (the whole row unless the fleet is instance-sharded)
+  const LaneLayout lay(RW);
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char *base = smem_raw + (size_t)wib * lay.per_warp;
+  const uint32_t *my_row = reinterpret_cast<const uint32_t *>(base + (size_t)lane * lay.stride);
+  DecisionCtx *ctx_one = reinterpret_cast<DecisionCtx *>(base + (size_t)32 * lay.stride);
+  uint64_t *bar = reinterpret_cast<uint64_t *>(base + (size_t)32 * lay.stride + ((sizeof(DecisionCtx) + 15) / 16) * 16);
+  if (lane == 0) {
+    mbar_init(bar, 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const int nb = (n + 31) >> 5;
+  const int gw = blockIdx.x * WARPS + wib, nw = gridDim.x * WARPS;
+  uint32_t parity = 0;
+  auto load_dec = [&](int b, mmp_decision_in &d) -> bool {
+    const int i = b * 32 + lane;
+    if (b >= nb || i >= n) return false;
+    const int4 *dp = reinterpret_cast<const int4 *>(in + i);
+    const int4 a = __ldg(dp), c = __ldg(dp + 1);
+    d.model = a.x; d.self = a.y; d.last_used = (int64_t)(((uint64_t)(uint32_t)a.w << 32) | (uint32_t)a.z);
+    d.flags = (uint32_t)c.x; d.fresh = c.y; d.extra_off = c.z; d.extra_n = c.w;
+    return true;
+  };
+  mmp_decision_in d;
+  bool valid = load_dec(gw, d);
+  for (int b = gw; b < nb; b += nw) {
+    // ---- stage this step's 32 rows ----
+    if (valid) {
+      const int m = (d.model >= 0 && d.model < s.n_models) ? d.model : 0;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // last step's reads of this slot precede the async write
+      mbar_expect_tx(bar, lay.row_bytes);
+      bulk_g2s(const_cast<uint32_t *>(my_row), s.excl + (size_t)m * RW, lay.row_bytes, bar);
+    } else mbar_arrive(bar);
+    // ---- context gathers overlap the row copies; the next step's decision record is fetched now too ----
+    DecisionCtx c;
+    c.slot = -2;
+    c.d.model = 0;
+    if (valid) prepare_ctx(s, d, fresh, n_fresh, c);
+    mmp_decision_in dn;
+    const bool valid_n = load_dec(b + nw, dn);
+    while (!mbar_try_wait(bar, parity)) {}
+    parity ^= 1u;
+    // ---- one decision per lane, the 32 lanes in lockstep ----
+    DecideOut o;
+    const bool handled = decide_stream(s, c, valid, my_row, now, seed, id_base + (uint64_t)(b * 32 + lane), WarpVote(), o, LANE_BUDGET);
+    // ---- what the lane routine declined (uncommon paths, long walks): the whole warp redoes it from the staged row ----
+    uint32_t pending = __ballot_sync(0xffffffffu, valid && !handled);
+    while (pending) {
+      const int l = __ffs((int)pending) - 1;
+      pending &= pending - 1;
+      if (lane == l) *ctx_one = c;
+      __syncwarp();
+      int32_t t2, c2;
+      decide_warp(s, *ctx_one, reinterpret_cast<const uint32_t *>(base + (size_t)l * lay.stride), extra, now, seed,
+                  id_base + (uint64_t)(b * 32 + l), &t2, &c2);
+      if (lane == l) { o.target = t2; o.n_candidates = c2; }
+      __syncwarp();
+    }
+    if (valid) out[b * 32 + lane] = mmp_decision_out{o.target, o.n_candidates};
+    d = dn;
+    valid = valid_n;
+    __syncwarp();  // every lane is done with the stage before it is refilled
   }
 }
 
@@ -303,13 +408,13 @@ struct DevBuf {
 
 struct DeviceSnapshot {
   DevBuf excl, cand, candx, pref, has_pref, type_slot, full, rows, rank_of, csum, lsum, models;
-  DevBuf cap_col, lthreads_col, linprog_col, part_of_rank;
+  DevBuf cap_col, lthreads_col, linprog_col, part_of_rank, count_col;
   SnapshotView view{};
   HostSnapshot host;  // kept for introspection and the small host-side parts of stats / reaper
   int32_t n_models = 0;
   void release() {
     for (DevBuf *b : {&excl, &cand, &candx, &pref, &has_pref, &type_slot, &full, &rows, &rank_of, &csum, &lsum, &models,
-                      &cap_col, &lthreads_col, &linprog_col, &part_of_rank})
+                      &cap_col, &lthreads_col, &linprog_col, &part_of_rank, &count_col})
       b->release();
   }
 };
@@ -343,6 +448,7 @@ struct mmp_fleet {
   std::atomic<int64_t> launches{0};
   int tile = 16;                // lanes per decision in k_place (MMP_TILE = 8 | 16 | 32)
   int ring_k = 4;               // ring depth for rows <= 2 KiB (MMP_RING_K = 2 | 4)
+  int lanes = 1;                // MMP_KERNEL=tile selects the cooperative-tile kernel (k_place) instead of k_place_lanes
   // LRU store (plug point 3)
   DevBuf lru_ts, lru_seq, lru_weight, lru_model, lru_cap, lru_wsize, lru_count, lru_seqctr;
   int32_t lru_n = 0, lru_slots = 0;
@@ -415,7 +521,7 @@ struct PlaceArgs {
 template <int WARPS, int K, int MINB, int T, bool TRACE>
 static cudaError_t launch_place_t(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st) {
   static int attr_set = 0;
-  const RingLayout lay(a.s.row_words, K);
+  const RingLayout lay(a.s.excl_stride, K);
   const size_t smem = lay.per_warp * WARPS;
   auto kern = k_place<WARPS, K, MINB, T, TRACE>;
   if (!attr_set) {
@@ -435,8 +541,33 @@ static cudaError_t launch_place_t(mmp_fleet *f, const PlaceArgs &a, cudaStream_t
   return cudaGetLastError();
 }
 
+template <int WARPS>
+static cudaError_t launch_place_lanes(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st) {
+  static int attr_set = 0;
+  const LaneLayout lay(a.s.excl_stride);
+  const size_t smem = lay.per_warp * WARPS;
+  auto kern = k_place_lanes<WARPS>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = 1;
+  }
+  int bps = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, WARPS * 32, smem);
+  if (e != cudaSuccess) return e;
+  if (bps < 1) bps = 1;
+  const int want = (a.n + 32 * WARPS - 1) / (32 * WARPS);
+  int grid = std::min(want, f->sm_count * bps);
+  if (grid < 1) grid = 1;
+  kern<<<grid, WARPS * 32, smem, st>>>(a.s, a.in, a.n, a.fresh, a.n_fresh, a.extra, a.out, a.now, a.seed, a.id_base);
+  f->launches++;
+  return cudaGetLastError();
+}
+
 static cudaError_t launch_place(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st) {
   const int rw = a.s.row_words;
+  // production path: one decision per lane (rows up to 2 KiB + pad: at least three 32-row stages per SM)
+  if (!(a.tr || a.cand) && f->lanes && rw <= 512) return launch_place_lanes<1>(f, a, st);
   // tile width: how many lanes (= window words) resolve one decision; 32/T decisions advance per warp step.
   // The traced variant (parity tests) is a separate, single-decision-per-warp kernel so that the production kernel's
   // instruction footprint stays small.
@@ -480,6 +611,7 @@ int32_t mmp_fleet_create(const mmp_config *cfg, mmp_fleet **out) {
   CK(cudaStreamCreateWithFlags(&f->commit_stream, cudaStreamNonBlocking));
   f->hs.init(*cfg);
   if (const char *t = getenv("MMP_RING_K")) { int v = atoi(t); if (v == 2 || v == 4) f->ring_k = v; }
+  if (const char *t = getenv("MMP_KERNEL")) f->lanes = strcmp(t, "tile") != 0;
   if (const char *t = getenv("MMP_TILE")) { int v = atoi(t); if (v == 8 || v == 16 || v == 32) f->tile = v; }
   *out = f.release();
   return MMP_OK;
@@ -554,16 +686,19 @@ int32_t mmp_fleet_commit(mmp_fleet *f) {
   CK(upload_vec(ds.lsum, h.lsum, st)); CK(upload_vec(ds.cap_col, h.cap_col, st));
   CK(upload_vec(ds.lthreads_col, h.lthreads_col, st)); CK(upload_vec(ds.linprog_col, h.linprog_col, st));
   CK(upload_vec(ds.part_of_rank, h.part_of_rank, st));
+  CK(upload_vec(ds.count_col, h.count_col, st));
   // model rows (each snapshot keeps its own copy so in-flight readers of the other epoch are undisturbed)
   CK(ds.models.ensure((size_t)std::max(nm, 1) * sizeof(mmp_model_row)));
   if (nm) CK(cudaMemcpyAsync(ds.models.p, f->hs.models.data(), (size_t)nm * sizeof(mmp_model_row), cudaMemcpyHostToDevice, st));
   // exclusion bitmap in rank space: zero, then scatter the sparse loaded/failed lists
-  CK(ds.excl.ensure((size_t)std::max(nm, 1) * RW * 4));
+  const int ST = h.excl_stride;  // words per stored row: the whole row, or this instance shard's block
+  CK(ds.excl.ensure((size_t)std::max(nm, 1) * ST * 4));
   if (nm) {
-    CK(cudaMemsetAsync(ds.excl.p, 0, (size_t)nm * RW * 4, st));
+    CK(cudaMemsetAsync(ds.excl.p, 0, (size_t)nm * ST * 4, st));
     CK(f->d_edge_inl.ensure((size_t)nm * HostState::EDGE_INL * 4));
     CK(cudaMemcpyAsync(f->d_edge_inl.p, f->hs.edge_inl.data(), (size_t)nm * HostState::EDGE_INL * 4, cudaMemcpyHostToDevice, st));
-    k_build_bitmap<<<(nm + 255) / 256, 256, 0, st>>>(ds.excl.as<uint32_t>(), f->d_edge_inl.as<int4>(), ds.rank_of.as<int32_t>(), nm, RW);
+    k_build_bitmap<<<(nm + 255) / 256, 256, 0, st>>>(ds.excl.as<uint32_t>(), f->d_edge_inl.as<int4>(), ds.rank_of.as<int32_t>(), nm, ST,
+                                                     h.word_lo, h.word_hi);
     f->launches++;
     CK(cudaGetLastError());
     std::vector<int2> pairs;
@@ -572,7 +707,7 @@ int32_t mmp_fleet_commit(mmp_fleet *f) {
     if (!pairs.empty()) {
       CK(upload_vec(f->d_ovf_pairs, pairs, st));
       k_build_bitmap_ovf<<<((int)pairs.size() + 255) / 256, 256, 0, st>>>(ds.excl.as<uint32_t>(), f->d_ovf_pairs.as<int2>(),
-                                                                         (int)pairs.size(), ds.rank_of.as<int32_t>(), RW);
+                                                                         (int)pairs.size(), ds.rank_of.as<int32_t>(), ST, h.word_lo, h.word_hi);
       f->launches++;
       CK(cudaGetLastError());
     }
@@ -581,6 +716,8 @@ int32_t mmp_fleet_commit(mmp_fleet *f) {
   SnapshotView &v = ds.view;
   v.n_ranks = h.n_ranks; v.row_words = RW; v.n_models = nm; v.max_instances = f->hs.cfg.max_instances;
   v.any_rs = h.any_rs; v.n_type_ids = (int32_t)h.type_slot.size(); v.min_space = f->hs.cfg.min_space_units;
+  v.word_lo = h.word_lo; v.word_hi = h.word_hi; v.excl_stride = ST; v.shard_reserved = 0;
+  v.count_col = ds.count_col.as<int32_t>();
   v.excl = ds.excl.as<uint32_t>(); v.cand = ds.cand.as<uint32_t>(); v.pref = ds.pref.as<uint32_t>();
   v.has_pref = ds.has_pref.as<uint8_t>(); v.type_slot = ds.type_slot.as<uint16_t>(); v.candx = ds.candx.as<uint32_t>();
   v.full = ds.full.as<uint32_t>(); v.rows = ds.rows.as<RankRow>(); v.rank_of = ds.rank_of.as<int32_t>();

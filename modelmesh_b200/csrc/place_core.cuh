@@ -42,6 +42,19 @@ struct RankRow {  // one per PLACEMENT_ORDER rank, 32 bytes
   int32_t idx;    // instance index
   uint32_t flags; // bit0: isFull(rem)
 };
+// one 32-byte row as two 128-bit loads (device arrays are 256-byte aligned)
+MMP_HD RankRow load_row(const RankRow *p) {
+#if defined(__CUDA_ARCH__)
+  const int4 a = __ldg(reinterpret_cast<const int4 *>(p)), b = __ldg(reinterpret_cast<const int4 *>(p) + 1);
+  RankRow r;
+  r.lru = (int64_t)(((uint64_t)(uint32_t)a.y << 32) | (uint32_t)a.x);
+  r.rem = (int64_t)(((uint64_t)(uint32_t)a.w << 32) | (uint32_t)a.z);
+  r.count = b.x; r.rpm = b.y; r.idx = b.z; r.flags = (uint32_t)b.w;
+  return r;
+#else
+  return *p;
+#endif
+}
 struct WordSumI { int32_t lo, hi; };  // min/max count over the 32 ranks of a bitmap word
 struct WordSumL { int64_t lo, hi; };  // min/max lruTime
 struct FreshRow { int64_t lru, rem; int32_t count, rpm; };  // getFreshInstanceRecord() (MM:5369-5386), what the walk reads of it
@@ -49,8 +62,11 @@ struct FreshRow { int64_t lru, rem; int32_t count, rpm; };  // getFreshInstanceR
 struct SnapshotView {  // pointers into HBM (or host vectors in the CPU harness)
   int32_t n_ranks, row_words, n_models, max_instances;
   int32_t any_rs, n_type_ids;
+  // instance sharding: this process holds words [word_lo, word_hi) of every exclusion row, stored at a
+  // stride of excl_stride words; [0, row_words) and row_words when the fleet is not sharded
+  int32_t word_lo, word_hi, excl_stride, shard_reserved;
   int64_t min_space;
-  const uint32_t *excl;        // [n_models][row_words] loaded ∪ failed, bit = rank
+  const uint32_t *excl;        // [n_models][excl_stride] loaded ∪ failed, bit = rank (word 0 of a stored row = row word word_lo)
   const uint32_t *cand;        // [n_slots][row_words]  allowed(type) ∧ active
   const uint32_t *candx;       // [n_slots][row_words]  cand ∧ ¬(likely-replaced replicaset members)  (MM:4769-4770)
   const uint32_t *pref;        // [n_slots][row_words]
@@ -61,6 +77,7 @@ struct SnapshotView {  // pointers into HBM (or host vectors in the CPU harness)
   const int32_t *rank_of;      // [max_instances]
   const WordSumI *csum;        // [row_words]
   const WordSumL *lsum;        // [row_words]
+  const int32_t *count_col;    // [row_words*32] count by rank, 0 past the last rank (exact evaluation of a mixed word)
   const mmp_model_row *models; // [n_models]
 };
 
@@ -149,6 +166,8 @@ struct CoopHost {
   MMP_HD bool rany(bool p) const { return p; }
   MMP_HD uint32_t exscan(uint32_t) const { return 0; }
   MMP_HD uint32_t shfl(uint32_t x, uint32_t) const { return x; }
+  MMP_HD bool spend() const { return true; }    // scan budget (CoopLane only): one unit per row word visited
+  MMP_HD bool bailed() const { return false; }
   template <class F> MMP_HD uint32_t eval_word(uint32_t wi, int32_t n_ranks, F &&f) const {
     uint32_t m = 0;
     for (int b = 0; b < 32; b++) {
@@ -156,6 +175,10 @@ struct CoopHost {
       if ((int32_t)r < n_ranks && f(r)) m |= 1u << b;
     }
     return m;
+  }
+  // members of xm (a subset of word wi) for which f holds; only the lowest such bit is guaranteed to be reported
+  template <class F> MMP_HD uint32_t eval_members(uint32_t wi, uint32_t xm, int32_t n_ranks, F &&f) const {
+    return eval_word(wi, n_ranks, f) & xm;
   }
   // ---- window values (the GPU keeps one word per lane of the tile; here the WN words are an array) ----
   struct W { uint32_t v[WN_]; };
@@ -196,6 +219,36 @@ struct CoopHost {
 };
 typedef CoopHost<32> Coop1;
 
+// ---- one decision per GPU lane (k_place_lanes): the single-lane shape with a budget on the row words a decision may
+// visit.  PLACEMENT_ORDER puts best and the shortlist at the front of the order, so almost every decision ends inside
+// its first few words; a lane whose walk runs long gives up (bailed()) so that it does not hold up the other 31
+// decisions of its warp, and that decision is redone cooperatively by the whole warp (Coop32).  Also compiled by g++
+// into the CPU harness, which checks it against the oracle. ----
+struct CoopLane {
+  static constexpr uint32_t L = 1;
+  mutable int32_t budget;
+  MMP_HD explicit CoopLane(int32_t words) : budget(words) {}
+  MMP_HD uint32_t lane() const { return 0; }
+  MMP_HD uint32_t rmin(uint32_t x) const { return x; }
+  MMP_HD uint32_t rsum(uint32_t x) const { return x; }
+  MMP_HD int32_t rmin_i(int32_t x) const { return x; }
+  MMP_HD bool rany(bool p) const { return p; }
+  MMP_HD uint32_t exscan(uint32_t) const { return 0; }
+  MMP_HD uint32_t shfl(uint32_t x, uint32_t) const { return x; }
+  MMP_HD bool spend() const { return --budget >= 0; }
+  MMP_HD bool bailed() const { return budget < 0; }
+  template <class F> MMP_HD uint32_t eval_members(uint32_t wi, uint32_t xm, int32_t n_ranks, F &&f) const {
+    while (xm) {  // ascending; the first hit is all the callers need
+      const int b = ffs32(xm);
+      const uint32_t r = wi * 32u + (uint32_t)b;
+      if ((int32_t)r < n_ranks && f(r)) return 1u << b;
+      xm &= xm - 1;
+    }
+    return 0u;
+  }
+  template <class F> MMP_HD uint32_t eval_word(uint32_t wi, int32_t n_ranks, F &&f) const { return eval_members(wi, 0xffffffffu, n_ranks, f); }
+};
+
 #if defined(__CUDACC__)
 // ---- the cooperative shape on the GPU: a tile of T lanes (T = 32: one decision per warp; T = 16: two decisions per
 // warp, each half-warp with its own 16-word window).  A window is T consecutive words of the row, one per lane. ----
@@ -226,6 +279,11 @@ struct CoopTile {
       if (lane_ >= (uint32_t)o) v += t;
     }
     return v - x;
+  }
+  MMP_D bool spend() const { return true; }
+  MMP_D bool bailed() const { return false; }
+  template <class F> MMP_D uint32_t eval_members(uint32_t wi, uint32_t xm, int32_t n_ranks, F &&f) const {
+    return eval_word(wi, n_ranks, f) & xm;
   }
   // exact 32-rank evaluation of one word by the tile (T = 16: two ranks per lane)
   template <class F> MMP_D uint32_t eval_word(uint32_t wi, int32_t n_ranks, F &&f) const {
@@ -261,6 +319,7 @@ typedef CoopTile<32> Coop32;
 template <class C, class W>
 MMP_HD uint32_t scan_first(const C &co, uint32_t from_word, uint32_t end_word, W &&word) {
   for (uint32_t wb = from_word; wb < end_word; wb += C::L) {
+    if (!co.spend()) break;
     const uint32_t wi = wb + co.lane();
     const uint32_t x = wi < end_word ? word(wi) : 0u;
     const uint32_t r = co.rmin(x ? wi * 32u + (uint32_t)ffs32(x) : NONE_RANK);
@@ -274,6 +333,7 @@ MMP_HD uint32_t scan_first(const C &co, uint32_t from_word, uint32_t end_word, W
 template <class C, class W, class CLS, class EV>
 MMP_HD uint32_t scan_first_violator(const C &co, uint32_t from_word, uint32_t end_word, int32_t n_ranks, W &&word, CLS &&cls, EV &&eval) {
   for (uint32_t wb = from_word; wb < end_word; wb += C::L) {
+    if (!co.spend()) break;
     const uint32_t wi = wb + co.lane();
     const uint32_t x = wi < end_word ? word(wi) : 0u;
     uint32_t A = NONE_RANK, M = NONE_RANK;
@@ -285,7 +345,7 @@ MMP_HD uint32_t scan_first_violator(const C &co, uint32_t from_word, uint32_t en
     uint32_t Amin = co.rmin(A), Mmin = co.rmin(M);
     while (Mmin != NONE_RANK && Mmin * 32u < Amin) {
       const uint32_t xm = co.shfl(x, Mmin - wb);
-      const uint32_t vm = co.eval_word(Mmin, n_ranks, eval) & xm;
+      const uint32_t vm = co.eval_members(Mmin, xm, n_ranks, eval);
       if (vm) { const uint32_t r = Mmin * 32u + (uint32_t)ffs32(vm); if (r < Amin) Amin = r; break; }
       if (M == Mmin) M = NONE_RANK;
       Mmin = co.rmin(M);
@@ -298,6 +358,7 @@ template <class C, class W>
 MMP_HD uint32_t scan_count(const C &co, uint32_t from_word, uint32_t end_word, W &&word) {
   uint32_t mine = 0;
   for (uint32_t wb = from_word; wb < end_word; wb += C::L) {
+    if (!co.spend()) break;
     const uint32_t wi = wb + co.lane();
     if (wi < end_word) mine += (uint32_t)popc32(word(wi));
   }
@@ -307,6 +368,7 @@ MMP_HD uint32_t scan_count(const C &co, uint32_t from_word, uint32_t end_word, W
 template <class C, class W>
 MMP_HD uint32_t scan_select(const C &co, uint32_t from_word, uint32_t end_word, W &&word, uint32_t kth) {
   for (uint32_t wb = from_word; wb < end_word; wb += C::L) {
+    if (!co.spend()) break;
     const uint32_t wi = wb + co.lane();
     const uint32_t x = wi < end_word ? word(wi) : 0u;
     const uint32_t c = (uint32_t)popc32(x), tot = co.rsum(c);
@@ -319,10 +381,37 @@ MMP_HD uint32_t scan_select(const C &co, uint32_t from_word, uint32_t end_word, 
   return NONE_RANK;
 }
 
+#define MMP_TF_FAST 256  // trace flag (not part of the ABI): resolved by the one-window fast path
+#define MMP_TF_BAIL 512  // internal: a CoopLane walk ran out of budget; the result is void, redo cooperatively
+#define MMP_TF_OPEN 1024 // instance-sharded: the walk ran off the end of this shard's rank range (unresolved here)
+
 struct DecideOut {
   int32_t target, n_candidates;
   int32_t best, n_remaining, pick_index, flags, cut_rank, best_rank;
+  int32_t first_rank;  // rank of the first filtered entry (before preferred handling): the min-loc key of a shard
 };
+
+// ---- instance-sharded combine.  Every shard resolves the decision over its own rank range as if its
+// first filtered entry were the global one and publishes ONE 64-bit key; the minimum over shards is the answer of the
+// shard that holds the globally first entry (min-loc under PLACEMENT_ORDER), provided its walk stayed inside its range.
+//   63      replicaset filter dropped (MM:4798-4802): any shard with a surviving entry under the filter sorts first
+//   62..46  first_rank (0x1ffff = no entry in this shard)
+//   45      open: the walk needs ranks beyond this shard (resolved by the row-gather pass)
+//   44..27  target + 3        26..9  n_candidates        8..0  shard rank (diagnostics)
+MMP_HD uint64_t shard_key(const DecideOut &o, int shard_rank) {
+  if (o.target == TARGET_INVALID) return ((uint64_t)0 << 46) | ((uint64_t)(TARGET_INVALID + 3) << 27) | (uint64_t)(shard_rank & 511);
+  if (o.first_rank < 0) return ~(uint64_t)0;
+  const bool open = (o.flags & MMP_TF_OPEN) != 0;
+  return ((uint64_t)((o.flags & MMP_TF_RS_RETRY) ? 1 : 0) << 63) | ((uint64_t)((uint32_t)o.first_rank & 0x1ffffu) << 46) |
+         ((uint64_t)(open ? 1 : 0) << 45) | ((uint64_t)(uint32_t)((open ? MMP_TARGET_NONE : o.target) + 3) << 27) |
+         ((uint64_t)(uint32_t)(open ? 0 : o.n_candidates) << 9) | (uint64_t)(shard_rank & 511);
+}
+MMP_HD bool shard_key_open(uint64_t k) { return k != ~(uint64_t)0 && ((k >> 45) & 1u) != 0; }
+MMP_HD void shard_key_decode(uint64_t k, int32_t &target, int32_t &n_candidates) {
+  if (k == ~(uint64_t)0) { target = MMP_TARGET_NONE; n_candidates = 0; return; }
+  target = (int32_t)((k >> 27) & 0x3ffffu) - 3;
+  n_candidates = (int32_t)((k >> 9) & 0x3ffffu);
+}
 
 // rpm-filter predicate of MM:4966-4974 for one recorded rpm
 struct RpmFilter {
@@ -364,13 +453,13 @@ MMP_HD void prepare_ctx(const SnapshotView &s, const mmp_decision_in &d, const F
   c.last_used = (d.flags & MMP_DF_MODEL_LAST_USED) ? mr.last_used : d.last_used;
   c.self_rank = s.rank_of[d.self];
   if (d.fresh >= 0 && d.fresh < n_fresh) c.fr = fresh_tab[d.fresh];
-  else if (c.self_rank >= 0) { const RankRow sr = s.rows[c.self_rank]; c.fr.lru = sr.lru; c.fr.rem = sr.rem; c.fr.count = sr.count; c.fr.rpm = 0; }
+  else if (c.self_rank >= 0) { const RankRow sr = load_row(s.rows + c.self_rank); c.fr.lru = sr.lru; c.fr.rem = sr.rem; c.fr.count = sr.count; c.fr.rpm = 0; }
   else return;
   const int sl = s.type_slot[tid];
   c.slot = sl | ((s.has_pref[sl] ? 1 : 0) << 16);
 }
 
-#define MMP_TF_FAST 256  // trace flag (not part of the ABI): resolved by the one-window fast path
+#define MMP_BAIL_CHECK do { if (co.bailed()) { o.flags |= MMP_TF_BAIL; o.target = MMP_TARGET_NONE; return; } } while (0)
 
 // The common case of getNext resolved inside ONE window of C::WN words (32 words = 1 024 ranks for a warp-wide tile,
 // 16 words for a half-warp tile) whose words stay in registers: best, the non-simple (a) probe, the cut, the shortlist
@@ -524,6 +613,250 @@ MMP_HD bool decide_fast(const SnapshotView &s, const DecisionCtx &c, const uint3
   return true;
 }
 
+// ---- vote shapes for decide_stream: 32 decisions in lockstep on the GPU, one on the CPU harness ----
+struct SoloVote { MMP_HD bool any(bool p) const { return p; } };
+#if defined(__CUDACC__)
+struct WarpVote { MMP_D bool any(bool p) const { return __any_sync(0xffffffffu, p) != 0; } };
+#endif
+
+// The common case of getNext for ONE DECISION PER LANE (k_place_lanes), written so that the 32 lanes of a warp stay
+// converged: every phase is a word-at-a-time walk whose loop is left by a warp vote, bodies are predicated on a per-lane
+// state, and the scalar work between the walks is straight-line.  Phases:
+//   A   first entry of F = cand & ~excl from the start of the row (MM:4806)
+//   A'  non-simple (a), MM:4828-4852: the first later entry that is preferred or full
+//   B   the shortlist walk (MM:4901-4937): first member of S that fails its test; a word whose count summary is
+//       "mixed" is evaluated exactly (32 counts) by all lanes that stopped on one, in one converged step
+//   C   the hash-indexed pick (MM:4981-4986): k-th member of the shortlist
+// Same semantics and quirks as decide_ctx (N2: the non-self test reads the caller's fresh record).  Returns false --
+// and the caller redoes the decision with the cooperative general routine -- for everything outside the common case:
+// malformed decision, extra excludes, no entry / best full (replicaset retry, non-simple (b)), or a walk longer than
+// `budget` row words.  Instance-sharded: a walk that needs ranks beyond this shard's range sets MMP_TF_OPEN.
+// Must be called by every lane of the vote group (active = false for lanes without a decision).
+template <class V>
+MMP_HD bool decide_stream(const SnapshotView &s, const DecisionCtx &c, bool active, const uint32_t *erow, int64_t now,
+                          uint64_t seed, uint64_t decision_id, const V &vote, DecideOut &o, int32_t budget) {
+  o.target = MMP_TARGET_NONE; o.n_candidates = 0; o.best = -1; o.n_remaining = 0; o.pick_index = 0; o.flags = 0;
+  o.cut_rank = (int32_t)NONE_RANK; o.best_rank = -1; o.first_rank = -1;
+  const uint32_t NW = (uint32_t)s.row_words, WS = (uint32_t)s.word_lo, WE = (uint32_t)s.word_hi;
+  const bool open_end = WE < NW;
+  bool live = active && c.slot >= 0 && c.d.extra_n == 0;
+  const mmp_decision_in &d = c.d;
+  const uint32_t so = (uint32_t)(live ? ctx_slot(c) : 0) * NW;
+  const uint32_t *CX = (s.any_rs ? s.candx : s.cand) + so;
+  const uint32_t *P = s.pref + so;
+  const bool favour_self = (d.flags & MMP_DF_FAVOUR_SELF) != 0;
+  const int32_t self_rank = c.self_rank;
+  const FreshRow fr = c.fr;
+  int32_t left = budget;
+  auto Fw = [&](uint32_t wi) -> uint32_t { return CX[wi] & ~erow[wi - WS]; };
+  auto pbit = [&](uint32_t r) -> bool { return (P[r >> 5] >> (r & 31)) & 1u; };
+
+  // ---- A: first filtered entry ----
+  uint32_t b = NONE_RANK;
+  {
+    uint32_t wi = WS;
+    bool search = live;
+    for (;;) {
+      if (search) {
+        if (wi >= WE || left <= 0) search = false;
+        else {
+          const uint32_t x = Fw(wi);
+          if (x) { b = wi * 32u + (uint32_t)ffs32(x); search = false; }
+          else { wi++; left--; }
+        }
+      }
+      if (!vote.any(search)) break;
+    }
+  }
+  if (b == NONE_RANK) live = false;  // none in reach: the general routine decides (replicaset retry, null)
+  RankRow rb; rb.lru = 0; rb.rem = 0; rb.count = 0; rb.rpm = 0; rb.idx = -1; rb.flags = 0;
+  bool us = false, simple = true, use_pref = false;
+  int64_t best_rem = 0;
+  int32_t best_count = 0, best_rpm = 0, best_idx = -1;
+  uint32_t best_rank = b, lo = b, hi = NONE_RANK;
+  if (live) {
+    rb = load_row(s.rows + b);
+    us = rb.idx == d.self;
+    best_rem = us ? fr.rem : rb.rem; best_count = us ? fr.count : rb.count; best_rpm = us ? fr.rpm : rb.rpm; best_idx = rb.idx;
+    if (best_rem < s.min_space) live = false;  // best full (MM:4811): general routine
+    const bool has_pref = ctx_has_pref(c);
+    simple = !has_pref || pbit(b);
+    use_pref = has_pref && simple;  // best is preferred: preference is treated as required (MM:4905-4907)
+  }
+  // ---- A': non-simple (a) ----
+  uint32_t r1 = NONE_RANK;
+  {
+    uint32_t wi = b >> 5;
+    bool search = live && !simple;
+    for (;;) {
+      if (search) {
+        if (wi >= WE) search = false;
+        else if (left <= 0) { search = false; live = false; }
+        else {
+          uint32_t x = Fw(wi) & (P[wi] | s.full[wi]) & mask_above(wi * 32u, b);
+          if (x) { r1 = wi * 32u + (uint32_t)ffs32(x); search = false; }
+          else { wi++; left--; }
+        }
+      }
+      if (!vote.any(search)) break;
+    }
+  }
+  bool open = false;
+  if (live && !simple) {
+    if (r1 == NONE_RANK) open = open_end;  // else: neither kind follows, "no preference" logic over the whole remainder
+    else if (pbit(r1)) {
+      const RankRow rp = load_row(s.rows + r1);
+      best_rank = r1; best_idx = rp.idx; best_rem = rp.rem; best_count = rp.count; best_rpm = rp.rpm;
+      us = rp.idx == d.self;
+      lo = r1; use_pref = true;
+    } else hi = r1;
+  }
+  bool done = false;
+  int32_t fl = MMP_TF_SIMPLE | MMP_TF_FAST;
+  if (live && !open && us && favour_self) { o.target = MMP_TARGET_SELF; fl |= MMP_TF_FAVOUR_EXIT; done = true; }
+  // ---- the walk's per-decision constants ----
+  bool walk = live && !open && !done;
+  bool self_in_s = false, c_self = false, self_viol = false;
+  uint32_t sw_ = 0xffffffffu, sb_ = 0;
+  int32_t thr = 0;
+  auto cv = [&](int32_t cnt) { return cnt >= 10 && cnt > thr; };  // MM:4924-4927
+  if (walk) {
+    if (self_rank >= 0 && (uint32_t)self_rank > lo && (uint32_t)self_rank < hi) {
+      const uint32_t w = (uint32_t)self_rank >> 5, bit = 1u << (self_rank & 31);
+      if (w - WS < WE - WS && (Fw(w) & bit) != 0 && (!use_pref || (P[w] & bit) != 0)) { self_in_s = true; sw_ = w; sb_ = bit; }
+    }
+    const int64_t q = best_rem >> 2;
+    c_self = fr.rem < s.min_space || fr.rem < q;
+    self_viol = rb.rem < s.min_space || rb.rem < q;
+    thr = jaddi(best_count, best_count >> 2);
+    if (self_in_s && cv(s.count_col[self_rank])) self_viol = true;
+  }
+  const uint32_t cut_self = (self_in_s && self_viol) ? (uint32_t)self_rank : NONE_RANK;
+  // S' = F restricted to (lo, lim), lim = min(hi, cut_self): nothing at or beyond a failing self can be a candidate
+  const uint32_t lim = hi < cut_self ? hi : cut_self;
+  uint32_t stop_w = WE;
+  if (lim != NONE_RANK) { const uint32_t e = (lim + 31u) >> 5; stop_w = e < WE ? e : WE; }
+  auto Sw = [&](uint32_t wi) -> uint32_t {
+    uint32_t m = Fw(wi) & mask_above(wi * 32u, lo) & mask_below(wi * 32u, lim);
+    return use_pref ? (m & P[wi]) : m;
+  };
+  // ---- B: first member of S' that fails its walk test, counting the members before it ----
+  uint32_t cut_others = NONE_RANK, n_in = 0;
+  {
+    uint32_t wi = lo >> 5, xt = 0;
+    bool search = walk, mixed = false;
+    for (;;) {
+      for (;;) {
+        if (search) {
+          if (wi >= stop_w) { search = false; if (lim == NONE_RANK && open_end) open = true; }
+          else if (left <= 0) { search = false; live = false; }
+          else {
+            const uint32_t x = Sw(wi);
+            int cls = 0;  // 0: no member fails, 1: every member (but a passing self) fails, 2: look at the counts
+            uint32_t v = x;
+            if (c_self) { if (wi == sw_) v &= ~sb_; cls = v ? 1 : 0; }
+            else if (x) { const WordSumI m = s.csum[wi]; cls = !cv(m.hi) ? 0 : (cv(m.lo) ? 1 : 2); }
+            if (cls == 0) { n_in += (uint32_t)popc32(x); wi++; left--; }
+            else {
+              search = false; xt = x;
+              if (cls == 1) cut_others = wi * 32u + (uint32_t)ffs32(v);
+              else mixed = true;
+            }
+          }
+        }
+        if (!vote.any(search)) break;
+      }
+      if (!vote.any(mixed)) break;
+      if (mixed) {  // exact evaluation of a mixed word: 32 counts, zero-padded past the last rank
+        mixed = false;
+        uint32_t vm = 0;
+#if defined(__CUDA_ARCH__)
+        const int4 *cc = reinterpret_cast<const int4 *>(s.count_col + (size_t)wi * 32u);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int4 q = __ldg(cc + j);
+          vm |= ((cv(q.x) ? 1u : 0u) | (cv(q.y) ? 2u : 0u) | (cv(q.z) ? 4u : 0u) | (cv(q.w) ? 8u : 0u)) << (4 * j);
+        }
+#else
+        const int32_t *cc = s.count_col + (size_t)wi * 32u;
+        for (int j = 0; j < 32; j++) vm |= (cv(cc[j]) ? 1u : 0u) << j;
+#endif
+        vm &= xt;
+        if (vm) cut_others = wi * 32u + (uint32_t)ffs32(vm);
+        else { n_in += (uint32_t)popc32(xt); wi++; left--; search = true; }
+      }
+      if (!vote.any(search)) break;
+    }
+    if (cut_others != NONE_RANK) n_in += (uint32_t)popc32(xt & mask_below((cut_others >> 5) * 32u, cut_others));
+  }
+  walk = walk && live && !open;
+  const uint32_t cut = cut_others < cut_self ? cut_others : cut_self;
+  const bool self_in_sl = self_in_s && (uint32_t)self_rank < cut;
+  bool keep_best = true, keep_others = true, keep_self = true, sel = false;
+  int32_t remaining = 0, ccount = 0;
+  uint32_t index = 0, kth = 0, chosen_rank = best_rank;
+  if (walk) {
+    if (favour_self && self_in_sl) { o.target = MMP_TARGET_SELF; fl |= MMP_TF_FAVOUR_EXIT; done = true; }
+    else {
+      const int32_t n_others = (int32_t)n_in - (self_in_sl ? 1 : 0);
+      ccount = 1 + (int32_t)n_in;
+      remaining = ccount;
+      if (ccount > 1) {
+        const int64_t ago = age_of(c.last_used, now);
+        if (ago < 432000000LL) {  // FIVE_DAYS_MS
+          int32_t mn = best_rpm;
+          if (n_others > 0 && fr.rpm < mn) mn = fr.rpm;
+          if (self_in_sl && rb.rpm < mn) mn = rb.rpm;
+          RpmFilter rf; rf.init(mn, ago);
+          keep_best = !rf.drop(best_rpm); keep_others = !rf.drop(fr.rpm); keep_self = !rf.drop(rb.rpm);
+          remaining = (keep_best ? 1 : 0) + (keep_others ? n_others : 0) + ((self_in_sl && keep_self) ? 1 : 0);
+        }
+        index = remaining == 1 ? 0u : hash_index(seed, decision_id, (uint32_t)remaining);
+      }
+      kth = index;
+      if (!(keep_best && kth == 0)) {
+        if (keep_best) kth--;
+        if (!keep_others) chosen_rank = (uint32_t)self_rank;  // the only other survivor can be the self candidate
+        else sel = true;
+      }
+    }
+  }
+  // ---- C: k-th survivor in rank order ----
+  {
+    const bool drop_self = self_in_sl && !keep_self;
+    uint32_t wi = lo >> 5;
+    bool search = sel;
+    for (;;) {
+      if (search) {
+        if (wi >= stop_w) { search = false; live = false; }  // cannot happen: kth < number of survivors
+        else {
+          uint32_t x = Sw(wi) & mask_below(wi * 32u, cut);
+          if (drop_self && wi == sw_) x &= ~sb_;
+          const uint32_t n = (uint32_t)popc32(x);
+          if (kth < n) { chosen_rank = wi * 32u + (uint32_t)nth_bit(x, kth); search = false; }
+          else { kth -= n; wi++; }
+        }
+      }
+      if (!vote.any(search)) break;
+    }
+  }
+  if (!active) return true;
+  if (!live) return false;
+  o.first_rank = (int32_t)b;
+  o.best = best_idx; o.best_rank = (int32_t)best_rank;
+  if (open) { o.flags = MMP_TF_OPEN; return true; }
+  if (!done) {
+    const int32_t cidx = chosen_rank == best_rank ? best_idx : s.rows[chosen_rank].idx;
+    o.target = (!favour_self && cidx == d.self) ? MMP_TARGET_SELF : cidx;
+    o.n_candidates = ccount;
+    o.n_remaining = remaining; o.pick_index = (int32_t)index;
+    fl |= (keep_best ? MMP_TF_KEEP_BEST : 0) | (keep_others ? MMP_TF_KEEP_OTHERS : 0) | (keep_self ? MMP_TF_KEEP_SELF : 0);
+  }
+  o.cut_rank = (int32_t)(walk || (done && cut != NONE_RANK) ? cut : NONE_RANK);
+  o.flags = fl;
+  return true;
+}
+
 // One getNext.  erow: this decision's exclusion row, readable by every lane (shared memory on the GPU) until the
 // routine returns.  cand_rows (optional, trace): [2][row_words] receives the candidate mask (other than best) and the
 // survivor mask.
@@ -531,8 +864,11 @@ template <class C>
 MMP_HD void decide_ctx(const SnapshotView &s, const DecisionCtx &c, const uint32_t *erow, const int32_t *extra, int64_t now,
                        uint64_t seed, uint64_t decision_id, const C &co, DecideOut &o, uint32_t *cand_rows) {
   o.target = MMP_TARGET_NONE; o.n_candidates = 0; o.best = -1; o.n_remaining = 0; o.pick_index = 0; o.flags = 0;
-  o.cut_rank = (int32_t)NONE_RANK; o.best_rank = -1;
+  o.cut_rank = (int32_t)NONE_RANK; o.best_rank = -1; o.first_rank = -1;
   const uint32_t NW = (uint32_t)s.row_words;
+  // this process's part of the row: words [WS, WE); erow[0] is row word WS.  Not sharded: [0, NW).
+  const uint32_t WS = (uint32_t)s.word_lo, WE = (uint32_t)s.word_hi;
+  const bool open_end = WE < NW;  // ranks from WE*32 on live in another shard
   if (c.slot < 0) { o.target = TARGET_INVALID; return; }
   const mmp_decision_in &d = c.d;
   const int slot = ctx_slot(c);
@@ -543,37 +879,41 @@ MMP_HD void decide_ctx(const SnapshotView &s, const DecisionCtx &c, const uint32
   const uint32_t *P = s.pref + (size_t)slot * NW;
   const int n_extra = d.extra_n < 16 ? d.extra_n : 16;
   auto end_for = [&](uint32_t hi_rank) -> uint32_t {  // one past the last word that can hold a rank < hi_rank
-    if (hi_rank == NONE_RANK) return NW;
+    if (hi_rank == NONE_RANK) return WE;
     uint32_t e = (hi_rank + 31u) >> 5;
-    return e < NW ? e : NW;
+    return e < WE ? e : WE;
   };
   auto emit_rows = [&](auto &&w0f, auto &&w1f) {  // trace only
-    for (uint32_t wb = 0; wb < NW; wb += C::L) {
+    for (uint32_t wb = WS; wb < WE; wb += C::L) {
       uint32_t wi = wb + co.lane();
-      if (wi < NW) { cand_rows[wi] = w0f(wi); cand_rows[NW + wi] = w1f(wi); }
+      if (wi < WE) { cand_rows[wi] = w0f(wi); cand_rows[NW + wi] = w1f(wi); }
     }
   };
 
   // ---- filter (MM:4760-4771): candx already excludes likely-replaced replicaset members ----
   const uint32_t *CX = s.any_rs ? s.candx + (size_t)slot * NW : CAND;
   // word wi of the filtered set F
-  auto Fw = [&](uint32_t wi) -> uint32_t {
-    uint32_t m = CX[wi] & ~erow[wi];
+  auto Fw = [&](uint32_t wi) -> uint32_t {  // wi in [WS, WE)
+    uint32_t m = CX[wi] & ~erow[wi - WS];
     for (int e = 0; e < n_extra; e++) {
       int32_t x = extra[d.extra_off + e];
       if (x >= 0 && x < s.max_instances) { int32_t r = s.rank_of[x]; if (r >= 0 && (uint32_t)(r >> 5) == wi) m &= ~(1u << (r & 31)); }
     }
     return m;
   };
-  uint32_t b = scan_first(co, 0, NW, Fw);
+  uint32_t b = scan_first(co, WS, WE, Fw);
+  MMP_BAIL_CHECK;
   if (b == NONE_RANK && s.any_rs) {
     // MM:4798-4802: nothing survives; run the filter again without the replicaset exclusion
     o.flags |= MMP_TF_RS_RETRY;
     CX = CAND;
-    b = scan_first(co, 0, NW, Fw);
+    b = scan_first(co, WS, WE, Fw);
+    MMP_BAIL_CHECK;
   }
   if (b == NONE_RANK) return;  // null
-  auto in_filter = [&](uint32_t r) -> bool { return (Fw(r >> 5) >> (r & 31)) & 1u; };
+  // a rank outside this shard's range reads as "not in the filtered set": it can only be asked about self, and self
+  // matters to a walk only below the cut, i.e. inside the range whenever the walk is resolved here
+  auto in_filter = [&](uint32_t r) -> bool { return ((r >> 5) - WS) < (WE - WS) && ((Fw(r >> 5) >> (r & 31)) & 1u); };
   auto pref_bit = [&](uint32_t r) -> bool { return (P[r >> 5] >> (r & 31)) & 1u; };
 
   const RankRow rb = s.rows[b];  // bestEntry.getValue()
@@ -587,17 +927,19 @@ MMP_HD void decide_ctx(const SnapshotView &s, const DecisionCtx &c, const uint32
   bool simple = !has_pref || pref_bit(b);
   uint32_t lo = b, hi = NONE_RANK;
   bool use_pref = has_pref && simple;  // best is preferred: preference is treated as required (MM:4905-4907)
-  o.best = best_idx; o.best_rank = (int32_t)b;
+  o.best = best_idx; o.best_rank = (int32_t)b; o.first_rank = (int32_t)b;
+#define MMP_OPEN_EXIT do { o.flags |= MMP_TF_OPEN; o.target = MMP_TARGET_NONE; o.n_candidates = 0; return; } while (0)
 
   if (!simple) {
     if (!best_full) {
       // non-simple (a) MM:4828-4852: first later entry that is preferred, unless a full one comes first.
       // One fused scan: stop at the first window that holds either.
       uint32_t p1 = NONE_RANK, f1 = NONE_RANK;
-      for (uint32_t wb = b >> 5; wb < NW; wb += C::L) {
+      for (uint32_t wb = b >> 5; wb < WE; wb += C::L) {
+        if (!co.spend()) break;
         const uint32_t wi = wb + co.lane();
         uint32_t xp = 0, xf = 0;
-        if (wi < NW) {
+        if (wi < WE) {
           const uint32_t x = Fw(wi) & mask_above(wi * 32u, b), pw = P[wi];
           xp = x & pw; xf = x & s.full[wi] & ~pw;
         }
@@ -605,6 +947,8 @@ MMP_HD void decide_ctx(const SnapshotView &s, const DecisionCtx &c, const uint32
         f1 = co.rmin(xf ? wi * 32u + (uint32_t)ffs32(xf) : NONE_RANK);
         if (p1 != NONE_RANK || f1 != NONE_RANK) break;
       }
+      MMP_BAIL_CHECK;
+      if (open_end && p1 == NONE_RANK && f1 == NONE_RANK) MMP_OPEN_EXIT;  // the deciding entry is in a later shard
       if (p1 < f1) {
         const RankRow rp = s.rows[p1];
         best_rank = p1; best_idx = rp.idx; best_rem = rp.rem; best_lru = rp.lru; best_count = rp.count; best_rpm = rp.rpm;
@@ -617,13 +961,16 @@ MMP_HD void decide_ctx(const SnapshotView &s, const DecisionCtx &c, const uint32
       // non-simple (b) MM:4853-4887
       const int64_t oldest = best_lru, a4 = age_of(oldest, now) / 4;
       auto viol = [&](int64_t l) { int64_t diff = jsub(l, oldest); return diff > 120000 && diff > a4; };
-      const uint32_t kb = scan_first_violator(co, b >> 5, NW, s.n_ranks,
+      const uint32_t kb = scan_first_violator(co, b >> 5, WE, s.n_ranks,
           [&](uint32_t wi) { return Fw(wi) & mask_above(wi * 32u, b); },
           [&](uint32_t wi) { WordSumL m = s.lsum[wi]; return !viol(m.hi) ? 0 : (viol(m.lo) ? 1 : 2); },
           [&](uint32_t r) { return viol(s.rows[r].lru); });
+      MMP_BAIL_CHECK;
+      if (open_end && kb == NONE_RANK) MMP_OPEN_EXIT;
       const uint32_t endb = end_for(kb);
       auto Cw = [&](uint32_t wi) { return Fw(wi) & P[wi] & mask_above(wi * 32u, b) & mask_below(wi * 32u, kb); };
       const uint32_t firstp = scan_first(co, b >> 5, endb, Cw);
+      MMP_BAIL_CHECK;
       if (firstp != NONE_RANK) {
         // only preferred instances within the age distance are candidates; each records its own published rpm
         o.flags |= MMP_TF_PREF_B;
@@ -635,6 +982,7 @@ MMP_HD void decide_ctx(const SnapshotView &s, const DecisionCtx &c, const uint32
           return;
         }
         const int32_t ccount = (int32_t)scan_count(co, firstp >> 5, endb, Cw);
+        MMP_BAIL_CHECK;
         o.n_candidates = ccount;
         uint32_t chosen;
         if (ccount == 1) {
@@ -649,6 +997,7 @@ MMP_HD void decide_ctx(const SnapshotView &s, const DecisionCtx &c, const uint32
           if (filter) {
             int32_t mn = 2147483647;
             for (uint32_t wb = firstp >> 5; wb < endb; wb += C::L) {
+              if (!co.spend()) break;
               const uint32_t wi = wb + co.lane();
               uint32_t w = wi < endb ? Cw(wi) : 0u;
               while (w) { int bt = ffs32(w); w &= w - 1; int32_t v = s.rows[wi * 32 + bt].rpm; if (v < mn) mn = v; }
@@ -663,6 +1012,7 @@ MMP_HD void decide_ctx(const SnapshotView &s, const DecisionCtx &c, const uint32
           if (filter) remaining = (int32_t)scan_count(co, firstp >> 5, endb, Kw);
           uint32_t index = remaining == 1 ? 0u : hash_index(seed, decision_id, (uint32_t)remaining);
           chosen = scan_select(co, firstp >> 5, endb, Kw, index);
+          MMP_BAIL_CHECK;
           o.n_remaining = remaining; o.pick_index = (int32_t)index;
           if (cand_rows) emit_rows(Cw, Kw);
         }
@@ -713,14 +1063,17 @@ MMP_HD void decide_ctx(const SnapshotView &s, const DecisionCtx &c, const uint32
         [&](uint32_t wi) { WordSumI m = s.csum[wi]; return !cv(m.hi) ? 0 : (cv(m.lo) ? 1 : 2); },
         [&](uint32_t r) { return cv(s.rows[r].count); });
   }
+  MMP_BAIL_CHECK;
   const uint32_t cut_self = (self_in_s && self_viol) ? (uint32_t)self_rank : NONE_RANK;
   const uint32_t cut = cut_others < cut_self ? cut_others : cut_self;
   o.cut_rank = (int32_t)cut;
+  if (open_end && cut == NONE_RANK && hi == NONE_RANK) MMP_OPEN_EXIT;  // the shortlist runs on into the next shard
   const bool self_in_sl = self_in_s && (uint32_t)self_rank < cut;
   if (favour_self && self_in_sl) { o.flags |= MMP_TF_FAVOUR_EXIT; o.target = MMP_TARGET_SELF; return; }
   const uint32_t endc = cut == NONE_RANK ? end : (end_for(cut) < end ? end_for(cut) : end);
   auto SLw = [&](uint32_t wi) -> uint32_t { return Sw(wi) & mask_below(wi * 32u, cut); };  // candidates other than best
   const int32_t n_in = (int32_t)scan_count(co, from, endc, SLw);
+  MMP_BAIL_CHECK;
   const int32_t n_others = n_in - (self_in_sl ? 1 : 0);
   const int32_t ccount = 1 + n_in;
   o.n_candidates = ccount;
@@ -756,6 +1109,7 @@ MMP_HD void decide_ctx(const SnapshotView &s, const DecisionCtx &c, const uint32
     if (keep_best) kth--;
     if (!keep_others) chosen_rank = (uint32_t)self_rank;  // the only other survivor can be the self candidate
     else chosen_rank = scan_select(co, from, endc, SVw, kth);
+    MMP_BAIL_CHECK;
   }
   const int32_t cidx = chosen_rank == best_rank ? best_idx : s.rows[chosen_rank].idx;
   o.target = (!favour_self && cidx == d.self) ? MMP_TARGET_SELF : cidx;

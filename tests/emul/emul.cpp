@@ -23,18 +23,29 @@ struct mmp_fleet {
   std::vector<mmp_model_row> models;
   int32_t epoch = 0;
   int64_t launches = 0;
+  uint64_t *keys = nullptr;  // harness-only: per-decision instance-shard keys of the next batch (mmp_emul_set_keys)
 };
 static thread_local std::string g_err;
-static int g_window = 32;  // fast-path window width under test (32: warp tile, 16: half-warp tile)
+static int g_window = 32;  // fast-path window width under test (32: warp tile, 16: half-warp tile); 1: lane-per-decision shape
+static int g_lane_budget = 48;  // CoopLane walk budget (row words) when g_window == 1
+static long g_bails = 0, g_lane_decisions = 0;
 
 extern "C" {
 
 int32_t mmp_abi_version(void) { return MMP_ABI_VERSION; }
-void mmp_emul_set_window(int w) { g_window = (w == 16 || w == 8) ? w : 32; }  // harness-only entry point
+void mmp_emul_set_window(int w) { g_window = (w == 16 || w == 8 || w == 1 || w == 2) ? w : 32; }  // harness-only entry points
+void mmp_emul_set_lane_budget(int words) { g_lane_budget = words; }
+void mmp_emul_set_keys(mmp_fleet *f, uint64_t *keys) { f->keys = keys; }
+void mmp_emul_key_decode(uint64_t k, int32_t *target, int32_t *n_candidates, int32_t *open) {
+  shard_key_decode(k, *target, *n_candidates);
+  *open = shard_key_open(k) ? 1 : 0;
+}
+long mmp_emul_lane_bails(long *decisions) { long b = g_bails; if (decisions) *decisions = g_lane_decisions; g_bails = g_lane_decisions = 0; return b; }
 const char *mmp_last_error(mmp_fleet *) { return g_err.c_str(); }
 
 int32_t mmp_fleet_create(const mmp_config *cfg, mmp_fleet **out) {
   if (!cfg || !out || cfg->max_instances <= 0 || cfg->max_instances > 65536 || cfg->max_models <= 0) { g_err = "bad config"; return MMP_E_ARG; }
+  if (cfg->shard_count < 1 || cfg->shard_rank < 0 || cfg->shard_rank >= cfg->shard_count) { g_err = "bad shard_rank/shard_count"; return MMP_E_ARG; }
   auto *f = new mmp_fleet();
   f->hs.init(*cfg);
   *out = f;
@@ -71,10 +82,12 @@ int32_t mmp_fleet_commit(mmp_fleet *f) {
   const int RW = f->snap.row_words;
   const int32_t nm = f->hs.n_models_used;
   f->models.assign(f->hs.models.begin(), f->hs.models.begin() + nm);
-  f->excl.assign((size_t)nm * RW, 0u);
+  const int32_t WS = f->snap.word_lo, WE = f->snap.word_hi, ST = f->snap.excl_stride;
+  (void)RW;
+  f->excl.assign((size_t)nm * ST, 0u);
   auto setbit = [&](int32_t m, int32_t inst) {
     int32_t r = f->snap.rank_of[inst];
-    if (r >= 0) f->excl[(size_t)m * RW + (r >> 5)] |= 1u << (r & 31);
+    if (r >= 0 && (r >> 5) >= WS && (r >> 5) < WE) f->excl[(size_t)m * ST + ((r >> 5) - WS)] |= 1u << (r & 31);
   };
   for (int32_t m = 0; m < nm; m++)
     for (int i = 0; i < HostState::EDGE_INL; i++) {
@@ -91,6 +104,8 @@ static SnapshotView make_view(mmp_fleet *f) {
   const HostSnapshot &s = f->snap;
   v.n_ranks = s.n_ranks; v.row_words = s.row_words; v.n_models = (int32_t)f->models.size(); v.max_instances = f->hs.cfg.max_instances;
   v.any_rs = s.any_rs; v.n_type_ids = (int32_t)s.type_slot.size(); v.min_space = f->hs.cfg.min_space_units;
+  v.word_lo = s.word_lo; v.word_hi = s.word_hi; v.excl_stride = s.excl_stride; v.shard_reserved = 0;
+  v.count_col = s.count_col.data();
   v.excl = f->excl.data(); v.cand = s.cand.data(); v.candx = s.candx.data(); v.pref = s.pref.data(); v.has_pref = s.has_pref.data();
   v.type_slot = s.type_slot.data(); v.full = s.full.data(); v.rows = s.rows.data();
   v.rank_of = s.rank_of.data(); v.csum = s.csum.data(); v.lsum = s.lsum.data(); v.models = f->models.data();
@@ -115,15 +130,29 @@ int32_t mmp_place_batch_trace(mmp_fleet *f, const mmp_decision_in *in, int32_t n
     DecideOut o;
     DecisionCtx cx;
     prepare_ctx(v, in[i], fr.data(), n_fresh, cx);
-    const uint32_t *erow = v.excl + (size_t)(cx.slot >= 0 ? in[i].model : 0) * v.row_words;
+    const uint32_t *erow = v.excl + (size_t)(cx.slot >= 0 ? in[i].model : 0) * v.excl_stride;
+    const bool sharded = v.word_lo != 0 || v.word_hi != v.row_words;
     bool done = false;
-    if (!cand_mask) done = win == 16 ? decide_fast<true>(v, cx, erow, now_ms, seed, (uint64_t)i, co16, o)
+    if (win == 2 && !cand_mask) {  // the lockstep lane routine of k_place_lanes (one decision per lane), general routine when it declines
+      done = decide_stream(v, cx, true, erow, now_ms, seed, (uint64_t)i, SoloVote(), o, g_lane_budget);
+      g_lane_decisions++;
+      if (!done) g_bails++;
+    } else if (sharded) {
+      // instance-sharded harness: only the general routine knows about rank ranges (decide_fast assumes whole rows)
+    } else if (win == 1 && !cand_mask) {  // the lane-per-decision shape of k_place_lanes: budgeted walk, cooperative redo when it bails
+      CoopLane cl(g_lane_budget);
+      decide_ctx<CoopLane>(v, cx, erow, extra, now_ms, seed, (uint64_t)i, cl, o, nullptr);
+      g_lane_decisions++;
+      done = !(o.flags & MMP_TF_BAIL);
+      if (!done) g_bails++;
+    } else if (!cand_mask) done = win == 16 ? decide_fast<true>(v, cx, erow, now_ms, seed, (uint64_t)i, co16, o)
                          : win == 8 ? decide_fast<true>(v, cx, erow, now_ms, seed, (uint64_t)i, co8, o)
                                     : decide_fast<true>(v, cx, erow, now_ms, seed, (uint64_t)i, co, o);
     if (!done)
       decide_ctx<Coop1>(v, cx, erow, extra, now_ms, seed, (uint64_t)i, co, o,
                         cand_mask ? cand_mask + (size_t)i * 2 * v.row_words : nullptr);
     out[i].target = o.target; out[i].n_candidates = o.n_candidates;
+    if (f->keys) f->keys[i] = shard_key(o, f->hs.cfg.shard_rank);
     if (trace) {
       trace[i].best = o.best; trace[i].n_remaining = o.n_remaining; trace[i].pick_index = o.pick_index; trace[i].flags = o.flags;
       trace[i].cut_rank = o.cut_rank; trace[i].best_rank = o.best_rank; trace[i].reserved[0] = trace[i].reserved[1] = 0;

@@ -54,3 +54,52 @@ def test_half_warp_window_matches_oracle(emul_lib, oracle_lib, config, nm, ni, s
         compare_decisions(fl, sd, o, s, seed=seed)
     finally:
         emul_lib.mmp_emul_set_window(32)
+
+
+@pytest.mark.parametrize("budget", [2, 48])
+@pytest.mark.parametrize("shape", [1, 2])
+@pytest.mark.parametrize("config,nm,ni,seed", [("C2", 2000, 1000, 12), ("C3", 4000, 700, 3), ("C5", 3000, 500, 5), ("MIX", 600, 160, 8),
+                                               ("MIX", 600, 300, 14), ("MIX", 600, 97, 21), ("C3", 1500, 1300, 33)])
+def test_lane_shape_matches_oracle(emul_lib, oracle_lib, config, nm, ni, seed, budget, shape):
+    """The lane-per-decision shapes: 1 = the general routine as a budgeted single-lane walk (CoopLane), 2 = the lockstep
+    streaming routine k_place_lanes runs (decide_stream); both with the cooperative redo when the lane declines.
+    budget=2 forces most decisions through the redo path; 48 is the kernel's setting."""
+    import ctypes as C
+    emul_lib.mmp_emul_lane_bails.restype = C.c_long
+    emul_lib.mmp_emul_set_window(shape)
+    emul_lib.mmp_emul_set_lane_budget(budget)
+    try:
+        fl = make_fleet(config, nm, ni, seed)
+        o = oracle_from_synth(fl)
+        s = solver_from_synth(fl, emul_lib)
+        emul_lib.mmp_emul_lane_bails(None)
+        sd = make_decisions(fl, 2500, seed)
+        compare_decisions(fl, sd, o, s, seed=seed * 31)
+        sd = make_decisions(fl, 1500, seed + 1, sweep=True, plain=True)
+        compare_decisions(fl, sd, o, s, seed=seed)
+        n = C.c_long()
+        bails = emul_lib.mmp_emul_lane_bails(C.byref(n))
+        assert n.value > 0
+        if budget == 2 and ni >= 300:
+            assert bails > 0  # the redo path was exercised
+    finally:
+        emul_lib.mmp_emul_set_window(32)
+        emul_lib.mmp_emul_set_lane_budget(48)
+
+
+@pytest.mark.parametrize("seed", range(40, 70))
+def test_stream_routine_mixed_regimes(emul_lib, oracle_lib, seed):
+    """decide_stream (the lockstep lane routine) on regime-randomised fleets, with a budget small enough that both its
+    own answers and its hand-offs to the general routine occur."""
+    emul_lib.mmp_emul_set_window(2)
+    emul_lib.mmp_emul_set_lane_budget([3, 8, 48][seed % 3])
+    try:
+        ni = [33, 64, 97, 160, 300, 700][seed % 6]
+        fl = make_fleet("MIX", 500, ni, seed)
+        o = oracle_from_synth(fl)
+        s = solver_from_synth(fl, emul_lib)
+        sd = make_decisions(fl, 1200, seed)
+        compare_decisions(fl, sd, o, s, seed=seed + 5, full_lists=False)
+    finally:
+        emul_lib.mmp_emul_set_window(32)
+        emul_lib.mmp_emul_set_lane_budget(48)

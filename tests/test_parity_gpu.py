@@ -35,3 +35,21 @@ def test_mixed_regimes_match_oracle(product_lib, oracle_lib, seed):
     assert np.array_equal(s.cluster_order(), o.cluster_order())
     sd = make_decisions(fl, 1500, seed)
     compare_decisions(fl, sd, o, s, seed=seed + 99)
+
+
+@pytest.mark.parametrize("kernel,tile,ring_k", [("lanes", 16, 4), ("tile", 8, 4), ("tile", 16, 2), ("tile", 16, 4), ("tile", 32, 4)])
+@pytest.mark.parametrize("config,nm,ni,seed", [("C3", 4000, 10000, 3), ("C5", 3000, 5000, 5), ("MIX", 600, 300, 14), ("C2", 3000, 1000, 2),
+                                               ("C3", 2000, 16000, 7)])
+def test_kernel_variants_match_oracle(product_lib, oracle_lib, monkeypatch, kernel, tile, ring_k, config, nm, ni, seed):
+    """k_place_lanes (one decision per lane, the default) and every tile width / ring depth of the cooperative k_place
+    give the same, oracle-identical answers."""
+    monkeypatch.setenv("MMP_KERNEL", kernel)
+    monkeypatch.setenv("MMP_TILE", str(tile))
+    monkeypatch.setenv("MMP_RING_K", str(ring_k))
+    fl = make_fleet(config, nm, ni, seed)
+    o = oracle_from_synth(fl)
+    s = solver_from_synth(fl, product_lib)
+    sd = make_decisions(fl, 2500, seed)
+    compare_decisions(fl, sd, o, s, seed=seed * 17, full_lists=False)
+    sd = make_decisions(fl, 2500, seed + 1, sweep=True, plain=True)
+    compare_decisions(fl, sd, o, s, seed=seed, full_lists=False)
