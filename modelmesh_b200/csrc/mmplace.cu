@@ -289,53 +289,71 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_place(const SnapshotView s
 // ---------------------------------------------------------------------------------------------------------------
 // k_place_lanes — the production scoring kernel: ONE DECISION PER LANE.
 //
-// Each warp owns a stage of 32 exclusion rows in shared memory.  Per step every lane (1) reads its decision record,
-// (2) issues the TMA bulk copy of its model's bitmap row (cp.async.bulk, one mbarrier per warp: 32 arrivals + 32 x
-// row_bytes transaction bytes), (3) gathers its decision context (model row, rank_of[self], the caller's row, type slot)
-// while the 32 rows stream in from HBM, (4) resolves its decision out of its staged row with the single-lane walk
-// (mmp::decide_ctx<CoopLane>: the same routine the CPU harness checks against the oracle), (5) writes its 8-byte
-// result (coalesced).  Blocks are single warps, so an SM holds floor(227 KB / stage) independent warps (5 at 10k
-// instances) whose load and compute phases interleave: ~200 KB of rows in flight per SM keeps HBM saturated while the
-// per-decision instruction cost drops from ~450 warp instructions (cooperative tiles) to ~30.
-// A walk that exceeds its word budget (long shortlists: adversarial fleets) bails and is redone by the whole warp
-// (decide_warp: Coop32 fast path, then the general routine) from the same staged row.
-// Rows are staged at a stride of row_bytes + 16 so that lanes reading the same word of their own rows spread over
-// the banks (16-byte granules: 8 lanes cover the 32 banks).
+// One persistent block per SM.  Shared memory holds NS "landing stages" of 32 exclusion rows each (TMA bulk-copy
+// destinations, one mbarrier per stage) that the block's warps share, and a small private window buffer per warp.
+// A warp's step over a batch of 32 decisions:
+//   1. claim the batch (atomic counter) and read its 32 decision records (prefetched one step ahead);
+//   2. acquire a free landing stage; every lane issues the cp.async.bulk of its model's bitmap row into it
+//      (32 arrivals + 32 x row bytes of transaction count on the stage's mbarrier);
+//   3. gather the decision context (model row, rank_of[self], the caller's row, type slot) while the rows stream in;
+//   4. when the stage has landed, copy the first WIN words of its row and the word holding self's bit out of the stage
+//      and RELEASE the stage, so the next 41 KB of rows is in flight while this warp is still computing;
+//   5. resolve the 32 decisions in lockstep from the window buffer (mmp::decide_stream) and write the 8-byte results.
+// PLACEMENT_ORDER puts best and the shortlist at the front of the rank order, so the window answers almost every
+// decision; what it cannot (long walks on adversarial fleets, uncommon paths) is redone by the whole warp with the
+// cooperative general routine reading the row from global memory (it was just streamed: L2).
+// The stages keep ~NS x 41 KB per SM in flight from HBM independently of how many warps are computing, and the
+// per-decision instruction cost is ~70 warp instructions / 32 lanes instead of ~450 for a cooperative tile.
+// Rows are staged at a stride of row_bytes + 16 so that lanes reading their own rows spread over the banks.
 // ---------------------------------------------------------------------------------------------------------------
+static constexpr int LANE_WIN = 16;     // row words copied out of the landing stage per decision
+static constexpr int LANE_BUDGET = 64;  // row-word visits a lane may spend before handing its decision to the warp
 struct LaneLayout {
-  uint32_t row_bytes, stride;
-  size_t per_warp;
-  __host__ __device__ explicit LaneLayout(int row_words) : row_bytes((uint32_t)row_words * 4u), stride((uint32_t)row_words * 4u + 16u) {
-    per_warp = ((size_t)32 * stride + sizeof(DecisionCtx) + 16 + 127) / 128 * 128;
+  uint32_t row_bytes, stride, stage_bytes, ns, warps;
+  uint32_t off_bar, off_busy, off_uses, off_warp, per_warp;
+  size_t total;
+  __host__ __device__ LaneLayout(int row_words, int ns_, int warps_) {
+    row_bytes = (uint32_t)row_words * 4u; stride = row_bytes + 16u;
+    stage_bytes = (32u * stride + 127u) / 128u * 128u;
+    ns = (uint32_t)ns_; warps = (uint32_t)warps_;
+    off_bar = ns * stage_bytes; off_busy = off_bar + ns * 8u; off_uses = off_busy + ns * 4u;
+    off_warp = (off_uses + ns * 4u + 127u) / 128u * 128u;
+    per_warp = (32u * (LANE_WIN + 1) * 4u + (uint32_t)((sizeof(DecisionCtx) + 15) / 16 * 16) + 127u) / 128u * 128u;
+    total = (size_t)off_warp + (size_t)warps * per_warp;
   }
 };
-static constexpr int LANE_BUDGET = 48;  // row words one lane may visit before handing its decision to the warp
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) k_place_lanes(const SnapshotView s, const mmp_decision_in *__restrict__ in, int n,
-                                                            const FreshRow *__restrict__ fresh, int n_fresh,
-                                                            const int32_t *__restrict__ extra, mmp_decision_out *__restrict__ out,
-                                                            int64_t now, uint64_t seed, uint64_t id_base) {
+__global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotView s, const mmp_decision_in *__restrict__ in, int n,
+                                                               const FreshRow *__restrict__ fresh, int n_fresh,
+                                                               const int32_t *__restrict__ extra, mmp_decision_out *__restrict__ out,
+                                                               int64_t now, uint64_t seed, uint64_t id_base, int ns,
+                                                               int *__restrict__ batch_counter) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int RW = s.excl_stride;  // words per stored row (the whole row unless the fleet is instance-sharded)
-  const LaneLayout lay(RW);
+  const LaneLayout lay(RW, ns, WARPS);
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned char *base = smem_raw + (size_t)wib * lay.per_warp;
-  const uint32_t *my_row = reinterpret_cast<const uint32_t *>(base + (size_t)lane * lay.stride);
-  DecisionCtx *ctx_one = reinterpret_cast<DecisionCtx *>(base + (size_t)32 * lay.stride);
-  uint64_t *bar = reinterpret_cast<uint64_t *>(base + (size_t)32 * lay.stride + ((sizeof(DecisionCtx) + 15) / 16) * 16);
-  if (lane == 0) {
-    mbar_init(bar, 32);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + lay.off_bar);
+  int *busy = reinterpret_cast<int *>(smem_raw + lay.off_busy);
+  uint32_t *uses = reinterpret_cast<uint32_t *>(smem_raw + lay.off_uses);
+  uint32_t *win = reinterpret_cast<uint32_t *>(smem_raw + lay.off_warp + (size_t)wib * lay.per_warp);  // [32][LANE_WIN + 1]
+  DecisionCtx *ctx_one = reinterpret_cast<DecisionCtx *>(win + 32 * (LANE_WIN + 1));
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < ns; k++) { mbar_init(&bars[k], 32); busy[k] = 0; uses[k] = 0; }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncwarp();
+  __syncthreads();
   const int nb = (n + 31) >> 5;
-  const int gw = blockIdx.x * WARPS + wib, nw = gridDim.x * WARPS;
-  uint32_t parity = 0;
+  const uint32_t win_words = (uint32_t)min(LANE_WIN, min(RW, s.word_hi - s.word_lo));
+  auto claim = [&]() -> int {
+    int b = 0;
+    if (lane == 0) b = atomicAdd(batch_counter, 1);
+    return __shfl_sync(0xffffffffu, b, 0);
+  };
   auto load_dec = [&](int b, mmp_decision_in &d) -> bool {
     const int i = b * 32 + lane;
     if (b >= nb || i >= n) return false;
@@ -345,45 +363,80 @@ __global__ void __launch_bounds__(WARPS * 32) k_place_lanes(const SnapshotView s
     d.flags = (uint32_t)c.x; d.fresh = c.y; d.extra_off = c.z; d.extra_n = c.w;
     return true;
   };
+  int b = claim();
   mmp_decision_in d;
-  bool valid = load_dec(gw, d);
-  for (int b = gw; b < nb; b += nw) {
-    // ---- stage this step's 32 rows ----
+  bool valid = load_dec(b, d);
+  int hint = wib % ns;
+  while (b < nb) {
+    const int bn = claim();
+    // ---- acquire a landing stage ----
+    int st = 0;
+    uint32_t parity = 0;
+    if (lane == 0) {
+      st = hint;
+      while (atomicCAS(&busy[st], 0, 1) != 0) { st = st + 1 == ns ? 0 : st + 1; if (st == hint) __nanosleep(100); }
+      __threadfence_block();
+      parity = uses[st] & 1u;
+      uses[st]++;
+    }
+    st = __shfl_sync(0xffffffffu, st, 0);
+    parity = __shfl_sync(0xffffffffu, parity, 0);
+    hint = st + 1 == ns ? 0 : st + 1;
+    unsigned char *stage = smem_raw + (size_t)st * lay.stage_bytes;
+    const uint32_t *my_row = reinterpret_cast<const uint32_t *>(stage + (size_t)lane * lay.stride);
+    const int m = (valid && d.model >= 0 && d.model < s.n_models) ? d.model : 0;
     if (valid) {
-      const int m = (d.model >= 0 && d.model < s.n_models) ? d.model : 0;
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // last step's reads of this slot precede the async write
-      mbar_expect_tx(bar, lay.row_bytes);
-      bulk_g2s(const_cast<uint32_t *>(my_row), s.excl + (size_t)m * RW, lay.row_bytes, bar);
-    } else mbar_arrive(bar);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the previous owner's reads precede this async write
+      mbar_expect_tx(&bars[st], lay.row_bytes);
+      bulk_g2s(const_cast<uint32_t *>(my_row), s.excl + (size_t)m * RW, lay.row_bytes, &bars[st]);
+    } else mbar_arrive(&bars[st]);
     // ---- context gathers overlap the row copies; the next step's decision record is fetched now too ----
     DecisionCtx c;
     c.slot = -2;
     c.d.model = 0;
+    c.self_rank = -1;
     if (valid) prepare_ctx(s, d, fresh, n_fresh, c);
     mmp_decision_in dn;
-    const bool valid_n = load_dec(b + nw, dn);
-    while (!mbar_try_wait(bar, parity)) {}
-    parity ^= 1u;
+    const bool valid_n = load_dec(bn, dn);
+    while (!mbar_try_wait(&bars[st], parity)) {}
+    // ---- copy the window out and hand the stage on ----
+    uint32_t self_eword = 0;
+    {
+      uint32_t *w = win + lane * (LANE_WIN + 1);
+#pragma unroll
+      for (int j = 0; j < LANE_WIN / 4; j++) {
+        if ((uint32_t)(j * 4) < win_words) {
+          const uint4 q = *reinterpret_cast<const uint4 *>(my_row + j * 4);
+          w[j * 4] = q.x; w[j * 4 + 1] = q.y; w[j * 4 + 2] = q.z; w[j * 4 + 3] = q.w;
+        }
+      }
+      const int sw = c.self_rank >> 5;
+      if (c.self_rank >= 0 && sw >= s.word_lo && sw < s.word_hi) self_eword = my_row[sw - s.word_lo];
+    }
+    __syncwarp();
+    if (lane == 0) { __threadfence_block(); atomicExch(&busy[st], 0); }
     // ---- one decision per lane, the 32 lanes in lockstep ----
     DecideOut o;
-    const bool handled = decide_stream(s, c, valid, my_row, now, seed, id_base + (uint64_t)(b * 32 + lane), WarpVote(), o, LANE_BUDGET);
-    // ---- what the lane routine declined (uncommon paths, long walks): the whole warp redoes it from the staged row ----
+    const bool handled = decide_stream(s, c, valid, win + lane * (LANE_WIN + 1), win_words, self_eword, now, seed,
+                                       id_base + (uint64_t)(b * 32 + lane), WarpVote(), o, LANE_BUDGET);
+    // ---- what the lane routine declined: the whole warp redoes it, reading the row from global memory (L2) ----
     uint32_t pending = __ballot_sync(0xffffffffu, valid && !handled);
     while (pending) {
       const int l = __ffs((int)pending) - 1;
       pending &= pending - 1;
       if (lane == l) *ctx_one = c;
+      const int ml = __shfl_sync(0xffffffffu, m, l);
       __syncwarp();
       int32_t t2, c2;
-      decide_warp(s, *ctx_one, reinterpret_cast<const uint32_t *>(base + (size_t)l * lay.stride), extra, now, seed,
-                  id_base + (uint64_t)(b * 32 + l), &t2, &c2);
+      decide_warp(s, *ctx_one, s.excl + (size_t)ml * RW, extra, now, seed, id_base + (uint64_t)(b * 32 + l), &t2, &c2);
       if (lane == l) { o.target = t2; o.n_candidates = c2; }
       __syncwarp();
     }
     if (valid) out[b * 32 + lane] = mmp_decision_out{o.target, o.n_candidates};
+    b = bn;
     d = dn;
     valid = valid_n;
-    __syncwarp();  // every lane is done with the stage before it is refilled
+    __syncwarp();
   }
 }
 
@@ -424,7 +477,10 @@ struct PlaceCtx {
   static constexpr int NPIPE = 3;
   cudaStream_t pipe[NPIPE] = {nullptr, nullptr, nullptr};  // H2D / kernel / D2H of consecutive chunks overlap across these
   cudaEvent_t e0 = nullptr, e1 = nullptr, ready = nullptr;
-  DevBuf d_in, d_out, d_fresh, d_extra, d_trace, d_cand;
+  DevBuf d_in, d_out, d_fresh, d_extra, d_trace, d_cand, d_counters;
+  static constexpr int NCOUNTERS = 64;  // batch counters of k_place_lanes, one per launch in flight on this context
+  int next_counter = 0;
+  int *counter() { return d_counters.as<int>() + (next_counter++ % NCOUNTERS); }
   std::vector<FreshRow> fresh_host;
   // pinned, device-mapped scratch for tiny batches: the kernel reads the decisions and writes the results straight
   // through PCIe, so a B = 1 call is one launch + one synchronise (no copy calls)
@@ -449,6 +505,7 @@ struct mmp_fleet {
   int tile = 16;                // lanes per decision in k_place (MMP_TILE = 8 | 16 | 32)
   int ring_k = 4;               // ring depth for rows <= 2 KiB (MMP_RING_K = 2 | 4)
   int lanes = 1;                // MMP_KERNEL=tile selects the cooperative-tile kernel (k_place) instead of k_place_lanes
+  int lane_warps = 12;          // warps per block of k_place_lanes (MMP_LANE_WARPS = 8 | 12 | 16 | 20); 12 measured best at 10k instances
   // LRU store (plug point 3)
   DevBuf lru_ts, lru_seq, lru_weight, lru_model, lru_cap, lru_wsize, lru_count, lru_seqctr;
   int32_t lru_n = 0, lru_slots = 0;
@@ -483,6 +540,7 @@ static PlaceCtx *acquire_ctx(mmp_fleet *f) {
             cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming) == cudaSuccess &&
             cudaHostAlloc((void **)&c->mapped, PlaceCtx::MAPPED_BYTES, cudaHostAllocMapped) == cudaSuccess;
   for (int i = 0; ok && i < PlaceCtx::NPIPE; i++) ok = cudaStreamCreateWithFlags(&c->pipe[i], cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && c->d_counters.ensure(PlaceCtx::NCOUNTERS * sizeof(int)) == cudaSuccess;
   if (!ok) { delete c; return nullptr; }
   return c;
 }
@@ -491,7 +549,7 @@ static void release_ctx(mmp_fleet *f, PlaceCtx *c) {
   f->ctx_free.emplace_back(c);
 }
 static void destroy_ctx(PlaceCtx *c) {
-  for (DevBuf *b : {&c->d_in, &c->d_out, &c->d_fresh, &c->d_extra, &c->d_trace, &c->d_cand}) b->release();
+  for (DevBuf *b : {&c->d_in, &c->d_out, &c->d_fresh, &c->d_extra, &c->d_trace, &c->d_cand, &c->d_counters}) b->release();
   if (c->e0) cudaEventDestroy(c->e0);
   if (c->e1) cudaEventDestroy(c->e1);
   if (c->ready) cudaEventDestroy(c->ready);
@@ -515,6 +573,7 @@ struct PlaceArgs {
   uint32_t *cand;
   int64_t now;
   uint64_t seed, id_base;
+  int *batch_counter;  // device int, zeroed by the launcher: k_place_lanes warps claim batches of 32 decisions from it
 };
 
 // ring depth (a power of two) / warps per block by row size: rows up to 2 KiB (16k instances) K=4 x 8 warps, up to 4 KiB K=2 x 8, beyond K=2 x 4
@@ -541,25 +600,29 @@ static cudaError_t launch_place_t(mmp_fleet *f, const PlaceArgs &a, cudaStream_t
   return cudaGetLastError();
 }
 
+// stages x warps for a stored row width: as many 32-row landing stages as fit beside the warps' window buffers
+static bool lanes_geometry(int row_words, int warps, int &ns) {
+  for (ns = 8; ns >= 2; ns--)
+    if (LaneLayout(row_words, ns, warps).total <= (size_t)220 * 1024) return true;
+  return false;
+}
+
 template <int WARPS>
-static cudaError_t launch_place_lanes(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st) {
+static cudaError_t launch_place_lanes(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st, int ns) {
   static int attr_set = 0;
-  const LaneLayout lay(a.s.excl_stride);
-  const size_t smem = lay.per_warp * WARPS;
+  const LaneLayout lay(a.s.excl_stride, ns, WARPS);
   auto kern = k_place_lanes<WARPS>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = 1;
   }
-  int bps = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, WARPS * 32, smem);
+  const int nb = (a.n + 31) / 32;
+  const int grid = std::max(1, std::min((nb + WARPS - 1) / WARPS, f->sm_count));
+  cudaError_t e = cudaMemsetAsync(a.batch_counter, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
-  if (bps < 1) bps = 1;
-  const int want = (a.n + 32 * WARPS - 1) / (32 * WARPS);
-  int grid = std::min(want, f->sm_count * bps);
-  if (grid < 1) grid = 1;
-  kern<<<grid, WARPS * 32, smem, st>>>(a.s, a.in, a.n, a.fresh, a.n_fresh, a.extra, a.out, a.now, a.seed, a.id_base);
+  kern<<<grid, WARPS * 32, lay.total, st>>>(a.s, a.in, a.n, a.fresh, a.n_fresh, a.extra, a.out, a.now, a.seed, a.id_base, ns,
+                                            a.batch_counter);
   f->launches++;
   return cudaGetLastError();
 }
@@ -567,7 +630,14 @@ static cudaError_t launch_place_lanes(mmp_fleet *f, const PlaceArgs &a, cudaStre
 static cudaError_t launch_place(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st) {
   const int rw = a.s.row_words;
   // production path: one decision per lane (rows up to 2 KiB + pad: at least three 32-row stages per SM)
-  if (!(a.tr || a.cand) && f->lanes && rw <= 512) return launch_place_lanes<1>(f, a, st);
+  if (!(a.tr || a.cand) && f->lanes && a.batch_counter) {
+    int ns = 0;
+    if (f->lane_warps == 8 && lanes_geometry(a.s.excl_stride, 8, ns)) return launch_place_lanes<8>(f, a, st, ns);
+    if (f->lane_warps == 12 && lanes_geometry(a.s.excl_stride, 12, ns)) return launch_place_lanes<12>(f, a, st, ns);
+    if (f->lane_warps == 20 && lanes_geometry(a.s.excl_stride, 20, ns)) return launch_place_lanes<20>(f, a, st, ns);
+    if (f->lane_warps == 16 && lanes_geometry(a.s.excl_stride, 16, ns)) return launch_place_lanes<16>(f, a, st, ns);
+    if (lanes_geometry(a.s.excl_stride, 12, ns)) return launch_place_lanes<12>(f, a, st, ns);
+  }
   // tile width: how many lanes (= window words) resolve one decision; 32/T decisions advance per warp step.
   // The traced variant (parity tests) is a separate, single-decision-per-warp kernel so that the production kernel's
   // instruction footprint stays small.
@@ -612,6 +682,7 @@ int32_t mmp_fleet_create(const mmp_config *cfg, mmp_fleet **out) {
   f->hs.init(*cfg);
   if (const char *t = getenv("MMP_RING_K")) { int v = atoi(t); if (v == 2 || v == 4) f->ring_k = v; }
   if (const char *t = getenv("MMP_KERNEL")) f->lanes = strcmp(t, "tile") != 0;
+  if (const char *t = getenv("MMP_LANE_WARPS")) { int v = atoi(t); if (v == 8 || v == 12 || v == 16 || v == 20) f->lane_warps = v; }
   if (const char *t = getenv("MMP_TILE")) { int v = atoi(t); if (v == 8 || v == 16 || v == 32) f->tile = v; }
   *out = f.release();
   return MMP_OK;
@@ -767,7 +838,7 @@ static int32_t place_impl(mmp_fleet *f, const mmp_decision_in *in, int32_t n, co
       if (n_fresh) memcpy(h + o_fr, c->fresh_host.data(), (size_t)n_fresh * sizeof(FreshRow));
       if (n_extra) memcpy(h + o_ex, extra, (size_t)n_extra * 4);
       PlaceArgs a{ds.view, (const mmp_decision_in *)(dbase + o_in), n, (const FreshRow *)(dbase + o_fr), n_fresh,
-                  (const int32_t *)(dbase + o_ex), (mmp_decision_out *)(dbase + o_out), nullptr, nullptr, now_ms, seed, 0};
+                  (const int32_t *)(dbase + o_ex), (mmp_decision_out *)(dbase + o_out), nullptr, nullptr, now_ms, seed, 0, c->counter()};
       CK(launch_place(f, a, st));
       CK(cudaStreamSynchronize(st));
       memcpy(out, h + o_out, (size_t)n * sizeof(mmp_decision_out));
@@ -794,7 +865,7 @@ static int32_t place_impl(mmp_fleet *f, const mmp_decision_in *in, int32_t n, co
       cudaStream_t ps = c->pipe[ci % PlaceCtx::NPIPE];
       CK(cudaMemcpyAsync(c->d_in.as<mmp_decision_in>() + lo, in + lo, (size_t)cnt * sizeof(mmp_decision_in), cudaMemcpyHostToDevice, ps));
       PlaceArgs a{ds.view, c->d_in.as<mmp_decision_in>() + lo, cnt, c->d_fresh.as<FreshRow>(), n_fresh, c->d_extra.as<int32_t>(),
-                  c->d_out.as<mmp_decision_out>() + lo, nullptr, nullptr, now_ms, seed, (uint64_t)lo};
+                  c->d_out.as<mmp_decision_out>() + lo, nullptr, nullptr, now_ms, seed, (uint64_t)lo, c->counter()};
       CK(launch_place(f, a, ps));
       CK(cudaMemcpyAsync(out + lo, c->d_out.as<mmp_decision_out>() + lo, (size_t)cnt * sizeof(mmp_decision_out), cudaMemcpyDeviceToHost, ps));
     }
@@ -805,7 +876,7 @@ static int32_t place_impl(mmp_fleet *f, const mmp_decision_in *in, int32_t n, co
   if (cand_mask) CK(cudaMemsetAsync(c->d_cand.p, 0, (size_t)n * 2 * RW * 4, st));
   PlaceArgs a{ds.view, c->d_in.as<mmp_decision_in>(), n, c->d_fresh.as<FreshRow>(), n_fresh, c->d_extra.as<int32_t>(),
               c->d_out.as<mmp_decision_out>(), trace ? c->d_trace.as<mmp_decision_trace>() : nullptr,
-              cand_mask ? c->d_cand.as<uint32_t>() : nullptr, now_ms, seed, 0};
+              cand_mask ? c->d_cand.as<uint32_t>() : nullptr, now_ms, seed, 0, c->counter()};
   CK(launch_place(f, a, st));
   CK(cudaMemcpyAsync(out, c->d_out.p, (size_t)n * sizeof(mmp_decision_out), cudaMemcpyDeviceToHost, st));
   if (trace) CK(cudaMemcpyAsync(trace, c->d_trace.p, (size_t)n * sizeof(mmp_decision_trace), cudaMemcpyDeviceToHost, st));
@@ -845,7 +916,7 @@ int32_t mmp_place_batch_device(mmp_fleet *f, const void *d_in, int32_t n, void *
   CK(c->d_fresh.ensure(sizeof(FreshRow)));
   CK(c->d_extra.ensure(4));
   PlaceArgs a{ds.view, (const mmp_decision_in *)d_in, n, c->d_fresh.as<FreshRow>(), 0, c->d_extra.as<int32_t>(),
-              (mmp_decision_out *)d_out, nullptr, nullptr, now_ms, seed, 0};
+              (mmp_decision_out *)d_out, nullptr, nullptr, now_ms, seed, 0, c->counter()};
   CK(cudaEventRecord(c->e0, c->stream));
   CK(launch_place(f, a, c->stream));
   CK(cudaEventRecord(c->e1, c->stream));

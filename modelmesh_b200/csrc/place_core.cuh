@@ -631,10 +631,14 @@ struct WarpVote { MMP_D bool any(bool p) const { return __any_sync(0xffffffffu, 
 // and the caller redoes the decision with the cooperative general routine -- for everything outside the common case:
 // malformed decision, extra excludes, no entry / best full (replicaset retry, non-simple (b)), or a walk longer than
 // `budget` row words.  Instance-sharded: a walk that needs ranks beyond this shard's range sets MMP_TF_OPEN.
+// erow holds only the first win_words words of the decision's (stored) row -- k_place_lanes copies that window out of
+// the TMA landing stage so the stage can take the next rows while the lanes compute; a walk that leaves the window is
+// declined like one that exceeds the budget.  self_eword = the row word that holds self's bit (anywhere in the row).
 // Must be called by every lane of the vote group (active = false for lanes without a decision).
 template <class V>
-MMP_HD bool decide_stream(const SnapshotView &s, const DecisionCtx &c, bool active, const uint32_t *erow, int64_t now,
-                          uint64_t seed, uint64_t decision_id, const V &vote, DecideOut &o, int32_t budget) {
+MMP_HD bool decide_stream(const SnapshotView &s, const DecisionCtx &c, bool active, const uint32_t *erow, uint32_t win_words,
+                          uint32_t self_eword, int64_t now, uint64_t seed, uint64_t decision_id, const V &vote, DecideOut &o,
+                          int32_t budget) {
   o.target = MMP_TARGET_NONE; o.n_candidates = 0; o.best = -1; o.n_remaining = 0; o.pick_index = 0; o.flags = 0;
   o.cut_rank = (int32_t)NONE_RANK; o.best_rank = -1; o.first_rank = -1;
   const uint32_t NW = (uint32_t)s.row_words, WS = (uint32_t)s.word_lo, WE = (uint32_t)s.word_hi;
@@ -658,7 +662,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const DecisionCtx &c, bool acti
     bool search = live;
     for (;;) {
       if (search) {
-        if (wi >= WE || left <= 0) search = false;
+        if (wi >= WE || left <= 0 || wi - WS >= win_words) search = false;
         else {
           const uint32_t x = Fw(wi);
           if (x) { b = wi * 32u + (uint32_t)ffs32(x); search = false; }
@@ -691,7 +695,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const DecisionCtx &c, bool acti
     for (;;) {
       if (search) {
         if (wi >= WE) search = false;
-        else if (left <= 0) { search = false; live = false; }
+        else if (left <= 0 || wi - WS >= win_words) { search = false; live = false; }
         else {
           uint32_t x = Fw(wi) & (P[wi] | s.full[wi]) & mask_above(wi * 32u, b);
           if (x) { r1 = wi * 32u + (uint32_t)ffs32(x); search = false; }
@@ -723,7 +727,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const DecisionCtx &c, bool acti
   if (walk) {
     if (self_rank >= 0 && (uint32_t)self_rank > lo && (uint32_t)self_rank < hi) {
       const uint32_t w = (uint32_t)self_rank >> 5, bit = 1u << (self_rank & 31);
-      if (w - WS < WE - WS && (Fw(w) & bit) != 0 && (!use_pref || (P[w] & bit) != 0)) { self_in_s = true; sw_ = w; sb_ = bit; }
+      if (w - WS < WE - WS && (CX[w] & ~self_eword & bit) != 0 && (!use_pref || (P[w] & bit) != 0)) { self_in_s = true; sw_ = w; sb_ = bit; }
     }
     const int64_t q = best_rem >> 2;
     c_self = fr.rem < s.min_space || fr.rem < q;
@@ -749,7 +753,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const DecisionCtx &c, bool acti
       for (;;) {
         if (search) {
           if (wi >= stop_w) { search = false; if (lim == NONE_RANK && open_end) open = true; }
-          else if (left <= 0) { search = false; live = false; }
+          else if (left <= 0 || wi - WS >= win_words) { search = false; live = false; }
           else {
             const uint32_t x = Sw(wi);
             int cls = 0;  // 0: no member fails, 1: every member (but a passing self) fails, 2: look at the counts

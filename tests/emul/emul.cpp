@@ -28,6 +28,7 @@ struct mmp_fleet {
 static thread_local std::string g_err;
 static int g_window = 32;  // fast-path window width under test (32: warp tile, 16: half-warp tile); 1: lane-per-decision shape
 static int g_lane_budget = 48;  // CoopLane walk budget (row words) when g_window == 1
+static int g_lane_window = 16;  // decide_stream: row words available to a lane (k_place_lanes copies this window out of the landing stage)
 static long g_bails = 0, g_lane_decisions = 0;
 
 extern "C" {
@@ -35,6 +36,7 @@ extern "C" {
 int32_t mmp_abi_version(void) { return MMP_ABI_VERSION; }
 void mmp_emul_set_window(int w) { g_window = (w == 16 || w == 8 || w == 1 || w == 2) ? w : 32; }  // harness-only entry points
 void mmp_emul_set_lane_budget(int words) { g_lane_budget = words; }
+void mmp_emul_set_lane_window(int words) { g_lane_window = words; }
 void mmp_emul_set_keys(mmp_fleet *f, uint64_t *keys) { f->keys = keys; }
 void mmp_emul_key_decode(uint64_t k, int32_t *target, int32_t *n_candidates, int32_t *open) {
   shard_key_decode(k, *target, *n_candidates);
@@ -134,7 +136,9 @@ int32_t mmp_place_batch_trace(mmp_fleet *f, const mmp_decision_in *in, int32_t n
     const bool sharded = v.word_lo != 0 || v.word_hi != v.row_words;
     bool done = false;
     if (win == 2 && !cand_mask) {  // the lockstep lane routine of k_place_lanes (one decision per lane), general routine when it declines
-      done = decide_stream(v, cx, true, erow, now_ms, seed, (uint64_t)i, SoloVote(), o, g_lane_budget);
+      uint32_t self_eword = 0;
+      if (cx.self_rank >= 0 && (cx.self_rank >> 5) >= v.word_lo && (cx.self_rank >> 5) < v.word_hi) self_eword = erow[(cx.self_rank >> 5) - v.word_lo];
+      done = decide_stream(v, cx, true, erow, (uint32_t)g_lane_window, self_eword, now_ms, seed, (uint64_t)i, SoloVote(), o, g_lane_budget);
       g_lane_decisions++;
       if (!done) g_bails++;
     } else if (sharded) {
