@@ -131,5 +131,6 @@ _product = None
 def load_product() -> C.CDLL:
     global _product
     if _product is None:
-        _product = load(PRODUCT_SO)
+        # MMP_LIB: an alternative build of the same CUDA library (A/B runs of kernel variants on one GPU box)
+        _product = load(os.environ.get("MMP_LIB", PRODUCT_SO))
     return _product

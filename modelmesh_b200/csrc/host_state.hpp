@@ -92,6 +92,7 @@ struct HostSnapshot {
   std::vector<uint8_t> has_pref;      // [n_slots]
   std::vector<uint8_t> allowed_null;  // [n_slots] (introspection only)
   std::vector<uint16_t> type_slot;    // [n_type_ids] type id -> mask slot
+  std::vector<uint16_t> type_slot_hp; // [n_type_ids] slot | has_pref << 15: what the decision context reads (one gather instead of two)
   std::vector<uint32_t> rs, full;     // [row_words]
   std::vector<WordSumI> csum;         // [row_words]
   std::vector<WordSumL> lsum;         // [row_words]
@@ -360,6 +361,10 @@ class HostState {
     s.candx = s.cand;
     for (int32_t sl = 0; sl < s.n_slots; sl++)
       for (int32_t w = 0; w < RW; w++) s.candx[(size_t)sl * RW + w] &= ~s.rs[w];
+    if (s.n_slots > 0x7fff) return "more than 32767 distinct type-constraint masks";
+    s.type_slot_hp.resize(s.type_slot.size());
+    for (size_t t = 0; t < s.type_slot.size(); t++)
+      s.type_slot_hp[t] = (uint16_t)(s.type_slot[t] | (s.has_pref[s.type_slot[t]] ? 0x8000u : 0u));
     s.candx_before.assign((size_t)s.n_slots, 0);
     for (int32_t sl = 0; sl < s.n_slots; sl++)
       for (int32_t w = 0; w < s.word_lo; w++) s.candx_before[sl] += __builtin_popcount(s.candx[(size_t)sl * RW + w]);

@@ -304,22 +304,29 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_place(const SnapshotView s
 // cooperative general routine reading the row from global memory (it was just streamed: L2).
 // The stages keep ~NS x 41 KB per SM in flight from HBM independently of how many warps are computing, and the
 // per-decision instruction cost is ~70 warp instructions / 32 lanes instead of ~450 for a cooperative tile.
-// Rows are staged at a stride of row_bytes + 16 so that lanes reading their own rows spread over the banks.
 // ---------------------------------------------------------------------------------------------------------------
-static constexpr int LANE_WIN = 16;     // row words copied out of the landing stage per decision
+static constexpr int LANE_WIN = 14;     // row words copied out of the landing stage per decision (448 ranks)
 static constexpr int LANE_BUDGET = 64;  // row-word visits a lane may spend before handing its decision to the warp
+static constexpr int LANE_SLOTS = 64;   // type-constraint mask slots whose window words are kept in shared memory
 struct LaneLayout {
   uint32_t row_bytes, stride, stage_bytes, ns, warps;
   uint32_t off_bar, off_busy, off_uses, off_warp, per_warp;
+  uint32_t off_cx, off_p, off_full, off_csum, off_count, off_rows;  // the front (window) part of the lane tables
   size_t total;
-  __host__ __device__ LaneLayout(int row_words, int ns_, int warps_) {
-    row_bytes = (uint32_t)row_words * 4u; stride = row_bytes + 16u;
+  __host__ __device__ LaneLayout(int row_words, int ns_, int warps_, bool front) {
+    row_bytes = (uint32_t)row_words * 4u; stride = row_bytes + 16u;  // + 16: lanes copying their windows out spread over the banks
     stage_bytes = (32u * stride + 127u) / 128u * 128u;
     ns = (uint32_t)ns_; warps = (uint32_t)warps_;
     off_bar = ns * stage_bytes; off_busy = off_bar + ns * 8u; off_uses = off_busy + ns * 4u;
     off_warp = (off_uses + ns * 4u + 127u) / 128u * 128u;
-    per_warp = (32u * (LANE_WIN + 1) * 4u + (uint32_t)((sizeof(DecisionCtx) + 15) / 16 * 16) + 127u) / 128u * 128u;
-    total = (size_t)off_warp + (size_t)warps * per_warp;
+    per_warp = 32u * (LANE_WIN + 1) * 4u + (uint32_t)((sizeof(DecisionCtx) + 15) / 16 * 16);  // window rows are LANE_WIN + 1 words apart: bank-conflict free
+    off_cx = (off_warp + warps * per_warp + 15u) / 16u * 16u;
+    off_p = off_cx + LANE_SLOTS * LANE_WIN * 4u;
+    off_full = off_p + LANE_SLOTS * LANE_WIN * 4u;
+    off_csum = off_full + ((LANE_WIN * 4u + 7u) / 8u) * 8u;
+    off_count = (off_csum + LANE_WIN * 8u + 15u) / 16u * 16u;
+    off_rows = off_count + LANE_WIN * 32u * 4u;
+    total = front ? (size_t)off_rows + (size_t)LANE_WIN * 32u * sizeof(RankRow) : (size_t)off_cx;
   }
 };
 
@@ -332,28 +339,57 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotVie
                                                                const FreshRow *__restrict__ fresh, int n_fresh,
                                                                const int32_t *__restrict__ extra, mmp_decision_out *__restrict__ out,
                                                                int64_t now, uint64_t seed, uint64_t id_base, int ns,
-                                                               int *__restrict__ batch_counter) {
+                                                               int front_tables, int mode, unsigned long long *__restrict__ dbg) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int RW = s.excl_stride;  // words per stored row (the whole row unless the fleet is instance-sharded)
-  const LaneLayout lay(RW, ns, WARPS);
+  const LaneLayout lay(RW, ns, WARPS, front_tables != 0);
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + lay.off_bar);
-  int *busy = reinterpret_cast<int *>(smem_raw + lay.off_busy);
-  uint32_t *uses = reinterpret_cast<uint32_t *>(smem_raw + lay.off_uses);
+  int *ticket = reinterpret_cast<int *>(smem_raw + lay.off_busy);               // next stage ticket of this block
+  uint32_t *released = reinterpret_cast<uint32_t *>(smem_raw + lay.off_uses);  // [ns] completed uses per stage
   uint32_t *win = reinterpret_cast<uint32_t *>(smem_raw + lay.off_warp + (size_t)wib * lay.per_warp);  // [32][LANE_WIN + 1]
   DecisionCtx *ctx_one = reinterpret_cast<DecisionCtx *>(win + 32 * (LANE_WIN + 1));
   if (threadIdx.x == 0) {
-    for (int k = 0; k < ns; k++) { mbar_init(&bars[k], 32); busy[k] = 0; uses[k] = 0; }
+    for (int k = 0; k < ns; k++) { mbar_init(&bars[k], 32); released[k] = 0; }
+    *ticket = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
   const int nb = (n + 31) >> 5;
   const uint32_t win_words = (uint32_t)min(LANE_WIN, min(RW, s.word_hi - s.word_lo));
-  auto claim = [&]() -> int {
-    int b = 0;
-    if (lane == 0) b = atomicAdd(batch_counter, 1);
-    return __shfl_sync(0xffffffffu, b, 0);
-  };
+  // ---- the window part of the per-word / per-rank tables, once per block (with the SM's shared memory given to the
+  // landing stages the L1 is too small to hold them, and the lane routine's gathers would be L2 round trips) ----
+  uint32_t *f_cx = reinterpret_cast<uint32_t *>(smem_raw + lay.off_cx), *f_p = reinterpret_cast<uint32_t *>(smem_raw + lay.off_p);
+  uint32_t *f_full = reinterpret_cast<uint32_t *>(smem_raw + lay.off_full);
+  WordSumI *f_csum = reinterpret_cast<WordSumI *>(smem_raw + lay.off_csum);
+  int32_t *f_count = reinterpret_cast<int32_t *>(smem_raw + lay.off_count);
+  RankRow *f_rows = reinterpret_cast<RankRow *>(smem_raw + lay.off_rows);
+  const int WS = s.word_lo;
+  const bool front = front_tables != 0 && nb >= 64;  // tiny launches (the B = 1 latency path) read the snapshot directly
+  if (front) {
+    const int nsl = min(s.n_slots, LANE_SLOTS);
+    const uint32_t *gcx = s.any_rs ? s.candx : s.cand;
+    for (int i = threadIdx.x; i < nsl * LANE_WIN; i += blockDim.x) {
+      const int sl = i / LANE_WIN, w = i - sl * LANE_WIN;
+      const bool in = (uint32_t)w < win_words;
+      f_cx[i] = in ? gcx[(size_t)sl * s.row_words + WS + w] : 0u;
+      f_p[i] = in ? s.pref[(size_t)sl * s.row_words + WS + w] : 0u;
+    }
+    for (int w = threadIdx.x; w < LANE_WIN; w += blockDim.x) {
+      const bool in = (uint32_t)w < win_words;
+      f_full[w] = in ? s.full[WS + w] : 0u;
+      f_csum[w] = in ? s.csum[WS + w] : WordSumI{0, 0};
+    }
+    for (int i = threadIdx.x; i < LANE_WIN * 32; i += blockDim.x) {
+      const int r = WS * 32 + i;
+      const bool in = (uint32_t)(i >> 5) < win_words && r < s.n_ranks;
+      f_count[i] = in ? s.count_col[r] : 0;
+      RankRow z; z.lru = 0; z.rem = 0; z.count = 0; z.rpm = 0; z.idx = -1; z.flags = 0;
+      f_rows[i] = in ? s.rows[r] : z;
+    }
+  }
+  __syncthreads();
+  // batches of 32 decisions are dealt round-robin to the grid's warps (consecutive batches to the warps of one block)
+  const int gw = blockIdx.x * WARPS + wib, nw = gridDim.x * WARPS;
   auto load_dec = [&](int b, mmp_decision_in &d) -> bool {
     const int i = b * 32 + lane;
     if (b >= nb || i >= n) return false;
@@ -363,25 +399,43 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotVie
     d.flags = (uint32_t)c.x; d.fresh = c.y; d.extra_off = c.z; d.extra_n = c.w;
     return true;
   };
-  int b = claim();
+  // Software pipeline per warp (every load is issued at least one phase before its first use, because a warp stalls in
+  // order): batch k+2 is claimed and its records requested while batch k is resolved; the first context gathers of batch
+  // k+1 (model row from HBM, rank_of[self]) are issued right after batch k's stage has been handed on; what depends on
+  // them (type slot, the caller's row, self's mask bits) is gathered while batch k+1's rows are in flight.
+  int b = gw;
   mmp_decision_in d;
   bool valid = load_dec(b, d);
-  int hint = wib % ns;
+  CtxA ca;
+  prepare_ctx_a(s, d, ca);
+  int bn = b + nw;
+  mmp_decision_in dn;
+  bool valid_n = load_dec(bn, dn);
+  // MMP_LANE_MODE bit 1: per-phase cycle sums (measurement aid): wait-for-stage, issue, context, flight-left, copy-out, requests, decide
+  long long tsum[7] = {0, 0, 0, 0, 0, 0, 0};
+  long long tsteps = 0;
+  const bool timing = (mode & 2) != 0 && dbg != nullptr;
+#define LANE_T(k) do { if (timing) { const long long t_ = clock64(); tsum[k] += t_ - tprev; tprev = t_; } } while (0)
   while (b < nb) {
-    const int bn = claim();
-    // ---- acquire a landing stage ----
+    long long tprev = timing ? clock64() : 0;
+    // ---- acquire a landing stage and send the 32 rows on their way ----
     int st = 0;
     uint32_t parity = 0;
     if (lane == 0) {
-      st = hint;
-      while (atomicCAS(&busy[st], 0, 1) != 0) { st = st + 1 == ns ? 0 : st + 1; if (st == hint) __nanosleep(100); }
+      // stages are handed out in ticket order (a FIFO ring): ticket q uses stage q % ns for the (q / ns)-th time and may
+      // start when that stage's previous use has been released.  The wait is a plain poll of a shared-memory counter:
+      // a hand-over costs tens of cycles (a sleeping poll left the stages idle two thirds of the time).
+      const uint32_t q = (uint32_t)atomicAdd(ticket, 1);
+      st = (int)(q % (uint32_t)ns);
+      const uint32_t u = q / (uint32_t)ns;
+      volatile uint32_t *rel = released + st;
+      while (*rel < u) {}
       __threadfence_block();
-      parity = uses[st] & 1u;
-      uses[st]++;
+      parity = u & 1u;
     }
     st = __shfl_sync(0xffffffffu, st, 0);
     parity = __shfl_sync(0xffffffffu, parity, 0);
-    hint = st + 1 == ns ? 0 : st + 1;
+    LANE_T(0);
     unsigned char *stage = smem_raw + (size_t)st * lay.stage_bytes;
     const uint32_t *my_row = reinterpret_cast<const uint32_t *>(stage + (size_t)lane * lay.stride);
     const int m = (valid && d.model >= 0 && d.model < s.n_models) ? d.model : 0;
@@ -390,35 +444,54 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotVie
       mbar_expect_tx(&bars[st], lay.row_bytes);
       bulk_g2s(const_cast<uint32_t *>(my_row), s.excl + (size_t)m * RW, lay.row_bytes, &bars[st]);
     } else mbar_arrive(&bars[st]);
-    // ---- context gathers overlap the row copies; the next step's decision record is fetched now too ----
+    LANE_T(1);
+    // ---- the rest of this batch's context while its rows are in flight ----
     DecisionCtx c;
-    c.slot = -2;
-    c.d.model = 0;
-    c.self_rank = -1;
-    if (valid) prepare_ctx(s, d, fresh, n_fresh, c);
-    mmp_decision_in dn;
-    const bool valid_n = load_dec(bn, dn);
+    c.slot = -2; c.d.model = 0; c.self_rank = -1; c.self_bits = 0; c.self_count = 0;
+    if (valid) prepare_ctx_b(s, d, ca, fresh, n_fresh, c);
+    if (timing && __shfl_xor_sync(0xffffffffu, c.slot ^ (int)c.self_bits, 1) == 0x7fffffff) tsum[2]++;  // consume the gathers before the timestamp
+    LANE_T(2);
     while (!mbar_try_wait(&bars[st], parity)) {}
+    LANE_T(3);
     // ---- copy the window out and hand the stage on ----
     uint32_t self_eword = 0;
     {
       uint32_t *w = win + lane * (LANE_WIN + 1);
 #pragma unroll
-      for (int j = 0; j < LANE_WIN / 4; j++) {
+      for (int j = 0; j < (LANE_WIN + 3) / 4; j++) {
         if ((uint32_t)(j * 4) < win_words) {
           const uint4 q = *reinterpret_cast<const uint4 *>(my_row + j * 4);
-          w[j * 4] = q.x; w[j * 4 + 1] = q.y; w[j * 4 + 2] = q.z; w[j * 4 + 3] = q.w;
+          w[j * 4] = q.x; w[j * 4 + 1] = q.y;
+          if (j * 4 + 2 < LANE_WIN) { w[j * 4 + 2] = q.z; w[j * 4 + 3] = q.w; }
         }
       }
       const int sw = c.self_rank >> 5;
       if (c.self_rank >= 0 && sw >= s.word_lo && sw < s.word_hi) self_eword = my_row[sw - s.word_lo];
     }
     __syncwarp();
-    if (lane == 0) { __threadfence_block(); atomicExch(&busy[st], 0); }
+    if (lane == 0) { __threadfence_block(); atomicAdd(const_cast<uint32_t *>(released + st), 1u); }
+    LANE_T(4);
+    // ---- requests for the batches behind this one ----
+    CtxA cn;
+    cn.ok = 0; cn.self_rank = -1;
+    if (valid_n) prepare_ctx_a(s, dn, cn);
+    const int bnn = bn + nw;
+    mmp_decision_in dnn;
+    const bool valid_nn = load_dec(bnn, dnn);
+    LANE_T(5);
     // ---- one decision per lane, the 32 lanes in lockstep ----
     DecideOut o;
-    const bool handled = decide_stream(s, c, valid, win + lane * (LANE_WIN + 1), win_words, self_eword, now, seed,
-                                       id_base + (uint64_t)(b * 32 + lane), WarpVote(), o, LANE_BUDGET);
+    const int slot = c.slot >= 0 ? ctx_slot(c) : 0;
+    LaneTables T = lane_tables_global(s, slot);
+    if (front) {  // tables indexed by absolute row word / rank: bias the shared-memory copies by the window's first word
+      if (slot < LANE_SLOTS) { T.cx = f_cx + slot * LANE_WIN - WS; T.p = f_p + slot * LANE_WIN - WS; }
+      T.full = f_full - WS; T.csum = f_csum - WS; T.count_col = f_count - WS * 32; T.rows = f_rows - WS * 32;
+    }
+    bool handled = true;
+    if ((mode & 1) == 0)
+      handled = decide_stream(s, T, c, valid, win + lane * (LANE_WIN + 1), win_words, self_eword, now, seed,
+                              id_base + (uint64_t)(b * 32 + lane), WarpVote(), o, LANE_BUDGET);
+    else { o.target = (int32_t)(self_eword & 1u) - 1; o.n_candidates = 0; }  // MMP_LANE_MODE=1: stream-only probe (no decisions)
     // ---- what the lane routine declined: the whole warp redoes it, reading the row from global memory (L2) ----
     uint32_t pending = __ballot_sync(0xffffffffu, valid && !handled);
     while (pending) {
@@ -433,11 +506,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotVie
       __syncwarp();
     }
     if (valid) out[b * 32 + lane] = mmp_decision_out{o.target, o.n_candidates};
-    b = bn;
-    d = dn;
-    valid = valid_n;
+    b = bn; d = dn; valid = valid_n; ca = cn;
+    bn = bnn; dn = dnn; valid_n = valid_nn;
     __syncwarp();
+    LANE_T(6);
+    tsteps++;
   }
+  if (timing && lane == 0) {
+    for (int k = 0; k < 7; k++) atomicAdd(&dbg[k], (unsigned long long)tsum[k]);
+    atomicAdd(&dbg[7], (unsigned long long)tsteps);
+  }
+#undef LANE_T
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -498,12 +577,18 @@ struct mmp_fleet {
   int cur = 0;
   int32_t epoch = 0;
   cudaStream_t commit_stream = nullptr;
-  DevBuf d_edge_inl, d_ovf_pairs, d_flush;
+  DevBuf d_edge_inl, d_ovf_pairs, d_flush, d_dbg;
   std::mutex ctx_mu;
   std::vector<std::unique_ptr<PlaceCtx>> ctx_free;
   std::atomic<int64_t> launches{0};
   int tile = 16;                // lanes per decision in k_place (MMP_TILE = 8 | 16 | 32)
   int ring_k = 4;               // ring depth for rows <= 2 KiB (MMP_RING_K = 2 | 4)
+  int lane_stages = 4;          // MMP_LANE_STAGES caps the landing stages per SM (0: as many as fit).  Measured on B200 at 10k
+                                // instances: 3 stages 3.5, 4 stages 4.1-4.3, 5 stages 3.8 G decisions/s (the fifth stage costs the L1
+                                // its 196 -> 228 KB carve-out step and the lane tables no longer stay resident)
+  int lane_front = 0;           // MMP_LANE_FRONT=1: lane tables from a shared-memory copy instead of the snapshot (L1/L2); measured
+                                // slower (3.8 vs 4.2 G/s): the copy pushes shared memory past the 196 KB carve-out step
+  int lane_mode = 0;            // MMP_LANE_MODE=1: stream-only probe (rows staged, no decisions) -- measurement aid, results void
   int lanes = 1;                // MMP_KERNEL=tile selects the cooperative-tile kernel (k_place) instead of k_place_lanes
   int lane_warps = 12;          // warps per block of k_place_lanes (MMP_LANE_WARPS = 8 | 12 | 16 | 20); 12 measured best at 10k instances
   // LRU store (plug point 3)
@@ -601,28 +686,27 @@ static cudaError_t launch_place_t(mmp_fleet *f, const PlaceArgs &a, cudaStream_t
 }
 
 // stages x warps for a stored row width: as many 32-row landing stages as fit beside the warps' window buffers
-static bool lanes_geometry(int row_words, int warps, int &ns) {
+static bool lanes_geometry(int row_words, int warps, bool front, int &ns) {
   for (ns = 8; ns >= 2; ns--)
-    if (LaneLayout(row_words, ns, warps).total <= (size_t)220 * 1024) return true;
+    if (LaneLayout(row_words, ns, warps, front).total <= (size_t)227 * 1024) return true;
   return false;
 }
 
 template <int WARPS>
 static cudaError_t launch_place_lanes(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st, int ns) {
   static int attr_set = 0;
-  const LaneLayout lay(a.s.excl_stride, ns, WARPS);
+  if (f->lane_stages >= 2 && f->lane_stages < ns) ns = f->lane_stages;
+  const LaneLayout lay(a.s.excl_stride, ns, WARPS, f->lane_front != 0);
   auto kern = k_place_lanes<WARPS>;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = 1;
   }
   const int nb = (a.n + 31) / 32;
   const int grid = std::max(1, std::min((nb + WARPS - 1) / WARPS, f->sm_count));
-  cudaError_t e = cudaMemsetAsync(a.batch_counter, 0, sizeof(int), st);
-  if (e != cudaSuccess) return e;
   kern<<<grid, WARPS * 32, lay.total, st>>>(a.s, a.in, a.n, a.fresh, a.n_fresh, a.extra, a.out, a.now, a.seed, a.id_base, ns,
-                                            a.batch_counter);
+                                            f->lane_front, f->lane_mode, f->d_dbg.as<unsigned long long>());
   f->launches++;
   return cudaGetLastError();
 }
@@ -632,11 +716,13 @@ static cudaError_t launch_place(mmp_fleet *f, const PlaceArgs &a, cudaStream_t s
   // production path: one decision per lane (rows up to 2 KiB + pad: at least three 32-row stages per SM)
   if (!(a.tr || a.cand) && f->lanes && a.batch_counter) {
     int ns = 0;
-    if (f->lane_warps == 8 && lanes_geometry(a.s.excl_stride, 8, ns)) return launch_place_lanes<8>(f, a, st, ns);
-    if (f->lane_warps == 12 && lanes_geometry(a.s.excl_stride, 12, ns)) return launch_place_lanes<12>(f, a, st, ns);
-    if (f->lane_warps == 20 && lanes_geometry(a.s.excl_stride, 20, ns)) return launch_place_lanes<20>(f, a, st, ns);
-    if (f->lane_warps == 16 && lanes_geometry(a.s.excl_stride, 16, ns)) return launch_place_lanes<16>(f, a, st, ns);
-    if (lanes_geometry(a.s.excl_stride, 12, ns)) return launch_place_lanes<12>(f, a, st, ns);
+    if (f->lane_warps == 8 && lanes_geometry(a.s.excl_stride, 8, f->lane_front != 0, ns)) return launch_place_lanes<8>(f, a, st, ns);
+    if (f->lane_warps == 10 && lanes_geometry(a.s.excl_stride, 10, f->lane_front != 0, ns)) return launch_place_lanes<10>(f, a, st, ns);
+    if (f->lane_warps == 14 && lanes_geometry(a.s.excl_stride, 14, f->lane_front != 0, ns)) return launch_place_lanes<14>(f, a, st, ns);
+    if (f->lane_warps == 12 && lanes_geometry(a.s.excl_stride, 12, f->lane_front != 0, ns)) return launch_place_lanes<12>(f, a, st, ns);
+    if (f->lane_warps == 20 && lanes_geometry(a.s.excl_stride, 20, f->lane_front != 0, ns)) return launch_place_lanes<20>(f, a, st, ns);
+    if (f->lane_warps == 16 && lanes_geometry(a.s.excl_stride, 16, f->lane_front != 0, ns)) return launch_place_lanes<16>(f, a, st, ns);
+    if (lanes_geometry(a.s.excl_stride, 12, f->lane_front != 0, ns)) return launch_place_lanes<12>(f, a, st, ns);
   }
   // tile width: how many lanes (= window words) resolve one decision; 32/T decisions advance per warp step.
   // The traced variant (parity tests) is a separate, single-decision-per-warp kernel so that the production kernel's
@@ -682,7 +768,11 @@ int32_t mmp_fleet_create(const mmp_config *cfg, mmp_fleet **out) {
   f->hs.init(*cfg);
   if (const char *t = getenv("MMP_RING_K")) { int v = atoi(t); if (v == 2 || v == 4) f->ring_k = v; }
   if (const char *t = getenv("MMP_KERNEL")) f->lanes = strcmp(t, "tile") != 0;
-  if (const char *t = getenv("MMP_LANE_WARPS")) { int v = atoi(t); if (v == 8 || v == 12 || v == 16 || v == 20) f->lane_warps = v; }
+  if (const char *t = getenv("MMP_LANE_WARPS")) { int v = atoi(t); if (v == 8 || v == 10 || v == 12 || v == 14 || v == 16 || v == 20) f->lane_warps = v; }
+  if (const char *t = getenv("MMP_LANE_STAGES")) f->lane_stages = atoi(t);
+  if (const char *t = getenv("MMP_LANE_FRONT")) f->lane_front = atoi(t) != 0;
+  if (const char *t = getenv("MMP_LANE_MODE")) f->lane_mode = atoi(t);
+  if (f->lane_mode & 2) { CK(f->d_dbg.ensure(64)); CK(cudaMemset(f->d_dbg.p, 0, 64)); }
   if (const char *t = getenv("MMP_TILE")) { int v = atoi(t); if (v == 8 || v == 16 || v == 32) f->tile = v; }
   *out = f.release();
   return MMP_OK;
@@ -692,6 +782,15 @@ void mmp_fleet_destroy(mmp_fleet *f) {
   if (!f) return;
   cudaSetDevice(f->device);
   cudaDeviceSynchronize();
+  if ((f->lane_mode & 2) && f->d_dbg.p) {  // MMP_LANE_MODE bit 1: print the per-phase averages of k_place_lanes
+    unsigned long long h[8];
+    if (cudaMemcpy(h, f->d_dbg.p, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess && h[7]) {
+      static const char *nm[7] = {"wait-for-stage", "issue", "context", "flight-left", "copy-out+release", "requests", "decide+store"};
+      fprintf(stderr, "[k_place_lanes phases, cycles per warp step over %llu steps]", h[7]);
+      for (int k = 0; k < 7; k++) fprintf(stderr, " %s=%.0f", nm[k], (double)h[k] / (double)h[7]);
+      fprintf(stderr, "\n");
+    }
+  }
   for (auto &c : f->ctx_free) { destroy_ctx(c.get()); }
   f->ctx_free.clear();
   f->snaps[0].release(); f->snaps[1].release();
@@ -752,7 +851,7 @@ int32_t mmp_fleet_commit(mmp_fleet *f) {
   const int32_t nm = f->hs.n_models_used;
   ds.n_models = nm;
   CK(upload_vec(ds.cand, h.cand, st)); CK(upload_vec(ds.pref, h.pref, st)); CK(upload_vec(ds.has_pref, h.has_pref, st));
-  CK(upload_vec(ds.type_slot, h.type_slot, st)); CK(upload_vec(ds.candx, h.candx, st)); CK(upload_vec(ds.full, h.full, st));
+  CK(upload_vec(ds.type_slot, h.type_slot_hp, st)); CK(upload_vec(ds.candx, h.candx, st)); CK(upload_vec(ds.full, h.full, st));
   CK(upload_vec(ds.rows, h.rows, st)); CK(upload_vec(ds.rank_of, h.rank_of, st)); CK(upload_vec(ds.csum, h.csum, st));
   CK(upload_vec(ds.lsum, h.lsum, st)); CK(upload_vec(ds.cap_col, h.cap_col, st));
   CK(upload_vec(ds.lthreads_col, h.lthreads_col, st)); CK(upload_vec(ds.linprog_col, h.linprog_col, st));
@@ -787,7 +886,7 @@ int32_t mmp_fleet_commit(mmp_fleet *f) {
   SnapshotView &v = ds.view;
   v.n_ranks = h.n_ranks; v.row_words = RW; v.n_models = nm; v.max_instances = f->hs.cfg.max_instances;
   v.any_rs = h.any_rs; v.n_type_ids = (int32_t)h.type_slot.size(); v.min_space = f->hs.cfg.min_space_units;
-  v.word_lo = h.word_lo; v.word_hi = h.word_hi; v.excl_stride = ST; v.shard_reserved = 0;
+  v.word_lo = h.word_lo; v.word_hi = h.word_hi; v.excl_stride = ST; v.n_slots = h.n_slots;
   v.count_col = ds.count_col.as<int32_t>();
   v.excl = ds.excl.as<uint32_t>(); v.cand = ds.cand.as<uint32_t>(); v.pref = ds.pref.as<uint32_t>();
   v.has_pref = ds.has_pref.as<uint8_t>(); v.type_slot = ds.type_slot.as<uint16_t>(); v.candx = ds.candx.as<uint32_t>();

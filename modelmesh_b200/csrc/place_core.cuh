@@ -64,14 +64,14 @@ struct SnapshotView {  // pointers into HBM (or host vectors in the CPU harness)
   int32_t any_rs, n_type_ids;
   // instance sharding: this process holds words [word_lo, word_hi) of every exclusion row, stored at a
   // stride of excl_stride words; [0, row_words) and row_words when the fleet is not sharded
-  int32_t word_lo, word_hi, excl_stride, shard_reserved;
+  int32_t word_lo, word_hi, excl_stride, n_slots;
   int64_t min_space;
   const uint32_t *excl;        // [n_models][excl_stride] loaded ∪ failed, bit = rank (word 0 of a stored row = row word word_lo)
   const uint32_t *cand;        // [n_slots][row_words]  allowed(type) ∧ active
   const uint32_t *candx;       // [n_slots][row_words]  cand ∧ ¬(likely-replaced replicaset members)  (MM:4769-4770)
   const uint32_t *pref;        // [n_slots][row_words]
   const uint8_t *has_pref;     // [n_slots]
-  const uint16_t *type_slot;   // [n_type_ids]
+  const uint16_t *type_slot;   // [n_type_ids] mask slot | has_pref << 15
   const uint32_t *full;        // [row_words] isFull(remaining) (MM:4640-4642)
   const RankRow *rows;         // [n_ranks]
   const int32_t *rank_of;      // [max_instances]
@@ -439,24 +439,47 @@ struct DecisionCtx {
   FreshRow fr;         // the caller's fresh record (MM:5369), or its published row with rpm 0 (N7)
   int32_t self_rank;
   int32_t slot;        // type-constraint mask slot | (has_pref << 16); -1 = malformed decision, -2 = absent
+  uint32_t self_bits;  // bit 0: self is in the slot's candidate mask (replicaset filter applied); bit 1: in its preferred mask
+  int32_t self_count;  // published count of self (IR:39)
 };
 MMP_HD int ctx_slot(const DecisionCtx &c) { return c.slot & 0xffff; }
 MMP_HD bool ctx_has_pref(const DecisionCtx &c) { return (c.slot >> 16) & 1; }
 
-MMP_HD void prepare_ctx(const SnapshotView &s, const mmp_decision_in &d, const FreshRow *fresh_tab, int32_t n_fresh,
-                        DecisionCtx &c) {
-  c.d = d; c.slot = -1; c.self_rank = -1; c.last_used = 0;
+// The context is gathered in two steps so that a kernel can issue the first (two independent gathers that depend only on
+// the decision record: the model row from HBM, rank_of[self]) a whole step ahead of the second (what depends on them).
+struct CtxA { mmp_model_row mr; int32_t self_rank; int32_t ok; };
+MMP_HD void prepare_ctx_a(const SnapshotView &s, const mmp_decision_in &d, CtxA &a) {
+  a.ok = !(d.model < 0 || d.model >= s.n_models || d.self < 0 || d.self >= s.max_instances);
+  a.self_rank = -1;
+  a.mr.last_used = 0; a.mr.size_units = 0; a.mr.rpm = 0; a.mr.type_id = 0; a.mr.copy_count = 0; a.mr.fail_count = 0; a.mr.reserved = 0;
+  if (a.ok) { a.mr = s.models[d.model]; a.self_rank = s.rank_of[d.self]; }
+}
+MMP_HD void prepare_ctx_b(const SnapshotView &s, const mmp_decision_in &d, const CtxA &a, const FreshRow *fresh_tab, int32_t n_fresh,
+                          DecisionCtx &c) {
+  c.d = d; c.slot = -1; c.self_rank = -1; c.last_used = 0; c.self_bits = 0; c.self_count = 0;
   c.fr.lru = 0; c.fr.rem = 0; c.fr.count = 0; c.fr.rpm = 0;
-  if (d.model < 0 || d.model >= s.n_models || d.self < 0 || d.self >= s.max_instances) return;
-  const mmp_model_row mr = s.models[d.model];
-  const int tid = mr.type_id < s.n_type_ids ? mr.type_id : 0;
-  c.last_used = (d.flags & MMP_DF_MODEL_LAST_USED) ? mr.last_used : d.last_used;
-  c.self_rank = s.rank_of[d.self];
+  if (!a.ok) return;
+  const int tid = a.mr.type_id < s.n_type_ids ? a.mr.type_id : 0;
+  c.last_used = (d.flags & MMP_DF_MODEL_LAST_USED) ? a.mr.last_used : d.last_used;
+  c.self_rank = a.self_rank;
+  const uint32_t ts = s.type_slot[tid];  // slot | has_pref << 15
   if (d.fresh >= 0 && d.fresh < n_fresh) c.fr = fresh_tab[d.fresh];
   else if (c.self_rank >= 0) { const RankRow sr = load_row(s.rows + c.self_rank); c.fr.lru = sr.lru; c.fr.rem = sr.rem; c.fr.count = sr.count; c.fr.rpm = 0; }
   else return;
-  const int sl = s.type_slot[tid];
-  c.slot = sl | ((s.has_pref[sl] ? 1 : 0) << 16);
+  const int sl = (int)(ts & 0x7fffu);
+  c.slot = sl | ((int)(ts >> 15) << 16);
+  if (c.self_rank >= 0) {  // what the walk asks about self, gathered here so that it is not a dependent load inside the walk
+    const size_t so = (size_t)sl * (size_t)s.row_words + ((uint32_t)c.self_rank >> 5);
+    const uint32_t sh = (uint32_t)c.self_rank & 31u;
+    c.self_bits = (((s.any_rs ? s.candx : s.cand)[so] >> sh) & 1u) | (((s.pref[so] >> sh) & 1u) << 1);
+    c.self_count = s.count_col[c.self_rank];
+  }
+}
+MMP_HD void prepare_ctx(const SnapshotView &s, const mmp_decision_in &d, const FreshRow *fresh_tab, int32_t n_fresh,
+                        DecisionCtx &c) {
+  CtxA a;
+  prepare_ctx_a(s, d, a);
+  prepare_ctx_b(s, d, a, fresh_tab, n_fresh, c);
 }
 
 #define MMP_BAIL_CHECK do { if (co.bailed()) { o.flags |= MMP_TF_BAIL; o.target = MMP_TARGET_NONE; return; } } while (0)
@@ -613,6 +636,37 @@ MMP_HD bool decide_fast(const SnapshotView &s, const DecisionCtx &c, const uint3
   return true;
 }
 
+// The per-rank / per-word tables a lane reads INSIDE its window, indexable by absolute row word / rank.  k_place_lanes
+// points them at a shared-memory copy of the front of each table (with the SM's shared memory given to the landing
+// stages, L1 is too small to keep them resident and every gather would be an L2 round trip); the CPU harness and
+// small launches point them at the snapshot's own arrays.
+struct LaneTables {
+  const uint32_t *cx, *p;   // this decision's candidate (filter applied) and preferred mask rows
+  const uint32_t *full;
+  const WordSumI *csum;
+  const int32_t *count_col;
+  const RankRow *rows;
+};
+MMP_HD RankRow load_row_any(const RankRow *p) {  // generic address space (shared or global)
+#if defined(__CUDA_ARCH__)
+  const int4 a = reinterpret_cast<const int4 *>(p)[0], b = reinterpret_cast<const int4 *>(p)[1];
+  RankRow r;
+  r.lru = (int64_t)(((uint64_t)(uint32_t)a.y << 32) | (uint32_t)a.x);
+  r.rem = (int64_t)(((uint64_t)(uint32_t)a.w << 32) | (uint32_t)a.z);
+  r.count = b.x; r.rpm = b.y; r.idx = b.z; r.flags = (uint32_t)b.w;
+  return r;
+#else
+  return *p;
+#endif
+}
+MMP_HD LaneTables lane_tables_global(const SnapshotView &s, int slot) {
+  LaneTables t;
+  const size_t so = (size_t)slot * (size_t)s.row_words;
+  t.cx = (s.any_rs ? s.candx : s.cand) + so; t.p = s.pref + so; t.full = s.full; t.csum = s.csum; t.count_col = s.count_col;
+  t.rows = s.rows;
+  return t;
+}
+
 // ---- vote shapes for decide_stream: 32 decisions in lockstep on the GPU, one on the CPU harness ----
 struct SoloVote { MMP_HD bool any(bool p) const { return p; } };
 #if defined(__CUDACC__)
@@ -636,18 +690,16 @@ struct WarpVote { MMP_D bool any(bool p) const { return __any_sync(0xffffffffu, 
 // declined like one that exceeds the budget.  self_eword = the row word that holds self's bit (anywhere in the row).
 // Must be called by every lane of the vote group (active = false for lanes without a decision).
 template <class V>
-MMP_HD bool decide_stream(const SnapshotView &s, const DecisionCtx &c, bool active, const uint32_t *erow, uint32_t win_words,
-                          uint32_t self_eword, int64_t now, uint64_t seed, uint64_t decision_id, const V &vote, DecideOut &o,
-                          int32_t budget) {
+MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const DecisionCtx &c, bool active, const uint32_t *erow,
+                          uint32_t win_words, uint32_t self_eword, int64_t now, uint64_t seed, uint64_t decision_id, const V &vote,
+                          DecideOut &o, int32_t budget) {
   o.target = MMP_TARGET_NONE; o.n_candidates = 0; o.best = -1; o.n_remaining = 0; o.pick_index = 0; o.flags = 0;
   o.cut_rank = (int32_t)NONE_RANK; o.best_rank = -1; o.first_rank = -1;
   const uint32_t NW = (uint32_t)s.row_words, WS = (uint32_t)s.word_lo, WE = (uint32_t)s.word_hi;
   const bool open_end = WE < NW;
   bool live = active && c.slot >= 0 && c.d.extra_n == 0;
   const mmp_decision_in &d = c.d;
-  const uint32_t so = (uint32_t)(live ? ctx_slot(c) : 0) * NW;
-  const uint32_t *CX = (s.any_rs ? s.candx : s.cand) + so;
-  const uint32_t *P = s.pref + so;
+  const uint32_t *CX = T.cx, *P = T.p;  // window words only; the self check below reads the snapshot's own rows
   const bool favour_self = (d.flags & MMP_DF_FAVOUR_SELF) != 0;
   const int32_t self_rank = c.self_rank;
   const FreshRow fr = c.fr;
@@ -679,7 +731,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const DecisionCtx &c, bool acti
   int32_t best_count = 0, best_rpm = 0, best_idx = -1;
   uint32_t best_rank = b, lo = b, hi = NONE_RANK;
   if (live) {
-    rb = load_row(s.rows + b);
+    rb = load_row_any(T.rows + b);
     us = rb.idx == d.self;
     best_rem = us ? fr.rem : rb.rem; best_count = us ? fr.count : rb.count; best_rpm = us ? fr.rpm : rb.rpm; best_idx = rb.idx;
     if (best_rem < s.min_space) live = false;  // best full (MM:4811): general routine
@@ -697,7 +749,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const DecisionCtx &c, bool acti
         if (wi >= WE) search = false;
         else if (left <= 0 || wi - WS >= win_words) { search = false; live = false; }
         else {
-          uint32_t x = Fw(wi) & (P[wi] | s.full[wi]) & mask_above(wi * 32u, b);
+          uint32_t x = Fw(wi) & (P[wi] | T.full[wi]) & mask_above(wi * 32u, b);
           if (x) { r1 = wi * 32u + (uint32_t)ffs32(x); search = false; }
           else { wi++; left--; }
         }
@@ -709,7 +761,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const DecisionCtx &c, bool acti
   if (live && !simple) {
     if (r1 == NONE_RANK) open = open_end;  // else: neither kind follows, "no preference" logic over the whole remainder
     else if (pbit(r1)) {
-      const RankRow rp = load_row(s.rows + r1);
+      const RankRow rp = load_row_any(T.rows + r1);
       best_rank = r1; best_idx = rp.idx; best_rem = rp.rem; best_count = rp.count; best_rpm = rp.rpm;
       us = rp.idx == d.self;
       lo = r1; use_pref = true;
@@ -727,13 +779,16 @@ MMP_HD bool decide_stream(const SnapshotView &s, const DecisionCtx &c, bool acti
   if (walk) {
     if (self_rank >= 0 && (uint32_t)self_rank > lo && (uint32_t)self_rank < hi) {
       const uint32_t w = (uint32_t)self_rank >> 5, bit = 1u << (self_rank & 31);
-      if (w - WS < WE - WS && (CX[w] & ~self_eword & bit) != 0 && (!use_pref || (P[w] & bit) != 0)) { self_in_s = true; sw_ = w; sb_ = bit; }
+      // self may sit anywhere in the row: its mask bits were gathered with the context, its row word by the caller
+      if (w - WS < WE - WS && (c.self_bits & 1u) != 0 && (self_eword & bit) == 0 && (!use_pref || (c.self_bits & 2u) != 0)) {
+        self_in_s = true; sw_ = w; sb_ = bit;
+      }
     }
     const int64_t q = best_rem >> 2;
     c_self = fr.rem < s.min_space || fr.rem < q;
     self_viol = rb.rem < s.min_space || rb.rem < q;
     thr = jaddi(best_count, best_count >> 2);
-    if (self_in_s && cv(s.count_col[self_rank])) self_viol = true;
+    if (self_in_s && cv(c.self_count)) self_viol = true;
   }
   const uint32_t cut_self = (self_in_s && self_viol) ? (uint32_t)self_rank : NONE_RANK;
   // S' = F restricted to (lo, lim), lim = min(hi, cut_self): nothing at or beyond a failing self can be a candidate
@@ -759,7 +814,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const DecisionCtx &c, bool acti
             int cls = 0;  // 0: no member fails, 1: every member (but a passing self) fails, 2: look at the counts
             uint32_t v = x;
             if (c_self) { if (wi == sw_) v &= ~sb_; cls = v ? 1 : 0; }
-            else if (x) { const WordSumI m = s.csum[wi]; cls = !cv(m.hi) ? 0 : (cv(m.lo) ? 1 : 2); }
+            else if (x) { const WordSumI m = T.csum[wi]; cls = !cv(m.hi) ? 0 : (cv(m.lo) ? 1 : 2); }
             if (cls == 0) { n_in += (uint32_t)popc32(x); wi++; left--; }
             else {
               search = false; xt = x;
@@ -775,14 +830,14 @@ MMP_HD bool decide_stream(const SnapshotView &s, const DecisionCtx &c, bool acti
         mixed = false;
         uint32_t vm = 0;
 #if defined(__CUDA_ARCH__)
-        const int4 *cc = reinterpret_cast<const int4 *>(s.count_col + (size_t)wi * 32u);
+        const int4 *cc = reinterpret_cast<const int4 *>(T.count_col + (size_t)wi * 32u);
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-          const int4 q = __ldg(cc + j);
+          const int4 q = cc[j];
           vm |= ((cv(q.x) ? 1u : 0u) | (cv(q.y) ? 2u : 0u) | (cv(q.z) ? 4u : 0u) | (cv(q.w) ? 8u : 0u)) << (4 * j);
         }
 #else
-        const int32_t *cc = s.count_col + (size_t)wi * 32u;
+        const int32_t *cc = T.count_col + (size_t)wi * 32u;
         for (int j = 0; j < 32; j++) vm |= (cv(cc[j]) ? 1u : 0u) << j;
 #endif
         vm &= xt;
@@ -850,7 +905,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const DecisionCtx &c, bool acti
   o.best = best_idx; o.best_rank = (int32_t)best_rank;
   if (open) { o.flags = MMP_TF_OPEN; return true; }
   if (!done) {
-    const int32_t cidx = chosen_rank == best_rank ? best_idx : s.rows[chosen_rank].idx;
+    const int32_t cidx = chosen_rank == best_rank ? best_idx : ((int32_t)chosen_rank == self_rank ? d.self : T.rows[chosen_rank].idx);
     o.target = (!favour_self && cidx == d.self) ? MMP_TARGET_SELF : cidx;
     o.n_candidates = ccount;
     o.n_remaining = remaining; o.pick_index = (int32_t)index;

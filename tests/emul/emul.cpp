@@ -106,10 +106,10 @@ static SnapshotView make_view(mmp_fleet *f) {
   const HostSnapshot &s = f->snap;
   v.n_ranks = s.n_ranks; v.row_words = s.row_words; v.n_models = (int32_t)f->models.size(); v.max_instances = f->hs.cfg.max_instances;
   v.any_rs = s.any_rs; v.n_type_ids = (int32_t)s.type_slot.size(); v.min_space = f->hs.cfg.min_space_units;
-  v.word_lo = s.word_lo; v.word_hi = s.word_hi; v.excl_stride = s.excl_stride; v.shard_reserved = 0;
+  v.word_lo = s.word_lo; v.word_hi = s.word_hi; v.excl_stride = s.excl_stride; v.n_slots = s.n_slots;
   v.count_col = s.count_col.data();
   v.excl = f->excl.data(); v.cand = s.cand.data(); v.candx = s.candx.data(); v.pref = s.pref.data(); v.has_pref = s.has_pref.data();
-  v.type_slot = s.type_slot.data(); v.full = s.full.data(); v.rows = s.rows.data();
+  v.type_slot = s.type_slot_hp.data(); v.full = s.full.data(); v.rows = s.rows.data();
   v.rank_of = s.rank_of.data(); v.csum = s.csum.data(); v.lsum = s.lsum.data(); v.models = f->models.data();
   return v;
 }
@@ -138,7 +138,7 @@ int32_t mmp_place_batch_trace(mmp_fleet *f, const mmp_decision_in *in, int32_t n
     if (win == 2 && !cand_mask) {  // the lockstep lane routine of k_place_lanes (one decision per lane), general routine when it declines
       uint32_t self_eword = 0;
       if (cx.self_rank >= 0 && (cx.self_rank >> 5) >= v.word_lo && (cx.self_rank >> 5) < v.word_hi) self_eword = erow[(cx.self_rank >> 5) - v.word_lo];
-      done = decide_stream(v, cx, true, erow, (uint32_t)g_lane_window, self_eword, now_ms, seed, (uint64_t)i, SoloVote(), o, g_lane_budget);
+      done = decide_stream(v, lane_tables_global(v, cx.slot >= 0 ? ctx_slot(cx) : 0), cx, true, erow, (uint32_t)g_lane_window, self_eword, now_ms, seed, (uint64_t)i, SoloVote(), o, g_lane_budget);
       g_lane_decisions++;
       if (!done) g_bails++;
     } else if (sharded) {
