@@ -183,6 +183,19 @@ int32_t mmp_host_alloc(mmp_fleet *, int64_t bytes, void **out);
 int32_t mmp_host_free(mmp_fleet *, void *p);
 int32_t mmp_flush_l2(mmp_fleet *); /* writes a buffer larger than L2 (bench hygiene) */
 
+/* ---- instance-sharded multi-GPU: one process per GPU, mmp_config.shard_rank / shard_count.
+ * Every process ingests the whole fleet; shard k keeps ranks [lo, hi) of every exclusion-bitmap row in its GPU's HBM
+ * (contiguous ranges of PLACEMENT_ORDER ranks in 16-byte granules) and the small per-instance tables in full.
+ * mmp_place_batch / mmp_place_batch_device on such a fleet must be called by all shards with the same batch; each shard
+ * resolves every decision over its own range, ONE ncclAllReduce(min) over 64-bit min-loc keys picks the answer of the
+ * shard that holds the first entry under PLACEMENT_ORDER (MM:4806), and decisions whose shortlist walk (MM:4901-4937)
+ * left that shard's range are finished from all-gathered row blocks.  Every shard returns the full results.
+ * Replaces nothing in the reference (one JVM decides alone); it is the scale-out of plug point 1. ---- */
+int32_t mmp_shard_unique_id(void *id128);                       /* shard 0: ncclGetUniqueId; the host passes the 128 bytes to its peers */
+int32_t mmp_shard_connect(mmp_fleet *, const void *id128);      /* all shards: ncclCommInitRank(shard_count, id, shard_rank) */
+int32_t mmp_shard_words(mmp_fleet *, int32_t *word_lo, int32_t *word_hi); /* this shard's row words [lo, hi); returns the stored row stride */
+int64_t mmp_shard_open_decisions(mmp_fleet *);                  /* decisions that needed the row-gather pass so far */
+
 /* ---- snapshot introspection ---- */
 int32_t mmp_row_words(mmp_fleet *);                                   /* 32-bit words per exclusion-bitmap row */
 int32_t mmp_live_instances(mmp_fleet *);                              /* number of ranked instances in the snapshot */

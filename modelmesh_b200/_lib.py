@@ -98,6 +98,10 @@ SYMBOLS = [
     ("mmp_lru_init", _I32, [_P, _I32, _P, _I32]),
     ("mmp_lru_apply", _I32, [_P, _P, _I32, _I64, _P, _I32]),
     ("mmp_lru_state", _I32, [_P, _I32, _P, _P, _P]),
+    ("mmp_shard_unique_id", _I32, [_P]),
+    ("mmp_shard_connect", _I32, [_P, _P]),
+    ("mmp_shard_words", _I32, [_P, C.POINTER(_I32), C.POINTER(_I32)]),
+    ("mmp_shard_open_decisions", _I64, [_P]),
 ]
 
 

@@ -31,7 +31,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return SO
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-Xlinker", "-Bsymbolic", "-shared", "-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
+           "-Xcompiler", "-fPIC", "-Xlinker", "-Bsymbolic", "-shared", "-ldl", "-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -171,6 +171,7 @@ class HostState {
     for (int32_t i = 0; i < n_ids; i++)
       if (ids[i] < 0 || ids[i] >= cfg.max_instances) { err = "model instance id out of range"; return MMP_E_ARG; }
     models[m] = *row;
+    models[m].reserved = (uint32_t)n_ids;  // library-private: size of the exclusion row (instance-shard early-out)
     for (int i = 0; i < EDGE_INL; i++) edge_inl[(size_t)m * EDGE_INL + i] = i < n_ids ? ids[i] : -1;
     if (n_ids > EDGE_INL) edge_ovf[m].assign(ids + EDGE_INL, ids + n_ids);
     else if (!edge_ovf.empty()) edge_ovf.erase(m);
@@ -378,7 +379,7 @@ class HostState {
     const int32_t block = ((row_words + count - 1) / count + 3) / 4 * 4;
     lo = std::min(row_words, rank * block);
     hi = std::min(row_words, lo + block);
-    stride = std::max(4, (hi - lo + 3) / 4 * 4);
+    stride = block;  // the same for every shard (a short or empty last shard is zero-padded): the row gather is a plain all-gather
   }
 
  private:

@@ -12,6 +12,11 @@
 // Kernels: k_build_bitmap / k_build_bitmap_ovf (commit), k_place<NWL,K,WARPS> (one warp per decision, TMA-staged rows),
 //          k_stats, k_reaper_*, k_lru_apply (see below).
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include <atomic>
 #include <condition_variable>
@@ -106,12 +111,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 // The warp-wide redo of a decision its tile could not resolve inside its window: the 32-word fast path first, then the
 // general routine.  Kept out of line so the kernel's tile loop stays small.
 __device__ __noinline__ void decide_warp(const SnapshotView s, const DecisionCtx &c, const uint32_t *erow, const int32_t *extra,
-                                         int64_t now, uint64_t seed, uint64_t decision_id, int32_t *target, int32_t *n_candidates) {
+                                         int64_t now, uint64_t seed, uint64_t decision_id, int32_t *target, int32_t *n_candidates,
+                                         int32_t *first_rank = nullptr, int32_t *flags = nullptr) {
   Coop32 co;
   DecideOut o;
+  o.first_rank = -1; o.flags = 0;
   const bool whole_rows = s.word_lo == 0 && s.word_hi == s.row_words;  // decide_fast reads rows by absolute word index
   if (!whole_rows || !decide_fast<false>(s, c, erow, now, seed, decision_id, co, o)) decide_ctx(s, c, erow, extra, now, seed, decision_id, co, o, nullptr);
   *target = o.target; *n_candidates = o.n_candidates;
+  if (first_rank) { *first_rank = o.first_rank; *flags = o.flags; }
 }
 
 struct RingLayout {
@@ -339,7 +347,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotVie
                                                                const FreshRow *__restrict__ fresh, int n_fresh,
                                                                const int32_t *__restrict__ extra, mmp_decision_out *__restrict__ out,
                                                                int64_t now, uint64_t seed, uint64_t id_base, int ns,
-                                                               int front_tables, int mode, unsigned long long *__restrict__ dbg) {
+                                                               int front_tables, int mode, unsigned long long *__restrict__ dbg,
+                                                               int emit_keys, int shard_rank, const int32_t *__restrict__ orig_id) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int RW = s.excl_stride;  // words per stored row (the whole row unless the fleet is instance-sharded)
   const LaneLayout lay(RW, ns, WARPS, front_tables != 0);
@@ -438,17 +447,22 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotVie
     LANE_T(0);
     unsigned char *stage = smem_raw + (size_t)st * lay.stage_bytes;
     const uint32_t *my_row = reinterpret_cast<const uint32_t *>(stage + (size_t)lane * lay.stride);
-    const int m = (valid && d.model >= 0 && d.model < s.n_models) ? d.model : 0;
-    if (valid) {
+    // row of this decision: its model's, or row i of a gathered row set (orig_id != nullptr: the instance-shard gather pass)
+    const int m = orig_id ? (valid ? b * 32 + lane : 0) : ((valid && d.model >= 0 && d.model < s.n_models) ? d.model : 0);
+    DecisionCtx c;
+    c.slot = -2; c.d.model = 0; c.self_rank = -1; c.self_bits = 0; c.self_count = 0;
+    bool skip = false;  // instance-sharded, not the first shard: an entry in a lower shard wins, the row is not even read
+    if (s.word_lo > 0) {
+      if (valid) { prepare_ctx_b(s, d, ca, fresh, n_fresh, c); skip = shard_cannot_win(s, c, ca.mr.reserved); }
+    }
+    if (valid && !skip) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the previous owner's reads precede this async write
       mbar_expect_tx(&bars[st], lay.row_bytes);
       bulk_g2s(const_cast<uint32_t *>(my_row), s.excl + (size_t)m * RW, lay.row_bytes, &bars[st]);
     } else mbar_arrive(&bars[st]);
     LANE_T(1);
     // ---- the rest of this batch's context while its rows are in flight ----
-    DecisionCtx c;
-    c.slot = -2; c.d.model = 0; c.self_rank = -1; c.self_bits = 0; c.self_count = 0;
-    if (valid) prepare_ctx_b(s, d, ca, fresh, n_fresh, c);
+    if (s.word_lo == 0 && valid) prepare_ctx_b(s, d, ca, fresh, n_fresh, c);
     if (timing && __shfl_xor_sync(0xffffffffu, c.slot ^ (int)c.self_bits, 1) == 0x7fffffff) tsum[2]++;  // consume the gathers before the timestamp
     LANE_T(2);
     while (!mbar_try_wait(&bars[st], parity)) {}
@@ -466,7 +480,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotVie
         }
       }
       const int sw = c.self_rank >> 5;
-      if (c.self_rank >= 0 && sw >= s.word_lo && sw < s.word_hi) self_eword = my_row[sw - s.word_lo];
+      if (!skip && c.self_rank >= 0 && sw >= s.word_lo && sw < s.word_hi) self_eword = my_row[sw - s.word_lo];
     }
     __syncwarp();
     if (lane == 0) { __threadfence_block(); atomicAdd(const_cast<uint32_t *>(released + st), 1u); }
@@ -488,24 +502,32 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotVie
       T.full = f_full - WS; T.csum = f_csum - WS; T.count_col = f_count - WS * 32; T.rows = f_rows - WS * 32;
     }
     bool handled = true;
+    const uint64_t my_id = id_base + (uint64_t)(orig_id ? (valid ? orig_id[b * 32 + lane] : 0) : b * 32 + lane);
     if ((mode & 1) == 0)
-      handled = decide_stream(s, T, c, valid, win + lane * (LANE_WIN + 1), win_words, self_eword, now, seed,
-                              id_base + (uint64_t)(b * 32 + lane), WarpVote(), o, LANE_BUDGET);
+      handled = decide_stream(s, T, c, valid && !skip, win + lane * (LANE_WIN + 1), win_words, self_eword, now, seed, my_id,
+                              WarpVote(), o, LANE_BUDGET);
     else { o.target = (int32_t)(self_eword & 1u) - 1; o.n_candidates = 0; }  // MMP_LANE_MODE=1: stream-only probe (no decisions)
     // ---- what the lane routine declined: the whole warp redoes it, reading the row from global memory (L2) ----
-    uint32_t pending = __ballot_sync(0xffffffffu, valid && !handled);
+    uint32_t pending = __ballot_sync(0xffffffffu, valid && !skip && !handled);
     while (pending) {
       const int l = __ffs((int)pending) - 1;
       pending &= pending - 1;
       if (lane == l) *ctx_one = c;
       const int ml = __shfl_sync(0xffffffffu, m, l);
+      const uint64_t idl = __shfl_sync(0xffffffffu, my_id, l);
       __syncwarp();
-      int32_t t2, c2;
-      decide_warp(s, *ctx_one, s.excl + (size_t)ml * RW, extra, now, seed, id_base + (uint64_t)(b * 32 + l), &t2, &c2);
-      if (lane == l) { o.target = t2; o.n_candidates = c2; }
+      int32_t t2, c2, f2, g2;
+      decide_warp(s, *ctx_one, s.excl + (size_t)ml * RW, extra, now, seed, idl, &t2, &c2, &f2, &g2);
+      if (lane == l) { o.target = t2; o.n_candidates = c2; o.first_rank = f2; o.flags = g2; }
       __syncwarp();
     }
-    if (valid) out[b * 32 + lane] = mmp_decision_out{o.target, o.n_candidates};
+    if (valid) {
+      if (emit_keys) {  // instance-sharded: one min-loc key per decision instead of the result (same 8 bytes)
+        uint64_t key = ~(uint64_t)0;
+        if (!skip) key = shard_key(o, shard_rank);
+        reinterpret_cast<uint64_t *>(out)[b * 32 + lane] = key;
+      } else out[b * 32 + lane] = mmp_decision_out{o.target, o.n_candidates};
+    }
     b = bn; d = dn; valid = valid_n; ca = cn;
     bn = bnn; dn = dnn; valid_n = valid_nn;
     __syncwarp();
@@ -518,6 +540,89 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotVie
   }
 #undef LANE_T
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// instance-sharded combine: kernels around the one collective
+// ---------------------------------------------------------------------------------------------------------------
+// keys -> results in place (both 8 bytes per decision) + a flag per decision whose winning shard left it open
+__global__ void k_shard_decode(uint64_t *__restrict__ keys_out, int n, uint8_t *__restrict__ open_flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t k = keys_out[i];
+  int32_t t, c;
+  shard_key_decode(k, t, c);
+  const bool open = shard_key_open(k);
+  open_flag[i] = open ? 1 : 0;
+  reinterpret_cast<mmp_decision_out *>(keys_out)[i] = mmp_decision_out{open ? MMP_TARGET_NONE : t, open ? 0 : c};
+}
+// this shard's block of the exclusion row of every open decision, and the decision records themselves, compacted
+__global__ void k_shard_pack(const SnapshotView s, const mmp_decision_in *__restrict__ in, const int32_t *__restrict__ open_idx,
+                             int n_open, uint32_t *__restrict__ blocks, mmp_decision_in *__restrict__ in_open) {
+  const int stride = s.excl_stride;
+  const size_t total = (size_t)n_open * stride;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(t / stride), w = (int)(t - (size_t)j * stride);
+    const mmp_decision_in d = in[open_idx[j]];
+    const int m = (d.model >= 0 && d.model < s.n_models) ? d.model : 0;
+    blocks[t] = s.excl[(size_t)m * stride + w];
+    if (w == 0) in_open[j] = d;
+  }
+}
+// gathered[g][j][stride] -> rows[j][row_words]
+__global__ void k_shard_assemble(const uint32_t *__restrict__ gathered, int n_open, int stride, int shards, int row_words,
+                                 uint32_t *__restrict__ rows) {
+  const size_t total = (size_t)n_open * row_words;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(t / row_words), w = (int)(t - (size_t)j * row_words);
+    const int g = w / stride;
+    rows[t] = g < shards ? gathered[((size_t)g * n_open + j) * stride + (w - g * stride)] : 0u;
+  }
+}
+__global__ void k_shard_scatter(const mmp_decision_out *__restrict__ res, const int32_t *__restrict__ open_idx, int n_open,
+                                mmp_decision_out *__restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n_open) out[open_idx[j]] = res[j];
+}
+
+// NCCL is bound at run time (dlopen): a single-GPU deployment needs no NCCL at all, and inside a process that already
+// carries a copy (PyTorch's) the same one is used.
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+static NcclApi &nccl_api() {
+  static NcclApi a = [] {
+    NcclApi x;
+    for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+      x.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (x.lib) break;
+    }
+    if (!x.lib) return x;
+    x.GetUniqueId = (decltype(x.GetUniqueId))dlsym(x.lib, "ncclGetUniqueId");
+    x.CommInitRank = (decltype(x.CommInitRank))dlsym(x.lib, "ncclCommInitRank");
+    x.CommDestroy = (decltype(x.CommDestroy))dlsym(x.lib, "ncclCommDestroy");
+    x.AllReduce = (decltype(x.AllReduce))dlsym(x.lib, "ncclAllReduce");
+    x.AllGather = (decltype(x.AllGather))dlsym(x.lib, "ncclAllGather");
+    x.GetErrorString = (decltype(x.GetErrorString))dlsym(x.lib, "ncclGetErrorString");
+    x.ok = x.GetUniqueId && x.CommInitRank && x.CommDestroy && x.AllReduce && x.AllGather && x.GetErrorString;
+    return x;
+  }();
+  return a;
+}
+#define NK(call)                                                                                         \
+  do {                                                                                                   \
+    ncclResult_t r_ = (call);                                                                            \
+    if (r_ != ncclSuccess) {                                                                             \
+      g_err = std::string(#call) + ": " + nccl_api().GetErrorString(r_);                                 \
+      return MMP_E_NCCL;                                                                                 \
+    }                                                                                                    \
+  } while (0)
 
 // ---------------------------------------------------------------------------------------------------------------
 // device-side containers
@@ -540,13 +645,13 @@ struct DevBuf {
 
 struct DeviceSnapshot {
   DevBuf excl, cand, candx, pref, has_pref, type_slot, full, rows, rank_of, csum, lsum, models;
-  DevBuf cap_col, lthreads_col, linprog_col, part_of_rank, count_col;
+  DevBuf cap_col, lthreads_col, linprog_col, part_of_rank, count_col, cand_before;
   SnapshotView view{};
   HostSnapshot host;  // kept for introspection and the small host-side parts of stats / reaper
   int32_t n_models = 0;
   void release() {
     for (DevBuf *b : {&excl, &cand, &candx, &pref, &has_pref, &type_slot, &full, &rows, &rank_of, &csum, &lsum, &models,
-                      &cap_col, &lthreads_col, &linprog_col, &part_of_rank, &count_col})
+                      &cap_col, &lthreads_col, &linprog_col, &part_of_rank, &count_col, &cand_before})
       b->release();
   }
 };
@@ -557,6 +662,7 @@ struct PlaceCtx {
   cudaStream_t pipe[NPIPE] = {nullptr, nullptr, nullptr};  // H2D / kernel / D2H of consecutive chunks overlap across these
   cudaEvent_t e0 = nullptr, e1 = nullptr, ready = nullptr;
   DevBuf d_in, d_out, d_fresh, d_extra, d_trace, d_cand, d_counters;
+  DevBuf d_open_flag, d_open_idx, d_n_open, d_cub, d_blocks, d_gathered, d_rows, d_in_open, d_out_open;  // instance-shard combine
   static constexpr int NCOUNTERS = 64;  // batch counters of k_place_lanes, one per launch in flight on this context
   int next_counter = 0;
   int *counter() { return d_counters.as<int>() + (next_counter++ % NCOUNTERS); }
@@ -578,6 +684,9 @@ struct mmp_fleet {
   int32_t epoch = 0;
   cudaStream_t commit_stream = nullptr;
   DevBuf d_edge_inl, d_ovf_pairs, d_flush, d_dbg;
+  ncclComm_t comm = nullptr;    // instance-shard communicator (mmp_shard_connect)
+  std::mutex comm_mu;           // collectives of one communicator are issued by one thread at a time
+  std::atomic<int64_t> open_decisions{0};  // decisions that needed the row-gather pass so far
   std::mutex ctx_mu;
   std::vector<std::unique_ptr<PlaceCtx>> ctx_free;
   std::atomic<int64_t> launches{0};
@@ -634,7 +743,9 @@ static void release_ctx(mmp_fleet *f, PlaceCtx *c) {
   f->ctx_free.emplace_back(c);
 }
 static void destroy_ctx(PlaceCtx *c) {
-  for (DevBuf *b : {&c->d_in, &c->d_out, &c->d_fresh, &c->d_extra, &c->d_trace, &c->d_cand, &c->d_counters}) b->release();
+  for (DevBuf *b : {&c->d_in, &c->d_out, &c->d_fresh, &c->d_extra, &c->d_trace, &c->d_cand, &c->d_counters, &c->d_open_flag,
+                    &c->d_open_idx, &c->d_n_open, &c->d_cub, &c->d_blocks, &c->d_gathered, &c->d_rows, &c->d_in_open, &c->d_out_open})
+    b->release();
   if (c->e0) cudaEventDestroy(c->e0);
   if (c->e1) cudaEventDestroy(c->e1);
   if (c->ready) cudaEventDestroy(c->ready);
@@ -658,7 +769,9 @@ struct PlaceArgs {
   uint32_t *cand;
   int64_t now;
   uint64_t seed, id_base;
-  int *batch_counter;  // device int, zeroed by the launcher: k_place_lanes warps claim batches of 32 decisions from it
+  int *batch_counter;  // (unused since batches are dealt statically; kept so every launch site names its context)
+  int emit_keys = 0;            // instance-sharded: write shard keys (uint64) into `out` instead of results
+  const int32_t *orig_id = nullptr;  // gather pass: decision i reads row i of s.excl and hashes with id orig_id[i]
 };
 
 // ring depth (a power of two) / warps per block by row size: rows up to 2 KiB (16k instances) K=4 x 8 warps, up to 4 KiB K=2 x 8, beyond K=2 x 4
@@ -706,7 +819,8 @@ static cudaError_t launch_place_lanes(mmp_fleet *f, const PlaceArgs &a, cudaStre
   const int nb = (a.n + 31) / 32;
   const int grid = std::max(1, std::min((nb + WARPS - 1) / WARPS, f->sm_count));
   kern<<<grid, WARPS * 32, lay.total, st>>>(a.s, a.in, a.n, a.fresh, a.n_fresh, a.extra, a.out, a.now, a.seed, a.id_base, ns,
-                                            f->lane_front, f->lane_mode, f->d_dbg.as<unsigned long long>());
+                                            f->lane_front, f->lane_mode, f->d_dbg.as<unsigned long long>(), a.emit_keys,
+                                            f->hs.cfg.shard_rank, a.orig_id);
   f->launches++;
   return cudaGetLastError();
 }
@@ -740,9 +854,109 @@ static cudaError_t launch_place(mmp_fleet *f, const PlaceArgs &a, cudaStream_t s
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// instance-sharded placement: every shard resolves the whole batch over its own rank range, ONE all-reduce(min) of the
+// 64-bit keys gives every rank the answer of the shard that holds the first entry under PLACEMENT_ORDER (min-loc), and
+// the (rare) decisions whose walk left the winning shard's range are finished from all-gathered row blocks.
+// d_in/d_out are device buffers; every rank is given the same batch and ends with the same results.
+// ---------------------------------------------------------------------------------------------------------------
+static int32_t place_sharded(mmp_fleet *f, PlaceCtx *c, const DeviceSnapshot &ds, const mmp_decision_in *d_in, int32_t n,
+                             const FreshRow *d_fresh, int32_t n_fresh, const int32_t *d_extra, mmp_decision_out *d_out,
+                             int64_t now_ms, uint64_t seed, cudaStream_t st) {
+  if (!f->comm) { g_err = "instance-sharded fleet is not connected (mmp_shard_connect)"; return MMP_E_STATE; }
+  NcclApi &nc = nccl_api();
+  std::lock_guard<std::mutex> g(f->comm_mu);
+  const int G = f->hs.cfg.shard_count;
+  // 1. per-shard keys (the scoring kernel)
+  PlaceArgs a{ds.view, d_in, n, d_fresh, n_fresh, d_extra, d_out, nullptr, nullptr, now_ms, seed, 0, c->counter()};
+  a.emit_keys = 1;
+  CK(launch_place(f, a, st));
+  // 2. min-loc combine over NVLink
+  NK(nc.AllReduce(d_out, d_out, (size_t)n, ncclUint64, ncclMin, f->comm, st));
+  // 3. keys -> results, flag what is still open
+  CK(c->d_open_flag.ensure((size_t)n));
+  CK(c->d_open_idx.ensure((size_t)n * 4));
+  CK(c->d_n_open.ensure(16));
+  k_shard_decode<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<uint64_t *>(d_out), n, c->d_open_flag.as<uint8_t>());
+  f->launches++;
+  CK(cudaGetLastError());
+  size_t tmp_bytes = 0;
+  thrust::counting_iterator<int32_t> iota(0);
+  CK(cub::DeviceSelect::Flagged(nullptr, tmp_bytes, iota, c->d_open_flag.as<uint8_t>(), c->d_open_idx.as<int32_t>(), c->d_n_open.as<int>(), n, st));
+  CK(c->d_cub.ensure(tmp_bytes + 16));
+  CK(cub::DeviceSelect::Flagged(c->d_cub.p, tmp_bytes, iota, c->d_open_flag.as<uint8_t>(), c->d_open_idx.as<int32_t>(), c->d_n_open.as<int>(), n, st));
+  f->launches += 2;
+  int n_open = 0;
+  CK(cudaMemcpyAsync(&n_open, c->d_n_open.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (n_open == 0) return MMP_OK;
+  f->open_decisions += n_open;
+  // 4. the open decisions, from whole rows: all-gather every shard's block of their exclusion rows (the same ordered
+  // list on every rank), assemble, and run the same kernel on the assembled rows with the snapshot's whole rank range
+  const int ST = ds.view.excl_stride, NW = ds.view.row_words;
+  CK(c->d_blocks.ensure((size_t)n_open * ST * 4));
+  CK(c->d_gathered.ensure((size_t)G * n_open * ST * 4));
+  CK(c->d_rows.ensure((size_t)n_open * NW * 4));
+  CK(c->d_in_open.ensure((size_t)n_open * sizeof(mmp_decision_in)));
+  CK(c->d_out_open.ensure((size_t)n_open * sizeof(mmp_decision_out)));
+  const int pack_blocks = (int)std::min<size_t>(((size_t)n_open * ST + 255) / 256, (size_t)f->sm_count * 8);
+  k_shard_pack<<<std::max(pack_blocks, 1), 256, 0, st>>>(ds.view, d_in, c->d_open_idx.as<int32_t>(), n_open, c->d_blocks.as<uint32_t>(),
+                                                         c->d_in_open.as<mmp_decision_in>());
+  CK(cudaGetLastError());
+  NK(nc.AllGather(c->d_blocks.p, c->d_gathered.p, (size_t)n_open * ST, ncclUint32, f->comm, st));
+  const int asm_blocks = (int)std::min<size_t>(((size_t)n_open * NW + 255) / 256, (size_t)f->sm_count * 8);
+  k_shard_assemble<<<std::max(asm_blocks, 1), 256, 0, st>>>(c->d_gathered.as<uint32_t>(), n_open, ST, G, NW, c->d_rows.as<uint32_t>());
+  CK(cudaGetLastError());
+  f->launches += 2;
+  SnapshotView whole = ds.view;
+  whole.excl = c->d_rows.as<uint32_t>();
+  whole.excl_stride = NW; whole.word_lo = 0; whole.word_hi = NW;
+  PlaceArgs b{whole, c->d_in_open.as<mmp_decision_in>(), n_open, d_fresh, n_fresh, d_extra, c->d_out_open.as<mmp_decision_out>(),
+              nullptr, nullptr, now_ms, seed, 0, c->counter()};
+  b.orig_id = c->d_open_idx.as<int32_t>();
+  CK(launch_place(f, b, st));
+  k_shard_scatter<<<(n_open + 255) / 256, 256, 0, st>>>(c->d_out_open.as<mmp_decision_out>(), c->d_open_idx.as<int32_t>(), n_open, d_out);
+  f->launches++;
+  CK(cudaGetLastError());
+  return MMP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------------------------
 extern "C" {
+
+int32_t mmp_shard_unique_id(void *id128) {
+  if (!id128) { g_err = "null argument"; return MMP_E_ARG; }
+  NcclApi &nc = nccl_api();
+  if (!nc.ok) { g_err = "libnccl.so.2 not found (needed only for instance-sharded fleets)"; return MMP_E_NCCL; }
+  ncclUniqueId id;
+  NK(nc.GetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(id128, &id, sizeof(id));
+  return MMP_OK;
+}
+int32_t mmp_shard_connect(mmp_fleet *f, const void *id128) {
+  if (!f || !id128) { g_err = "null argument"; return MMP_E_ARG; }
+  if (f->hs.cfg.shard_count < 2) { g_err = "fleet is not instance-sharded (shard_count < 2)"; return MMP_E_STATE; }
+  NcclApi &nc = nccl_api();
+  if (!nc.ok) { g_err = "libnccl.so.2 not found"; return MMP_E_NCCL; }
+  CK(cudaSetDevice(f->device));
+  std::lock_guard<std::mutex> g(f->comm_mu);
+  if (f->comm) { nc.CommDestroy(f->comm); f->comm = nullptr; }
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  NK(nc.CommInitRank(&f->comm, f->hs.cfg.shard_count, id, f->hs.cfg.shard_rank));
+  return MMP_OK;
+}
+int32_t mmp_shard_words(mmp_fleet *f, int32_t *word_lo, int32_t *word_hi) {
+  if (!f) { g_err = "null fleet"; return MMP_E_ARG; }
+  int32_t lo, hi, st;
+  HostState::shard_words(f->hs.row_words(), f->hs.cfg.shard_rank, f->hs.cfg.shard_count, lo, hi, st);
+  if (word_lo) *word_lo = lo;
+  if (word_hi) *word_hi = hi;
+  return st;
+}
+int64_t mmp_shard_open_decisions(mmp_fleet *f) { return f ? f->open_decisions.load() : 0; }
 
 int32_t mmp_abi_version(void) { return MMP_ABI_VERSION; }
 const char *mmp_last_error(mmp_fleet *) { return g_err.c_str(); }
@@ -791,6 +1005,7 @@ void mmp_fleet_destroy(mmp_fleet *f) {
       fprintf(stderr, "\n");
     }
   }
+  if (f->comm && nccl_api().ok) { nccl_api().CommDestroy(f->comm); f->comm = nullptr; }
   for (auto &c : f->ctx_free) { destroy_ctx(c.get()); }
   f->ctx_free.clear();
   f->snaps[0].release(); f->snaps[1].release();
@@ -857,6 +1072,7 @@ int32_t mmp_fleet_commit(mmp_fleet *f) {
   CK(upload_vec(ds.lthreads_col, h.lthreads_col, st)); CK(upload_vec(ds.linprog_col, h.linprog_col, st));
   CK(upload_vec(ds.part_of_rank, h.part_of_rank, st));
   CK(upload_vec(ds.count_col, h.count_col, st));
+  CK(upload_vec(ds.cand_before, h.candx_before, st));
   // model rows (each snapshot keeps its own copy so in-flight readers of the other epoch are undisturbed)
   CK(ds.models.ensure((size_t)std::max(nm, 1) * sizeof(mmp_model_row)));
   if (nm) CK(cudaMemcpyAsync(ds.models.p, f->hs.models.data(), (size_t)nm * sizeof(mmp_model_row), cudaMemcpyHostToDevice, st));
@@ -887,7 +1103,7 @@ int32_t mmp_fleet_commit(mmp_fleet *f) {
   v.n_ranks = h.n_ranks; v.row_words = RW; v.n_models = nm; v.max_instances = f->hs.cfg.max_instances;
   v.any_rs = h.any_rs; v.n_type_ids = (int32_t)h.type_slot.size(); v.min_space = f->hs.cfg.min_space_units;
   v.word_lo = h.word_lo; v.word_hi = h.word_hi; v.excl_stride = ST; v.n_slots = h.n_slots;
-  v.count_col = ds.count_col.as<int32_t>();
+  v.count_col = ds.count_col.as<int32_t>(); v.cand_before = ds.cand_before.as<int32_t>();
   v.excl = ds.excl.as<uint32_t>(); v.cand = ds.cand.as<uint32_t>(); v.pref = ds.pref.as<uint32_t>();
   v.has_pref = ds.has_pref.as<uint8_t>(); v.type_slot = ds.type_slot.as<uint16_t>(); v.candx = ds.candx.as<uint32_t>();
   v.full = ds.full.as<uint32_t>(); v.rows = ds.rows.as<RankRow>(); v.rank_of = ds.rank_of.as<int32_t>();
@@ -925,6 +1141,22 @@ static int32_t place_impl(mmp_fleet *f, const mmp_decision_in *in, int32_t n, co
   const int RW = ds.view.row_words;
   cudaStream_t st = c->stream;
   const bool traced = trace || cand_mask;
+  if (f->hs.cfg.shard_count > 1) {  // instance-sharded: keys, one all-reduce(min), decode (+ row gather for open walks)
+    if (traced) { g_err = "traces are not available on an instance-sharded fleet"; return MMP_E_STATE; }
+    CK(c->d_in.ensure((size_t)n * sizeof(mmp_decision_in)));
+    CK(c->d_out.ensure((size_t)n * sizeof(mmp_decision_out)));
+    CK(c->d_fresh.ensure((size_t)std::max(n_fresh, 1) * sizeof(FreshRow)));
+    CK(c->d_extra.ensure((size_t)std::max(n_extra, 1) * 4));
+    if (n_fresh) CK(cudaMemcpyAsync(c->d_fresh.p, c->fresh_host.data(), (size_t)n_fresh * sizeof(FreshRow), cudaMemcpyHostToDevice, st));
+    if (n_extra) CK(cudaMemcpyAsync(c->d_extra.p, extra, (size_t)n_extra * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_in.p, in, (size_t)n * sizeof(mmp_decision_in), cudaMemcpyHostToDevice, st));
+    int32_t rcs = place_sharded(f, c, ds, c->d_in.as<mmp_decision_in>(), n, c->d_fresh.as<FreshRow>(), n_fresh, c->d_extra.as<int32_t>(),
+                                c->d_out.as<mmp_decision_out>(), now_ms, seed, st);
+    if (rcs < 0) return rcs;
+    CK(cudaMemcpyAsync(out, c->d_out.p, (size_t)n * sizeof(mmp_decision_out), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return MMP_OK;
+  }
   // ---- tiny batches: zero-copy through pinned mapped memory (one launch + one synchronise) ----
   {
     const size_t need = (size_t)n * (sizeof(mmp_decision_in) + sizeof(mmp_decision_out)) + (size_t)n_fresh * sizeof(FreshRow) + (size_t)n_extra * 4 + 64;
@@ -1017,7 +1249,11 @@ int32_t mmp_place_batch_device(mmp_fleet *f, const void *d_in, int32_t n, void *
   PlaceArgs a{ds.view, (const mmp_decision_in *)d_in, n, c->d_fresh.as<FreshRow>(), 0, c->d_extra.as<int32_t>(),
               (mmp_decision_out *)d_out, nullptr, nullptr, now_ms, seed, 0, c->counter()};
   CK(cudaEventRecord(c->e0, c->stream));
-  CK(launch_place(f, a, c->stream));
+  if (f->hs.cfg.shard_count > 1) {
+    int32_t rcs = place_sharded(f, c, ds, (const mmp_decision_in *)d_in, n, c->d_fresh.as<FreshRow>(), 0, c->d_extra.as<int32_t>(),
+                                (mmp_decision_out *)d_out, now_ms, seed, c->stream);
+    if (rcs < 0) return rcs;
+  } else CK(launch_place(f, a, c->stream));
   CK(cudaEventRecord(c->e1, c->stream));
   CK(cudaEventSynchronize(c->e1));
   if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, c->e0, c->e1));

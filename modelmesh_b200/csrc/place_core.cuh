@@ -78,6 +78,7 @@ struct SnapshotView {  // pointers into HBM (or host vectors in the CPU harness)
   const WordSumI *csum;        // [row_words]
   const WordSumL *lsum;        // [row_words]
   const int32_t *count_col;    // [row_words*32] count by rank, 0 past the last rank (exact evaluation of a mixed word)
+  const int32_t *cand_before;  // [n_slots] members of candx at ranks below word_lo*32 (instance-sharded; all 0 otherwise)
   const mmp_model_row *models; // [n_models]
 };
 
@@ -506,6 +507,7 @@ MMP_HD bool decide_fast(const SnapshotView &s, const DecisionCtx &c, const uint3
   W fw = co.wmap(w0, NW, [&](uint32_t wi) { return CX[wi] & ~erow[wi]; });
   const uint32_t b = co.wfirst(w0, fw);
   if (b == NONE_RANK) return false;  // deeper in the row, or empty (replicaset retry): general routine
+  o.first_rank = (int32_t)b;
   if ((b >> 5) >= C::WN / 2) {       // re-centre so that the window starts at best's word
     w0 = b >> 5;
     fw = co.wmap(w0, NW, [&](uint32_t wi) { return CX[wi] & ~erow[wi]; });
@@ -665,6 +667,14 @@ MMP_HD LaneTables lane_tables_global(const SnapshotView &s, int slot) {
   t.cx = (s.any_rs ? s.candx : s.cand) + so; t.p = s.pref + so; t.full = s.full; t.csum = s.csum; t.count_col = s.count_col;
   t.rows = s.rows;
   return t;
+}
+
+// Instance-sharded early-out: an entry of the filtered set in a LOWER shard beats anything this shard can offer
+// (min-loc under PLACEMENT_ORDER), and one must exist when the slot has more candidates below this shard's range than
+// the decision can exclude (the model's loaded ∪ failed row plus its extra excludes).  models[].reserved = row size.
+MMP_HD bool shard_cannot_win(const SnapshotView &s, const DecisionCtx &c, uint32_t n_row_bits) {
+  if (s.word_lo == 0 || c.slot < 0) return false;
+  return (int64_t)s.cand_before[ctx_slot(c)] > (int64_t)n_row_bits + (int64_t)(c.d.extra_n > 0 ? c.d.extra_n : 0);
 }
 
 // ---- vote shapes for decide_stream: 32 decisions in lockstep on the GPU, one on the CPU harness ----

@@ -132,6 +132,25 @@ class Fleet:
         self._ck(self.lib.mmp_place_one(self.h, _ptr(dec), _ptr(fresh_a), _ptr(extra_a), _ptr(out), now_ms, seed))
         return out[0]
 
+    # ---- instance-sharded multi-GPU ----
+    def shard_unique_id(self) -> bytes:
+        """Shard 0: the 128-byte NCCL id the host hands to its peers (any transport)."""
+        buf = C.create_string_buffer(128)
+        self._ck(self.lib.mmp_shard_unique_id(buf))
+        return buf.raw
+
+    def shard_connect(self, uid: bytes):
+        assert len(uid) == 128
+        self._ck(self.lib.mmp_shard_connect(self.h, C.c_char_p(uid)))
+
+    def shard_words(self):
+        lo, hi = C.c_int32(), C.c_int32()
+        stride = self._ck(self.lib.mmp_shard_words(self.h, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value, stride
+
+    def shard_open_decisions(self) -> int:
+        return int(self.lib.mmp_shard_open_decisions(self.h))
+
     # ---- introspection ----
     def row_words(self) -> int:
         return self._ck(self.lib.mmp_row_words(self.h))

@@ -36,3 +36,22 @@ def localize_decisions(dec: np.ndarray, lo: int, hi: int) -> np.ndarray:
     out = dec[sel].copy()
     out["model"] -= lo
     return out
+
+
+# ---- instance sharding: one 64-bit key per (decision, shard), combined by an unsigned minimum ----
+# layout (csrc/place_core.cuh shard_key): 63 filter-dropped | 62..46 first rank | 45 open | 44..27 target+3 | 26..9 n_candidates
+def combine_shard_keys(keys: np.ndarray) -> np.ndarray:
+    """keys: uint64[world, n] -> uint64[n], what ncclAllReduce(ncclMin, ncclUint64) leaves on every rank."""
+    return np.min(np.asarray(keys, dtype=np.uint64), axis=0)
+
+
+def decode_shard_keys(best: np.ndarray):
+    """-> (target int32[n], n_candidates int32[n], open bool[n]); open = needs the row-gather pass."""
+    best = np.asarray(best, dtype=np.uint64)
+    none = best == np.uint64(0xFFFFFFFFFFFFFFFF)
+    target = ((best >> np.uint64(27)) & np.uint64(0x3FFFF)).astype(np.int64) - 3
+    ncand = ((best >> np.uint64(9)) & np.uint64(0x3FFFF)).astype(np.int64)
+    is_open = (((best >> np.uint64(45)) & np.uint64(1)) != 0) & ~none
+    target = np.where(none, -1, target)
+    ncand = np.where(none | is_open, 0, ncand)
+    return target.astype(np.int32), ncand.astype(np.int32), is_open

@@ -107,7 +107,7 @@ static SnapshotView make_view(mmp_fleet *f) {
   v.n_ranks = s.n_ranks; v.row_words = s.row_words; v.n_models = (int32_t)f->models.size(); v.max_instances = f->hs.cfg.max_instances;
   v.any_rs = s.any_rs; v.n_type_ids = (int32_t)s.type_slot.size(); v.min_space = f->hs.cfg.min_space_units;
   v.word_lo = s.word_lo; v.word_hi = s.word_hi; v.excl_stride = s.excl_stride; v.n_slots = s.n_slots;
-  v.count_col = s.count_col.data();
+  v.count_col = s.count_col.data(); v.cand_before = s.candx_before.data();
   v.excl = f->excl.data(); v.cand = s.cand.data(); v.candx = s.candx.data(); v.pref = s.pref.data(); v.has_pref = s.has_pref.data();
   v.type_slot = s.type_slot_hp.data(); v.full = s.full.data(); v.rows = s.rows.data();
   v.rank_of = s.rank_of.data(); v.csum = s.csum.data(); v.lsum = s.lsum.data(); v.models = f->models.data();
@@ -135,6 +135,11 @@ int32_t mmp_place_batch_trace(mmp_fleet *f, const mmp_decision_in *in, int32_t n
     const uint32_t *erow = v.excl + (size_t)(cx.slot >= 0 ? in[i].model : 0) * v.excl_stride;
     const bool sharded = v.word_lo != 0 || v.word_hi != v.row_words;
     bool done = false;
+    if (sharded && !cand_mask && cx.slot >= 0 && shard_cannot_win(v, cx, f->models[in[i].model].reserved)) {
+      // a lower shard holds an entry: this shard publishes "none" without looking at its row (as k_place_lanes does)
+      o = DecideOut(); o.target = MMP_TARGET_NONE; o.first_rank = -1; o.best = -1; o.best_rank = -1; o.cut_rank = (int32_t)NONE_RANK;
+      done = true;
+    } else
     if (win == 2 && !cand_mask) {  // the lockstep lane routine of k_place_lanes (one decision per lane), general routine when it declines
       uint32_t self_eword = 0;
       if (cx.self_rank >= 0 && (cx.self_rank >> 5) >= v.word_lo && (cx.self_rank >> 5) < v.word_hi) self_eword = erow[(cx.self_rank >> 5) - v.word_lo];
