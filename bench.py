@@ -177,6 +177,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-instance-shards", action="store_true", help="N > 1: skip the instance-sharded leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", 0))
@@ -208,6 +209,7 @@ def main():
     solver = Fleet(fl.min_space_units, fl.min_churn_age_ms, fl.default_model_size_units, fl.n_instances, N_MODELS,
                    device=local_rank, lib=lib)
     load_into_fleet(fl, solver)
+    solver._ck(lib.mmp_fleet_set_id_base(solver.h, lo))  # this rank's slice of the sweep keeps the sweep's decision numbering
     dec = np.ascontiguousarray(sd_all.dec[lo:hi])
     row_words = solver.row_words()
 
@@ -277,6 +279,46 @@ def main():
                 ts.append(1e6 * (time.perf_counter() - t0))
         lat = {"p50_us": float(np.percentile(ts, 50)), "p99_us": float(np.percentile(ts, 99)), "n": len(ts)}
 
+    # ---- N > 1: the instance-sharded path of the north star, measured in the same run.  Every rank holds
+    # a column block of the bitmap for ALL models, resolves the whole batch over its rank range, and one
+    # ncclAllReduce(min) over 64-bit min-loc keys combines the shards (inside mmp_place_batch_device). ----
+    inst = None
+    if world > 1 and not args.no_instance_shards:
+        solver.close()  # free the registry shard's bitmap before building the column block
+        sh = Fleet(fl.min_space_units, fl.min_churn_age_ms, fl.default_model_size_units, fl.n_instances, N_MODELS,
+                   device=local_rank, shard_rank=rank, shard_count=world, lib=lib)
+        load_into_fleet(fl, sh)
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(sh.shard_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, src=0)
+        sh.shard_connect(bytes(uid.cpu().numpy().tobytes()))
+        dec_all = np.ascontiguousarray(sd_all.dec)
+        di, do = C.c_void_p(), C.c_void_p()
+        sh._ck(lib.mmp_device_alloc(sh.h, dec_all.nbytes, C.byref(di)))
+        sh._ck(lib.mmp_device_alloc(sh.h, N_MODELS * DECISION_OUT.itemsize, C.byref(do)))
+        sh._ck(lib.mmp_device_upload(sh.h, di, dec_all.ctypes.data_as(C.c_void_p), dec_all.nbytes))
+        for _ in range(args.warmup):
+            sh._ck(lib.mmp_place_batch_device(sh.h, di, N_MODELS, do, fl.now_ms, SEED, C.byref(kms)))
+        barrier()
+        ims = []
+        for _ in range(args.steps):
+            sh._ck(lib.mmp_place_batch_device(sh.h, di, N_MODELS, do, fl.now_ms, SEED, C.byref(kms)))
+            ims.append(float(kms.value))
+        barrier()
+        out_sh = np.zeros(N_MODELS, dtype=DECISION_OUT)
+        sh._ck(lib.mmp_device_download(sh.h, out_sh.ctypes.data_as(C.c_void_p), do, out_sh.nbytes))
+        # every shard must hold the registry-sharded answers for its own model range
+        agree = bool(np.array_equal(out_sh[lo:hi], out_dev))
+        t = torch.tensor([float(np.sum(ims)), 0.0 if agree else 1.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wlo, whi, wst = sh.shard_words()
+        inst = {"value": N_MODELS * args.steps / (float(t[0]) / 1000.0), "unit": "decisions/s", "ms_per_step": float(t[0]) / args.steps,
+                "scaling": "strong", "collective": "one ncclAllReduce(min, uint64) of %d min-loc keys per step (%.1f MB) + row-gather "
+                "pass for open walks" % (N_MODELS, N_MODELS * 8 / 1e6), "open_decisions_per_step": sh.shard_open_decisions() // (args.steps + args.warmup),
+                "rank0_row_words": [wlo, whi], "stored_row_bytes": wst * 4, "matches_registry_sharded": float(t[1]) == 0.0}
+        sh.close()
+
     # ---- max over ranks ----
     stats = torch.tensor([dev_ms, float(np.sum(e2e_ms)) if e2e_ms else 0.0], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -322,6 +364,8 @@ def main():
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "latency_b1": lat, "wall_s_timed_region": wall_s,
         }
+        if inst is not None:
+            line["instance_sharded"] = inst
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

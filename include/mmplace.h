@@ -195,6 +195,11 @@ int32_t mmp_shard_unique_id(void *id128);                       /* shard 0: nccl
 int32_t mmp_shard_connect(mmp_fleet *, const void *id128);      /* all shards: ncclCommInitRank(shard_count, id, shard_rank) */
 int32_t mmp_shard_words(mmp_fleet *, int32_t *word_lo, int32_t *word_hi); /* this shard's row words [lo, hi); returns the stored row stride */
 int64_t mmp_shard_open_decisions(mmp_fleet *);                  /* decisions that needed the row-gather pass so far */
+/* Registry (model) sharding needs no exchange: each process places the decisions of its own models against the whole
+ * instance table.  The only cross-shard convention is the numbering of decisions for the hash-indexed pick (N4, MM:4981):
+ * decision i of a batch hashes as id_base + i, so a shard that is handed the slice [lo, hi) of a larger batch sets
+ * id_base = lo and returns exactly what the unsharded run returns for that slice. */
+int32_t mmp_fleet_set_id_base(mmp_fleet *, uint64_t id_base);
 
 /* ---- snapshot introspection ---- */
 int32_t mmp_row_words(mmp_fleet *);                                   /* 32-bit words per exclusion-bitmap row */

@@ -102,6 +102,7 @@ SYMBOLS = [
     ("mmp_shard_connect", _I32, [_P, _P]),
     ("mmp_shard_words", _I32, [_P, C.POINTER(_I32), C.POINTER(_I32)]),
     ("mmp_shard_open_decisions", _I64, [_P]),
+    ("mmp_fleet_set_id_base", _I32, [_P, _U64]),
 ]
 
 

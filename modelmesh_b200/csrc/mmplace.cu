@@ -687,6 +687,7 @@ struct mmp_fleet {
   ncclComm_t comm = nullptr;    // instance-shard communicator (mmp_shard_connect)
   std::mutex comm_mu;           // collectives of one communicator are issued by one thread at a time
   std::atomic<int64_t> open_decisions{0};  // decisions that needed the row-gather pass so far
+  std::atomic<uint64_t> id_base{0};        // decision i of a batch hashes as id_base + i (mmp_fleet_set_id_base)
   std::mutex ctx_mu;
   std::vector<std::unique_ptr<PlaceCtx>> ctx_free;
   std::atomic<int64_t> launches{0};
@@ -867,7 +868,7 @@ static int32_t place_sharded(mmp_fleet *f, PlaceCtx *c, const DeviceSnapshot &ds
   std::lock_guard<std::mutex> g(f->comm_mu);
   const int G = f->hs.cfg.shard_count;
   // 1. per-shard keys (the scoring kernel)
-  PlaceArgs a{ds.view, d_in, n, d_fresh, n_fresh, d_extra, d_out, nullptr, nullptr, now_ms, seed, 0, c->counter()};
+  PlaceArgs a{ds.view, d_in, n, d_fresh, n_fresh, d_extra, d_out, nullptr, nullptr, now_ms, seed, f->id_base.load(), c->counter()};
   a.emit_keys = 1;
   CK(launch_place(f, a, st));
   // 2. min-loc combine over NVLink
@@ -911,7 +912,7 @@ static int32_t place_sharded(mmp_fleet *f, PlaceCtx *c, const DeviceSnapshot &ds
   whole.excl = c->d_rows.as<uint32_t>();
   whole.excl_stride = NW; whole.word_lo = 0; whole.word_hi = NW;
   PlaceArgs b{whole, c->d_in_open.as<mmp_decision_in>(), n_open, d_fresh, n_fresh, d_extra, c->d_out_open.as<mmp_decision_out>(),
-              nullptr, nullptr, now_ms, seed, 0, c->counter()};
+              nullptr, nullptr, now_ms, seed, f->id_base.load(), c->counter()};
   b.orig_id = c->d_open_idx.as<int32_t>();
   CK(launch_place(f, b, st));
   k_shard_scatter<<<(n_open + 255) / 256, 256, 0, st>>>(c->d_out_open.as<mmp_decision_out>(), c->d_open_idx.as<int32_t>(), n_open, d_out);
@@ -957,6 +958,11 @@ int32_t mmp_shard_words(mmp_fleet *f, int32_t *word_lo, int32_t *word_hi) {
   return st;
 }
 int64_t mmp_shard_open_decisions(mmp_fleet *f) { return f ? f->open_decisions.load() : 0; }
+int32_t mmp_fleet_set_id_base(mmp_fleet *f, uint64_t id_base) {
+  if (!f) { g_err = "null fleet"; return MMP_E_ARG; }
+  f->id_base = id_base;
+  return MMP_OK;
+}
 
 int32_t mmp_abi_version(void) { return MMP_ABI_VERSION; }
 const char *mmp_last_error(mmp_fleet *) { return g_err.c_str(); }
@@ -1169,7 +1175,7 @@ static int32_t place_impl(mmp_fleet *f, const mmp_decision_in *in, int32_t n, co
       if (n_fresh) memcpy(h + o_fr, c->fresh_host.data(), (size_t)n_fresh * sizeof(FreshRow));
       if (n_extra) memcpy(h + o_ex, extra, (size_t)n_extra * 4);
       PlaceArgs a{ds.view, (const mmp_decision_in *)(dbase + o_in), n, (const FreshRow *)(dbase + o_fr), n_fresh,
-                  (const int32_t *)(dbase + o_ex), (mmp_decision_out *)(dbase + o_out), nullptr, nullptr, now_ms, seed, 0, c->counter()};
+                  (const int32_t *)(dbase + o_ex), (mmp_decision_out *)(dbase + o_out), nullptr, nullptr, now_ms, seed, f->id_base.load(), c->counter()};
       CK(launch_place(f, a, st));
       CK(cudaStreamSynchronize(st));
       memcpy(out, h + o_out, (size_t)n * sizeof(mmp_decision_out));
@@ -1196,7 +1202,7 @@ static int32_t place_impl(mmp_fleet *f, const mmp_decision_in *in, int32_t n, co
       cudaStream_t ps = c->pipe[ci % PlaceCtx::NPIPE];
       CK(cudaMemcpyAsync(c->d_in.as<mmp_decision_in>() + lo, in + lo, (size_t)cnt * sizeof(mmp_decision_in), cudaMemcpyHostToDevice, ps));
       PlaceArgs a{ds.view, c->d_in.as<mmp_decision_in>() + lo, cnt, c->d_fresh.as<FreshRow>(), n_fresh, c->d_extra.as<int32_t>(),
-                  c->d_out.as<mmp_decision_out>() + lo, nullptr, nullptr, now_ms, seed, (uint64_t)lo, c->counter()};
+                  c->d_out.as<mmp_decision_out>() + lo, nullptr, nullptr, now_ms, seed, f->id_base.load() + (uint64_t)lo, c->counter()};
       CK(launch_place(f, a, ps));
       CK(cudaMemcpyAsync(out + lo, c->d_out.as<mmp_decision_out>() + lo, (size_t)cnt * sizeof(mmp_decision_out), cudaMemcpyDeviceToHost, ps));
     }
@@ -1207,7 +1213,7 @@ static int32_t place_impl(mmp_fleet *f, const mmp_decision_in *in, int32_t n, co
   if (cand_mask) CK(cudaMemsetAsync(c->d_cand.p, 0, (size_t)n * 2 * RW * 4, st));
   PlaceArgs a{ds.view, c->d_in.as<mmp_decision_in>(), n, c->d_fresh.as<FreshRow>(), n_fresh, c->d_extra.as<int32_t>(),
               c->d_out.as<mmp_decision_out>(), trace ? c->d_trace.as<mmp_decision_trace>() : nullptr,
-              cand_mask ? c->d_cand.as<uint32_t>() : nullptr, now_ms, seed, 0, c->counter()};
+              cand_mask ? c->d_cand.as<uint32_t>() : nullptr, now_ms, seed, f->id_base.load(), c->counter()};
   CK(launch_place(f, a, st));
   CK(cudaMemcpyAsync(out, c->d_out.p, (size_t)n * sizeof(mmp_decision_out), cudaMemcpyDeviceToHost, st));
   if (trace) CK(cudaMemcpyAsync(trace, c->d_trace.p, (size_t)n * sizeof(mmp_decision_trace), cudaMemcpyDeviceToHost, st));
@@ -1247,7 +1253,7 @@ int32_t mmp_place_batch_device(mmp_fleet *f, const void *d_in, int32_t n, void *
   CK(c->d_fresh.ensure(sizeof(FreshRow)));
   CK(c->d_extra.ensure(4));
   PlaceArgs a{ds.view, (const mmp_decision_in *)d_in, n, c->d_fresh.as<FreshRow>(), 0, c->d_extra.as<int32_t>(),
-              (mmp_decision_out *)d_out, nullptr, nullptr, now_ms, seed, 0, c->counter()};
+              (mmp_decision_out *)d_out, nullptr, nullptr, now_ms, seed, f->id_base.load(), c->counter()};
   CK(cudaEventRecord(c->e0, c->stream));
   if (f->hs.cfg.shard_count > 1) {
     int32_t rcs = place_sharded(f, c, ds, (const mmp_decision_in *)d_in, n, c->d_fresh.as<FreshRow>(), 0, c->d_extra.as<int32_t>(),
