@@ -104,6 +104,19 @@ def measured_hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def captured_traffic(batch: int):
+    """dram__bytes_read + dram__bytes_write of one k_place_lanes launch from the committed `ncu --set full` capture
+    (profiles/r01_ncu_k_place_lanes.json, written by tools/ncu_summary.py), if it was taken on this batch size."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_k_place_lanes.json")) as f:
+            d = json.load(f)
+        if int(d.get("n_decisions") or 0) == int(batch):
+            return float(d["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
 def build_oracle(fl):
     """CPU baseline / checker only."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -337,7 +350,8 @@ def main():
         k_avg_s = float(np.mean(kernel_ms)) / 1000.0
         achieved = alg_bytes / k_avg_s / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "kernel": "k_place",
+                    "traffic": captured_traffic(B), "peak_source": peak_src, "kernel": "k_place_lanes",
+                    "traffic_source": "profiles/r01_ncu_k_place_lanes.txt (ncu --set full, same command, one launch)",
                     "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms_avg": 1000.0 * k_avg_s}
         cpu = None
         if not args.no_cpu:

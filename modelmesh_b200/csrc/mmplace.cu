@@ -700,7 +700,7 @@ struct mmp_fleet {
                                 // slower (3.8 vs 4.2 G/s): the copy pushes shared memory past the 196 KB carve-out step
   int lane_mode = 0;            // MMP_LANE_MODE=1: stream-only probe (rows staged, no decisions) -- measurement aid, results void
   int lanes = 1;                // MMP_KERNEL=tile selects the cooperative-tile kernel (k_place) instead of k_place_lanes
-  int lane_warps = 12;          // warps per block of k_place_lanes (MMP_LANE_WARPS = 8 | 12 | 16 | 20); 12 measured best at 10k instances
+  int lane_warps = 0;           // warps per block of k_place_lanes (MMP_LANE_WARPS = 8 | 10 | 12 | 14 | 16 | 20); 0 = by launch size
   // LRU store (plug point 3)
   DevBuf lru_ts, lru_seq, lru_weight, lru_model, lru_cap, lru_wsize, lru_count, lru_seqctr;
   int32_t lru_n = 0, lru_slots = 0;
@@ -831,12 +831,27 @@ static cudaError_t launch_place(mmp_fleet *f, const PlaceArgs &a, cudaStream_t s
   // production path: one decision per lane (rows up to 2 KiB + pad: at least three 32-row stages per SM)
   if (!(a.tr || a.cand) && f->lanes && a.batch_counter) {
     int ns = 0;
-    if (f->lane_warps == 8 && lanes_geometry(a.s.excl_stride, 8, f->lane_front != 0, ns)) return launch_place_lanes<8>(f, a, st, ns);
-    if (f->lane_warps == 10 && lanes_geometry(a.s.excl_stride, 10, f->lane_front != 0, ns)) return launch_place_lanes<10>(f, a, st, ns);
-    if (f->lane_warps == 14 && lanes_geometry(a.s.excl_stride, 14, f->lane_front != 0, ns)) return launch_place_lanes<14>(f, a, st, ns);
-    if (f->lane_warps == 12 && lanes_geometry(a.s.excl_stride, 12, f->lane_front != 0, ns)) return launch_place_lanes<12>(f, a, st, ns);
-    if (f->lane_warps == 20 && lanes_geometry(a.s.excl_stride, 20, f->lane_front != 0, ns)) return launch_place_lanes<20>(f, a, st, ns);
-    if (f->lane_warps == 16 && lanes_geometry(a.s.excl_stride, 16, f->lane_front != 0, ns)) return launch_place_lanes<16>(f, a, st, ns);
+    // warps per block.  Large launches are HBM-bound and 12 warps per SM measured best; a small launch (a registry shard
+    // of a strong-scaled batch, a micro-batch) is bound by how many rounds of 32-decision steps its warps need, so it
+    // takes the width with the fewest rounds.
+    int lw = f->lane_warps;
+    if (lw == 0) {
+      lw = 12;
+      const int nb = (a.n + 31) / 32;
+      if (nb <= 4 * f->sm_count * 16) {
+        int best_rounds = (nb + f->sm_count * 12 - 1) / (f->sm_count * 12);
+        for (int w : {14, 16}) {
+          const int r = (nb + f->sm_count * w - 1) / (f->sm_count * w);
+          if (r < best_rounds) { best_rounds = r; lw = w; }
+        }
+      }
+    }
+    if (lw == 8 && lanes_geometry(a.s.excl_stride, 8, f->lane_front != 0, ns)) return launch_place_lanes<8>(f, a, st, ns);
+    if (lw == 10 && lanes_geometry(a.s.excl_stride, 10, f->lane_front != 0, ns)) return launch_place_lanes<10>(f, a, st, ns);
+    if (lw == 14 && lanes_geometry(a.s.excl_stride, 14, f->lane_front != 0, ns)) return launch_place_lanes<14>(f, a, st, ns);
+    if (lw == 12 && lanes_geometry(a.s.excl_stride, 12, f->lane_front != 0, ns)) return launch_place_lanes<12>(f, a, st, ns);
+    if (lw == 20 && lanes_geometry(a.s.excl_stride, 20, f->lane_front != 0, ns)) return launch_place_lanes<20>(f, a, st, ns);
+    if (lw == 16 && lanes_geometry(a.s.excl_stride, 16, f->lane_front != 0, ns)) return launch_place_lanes<16>(f, a, st, ns);
     if (lanes_geometry(a.s.excl_stride, 12, f->lane_front != 0, ns)) return launch_place_lanes<12>(f, a, st, ns);
   }
   // tile width: how many lanes (= window words) resolve one decision; 32/T decisions advance per warp step.
