@@ -831,21 +831,9 @@ static cudaError_t launch_place(mmp_fleet *f, const PlaceArgs &a, cudaStream_t s
   // production path: one decision per lane (rows up to 2 KiB + pad: at least three 32-row stages per SM)
   if (!(a.tr || a.cand) && f->lanes && a.batch_counter) {
     int ns = 0;
-    // warps per block.  Large launches are HBM-bound and 12 warps per SM measured best; a small launch (a registry shard
-    // of a strong-scaled batch, a micro-batch) is bound by how many rounds of 32-decision steps its warps need, so it
-    // takes the width with the fewest rounds.
-    int lw = f->lane_warps;
-    if (lw == 0) {
-      lw = 12;
-      const int nb = (a.n + 31) / 32;
-      if (nb <= 4 * f->sm_count * 16) {
-        int best_rounds = (nb + f->sm_count * 12 - 1) / (f->sm_count * 12);
-        for (int w : {14, 16}) {
-          const int r = (nb + f->sm_count * w - 1) / (f->sm_count * w);
-          if (r < best_rounds) { best_rounds = r; lw = w; }
-        }
-      }
-    }
+    // warps per block: 12 per SM measured best at 10k instances (8: 3.7-3.8, 12: 4.1-4.3, 16: 3.6-3.9 G decisions/s); picking
+    // the width with the fewest rounds of steps for small launches was measured too and made no difference
+    const int lw = f->lane_warps ? f->lane_warps : 12;
     if (lw == 8 && lanes_geometry(a.s.excl_stride, 8, f->lane_front != 0, ns)) return launch_place_lanes<8>(f, a, st, ns);
     if (lw == 10 && lanes_geometry(a.s.excl_stride, 10, f->lane_front != 0, ns)) return launch_place_lanes<10>(f, a, st, ns);
     if (lw == 14 && lanes_geometry(a.s.excl_stride, 14, f->lane_front != 0, ns)) return launch_place_lanes<14>(f, a, st, ns);
