@@ -300,10 +300,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_place(const SnapshotView s
 // One persistent block per SM.  Shared memory holds NS "landing stages" of 32 exclusion rows each (TMA bulk-copy
 // destinations, one mbarrier per stage) that the block's warps share, and a small private window buffer per warp.
 // A warp's step over a batch of 32 decisions:
-//   1. claim the batch (atomic counter) and read its 32 decision records (prefetched one step ahead);
-//   2. acquire a free landing stage; every lane issues the cp.async.bulk of its model's bitmap row into it
+//   1. batches are dealt round-robin to the grid's warps; the batch's 32 decision records were requested a step ahead;
+//   2. take a landing stage (FIFO tickets); every lane issues the cp.async.bulk of its model's bitmap row into it
 //      (32 arrivals + 32 x row bytes of transaction count on the stage's mbarrier);
-//   3. gather the decision context (model row, rank_of[self], the caller's row, type slot) while the rows stream in;
+//   3. finish the decision context (type slot, the caller's row, self's mask bits) while the rows stream in; its
+//      first gathers (model row from HBM, rank_of[self]) were issued a step ahead -- a warp stalls in order;
 //   4. when the stage has landed, copy the first WIN words of its row and the word holding self's bit out of the stage
 //      and RELEASE the stage, so the next 41 KB of rows is in flight while this warp is still computing;
 //   5. resolve the 32 decisions in lockstep from the window buffer (mmp::decide_stream) and write the 8-byte results.
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_place(const SnapshotView s
 // decision; what it cannot (long walks on adversarial fleets, uncommon paths) is redone by the whole warp with the
 // cooperative general routine reading the row from global memory (it was just streamed: L2).
 // The stages keep ~NS x 41 KB per SM in flight from HBM independently of how many warps are computing, and the
-// per-decision instruction cost is ~70 warp instructions / 32 lanes instead of ~450 for a cooperative tile.
+// per-decision instruction cost is ~85 warp instructions instead of ~450 for a cooperative tile (ncu, C3 sweep).
 // ---------------------------------------------------------------------------------------------------------------
 static constexpr int LANE_WIN = 14;     // row words copied out of the landing stage per decision (448 ranks)
 static constexpr int LANE_BUDGET = 64;  // row-word visits a lane may spend before handing its decision to the warp
@@ -661,11 +662,8 @@ struct PlaceCtx {
   static constexpr int NPIPE = 3;
   cudaStream_t pipe[NPIPE] = {nullptr, nullptr, nullptr};  // H2D / kernel / D2H of consecutive chunks overlap across these
   cudaEvent_t e0 = nullptr, e1 = nullptr, ready = nullptr;
-  DevBuf d_in, d_out, d_fresh, d_extra, d_trace, d_cand, d_counters;
+  DevBuf d_in, d_out, d_fresh, d_extra, d_trace, d_cand;
   DevBuf d_open_flag, d_open_idx, d_n_open, d_cub, d_blocks, d_gathered, d_rows, d_in_open, d_out_open;  // instance-shard combine
-  static constexpr int NCOUNTERS = 64;  // batch counters of k_place_lanes, one per launch in flight on this context
-  int next_counter = 0;
-  int *counter() { return d_counters.as<int>() + (next_counter++ % NCOUNTERS); }
   std::vector<FreshRow> fresh_host;
   // pinned, device-mapped scratch for tiny batches: the kernel reads the decisions and writes the results straight
   // through PCIe, so a B = 1 call is one launch + one synchronise (no copy calls)
@@ -735,7 +733,6 @@ static PlaceCtx *acquire_ctx(mmp_fleet *f) {
             cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming) == cudaSuccess &&
             cudaHostAlloc((void **)&c->mapped, PlaceCtx::MAPPED_BYTES, cudaHostAllocMapped) == cudaSuccess;
   for (int i = 0; ok && i < PlaceCtx::NPIPE; i++) ok = cudaStreamCreateWithFlags(&c->pipe[i], cudaStreamNonBlocking) == cudaSuccess;
-  ok = ok && c->d_counters.ensure(PlaceCtx::NCOUNTERS * sizeof(int)) == cudaSuccess;
   if (!ok) { delete c; return nullptr; }
   return c;
 }
@@ -744,7 +741,7 @@ static void release_ctx(mmp_fleet *f, PlaceCtx *c) {
   f->ctx_free.emplace_back(c);
 }
 static void destroy_ctx(PlaceCtx *c) {
-  for (DevBuf *b : {&c->d_in, &c->d_out, &c->d_fresh, &c->d_extra, &c->d_trace, &c->d_cand, &c->d_counters, &c->d_open_flag,
+  for (DevBuf *b : {&c->d_in, &c->d_out, &c->d_fresh, &c->d_extra, &c->d_trace, &c->d_cand, &c->d_open_flag,
                     &c->d_open_idx, &c->d_n_open, &c->d_cub, &c->d_blocks, &c->d_gathered, &c->d_rows, &c->d_in_open, &c->d_out_open})
     b->release();
   if (c->e0) cudaEventDestroy(c->e0);
@@ -770,7 +767,6 @@ struct PlaceArgs {
   uint32_t *cand;
   int64_t now;
   uint64_t seed, id_base;
-  int *batch_counter;  // (unused since batches are dealt statically; kept so every launch site names its context)
   int emit_keys = 0;            // instance-sharded: write shard keys (uint64) into `out` instead of results
   const int32_t *orig_id = nullptr;  // gather pass: decision i reads row i of s.excl and hashes with id orig_id[i]
 };
@@ -829,7 +825,7 @@ static cudaError_t launch_place_lanes(mmp_fleet *f, const PlaceArgs &a, cudaStre
 static cudaError_t launch_place(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st) {
   const int rw = a.s.row_words;
   // production path: one decision per lane (rows up to 2 KiB + pad: at least three 32-row stages per SM)
-  if (!(a.tr || a.cand) && f->lanes && a.batch_counter) {
+  if (!(a.tr || a.cand) && f->lanes) {
     int ns = 0;
     // warps per block: 12 per SM measured best at 10k instances (8: 3.7-3.8, 12: 4.1-4.3, 16: 3.6-3.9 G decisions/s); picking
     // the width with the fewest rounds of steps for small launches was measured too and made no difference
@@ -871,7 +867,7 @@ static int32_t place_sharded(mmp_fleet *f, PlaceCtx *c, const DeviceSnapshot &ds
   std::lock_guard<std::mutex> g(f->comm_mu);
   const int G = f->hs.cfg.shard_count;
   // 1. per-shard keys (the scoring kernel)
-  PlaceArgs a{ds.view, d_in, n, d_fresh, n_fresh, d_extra, d_out, nullptr, nullptr, now_ms, seed, f->id_base.load(), c->counter()};
+  PlaceArgs a{ds.view, d_in, n, d_fresh, n_fresh, d_extra, d_out, nullptr, nullptr, now_ms, seed, f->id_base.load()};
   a.emit_keys = 1;
   CK(launch_place(f, a, st));
   // 2. min-loc combine over NVLink
@@ -915,7 +911,7 @@ static int32_t place_sharded(mmp_fleet *f, PlaceCtx *c, const DeviceSnapshot &ds
   whole.excl = c->d_rows.as<uint32_t>();
   whole.excl_stride = NW; whole.word_lo = 0; whole.word_hi = NW;
   PlaceArgs b{whole, c->d_in_open.as<mmp_decision_in>(), n_open, d_fresh, n_fresh, d_extra, c->d_out_open.as<mmp_decision_out>(),
-              nullptr, nullptr, now_ms, seed, f->id_base.load(), c->counter()};
+              nullptr, nullptr, now_ms, seed, f->id_base.load()};
   b.orig_id = c->d_open_idx.as<int32_t>();
   CK(launch_place(f, b, st));
   k_shard_scatter<<<(n_open + 255) / 256, 256, 0, st>>>(c->d_out_open.as<mmp_decision_out>(), c->d_open_idx.as<int32_t>(), n_open, d_out);
@@ -1178,7 +1174,7 @@ static int32_t place_impl(mmp_fleet *f, const mmp_decision_in *in, int32_t n, co
       if (n_fresh) memcpy(h + o_fr, c->fresh_host.data(), (size_t)n_fresh * sizeof(FreshRow));
       if (n_extra) memcpy(h + o_ex, extra, (size_t)n_extra * 4);
       PlaceArgs a{ds.view, (const mmp_decision_in *)(dbase + o_in), n, (const FreshRow *)(dbase + o_fr), n_fresh,
-                  (const int32_t *)(dbase + o_ex), (mmp_decision_out *)(dbase + o_out), nullptr, nullptr, now_ms, seed, f->id_base.load(), c->counter()};
+                  (const int32_t *)(dbase + o_ex), (mmp_decision_out *)(dbase + o_out), nullptr, nullptr, now_ms, seed, f->id_base.load()};
       CK(launch_place(f, a, st));
       CK(cudaStreamSynchronize(st));
       memcpy(out, h + o_out, (size_t)n * sizeof(mmp_decision_out));
@@ -1205,7 +1201,7 @@ static int32_t place_impl(mmp_fleet *f, const mmp_decision_in *in, int32_t n, co
       cudaStream_t ps = c->pipe[ci % PlaceCtx::NPIPE];
       CK(cudaMemcpyAsync(c->d_in.as<mmp_decision_in>() + lo, in + lo, (size_t)cnt * sizeof(mmp_decision_in), cudaMemcpyHostToDevice, ps));
       PlaceArgs a{ds.view, c->d_in.as<mmp_decision_in>() + lo, cnt, c->d_fresh.as<FreshRow>(), n_fresh, c->d_extra.as<int32_t>(),
-                  c->d_out.as<mmp_decision_out>() + lo, nullptr, nullptr, now_ms, seed, f->id_base.load() + (uint64_t)lo, c->counter()};
+                  c->d_out.as<mmp_decision_out>() + lo, nullptr, nullptr, now_ms, seed, f->id_base.load() + (uint64_t)lo};
       CK(launch_place(f, a, ps));
       CK(cudaMemcpyAsync(out + lo, c->d_out.as<mmp_decision_out>() + lo, (size_t)cnt * sizeof(mmp_decision_out), cudaMemcpyDeviceToHost, ps));
     }
@@ -1216,7 +1212,7 @@ static int32_t place_impl(mmp_fleet *f, const mmp_decision_in *in, int32_t n, co
   if (cand_mask) CK(cudaMemsetAsync(c->d_cand.p, 0, (size_t)n * 2 * RW * 4, st));
   PlaceArgs a{ds.view, c->d_in.as<mmp_decision_in>(), n, c->d_fresh.as<FreshRow>(), n_fresh, c->d_extra.as<int32_t>(),
               c->d_out.as<mmp_decision_out>(), trace ? c->d_trace.as<mmp_decision_trace>() : nullptr,
-              cand_mask ? c->d_cand.as<uint32_t>() : nullptr, now_ms, seed, f->id_base.load(), c->counter()};
+              cand_mask ? c->d_cand.as<uint32_t>() : nullptr, now_ms, seed, f->id_base.load()};
   CK(launch_place(f, a, st));
   CK(cudaMemcpyAsync(out, c->d_out.p, (size_t)n * sizeof(mmp_decision_out), cudaMemcpyDeviceToHost, st));
   if (trace) CK(cudaMemcpyAsync(trace, c->d_trace.p, (size_t)n * sizeof(mmp_decision_trace), cudaMemcpyDeviceToHost, st));
@@ -1256,7 +1252,7 @@ int32_t mmp_place_batch_device(mmp_fleet *f, const void *d_in, int32_t n, void *
   CK(c->d_fresh.ensure(sizeof(FreshRow)));
   CK(c->d_extra.ensure(4));
   PlaceArgs a{ds.view, (const mmp_decision_in *)d_in, n, c->d_fresh.as<FreshRow>(), 0, c->d_extra.as<int32_t>(),
-              (mmp_decision_out *)d_out, nullptr, nullptr, now_ms, seed, f->id_base.load(), c->counter()};
+              (mmp_decision_out *)d_out, nullptr, nullptr, now_ms, seed, f->id_base.load()};
   CK(cudaEventRecord(c->e0, c->stream));
   if (f->hs.cfg.shard_count > 1) {
     int32_t rcs = place_sharded(f, c, ds, (const mmp_decision_in *)d_in, n, c->d_fresh.as<FreshRow>(), 0, c->d_extra.as<int32_t>(),

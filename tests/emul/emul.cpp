@@ -23,6 +23,7 @@ struct mmp_fleet {
   std::vector<mmp_model_row> models;
   int32_t epoch = 0;
   int64_t launches = 0;
+  uint64_t id_base = 0;      // mmp_fleet_set_id_base
   uint64_t *keys = nullptr;  // harness-only: per-decision instance-shard keys of the next batch (mmp_emul_set_keys)
 };
 static thread_local std::string g_err;
@@ -143,22 +144,22 @@ int32_t mmp_place_batch_trace(mmp_fleet *f, const mmp_decision_in *in, int32_t n
     if (win == 2 && !cand_mask) {  // the lockstep lane routine of k_place_lanes (one decision per lane), general routine when it declines
       uint32_t self_eword = 0;
       if (cx.self_rank >= 0 && (cx.self_rank >> 5) >= v.word_lo && (cx.self_rank >> 5) < v.word_hi) self_eword = erow[(cx.self_rank >> 5) - v.word_lo];
-      done = decide_stream(v, lane_tables_global(v, cx.slot >= 0 ? ctx_slot(cx) : 0), cx, true, erow, (uint32_t)g_lane_window, self_eword, now_ms, seed, (uint64_t)i, SoloVote(), o, g_lane_budget);
+      done = decide_stream(v, lane_tables_global(v, cx.slot >= 0 ? ctx_slot(cx) : 0), cx, true, erow, (uint32_t)g_lane_window, self_eword, now_ms, seed, f->id_base + (uint64_t)i, SoloVote(), o, g_lane_budget);
       g_lane_decisions++;
       if (!done) g_bails++;
     } else if (sharded) {
       // instance-sharded harness: only the general routine knows about rank ranges (decide_fast assumes whole rows)
     } else if (win == 1 && !cand_mask) {  // the lane-per-decision shape of k_place_lanes: budgeted walk, cooperative redo when it bails
       CoopLane cl(g_lane_budget);
-      decide_ctx<CoopLane>(v, cx, erow, extra, now_ms, seed, (uint64_t)i, cl, o, nullptr);
+      decide_ctx<CoopLane>(v, cx, erow, extra, now_ms, seed, f->id_base + (uint64_t)i, cl, o, nullptr);
       g_lane_decisions++;
       done = !(o.flags & MMP_TF_BAIL);
       if (!done) g_bails++;
-    } else if (!cand_mask) done = win == 16 ? decide_fast<true>(v, cx, erow, now_ms, seed, (uint64_t)i, co16, o)
-                         : win == 8 ? decide_fast<true>(v, cx, erow, now_ms, seed, (uint64_t)i, co8, o)
-                                    : decide_fast<true>(v, cx, erow, now_ms, seed, (uint64_t)i, co, o);
+    } else if (!cand_mask) done = win == 16 ? decide_fast<true>(v, cx, erow, now_ms, seed, f->id_base + (uint64_t)i, co16, o)
+                         : win == 8 ? decide_fast<true>(v, cx, erow, now_ms, seed, f->id_base + (uint64_t)i, co8, o)
+                                    : decide_fast<true>(v, cx, erow, now_ms, seed, f->id_base + (uint64_t)i, co, o);
     if (!done)
-      decide_ctx<Coop1>(v, cx, erow, extra, now_ms, seed, (uint64_t)i, co, o,
+      decide_ctx<Coop1>(v, cx, erow, extra, now_ms, seed, f->id_base + (uint64_t)i, co, o,
                         cand_mask ? cand_mask + (size_t)i * 2 * v.row_words : nullptr);
     out[i].target = o.target; out[i].n_candidates = o.n_candidates;
     if (f->keys) f->keys[i] = shard_key(o, f->hs.cfg.shard_rank);
@@ -201,5 +202,6 @@ int32_t mmp_instance_partition(mmp_fleet *f, int32_t idx) {
   return f->snap.part_of_rank[f->snap.rank_of[idx]];
 }
 int64_t mmp_kernel_launches(mmp_fleet *f) { return f->launches; }
+int32_t mmp_fleet_set_id_base(mmp_fleet *f, uint64_t b) { f->id_base = b; return MMP_OK; }
 
 }  // extern "C"

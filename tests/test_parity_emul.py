@@ -103,3 +103,25 @@ def test_stream_routine_mixed_regimes(emul_lib, oracle_lib, seed):
     finally:
         emul_lib.mmp_emul_set_window(32)
         emul_lib.mmp_emul_set_lane_budget(48)
+
+
+def test_slices_with_id_base_equal_the_batch(emul_lib, oracle_lib):
+    """A registry shard places a slice of a larger batch: with mmp_fleet_set_id_base(lo) the hash-indexed pick (N4) of
+    decision lo + i is the one the whole batch gives it."""
+    fl = make_fleet("C3", 3000, 700, 3)
+    s = solver_from_synth(fl, emul_lib)
+    for shape in (32, 2):
+        emul_lib.mmp_emul_set_window(shape)
+        try:
+            sd = make_decisions(fl, 3000, 4, sweep=True, plain=True)
+            whole = s.place_batch(sd.dec, fl.now_ms, 5)
+            parts = []
+            cuts = [0, 1, 33, 1000, 3000]
+            for lo, hi in zip(cuts[:-1], cuts[1:]):
+                s._ck(emul_lib.mmp_fleet_set_id_base(s.h, lo))
+                parts.append(s.place_batch(sd.dec[lo:hi], fl.now_ms, 5))
+            s._ck(emul_lib.mmp_fleet_set_id_base(s.h, 0))
+            assert np.array_equal(np.concatenate(parts), whole)
+            assert len(np.unique(whole["target"])) > 3
+        finally:
+            emul_lib.mmp_emul_set_window(32)

@@ -53,3 +53,71 @@ def test_kernel_variants_match_oracle(product_lib, oracle_lib, monkeypatch, kern
     compare_decisions(fl, sd, o, s, seed=seed * 17, full_lists=False)
     sd = make_decisions(fl, 2500, seed + 1, sweep=True, plain=True)
     compare_decisions(fl, sd, o, s, seed=seed, full_lists=False)
+
+
+def _oracle_results(fl, sd, oracle, seed, ids=None):
+    from helpers import oracle_inputs_fast
+    od, off, idx = oracle_inputs_fast(fl, sd)
+    if ids is not None:
+        od["decision_id"] = ids
+    return oracle.get_next_batch(od, fl.type_names, off, idx, fl.now_ms, seed, fresh=sd.fresh if len(sd.fresh) else None)
+
+
+@pytest.mark.parametrize("config,nm,ni,seed", [("C2", 100_000, 1_000, 2), ("C5", 100_000, 10_000, 5), ("C3", 150_000, 10_000, 3)])
+def test_baseline_sized_fleets_match_oracle(product_lib, oracle_lib, config, nm, ni, seed):
+    """BASELINE.json configurations at (C2) or near (C3/C5: 10k instances, a 100-150k slice of the registry) their full
+    size: every decision of a registry sweep and of a mixed batch equals the oracle's (target, n_candidates).
+    C5 is the adversarial fleet: 70 % of its walks leave the lane routine's window and are redone cooperatively."""
+    fl = make_fleet(config, nm, ni, seed)
+    o = oracle_from_synth(fl)
+    s = solver_from_synth(fl, product_lib)
+    for plain in (True, False):
+        sd = make_decisions(fl, min(nm, 100_000), seed, sweep=plain, plain=plain)
+        want = _oracle_results(fl, sd, o, seed)
+        got = s.place_batch(sd.dec, fl.now_ms, seed, fresh=sd.fresh if len(sd.fresh) else None, extra=sd.extra if len(sd.extra) else None)
+        bad = np.nonzero((got["target"] != want["target"]) | (got["n_candidates"] != want["n_candidates"]))[0]
+        assert len(bad) == 0, (config, plain, len(bad), bad[:5], got[bad[:5]], want[bad[:5]])
+
+
+def test_batch_properties(product_lib, oracle_lib):
+    """Size-independent properties of the batched entry points on a 10k-instance fleet: a batch is idempotent; a batch
+    equals its slices placed separately with mmp_fleet_set_id_base (what a registry shard does); the device-resident
+    entry point equals the host one; a one-decision call equals the batch's entry."""
+    import ctypes as C
+    from modelmesh_b200._lib import DECISION_OUT
+    fl = make_fleet("C3", 60_000, 10_000, 3)
+    s = solver_from_synth(fl, product_lib)
+    lib = product_lib
+    sd = make_decisions(fl, 60_000, 9, sweep=True, plain=True)
+    a = s.place_batch(sd.dec, fl.now_ms, 5)
+    b = s.place_batch(sd.dec, fl.now_ms, 5)
+    assert np.array_equal(a, b)
+    # slices with their id base
+    cuts = [0, 1, 31, 32, 33, 20_000, 20_007, 60_000]
+    parts = []
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        s._ck(lib.mmp_fleet_set_id_base(s.h, lo))
+        parts.append(s.place_batch(sd.dec[lo:hi], fl.now_ms, 5))
+    s._ck(lib.mmp_fleet_set_id_base(s.h, 0))
+    assert np.array_equal(np.concatenate(parts), a)
+    # device-resident entry point
+    d_in, d_out = C.c_void_p(), C.c_void_p()
+    dec = np.ascontiguousarray(sd.dec)
+    s._ck(lib.mmp_device_alloc(s.h, dec.nbytes, C.byref(d_in)))
+    s._ck(lib.mmp_device_alloc(s.h, len(dec) * DECISION_OUT.itemsize, C.byref(d_out)))
+    s._ck(lib.mmp_device_upload(s.h, d_in, dec.ctypes.data_as(C.c_void_p), dec.nbytes))
+    ms = C.c_float()
+    s._ck(lib.mmp_place_batch_device(s.h, d_in, len(dec), d_out, fl.now_ms, 5, C.byref(ms)))
+    dev = np.zeros(len(dec), dtype=DECISION_OUT)
+    s._ck(lib.mmp_device_download(s.h, dev.ctypes.data_as(C.c_void_p), d_out, dev.nbytes))
+    assert np.array_equal(dev, a) and ms.value > 0
+    s._ck(lib.mmp_device_free(s.h, d_in)); s._ck(lib.mmp_device_free(s.h, d_out))
+    # single-decision calls (decision id 0 of their own batch)
+    for i in (0, 17, 59_999):
+        s._ck(lib.mmp_fleet_set_id_base(s.h, i))
+        one = s.place_one(sd.dec[i], fl.now_ms, 5)
+        assert (one["target"], one["n_candidates"]) == (a[i]["target"], a[i]["n_candidates"])
+    s._ck(lib.mmp_fleet_set_id_base(s.h, 0))
+    # and the whole thing against the oracle
+    want = _oracle_results(fl, sd, oracle_from_synth(fl), 5)
+    assert np.array_equal(a["target"], want["target"]) and np.array_equal(a["n_candidates"], want["n_candidates"])
