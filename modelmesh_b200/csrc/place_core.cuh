@@ -752,14 +752,16 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
   // ---- A': non-simple (a) ----
   uint32_t r1 = NONE_RANK;
   {
-    uint32_t wi = b >> 5;
+    const uint32_t b_w = b >> 5, m_b = mask_above(b_w * 32u, b);
+    uint32_t wi = b_w;
     bool search = live && !simple;
     for (;;) {
       if (search) {
         if (wi >= WE) search = false;
         else if (left <= 0 || wi - WS >= win_words) { search = false; live = false; }
         else {
-          uint32_t x = Fw(wi) & (P[wi] | T.full[wi]) & mask_above(wi * 32u, b);
+          uint32_t x = Fw(wi) & (P[wi] | T.full[wi]);
+          if (wi == b_w) x &= m_b;
           if (x) { r1 = wi * 32u + (uint32_t)ffs32(x); search = false; }
           else { wi++; left--; }
         }
@@ -784,8 +786,8 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
   bool walk = live && !open && !done;
   bool self_in_s = false, c_self = false, self_viol = false;
   uint32_t sw_ = 0xffffffffu, sb_ = 0;
-  int32_t thr = 0;
-  auto cv = [&](int32_t cnt) { return cnt >= 10 && cnt > thr; };  // MM:4924-4927
+  int32_t cv_min = 10;  // cv(cnt) = cnt >= 10 && cnt > thr (MM:4924-4927) = cnt >= max(10, thr + 1); thr <= 1.25e9 by the input domain
+  auto cv = [&](int32_t cnt) { return cnt >= cv_min; };
   if (walk) {
     if (self_rank >= 0 && (uint32_t)self_rank > lo && (uint32_t)self_rank < hi) {
       const uint32_t w = (uint32_t)self_rank >> 5, bit = 1u << (self_rank & 31);
@@ -797,7 +799,8 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
     const int64_t q = best_rem >> 2;
     c_self = fr.rem < s.min_space || fr.rem < q;
     self_viol = rb.rem < s.min_space || rb.rem < q;
-    thr = jaddi(best_count, best_count >> 2);
+    const int32_t thr = jaddi(best_count, best_count >> 2);
+    cv_min = thr >= 9 ? thr + 1 : 10;
     if (self_in_s && cv(c.self_count)) self_viol = true;
   }
   const uint32_t cut_self = (self_in_s && self_viol) ? (uint32_t)self_rank : NONE_RANK;
@@ -805,27 +808,37 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
   const uint32_t lim = hi < cut_self ? hi : cut_self;
   uint32_t stop_w = WE;
   if (lim != NONE_RANK) { const uint32_t e = (lim + 31u) >> 5; stop_w = e < WE ? e : WE; }
+  // a word of S': only the word that holds lo and the one that holds lim are cut (none beyond lim's is ever visited)
+  const uint32_t lo_w = lo >> 5, m_lo = mask_above(lo_w * 32u, lo);
+  const uint32_t lim_w = lim >> 5, m_lim = mask_below(lim_w * 32u, lim);  // lim == NONE_RANK: lim_w is no real word
   auto Sw = [&](uint32_t wi) -> uint32_t {
-    uint32_t m = Fw(wi) & mask_above(wi * 32u, lo) & mask_below(wi * 32u, lim);
+    uint32_t m = Fw(wi);
+    if (wi == lo_w) m &= m_lo;
+    if (wi == lim_w) m &= m_lim;
     return use_pref ? (m & P[wi]) : m;
   };
+  // the walk may visit words [lo_w, end_b): up to the natural end (stop_w), the window and the visit budget
+  uint32_t end_b = stop_w < WS + win_words ? stop_w : WS + win_words;
+  { const uint32_t cap = lo_w + (uint32_t)(left > 0 ? left : 0); if (cap < end_b) end_b = cap; }
   // ---- B: first member of S' that fails its walk test, counting the members before it ----
   uint32_t cut_others = NONE_RANK, n_in = 0;
   {
-    uint32_t wi = lo >> 5, xt = 0;
+    uint32_t wi = lo_w, xt = 0;
     bool search = walk, mixed = false;
     for (;;) {
       for (;;) {
         if (search) {
-          if (wi >= stop_w) { search = false; if (lim == NONE_RANK && open_end) open = true; }
-          else if (left <= 0 || wi - WS >= win_words) { search = false; live = false; }
-          else {
+          if (wi >= end_b) {
+            search = false;
+            if (wi < stop_w) live = false;  // window or budget exhausted before the walk's natural end
+            else if (lim == NONE_RANK && open_end) open = true;
+          } else {
             const uint32_t x = Sw(wi);
             int cls = 0;  // 0: no member fails, 1: every member (but a passing self) fails, 2: look at the counts
             uint32_t v = x;
             if (c_self) { if (wi == sw_) v &= ~sb_; cls = v ? 1 : 0; }
             else if (x) { const WordSumI m = T.csum[wi]; cls = !cv(m.hi) ? 0 : (cv(m.lo) ? 1 : 2); }
-            if (cls == 0) { n_in += (uint32_t)popc32(x); wi++; left--; }
+            if (cls == 0) { n_in += (uint32_t)popc32(x); wi++; }
             else {
               search = false; xt = x;
               if (cls == 1) cut_others = wi * 32u + (uint32_t)ffs32(v);
@@ -852,7 +865,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
 #endif
         vm &= xt;
         if (vm) cut_others = wi * 32u + (uint32_t)ffs32(vm);
-        else { n_in += (uint32_t)popc32(xt); wi++; left--; search = true; }
+        else { n_in += (uint32_t)popc32(xt); wi++; search = true; }
       }
       if (!vote.any(search)) break;
     }
@@ -893,13 +906,15 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
   // ---- C: k-th survivor in rank order ----
   {
     const bool drop_self = self_in_sl && !keep_self;
-    uint32_t wi = lo >> 5;
+    const uint32_t cut_w = cut >> 5, m_cut = mask_below(cut_w * 32u, cut);
+    uint32_t wi = lo_w;
     bool search = sel;
     for (;;) {
       if (search) {
-        if (wi >= stop_w) { search = false; live = false; }  // cannot happen: kth < number of survivors
+        if (wi >= end_b) { search = false; live = false; }  // cannot happen: kth < number of survivors, all in visited words
         else {
-          uint32_t x = Sw(wi) & mask_below(wi * 32u, cut);
+          uint32_t x = Sw(wi);
+          if (wi == cut_w) x &= m_cut;
           if (drop_self && wi == sw_) x &= ~sb_;
           const uint32_t n = (uint32_t)popc32(x);
           if (kth < n) { chosen_rank = wi * 32u + (uint32_t)nth_bit(x, kth); search = false; }
