@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotVie
 // instance-sharded combine: kernels around the one collective
 // ---------------------------------------------------------------------------------------------------------------
 // keys -> results in place (both 8 bytes per decision) + a flag per decision whose winning shard left it open
-__global__ void k_shard_decode(uint64_t *__restrict__ keys_out, int n, uint8_t *__restrict__ open_flag) {
+__global__ void k_shard_decode(uint64_t *__restrict__ keys_out, int n, uint8_t *__restrict__ open_flag, int *__restrict__ n_open) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t k = keys_out[i];
@@ -554,6 +554,7 @@ __global__ void k_shard_decode(uint64_t *__restrict__ keys_out, int n, uint8_t *
   shard_key_decode(k, t, c);
   const bool open = shard_key_open(k);
   open_flag[i] = open ? 1 : 0;
+  if (open) atomicAdd(n_open, 1);  // only a count: the ordered list is built (cub::DeviceSelect) when there is anything to list
   reinterpret_cast<mmp_decision_out *>(keys_out)[i] = mmp_decision_out{open ? MMP_TARGET_NONE : t, open ? 0 : c};
 }
 // this shard's block of the exclusion row of every open decision, and the decision records themselves, compacted
@@ -662,6 +663,8 @@ struct PlaceCtx {
   static constexpr int NPIPE = 3;
   cudaStream_t pipe[NPIPE] = {nullptr, nullptr, nullptr};  // H2D / kernel / D2H of consecutive chunks overlap across these
   cudaEvent_t e0 = nullptr, e1 = nullptr, ready = nullptr;
+  static constexpr int NSHARD_CHUNKS = 4;  // instance-sharded batches: scoring of chunk k+1 overlaps the all-reduce of chunk k
+  cudaEvent_t shard_ev[NSHARD_CHUNKS + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   DevBuf d_in, d_out, d_fresh, d_extra, d_trace, d_cand;
   DevBuf d_open_flag, d_open_idx, d_n_open, d_cub, d_blocks, d_gathered, d_rows, d_in_open, d_out_open;  // instance-shard combine
   std::vector<FreshRow> fresh_host;
@@ -696,6 +699,7 @@ struct mmp_fleet {
                                 // its 196 -> 228 KB carve-out step and the lane tables no longer stay resident)
   int lane_front = 0;           // MMP_LANE_FRONT=1: lane tables from a shared-memory copy instead of the snapshot (L1/L2); measured
                                 // slower (3.8 vs 4.2 G/s): the copy pushes shared memory past the 196 KB carve-out step
+  int shard_chunks = 1;         // MMP_SHARD_CHUNKS (see place_sharded)
   int lane_mode = 0;            // MMP_LANE_MODE=1: stream-only probe (rows staged, no decisions) -- measurement aid, results void
   int lanes = 1;                // MMP_KERNEL=tile selects the cooperative-tile kernel (k_place) instead of k_place_lanes
   int lane_warps = 0;           // warps per block of k_place_lanes (MMP_LANE_WARPS = 8 | 10 | 12 | 14 | 16 | 20); 0 = by launch size
@@ -733,6 +737,7 @@ static PlaceCtx *acquire_ctx(mmp_fleet *f) {
             cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming) == cudaSuccess &&
             cudaHostAlloc((void **)&c->mapped, PlaceCtx::MAPPED_BYTES, cudaHostAllocMapped) == cudaSuccess;
   for (int i = 0; ok && i < PlaceCtx::NPIPE; i++) ok = cudaStreamCreateWithFlags(&c->pipe[i], cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; ok && i <= PlaceCtx::NSHARD_CHUNKS; i++) ok = cudaEventCreateWithFlags(&c->shard_ev[i], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) { delete c; return nullptr; }
   return c;
 }
@@ -747,6 +752,7 @@ static void destroy_ctx(PlaceCtx *c) {
   if (c->e0) cudaEventDestroy(c->e0);
   if (c->e1) cudaEventDestroy(c->e1);
   if (c->ready) cudaEventDestroy(c->ready);
+  for (int i = 0; i <= PlaceCtx::NSHARD_CHUNKS; i++) if (c->shard_ev[i]) cudaEventDestroy(c->shard_ev[i]);
   if (c->mapped) cudaFreeHost(c->mapped);
   for (int i = 0; i < PlaceCtx::NPIPE; i++) if (c->pipe[i]) cudaStreamDestroy(c->pipe[i]);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -806,7 +812,7 @@ template <int WARPS>
 static cudaError_t launch_place_lanes(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st, int ns) {
   static int attr_set = 0;
   if (f->lane_stages >= 2 && f->lane_stages < ns) ns = f->lane_stages;
-  const LaneLayout lay(a.s.excl_stride, ns, WARPS, f->lane_front != 0);
+  const LaneLayout lay(a.s.excl_stride, ns, WARPS, f->lane_front != 0);  // (instance-sharded rows are short: well under half an SM's shared memory)
   auto kern = k_place_lanes<WARPS>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -866,30 +872,46 @@ static int32_t place_sharded(mmp_fleet *f, PlaceCtx *c, const DeviceSnapshot &ds
   NcclApi &nc = nccl_api();
   std::lock_guard<std::mutex> g(f->comm_mu);
   const int G = f->hs.cfg.shard_count;
-  // 1. per-shard keys (the scoring kernel)
-  PlaceArgs a{ds.view, d_in, n, d_fresh, n_fresh, d_extra, d_out, nullptr, nullptr, now_ms, seed, f->id_base.load()};
-  a.emit_keys = 1;
-  CK(launch_place(f, a, st));
-  // 2. min-loc combine over NVLink
-  NK(nc.AllReduce(d_out, d_out, (size_t)n, ncclUint64, ncclMin, f->comm, st));
-  // 3. keys -> results, flag what is still open
   CK(c->d_open_flag.ensure((size_t)n));
   CK(c->d_open_idx.ensure((size_t)n * 4));
   CK(c->d_n_open.ensure(16));
-  k_shard_decode<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<uint64_t *>(d_out), n, c->d_open_flag.as<uint8_t>());
-  f->launches++;
-  CK(cudaGetLastError());
+  CK(cudaMemsetAsync(c->d_n_open.p, 0, sizeof(int), st));
+  // 1-3. per-shard keys (the scoring kernel), the min-loc combine over NVLink, keys -> results.  MMP_SHARD_CHUNKS = 2..4
+  // splits a large batch so that the all-reduce and decode of chunk k run on a second stream while the scoring kernel
+  // works on chunk k + 1; measured on 2 x B200 at 1 M decisions it is SLOWER than one all-reduce (0.316 vs 0.267 ms per
+  // step: four short launches and four collectives cost more than the 8 MB exchange they hide), so the default is 1.
+  const int K = (n >= (1 << 18) && f->shard_chunks > 1) ? std::min(f->shard_chunks, (int)PlaceCtx::NSHARD_CHUNKS) : 1;
+  const int32_t chunk = ((n + K - 1) / K + 31) / 32 * 32;
+  cudaStream_t side = c->pipe[0];
+  CK(cudaEventRecord(c->shard_ev[PlaceCtx::NSHARD_CHUNKS], st));  // the side stream starts after what precedes this call on st
+  CK(cudaStreamWaitEvent(side, c->shard_ev[PlaceCtx::NSHARD_CHUNKS], 0));
+  int k = 0;
+  for (int32_t lo = 0; lo < n; lo += chunk, k++) {
+    const int32_t cnt = std::min(chunk, n - lo);
+    PlaceArgs a{ds.view, d_in + lo, cnt, d_fresh, n_fresh, d_extra, d_out + lo, nullptr, nullptr, now_ms, seed, f->id_base.load() + (uint64_t)lo};
+    a.emit_keys = 1;
+    CK(launch_place(f, a, st));
+    cudaStream_t cs = K > 1 ? side : st;
+    if (K > 1) { CK(cudaEventRecord(c->shard_ev[k], st)); CK(cudaStreamWaitEvent(side, c->shard_ev[k], 0)); }
+    NK(nc.AllReduce(d_out + lo, d_out + lo, (size_t)cnt, ncclUint64, ncclMin, f->comm, cs));
+    k_shard_decode<<<(cnt + 255) / 256, 256, 0, cs>>>(reinterpret_cast<uint64_t *>(d_out + lo), cnt, c->d_open_flag.as<uint8_t>() + lo,
+                                                       c->d_n_open.as<int>());
+    f->launches++;
+    CK(cudaGetLastError());
+  }
+  if (K > 1) { CK(cudaEventRecord(c->shard_ev[PlaceCtx::NSHARD_CHUNKS], side)); CK(cudaStreamWaitEvent(st, c->shard_ev[PlaceCtx::NSHARD_CHUNKS], 0)); }
+  int n_open = 0;
+  CK(cudaMemcpyAsync(&n_open, c->d_n_open.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (n_open == 0) return MMP_OK;
+  f->open_decisions += n_open;
+  // the open decisions as an ordered list, identical on every rank
   size_t tmp_bytes = 0;
   thrust::counting_iterator<int32_t> iota(0);
   CK(cub::DeviceSelect::Flagged(nullptr, tmp_bytes, iota, c->d_open_flag.as<uint8_t>(), c->d_open_idx.as<int32_t>(), c->d_n_open.as<int>(), n, st));
   CK(c->d_cub.ensure(tmp_bytes + 16));
   CK(cub::DeviceSelect::Flagged(c->d_cub.p, tmp_bytes, iota, c->d_open_flag.as<uint8_t>(), c->d_open_idx.as<int32_t>(), c->d_n_open.as<int>(), n, st));
   f->launches += 2;
-  int n_open = 0;
-  CK(cudaMemcpyAsync(&n_open, c->d_n_open.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  if (n_open == 0) return MMP_OK;
-  f->open_decisions += n_open;
   // 4. the open decisions, from whole rows: all-gather every shard's block of their exclusion rows (the same ordered
   // list on every rank), assemble, and run the same kernel on the assembled rows with the snapshot's whole rank range
   const int ST = ds.view.excl_stride, NW = ds.view.row_words;
@@ -991,6 +1013,7 @@ int32_t mmp_fleet_create(const mmp_config *cfg, mmp_fleet **out) {
   if (const char *t = getenv("MMP_LANE_STAGES")) f->lane_stages = atoi(t);
   if (const char *t = getenv("MMP_LANE_FRONT")) f->lane_front = atoi(t) != 0;
   if (const char *t = getenv("MMP_LANE_MODE")) f->lane_mode = atoi(t);
+  if (const char *t = getenv("MMP_SHARD_CHUNKS")) f->shard_chunks = atoi(t);
   if (f->lane_mode & 2) { CK(f->d_dbg.ensure(64)); CK(cudaMemset(f->d_dbg.p, 0, 64)); }
   if (const char *t = getenv("MMP_TILE")) { int v = atoi(t); if (v == 8 || v == 16 || v == 32) f->tile = v; }
   *out = f.release();
