@@ -959,7 +959,7 @@ int32_t mmp_shard_unique_id(void *id128) {
 }
 int32_t mmp_shard_connect(mmp_fleet *f, const void *id128) {
   if (!f || !id128) { g_err = "null argument"; return MMP_E_ARG; }
-  if (f->hs.cfg.shard_count < 2) { g_err = "fleet is not instance-sharded (shard_count < 2)"; return MMP_E_STATE; }
+  // (a single shard may connect too: its batches then take the same keys -> all-reduce -> decode path over whole rows)
   NcclApi &nc = nccl_api();
   if (!nc.ok) { g_err = "libnccl.so.2 not found"; return MMP_E_NCCL; }
   CK(cudaSetDevice(f->device));
@@ -1169,7 +1169,7 @@ static int32_t place_impl(mmp_fleet *f, const mmp_decision_in *in, int32_t n, co
   const int RW = ds.view.row_words;
   cudaStream_t st = c->stream;
   const bool traced = trace || cand_mask;
-  if (f->hs.cfg.shard_count > 1) {  // instance-sharded: keys, one all-reduce(min), decode (+ row gather for open walks)
+  if (f->hs.cfg.shard_count > 1 || (f->comm && !traced)) {  // instance-sharded: keys, one all-reduce(min), decode (+ row gather for open walks)
     if (traced) { g_err = "traces are not available on an instance-sharded fleet"; return MMP_E_STATE; }
     CK(c->d_in.ensure((size_t)n * sizeof(mmp_decision_in)));
     CK(c->d_out.ensure((size_t)n * sizeof(mmp_decision_out)));
@@ -1277,7 +1277,7 @@ int32_t mmp_place_batch_device(mmp_fleet *f, const void *d_in, int32_t n, void *
   PlaceArgs a{ds.view, (const mmp_decision_in *)d_in, n, c->d_fresh.as<FreshRow>(), 0, c->d_extra.as<int32_t>(),
               (mmp_decision_out *)d_out, nullptr, nullptr, now_ms, seed, f->id_base.load()};
   CK(cudaEventRecord(c->e0, c->stream));
-  if (f->hs.cfg.shard_count > 1) {
+  if (f->hs.cfg.shard_count > 1 || f->comm) {
     int32_t rcs = place_sharded(f, c, ds, (const mmp_decision_in *)d_in, n, c->d_fresh.as<FreshRow>(), 0, c->d_extra.as<int32_t>(),
                                 (mmp_decision_out *)d_out, now_ms, seed, c->stream);
     if (rcs < 0) return rcs;

@@ -89,3 +89,33 @@ def test_sharded_matches_unsharded(product_lib, world):
         k += 1
         ref_f.close()
     assert total_open > 0  # the row-gather pass was exercised (C5 / MIX walks cross shard boundaries)
+
+
+@pytest.mark.gpu
+def test_single_shard_takes_the_collective_path(product_lib, oracle_lib):
+    """One GPU: a fleet of ONE shard that connects (ncclCommInitRank with one rank) sends its batches through the same
+    keys -> ncclAllReduce(min) -> decode path as a sharded fleet, over whole rows.  Results must equal the plain path's
+    (and the oracle's), including decisions the lane routine hands to the cooperative routine."""
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from helpers import oracle_from_synth, oracle_inputs_fast
+    from modelmesh_b200.fleet import Fleet
+    for config, nm, ni, seed in [("C3", 40_000, 10_000, 3), ("C5", 3000, 5000, 5), ("MIX", 500, 300, 14)]:
+        fl = make_fleet(config, nm, ni, seed)
+        plain_f = Fleet(fl.min_space_units, fl.min_churn_age_ms, fl.default_model_size_units, fl.n_instances, fl.n_models, lib=product_lib)
+        load_into_fleet(fl, plain_f)
+        f = Fleet(fl.min_space_units, fl.min_churn_age_ms, fl.default_model_size_units, fl.n_instances, fl.n_models, lib=product_lib)
+        load_into_fleet(fl, f)
+        f.shard_connect(f.shard_unique_id())
+        for plain in (True, False):
+            sd = make_decisions(fl, min(nm, 40_000), seed, sweep=plain, plain=plain)
+            kw = dict(fresh=sd.fresh if len(sd.fresh) else None, extra=sd.extra if len(sd.extra) else None)
+            want = plain_f.place_batch(sd.dec, fl.now_ms, 77, **kw)
+            got = f.place_batch(sd.dec, fl.now_ms, 77, **kw)
+            assert np.array_equal(got, want)
+        assert f.shard_open_decisions() == 0  # a single shard's range is the whole row: no walk can leave it
+        o = oracle_from_synth(fl)
+        od, off, idx = oracle_inputs_fast(fl, sd)
+        res = o.get_next_batch(od, fl.type_names, off, idx, fl.now_ms, 77, fresh=sd.fresh if len(sd.fresh) else None)
+        assert np.array_equal(got["target"], res["target"]) and np.array_equal(got["n_candidates"], res["n_candidates"])
+        f.close(); plain_f.close()
