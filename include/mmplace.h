@@ -139,6 +139,14 @@ int32_t mmp_instance_upsert(mmp_fleet *, int32_t idx, const mmp_instance_row *ro
 /* update only the numeric columns of an instance already present (the common KV update event) */
 int32_t mmp_instance_update(mmp_fleet *, int32_t idx, const mmp_instance_row *row);
 int32_t mmp_instance_remove(mmp_fleet *, int32_t idx);
+/* The same from the records as the KV store holds them (jackson JSON): InstanceRecord (IR:37-69: lruTime count cap used
+ * lThreads lInProg rpm shutdown startTime vers loc zone labels) and ModelRecord (MR:61-114: type, instanceIds and failedIn
+ * maps keyed by instance id, lu).  Unknown properties are ignored, absent ones keep the jackson-constructor defaults.
+ * `active` = the instance is in litelinks' service-instance list (not part of the record).  Instance ids in a model
+ * record are resolved through the ids given to mmp_instance_upsert*; ids of instances not present are skipped (they
+ * cannot be candidates either).  size_units = CacheEntry weight / KNOWN_SIZE (not part of the record). */
+int32_t mmp_instance_upsert_json(mmp_fleet *, int32_t idx, const char *id, const char *record_json, int32_t active);
+int32_t mmp_model_upsert_json(mmp_fleet *, int32_t model, const char *record_json, int32_t size_units);
 /* MM_TYPE_CONSTRAINTS json (TCM:79-98, 193-206; config/examples/type-constraints-example):
  * {"type": {"required": ["l1",..], "preferred": ["l2",..]}, "_default": {...}}.  NULL/"" = typeConstraints == null. */
 int32_t mmp_types_set_json(mmp_fleet *, const char *json);

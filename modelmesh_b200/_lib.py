@@ -70,6 +70,8 @@ SYMBOLS = [
     ("mmp_instance_upsert", _I32, [_P, _I32, _P, C.c_char_p, C.c_char_p, C.c_char_p, _STRS, _I32]),
     ("mmp_instance_update", _I32, [_P, _I32, _P]),
     ("mmp_instance_remove", _I32, [_P, _I32]),
+    ("mmp_instance_upsert_json", _I32, [_P, _I32, C.c_char_p, C.c_char_p, _I32]),
+    ("mmp_model_upsert_json", _I32, [_P, _I32, C.c_char_p, _I32]),
     ("mmp_types_set_json", _I32, [_P, C.c_char_p]),
     ("mmp_type_id", _I32, [_P, C.c_char_p]),
     ("mmp_replicasets_set", _I32, [_P, _STRS, _I32]),

@@ -11,7 +11,9 @@
 // UT = UpgradeTracker.java (kserve/modelmesh @ ea13cdc5).
 #pragma once
 #include <algorithm>
+#include <cerrno>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <set>
@@ -184,6 +186,8 @@ class HostState {
   int32_t row_words() const { return ((cfg.max_instances + 31) / 32 + 31) / 32 * 32; }
 
   int32_t set_types_json(const char *json);  // defined after TcJson
+  int32_t upsert_instance_json(int32_t idx, const char *id, const char *json, int32_t active);  // defined after RecordJson
+  int32_t set_model_json(int32_t m, const char *json, int32_t size_units);
 
   static const char *validate_row(const mmp_instance_row &r) {
     if (r.lru_time < 0) return "lru_time must be >= 0 (Long.MAX_VALUE when empty)";
@@ -544,7 +548,7 @@ class TcJson {
     }
   }
 
- private:
+ protected:
   const char *p_;
   void ws() { while (*p_ == ' ' || *p_ == '\t' || *p_ == '\n' || *p_ == '\r') p_++; }
   bool eat(char c) { if (*p_ == c) { p_++; return true; } return false; }
@@ -649,6 +653,173 @@ class TcJson {
     }
   }
 };
+
+// ---- KV-record codecs: the registry keeps InstanceRecord / ModelRecord as jackson JSON; a host that
+// watches the KV store can hand the bytes over as they are.  Unknown properties are ignored, absent ones keep the
+// defaults of the record's jackson constructor (IR:76-78, MR:117-125). ----
+class RecordJson : public TcJson {
+ public:
+  explicit RecordJson(const char *s) : TcJson(s) {}
+  // InstanceRecord wire format (IR:37-69): lruTime count cap used lThreads lInProg rpm shutdown startTime vers loc zone labels
+  bool instance(mmp_instance_row &row, std::string &loc, bool &has_loc, std::string &zone, bool &has_zone,
+                std::vector<std::string> &labels, std::string &err) {
+    memset(&row, 0, sizeof(row));
+    has_loc = has_zone = false;
+    labels.clear();
+    return object([&](const std::string &k) -> bool {
+      int64_t v = 0;
+      if (k == "lruTime") { if (!integer(v)) return false; row.lru_time = v; }
+      else if (k == "count") { if (!integer(v)) return false; row.count = (int32_t)v; }
+      else if (k == "cap") { if (!integer(v)) return false; row.capacity = v; }
+      else if (k == "used") { if (!integer(v)) return false; row.used = v; }
+      else if (k == "lThreads") { if (!integer(v)) return false; row.l_threads = (int32_t)v; }
+      else if (k == "lInProg") { if (!integer(v)) return false; row.l_in_prog = (int32_t)v; }
+      else if (k == "rpm") { if (!integer(v)) return false; row.rpm = (int32_t)v; }
+      else if (k == "shutdown") { bool b; if (!boolean(b)) return false; row.shutting_down = b ? 1 : 0; }
+      else if (k == "startTime") { if (!integer(v)) return false; row.start_time = v; }
+      else if (k == "vers") { if (!integer(v)) return false; row.vers = v; }
+      else if (k == "loc") return nullable_string(loc, has_loc);
+      else if (k == "zone") return nullable_string(zone, has_zone);
+      else if (k == "labels") return string_list(labels);
+      else return skip();
+      return true;
+    }, err);
+  }
+  // ModelRecord wire format (MR:61-114): type, instanceIds {iid: loadStart}, failedIn {iid: failTime}, lu; the rest is ignored
+  bool model(std::string &type, std::vector<std::string> &loaded, std::vector<std::string> &failed, int64_t &last_used,
+             std::string &err) {
+    type.clear(); loaded.clear(); failed.clear(); last_used = 0;
+    return object([&](const std::string &k) -> bool {
+      bool has;
+      if (k == "type") return nullable_string(type, has);
+      if (k == "instanceIds") return key_list(loaded);
+      if (k == "failedIn") return key_list(failed);
+      if (k == "lu") return integer(last_used);
+      return skip();
+    }, err);
+  }
+
+ private:
+  template <class F> bool object(F &&field, std::string &err) {
+    ws();
+    if (!eat('{')) { err = "expected '{'"; return false; }
+    ws();
+    if (eat('}')) return tail(err);
+    for (;;) {
+      std::string k;
+      ws();
+      if (!str(k)) { err = "expected property name"; return false; }
+      ws();
+      if (!eat(':')) { err = "expected ':'"; return false; }
+      ws();
+      if (!field(k)) { err = "bad value for property " + k; return false; }
+      ws();
+      if (eat(',')) continue;
+      if (eat('}')) return tail(err);
+      err = "expected ',' or '}'";
+      return false;
+    }
+  }
+  bool skip() { return skip_value(); }
+  bool integer(int64_t &v) {
+    ws();
+    char *end = nullptr;
+    errno = 0;
+    long long x = strtoll(p_, &end, 10);
+    if (end == p_ || errno == ERANGE) return false;
+    if (*end == '.' || *end == 'e' || *end == 'E') return false;  // jackson would coerce; the records never hold fractions
+    p_ = end; v = (int64_t)x;
+    return true;
+  }
+  bool boolean(bool &b) {
+    ws();
+    if (!strncmp(p_, "true", 4)) { p_ += 4; b = true; return true; }
+    if (!strncmp(p_, "false", 5)) { p_ += 5; b = false; return true; }
+    return false;
+  }
+  bool nullable_string(std::string &s, bool &has) {
+    ws();
+    if (!strncmp(p_, "null", 4)) { p_ += 4; has = false; s.clear(); return true; }
+    s.clear(); has = true;
+    return str(s);
+  }
+  bool string_list(std::vector<std::string> &out) {
+    ws();
+    if (!strncmp(p_, "null", 4)) { p_ += 4; return true; }
+    if (!eat('[')) return false;
+    ws();
+    if (eat(']')) return true;
+    for (;;) {
+      std::string s8;
+      ws();
+      if (!str(s8)) return false;
+      out.push_back(s8);
+      ws();
+      if (eat(',')) continue;
+      return eat(']');
+    }
+  }
+  bool key_list(std::vector<std::string> &keys) {  // {"iid": 123, ...} -> the keys
+    ws();
+    if (!strncmp(p_, "null", 4)) { p_ += 4; return true; }
+    if (!eat('{')) return false;
+    ws();
+    if (eat('}')) return true;
+    for (;;) {
+      std::string k;
+      ws();
+      if (!str(k)) return false;
+      ws();
+      if (!eat(':')) return false;
+      if (!skip_value()) return false;
+      keys.push_back(k);
+      ws();
+      if (eat(',')) continue;
+      return eat('}');
+    }
+  }
+};
+
+inline int32_t HostState::upsert_instance_json(int32_t idx, const char *id, const char *json, int32_t active) {
+  if (!json || !id) { err = "null argument"; return MMP_E_ARG; }
+  mmp_instance_row row;
+  std::string loc, zone, e;
+  bool has_loc, has_zone;
+  std::vector<std::string> labels;
+  if (!RecordJson(json).instance(row, loc, has_loc, zone, has_zone, labels, e)) { err = "instance record json: " + e; return MMP_E_ARG; }
+  row.active = active ? 1 : 0;
+  std::vector<const char *> lp;
+  for (auto &l : labels) lp.push_back(l.c_str());
+  return upsert_instance(idx, &row, id, has_loc ? loc.c_str() : nullptr, has_zone ? zone.c_str() : nullptr, lp.data(), (int32_t)lp.size());
+}
+
+inline int32_t HostState::set_model_json(int32_t m, const char *json, int32_t size_units) {
+  if (!json) { err = "null argument"; return MMP_E_ARG; }
+  std::string type, e;
+  std::vector<std::string> loaded, failed;
+  int64_t lu = 0;
+  if (!RecordJson(json).model(type, loaded, failed, lu, e)) { err = "model record json: " + e; return MMP_E_ARG; }
+  // instance ids -> indices through the ingest dictionary; an id that names no present instance cannot be a candidate
+  // either, so leaving it out of the exclusion row changes nothing (MM:4735-4743 tests membership by id)
+  std::unordered_map<JStr, int32_t> by_id;  // std::hash<std::u16string>
+  for (int32_t i = 0; i < cfg.max_instances; i++)
+    if (inst[i].present) by_id.emplace(inst[i].id, i);
+  std::vector<int32_t> ids;
+  for (const auto *lst : {&loaded, &failed})
+    for (const auto &s8 : *lst) {
+      auto it = by_id.find(utf8_to_utf16(s8.c_str()));
+      if (it != by_id.end() && std::find(ids.begin(), ids.end(), it->second) == ids.end()) ids.push_back(it->second);
+    }
+  mmp_model_row row{};
+  row.last_used = lu;
+  row.size_units = size_units;
+  const int32_t tid = type.empty() ? 0 : intern_type(type);
+  if (tid < 0) { err = "more than 65534 model types"; return MMP_E_ARG; }
+  row.type_id = (uint16_t)tid;
+  row.copy_count = (uint8_t)std::min<size_t>(255, loaded.size());
+  row.fail_count = (uint8_t)std::min<size_t>(255, failed.size());
+  return set_model(m, &row, ids.data(), (int32_t)ids.size());
+}
 
 inline int32_t HostState::set_types_json(const char *json) {
   if (!json || !*json) { tc_enabled = false; tc_config.clear(); return MMP_OK; }

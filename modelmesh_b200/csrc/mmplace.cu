@@ -1053,6 +1053,11 @@ int32_t mmp_instance_upsert(mmp_fleet *f, int32_t idx, const mmp_instance_row *r
   FWD(f->hs.upsert_instance(idx, row, id, loc, zone, labels, n_labels));
 }
 int32_t mmp_instance_update(mmp_fleet *f, int32_t idx, const mmp_instance_row *row) { NEED(f); FWD(f->hs.update_instance(idx, row)); }
+int32_t mmp_instance_upsert_json(mmp_fleet *f, int32_t idx, const char *id, const char *json, int32_t active) {
+  NEED(f);
+  FWD(f->hs.upsert_instance_json(idx, id, json, active));
+}
+int32_t mmp_model_upsert_json(mmp_fleet *f, int32_t m, const char *json, int32_t size_units) { NEED(f); FWD(f->hs.set_model_json(m, json, size_units)); }
 int32_t mmp_instance_remove(mmp_fleet *f, int32_t idx) { NEED(f); FWD(f->hs.remove_instance(idx)); }
 int32_t mmp_types_set_json(mmp_fleet *f, const char *json) { NEED(f); FWD(f->hs.set_types_json(json)); }
 int32_t mmp_type_id(mmp_fleet *f, const char *name) {

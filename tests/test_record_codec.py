@@ -1,0 +1,85 @@
+"""KV-record codecs (mmp_instance_upsert_json / mmp_model_upsert_json): a fleet ingested from the registry's jackson JSON
+(InstanceRecord IR:37-69, ModelRecord MR:61-114) is the fleet ingested through the struct API -- same PLACEMENT_ORDER,
+same type sets, same decisions.  Host logic only: runs on the CPU harness (it compiles the product's host_state.hpp)."""
+import json
+
+import numpy as np
+import pytest
+
+from modelmesh_b200._lib import MODEL_ROW
+from modelmesh_b200.fleet import Fleet, MmpError
+from modelmesh_b200.synth import load_into_fleet, make_decisions, make_fleet
+
+LONG_MAX = 9223372036854775807
+
+
+def instance_json(fl, i, extra=None):
+    r = fl.inst_rows[i]
+    d = {"lruTime": int(r["lru_time"]), "count": int(r["count"]), "cap": int(r["capacity"]), "used": int(r["used"]),
+         "lThreads": int(r["l_threads"]), "lInProg": int(r["l_in_prog"]), "rpm": int(r["rpm"]), "shutdown": bool(r["shutting_down"]),
+         "startTime": int(r["start_time"]), "vers": int(r["vers"]), "loc": fl.inst_locs[i], "zone": fl.inst_zones[i],
+         "labels": list(fl.inst_labels[i])}
+    if extra:
+        d.update(extra)
+    return json.dumps(d)
+
+
+def model_json(fl, m, tname):
+    a, b = int(fl.edge_off[m]), int(fl.edge_off[m + 1])
+    ids = [fl.inst_ids[int(x)] for x in fl.edge_inst[a:b]]
+    nl = int(fl.n_loaded[m])
+    loaded = {iid: 1700000000000 + k for k, iid in enumerate(ids[:nl])}
+    failed = {iid: 1700000001000 + k for k, iid in enumerate(ids[nl:])}
+    return json.dumps({"type": tname, "encKey": None, "mPath": "s3://bucket/m%d" % m, "instanceIds": loaded, "failedIn": failed,
+                       "fails": {}, "refs": 0, "autoDel": False, "lu": int(fl.model_last_used[m]), "lul": 0})
+
+
+@pytest.mark.parametrize("config,nm,ni,seed", [("C3", 600, 300, 3), ("MIX", 400, 97, 21), ("C5", 500, 200, 5)])
+def test_fleet_from_json_records_equals_struct_ingest(emul_lib, config, nm, ni, seed):
+    lib = emul_lib
+    fl = make_fleet(config, nm, ni, seed)
+    a = Fleet(fl.min_space_units, fl.min_churn_age_ms, fl.default_model_size_units, fl.n_instances, fl.n_models, lib=lib)
+    load_into_fleet(fl, a)
+    b = Fleet(fl.min_space_units, fl.min_churn_age_ms, fl.default_model_size_units, fl.n_instances, fl.n_models, lib=lib)
+    b.types_set_json(fl.type_json())
+    b.replicasets_set(fl.replaced_replicasets)
+    for i in range(fl.n_instances):
+        extra = {"futureField": {"x": [1, 2, {"y": "z"}]}, "kvVersion": 7} if i % 3 == 0 else None  # unknown properties are ignored
+        b._ck(lib.mmp_instance_upsert_json(b.h, i, fl.inst_ids[i].encode(), instance_json(fl, i, extra).encode(), int(fl.inst_rows[i]["active"])))
+    for m in range(fl.n_models):
+        b._ck(lib.mmp_model_upsert_json(b.h, m, model_json(fl, m, fl.type_names[int(fl.model_type[m])]).encode(), int(fl.model_size[m])))
+    b.commit()
+    assert np.array_equal(a.cluster_order(), b.cluster_order())
+    for t in fl.type_names:  # type ids are interned in encounter order (opaque); the sets behind them must agree
+        sa, sb = a.type_sets(a.type_id(t), fl.n_instances), b.type_sets(b.type_id(t), fl.n_instances)
+        for x, y in zip(sa, sb):
+            assert (x is None) == (y is None) and (x is None or np.array_equal(x, y))
+    sd = make_decisions(fl, 1500, seed)
+    kw = dict(fresh=sd.fresh if len(sd.fresh) else None, extra=sd.extra if len(sd.extra) else None)
+    ra = a.place_batch(sd.dec, fl.now_ms, 5, **kw)
+    rb = b.place_batch(sd.dec, fl.now_ms, 5, **kw)
+    assert np.array_equal(ra, rb)
+
+
+def test_record_defaults_and_errors(emul_lib):
+    lib = emul_lib
+    f = Fleet(2560, 600000, 2560, 8, 8, lib=lib)
+    # jackson-constructor defaults (IR:76-78): everything absent -> zeros, null loc/zone, no labels
+    f._ck(lib.mmp_instance_upsert_json(f.h, 0, b"pod-a", b"{}", 1))
+    f._ck(lib.mmp_instance_upsert_json(f.h, 1, b"pod-b", json.dumps({"lruTime": LONG_MAX, "cap": 25600, "used": 100, "lThreads": 8,
+                                                                     "labels": None, "loc": None, "zone": "zé中"}).encode(), 1))
+    f._ck(lib.mmp_instance_upsert_json(f.h, 2, b"pod-c", b' { "cap" : 25600 , "used":25600, "shutdown" : true } ', 1))
+    f._ck(lib.mmp_model_upsert_json(f.h, 0, json.dumps({"type": "t1", "instanceIds": {"pod-b": 5, "pod-zzz": 6}, "lu": 123}).encode(), 256))
+    f._ck(lib.mmp_model_upsert_json(f.h, 1, b'{"type":null}', 256))
+    f.commit()
+    # pod-c is shutting down: treated as deleted (MM:1462-1464); pod-a has no capacity at all: full, ranks after pod-b
+    assert list(f.cluster_order()) == [1, 0]
+    for bad in (b"", b"[]", b'{"cap": 1.5}', b'{"cap": }', b'{"labels": [1]}', b'{"lruTime": 99999999999999999999}', b'{"cap":1} x'):
+        with pytest.raises(MmpError):
+            f._ck(lib.mmp_instance_upsert_json(f.h, 3, b"pod-d", bad, 1))
+    for bad in (b'{"instanceIds": []}', b'{"lu": "x"}', b"{"):
+        with pytest.raises(MmpError):
+            f._ck(lib.mmp_model_upsert_json(f.h, 2, bad, 1))
+    # values outside the supported domain are refused like the struct API refuses them
+    with pytest.raises(MmpError):
+        f._ck(lib.mmp_instance_upsert_json(f.h, 3, b"pod-d", b'{"rpm": 600000000}', 1))
