@@ -780,14 +780,14 @@ struct PlaceArgs {
 // ring depth (a power of two) / warps per block by row size: rows up to 2 KiB (16k instances) K=4 x 8 warps, up to 4 KiB K=2 x 8, beyond K=2 x 4
 template <int WARPS, int K, int MINB, int T, bool TRACE>
 static cudaError_t launch_place_t(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st) {
-  static int attr_set = 0;
+  static std::atomic<bool> attr_set[64];  // function attributes are per device
   const RingLayout lay(a.s.excl_stride, K);
   const size_t smem = lay.per_warp * WARPS;
   auto kern = k_place<WARPS, K, MINB, T, TRACE>;
-  if (!attr_set) {
+  if (!attr_set[f->device & 63].load()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = 1;
+    attr_set[f->device & 63] = true;
   }
   int bps = 0;
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, WARPS * 32, smem);
@@ -810,14 +810,14 @@ static bool lanes_geometry(int row_words, int warps, bool front, int &ns) {
 
 template <int WARPS>
 static cudaError_t launch_place_lanes(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st, int ns) {
-  static int attr_set = 0;
+  static std::atomic<bool> attr_set[64];  // function attributes are per device
   if (f->lane_stages >= 2 && f->lane_stages < ns) ns = f->lane_stages;
   const LaneLayout lay(a.s.excl_stride, ns, WARPS, f->lane_front != 0);  // (instance-sharded rows are short: well under half an SM's shared memory)
   auto kern = k_place_lanes<WARPS>;
-  if (!attr_set) {
+  if (!attr_set[f->device & 63].load()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = 1;
+    attr_set[f->device & 63] = true;
   }
   const int nb = (a.n + 31) / 32;
   const int grid = std::max(1, std::min((nb + WARPS - 1) / WARPS, f->sm_count));
@@ -830,7 +830,7 @@ static cudaError_t launch_place_lanes(mmp_fleet *f, const PlaceArgs &a, cudaStre
 
 static cudaError_t launch_place(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st) {
   const int rw = a.s.row_words;
-  // production path: one decision per lane (rows up to 2 KiB + pad: at least three 32-row stages per SM)
+  // production path: one decision per lane (any row width of which at least two 32-row landing stages fit: ~3 KiB rows)
   if (!(a.tr || a.cand) && f->lanes) {
     int ns = 0;
     // warps per block: 12 per SM measured best at 10k instances (8: 3.7-3.8, 12: 4.1-4.3, 16: 3.6-3.9 G decisions/s); picking
