@@ -173,6 +173,13 @@ int32_t mmp_place_batch(mmp_fleet *, const mmp_decision_in *in, int32_t n, const
 int32_t mmp_place_batch_trace(mmp_fleet *, const mmp_decision_in *in, int32_t n, const mmp_instance_row *fresh,
                               int32_t n_fresh, const int32_t *extra, int32_t n_extra, mmp_decision_out *out,
                               mmp_decision_trace *trace, uint32_t *cand_mask, int64_t now_ms, uint64_t seed);
+/* Registry sweep -- the reference's natural batched caller: the leader's reaper walks the registry and calls
+ * ensureLoadedInternal per model (MM:6616-6735), i.e. getNext for model first_model + i on behalf of instance self[i]
+ * (self_stride = 1) or of one instance for the whole sweep (self_stride = 0: self[0]), lastUsedTime from the model record,
+ * no extra excludes; favour_bits (may be NULL): bit i = CacheMissExcludeSet.favourSelf.  Same results as mmp_place_batch
+ * on the equivalent 32-byte records, with 4 bytes (+1 bit) instead of 32 going to the device per decision. */
+int32_t mmp_place_sweep(mmp_fleet *, int32_t first_model, int32_t n, const int32_t *self, int32_t self_stride,
+                        const uint32_t *favour_bits, mmp_decision_out *out, int64_t now_ms, uint64_t seed);
 /* Single decision (latency path, B = 1). */
 int32_t mmp_place_one(mmp_fleet *, const mmp_decision_in *in, const mmp_instance_row *fresh, const int32_t *extra,
                       mmp_decision_out *out, int64_t now_ms, uint64_t seed);

@@ -586,6 +586,21 @@ __global__ void k_shard_scatter(const mmp_decision_out *__restrict__ res, const 
   if (j < n_open) out[open_idx[j]] = res[j];
 }
 
+// Registry sweep: decision i = place model first_model + i for instance self[i] (self[0] when self_stride == 0), lastUsed
+// from the model row, favourSelf from a bit vector -- the records the scoring kernel reads, built on the device
+__global__ void k_expand_sweep(mmp_decision_in *__restrict__ out, int n, int first_model, const int32_t *__restrict__ self,
+                               int self_stride, const uint32_t *__restrict__ favour_bits) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  mmp_decision_in d;
+  d.model = first_model + i;
+  d.self = self[(size_t)i * self_stride];
+  d.last_used = 0;
+  d.flags = MMP_DF_MODEL_LAST_USED | ((favour_bits && ((favour_bits[i >> 5] >> (i & 31)) & 1u)) ? MMP_DF_FAVOUR_SELF : 0u);
+  d.fresh = -1; d.extra_off = 0; d.extra_n = 0;
+  out[i] = d;
+}
+
 // NCCL is bound at run time (dlopen): a single-GPU deployment needs no NCCL at all, and inside a process that already
 // carries a copy (PyTorch's) the same one is used.
 struct NcclApi {
@@ -1264,6 +1279,59 @@ int32_t mmp_place_one(mmp_fleet *f, const mmp_decision_in *in, const mmp_instanc
   int32_t nf = (fresh && in->fresh >= 0) ? in->fresh + 1 : 0;
   int32_t ne = (extra && in->extra_n > 0) ? in->extra_off + in->extra_n : 0;
   return place_impl(f, in, 1, fresh, nf, extra, ne, out, nullptr, nullptr, now_ms, seed);
+}
+
+int32_t mmp_place_sweep(mmp_fleet *f, int32_t first_model, int32_t n, const int32_t *self, int32_t self_stride,
+                        const uint32_t *favour_bits, mmp_decision_out *out, int64_t now_ms, uint64_t seed) {
+  NEED(f);
+  if (n < 0 || first_model < 0 || (n > 0 && (!self || !out)) || (self_stride != 0 && self_stride != 1)) { g_err = "bad argument"; return MMP_E_ARG; }
+  if (n == 0) return MMP_OK;
+  int32_t rc = set_device(f);
+  if (rc < 0) return rc;
+  std::shared_lock<std::shared_mutex> rd(f->snap_mu);
+  if (f->epoch == 0) { g_err = "no committed snapshot (call mmp_fleet_commit)"; return MMP_E_EPOCH; }
+  const DeviceSnapshot &ds = f->snaps[f->cur];
+  if ((int64_t)first_model + n > ds.n_models) { g_err = "sweep runs past the registry"; return MMP_E_ARG; }
+  PlaceCtx *c = acquire_ctx(f);
+  if (!c) { g_err = "cannot create CUDA stream"; return MMP_E_CUDA; }
+  struct Rel { mmp_fleet *f; PlaceCtx *c; ~Rel() { release_ctx(f, c); } } rel{f, c};
+  cudaStream_t st = c->stream;
+  const size_t n_self = self_stride ? (size_t)n : 1, n_fav = favour_bits ? ((size_t)n + 31) / 32 : 0;
+  CK(c->d_in.ensure((size_t)n * sizeof(mmp_decision_in)));
+  CK(c->d_out.ensure((size_t)n * sizeof(mmp_decision_out)));
+  CK(c->d_fresh.ensure(sizeof(FreshRow)));
+  CK(c->d_extra.ensure(4));
+  CK(c->d_trace.ensure(n_self * 4 + n_fav * 4 + 16));  // scratch: self[] then favour bits
+  int32_t *d_self = c->d_trace.as<int32_t>();
+  uint32_t *d_fav = n_fav ? reinterpret_cast<uint32_t *>(d_self + n_self) : nullptr;
+  CK(cudaMemcpyAsync(d_self, self, n_self * 4, cudaMemcpyHostToDevice, st));
+  if (n_fav) CK(cudaMemcpyAsync(d_fav, favour_bits, n_fav * 4, cudaMemcpyHostToDevice, st));
+  k_expand_sweep<<<(n + 255) / 256, 256, 0, st>>>(c->d_in.as<mmp_decision_in>(), n, first_model, d_self, self_stride, d_fav);
+  f->launches++;
+  CK(cudaGetLastError());
+  if (f->hs.cfg.shard_count > 1 || f->comm) {
+    int32_t rcs = place_sharded(f, c, ds, c->d_in.as<mmp_decision_in>(), n, c->d_fresh.as<FreshRow>(), 0, c->d_extra.as<int32_t>(),
+                                c->d_out.as<mmp_decision_out>(), now_ms, seed, st);
+    if (rcs < 0) return rcs;
+    CK(cudaMemcpyAsync(out, c->d_out.p, (size_t)n * sizeof(mmp_decision_out), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return MMP_OK;
+  }
+  // chunks: the results of chunk k travel to the host while chunk k + 1 is scored
+  const int32_t CHUNK = 1 << 18;
+  CK(cudaEventRecord(c->ready, st));
+  for (int i = 0; i < PlaceCtx::NPIPE; i++) CK(cudaStreamWaitEvent(c->pipe[i], c->ready, 0));
+  int ci = 0;
+  for (int32_t lo = 0; lo < n; lo += CHUNK, ci++) {
+    const int32_t cnt = std::min(CHUNK, n - lo);
+    cudaStream_t ps = c->pipe[ci % PlaceCtx::NPIPE];
+    PlaceArgs a{ds.view, c->d_in.as<mmp_decision_in>() + lo, cnt, c->d_fresh.as<FreshRow>(), 0, c->d_extra.as<int32_t>(),
+                c->d_out.as<mmp_decision_out>() + lo, nullptr, nullptr, now_ms, seed, f->id_base.load() + (uint64_t)lo};
+    CK(launch_place(f, a, ps));
+    CK(cudaMemcpyAsync(out + lo, c->d_out.as<mmp_decision_out>() + lo, (size_t)cnt * sizeof(mmp_decision_out), cudaMemcpyDeviceToHost, ps));
+  }
+  for (int i = 0; i < PlaceCtx::NPIPE; i++) CK(cudaStreamSynchronize(c->pipe[i]));
+  return MMP_OK;
 }
 
 int32_t mmp_place_batch_device(mmp_fleet *f, const void *d_in, int32_t n, void *d_out, int64_t now_ms, uint64_t seed, float *kernel_ms) {

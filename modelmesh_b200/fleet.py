@@ -123,6 +123,22 @@ class Fleet:
                                                 _ptr(tr), _ptr(cm), now_ms, seed))
         return out, tr, cm
 
+    def place_sweep(self, first_model: int, n: int, self_idx, now_ms: int, seed: int, favour: Optional[np.ndarray] = None):
+        """Registry sweep (the reaper's batch, MM:6616-6735): model first_model + i on behalf of self_idx[i] (or one
+        instance for all when self_idx is an int); favour = optional bool[n] of favourSelf flags."""
+        out = np.zeros(n, dtype=DECISION_OUT)
+        if np.isscalar(self_idx):
+            sa, stride = np.asarray([self_idx], dtype=np.int32), 0
+        else:
+            sa, stride = np.ascontiguousarray(self_idx, dtype=np.int32), 1
+            assert len(sa) == n
+        bits = None
+        if favour is not None:
+            bits = np.packbits(np.asarray(favour, dtype=bool), bitorder="little")
+            bits = np.concatenate([bits, np.zeros((-len(bits)) % 4, dtype=np.uint8)]).view(np.uint32)
+        self._ck(self.lib.mmp_place_sweep(self.h, first_model, n, _ptr(sa), stride, _ptr(bits), _ptr(out), now_ms, seed))
+        return out
+
     def place_one(self, dec: np.ndarray, now_ms: int, seed: int, fresh: Optional[np.ndarray] = None,
                   extra: Optional[np.ndarray] = None):
         dec = np.ascontiguousarray(dec, dtype=DECISION_IN).reshape(1)

@@ -178,6 +178,19 @@ int32_t mmp_place_batch(mmp_fleet *f, const mmp_decision_in *in, int32_t n, cons
   return mmp_place_batch_trace(f, in, n, fresh, n_fresh, extra, n_extra, out, nullptr, nullptr, now_ms, seed);
 }
 
+int32_t mmp_place_sweep(mmp_fleet *f, int32_t first_model, int32_t n, const int32_t *self, int32_t self_stride,
+                        const uint32_t *favour_bits, mmp_decision_out *out, int64_t now_ms, uint64_t seed) {
+  if (n < 0 || first_model < 0 || (n > 0 && (!self || !out)) || (self_stride != 0 && self_stride != 1)) { g_err = "bad argument"; return MMP_E_ARG; }
+  if ((int64_t)first_model + n > (int64_t)f->models.size()) { g_err = "sweep runs past the registry"; return MMP_E_ARG; }
+  std::vector<mmp_decision_in> d((size_t)n);
+  for (int32_t i = 0; i < n; i++) {
+    d[i].model = first_model + i; d[i].self = self[(size_t)i * self_stride]; d[i].last_used = 0;
+    d[i].flags = MMP_DF_MODEL_LAST_USED | ((favour_bits && ((favour_bits[i >> 5] >> (i & 31)) & 1u)) ? MMP_DF_FAVOUR_SELF : 0u);
+    d[i].fresh = -1; d[i].extra_off = 0; d[i].extra_n = 0;
+  }
+  return mmp_place_batch(f, d.data(), n, nullptr, 0, nullptr, 0, out, now_ms, seed);
+}
+
 int32_t mmp_row_words(mmp_fleet *f) { return f->hs.row_words(); }
 int32_t mmp_live_instances(mmp_fleet *f) { return f->snap.n_ranks; }
 int32_t mmp_cluster_order(mmp_fleet *f, int32_t *out_idx, int32_t cap) {

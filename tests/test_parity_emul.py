@@ -125,3 +125,25 @@ def test_slices_with_id_base_equal_the_batch(emul_lib, oracle_lib):
             assert len(np.unique(whole["target"])) > 3
         finally:
             emul_lib.mmp_emul_set_window(32)
+
+
+def test_registry_sweep_equals_the_batch_of_records(emul_lib, oracle_lib):
+    """mmp_place_sweep (model first + i for self[i], lastUsed from the model row, favourSelf bits) = mmp_place_batch on
+    the equivalent records; with one self for the whole sweep it is the leader's reaper batch (MM:6616-6735)."""
+    from modelmesh_b200._lib import DF_FAVOUR_SELF
+    fl = make_fleet("C3", 3000, 700, 3)
+    s = solver_from_synth(fl, emul_lib)
+    sd = make_decisions(fl, 3000, 4, sweep=True, plain=True)
+    whole = s.place_batch(sd.dec, fl.now_ms, 5)
+    fav = (sd.dec["flags"] & DF_FAVOUR_SELF) != 0
+    assert np.array_equal(s.place_sweep(0, 3000, sd.dec["self"], fl.now_ms, 5, favour=fav), whole)
+    # a slice of the registry, numbered like the whole sweep
+    s._ck(emul_lib.mmp_fleet_set_id_base(s.h, 1000))
+    assert np.array_equal(s.place_sweep(1000, 777, sd.dec["self"][1000:1777], fl.now_ms, 5, favour=fav[1000:1777]), whole[1000:1777])
+    s._ck(emul_lib.mmp_fleet_set_id_base(s.h, 0))
+    # one caller for the whole sweep
+    leader = int(sd.dec["self"][0])
+    d2 = sd.dec.copy()
+    d2["self"] = leader
+    d2["flags"] &= ~np.uint32(DF_FAVOUR_SELF)
+    assert np.array_equal(s.place_sweep(0, 3000, leader, fl.now_ms, 5), s.place_batch(d2, fl.now_ms, 5))

@@ -121,3 +121,22 @@ def test_batch_properties(product_lib, oracle_lib):
     # and the whole thing against the oracle
     want = _oracle_results(fl, sd, oracle_from_synth(fl), 5)
     assert np.array_equal(a["target"], want["target"]) and np.array_equal(a["n_candidates"], want["n_candidates"])
+
+
+def test_registry_sweep_entry_point(product_lib, oracle_lib):
+    """mmp_place_sweep on the GPU (records built on the device, results streamed back chunk by chunk) = mmp_place_batch."""
+    from modelmesh_b200._lib import DF_FAVOUR_SELF
+    fl = make_fleet("C3", 300_000, 10_000, 3)
+    s = solver_from_synth(fl, product_lib)
+    sd = make_decisions(fl, 300_000, 4, sweep=True, plain=True)
+    whole = s.place_batch(sd.dec, fl.now_ms, 5)
+    fav = (sd.dec["flags"] & DF_FAVOUR_SELF) != 0
+    assert np.array_equal(s.place_sweep(0, 300_000, sd.dec["self"], fl.now_ms, 5, favour=fav), whole)
+    s._ck(product_lib.mmp_fleet_set_id_base(s.h, 1000))
+    assert np.array_equal(s.place_sweep(1000, 777, sd.dec["self"][1000:1777], fl.now_ms, 5, favour=fav[1000:1777]), whole[1000:1777])
+    s._ck(product_lib.mmp_fleet_set_id_base(s.h, 0))
+    leader = int(sd.dec["self"][0])
+    d2 = sd.dec.copy()
+    d2["self"] = leader
+    d2["flags"] &= ~np.uint32(DF_FAVOUR_SELF)
+    assert np.array_equal(s.place_sweep(0, 300_000, leader, fl.now_ms, 5), s.place_batch(d2, fl.now_ms, 5))
