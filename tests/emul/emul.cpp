@@ -29,7 +29,7 @@ struct mmp_fleet {
 static thread_local std::string g_err;
 static int g_window = 32;  // fast-path window width under test (32: warp tile, 16: half-warp tile); 1: lane-per-decision shape
 static int g_lane_budget = 48;  // CoopLane walk budget (row words) when g_window == 1
-static int g_lane_window = 16;  // decide_stream: row words available to a lane (k_place_lanes copies this window out of the landing stage)
+static int g_lane_window = 14;  // decide_stream: row words available to a lane (LANE_WIN of k_place_lanes: the window copied out of the landing stage)
 static long g_bails = 0, g_lane_decisions = 0;
 
 extern "C" {

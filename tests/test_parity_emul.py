@@ -147,3 +147,33 @@ def test_registry_sweep_equals_the_batch_of_records(emul_lib, oracle_lib):
     d2["self"] = leader
     d2["flags"] &= ~np.uint32(DF_FAVOUR_SELF)
     assert np.array_equal(s.place_sweep(0, 3000, leader, fl.now_ms, 5), s.place_batch(d2, fl.now_ms, 5))
+
+
+@pytest.mark.parametrize("window", [1, 2, 5, 14])
+@pytest.mark.parametrize("config,nm,ni,seed", [("C3", 2000, 1300, 33), ("C5", 1500, 500, 5), ("MIX", 500, 300, 14), ("MIX", 500, 700, 41)])
+def test_stream_routine_window_widths(emul_lib, oracle_lib, config, nm, ni, seed, window):
+    """decide_stream sees only the first `window` words of a row (k_place_lanes copies 14 out of the landing stage): a
+    walk that leaves the window must be declined, never answered from partial information."""
+    import ctypes as C
+    emul_lib.mmp_emul_lane_bails.restype = C.c_long
+    emul_lib.mmp_emul_set_window(2)
+    emul_lib.mmp_emul_set_lane_window(window)
+    emul_lib.mmp_emul_set_lane_budget(64)
+    try:
+        fl = make_fleet(config, nm, ni, seed)
+        o = oracle_from_synth(fl)
+        s = solver_from_synth(fl, emul_lib)
+        emul_lib.mmp_emul_lane_bails(None)
+        sd = make_decisions(fl, 2000, seed)
+        compare_decisions(fl, sd, o, s, seed=seed * 13, full_lists=False)
+        sd = make_decisions(fl, 1500, seed + 1, sweep=True, plain=True)
+        compare_decisions(fl, sd, o, s, seed=seed, full_lists=False)
+        n = C.c_long()
+        bails = emul_lib.mmp_emul_lane_bails(C.byref(n))
+        assert n.value > 0
+        if window == 1 and ni >= 300:
+            assert bails > 0
+    finally:
+        emul_lib.mmp_emul_set_window(32)
+        emul_lib.mmp_emul_set_lane_window(14)
+        emul_lib.mmp_emul_set_lane_budget(48)
