@@ -146,7 +146,10 @@ int32_t mmp_place_batch_trace(mmp_fleet *f, const mmp_decision_in *in, int32_t n
     if (win == 2 && !cand_mask) {  // the lockstep lane routine of k_place_lanes (one decision per lane), general routine when it declines
       uint32_t self_eword = 0;
       if (cx.self_rank >= 0 && (cx.self_rank >> 5) >= v.word_lo && (cx.self_rank >> 5) < v.word_hi) self_eword = erow[(cx.self_rank >> 5) - v.word_lo];
-      done = decide_stream(v, lane_tables_global(v, cx.slot >= 0 ? ctx_slot(cx) : 0), cx, true, erow, (uint32_t)g_lane_window, self_eword, now_ms, seed, f->id_base + (uint64_t)i, SoloVote(), o, g_lane_budget);
+      // the lane sees a COPY of exactly the window (as k_place_lanes gives it): an over-read is a heap overflow under ASAN
+      const uint32_t ww = (uint32_t)std::min<int64_t>(g_lane_window, std::min<int64_t>(v.excl_stride, v.word_hi - v.word_lo));
+      std::vector<uint32_t> window(erow, erow + ww);
+      done = decide_stream(v, lane_tables_global(v, cx.slot >= 0 ? ctx_slot(cx) : 0), cx, true, window.data(), ww, self_eword, now_ms, seed, f->id_base + (uint64_t)i, SoloVote(), o, g_lane_budget);
       g_lane_decisions++;
       if (!done) g_bails++;
     } else if (sharded) {

@@ -83,3 +83,44 @@ def test_record_defaults_and_errors(emul_lib):
     # values outside the supported domain are refused like the struct API refuses them
     with pytest.raises(MmpError):
         f._ck(lib.mmp_instance_upsert_json(f.h, 3, b"pod-d", b'{"rpm": 600000000}', 1))
+
+
+def test_json_readers_survive_garbage(emul_lib):
+    """The three JSON readers of the host code (type constraints, instance record, model record) take bytes that come from
+    a KV store: any input must end in MMP_OK or MMP_E_ARG, never in a crash or a hang (mutations of valid documents,
+    truncations, random bytes; NUL-free because the ABI takes C strings)."""
+    import random
+    lib = emul_lib
+    f = Fleet(2560, 600000, 2560, 8, 8, lib=lib)
+    f._ck(lib.mmp_instance_upsert_json(f.h, 0, b"pod-a", b'{"cap": 25600}', 1))
+    valid = [
+        b'{"lruTime":9223372036854775807,"count":3,"cap":131072,"used":5,"lThreads":8,"lInProg":0,"rpm":12,"shutdown":false,'
+        b'"startTime":1700000000000,"vers":7,"loc":null,"zone":"z\\u00e9\\ud83d\\ude00","labels":["b","a"]}',
+        b'{"type":"t1","encKey":null,"mPath":"p","instanceIds":{"pod-a":5,"x":6},"failedIn":{"pod-a":9},"fails":{"pod-a":{"msg":"m"}},"refs":0,"autoDel":false,"lu":12,"lul":0}',
+        b'{"t1":{"required":["l1","l2"],"preferred":["l3"]},"_default":{"preferred":[]},"t2":{}}',
+    ]
+    rng = random.Random(7)
+    def mutate(b):
+        b = bytearray(b)
+        for _ in range(rng.randint(1, 4)):
+            k = rng.randint(0, 3)
+            if k == 0 and b:
+                del b[rng.randrange(len(b))]
+            elif k == 1:
+                b.insert(rng.randrange(len(b) + 1), rng.choice(b'{}[]",:\\u0123456789-.eEtfn '))
+            elif k == 2 and b:
+                b[rng.randrange(len(b))] = rng.randrange(1, 256)
+            else:
+                b = b[:rng.randrange(len(b) + 1)]
+        return bytes(x for x in b if x != 0)
+    calls = 0
+    for it in range(4000):
+        src = valid[it % 3] if it % 5 else bytes(rng.randrange(1, 256) for _ in range(rng.randint(0, 40)))
+        doc = mutate(src)
+        for rc in (lib.mmp_instance_upsert_json(f.h, 1, b"pod-b", doc, 1), lib.mmp_model_upsert_json(f.h, 1, doc, 10),
+                   lib.mmp_types_set_json(f.h, doc)):
+            assert rc in (0, -1), (rc, doc)
+            calls += 1
+    assert calls == 12000
+    f._ck(lib.mmp_types_set_json(f.h, valid[2]))
+    f.commit()  # the host state is still consistent
