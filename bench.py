@@ -399,7 +399,13 @@ def main():
             for a, b_, res in results:
                 mism += int(np.count_nonzero(res["target"] != out_dev["target"][a:b_]))
                 mism += int(np.count_nonzero(res["n_candidates"] != out_dev["n_candidates"][a:b_]))
-            cpu = {"value": done / t_cpu, "unit": "decisions/s", "cores": threads, "kind": "port",
+            single = None
+            try:  # the same path on one thread, bounded sample (SURVEY.md §8d asks for both)
+                d1, t1, _ = cpu_leg(fl, SynthDecisions(dec[:100_000], sd_all.fresh, sd_all.extra), budget_s=6.0, chunk=25_000, threads=1)
+                single = {"value": d1 / t1, "unit": "decisions/s", "cores": 1, "sample": f"{d1} decisions"}
+            except Exception as ex:
+                print(f"[bench] single-thread cpu leg skipped: {ex}", file=sys.stderr)
+            cpu = {"value": done / t_cpu, "unit": "decisions/s", "cores": threads, "kind": "port", "single_thread": single,
                    "sample": f"{done} decisions of the same sweep, {threads} threads, C++ restatement of the reference's "
                              f"sorted-set walk (CacheMissForwardingLB.getNext); the Java reference cannot run here",
                    "parity_mismatches_vs_gpu": mism}
