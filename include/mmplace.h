@@ -34,9 +34,14 @@ enum {
 
 /* per-decision result codes in mmp_decision_out.target */
 enum {
-  MMP_TARGET_NONE = -1, /* getNext returned null        (MM:4796,4801,4872,4941) */
-  MMP_TARGET_SELF = -2  /* getNext returned ABORT_REQUEST (MM:4894,4932,4990)    */
+  MMP_TARGET_NONE = -1,   /* getNext returned null        (MM:4796,4801,4872,4941) */
+  MMP_TARGET_SELF = -2,   /* getNext returned ABORT_REQUEST (MM:4894,4932,4990)    */
+  MMP_TARGET_INVALID = -3 /* malformed decision, nothing was decided: model / self index out of range, self not live and no
+                             fresh row given, or an extra[] slice outside the table passed with the call (extra_off < 0,
+                             extra_n outside [0, MMP_MAX_EXTRA], extra_off + extra_n > n_extra).  The reference has no
+                             counterpart (a Java caller cannot form such a call); the batch itself still succeeds. */
 };
+#define MMP_MAX_EXTRA 16  /* per-decision additional excludes (tried-this-request ∪ explicit, MM:4706-4715) */
 
 typedef struct mmp_fleet mmp_fleet;
 
@@ -93,7 +98,8 @@ typedef struct {
                            self's published row with rpm = 0 (the reference never sets rpm on the fresh record) */
   int32_t extra_off;    /* offset into extra[] of this decision's additional excluded instance indices
                            (tried-this-request ∪ explicit, MM:4706-4715) */
-  int32_t extra_n;      /* how many (<= 16) */
+  int32_t extra_n;      /* how many, 0..MMP_MAX_EXTRA; the slice must lie inside extra[0, n_extra) or the decision is
+                           answered MMP_TARGET_INVALID (checked on the device; never read out of bounds) */
 } mmp_decision_in;
 
 typedef struct {
@@ -143,8 +149,10 @@ int32_t mmp_instance_remove(mmp_fleet *, int32_t idx);
  * lThreads lInProg rpm shutdown startTime vers loc zone labels) and ModelRecord (MR:61-114: type, instanceIds and failedIn
  * maps keyed by instance id, lu).  Unknown properties are ignored, absent ones keep the jackson-constructor defaults.
  * `active` = the instance is in litelinks' service-instance list (not part of the record).  Instance ids in a model
- * record are resolved through the ids given to mmp_instance_upsert*; ids of instances not present are skipped (they
- * cannot be candidates either).  size_units = CacheEntry weight / KNOWN_SIZE (not part of the record). */
+ * record are kept BY ID and resolved against the instance table at every mmp_fleet_commit (the reference tests membership
+ * by id at decision time, MM:4735-4743), so model and instance records may arrive in any order and an instance may
+ * re-register under another index.  A record without "type" gets ModelRecord's DEFAULT_TYPE "NLCLASSIFIER" (MR:117-130).
+ * size_units = CacheEntry weight / KNOWN_SIZE (not part of the record). */
 int32_t mmp_instance_upsert_json(mmp_fleet *, int32_t idx, const char *id, const char *record_json, int32_t active);
 int32_t mmp_model_upsert_json(mmp_fleet *, int32_t model, const char *record_json, int32_t size_units);
 /* MM_TYPE_CONSTRAINTS json (TCM:79-98, 193-206; config/examples/type-constraints-example):
@@ -169,7 +177,10 @@ int32_t mmp_fleet_commit(mmp_fleet *);
 int32_t mmp_place_batch(mmp_fleet *, const mmp_decision_in *in, int32_t n, const mmp_instance_row *fresh, int32_t n_fresh,
                         const int32_t *extra, int32_t n_extra, mmp_decision_out *out, int64_t now_ms, uint64_t seed);
 /* Same with the optional trace (trace may be NULL) and candidate masks: cand_mask (may be NULL) receives, per decision,
- * mmp_row_words() 32-bit words whose bit r is set iff the instance at PLACEMENT_ORDER rank r is a candidate other than best. */
+ * TWO planes of mmp_row_words() 32-bit words each, i.e. the caller provides n * 2 * mmp_row_words() * 4 bytes:
+ *   plane 0 (words [0, RW)):    bit r set iff the instance at PLACEMENT_ORDER rank r is a candidate other than best
+ *   plane 1 (words [RW, 2 RW)): bit r set iff that candidate survived the rpm filter (MM:4957-4980)
+ * (non-simple case (b), MMP_TF_PREF_B: both planes include best's own bit, see tests/helpers.py). */
 int32_t mmp_place_batch_trace(mmp_fleet *, const mmp_decision_in *in, int32_t n, const mmp_instance_row *fresh,
                               int32_t n_fresh, const int32_t *extra, int32_t n_extra, mmp_decision_out *out,
                               mmp_decision_trace *trace, uint32_t *cand_mask, int64_t now_ms, uint64_t seed);

@@ -104,6 +104,7 @@ struct HostSnapshot {
   std::vector<int32_t> candx_before;  // [n_slots] members of candx at ranks below word_lo*32 (entries that beat this shard)
   std::vector<int32_t> part_of_rank;  // [n_ranks] partition (PTS) id, 0 when no type constraints
   std::vector<std::vector<std::string>> part_types;  // prohibited type names per partition id
+  std::vector<std::vector<int32_t>> part_type_ids;   // the same as type ids of THIS epoch (readers never touch the ingest-side name table)
   // instance columns for the stats / reaper kernels, by rank
   std::vector<int64_t> cap_col;
   std::vector<int32_t> lthreads_col, linprog_col;
@@ -126,6 +127,11 @@ class HostState {
   int32_t n_models_used = 0;
   bool dirty_models = true;
   std::string err;
+  // Instance ids -> indices, maintained by upsert/remove.  Model records ingested as JSON name instances BY ID (MR:69,73);
+  // the ids are kept and resolved against this table at every commit, so the two KV listeners may deliver in any order.
+  std::unordered_map<JStr, int32_t> id_index;
+  std::unordered_map<int32_t, std::vector<JStr>> json_ids;  // model -> loaded ∪ failed ids as the record named them
+  uint64_t inst_gen = 1, json_resolved_gen = 0;             // id table generation / the one the JSON models were last resolved against
 
   void init(const mmp_config &c) {
     cfg = c;
@@ -140,9 +146,15 @@ class HostState {
     if (idx < 0 || idx >= cfg.max_instances || !row || !id || n_labels < 0) { err = "bad instance index or null argument"; return MMP_E_ARG; }
     if (const char *m = validate_row(*row)) { err = m; return MMP_E_ARG; }
     HostInstance &h = inst[idx];
+    JStr nid = utf8_to_utf16(id);
+    if (!h.present || h.id != nid) {  // the id table changes: models held by id are re-resolved at the next commit
+      if (h.present) { auto it = id_index.find(h.id); if (it != id_index.end() && it->second == idx) id_index.erase(it); }
+      id_index[nid] = idx;
+      inst_gen++;
+    }
     h.present = true;
     h.row = *row;
-    h.id = utf8_to_utf16(id);
+    h.id = std::move(nid);
     h.has_loc = loc != nullptr; h.loc = utf8_to_utf16(loc);
     h.has_zone = zone != nullptr; h.zone = utf8_to_utf16(zone);
     h.labels.clear();
@@ -158,6 +170,11 @@ class HostState {
   }
   int32_t remove_instance(int32_t idx) {
     if (idx < 0 || idx >= cfg.max_instances) { err = "bad instance index"; return MMP_E_ARG; }
+    if (inst[idx].present) {
+      auto it = id_index.find(inst[idx].id);
+      if (it != id_index.end() && it->second == idx) id_index.erase(it);
+      inst_gen++;
+    }
     inst[idx] = HostInstance();
     return MMP_OK;
   }
@@ -167,8 +184,9 @@ class HostState {
     for (int32_t i = 0; i < n; i++) replaced_rs.insert(utf8_to_utf16(prefixes[i]));
     return MMP_OK;
   }
-  int32_t set_model(int32_t m, const mmp_model_row *row, const int32_t *ids, int32_t n_ids) {
+  int32_t set_model(int32_t m, const mmp_model_row *row, const int32_t *ids, int32_t n_ids, bool from_json = false) {
     if (m < 0 || m >= cfg.max_models || !row || n_ids < 0 || (n_ids > 0 && !ids)) { err = "bad model index or null argument"; return MMP_E_ARG; }
+    if (!from_json && !json_ids.empty()) json_ids.erase(m);  // an index-based upsert replaces a record held by id
     if (row->type_id >= type_names.size()) { err = "unknown type_id (use mmp_type_id)"; return MMP_E_ARG; }
     for (int32_t i = 0; i < n_ids; i++)
       if (ids[i] < 0 || ids[i] >= cfg.max_instances) { err = "model instance id out of range"; return MMP_E_ARG; }
@@ -184,6 +202,23 @@ class HostState {
   // Words per bitmap row, rounded up to 32 words so that every row starts on a 128-byte line and is a whole number
   // of 16-byte TMA units (10 000 instances -> 320 words = 1 280 B).
   int32_t row_words() const { return ((cfg.max_instances + 31) / 32 + 31) / 32 * 32; }
+
+  // Resolve the instance ids of JSON-ingested model records against the current id table (commit time; the reference tests
+  // membership by id at decision time, MM:4735-4743).  An id that names no present instance cannot be a candidate either.
+  void resolve_json_models() {
+    if (json_ids.empty() || json_resolved_gen == inst_gen) return;
+    std::vector<int32_t> ids;
+    for (auto &kv : json_ids) {
+      ids.clear();
+      for (const JStr &s : kv.second) {
+        auto it = id_index.find(s);
+        if (it != id_index.end() && std::find(ids.begin(), ids.end(), it->second) == ids.end()) ids.push_back(it->second);
+      }
+      const mmp_model_row row = models[kv.first];
+      set_model(kv.first, &row, ids.data(), (int32_t)ids.size(), true);
+    }
+    json_resolved_gen = inst_gen;
+  }
 
   int32_t set_types_json(const char *json);  // defined after TcJson
   int32_t upsert_instance_json(int32_t idx, const char *id, const char *json, int32_t active);  // defined after RecordJson
@@ -370,6 +405,12 @@ class HostState {
     s.type_slot_hp.resize(s.type_slot.size());
     for (size_t t = 0; t < s.type_slot.size(); t++)
       s.type_slot_hp[t] = (uint16_t)(s.type_slot[t] | (s.has_pref[s.type_slot[t]] ? 0x8000u : 0u));
+    s.part_type_ids.assign(s.part_types.size(), {});
+    for (size_t p = 0; p < s.part_types.size(); p++)
+      for (const std::string &t : s.part_types[p]) {
+        auto it = type_ids.find(t);
+        if (it != type_ids.end()) s.part_type_ids[p].push_back(it->second);
+      }
     s.candx_before.assign((size_t)s.n_slots, 0);
     for (int32_t sl = 0; sl < s.n_slots; sl++)
       for (int32_t w = 0; w < s.word_lo; w++) s.candx_before[sl] += __builtin_popcount(s.candx[(size_t)sl * RW + w]);
@@ -799,26 +840,30 @@ inline int32_t HostState::set_model_json(int32_t m, const char *json, int32_t si
   std::vector<std::string> loaded, failed;
   int64_t lu = 0;
   if (!RecordJson(json).model(type, loaded, failed, lu, e)) { err = "model record json: " + e; return MMP_E_ARG; }
-  // instance ids -> indices through the ingest dictionary; an id that names no present instance cannot be a candidate
-  // either, so leaving it out of the exclusion row changes nothing (MM:4735-4743 tests membership by id)
-  std::unordered_map<JStr, int32_t> by_id;  // std::hash<std::u16string>
-  for (int32_t i = 0; i < cfg.max_instances; i++)
-    if (inst[i].present) by_id.emplace(inst[i].id, i);
+  // the ids are kept as the record names them and resolved against the id table now AND at every commit after the table
+  // changed (resolve_json_models), so a model record may arrive before the records of the instances it names
+  std::vector<JStr> raw;
   std::vector<int32_t> ids;
   for (const auto *lst : {&loaded, &failed})
     for (const auto &s8 : *lst) {
-      auto it = by_id.find(utf8_to_utf16(s8.c_str()));
-      if (it != by_id.end() && std::find(ids.begin(), ids.end(), it->second) == ids.end()) ids.push_back(it->second);
+      JStr j = utf8_to_utf16(s8.c_str());
+      if (std::find(raw.begin(), raw.end(), j) != raw.end()) continue;
+      auto it = id_index.find(j);
+      if (it != id_index.end() && std::find(ids.begin(), ids.end(), it->second) == ids.end()) ids.push_back(it->second);
+      raw.push_back(std::move(j));
     }
   mmp_model_row row{};
   row.last_used = lu;
   row.size_units = size_units;
-  const int32_t tid = type.empty() ? 0 : intern_type(type);
+  // a record without "type" is built by the jackson constructor with DEFAULT_TYPE (MR:117-130)
+  const int32_t tid = intern_type(type.empty() ? std::string("NLCLASSIFIER") : type);
   if (tid < 0) { err = "more than 65534 model types"; return MMP_E_ARG; }
   row.type_id = (uint16_t)tid;
   row.copy_count = (uint8_t)std::min<size_t>(255, loaded.size());
   row.fail_count = (uint8_t)std::min<size_t>(255, failed.size());
-  return set_model(m, &row, ids.data(), (int32_t)ids.size());
+  const int32_t rc = set_model(m, &row, ids.data(), (int32_t)ids.size(), true);
+  if (rc == MMP_OK) { if (raw.empty()) json_ids.erase(m); else json_ids[m] = std::move(raw); }
+  return rc;
 }
 
 inline int32_t HostState::set_types_json(const char *json) {

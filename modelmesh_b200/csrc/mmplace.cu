@@ -9,8 +9,9 @@
 //   rows      [n_ranks] RankRow 32 B      per-rank instance columns the walk reads (lru, remaining, count, rpm, idx)
 //   csum/lsum [row_words]                 per-32-rank min/max of count / lruTime (threshold searches skip whole words)
 //   rank_of   [max_instances] i32, models [n_models] mmp_model_row 24 B, type_slot [n_type_ids] u16
-// Kernels: k_build_bitmap / k_build_bitmap_ovf (commit), k_place<NWL,K,WARPS> (one warp per decision, TMA-staged rows),
-//          k_stats, k_reaper_*, k_lru_apply (see below).
+// Kernels: k_place_lanes<WARPS> (the production scoring kernel: one decision per lane, 32-row TMA landing stages shared by
+//          the block's warps, lock-step voted walks), k_place<...> (cooperative tiles: traced calls / very wide rows),
+//          k_build_bitmap* (commit), k_shard_* (instance-shard combine), k_stats, k_reaper_*, k_lru_apply (scan_kernels.cuh).
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
@@ -881,8 +882,10 @@ static cudaError_t launch_place(mmp_fleet *f, const PlaceArgs &a, cudaStream_t s
 // d_in/d_out are device buffers; every rank is given the same batch and ends with the same results.
 // ---------------------------------------------------------------------------------------------------------------
 static int32_t place_sharded(mmp_fleet *f, PlaceCtx *c, const DeviceSnapshot &ds, const mmp_decision_in *d_in, int32_t n,
-                             const FreshRow *d_fresh, int32_t n_fresh, const int32_t *d_extra, mmp_decision_out *d_out,
+                             const FreshRow *d_fresh, int32_t n_fresh, const int32_t *d_extra, int32_t n_extra, mmp_decision_out *d_out,
                              int64_t now_ms, uint64_t seed, cudaStream_t st) {
+  SnapshotView vw = ds.view;
+  vw.n_extra = n_extra;  // per call: bounds of the decisions' extra[] slices (checked on the device, prepare_ctx_a)
   if (!f->comm) { g_err = "instance-sharded fleet is not connected (mmp_shard_connect)"; return MMP_E_STATE; }
   NcclApi &nc = nccl_api();
   std::lock_guard<std::mutex> g(f->comm_mu);
@@ -903,7 +906,7 @@ static int32_t place_sharded(mmp_fleet *f, PlaceCtx *c, const DeviceSnapshot &ds
   int k = 0;
   for (int32_t lo = 0; lo < n; lo += chunk, k++) {
     const int32_t cnt = std::min(chunk, n - lo);
-    PlaceArgs a{ds.view, d_in + lo, cnt, d_fresh, n_fresh, d_extra, d_out + lo, nullptr, nullptr, now_ms, seed, f->id_base.load() + (uint64_t)lo};
+    PlaceArgs a{vw, d_in + lo, cnt, d_fresh, n_fresh, d_extra, d_out + lo, nullptr, nullptr, now_ms, seed, f->id_base.load() + (uint64_t)lo};
     a.emit_keys = 1;
     CK(launch_place(f, a, st));
     cudaStream_t cs = K > 1 ? side : st;
@@ -936,7 +939,7 @@ static int32_t place_sharded(mmp_fleet *f, PlaceCtx *c, const DeviceSnapshot &ds
   CK(c->d_in_open.ensure((size_t)n_open * sizeof(mmp_decision_in)));
   CK(c->d_out_open.ensure((size_t)n_open * sizeof(mmp_decision_out)));
   const int pack_blocks = (int)std::min<size_t>(((size_t)n_open * ST + 255) / 256, (size_t)f->sm_count * 8);
-  k_shard_pack<<<std::max(pack_blocks, 1), 256, 0, st>>>(ds.view, d_in, c->d_open_idx.as<int32_t>(), n_open, c->d_blocks.as<uint32_t>(),
+  k_shard_pack<<<std::max(pack_blocks, 1), 256, 0, st>>>(vw, d_in, c->d_open_idx.as<int32_t>(), n_open, c->d_blocks.as<uint32_t>(),
                                                          c->d_in_open.as<mmp_decision_in>());
   CK(cudaGetLastError());
   NK(nc.AllGather(c->d_blocks.p, c->d_gathered.p, (size_t)n_open * ST, ncclUint32, f->comm, st));
@@ -944,7 +947,7 @@ static int32_t place_sharded(mmp_fleet *f, PlaceCtx *c, const DeviceSnapshot &ds
   k_shard_assemble<<<std::max(asm_blocks, 1), 256, 0, st>>>(c->d_gathered.as<uint32_t>(), n_open, ST, G, NW, c->d_rows.as<uint32_t>());
   CK(cudaGetLastError());
   f->launches += 2;
-  SnapshotView whole = ds.view;
+  SnapshotView whole = vw;
   whole.excl = c->d_rows.as<uint32_t>();
   whole.excl_stride = NW; whole.word_lo = 0; whole.word_hi = NW;
   PlaceArgs b{whole, c->d_in_open.as<mmp_decision_in>(), n_open, d_fresh, n_fresh, d_extra, c->d_out_open.as<mmp_decision_out>(),
@@ -1107,6 +1110,7 @@ int32_t mmp_fleet_commit(mmp_fleet *f) {
   int32_t rc = set_device(f);
   if (rc < 0) return rc;
   DeviceSnapshot &ds = f->snaps[1 - f->cur];
+  f->hs.resolve_json_models();
   if (const char *m = f->hs.build_snapshot(ds.host)) { g_err = m; return MMP_E_ARG; }
   const HostSnapshot &h = ds.host;
   cudaStream_t st = f->commit_stream;
@@ -1189,6 +1193,8 @@ static int32_t place_impl(mmp_fleet *f, const mmp_decision_in *in, int32_t n, co
   const int RW = ds.view.row_words;
   cudaStream_t st = c->stream;
   const bool traced = trace || cand_mask;
+  SnapshotView vw = ds.view;
+  vw.n_extra = n_extra;  // per call: the device checks every decision's extra[] slice against it (prepare_ctx_a)
   if (f->hs.cfg.shard_count > 1 || (f->comm && !traced)) {  // instance-sharded: keys, one all-reduce(min), decode (+ row gather for open walks)
     if (traced) { g_err = "traces are not available on an instance-sharded fleet"; return MMP_E_STATE; }
     CK(c->d_in.ensure((size_t)n * sizeof(mmp_decision_in)));
@@ -1198,7 +1204,7 @@ static int32_t place_impl(mmp_fleet *f, const mmp_decision_in *in, int32_t n, co
     if (n_fresh) CK(cudaMemcpyAsync(c->d_fresh.p, c->fresh_host.data(), (size_t)n_fresh * sizeof(FreshRow), cudaMemcpyHostToDevice, st));
     if (n_extra) CK(cudaMemcpyAsync(c->d_extra.p, extra, (size_t)n_extra * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(c->d_in.p, in, (size_t)n * sizeof(mmp_decision_in), cudaMemcpyHostToDevice, st));
-    int32_t rcs = place_sharded(f, c, ds, c->d_in.as<mmp_decision_in>(), n, c->d_fresh.as<FreshRow>(), n_fresh, c->d_extra.as<int32_t>(),
+    int32_t rcs = place_sharded(f, c, ds, c->d_in.as<mmp_decision_in>(), n, c->d_fresh.as<FreshRow>(), n_fresh, c->d_extra.as<int32_t>(), n_extra,
                                 c->d_out.as<mmp_decision_out>(), now_ms, seed, st);
     if (rcs < 0) return rcs;
     CK(cudaMemcpyAsync(out, c->d_out.p, (size_t)n * sizeof(mmp_decision_out), cudaMemcpyDeviceToHost, st));
@@ -1216,7 +1222,7 @@ static int32_t place_impl(mmp_fleet *f, const mmp_decision_in *in, int32_t n, co
       memcpy(h + o_in, in, (size_t)n * sizeof(mmp_decision_in));
       if (n_fresh) memcpy(h + o_fr, c->fresh_host.data(), (size_t)n_fresh * sizeof(FreshRow));
       if (n_extra) memcpy(h + o_ex, extra, (size_t)n_extra * 4);
-      PlaceArgs a{ds.view, (const mmp_decision_in *)(dbase + o_in), n, (const FreshRow *)(dbase + o_fr), n_fresh,
+      PlaceArgs a{vw, (const mmp_decision_in *)(dbase + o_in), n, (const FreshRow *)(dbase + o_fr), n_fresh,
                   (const int32_t *)(dbase + o_ex), (mmp_decision_out *)(dbase + o_out), nullptr, nullptr, now_ms, seed, f->id_base.load()};
       CK(launch_place(f, a, st));
       CK(cudaStreamSynchronize(st));
@@ -1243,7 +1249,7 @@ static int32_t place_impl(mmp_fleet *f, const mmp_decision_in *in, int32_t n, co
       const int32_t cnt = std::min(CHUNK, n - lo);
       cudaStream_t ps = c->pipe[ci % PlaceCtx::NPIPE];
       CK(cudaMemcpyAsync(c->d_in.as<mmp_decision_in>() + lo, in + lo, (size_t)cnt * sizeof(mmp_decision_in), cudaMemcpyHostToDevice, ps));
-      PlaceArgs a{ds.view, c->d_in.as<mmp_decision_in>() + lo, cnt, c->d_fresh.as<FreshRow>(), n_fresh, c->d_extra.as<int32_t>(),
+      PlaceArgs a{vw, c->d_in.as<mmp_decision_in>() + lo, cnt, c->d_fresh.as<FreshRow>(), n_fresh, c->d_extra.as<int32_t>(),
                   c->d_out.as<mmp_decision_out>() + lo, nullptr, nullptr, now_ms, seed, f->id_base.load() + (uint64_t)lo};
       CK(launch_place(f, a, ps));
       CK(cudaMemcpyAsync(out + lo, c->d_out.as<mmp_decision_out>() + lo, (size_t)cnt * sizeof(mmp_decision_out), cudaMemcpyDeviceToHost, ps));
@@ -1253,7 +1259,7 @@ static int32_t place_impl(mmp_fleet *f, const mmp_decision_in *in, int32_t n, co
   }
   CK(cudaMemcpyAsync(c->d_in.p, in, (size_t)n * sizeof(mmp_decision_in), cudaMemcpyHostToDevice, st));
   if (cand_mask) CK(cudaMemsetAsync(c->d_cand.p, 0, (size_t)n * 2 * RW * 4, st));
-  PlaceArgs a{ds.view, c->d_in.as<mmp_decision_in>(), n, c->d_fresh.as<FreshRow>(), n_fresh, c->d_extra.as<int32_t>(),
+  PlaceArgs a{vw, c->d_in.as<mmp_decision_in>(), n, c->d_fresh.as<FreshRow>(), n_fresh, c->d_extra.as<int32_t>(),
               c->d_out.as<mmp_decision_out>(), trace ? c->d_trace.as<mmp_decision_trace>() : nullptr,
               cand_mask ? c->d_cand.as<uint32_t>() : nullptr, now_ms, seed, f->id_base.load()};
   CK(launch_place(f, a, st));
@@ -1310,7 +1316,7 @@ int32_t mmp_place_sweep(mmp_fleet *f, int32_t first_model, int32_t n, const int3
   f->launches++;
   CK(cudaGetLastError());
   if (f->hs.cfg.shard_count > 1 || f->comm) {
-    int32_t rcs = place_sharded(f, c, ds, c->d_in.as<mmp_decision_in>(), n, c->d_fresh.as<FreshRow>(), 0, c->d_extra.as<int32_t>(),
+    int32_t rcs = place_sharded(f, c, ds, c->d_in.as<mmp_decision_in>(), n, c->d_fresh.as<FreshRow>(), 0, c->d_extra.as<int32_t>(), 0,
                                 c->d_out.as<mmp_decision_out>(), now_ms, seed, st);
     if (rcs < 0) return rcs;
     CK(cudaMemcpyAsync(out, c->d_out.p, (size_t)n * sizeof(mmp_decision_out), cudaMemcpyDeviceToHost, st));
@@ -1351,7 +1357,7 @@ int32_t mmp_place_batch_device(mmp_fleet *f, const void *d_in, int32_t n, void *
               (mmp_decision_out *)d_out, nullptr, nullptr, now_ms, seed, f->id_base.load()};
   CK(cudaEventRecord(c->e0, c->stream));
   if (f->hs.cfg.shard_count > 1 || f->comm) {
-    int32_t rcs = place_sharded(f, c, ds, (const mmp_decision_in *)d_in, n, c->d_fresh.as<FreshRow>(), 0, c->d_extra.as<int32_t>(),
+    int32_t rcs = place_sharded(f, c, ds, (const mmp_decision_in *)d_in, n, c->d_fresh.as<FreshRow>(), 0, c->d_extra.as<int32_t>(), 0,
                                 (mmp_decision_out *)d_out, now_ms, seed, c->stream);
     if (rcs < 0) return rcs;
   } else CK(launch_place(f, a, c->stream));

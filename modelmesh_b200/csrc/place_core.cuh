@@ -65,6 +65,7 @@ struct SnapshotView {  // pointers into HBM (or host vectors in the CPU harness)
   // instance sharding: this process holds words [word_lo, word_hi) of every exclusion row, stored at a
   // stride of excl_stride words; [0, row_words) and row_words when the fleet is not sharded
   int32_t word_lo, word_hi, excl_stride, n_slots;
+  int32_t n_extra, pad_;       // PER CALL (set by the entry point, not by commit): number of entries in the call's extra[] table
   int64_t min_space;
   const uint32_t *excl;        // [n_models][excl_stride] loaded ∪ failed, bit = rank (word 0 of a stored row = row word word_lo)
   const uint32_t *cand;        // [n_slots][row_words]  allowed(type) ∧ active
@@ -451,6 +452,9 @@ MMP_HD bool ctx_has_pref(const DecisionCtx &c) { return (c.slot >> 16) & 1; }
 struct CtxA { mmp_model_row mr; int32_t self_rank; int32_t ok; };
 MMP_HD void prepare_ctx_a(const SnapshotView &s, const mmp_decision_in &d, CtxA &a) {
   a.ok = !(d.model < 0 || d.model >= s.n_models || d.self < 0 || d.self >= s.max_instances);
+  // the decision's slice of extra[] must lie inside the table the caller passed (at most 16 entries, MMP_MAX_EXTRA):
+  // anything else is a malformed decision (MMP_TARGET_INVALID), never an out-of-bounds read
+  if (d.extra_n < 0 || d.extra_n > 16 || (d.extra_n > 0 && (d.extra_off < 0 || (int64_t)d.extra_off + d.extra_n > (int64_t)s.n_extra))) a.ok = 0;
   a.self_rank = -1;
   a.mr.last_used = 0; a.mr.size_units = 0; a.mr.rpm = 0; a.mr.type_id = 0; a.mr.copy_count = 0; a.mr.fail_count = 0; a.mr.reserved = 0;
   if (a.ok) { a.mr = s.models[d.model]; a.self_rank = s.rank_of[d.self]; }

@@ -171,11 +171,9 @@ static int32_t reaper_impl(mmp_fleet *f, int32_t partition, int64_t now, uint8_t
   if (total_count <= 0) return 0;
   // prohibited types of this partition -> per type id flag
   std::vector<uint8_t> excl(h.type_slot.size(), 0);
-  if (partition >= 0)
-    for (const std::string &t : h.part_types[partition]) {
-      auto it = f->hs.type_ids.find(t);
-      if (it != f->hs.type_ids.end() && it->second < (int32_t)excl.size()) excl[it->second] = 1;
-    }
+  if (partition >= 0)  // ids as interned when this epoch was committed: the ingest-side name table is never read here
+    for (int32_t tid : h.part_type_ids[partition])
+      if (tid >= 0 && tid < (int32_t)excl.size()) excl[tid] = 1;
   const int nm = ds.n_models;
   if (nm == 0) return 0;
   PlaceCtx *c = acquire_ctx(f);

@@ -83,6 +83,7 @@ int32_t mmp_models_bulk(mmp_fleet *f, int32_t first, int32_t n, const mmp_model_
 }
 
 int32_t mmp_fleet_commit(mmp_fleet *f) {
+  f->hs.resolve_json_models();
   if (const char *m = f->hs.build_snapshot(f->snap)) { g_err = m; return MMP_E_ARG; }
   const int RW = f->snap.row_words;
   const int32_t nm = f->hs.n_models_used;
@@ -118,10 +119,11 @@ static SnapshotView make_view(mmp_fleet *f) {
 }
 
 int32_t mmp_place_batch_trace(mmp_fleet *f, const mmp_decision_in *in, int32_t n, const mmp_instance_row *fresh, int32_t n_fresh,
-                              const int32_t *extra, int32_t /*n_extra*/, mmp_decision_out *out, mmp_decision_trace *trace,
+                              const int32_t *extra, int32_t n_extra, mmp_decision_out *out, mmp_decision_trace *trace,
                               uint32_t *cand_mask, int64_t now_ms, uint64_t seed) {
   if (f->epoch == 0) { g_err = "no committed snapshot"; return MMP_E_EPOCH; }
   SnapshotView v = make_view(f);
+  v.n_extra = n_extra;
   std::vector<FreshRow> fr((size_t)(n_fresh > 0 ? n_fresh : 0));
   for (int32_t i = 0; i < n_fresh; i++) {
     if (const char *m = HostState::validate_row(fresh[i])) { g_err = m; return MMP_E_ARG; }

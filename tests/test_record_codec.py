@@ -6,6 +6,7 @@ import json
 import numpy as np
 import pytest
 
+from modelmesh_b200 import _lib as L
 from modelmesh_b200._lib import MODEL_ROW
 from modelmesh_b200.fleet import Fleet, MmpError
 from modelmesh_b200.synth import load_into_fleet, make_decisions, make_fleet
@@ -124,3 +125,85 @@ def test_json_readers_survive_garbage(emul_lib):
     assert calls == 12000
     f._ck(lib.mmp_types_set_json(f.h, valid[2]))
     f.commit()  # the host state is still consistent
+
+
+def _two_pod_fleet(lib):
+    f = Fleet(2560, 600000, 2560, 8, 8, lib=lib)
+    rec = json.dumps({"lruTime": LONG_MAX, "cap": 25600, "used": 100, "lThreads": 8}).encode()
+    return f, rec
+
+
+def _place(f, model, self_idx=0):
+    d = np.zeros(1, dtype=L.DECISION_IN)
+    d["model"], d["self"], d["fresh"], d["last_used"] = model, self_idx, -1, 1
+    return f.place_batch(d, 1_760_000_000_000, 1)[0]
+
+
+def test_model_record_may_arrive_before_its_instances(emul_lib):
+    """the two KV listeners deliver in any order.  A model record that names an instance
+    not yet in the table keeps the id and the exclusion edge appears at the first commit after the instance registers;
+    an instance that re-registers under another index keeps its edges (membership is by id, MM:4735-4743)."""
+    lib = emul_lib
+    f = Fleet(2560, 600000, 2560, 8, 8, lib=lib)
+    rec = lambda used, cap=25600: json.dumps({"lruTime": LONG_MAX, "cap": cap, "used": used, "lThreads": 8}).encode()
+    # the caller (pod-c, index 2) is full and not in the service-instance list: never a candidate, and its fresh record
+    # makes every non-self candidate fail the walk test (N2), so the answer is always the first filtered entry
+    f._ck(lib.mmp_instance_upsert_json(f.h, 2, b"pod-c", rec(25600), 0))
+    f._ck(lib.mmp_model_upsert_json(f.h, 0, json.dumps({"type": "t", "instanceIds": {"pod-b": 5}, "lu": 9}).encode(), 256))
+    f._ck(lib.mmp_model_upsert_json(f.h, 1, json.dumps({"type": "t", "lu": 9}).encode(), 256))
+    f._ck(lib.mmp_instance_upsert_json(f.h, 0, b"pod-a", rec(20000), 1))
+    f.commit()
+    assert _place(f, 0, 2)["target"] == 0  # only pod-a can take it
+    f._ck(lib.mmp_instance_upsert_json(f.h, 1, b"pod-b", rec(0, 51200), 1))
+    f.commit()
+    assert list(f.cluster_order())[:2] == [1, 0]
+    assert _place(f, 1, 2)["target"] == 1  # pod-b wins on free space ...
+    assert _place(f, 0, 2)["target"] == 0  # ... unless the model is already loaded there: the edge named by id is now resolved
+    # pod-b re-registers under index 5
+    f.instance_remove(1)
+    f._ck(lib.mmp_instance_upsert_json(f.h, 5, b"pod-b", rec(0, 51200), 1))
+    f.commit()
+    assert _place(f, 1, 2)["target"] == 5
+    assert _place(f, 0, 2)["target"] == 0
+    # an index-based upsert replaces the record held by id
+    row = np.zeros(1, dtype=L.MODEL_ROW)
+    f.model_upsert(0, row[0], [])
+    f.commit()
+    assert _place(f, 0, 2)["target"] == 5
+
+
+def test_absent_type_is_nlclassifier(emul_lib):
+    """a ModelRecord without "type" is DEFAULT_TYPE "NLCLASSIFIER" (MR:117-130), not an unconstrained type."""
+    lib = emul_lib
+    f = Fleet(2560, 600000, 2560, 8, 8, lib=lib)
+    f.types_set_json(json.dumps({"NLCLASSIFIER": {"required": ["gpu"]}}))
+    base = {"lruTime": LONG_MAX, "cap": 25600, "used": 0, "lThreads": 8}
+    f._ck(lib.mmp_instance_upsert_json(f.h, 0, b"pod-a", json.dumps(base).encode(), 1))
+    f._ck(lib.mmp_instance_upsert_json(f.h, 1, b"pod-b", json.dumps(dict(base, labels=["gpu"], used=20000)).encode(), 1))
+    f._ck(lib.mmp_model_upsert_json(f.h, 0, b'{"lu": 5}', 256))
+    f._ck(lib.mmp_model_upsert_json(f.h, 1, b'{"type": "other", "lu": 5}', 256))
+    f.commit()
+    assert _place(f, 0)["target"] == 1             # legacy record: only the labelled pod is allowed
+    assert _place(f, 1)["target"] == L.TARGET_SELF  # unconstrained type: the empty caller pod-a (pod-b is too full to be shortlisted)
+
+
+def test_extra_slice_out_of_bounds_is_invalid(emul_lib):
+    """a decision whose extra[] slice does not lie inside the table passed with the call is answered
+    MMP_TARGET_INVALID; the table is never read out of bounds."""
+    lib = emul_lib
+    f, rec = _two_pod_fleet(lib)
+    for i, name in enumerate((b"pod-a", b"pod-b", b"pod-c")):
+        f._ck(lib.mmp_instance_upsert_json(f.h, i, name, rec, 1))
+    f._ck(lib.mmp_model_upsert_json(f.h, 0, b'{"lu": 5}', 256))
+    f.commit()
+    d = np.zeros(6, dtype=L.DECISION_IN)
+    d["model"], d["self"], d["fresh"], d["last_used"] = 0, 0, -1, 1
+    d["extra_off"] = [0, 1, 2, -1, 0, 1 << 30]
+    d["extra_n"] = [2, 1, 1, 1, 17, 1]
+    extra = np.asarray([1, 2], dtype=np.int32)
+    out = f.place_batch(d, 1_760_000_000_000, 1, extra=extra)
+    assert list(out["target"] == L.TARGET_INVALID) == [False, False, True, True, True, True]
+    assert out["target"][0] == L.TARGET_SELF  # both other pods excluded
+    d["extra_n"][:] = 1
+    d["extra_off"][:] = 0
+    assert np.all(f.place_batch(d, 1_760_000_000_000, 1)["target"] == L.TARGET_INVALID)  # no table at all
