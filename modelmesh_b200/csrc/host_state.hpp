@@ -102,6 +102,10 @@ struct HostSnapshot {
   // instance sharding: the row words this process holds and the stride of a stored row
   int32_t word_lo = 0, word_hi = 0, excl_stride = 0;
   std::vector<int32_t> candx_before;  // [n_slots] members of candx at ranks below word_lo*32 (entries that beat this shard)
+  // compressed word lists (LaneTables, place_core.cuh): per slot the row words of [word_lo, word_hi) in which the candidate
+  // mask the lane routine reads (candx when a replicaset is flagged, else cand) has any bit, ascending
+  std::vector<uint16_t> nzw;          // [n_slots][row_words]
+  std::vector<int32_t> nz_n;          // [n_slots]
   std::vector<int32_t> part_of_rank;  // [n_ranks] partition (PTS) id, 0 when no type constraints
   std::vector<std::vector<std::string>> part_types;  // prohibited type names per partition id
   std::vector<std::vector<int32_t>> part_type_ids;   // the same as type ids of THIS epoch (readers never touch the ingest-side name table)
@@ -405,6 +409,15 @@ class HostState {
     s.type_slot_hp.resize(s.type_slot.size());
     for (size_t t = 0; t < s.type_slot.size(); t++)
       s.type_slot_hp[t] = (uint16_t)(s.type_slot[t] | (s.has_pref[s.type_slot[t]] ? 0x8000u : 0u));
+    s.nzw.assign((size_t)s.n_slots * RW, 0xffff);
+    s.nz_n.assign((size_t)s.n_slots, 0);
+    for (int32_t sl = 0; sl < s.n_slots; sl++) {
+      const uint32_t *cx = (s.any_rs ? s.candx.data() : s.cand.data()) + (size_t)sl * RW;
+      int32_t k = 0;
+      for (int32_t w = s.word_lo; w < s.word_hi; w++)
+        if (cx[w]) s.nzw[(size_t)sl * RW + k++] = (uint16_t)w;
+      s.nz_n[sl] = k;
+    }
     s.part_type_ids.assign(s.part_types.size(), {});
     for (size_t p = 0; p < s.part_types.size(); p++)
       for (const std::string &t : s.part_types[p]) {

@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_place(const SnapshotView s
       mmp_decision_in d;
       d.model = a.x; d.self = a.y; d.last_used = (int64_t)(((uint64_t)(uint32_t)a.w << 32) | (uint32_t)a.z);
       d.flags = (uint32_t)b.x; d.fresh = b.y; d.extra_off = b.z; d.extra_n = b.w;
-      prepare_ctx(s, d, fresh, n_fresh, cn);
+      prepare_ctx(s, d, fresh, n_fresh, extra, cn);
     }
     dst[lane] = cn;
   };
@@ -315,28 +315,21 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_place(const SnapshotView s
 // The stages keep ~NS x 41 KB per SM in flight from HBM independently of how many warps are computing, and the
 // per-decision instruction cost is ~85 warp instructions instead of ~450 for a cooperative tile (ncu, C3 sweep).
 // ---------------------------------------------------------------------------------------------------------------
-static constexpr int LANE_WIN = 14;     // row words copied out of the landing stage per decision (448 ranks)
-static constexpr int LANE_BUDGET = 64;  // row-word visits a lane may spend before handing its decision to the warp
-static constexpr int LANE_SLOTS = 64;   // type-constraint mask slots whose window words are kept in shared memory
+static constexpr int LANE_WIN = 14;     // row words copied out of the landing stage per decision: the first LANE_WIN words of the
+                                        // decision's compressed word list (LaneTables::nzw); later steps read the row from L2
+static constexpr int LANE_BUDGET = 96;  // walk steps a lane may spend before handing its decision to the whole warp
 struct LaneLayout {
   uint32_t row_bytes, stride, stage_bytes, ns, warps;
   uint32_t off_bar, off_busy, off_uses, off_warp, per_warp;
-  uint32_t off_cx, off_p, off_full, off_csum, off_count, off_rows;  // the front (window) part of the lane tables
   size_t total;
-  __host__ __device__ LaneLayout(int row_words, int ns_, int warps_, bool front) {
+  __host__ __device__ LaneLayout(int row_words, int ns_, int warps_) {
     row_bytes = (uint32_t)row_words * 4u; stride = row_bytes + 16u;  // + 16: lanes copying their windows out spread over the banks
     stage_bytes = (32u * stride + 127u) / 128u * 128u;
     ns = (uint32_t)ns_; warps = (uint32_t)warps_;
     off_bar = ns * stage_bytes; off_busy = off_bar + ns * 8u; off_uses = off_busy + ns * 4u;
     off_warp = (off_uses + ns * 4u + 127u) / 128u * 128u;
     per_warp = 32u * (LANE_WIN + 1) * 4u + (uint32_t)((sizeof(DecisionCtx) + 15) / 16 * 16);  // window rows are LANE_WIN + 1 words apart: bank-conflict free
-    off_cx = (off_warp + warps * per_warp + 15u) / 16u * 16u;
-    off_p = off_cx + LANE_SLOTS * LANE_WIN * 4u;
-    off_full = off_p + LANE_SLOTS * LANE_WIN * 4u;
-    off_csum = off_full + ((LANE_WIN * 4u + 7u) / 8u) * 8u;
-    off_count = (off_csum + LANE_WIN * 8u + 15u) / 16u * 16u;
-    off_rows = off_count + LANE_WIN * 32u * 4u;
-    total = front ? (size_t)off_rows + (size_t)LANE_WIN * 32u * sizeof(RankRow) : (size_t)off_cx;
+    total = (size_t)off_warp + (size_t)warps * per_warp;
   }
 };
 
@@ -349,11 +342,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotVie
                                                                const FreshRow *__restrict__ fresh, int n_fresh,
                                                                const int32_t *__restrict__ extra, mmp_decision_out *__restrict__ out,
                                                                int64_t now, uint64_t seed, uint64_t id_base, int ns,
-                                                               int front_tables, int mode, unsigned long long *__restrict__ dbg,
-                                                               int emit_keys, int shard_rank, const int32_t *__restrict__ orig_id) {
+                                                               int mode, unsigned long long *__restrict__ dbg,
+                                                               int emit_keys, int shard_rank, const int32_t *__restrict__ orig_id, int budget) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int RW = s.excl_stride;  // words per stored row (the whole row unless the fleet is instance-sharded)
-  const LaneLayout lay(RW, ns, WARPS, front_tables != 0);
+  const LaneLayout lay(RW, ns, WARPS);
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + lay.off_bar);
   int *ticket = reinterpret_cast<int *>(smem_raw + lay.off_busy);               // next stage ticket of this block
@@ -366,38 +359,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotVie
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   const int nb = (n + 31) >> 5;
-  const uint32_t win_words = (uint32_t)min(LANE_WIN, min(RW, s.word_hi - s.word_lo));
-  // ---- the window part of the per-word / per-rank tables, once per block (with the SM's shared memory given to the
-  // landing stages the L1 is too small to hold them, and the lane routine's gathers would be L2 round trips) ----
-  uint32_t *f_cx = reinterpret_cast<uint32_t *>(smem_raw + lay.off_cx), *f_p = reinterpret_cast<uint32_t *>(smem_raw + lay.off_p);
-  uint32_t *f_full = reinterpret_cast<uint32_t *>(smem_raw + lay.off_full);
-  WordSumI *f_csum = reinterpret_cast<WordSumI *>(smem_raw + lay.off_csum);
-  int32_t *f_count = reinterpret_cast<int32_t *>(smem_raw + lay.off_count);
-  RankRow *f_rows = reinterpret_cast<RankRow *>(smem_raw + lay.off_rows);
-  const int WS = s.word_lo;
-  const bool front = front_tables != 0 && nb >= 64;  // tiny launches (the B = 1 latency path) read the snapshot directly
-  if (front) {
-    const int nsl = min(s.n_slots, LANE_SLOTS);
-    const uint32_t *gcx = s.any_rs ? s.candx : s.cand;
-    for (int i = threadIdx.x; i < nsl * LANE_WIN; i += blockDim.x) {
-      const int sl = i / LANE_WIN, w = i - sl * LANE_WIN;
-      const bool in = (uint32_t)w < win_words;
-      f_cx[i] = in ? gcx[(size_t)sl * s.row_words + WS + w] : 0u;
-      f_p[i] = in ? s.pref[(size_t)sl * s.row_words + WS + w] : 0u;
-    }
-    for (int w = threadIdx.x; w < LANE_WIN; w += blockDim.x) {
-      const bool in = (uint32_t)w < win_words;
-      f_full[w] = in ? s.full[WS + w] : 0u;
-      f_csum[w] = in ? s.csum[WS + w] : WordSumI{0, 0};
-    }
-    for (int i = threadIdx.x; i < LANE_WIN * 32; i += blockDim.x) {
-      const int r = WS * 32 + i;
-      const bool in = (uint32_t)(i >> 5) < win_words && r < s.n_ranks;
-      f_count[i] = in ? s.count_col[r] : 0;
-      RankRow z; z.lru = 0; z.rem = 0; z.count = 0; z.rpm = 0; z.idx = -1; z.flags = 0;
-      f_rows[i] = in ? s.rows[r] : z;
-    }
-  }
   __syncthreads();
   // batches of 32 decisions are dealt round-robin to the grid's warps (consecutive batches to the warps of one block)
   const int gw = blockIdx.x * WARPS + wib, nw = gridDim.x * WARPS;
@@ -455,7 +416,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotVie
     c.slot = -2; c.d.model = 0; c.self_rank = -1; c.self_bits = 0; c.self_count = 0;
     bool skip = false;  // instance-sharded, not the first shard: an entry in a lower shard wins, the row is not even read
     if (s.word_lo > 0) {
-      if (valid) { prepare_ctx_b(s, d, ca, fresh, n_fresh, c); skip = shard_cannot_win(s, c, ca.mr.reserved); }
+      if (valid) { prepare_ctx_b(s, d, ca, fresh, n_fresh, extra, c); skip = shard_cannot_win(s, c, ca.mr.reserved); }
     }
     if (valid && !skip) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the previous owner's reads precede this async write
@@ -464,7 +425,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotVie
     } else mbar_arrive(&bars[st]);
     LANE_T(1);
     // ---- the rest of this batch's context while its rows are in flight ----
-    if (s.word_lo == 0 && valid) prepare_ctx_b(s, d, ca, fresh, n_fresh, c);
+    if (s.word_lo == 0 && valid) prepare_ctx_b(s, d, ca, fresh, n_fresh, extra, c);
+    // the compressed word list of the decision's type slot: the first LANE_WIN entries (two 16-byte loads) say which row
+    // words to keep when the stage is handed on
+    const int slot = c.slot >= 0 ? ctx_slot(c) : 0;
+    const LaneTables T = lane_tables_global(s, slot);
+    const uint32_t win_words = min((uint32_t)LANE_WIN, T.nz_n);
+    uint32_t wl[8];  // nzw[0..16) as 8 x 2 u16
+    {
+      const uint4 *np = reinterpret_cast<const uint4 *>(T.nzw);  // rows of nzw are row_words u16 = a multiple of 64 bytes
+      const uint4 n0 = __ldg(np), n1 = __ldg(np + 1);
+      wl[0] = n0.x; wl[1] = n0.y; wl[2] = n0.z; wl[3] = n0.w; wl[4] = n1.x; wl[5] = n1.y; wl[6] = n1.z; wl[7] = n1.w;
+    }
     if (timing && __shfl_xor_sync(0xffffffffu, c.slot ^ (int)c.self_bits, 1) == 0x7fffffff) tsum[2]++;  // consume the gathers before the timestamp
     LANE_T(2);
     while (!mbar_try_wait(&bars[st], parity)) {}
@@ -473,12 +445,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotVie
     uint32_t self_eword = 0;
     {
       uint32_t *w = win + lane * (LANE_WIN + 1);
+      const uint32_t WS_ = (uint32_t)s.word_lo;
+      if (!skip) {
 #pragma unroll
-      for (int j = 0; j < (LANE_WIN + 3) / 4; j++) {
-        if ((uint32_t)(j * 4) < win_words) {
-          const uint4 q = *reinterpret_cast<const uint4 *>(my_row + j * 4);
-          w[j * 4] = q.x; w[j * 4 + 1] = q.y;
-          if (j * 4 + 2 < LANE_WIN) { w[j * 4 + 2] = q.z; w[j * 4 + 3] = q.w; }
+        for (int j = 0; j < LANE_WIN; j++) {
+          const uint32_t wi = (wl[j >> 1] >> ((j & 1) * 16)) & 0xffffu;
+          if ((uint32_t)j < win_words) w[j] = my_row[wi - WS_];
         }
       }
       const int sw = c.self_rank >> 5;
@@ -497,20 +469,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotVie
     LANE_T(5);
     // ---- one decision per lane, the 32 lanes in lockstep ----
     DecideOut o;
-    const int slot = c.slot >= 0 ? ctx_slot(c) : 0;
-    LaneTables T = lane_tables_global(s, slot);
-    if (front) {  // tables indexed by absolute row word / rank: bias the shared-memory copies by the window's first word
-      if (slot < LANE_SLOTS) { T.cx = f_cx + slot * LANE_WIN - WS; T.p = f_p + slot * LANE_WIN - WS; }
-      T.full = f_full - WS; T.csum = f_csum - WS; T.count_col = f_count - WS * 32; T.rows = f_rows - WS * 32;
-    }
     bool handled = true;
     const uint64_t my_id = id_base + (uint64_t)(orig_id ? (valid ? orig_id[b * 32 + lane] : 0) : b * 32 + lane);
     if ((mode & 1) == 0)
-      handled = decide_stream(s, T, c, valid && !skip, win + lane * (LANE_WIN + 1), win_words, self_eword, now, seed, my_id,
-                              WarpVote(), o, LANE_BUDGET);
+      handled = decide_stream(s, T, c, valid && !skip, win + lane * (LANE_WIN + 1), win_words, s.excl + (size_t)m * RW, self_eword,
+                              now, seed, my_id, WarpVote(), o, budget);
     else { o.target = (int32_t)(self_eword & 1u) - 1; o.n_candidates = 0; }  // MMP_LANE_MODE=1: stream-only probe (no decisions)
     // ---- what the lane routine declined: the whole warp redoes it, reading the row from global memory (L2) ----
     uint32_t pending = __ballot_sync(0xffffffffu, valid && !skip && !handled);
+    if (timing && lane == 0 && pending) atomicAdd(&dbg[8], (unsigned long long)__popc(pending));  // decisions redone by the whole warp
     while (pending) {
       const int l = __ffs((int)pending) - 1;
       pending &= pending - 1;
@@ -663,13 +630,13 @@ struct DevBuf {
 
 struct DeviceSnapshot {
   DevBuf excl, cand, candx, pref, has_pref, type_slot, full, rows, rank_of, csum, lsum, models;
-  DevBuf cap_col, lthreads_col, linprog_col, part_of_rank, count_col, cand_before;
+  DevBuf cap_col, lthreads_col, linprog_col, part_of_rank, count_col, cand_before, nzw, nz_n;
   SnapshotView view{};
   HostSnapshot host;  // kept for introspection and the small host-side parts of stats / reaper
   int32_t n_models = 0;
   void release() {
     for (DevBuf *b : {&excl, &cand, &candx, &pref, &has_pref, &type_slot, &full, &rows, &rank_of, &csum, &lsum, &models,
-                      &cap_col, &lthreads_col, &linprog_col, &part_of_rank, &count_col, &cand_before})
+                      &cap_col, &lthreads_col, &linprog_col, &part_of_rank, &count_col, &cand_before, &nzw, &nz_n})
       b->release();
   }
 };
@@ -713,9 +680,8 @@ struct mmp_fleet {
   int lane_stages = 4;          // MMP_LANE_STAGES caps the landing stages per SM (0: as many as fit).  Measured on B200 at 10k
                                 // instances: 3 stages 3.5, 4 stages 4.1-4.3, 5 stages 3.8 G decisions/s (the fifth stage costs the L1
                                 // its 196 -> 228 KB carve-out step and the lane tables no longer stay resident)
-  int lane_front = 0;           // MMP_LANE_FRONT=1: lane tables from a shared-memory copy instead of the snapshot (L1/L2); measured
-                                // slower (3.8 vs 4.2 G/s): the copy pushes shared memory past the 196 KB carve-out step
   int shard_chunks = 1;         // MMP_SHARD_CHUNKS (see place_sharded)
+  int lane_budget = LANE_BUDGET;  // MMP_LANE_BUDGET: walk steps per lane before a decision is handed to the whole warp
   int lane_mode = 0;            // MMP_LANE_MODE=1: stream-only probe (rows staged, no decisions) -- measurement aid, results void
   int lanes = 1;                // MMP_KERNEL=tile selects the cooperative-tile kernel (k_place) instead of k_place_lanes
   int lane_warps = 0;           // warps per block of k_place_lanes (MMP_LANE_WARPS = 8 | 10 | 12 | 14 | 16 | 20); 0 = by launch size
@@ -818,9 +784,9 @@ static cudaError_t launch_place_t(mmp_fleet *f, const PlaceArgs &a, cudaStream_t
 }
 
 // stages x warps for a stored row width: as many 32-row landing stages as fit beside the warps' window buffers
-static bool lanes_geometry(int row_words, int warps, bool front, int &ns) {
+static bool lanes_geometry(int row_words, int warps, int &ns) {
   for (ns = 8; ns >= 2; ns--)
-    if (LaneLayout(row_words, ns, warps, front).total <= (size_t)227 * 1024) return true;
+    if (LaneLayout(row_words, ns, warps).total <= (size_t)227 * 1024) return true;
   return false;
 }
 
@@ -828,7 +794,7 @@ template <int WARPS>
 static cudaError_t launch_place_lanes(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st, int ns) {
   static std::atomic<bool> attr_set[64];  // function attributes are per device
   if (f->lane_stages >= 2 && f->lane_stages < ns) ns = f->lane_stages;
-  const LaneLayout lay(a.s.excl_stride, ns, WARPS, f->lane_front != 0);  // (instance-sharded rows are short: well under half an SM's shared memory)
+  const LaneLayout lay(a.s.excl_stride, ns, WARPS);  // (instance-sharded rows are short: well under half an SM's shared memory)
   auto kern = k_place_lanes<WARPS>;
   if (!attr_set[f->device & 63].load()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -838,8 +804,8 @@ static cudaError_t launch_place_lanes(mmp_fleet *f, const PlaceArgs &a, cudaStre
   const int nb = (a.n + 31) / 32;
   const int grid = std::max(1, std::min((nb + WARPS - 1) / WARPS, f->sm_count));
   kern<<<grid, WARPS * 32, lay.total, st>>>(a.s, a.in, a.n, a.fresh, a.n_fresh, a.extra, a.out, a.now, a.seed, a.id_base, ns,
-                                            f->lane_front, f->lane_mode, f->d_dbg.as<unsigned long long>(), a.emit_keys,
-                                            f->hs.cfg.shard_rank, a.orig_id);
+                                            f->lane_mode, f->d_dbg.as<unsigned long long>(), a.emit_keys,
+                                            f->hs.cfg.shard_rank, a.orig_id, f->lane_budget);
   f->launches++;
   return cudaGetLastError();
 }
@@ -852,13 +818,13 @@ static cudaError_t launch_place(mmp_fleet *f, const PlaceArgs &a, cudaStream_t s
     // warps per block: 12 per SM measured best at 10k instances (8: 3.7-3.8, 12: 4.1-4.3, 16: 3.6-3.9 G decisions/s); picking
     // the width with the fewest rounds of steps for small launches was measured too and made no difference
     const int lw = f->lane_warps ? f->lane_warps : 12;
-    if (lw == 8 && lanes_geometry(a.s.excl_stride, 8, f->lane_front != 0, ns)) return launch_place_lanes<8>(f, a, st, ns);
-    if (lw == 10 && lanes_geometry(a.s.excl_stride, 10, f->lane_front != 0, ns)) return launch_place_lanes<10>(f, a, st, ns);
-    if (lw == 14 && lanes_geometry(a.s.excl_stride, 14, f->lane_front != 0, ns)) return launch_place_lanes<14>(f, a, st, ns);
-    if (lw == 12 && lanes_geometry(a.s.excl_stride, 12, f->lane_front != 0, ns)) return launch_place_lanes<12>(f, a, st, ns);
-    if (lw == 20 && lanes_geometry(a.s.excl_stride, 20, f->lane_front != 0, ns)) return launch_place_lanes<20>(f, a, st, ns);
-    if (lw == 16 && lanes_geometry(a.s.excl_stride, 16, f->lane_front != 0, ns)) return launch_place_lanes<16>(f, a, st, ns);
-    if (lanes_geometry(a.s.excl_stride, 12, f->lane_front != 0, ns)) return launch_place_lanes<12>(f, a, st, ns);
+    if (lw == 8 && lanes_geometry(a.s.excl_stride, 8, ns)) return launch_place_lanes<8>(f, a, st, ns);
+    if (lw == 10 && lanes_geometry(a.s.excl_stride, 10, ns)) return launch_place_lanes<10>(f, a, st, ns);
+    if (lw == 14 && lanes_geometry(a.s.excl_stride, 14, ns)) return launch_place_lanes<14>(f, a, st, ns);
+    if (lw == 12 && lanes_geometry(a.s.excl_stride, 12, ns)) return launch_place_lanes<12>(f, a, st, ns);
+    if (lw == 20 && lanes_geometry(a.s.excl_stride, 20, ns)) return launch_place_lanes<20>(f, a, st, ns);
+    if (lw == 16 && lanes_geometry(a.s.excl_stride, 16, ns)) return launch_place_lanes<16>(f, a, st, ns);
+    if (lanes_geometry(a.s.excl_stride, 12, ns)) return launch_place_lanes<12>(f, a, st, ns);
   }
   // tile width: how many lanes (= window words) resolve one decision; 32/T decisions advance per warp step.
   // The traced variant (parity tests) is a separate, single-decision-per-warp kernel so that the production kernel's
@@ -1029,10 +995,10 @@ int32_t mmp_fleet_create(const mmp_config *cfg, mmp_fleet **out) {
   if (const char *t = getenv("MMP_KERNEL")) f->lanes = strcmp(t, "tile") != 0;
   if (const char *t = getenv("MMP_LANE_WARPS")) { int v = atoi(t); if (v == 8 || v == 10 || v == 12 || v == 14 || v == 16 || v == 20) f->lane_warps = v; }
   if (const char *t = getenv("MMP_LANE_STAGES")) f->lane_stages = atoi(t);
-  if (const char *t = getenv("MMP_LANE_FRONT")) f->lane_front = atoi(t) != 0;
   if (const char *t = getenv("MMP_LANE_MODE")) f->lane_mode = atoi(t);
+  if (const char *t = getenv("MMP_LANE_BUDGET")) { int v = atoi(t); if (v >= 1 && v <= 4096) f->lane_budget = v; }
   if (const char *t = getenv("MMP_SHARD_CHUNKS")) f->shard_chunks = atoi(t);
-  if (f->lane_mode & 2) { CK(f->d_dbg.ensure(64)); CK(cudaMemset(f->d_dbg.p, 0, 64)); }
+  if (f->lane_mode & 2) { CK(f->d_dbg.ensure(128)); CK(cudaMemset(f->d_dbg.p, 0, 128)); }
   if (const char *t = getenv("MMP_TILE")) { int v = atoi(t); if (v == 8 || v == 16 || v == 32) f->tile = v; }
   *out = f.release();
   return MMP_OK;
@@ -1043,12 +1009,12 @@ void mmp_fleet_destroy(mmp_fleet *f) {
   cudaSetDevice(f->device);
   cudaDeviceSynchronize();
   if ((f->lane_mode & 2) && f->d_dbg.p) {  // MMP_LANE_MODE bit 1: print the per-phase averages of k_place_lanes
-    unsigned long long h[8];
+    unsigned long long h[9];
     if (cudaMemcpy(h, f->d_dbg.p, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess && h[7]) {
       static const char *nm[7] = {"wait-for-stage", "issue", "context", "flight-left", "copy-out+release", "requests", "decide+store"};
       fprintf(stderr, "[k_place_lanes phases, cycles per warp step over %llu steps]", h[7]);
       for (int k = 0; k < 7; k++) fprintf(stderr, " %s=%.0f", nm[k], (double)h[k] / (double)h[7]);
-      fprintf(stderr, "\n");
+      fprintf(stderr, " warp-redone decisions=%llu (%.2f%% of %llu)\n", h[8], 100.0 * (double)h[8] / (32.0 * (double)h[7]), 32 * h[7]);
     }
   }
   if (f->comm && nccl_api().ok) { nccl_api().CommDestroy(f->comm); f->comm = nullptr; }
@@ -1125,6 +1091,7 @@ int32_t mmp_fleet_commit(mmp_fleet *f) {
   CK(upload_vec(ds.part_of_rank, h.part_of_rank, st));
   CK(upload_vec(ds.count_col, h.count_col, st));
   CK(upload_vec(ds.cand_before, h.candx_before, st));
+  CK(upload_vec(ds.nzw, h.nzw, st)); CK(upload_vec(ds.nz_n, h.nz_n, st));
   // model rows (each snapshot keeps its own copy so in-flight readers of the other epoch are undisturbed)
   CK(ds.models.ensure((size_t)std::max(nm, 1) * sizeof(mmp_model_row)));
   if (nm) CK(cudaMemcpyAsync(ds.models.p, f->hs.models.data(), (size_t)nm * sizeof(mmp_model_row), cudaMemcpyHostToDevice, st));
@@ -1156,6 +1123,7 @@ int32_t mmp_fleet_commit(mmp_fleet *f) {
   v.any_rs = h.any_rs; v.n_type_ids = (int32_t)h.type_slot.size(); v.min_space = f->hs.cfg.min_space_units;
   v.word_lo = h.word_lo; v.word_hi = h.word_hi; v.excl_stride = ST; v.n_slots = h.n_slots;
   v.count_col = ds.count_col.as<int32_t>(); v.cand_before = ds.cand_before.as<int32_t>();
+  v.nzw = ds.nzw.as<uint16_t>(); v.nz_n = ds.nz_n.as<int32_t>();
   v.excl = ds.excl.as<uint32_t>(); v.cand = ds.cand.as<uint32_t>(); v.pref = ds.pref.as<uint32_t>();
   v.has_pref = ds.has_pref.as<uint8_t>(); v.type_slot = ds.type_slot.as<uint16_t>(); v.candx = ds.candx.as<uint32_t>();
   v.full = ds.full.as<uint32_t>(); v.rows = ds.rows.as<RankRow>(); v.rank_of = ds.rank_of.as<int32_t>();

@@ -80,6 +80,8 @@ struct SnapshotView {  // pointers into HBM (or host vectors in the CPU harness)
   const WordSumL *lsum;        // [row_words]
   const int32_t *count_col;    // [row_words*32] count by rank, 0 past the last rank (exact evaluation of a mixed word)
   const int32_t *cand_before;  // [n_slots] members of candx at ranks below word_lo*32 (instance-sharded; all 0 otherwise)
+  const uint16_t *nzw;         // [n_slots][row_words] compressed word lists (see LaneTables), entries past nz_n[slot] unused
+  const int32_t *nz_n;         // [n_slots]
   const mmp_model_row *models; // [n_models]
 };
 
@@ -443,7 +445,9 @@ struct DecisionCtx {
   int32_t slot;        // type-constraint mask slot | (has_pref << 16); -1 = malformed decision, -2 = absent
   uint32_t self_bits;  // bit 0: self is in the slot's candidate mask (replicaset filter applied); bit 1: in its preferred mask
   int32_t self_count;  // published count of self (IR:39)
+  int32_t xr[4];       // ranks of the first (up to 4) extra excludes, -1 = none / not live: all the lane routine needs of extra[]
 };
+static constexpr int LANE_MAX_EXTRA = 4;  // decisions with more extra excludes go to the cooperative general routine
 MMP_HD int ctx_slot(const DecisionCtx &c) { return c.slot & 0xffff; }
 MMP_HD bool ctx_has_pref(const DecisionCtx &c) { return (c.slot >> 16) & 1; }
 
@@ -460,8 +464,9 @@ MMP_HD void prepare_ctx_a(const SnapshotView &s, const mmp_decision_in &d, CtxA 
   if (a.ok) { a.mr = s.models[d.model]; a.self_rank = s.rank_of[d.self]; }
 }
 MMP_HD void prepare_ctx_b(const SnapshotView &s, const mmp_decision_in &d, const CtxA &a, const FreshRow *fresh_tab, int32_t n_fresh,
-                          DecisionCtx &c) {
+                          const int32_t *extra, DecisionCtx &c) {
   c.d = d; c.slot = -1; c.self_rank = -1; c.last_used = 0; c.self_bits = 0; c.self_count = 0;
+  c.xr[0] = c.xr[1] = c.xr[2] = c.xr[3] = -1;
   c.fr.lru = 0; c.fr.rem = 0; c.fr.count = 0; c.fr.rpm = 0;
   if (!a.ok) return;
   const int tid = a.mr.type_id < s.n_type_ids ? a.mr.type_id : 0;
@@ -479,12 +484,16 @@ MMP_HD void prepare_ctx_b(const SnapshotView &s, const mmp_decision_in &d, const
     c.self_bits = (((s.any_rs ? s.candx : s.cand)[so] >> sh) & 1u) | (((s.pref[so] >> sh) & 1u) << 1);
     c.self_count = s.count_col[c.self_rank];
   }
+  if (d.extra_n > 0 && d.extra_n <= LANE_MAX_EXTRA) {  // (the slice was bounds-checked by prepare_ctx_a)
+    for (int e = 0; e < LANE_MAX_EXTRA; e++)
+      if (e < d.extra_n) { const int32_t x = extra[d.extra_off + e]; c.xr[e] = (x >= 0 && x < s.max_instances) ? s.rank_of[x] : -1; }
+  }
 }
 MMP_HD void prepare_ctx(const SnapshotView &s, const mmp_decision_in &d, const FreshRow *fresh_tab, int32_t n_fresh,
-                        DecisionCtx &c) {
+                        const int32_t *extra, DecisionCtx &c) {
   CtxA a;
   prepare_ctx_a(s, d, a);
-  prepare_ctx_b(s, d, a, fresh_tab, n_fresh, c);
+  prepare_ctx_b(s, d, a, fresh_tab, n_fresh, extra, c);
 }
 
 #define MMP_BAIL_CHECK do { if (co.bailed()) { o.flags |= MMP_TF_BAIL; o.target = MMP_TARGET_NONE; return; } } while (0)
@@ -642,35 +651,44 @@ MMP_HD bool decide_fast(const SnapshotView &s, const DecisionCtx &c, const uint3
   return true;
 }
 
-// The per-rank / per-word tables a lane reads INSIDE its window, indexable by absolute row word / rank.  k_place_lanes
-// points them at a shared-memory copy of the front of each table (with the SM's shared memory given to the landing
-// stages, L1 is too small to keep them resident and every gather would be an L2 round trip); the CPU harness and
-// small launches point them at the snapshot's own arrays.
+// What a lane of k_place_lanes reads besides its exclusion row: the snapshot's own tables (global memory: small, L1/L2
+// resident) and, per type-constraint slot, the COMPRESSED WORD LIST nzw[slot][k] = index of the k-th row word in which the
+// slot's candidate mask has any bit (within this process's word range).  A word without candidates contributes nothing to
+// the filtered set F = cand & ~excl, so every walk of decide_stream steps through the list instead of through the row:
+// on dense masks (C3: the list is 0, 1, 2, ...) nothing changes, on sparse ones (C5: a handful of candidates per type among
+// 10 000 instances) a walk that crossed 50-300 empty words becomes a few steps.
 struct LaneTables {
-  const uint32_t *cx, *p;   // this decision's candidate (filter applied) and preferred mask rows
+  const uint32_t *cx, *p;   // this decision's candidate (replicaset filter applied) and preferred mask rows, by absolute row word
   const uint32_t *full;
   const WordSumI *csum;
   const int32_t *count_col;
   const RankRow *rows;
+  const uint16_t *nzw;      // [nz_n] ascending row-word indices with cx[w] != 0, all in [word_lo, word_hi)
+  uint32_t nz_n;
 };
-MMP_HD RankRow load_row_any(const RankRow *p) {  // generic address space (shared or global)
-#if defined(__CUDA_ARCH__)
-  const int4 a = reinterpret_cast<const int4 *>(p)[0], b = reinterpret_cast<const int4 *>(p)[1];
-  RankRow r;
-  r.lru = (int64_t)(((uint64_t)(uint32_t)a.y << 32) | (uint32_t)a.x);
-  r.rem = (int64_t)(((uint64_t)(uint32_t)a.w << 32) | (uint32_t)a.z);
-  r.count = b.x; r.rpm = b.y; r.idx = b.z; r.flags = (uint32_t)b.w;
-  return r;
-#else
-  return *p;
-#endif
-}
 MMP_HD LaneTables lane_tables_global(const SnapshotView &s, int slot) {
   LaneTables t;
   const size_t so = (size_t)slot * (size_t)s.row_words;
   t.cx = (s.any_rs ? s.candx : s.cand) + so; t.p = s.pref + so; t.full = s.full; t.csum = s.csum; t.count_col = s.count_col;
   t.rows = s.rows;
+  t.nzw = s.nzw + so; t.nz_n = (uint32_t)s.nz_n[slot];
   return t;
+}
+// read-only table loads of the lane routine (ld.global.nc on the device)
+template <class T> MMP_HD T ldro(const T *p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+MMP_HD WordSumI ldro_sum(const WordSumI *p) {
+#if defined(__CUDA_ARCH__)
+  const int2 v = __ldg(reinterpret_cast<const int2 *>(p));
+  return WordSumI{v.x, v.y};
+#else
+  return *p;
+#endif
 }
 
 // Instance-sharded early-out: an entry of the filtered set in a LOWER shard beats anything this shard can offer
@@ -688,51 +706,113 @@ struct WarpVote { MMP_D bool any(bool p) const { return __any_sync(0xffffffffu, 
 #endif
 
 // The common case of getNext for ONE DECISION PER LANE (k_place_lanes), written so that the 32 lanes of a warp stay
-// converged: every phase is a word-at-a-time walk whose loop is left by a warp vote, bodies are predicated on a per-lane
-// state, and the scalar work between the walks is straight-line.  Phases:
-//   A   first entry of F = cand & ~excl from the start of the row (MM:4806)
+// converged: every phase is a walk whose loop is left by a warp vote, bodies are predicated on a per-lane state, and the
+// scalar work between the walks is straight-line.  A walk steps through the slot's compressed word list (LaneTables::nzw):
+// step k looks at row word W(k) = nzw[k], the k-th word that holds any candidate of the decision's type.  Phases:
+//   A   first entry of F = cand & ~excl & ~extra (MM:4806)
 //   A'  non-simple (a), MM:4828-4852: the first later entry that is preferred or full
 //   B   the shortlist walk (MM:4901-4937): first member of S that fails its test; a word whose count summary is
 //       "mixed" is evaluated exactly (32 counts) by all lanes that stopped on one, in one converged step
 //   C   the hash-indexed pick (MM:4981-4986): k-th member of the shortlist
 // Same semantics and quirks as decide_ctx (N2: the non-self test reads the caller's fresh record).  Returns false --
 // and the caller redoes the decision with the cooperative general routine -- for everything outside the common case:
-// malformed decision, extra excludes, no entry / best full (replicaset retry, non-simple (b)), or a walk longer than
-// `budget` row words.  Instance-sharded: a walk that needs ranks beyond this shard's range sets MMP_TF_OPEN.
-// erow holds only the first win_words words of the decision's (stored) row -- k_place_lanes copies that window out of
-// the TMA landing stage so the stage can take the next rows while the lanes compute; a walk that leaves the window is
-// declined like one that exceeds the budget.  self_eword = the row word that holds self's bit (anywhere in the row).
-// Must be called by every lane of the vote group (active = false for lanes without a decision).
+// malformed decision, more than LANE_MAX_EXTRA extra excludes, no entry / best full (replicaset retry, non-simple (b)), or
+// a walk of more than `budget` steps.  Instance-sharded: a walk that needs ranks beyond this shard's range sets MMP_TF_OPEN.
+// The decision's exclusion row is seen through a WINDOW: ewin[k] = row word W(k) for k < win_words (k_place_lanes copies
+// these out of the TMA landing stage so that the stage can take the next rows while the lanes compute); steps beyond the
+// window read the row itself (erow_g: global memory, word index relative to word_lo -- the row has just been streamed, so it
+// is an L2 hit), or end the lane's attempt when erow_g is null.  self_eword = the row word that holds self's bit (anywhere
+// in the row).  Must be called by every lane of the vote group (active = false for lanes without a decision).
 template <class V>
-MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const DecisionCtx &c, bool active, const uint32_t *erow,
-                          uint32_t win_words, uint32_t self_eword, int64_t now, uint64_t seed, uint64_t decision_id, const V &vote,
-                          DecideOut &o, int32_t budget) {
+MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const DecisionCtx &c, bool active, const uint32_t *ewin,
+                          uint32_t win_words, const uint32_t *erow_g, uint32_t self_eword, int64_t now, uint64_t seed,
+                          uint64_t decision_id, const V &vote, DecideOut &o, int32_t budget) {
   o.target = MMP_TARGET_NONE; o.n_candidates = 0; o.best = -1; o.n_remaining = 0; o.pick_index = 0; o.flags = 0;
   o.cut_rank = (int32_t)NONE_RANK; o.best_rank = -1; o.first_rank = -1;
   const uint32_t NW = (uint32_t)s.row_words, WS = (uint32_t)s.word_lo, WE = (uint32_t)s.word_hi;
   const bool open_end = WE < NW;
-  bool live = active && c.slot >= 0 && c.d.extra_n == 0;
+  bool live = active && c.slot >= 0 && c.d.extra_n <= LANE_MAX_EXTRA;
   const mmp_decision_in &d = c.d;
-  const uint32_t *CX = T.cx, *P = T.p;  // window words only; the self check below reads the snapshot's own rows
+  const uint32_t *CX = T.cx, *P = T.p;
+  const uint32_t NZ = T.nz_n;
   const bool favour_self = (d.flags & MMP_DF_FAVOUR_SELF) != 0;
   const int32_t self_rank = c.self_rank;
   const FreshRow fr = c.fr;
   int32_t left = budget;
-  auto Fw = [&](uint32_t wi) -> uint32_t { return CX[wi] & ~erow[wi - WS]; };
-  auto pbit = [&](uint32_t r) -> bool { return (P[r >> 5] >> (r & 31)) & 1u; };
+  const bool has_x = d.extra_n > 0;
+  // The word list and the part of the row beyond the window are read in CHUNKS of 8 steps: one 16-byte load of 8 list
+  // entries and 8 independent loads of the row words they name, issued together, so a long walk pays one L2 round trip
+  // per 8 steps instead of two dependent ones per step (C5: walks of 100+ steps over sparse candidate masks).
+  uint32_t cur_chunk = 0xffffffffu;
+  uint32_t wq[4] = {0, 0, 0, 0};                     // 8 list entries (u16 pairs) of the current chunk
+  uint32_t eq[8] = {0, 0, 0, 0, 0, 0, 0, 0};         // their row words when the chunk reaches beyond the window
+  bool reach = true;                                 // false: the chunk lies beyond the window and there is no row to read
+  auto wsel = [&](uint32_t j) -> uint32_t {          // entry j (0..7) of the chunk, without dynamic register indexing
+    uint32_t q = wq[0];
+    q = (j >> 1) == 1 ? wq[1] : q; q = (j >> 1) == 2 ? wq[2] : q; q = (j >> 1) == 3 ? wq[3] : q;
+    return (q >> ((j & 1u) * 16u)) & 0xffffu;
+  };
+  auto fetch = [&](uint32_t k) {                     // make the chunk of step k current (k < NZ)
+    const uint32_t ci = k >> 3;
+    if (ci == cur_chunk) return;
+    cur_chunk = ci;
+#if defined(__CUDA_ARCH__)
+    const uint4 q = __ldg(reinterpret_cast<const uint4 *>(T.nzw) + ci);  // list rows are row_words (a multiple of 32) entries long
+    wq[0] = q.x; wq[1] = q.y; wq[2] = q.z; wq[3] = q.w;
+#else
+    for (int j = 0; j < 4; j++) wq[j] = (uint32_t)T.nzw[ci * 8 + 2 * j] | ((uint32_t)T.nzw[ci * 8 + 2 * j + 1] << 16);
+#endif
+    reach = true;
+    if (ci * 8u + 8u > win_words) {
+      if (erow_g == nullptr) reach = false;
+      else {
+#pragma unroll
+        for (uint32_t j = 0; j < 8; j++) {
+          const uint32_t kk = ci * 8u + j;
+          eq[j] = (kk >= win_words && kk < NZ) ? ldro(erow_g + (wsel(j) - WS)) : 0u;
+        }
+      }
+    }
+  };
+  auto W = [&](uint32_t k) -> uint32_t { return wsel(k & 7u); };  // after fetch(k)
+  // word W(k) of the decision's exclusion row (after fetch(k)); false when it is out of reach
+  auto Ew = [&](uint32_t k, uint32_t, uint32_t &e) -> bool {
+    if (k < win_words) { e = ewin[k]; return true; }
+    if (!reach) return false;
+    const uint32_t j = k & 7u;
+    uint32_t v = eq[0];
+    v = j == 1 ? eq[1] : v; v = j == 2 ? eq[2] : v; v = j == 3 ? eq[3] : v; v = j == 4 ? eq[4] : v;
+    v = j == 5 ? eq[5] : v; v = j == 6 ? eq[6] : v; v = j == 7 ? eq[7] : v;
+    e = v;
+    return true;
+  };
+  auto xmask = [&](uint32_t wi) -> uint32_t {  // bits of word wi taken by the extra excludes
+    uint32_t m = 0;
+#pragma unroll
+    for (int e = 0; e < LANE_MAX_EXTRA; e++) { const int32_t r = c.xr[e]; if (r >= 0 && ((uint32_t)r >> 5) == wi) m |= 1u << (r & 31); }
+    return m;
+  };
+  auto pbit = [&](uint32_t r) -> bool { return (ldro(P + (r >> 5)) >> (r & 31)) & 1u; };
 
   // ---- A: first filtered entry ----
-  uint32_t b = NONE_RANK;
+  uint32_t b = NONE_RANK, kb = 0;
   {
-    uint32_t wi = WS;
+    uint32_t k = 0;
     bool search = live;
     for (;;) {
       if (search) {
-        if (wi >= WE || left <= 0 || wi - WS >= win_words) search = false;
+        if (k >= NZ || left <= 0) search = false;
         else {
-          const uint32_t x = Fw(wi);
-          if (x) { b = wi * 32u + (uint32_t)ffs32(x); search = false; }
-          else { wi++; left--; }
+          fetch(k);
+          const uint32_t wi = W(k);
+          uint32_t e;
+          if (!Ew(k, wi, e)) search = false;
+          else {
+            uint32_t x = ldro(CX + wi) & ~e;
+            if (has_x) x &= ~xmask(wi);
+            if (x) { b = wi * 32u + (uint32_t)ffs32(x); kb = k; search = false; }
+            else { k++; left--; }
+          }
         }
       }
       if (!vote.any(search)) break;
@@ -743,9 +823,9 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
   bool us = false, simple = true, use_pref = false;
   int64_t best_rem = 0;
   int32_t best_count = 0, best_rpm = 0, best_idx = -1;
-  uint32_t best_rank = b, lo = b, hi = NONE_RANK;
+  uint32_t best_rank = b, lo = b, hi = NONE_RANK, k_lo = kb;
   if (live) {
-    rb = load_row_any(T.rows + b);
+    rb = load_row(T.rows + b);
     us = rb.idx == d.self;
     best_rem = us ? fr.rem : rb.rem; best_count = us ? fr.count : rb.count; best_rpm = us ? fr.rpm : rb.rpm; best_idx = rb.idx;
     if (best_rem < s.min_space) live = false;  // best full (MM:4811): general routine
@@ -754,20 +834,27 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
     use_pref = has_pref && simple;  // best is preferred: preference is treated as required (MM:4905-4907)
   }
   // ---- A': non-simple (a) ----
-  uint32_t r1 = NONE_RANK;
+  uint32_t r1 = NONE_RANK, k1 = kb;
   {
     const uint32_t b_w = b >> 5, m_b = mask_above(b_w * 32u, b);
-    uint32_t wi = b_w;
+    uint32_t k = kb;
     bool search = live && !simple;
     for (;;) {
       if (search) {
-        if (wi >= WE) search = false;
-        else if (left <= 0 || wi - WS >= win_words) { search = false; live = false; }
+        if (k >= NZ) search = false;                         // natural end of the row
+        else if (left <= 0) { search = false; live = false; }
         else {
-          uint32_t x = Fw(wi) & (P[wi] | T.full[wi]);
-          if (wi == b_w) x &= m_b;
-          if (x) { r1 = wi * 32u + (uint32_t)ffs32(x); search = false; }
-          else { wi++; left--; }
+          fetch(k);
+          const uint32_t wi = W(k);
+          uint32_t e;
+          if (!Ew(k, wi, e)) { search = false; live = false; }
+          else {
+            uint32_t x = ldro(CX + wi) & ~e & (ldro(P + wi) | ldro(T.full + wi));
+            if (has_x) x &= ~xmask(wi);
+            if (wi == b_w) x &= m_b;
+            if (x) { r1 = wi * 32u + (uint32_t)ffs32(x); k1 = k; search = false; }
+            else { k++; left--; }
+          }
         }
       }
       if (!vote.any(search)) break;
@@ -777,10 +864,10 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
   if (live && !simple) {
     if (r1 == NONE_RANK) open = open_end;  // else: neither kind follows, "no preference" logic over the whole remainder
     else if (pbit(r1)) {
-      const RankRow rp = load_row_any(T.rows + r1);
+      const RankRow rp = load_row(T.rows + r1);
       best_rank = r1; best_idx = rp.idx; best_rem = rp.rem; best_count = rp.count; best_rpm = rp.rpm;
       us = rp.idx == d.self;
-      lo = r1; use_pref = true;
+      lo = r1; k_lo = k1; use_pref = true;
     } else hi = r1;
   }
   bool done = false;
@@ -796,9 +883,9 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
     if (self_rank >= 0 && (uint32_t)self_rank > lo && (uint32_t)self_rank < hi) {
       const uint32_t w = (uint32_t)self_rank >> 5, bit = 1u << (self_rank & 31);
       // self may sit anywhere in the row: its mask bits were gathered with the context, its row word by the caller
-      if (w - WS < WE - WS && (c.self_bits & 1u) != 0 && (self_eword & bit) == 0 && (!use_pref || (c.self_bits & 2u) != 0)) {
-        self_in_s = true; sw_ = w; sb_ = bit;
-      }
+      bool in = w - WS < WE - WS && (c.self_bits & 1u) != 0 && (self_eword & bit) == 0 && (!use_pref || (c.self_bits & 2u) != 0);
+      if (in && has_x) in = (xmask(w) & bit) == 0;  // an explicitly excluded self never passes the filter (MM:4780-4781)
+      if (in) { self_in_s = true; sw_ = w; sb_ = bit; }
     }
     const int64_t q = best_rem >> 2;
     c_self = fr.rem < s.min_space || fr.rem < q;
@@ -815,38 +902,41 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
   // a word of S': only the word that holds lo and the one that holds lim are cut (none beyond lim's is ever visited)
   const uint32_t lo_w = lo >> 5, m_lo = mask_above(lo_w * 32u, lo);
   const uint32_t lim_w = lim >> 5, m_lim = mask_below(lim_w * 32u, lim);  // lim == NONE_RANK: lim_w is no real word
-  auto Sw = [&](uint32_t wi) -> uint32_t {
-    uint32_t m = Fw(wi);
+  auto Sw = [&](uint32_t wi, uint32_t e) -> uint32_t {
+    uint32_t m = ldro(CX + wi) & ~e;
+    if (has_x) m &= ~xmask(wi);
     if (wi == lo_w) m &= m_lo;
     if (wi == lim_w) m &= m_lim;
-    return use_pref ? (m & P[wi]) : m;
+    return use_pref ? (m & ldro(P + wi)) : m;
   };
-  // the walk may visit words [lo_w, end_b): up to the natural end (stop_w), the window and the visit budget
-  uint32_t end_b = stop_w < WS + win_words ? stop_w : WS + win_words;
-  { const uint32_t cap = lo_w + (uint32_t)(left > 0 ? left : 0); if (cap < end_b) end_b = cap; }
   // ---- B: first member of S' that fails its walk test, counting the members before it ----
   uint32_t cut_others = NONE_RANK, n_in = 0;
   {
-    uint32_t wi = lo_w, xt = 0;
+    uint32_t k = k_lo, wi = lo_w, xt = 0;
     bool search = walk, mixed = false;
     for (;;) {
       for (;;) {
         if (search) {
-          if (wi >= end_b) {
+          if (k < NZ) fetch(k);
+          if (k >= NZ || (wi = W(k)) >= stop_w) {  // the walk's natural end
             search = false;
-            if (wi < stop_w) live = false;  // window or budget exhausted before the walk's natural end
-            else if (lim == NONE_RANK && open_end) open = true;
-          } else {
-            const uint32_t x = Sw(wi);
-            int cls = 0;  // 0: no member fails, 1: every member (but a passing self) fails, 2: look at the counts
-            uint32_t v = x;
-            if (c_self) { if (wi == sw_) v &= ~sb_; cls = v ? 1 : 0; }
-            else if (x) { const WordSumI m = T.csum[wi]; cls = !cv(m.hi) ? 0 : (cv(m.lo) ? 1 : 2); }
-            if (cls == 0) { n_in += (uint32_t)popc32(x); wi++; }
+            if (lim == NONE_RANK && open_end) open = true;
+          } else if (left <= 0) { search = false; live = false; }  // budget exhausted before the natural end
+          else {
+            uint32_t e;
+            if (!Ew(k, wi, e)) { search = false; live = false; }
             else {
-              search = false; xt = x;
-              if (cls == 1) cut_others = wi * 32u + (uint32_t)ffs32(v);
-              else mixed = true;
+              const uint32_t x = Sw(wi, e);
+              int cls = 0;  // 0: no member fails, 1: every member (but a passing self) fails, 2: look at the counts
+              uint32_t v = x;
+              if (c_self) { if (wi == sw_) v &= ~sb_; cls = v ? 1 : 0; }
+              else if (x) { const WordSumI m = ldro_sum(T.csum + wi); cls = !cv(m.hi) ? 0 : (cv(m.lo) ? 1 : 2); }
+              if (cls == 0) { n_in += (uint32_t)popc32(x); k++; left--; }
+              else {
+                search = false; xt = x;
+                if (cls == 1) cut_others = wi * 32u + (uint32_t)ffs32(v);
+                else mixed = true;
+              }
             }
           }
         }
@@ -860,7 +950,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
         const int4 *cc = reinterpret_cast<const int4 *>(T.count_col + (size_t)wi * 32u);
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-          const int4 q = cc[j];
+          const int4 q = __ldg(cc + j);
           vm |= ((cv(q.x) ? 1u : 0u) | (cv(q.y) ? 2u : 0u) | (cv(q.z) ? 4u : 0u) | (cv(q.w) ? 8u : 0u)) << (4 * j);
         }
 #else
@@ -869,7 +959,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
 #endif
         vm &= xt;
         if (vm) cut_others = wi * 32u + (uint32_t)ffs32(vm);
-        else { n_in += (uint32_t)popc32(xt); wi++; search = true; }
+        else { n_in += (uint32_t)popc32(xt); k++; left--; search = true; }
       }
       if (!vote.any(search)) break;
     }
@@ -907,22 +997,24 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
       }
     }
   }
-  // ---- C: k-th survivor in rank order ----
+  // ---- C: k-th survivor in rank order (re-walks words phase B has visited: no budget is spent) ----
   {
     const bool drop_self = self_in_sl && !keep_self;
     const uint32_t cut_w = cut >> 5, m_cut = mask_below(cut_w * 32u, cut);
-    uint32_t wi = lo_w;
+    uint32_t k = k_lo;
     bool search = sel;
     for (;;) {
       if (search) {
-        if (wi >= end_b) { search = false; live = false; }  // cannot happen: kth < number of survivors, all in visited words
+        uint32_t wi = 0, e = 0;
+        if (k < NZ) fetch(k);
+        if (k >= NZ || !Ew(k, (wi = W(k)), e)) { search = false; live = false; }  // cannot happen: kth < number of survivors, all in visited words
         else {
-          uint32_t x = Sw(wi);
+          uint32_t x = Sw(wi, e);
           if (wi == cut_w) x &= m_cut;
           if (drop_self && wi == sw_) x &= ~sb_;
           const uint32_t n = (uint32_t)popc32(x);
           if (kth < n) { chosen_rank = wi * 32u + (uint32_t)nth_bit(x, kth); search = false; }
-          else { kth -= n; wi++; }
+          else { kth -= n; k++; }
         }
       }
       if (!vote.any(search)) break;
@@ -934,7 +1026,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
   o.best = best_idx; o.best_rank = (int32_t)best_rank;
   if (open) { o.flags = MMP_TF_OPEN; return true; }
   if (!done) {
-    const int32_t cidx = chosen_rank == best_rank ? best_idx : ((int32_t)chosen_rank == self_rank ? d.self : T.rows[chosen_rank].idx);
+    const int32_t cidx = chosen_rank == best_rank ? best_idx : ((int32_t)chosen_rank == self_rank ? d.self : ldro(&T.rows[chosen_rank].idx));
     o.target = (!favour_self && cidx == d.self) ? MMP_TARGET_SELF : cidx;
     o.n_candidates = ccount;
     o.n_remaining = remaining; o.pick_index = (int32_t)index;

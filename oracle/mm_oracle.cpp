@@ -1523,3 +1523,5 @@ int64_t orc_reaper_select(orc_fleet *h, int32_t n, const orc_model_t *models, co
 }
 
 }  // extern "C"
+
+#include "mm_sim.inc"

@@ -177,6 +177,44 @@ int64_t orc_reaper_select(orc_fleet *, int32_t n, const orc_model_t *models, con
 
 uint64_t orc_hash64(uint64_t seed, uint64_t decision_id);
 
+/* ---- closed loop (mm_sim.inc): placement -> admission -> LRU insert -> eviction -> rebalance -> republish, one epoch
+ * (= one republish window) per call; see the header of mm_sim.inc for the epoch semantics both sides implement ---- */
+typedef struct orc_sim orc_sim;
+typedef struct { int64_t last_used; int32_t type_idx; int32_t size_units; } orc_sim_model_t;
+typedef struct { int32_t type; int32_t model; int32_t caller; uint32_t u; int64_t t; } orc_sim_event_t; /* type 0 REQUEST, 1 REMOVE */
+typedef struct { int32_t model, self, target, n_candidates, status, event; } orc_sim_decision_t;
+/* status: 0 accepted, 1 nowhere to load (getNext null), 2 churn guard (MM:3872-3884), 3 placeholder evicted immediately
+ * (MM:5145-5148), 4 early reject (MM:5185-5190), 5 evicted while growing (MM:2102-2106), 6 entry already there, 7 follow-on
+ * skipped (model has a copy again), 8 invalid, 9 accepted but evicted again later in the same epoch.
+ * event: index of the REQUEST that caused it, or -1 - k for the k-th queued ensureLoadedElsewhere of the previous epoch */
+typedef struct { int32_t instance, model; int64_t last_used; int32_t weight, order, reload; } orc_sim_eviction_t;
+orc_sim *orc_sim_create(orc_fleet *, int32_t n_models, const orc_sim_model_t *models, const char *const *type_names,
+                        int32_t n_types, const int64_t *edge_off, const int32_t *edge_inst, const int32_t *n_loaded,
+                        int32_t n_instances, const int64_t *capacity, int64_t load_timeout_ms, int64_t last_published_ms);
+void orc_sim_destroy(orc_sim *);
+int orc_sim_seed(orc_sim *, int32_t instance, int32_t n, const int32_t *model, const int64_t *last_used, const int32_t *weight,
+                 const int64_t *load_ts, int64_t now_ms);
+/* returns the number of ensureLoadedElsewhere requests queued for the next epoch */
+int64_t orc_sim_step(orc_sim *, const orc_sim_event_t *ev, int32_t n, int64_t now0, int64_t now1, uint64_t seed,
+                     orc_sim_decision_t *dec_out, int32_t dec_cap, int32_t *n_dec_out, orc_sim_eviction_t *evict_out,
+                     int32_t evict_cap, int32_t *n_evict_out, orc_inst_t *rows_out, int32_t *published_out);
+int64_t orc_sim_model_copies(orc_sim *, int32_t model, int32_t *out, int32_t cap, int64_t *last_used);
+int64_t orc_sim_lru_state(orc_sim *, int32_t instance, int64_t *oldest, int64_t *weighted, int64_t *count);
+int64_t orc_sim_coalesced(orc_sim *);
+
+/* ---- a14: scale-up / scale-down arithmetic (MM:5640-5806, 5835-5870, 6197-6335) ---- */
+int orc_second_copy_trigger(int32_t *i1, int32_t *i2, int32_t iteration, int32_t min_age_iters, int32_t max_age_iters,
+                            int64_t total_free, int64_t total_capacity, int64_t global_lru, int64_t now,
+                            int64_t second_copy_lru_threshold_ms);
+int32_t orc_scaleup_copies(int64_t count, int64_t time_delta_ms, int32_t scale_up_rpms, int32_t loaded_count, int32_t failed_count,
+                           int32_t suitable_inst_count, int32_t excluded_count, int32_t excluded_not_holding, int32_t recently_loaded,
+                           int32_t *rpm_out);
+int32_t orc_scaleup_exclude_set(orc_fleet *, int32_t self, int32_t scale_up_rpms, int32_t our_rpm, uint8_t *marks, int32_t n_idx);
+int orc_loaded_since(const int32_t *inst, const int64_t *load_ts, int32_t n, int64_t cutoff, int32_t ignore_instance);
+int orc_scale_down(orc_fleet *, int32_t self, const int32_t *copies, const int64_t *load_ts, int32_t n_copies, int64_t last_used,
+                   int64_t now, int64_t last_heavy_time, int64_t last_unload_time, int64_t last_check_time, int64_t interval_count,
+                   int32_t scale_up_rpm_threshold, int64_t rate_check_interval_ms, int64_t second_copy_remove_max_age_ms);
+
 #ifdef __cplusplus
 }
 #endif

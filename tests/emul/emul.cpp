@@ -29,6 +29,7 @@ struct mmp_fleet {
 static thread_local std::string g_err;
 static int g_window = 32;  // fast-path window width under test (32: warp tile, 16: half-warp tile); 1: lane-per-decision shape
 static int g_lane_budget = 48;  // CoopLane walk budget (row words) when g_window == 1
+static int g_lane_global = 1;  // decide_stream: steps beyond the window may read the row itself (the kernel's second chance: L2)
 static int g_lane_window = 14;  // decide_stream: row words available to a lane (LANE_WIN of k_place_lanes: the window copied out of the landing stage)
 static long g_bails = 0, g_lane_decisions = 0;
 
@@ -38,6 +39,7 @@ int32_t mmp_abi_version(void) { return MMP_ABI_VERSION; }
 void mmp_emul_set_window(int w) { g_window = (w == 16 || w == 8 || w == 1 || w == 2) ? w : 32; }  // harness-only entry points
 void mmp_emul_set_lane_budget(int words) { g_lane_budget = words; }
 void mmp_emul_set_lane_window(int words) { g_lane_window = words; }
+void mmp_emul_set_lane_global(int on) { g_lane_global = on; }
 void mmp_emul_set_keys(mmp_fleet *f, uint64_t *keys) { f->keys = keys; }
 void mmp_emul_key_decode(uint64_t k, int32_t *target, int32_t *n_candidates, int32_t *open) {
   shard_key_decode(k, *target, *n_candidates);
@@ -115,6 +117,7 @@ static SnapshotView make_view(mmp_fleet *f) {
   v.excl = f->excl.data(); v.cand = s.cand.data(); v.candx = s.candx.data(); v.pref = s.pref.data(); v.has_pref = s.has_pref.data();
   v.type_slot = s.type_slot_hp.data(); v.full = s.full.data(); v.rows = s.rows.data();
   v.rank_of = s.rank_of.data(); v.csum = s.csum.data(); v.lsum = s.lsum.data(); v.models = f->models.data();
+  v.nzw = s.nzw.data(); v.nz_n = s.nz_n.data();
   return v;
 }
 
@@ -136,7 +139,7 @@ int32_t mmp_place_batch_trace(mmp_fleet *f, const mmp_decision_in *in, int32_t n
   for (int32_t i = 0; i < n; i++) {
     DecideOut o;
     DecisionCtx cx;
-    prepare_ctx(v, in[i], fr.data(), n_fresh, cx);
+    prepare_ctx(v, in[i], fr.data(), n_fresh, extra, cx);
     const uint32_t *erow = v.excl + (size_t)(cx.slot >= 0 ? in[i].model : 0) * v.excl_stride;
     const bool sharded = v.word_lo != 0 || v.word_hi != v.row_words;
     bool done = false;
@@ -148,10 +151,14 @@ int32_t mmp_place_batch_trace(mmp_fleet *f, const mmp_decision_in *in, int32_t n
     if (win == 2 && !cand_mask) {  // the lockstep lane routine of k_place_lanes (one decision per lane), general routine when it declines
       uint32_t self_eword = 0;
       if (cx.self_rank >= 0 && (cx.self_rank >> 5) >= v.word_lo && (cx.self_rank >> 5) < v.word_hi) self_eword = erow[(cx.self_rank >> 5) - v.word_lo];
-      // the lane sees a COPY of exactly the window (as k_place_lanes gives it): an over-read is a heap overflow under ASAN
-      const uint32_t ww = (uint32_t)std::min<int64_t>(g_lane_window, std::min<int64_t>(v.excl_stride, v.word_hi - v.word_lo));
-      std::vector<uint32_t> window(erow, erow + ww);
-      done = decide_stream(v, lane_tables_global(v, cx.slot >= 0 ? ctx_slot(cx) : 0), cx, true, window.data(), ww, self_eword, now_ms, seed, f->id_base + (uint64_t)i, SoloVote(), o, g_lane_budget);
+      // the lane sees a COPY of exactly the window (as k_place_lanes gives it): row words W(0..ww) of the slot's compressed
+      // word list; an over-read is a heap overflow under ASAN
+      const LaneTables T = lane_tables_global(v, cx.slot >= 0 ? ctx_slot(cx) : 0);
+      const uint32_t ww = (uint32_t)std::min<int64_t>(g_lane_window, (int64_t)T.nz_n);
+      std::vector<uint32_t> window(ww);
+      for (uint32_t k = 0; k < ww; k++) window[k] = erow[T.nzw[k] - v.word_lo];
+      done = decide_stream(v, T, cx, true, window.data(), ww, g_lane_global ? erow : nullptr, self_eword, now_ms, seed,
+                           f->id_base + (uint64_t)i, SoloVote(), o, g_lane_budget);
       g_lane_decisions++;
       if (!done) g_bails++;
     } else if (sharded) {
