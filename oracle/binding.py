@@ -27,7 +27,17 @@ LRU_EVENT = np.dtype([("op", "<i4"), ("key", "<i4"), ("weight", "<i8"), ("last_u
 EVICTION = np.dtype([("key", "<i4"), ("event", "<i4"), ("last_used", "<i8"), ("weight", "<i8")], align=True)
 MODEL = np.dtype([("last_used", "<i8"), ("type_idx", "<i4"), ("n_loaded", "<i4"), ("n_failed", "<i4"), ("pad", "<i4")],
                  align=True)
+SIM_MODEL = np.dtype([("last_used", "<i8"), ("type_idx", "<i4"), ("size_units", "<i4")], align=True)
+SIM_EVENT = np.dtype([("type", "<i4"), ("model", "<i4"), ("caller", "<i4"), ("u", "<u4"), ("t", "<i8")], align=True)
+SIM_DECISION = np.dtype([("model", "<i4"), ("self", "<i4"), ("target", "<i4"), ("n_candidates", "<i4"), ("status", "<i4"),
+                         ("event", "<i4")], align=True)
+SIM_EVICTION = np.dtype([("instance", "<i4"), ("model", "<i4"), ("last_used", "<i8"), ("weight", "<i4"), ("order", "<i4"),
+                         ("reload", "<i4")], align=True)
 assert INST.itemsize == 64 and DECISION.itemsize == 32 and RESULT.itemsize == 24 and MODEL.itemsize == 24
+assert SIM_MODEL.itemsize == 16 and SIM_EVENT.itemsize == 24 and SIM_DECISION.itemsize == 24 and SIM_EVICTION.itemsize == 32
+SIM_REQUEST, SIM_REMOVE = 0, 1
+(SIM_ACCEPTED, SIM_NOWHERE, SIM_CHURN, SIM_FALLTHRU, SIM_EARLY, SIM_GROW_EVICTED, SIM_EXISTS, SIM_SKIPPED, SIM_INVALID,
+ SIM_EVICTED_LATER) = range(10)
 
 NONE, SELF = -1, -2
 ADDED, UPDATED, DELETED = 0, 1, 2
@@ -35,7 +45,7 @@ ADDED, UPDATED, DELETED = 0, 1, 2
 
 def build(force: bool = False) -> str:
     if force or not os.path.exists(SO) or any(
-            os.path.getmtime(os.path.join(HERE, f)) > os.path.getmtime(SO) for f in ("mm_oracle.cpp", "mm_oracle.h")):
+            os.path.getmtime(os.path.join(HERE, f)) > os.path.getmtime(SO) for f in ("mm_oracle.cpp", "mm_sim.inc", "mm_oracle.h")):
         subprocess.check_call(["make", "-C", HERE, "-s"])
     return SO
 
@@ -74,6 +84,17 @@ def lib() -> C.CDLL:
             "orc_early_reject": (C.c_int, [I64, I64, I64, I64, I64]),
             "orc_reaper_select": (I64, [P, I32, P, STRS, I32, I32, I64, P, P, I64]),
             "orc_hash64": (U64, [U64, U64]),
+            "orc_sim_create": (P, [P, I32, P, STRS, I32, P, P, P, I32, P, I64, I64]), "orc_sim_destroy": (None, [P]),
+            "orc_sim_seed": (C.c_int, [P, I32, I32, P, P, P, P, I64]),
+            "orc_sim_step": (I64, [P, P, I32, I64, I64, U64, P, I32, C.POINTER(I32), P, I32, C.POINTER(I32), P, C.POINTER(I32)]),
+            "orc_sim_model_copies": (I64, [P, I32, P, I32, C.POINTER(I64)]),
+            "orc_sim_lru_state": (I64, [P, I32, C.POINTER(I64), C.POINTER(I64), C.POINTER(I64)]),
+            "orc_sim_coalesced": (I64, [P]),
+            "orc_second_copy_trigger": (C.c_int, [C.POINTER(I32), C.POINTER(I32), I32, I32, I32, I64, I64, I64, I64, I64]),
+            "orc_scaleup_copies": (I32, [I64, I64, I32, I32, I32, I32, I32, I32, I32, C.POINTER(I32)]),
+            "orc_scaleup_exclude_set": (I32, [P, I32, I32, I32, P, I32]),
+            "orc_loaded_since": (C.c_int, [P, P, I32, I64, I32]),
+            "orc_scale_down": (C.c_int, [P, I32, P, P, I32, I64, I64, I64, I64, I64, I64, I32, I64, I64]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -277,3 +298,66 @@ class OracleLru:
         w = np.zeros(n, dtype=np.int64)
         self.L.orc_lru_dump(self.h, _ptr(k), _ptr(t), _ptr(w), n)
         return k, t, w
+
+
+class OracleSim:
+    """The closed loop (oracle/mm_sim.inc): one call of step() = one republish window of the whole fleet."""
+
+    def __init__(self, fleet: OracleFleet, models: np.ndarray, type_names: Sequence[str], edge_off: np.ndarray,
+                 edge_inst: np.ndarray, n_loaded: np.ndarray, capacity: np.ndarray, load_timeout_ms: int,
+                 last_published_ms: int):
+        self.L = lib()
+        self.fleet = fleet  # keep alive
+        models = np.ascontiguousarray(models, dtype=SIM_MODEL)
+        self.n_models, self.n_instances = len(models), len(capacity)
+        edge_off = np.ascontiguousarray(edge_off, dtype=np.int64)
+        edge_inst = np.ascontiguousarray(edge_inst, dtype=np.int32)
+        n_loaded = np.ascontiguousarray(n_loaded, dtype=np.int32)
+        capacity = np.ascontiguousarray(capacity, dtype=np.int64)
+        self.h = C.c_void_p(self.L.orc_sim_create(fleet.h, len(models), _ptr(models), _strs(type_names), len(type_names),
+                                                   _ptr(edge_off), _ptr(edge_inst), _ptr(n_loaded), len(capacity),
+                                                   _ptr(capacity), load_timeout_ms, last_published_ms))
+        assert self.h
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.orc_sim_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def seed(self, instance: int, model, last_used, weight, load_ts, now_ms: int):
+        m = np.ascontiguousarray(model, dtype=np.int32)
+        lu = np.ascontiguousarray(last_used, dtype=np.int64)
+        w = np.ascontiguousarray(weight, dtype=np.int32)
+        lt = np.ascontiguousarray(load_ts, dtype=np.int64)
+        rc = self.L.orc_sim_seed(self.h, instance, len(m), _ptr(m), _ptr(lu), _ptr(w), _ptr(lt), now_ms)
+        assert rc == 0, rc
+
+    def step(self, events: np.ndarray, now0: int, now1: int, seed: int):
+        ev = np.ascontiguousarray(events, dtype=SIM_EVENT)
+        cap_d = len(ev) + 65536
+        cap_e = 4 * len(ev) + 65536
+        dec = np.zeros(cap_d, dtype=SIM_DECISION)
+        evi = np.zeros(cap_e, dtype=SIM_EVICTION)
+        rows = np.zeros(self.n_instances, dtype=INST)
+        nd, ne, npub = C.c_int32(), C.c_int32(), C.c_int32()
+        carry = self.L.orc_sim_step(self.h, _ptr(ev), len(ev), now0, now1, seed, _ptr(dec), cap_d, C.byref(nd), _ptr(evi), cap_e,
+                                    C.byref(ne), _ptr(rows), C.byref(npub))
+        assert carry >= 0 and nd.value <= cap_d and ne.value <= cap_e
+        return dec[:nd.value].copy(), evi[:ne.value].copy(), rows, int(npub.value), int(carry)
+
+    def model_copies(self, model: int):
+        out = np.zeros(64, dtype=np.int32)
+        lu = C.c_int64()
+        n = self.L.orc_sim_model_copies(self.h, model, _ptr(out), 64, C.byref(lu))
+        return out[:n].copy(), int(lu.value)
+
+    def lru_state(self, instance: int):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        assert self.L.orc_sim_lru_state(self.h, instance, C.byref(a), C.byref(b), C.byref(c)) == 0
+        return int(a.value), int(b.value), int(c.value)
+
+    def coalesced(self) -> int:
+        return int(self.L.orc_sim_coalesced(self.h))

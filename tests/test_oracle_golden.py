@@ -192,3 +192,118 @@ def test_documented_constraint_shapes(oracle_lib):
     assert a3.tolist() == [False, False, True, True, False]
     assert ad.tolist() == [False] * 5  # _default: nowhere
     assert a2 is None  # no required labels: all instances are candidates
+
+
+def _dummy_cluster(n_inst, now):
+    """DummyModelMesh cluster (T/DummyModelMesh.java:39, T/ModelMeshEvictionsTest.java:558): n pods of 10 x 20 MiB, the
+    unload reserve (2560 units, MM:749-755) published out of the capacity (MM:5373-5378)."""
+    o = ob.OracleFleet(2560, 0, 2560)  # minChurnAgeMs 0: the churn guard is off in the test harness
+    o.types_set(None)
+    rows = np.zeros(n_inst, dtype=ob.INST)
+    rows["capacity"] = 25600 - 2560
+    rows["lru_time"] = (1 << 63) - 1
+    rows["l_threads"] = 8
+    rows["active"] = 1
+    for i in range(n_inst):
+        o.instance_event(ob.ADDED, i, rows[i], f"pod-{i}", now_ms=now)
+    return o, rows
+
+
+def test_multi_load_with_eviction_cluster_closed_loop(oracle_lib):
+    """T/ModelMeshEvictionsTest.java:324-357: a 3-instance cluster holds int(0.9 * 30) = 27 models of
+    20 MiB; loading 27 + 3 in sequence must keep every model but the oldest 3 + 2 x clusterSize ("wiggle room because
+    there is intentionally some thresholds around instance selection", :338-340).  Driven through the closed loop
+    (placement -> loadLocal -> LRU -> eviction -> republish), one request per republish window."""
+    now = 1_760_000_000_000
+    n_inst, size = 3, 2560
+    o, rows = _dummy_cluster(n_inst, now)
+    n_models = 30
+    models = np.zeros(n_models, dtype=ob.SIM_MODEL)
+    models["type_idx"], models["size_units"] = 0, size
+    sim = ob.OracleSim(o, models, ["ExampleType"], np.zeros(n_models + 1, dtype=np.int64), np.zeros(0, dtype=np.int32),
+                       np.zeros(n_models, dtype=np.int32), rows["capacity"], load_timeout_ms=30_000, last_published_ms=now - 60_000)
+    evicted = []
+    for m in range(n_models):
+        e = np.zeros(1, dtype=ob.SIM_EVENT)
+        e["type"], e["model"], e["caller"], e["u"], e["t"] = ob.SIM_REQUEST, m, m % n_inst, m, now + 2000 * m + 1
+        dec, evi, _, _, _ = sim.step(e, now + 2000 * m, now + 2000 * (m + 1), seed=m)
+        assert len(dec) == 1 and dec["status"][0] == ob.SIM_ACCEPTED, (m, dec)
+        evicted += [int(x) for x in evi["model"]]
+    loaded = [m for m in range(n_models) if len(sim.model_copies(m)[0]) > 0]
+    # :347-354 idsForModelsWhichShouldBeLoaded = everything but the oldest 3 + wiggle room; the overflow itself need not be
+    # spread evenly over the pods (which pod evicts follows the LRU-distance shortlist of the full case, MM:4913-4917)
+    assert set(range(3 + 2 * n_inst, n_models)) <= set(loaded)
+    assert 3 <= len(evicted) <= 3 + 2 * n_inst and all(m < 3 + 2 * n_inst for m in evicted)
+    assert len(loaded) == n_models - len(evicted)
+    assert all(sim.lru_state(i)[1] <= 9 * size for i in range(n_inst))
+
+
+def test_multi_load_with_eviction_cluster_reuse(oracle_lib):
+    """T/ModelMeshEvictionsTest.java:371-410: fill the cluster (27), use the first five again, load three more: the three
+    new ones and the five reused ones must all be loaded afterwards (touch protects an entry from eviction)."""
+    now = 1_760_000_000_000
+    n_inst, size = 3, 2560
+    o, rows = _dummy_cluster(n_inst, now)
+    n_models = 30
+    models = np.zeros(n_models, dtype=ob.SIM_MODEL)
+    models["type_idx"], models["size_units"] = 0, size
+    sim = ob.OracleSim(o, models, ["ExampleType"], np.zeros(n_models + 1, dtype=np.int64), np.zeros(0, dtype=np.int32),
+                       np.zeros(n_models, dtype=np.int32), rows["capacity"], load_timeout_ms=30_000, last_published_ms=now - 60_000)
+    step = 0
+
+    def request(m):
+        nonlocal step
+        e = np.zeros(1, dtype=ob.SIM_EVENT)
+        e["type"], e["model"], e["caller"], e["u"], e["t"] = ob.SIM_REQUEST, m, step % n_inst, step, now + 2000 * step + 1
+        out = sim.step(e, now + 2000 * step, now + 2000 * (step + 1), seed=step)
+        step += 1
+        return out
+
+    for m in range(27):
+        request(m)
+    # (the pick among the shortlist is a draw, MM:4981: a pod may already have evicted during the fill -- the wiggle room of
+    # :338-340 -- so "reused" = the five oldest models that are loaded now)
+    held = [m for m in range(27) if len(sim.model_copies(m)[0]) == 1]
+    assert len(held) >= 27 - 2 * n_inst
+    reused = held[:5]
+    for m in reused:
+        dec, evi, _, _, _ = request(m)   # a cache hit: runtimeCache.get(model, now)
+        assert len(dec) == 0 and len(evi) == 0
+    for m in range(27, 30):
+        request(m)
+    loaded = {m for m in range(n_models) if len(sim.model_copies(m)[0]) > 0}
+    assert {27, 28, 29} <= loaded and set(reused) <= loaded   # :397-404
+
+
+def test_second_copy_trigger_timing(oracle_lib):
+    """T/ModelMeshEvictionsTest.java:412-446 testSecondCopyTrigger with its settings (:98-102: max age 10 s, min age 4 s, rate
+    task every 100 ms => [40, 100] iterations): uses at 0.06 s, 1.06 s, 12.56 s, 17.56 s; only the last one -- another
+    use 5 s earlier -- adds the second copy (pins MM:5726-5758)."""
+    import ctypes as C
+    i1, i2 = C.c_int32(-(1 << 31)), C.c_int32(-(1 << 31))  # CacheEntry initial values MM:1648
+    now = 1_760_000_000_000
+    fired = []
+    for t_ms in (60, 1060, 12560, 17560):
+        it = t_ms // 100 + 1  # the first run of the task after the use
+        fired.append(oracle_lib.orc_second_copy_trigger(C.byref(i1), C.byref(i2), it, 40, 100, 50_000, 69_120, now - 3_600_000,
+                                                        now + t_ms, max(10 * 3 * 10 * 1000, 6 * 3_600_000)))
+    assert fired == [0, 0, 0, 1]
+    # > 90 % full and a young cache: the trigger is suppressed (MM:5750-5752)
+    i1, i2 = C.c_int32(120), C.c_int32(126)
+    assert oracle_lib.orc_second_copy_trigger(C.byref(i1), C.byref(i2), 176, 40, 100, 1000, 69_120, now - 3_600_000, now, 6 * 3_600_000) == 0
+    i1, i2 = C.c_int32(120), C.c_int32(126)
+    assert oracle_lib.orc_second_copy_trigger(C.byref(i1), C.byref(i2), 176, 40, 100, 1000, 69_120, now - 7 * 3_600_000, now, 6 * 3_600_000) == 1
+
+
+def test_scaleup_copies_arithmetic(oracle_lib):
+    """MM:5718, 5760-5795 on hand-computed cases (parity unpinned by reference tests)."""
+    import ctypes as C
+    rpm = C.c_int32()
+    f = oracle_lib.orc_scaleup_copies
+    # 5000 requests in 10 s = 30 000 rpm, threshold 2000: min(15, candidates 10 - 1 - 0 = 9) = 9 -> capped at 10 // 3 = 3
+    assert f(5000, 10_000, 2000, 1, 0, 10, 0, 0, 0, C.byref(rpm)) == 3 and rpm.value == 30_000
+    assert f(500, 10_000, 2000, 1, 0, 10, 0, 0, 0, C.byref(rpm)) == 1 and rpm.value == 3000       # 1.5 x threshold: one copy
+    assert f(300, 10_000, 2000, 1, 0, 10, 0, 0, 0, C.byref(rpm)) == 0                              # below the threshold
+    assert f(5000, 10_000, 2000, 1, 0, 10, 0, 0, 1, None) == 0                                     # a copy was loaded too recently
+    assert f(5000, 10_000, 2000, 4, 2, 6, 0, 0, 0, None) == 0                                      # nowhere left to load
+    assert f(5000, 10_000, 2000, 2, 0, 10, 3, 2, 0, None) == 3                                     # 10 - 2 = 8, - 2 - 3 = 3: min(15, 3) = 3, cap 10 // 3 = 3

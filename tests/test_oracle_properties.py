@@ -1,0 +1,214 @@
+"""Brute-force cross-checks OF THE ORACLE (not of the GPU against the oracle) for the parts of getNext that no reference test
+pins ("parity unpinned by reference tests"): an independent, deliberately naive Python re-derivation from
+the Java text, structured differently from oracle/mm_oracle.cpp (lists and dicts, the filtered set materialised, the
+shortlist as a sorted-prefix enumeration), must give the same ordered shortlist, rpm-filter survivors and pick.
+
+  * shortlist == brute-force filter -> sort -> prefix (MM:4760-4771, 4806-4811, 4889-4937, N2/N3 literal)
+  * rpm filter == independent re-derivation (MM:4957-4980)
+  * PLACEMENT_ORDER is a strict weak order on uniform-`vers` fleets and the cluster order is sorted under it (MM:4646-4703)
+"""
+import numpy as np
+import pytest
+
+from helpers import oracle_from_synth, oracle_inputs
+from modelmesh_b200 import _lib as L
+from modelmesh_b200.synth import LONG_MAX, make_decisions, make_fleet
+from oracle import binding as ob
+
+M64 = (1 << 64) - 1
+
+
+def _i64(x):  # Java long wrap
+    x &= M64
+    return x - (1 << 64) if x >> 63 else x
+
+
+def _age(t, now):  # MM:4162-4164
+    return 0 if t == 0 else _i64(now - t)
+
+
+def _hash64(seed, did):  # N4 (same contract as the oracle and the kernel)
+    z = (seed + 0x9E3779B97F4A7C15 * (did + 1)) & M64
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M64
+    return z ^ (z >> 31)
+
+
+def _java_int(d):  # (int) double: truncation toward zero, saturating
+    if d != d:
+        return 0
+    return max(-(1 << 31), min((1 << 31) - 1, int(d)))
+
+
+def _rem(r):
+    return max(0, int(r["capacity"]) - int(r["used"]))
+
+
+def brute_get_next(order, rows, ids, active, replaced, min_space, self_idx, fresh, favour_self, last_used, excluded, now, rnd):
+    """getNext for a type WITHOUT constraints or preferences (constrainTo == null, prefer == null), naive form."""
+    def in_filter(i, use_rs):
+        if i in excluded or not active[i]:
+            return False
+        if use_rs and replaced and len(ids[i]) >= 7 and ids[i][:6] in replaced:
+            return False
+        return True
+    flt = [i for i in order if in_filter(i, True)]                      # MM:4760-4771 materialised
+    if not flt and replaced:
+        flt = [i for i in order if in_filter(i, False)]                 # MM:4798-4802
+    if not flt:
+        return dict(target=ob.NONE, cands=[], keep=[], n_remaining=0, pick=0)
+    best = flt[0]
+    exclude_self = self_idx in excluded
+    us = best == self_idx and not exclude_self                          # MM:4808
+    best_rec = fresh if us else rows[best]
+    best_full = _rem(best_rec) < min_space
+    if us and favour_self:
+        return dict(target=ob.SELF, cands=[], keep=[], n_remaining=0, pick=0)
+    cands, loads = [best], [int(best_rec["rpm"])]
+    oldest = int(best_rec["lru_time"])
+    first_entry_rec = rows[best]                                        # bestEntry.getValue(): the PUBLISHED record of the first entry
+    for i in flt[1:]:
+        us = (not us) and (not exclude_self) and i == self_idx          # N3
+        cur = first_entry_rec if us else fresh                          # N2 (literal)
+        if best_full:
+            diff = _i64(int(cur["lru_time"]) - oldest)
+            a10 = int(_age(oldest, now) / 10)                           # Java long division truncates toward zero
+            if diff > 45_000 and diff > a10:
+                break
+        else:
+            rem = _rem(cur)
+            if rem < min_space or rem < (_rem(best_rec) >> 2):
+                break
+            cnt, first = int(rows[i]["count"]), int(best_rec["count"])
+            if cnt >= 10 and cnt > first + (first >> 2):
+                break
+        if us and favour_self:
+            return dict(target=ob.SELF, cands=cands, keep=[], n_remaining=0, pick=0, early=True)
+        cands.append(i)
+        loads.append(int(cur["rpm"]))
+    keep = [True] * len(cands)
+    remaining, index = len(cands), 0
+    if len(cands) > 1:
+        ago = _age(last_used, now)
+        if ago < 5 * 86_400_000:
+            mn = max(100, min(loads))
+            m11, m15 = _java_int(1.1 * mn), _java_int(1.5 * mn)
+            for k, rpm in enumerate(loads):
+                if rpm >= 100 and ((ago < -1000 and rpm > m11) or (ago < 5000 and rpm > m15) or (ago < 720_000 and rpm > mn * 3)
+                                   or (ago < 86_400_000 and rpm > mn * 4)):
+                    keep[k] = False
+                    remaining -= 1
+                    if remaining == 1:
+                        break
+        index = 0 if remaining == 1 else (((rnd >> 32) * remaining) >> 32)
+    chosen = [c for c, k in zip(cands, keep) if k][index]
+    target = ob.SELF if (not favour_self and chosen == self_idx) else chosen
+    return dict(target=target, cands=cands, keep=keep, n_remaining=remaining, pick=index)
+
+
+@pytest.mark.parametrize("config,nm,ni,seed", [("C2", 1500, 400, 2), ("C2", 1500, 97, 9), ("C1", 300, 16, 1), ("MIX", 500, 160, 2),
+                                               ("MIX", 500, 300, 6), ("MIX", 500, 97, 8), ("MIX", 500, 64, 13), ("MIX", 500, 33, 20),
+                                               ("MIX", 500, 160, 23), ("MIX", 500, 300, 24), ("MIX", 500, 200, 25), ("MIX", 500, 120, 29),
+                                               ("MIX", 500, 250, 35), ("MIX", 500, 97, 36), ("MIX", 500, 180, 43)])
+def test_shortlist_is_the_sorted_prefix_parity_unpinned_by_reference_tests(oracle_lib, config, nm, ni, seed):
+    fl = make_fleet(config, nm, ni, seed)
+    if fl.type_config is not None:
+        pytest.skip("this seed draws type constraints; the brute force covers constrainTo == null, prefer == null")
+    o = oracle_from_synth(fl)
+    sd = make_decisions(fl, 1200, seed)
+    od, off, idx = oracle_inputs(fl, sd)
+    fresh = sd.fresh if len(sd.fresh) else None
+    res, coff, cidx, cload, ckeep = o.get_next_batch(od, fl.type_names, off, idx, fl.now_ms, seed * 7, fresh=fresh, want_candidates=True)
+    order = [int(x) for x in o.cluster_order()]
+    rows = fl.inst_rows
+    active = [bool(a) and not bool(s) for a, s in zip(rows["active"], rows["shutting_down"])]
+    replaced = set(fl.replaced_replicasets)
+    full_seen = nonfull_seen = multi = 0
+    for i in range(len(od)):
+        d = sd.dec[i]
+        self_idx = int(d["self"])
+        if d["fresh"] >= 0:
+            fr = sd.fresh[int(d["fresh"])]
+        else:
+            fr = rows[self_idx].copy()
+            fr["rpm"] = 0                                               # N7
+        b = brute_get_next(order, rows, fl.inst_ids, active, replaced, fl.min_space_units, self_idx, fr,
+                           bool(d["flags"] & L.DF_FAVOUR_SELF), int(od["last_used"][i]), set(int(x) for x in idx[off[i]:off[i + 1]]),
+                           fl.now_ms, _hash64(seed * 7, i))
+        assert b["target"] == int(res["target"][i]), (i, b, res[i])
+        if b.get("early") or not b["cands"]:
+            continue
+        want = [int(x) for x in cidx[coff[i]:coff[i + 1]]]
+        assert b["cands"] == want, (i, b["cands"][:6], want[:6])
+        assert b["keep"] == [bool(k) for k in ckeep[coff[i]:coff[i + 1]]], i
+        assert b["n_remaining"] == int(res["n_remaining"][i]) and b["pick"] == int(res["pick_index"][i]), i
+        multi += len(want) > 1
+        if res["flags"][i] & 4:
+            full_seen += 1
+        else:
+            nonfull_seen += 1
+    assert multi > 0 and full_seen + nonfull_seen > 100  # (MIX seeds draw all-full, mixed and all-free regimes: both walk tests are reached over the set)
+    test_shortlist_is_the_sorted_prefix_parity_unpinned_by_reference_tests.seen = getattr(
+        test_shortlist_is_the_sorted_prefix_parity_unpinned_by_reference_tests, "seen", np.zeros(2, dtype=np.int64)) + [full_seen, nonfull_seen]
+
+
+def test_brute_force_reached_both_walk_tests():
+    seen = getattr(test_shortlist_is_the_sorted_prefix_parity_unpinned_by_reference_tests, "seen", None)
+    if seen is None:
+        pytest.skip("runs after the brute-force cases")
+    assert seen[0] > 200 and seen[1] > 200, seen
+
+
+@pytest.mark.parametrize("config,ni,seed", [("C2", 300, 2), ("C3", 500, 3), ("C5", 400, 5), ("MIX", 200, 8), ("MIX", 200, 14), ("MIX", 120, 21)])
+def test_placement_order_is_a_strict_weak_order_on_uniform_vers_fleets(oracle_lib, config, ni, seed):
+    """Antisymmetry, transitivity (sampled triples) and agreement with the sorted cluster state; vers is uniform in the
+    synthetic fleets, so N1's non-transitive corner cannot occur."""
+    fl = make_fleet(config, 50, ni, seed)
+    assert len(set(int(v) for v in fl.inst_rows["vers"])) == 1
+    o = oracle_from_synth(fl)
+    order = [int(x) for x in o.cluster_order()]
+    n = len(order)
+    assert n == int(np.count_nonzero(fl.inst_rows["shutting_down"] == 0))
+    rng = np.random.default_rng(seed)
+    for a, b in zip(order[:-1], order[1:]):
+        assert o.compare(a, b) < 0 and o.compare(b, a) > 0
+    pos = {x: k for k, x in enumerate(order)}
+    for _ in range(3000):
+        a, b, c = (order[int(k)] for k in rng.integers(0, n, 3))
+        ab, ba = o.compare(a, b), o.compare(b, a)
+        assert (ab > 0) == (ba < 0) and (ab == 0) == (ba == 0) == (a == b)
+        assert (ab < 0) == (pos[a] < pos[b])
+        if ab < 0 and o.compare(b, c) < 0:
+            assert o.compare(a, c) < 0
+
+
+def test_rpm_filter_thresholds_independent_rederivation(oracle_lib):
+    """MM:4957-4980 on hand-built shortlists: three instances with equal keys except rpm, decisions whose lastUsed walks
+    through the five age bands.  The caller is never a candidate (inactive), so every non-best candidate records the
+    caller's fresh rpm (N2) -- given explicitly through a fresh row."""
+    now = 1_760_000_000_000
+    o = ob.OracleFleet(1000, 600_000, 2560)
+    o.types_set(None)
+    rows = np.zeros(4, dtype=ob.INST)
+    rows["capacity"], rows["used"], rows["lru_time"], rows["l_threads"], rows["active"] = 100_000, 10_000, now - 3_600_000, 8, 1
+    rows["rpm"] = [150, 400, 700, 0]
+    rows["active"][3] = 0
+    for i in range(4):
+        o.instance_event(ob.ADDED, i, rows[i], f"pod-{i}", now_ms=now)
+    for fresh_rpm in (0, 120, 200, 460, 650):
+        fresh = rows[3:4].copy()
+        fresh["rpm"] = fresh_rpm
+        for ago in (-5000, 1000, 60_000, 3_600_000, 2 * 86_400_000, 6 * 86_400_000):
+            od = np.zeros(1, dtype=ob.DECISION)
+            od["type_idx"], od["self"], od["fresh_idx"], od["last_used"] = -1, 3, 0, now - ago
+            res, coff, cidx, cload, ckeep = o.get_next_batch(od, [], np.zeros(2, dtype=np.int64), np.zeros(0, dtype=np.int32), now, 5,
+                                                            fresh=fresh, want_candidates=True)
+            loads = [150, fresh_rpm, fresh_rpm]                        # best records its own rpm, the others the caller's (N2)
+            assert [int(x) for x in cload[:3]] == loads
+            mn = max(100, min(loads))
+            def drop(rpm):
+                if rpm < 100 or ago >= 5 * 86_400_000:
+                    return False
+                return ((ago < -1000 and rpm > int(1.1 * mn)) or (ago < 5000 and rpm > int(1.5 * mn)) or (ago < 720_000 and rpm > 3 * mn)
+                        or (ago < 86_400_000 and rpm > 4 * mn))
+            assert [bool(k) for k in ckeep[:3]] == [not drop(r) for r in loads], (fresh_rpm, ago)
