@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define MMP_ABI_VERSION 1
+#define MMP_ABI_VERSION 2
 
 enum {
   MMP_OK = 0,
@@ -249,7 +249,16 @@ int32_t mmp_instance_partition(mmp_fleet *, int32_t idx);
 int32_t mmp_reaper_select(mmp_fleet *, int32_t partition, int64_t now_ms, uint8_t *taken, int32_t *out_models, int32_t cap);
 
 /* ---- plug point 3: per-instance time-ordered weighted LRU (CLHM:821-858, 590-652, 329-352; LD:243-288) ---- */
-enum { MMP_LRU_INSERT = 0, MMP_LRU_TOUCH = 1, MMP_LRU_RESIZE = 2, MMP_LRU_REMOVE = 3, MMP_LRU_SET_CAPACITY = 4 };
+enum { MMP_LRU_INSERT = 0, MMP_LRU_TOUCH = 1, MMP_LRU_RESIZE = 2, MMP_LRU_REMOVE = 3, MMP_LRU_SET_CAPACITY = 4,
+       /* loadLocal's admission as ONE checked event: churn guard (MM:3872-3884: instance full and its
+        * oldest entry younger than min_churn_age_ms -> rejected), putIfAbsent of a 1-unit placeholder at last_used
+        * (INSERTION_WEIGHT MM:5011, 5061), "the new entry was immediately evicted" (MM:5145-5148), early reject (MM:5185-5190:
+        * weight > capacity, or last_used > 0 && weight > free && last_used < oldestTime), then inflate to `weight` and
+        * "check whether we were evicted when growing" (MM:2094-2106).  Outcome per event through mmp_lru_apply_status. */
+       MMP_LRU_LOAD = 5 };
+/* outcome of an MMP_LRU_LOAD event (-1 for other events) */
+enum { MMP_LOAD_ACCEPTED = 0, MMP_LOAD_CHURN_REJECT = 2, MMP_LOAD_FELL_THROUGH = 3, MMP_LOAD_EARLY_REJECT = 4, MMP_LOAD_EVICTED_GROWING = 5,
+       MMP_LOAD_ENTRY_EXISTS = 6 };
 typedef struct {
   int32_t op;         /* MMP_LRU_* */
   int32_t instance;   /* which instance's cache */
@@ -268,8 +277,58 @@ int32_t mmp_lru_init(mmp_fleet *, int32_t n_instances, const int64_t *capacity, 
 /* applies events in order per instance (instances are independent); evictions are returned grouped by event order
  * within each instance, oldest first (CLHM:329-352).  Returns the number of evictions (<= cap written). */
 int32_t mmp_lru_apply(mmp_fleet *, const mmp_lru_event *ev, int32_t n, int64_t now_ms, mmp_eviction *out, int32_t cap);
+/* the same, also returning the outcome of every event (status[i] = MMP_LOAD_* for MMP_LRU_LOAD events, -1 otherwise) */
+int32_t mmp_lru_apply_status(mmp_fleet *, const mmp_lru_event *ev, int32_t n, int64_t now_ms, mmp_eviction *out, int32_t cap,
+                             int32_t *status);
 /* per-instance oldestTime() (CLHM:1125-1133, -1 if empty), weightedSize() and size() */
 int32_t mmp_lru_state(mmp_fleet *, int32_t n_instances, int64_t *oldest, int64_t *weighted, int32_t *count);
+
+/* ---- the closed loop on the device (SURVEY.md §8a rows a11 admission, a12 rebalance; §8f-1 ingest / ordering maintenance,
+ * §8f-4 fleet simulator; BASELINE.json configs[3] "churn").  One call = one republish window (2 s, INSTANCE_REC_PUBLISH_MIN_
+ * PERIOD_MS MM:232) of the WHOLE fleet, evaluated against the instance and model records as committed at its start (N6):
+ *   REQUEST of a model with registered copies -> runtimeCache.get on copy (u mod copies) in registration order;
+ *   REQUEST of a model with none: the first one in the window is a cache miss -> getNext (self = caller, lastUsed = t) ->
+ *     loadLocal on the target (MMP_LRU_LOAD's admission rules) -> evictions -> onEviction (MM:2875-2931: deregistration;
+ *     a copy loaded more than 2 x load_timeout_ms ago whose type set is < 95 % full is queued for ensureLoadedElsewhere and
+ *     placed first in the next window, MM:2915-2931); later misses of the same model in the window are coalesced;
+ *   REMOVE -> runtimeCache.remove on every registered copy;
+ *   then the registry changes, publishInstanceRecord with its significance thresholds (MM:5390-5470) per instance, and a
+ *   commit (re-rank under PLACEMENT_ORDER, tables, bitmap) -- all on the device.  The host only reads the reports.
+ * Requires an unsharded fleet whose models have at most 4 registered copies + failed loads.  Replaces nothing in the
+ * reference 1:1 (each pod runs its own loop there); it is the batched, fleet-wide form of it for simulation / what-if runs. ---- */
+enum { MMP_CHURN_REQUEST = 0, MMP_CHURN_REMOVE = 1 };
+typedef struct { int32_t type; int32_t model; int32_t caller; uint32_t u; int64_t t; } mmp_churn_event;
+typedef struct {
+  int32_t model, self, target, n_candidates;
+  int32_t status;  /* MMP_LOAD_* of the load, 1 = nowhere to load (getNext null), 7 = queued reload skipped (the model has a
+                      copy again), 8 = malformed, 9 = accepted but evicted again later in the window */
+  int32_t event;   /* index of the REQUEST that caused it, or -1 - k for the k-th queued ensureLoadedElsewhere */
+} mmp_churn_decision;
+typedef struct { int32_t instance, model; int64_t last_used; int32_t weight, order, reload; } mmp_churn_eviction;
+typedef struct { int64_t load_timeout_ms; int64_t last_published_ms; int32_t slots_per_instance; int32_t reserved; } mmp_churn_config;
+typedef struct {
+  int32_t n_published, n_carry, n_coalesced, n_lru_events;
+  float ms_classify, ms_place, ms_route, ms_apply, ms_registry, ms_commit, ms_total;  /* CUDA-event times of the phases */
+  float reserved;
+} mmp_churn_report;
+/* one cache per instance index (capacity = its published capacity), empty; needs a committed snapshot */
+int32_t mmp_churn_init(mmp_fleet *, const mmp_churn_config *cfg);
+/* resident copies at the start of a trace: putIfAbsent(model, weight, last_used) on `instance`, registered at load_ts.
+ * (The registry side -- mmp_model_upsert with the same instances as loaded copies -- is the caller's.) */
+int32_t mmp_churn_seed(mmp_fleet *, int32_t n, const int32_t *instance, const int32_t *model, const int64_t *last_used,
+                       const int32_t *weight, const int64_t *load_ts, int64_t now_ms);
+/* events in trace order with now0 <= t < now1.  Reports: the window's decisions in order (queued reloads first), its
+ * evictions grouped by instance in listener order, every instance's published row after the window (rows_out: max_instances
+ * rows, may be NULL).  Ends with a committed snapshot: placement calls after it see the new epoch. */
+int32_t mmp_churn_step(mmp_fleet *, const mmp_churn_event *ev, int32_t n, int64_t now0, int64_t now1, uint64_t seed,
+                       mmp_churn_decision *dec_out, int32_t dec_cap, int32_t *n_dec, mmp_churn_eviction *evict_out, int32_t evict_cap,
+                       int32_t *n_evict, mmp_instance_row *rows_out, mmp_churn_report *report);
+/* registry state of one model as the device holds it: row + the 4 inline instance indices (first copy_count = loaded) */
+int32_t mmp_churn_model(mmp_fleet *, int32_t model, mmp_model_row *row, int32_t *instances4);
+/* which path the last mmp_fleet_commit took: 1 = structural (host: string ranks, type-constraint sets, sort), 2 = device
+ * (numeric instance updates / model-record deltas only: scattered into the device-resident tables, re-ranked and rebuilt
+ * there); and its duration on the host clock */
+int32_t mmp_commit_info(mmp_fleet *, int32_t *path, double *ms);
 
 #ifdef __cplusplus
 }

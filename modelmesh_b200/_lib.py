@@ -38,7 +38,26 @@ EVICTION = np.dtype([("instance", "<i4"), ("model", "<i4"), ("last_used", "<i8")
                     align=True)
 assert INSTANCE_ROW.itemsize == 64 and MODEL_ROW.itemsize == 24 and DECISION_IN.itemsize == 32
 assert DECISION_OUT.itemsize == 8 and DECISION_TRACE.itemsize == 32 and CLUSTER_STATS.itemsize == 32
+CHURN_EVENT = np.dtype([("type", "<i4"), ("model", "<i4"), ("caller", "<i4"), ("u", "<u4"), ("t", "<i8")], align=True)
+CHURN_DECISION = np.dtype([("model", "<i4"), ("self", "<i4"), ("target", "<i4"), ("n_candidates", "<i4"), ("status", "<i4"),
+                           ("event", "<i4")], align=True)
+CHURN_EVICTION = np.dtype([("instance", "<i4"), ("model", "<i4"), ("last_used", "<i8"), ("weight", "<i4"), ("order", "<i4"),
+                           ("reload", "<i4")], align=True)
 assert LRU_EVENT.itemsize == 24 and EVICTION.itemsize == 24
+assert CHURN_EVENT.itemsize == 24 and CHURN_DECISION.itemsize == 24 and CHURN_EVICTION.itemsize == 32
+LRU_LOAD = 5
+CHURN_REQUEST, CHURN_REMOVE = 0, 1
+
+
+class ChurnConfig(C.Structure):
+    _fields_ = [("load_timeout_ms", C.c_int64), ("last_published_ms", C.c_int64), ("slots_per_instance", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class ChurnReport(C.Structure):
+    _fields_ = [("n_published", C.c_int32), ("n_carry", C.c_int32), ("n_coalesced", C.c_int32), ("n_lru_events", C.c_int32),
+                ("ms_classify", C.c_float), ("ms_place", C.c_float), ("ms_route", C.c_float), ("ms_apply", C.c_float),
+                ("ms_registry", C.c_float), ("ms_commit", C.c_float), ("ms_total", C.c_float), ("reserved", C.c_float)]
 
 DF_FAVOUR_SELF = 1
 DF_MODEL_LAST_USED = 2
@@ -101,6 +120,12 @@ SYMBOLS = [
     ("mmp_lru_init", _I32, [_P, _I32, _P, _I32]),
     ("mmp_lru_apply", _I32, [_P, _P, _I32, _I64, _P, _I32]),
     ("mmp_lru_state", _I32, [_P, _I32, _P, _P, _P]),
+    ("mmp_lru_apply_status", _I32, [_P, _P, _I32, _I64, _P, _I32, _P]),
+    ("mmp_churn_init", _I32, [_P, C.c_void_p]),
+    ("mmp_churn_seed", _I32, [_P, _I32, _P, _P, _P, _P, _P, _I64]),
+    ("mmp_churn_step", _I32, [_P, _P, _I32, _I64, _I64, _U64, _P, _I32, C.POINTER(_I32), _P, _I32, C.POINTER(_I32), _P, C.c_void_p]),
+    ("mmp_churn_model", _I32, [_P, _I32, _P, _P]),
+    ("mmp_commit_info", _I32, [_P, C.POINTER(_I32), C.POINTER(C.c_double)]),
     ("mmp_shard_unique_id", _I32, [_P]),
     ("mmp_shard_connect", _I32, [_P, _P]),
     ("mmp_shard_words", _I32, [_P, C.POINTER(_I32), C.POINTER(_I32)]),

@@ -112,6 +112,9 @@ struct HostSnapshot {
   // instance columns for the stats / reaper kernels, by rank
   std::vector<int64_t> cap_col;
   std::vector<int32_t> lthreads_col, linprog_col;
+  // dense string ranks of the tie-break chain (MM:4697-4700), by rank: kept for the device-side re-ranking of later,
+  // non-structural commits (strings do not change between structural commits)
+  std::vector<uint32_t> tie_id, tie_loc, tie_zone, tie_lab;
 };
 
 class HostState {
@@ -129,13 +132,33 @@ class HostState {
   std::vector<int32_t> edge_inl;
   std::unordered_map<int32_t, std::vector<int32_t>> edge_ovf;
   int32_t n_models_used = 0;
-  bool dirty_models = true;
   std::string err;
   // Instance ids -> indices, maintained by upsert/remove.  Model records ingested as JSON name instances BY ID (MR:69,73);
   // the ids are kept and resolved against this table at every commit, so the two KV listeners may deliver in any order.
   std::unordered_map<JStr, int32_t> id_index;
   std::unordered_map<int32_t, std::vector<JStr>> json_ids;  // model -> loaded ∪ failed ids as the record named them
   uint64_t inst_gen = 1, json_resolved_gen = 0;             // id table generation / the one the JSON models were last resolved against
+  // ---- what changed since the last commit (mmp_fleet_commit picks its path from these) ----
+  // structural: the set of live instances, their strings / labels / siMap membership, the type configuration or the
+  // replicaset list changed -> string ranks, type masks and partitions are rebuilt on the host (build_snapshot).
+  // Otherwise only numeric columns and model records changed: they are scattered into the device-resident tables and
+  // the snapshot is re-ranked and rebuilt ON THE DEVICE (commit_kernels.cuh).
+  bool structural_dirty = true;
+  std::vector<int32_t> dirty_inst, dirty_models;
+  std::vector<uint8_t> inst_dirty_flag, model_dirty_flag;
+  bool all_models_dirty = true, ovf_dirty = true;
+  void mark_inst(int32_t idx) { if (!inst_dirty_flag[idx]) { inst_dirty_flag[idx] = 1; dirty_inst.push_back(idx); } }
+  void mark_model(int32_t m) {
+    if (all_models_dirty) return;
+    if (!model_dirty_flag[m]) { model_dirty_flag[m] = 1; dirty_models.push_back(m); }
+    if (dirty_models.size() > models.size() / 8 + 1024) all_models_dirty = true;
+  }
+  void clear_dirty() {
+    structural_dirty = false; all_models_dirty = false; ovf_dirty = false;
+    for (int32_t i : dirty_inst) inst_dirty_flag[i] = 0;
+    for (int32_t m : dirty_models) model_dirty_flag[m] = 0;
+    dirty_inst.clear(); dirty_models.clear();
+  }
 
   void init(const mmp_config &c) {
     cfg = c;
@@ -143,6 +166,8 @@ class HostState {
     type_names.assign(1, std::string());
     models.assign((size_t)c.max_models, mmp_model_row{});
     edge_inl.assign((size_t)c.max_models * EDGE_INL, -1);
+    inst_dirty_flag.assign((size_t)c.max_instances, 0);
+    model_dirty_flag.assign((size_t)c.max_models, 0);
   }
 
   int32_t upsert_instance(int32_t idx, const mmp_instance_row *row, const char *id, const char *loc, const char *zone,
@@ -151,6 +176,15 @@ class HostState {
     if (const char *m = validate_row(*row)) { err = m; return MMP_E_ARG; }
     HostInstance &h = inst[idx];
     JStr nid = utf8_to_utf16(id);
+    {  // anything but a change of the numeric columns is structural
+      std::vector<JStr> nl;
+      for (int32_t i = 0; i < n_labels; i++) nl.push_back(utf8_to_utf16(labels[i]));
+      std::sort(nl.begin(), nl.end());
+      if (!h.present || h.id != nid || h.has_loc != (loc != nullptr) || h.loc != utf8_to_utf16(loc) || h.has_zone != (zone != nullptr) ||
+          h.zone != utf8_to_utf16(zone) || h.labels != nl || h.row.active != row->active || h.row.shutting_down != row->shutting_down)
+        structural_dirty = true;
+      else mark_inst(idx);
+    }
     if (!h.present || h.id != nid) {  // the id table changes: models held by id are re-resolved at the next commit
       if (h.present) { auto it = id_index.find(h.id); if (it != id_index.end() && it->second == idx) id_index.erase(it); }
       id_index[nid] = idx;
@@ -169,6 +203,8 @@ class HostState {
   int32_t update_instance(int32_t idx, const mmp_instance_row *row) {
     if (idx < 0 || idx >= cfg.max_instances || !row || !inst[idx].present) { err = "instance not present"; return MMP_E_ARG; }
     if (const char *m = validate_row(*row)) { err = m; return MMP_E_ARG; }
+    if (inst[idx].row.active != row->active || inst[idx].row.shutting_down != row->shutting_down) structural_dirty = true;
+    else mark_inst(idx);
     inst[idx].row = *row;
     return MMP_OK;
   }
@@ -178,6 +214,7 @@ class HostState {
       auto it = id_index.find(inst[idx].id);
       if (it != id_index.end() && it->second == idx) id_index.erase(it);
       inst_gen++;
+      structural_dirty = true;
     }
     inst[idx] = HostInstance();
     return MMP_OK;
@@ -186,6 +223,7 @@ class HostState {
     if (n < 0 || (n > 0 && !prefixes)) { err = "bad replicaset list"; return MMP_E_ARG; }
     replaced_rs.clear();
     for (int32_t i = 0; i < n; i++) replaced_rs.insert(utf8_to_utf16(prefixes[i]));
+    structural_dirty = true;
     return MMP_OK;
   }
   int32_t set_model(int32_t m, const mmp_model_row *row, const int32_t *ids, int32_t n_ids, bool from_json = false) {
@@ -197,10 +235,10 @@ class HostState {
     models[m] = *row;
     models[m].reserved = (uint32_t)n_ids;  // library-private: size of the exclusion row (instance-shard early-out)
     for (int i = 0; i < EDGE_INL; i++) edge_inl[(size_t)m * EDGE_INL + i] = i < n_ids ? ids[i] : -1;
-    if (n_ids > EDGE_INL) edge_ovf[m].assign(ids + EDGE_INL, ids + n_ids);
-    else if (!edge_ovf.empty()) edge_ovf.erase(m);
+    if (n_ids > EDGE_INL) { edge_ovf[m].assign(ids + EDGE_INL, ids + n_ids); ovf_dirty = true; }
+    else if (!edge_ovf.empty() && edge_ovf.erase(m)) ovf_dirty = true;
+    mark_model(m);
     if (m + 1 > n_models_used) n_models_used = m + 1;
-    dirty_models = true;
     return MMP_OK;
   }
   // Words per bitmap row, rounded up to 32 words so that every row starts on a 128-byte line and is a whole number
@@ -243,6 +281,7 @@ class HostState {
     int32_t id = (int32_t)type_names.size();
     type_names.push_back(name);
     type_ids[name] = id;
+    structural_dirty = true;  // the type-id -> mask-slot table grows
     return id;
   }
 
@@ -259,35 +298,10 @@ class HostState {
     return v;
   }
 
-  // ---- PLACEMENT_ORDER as a comparator over numeric columns + dense string ranks ----
-  struct OrderKey {
-    int64_t vers, rem, lru, cap;
-    int32_t count, free_threads, lip, rpm;
-    uint32_t id_rank, loc_rank, zone_rank, labels_rank;
-    bool full, shutting_down;
-  };
-  // literal restatement of MM:4646-4703 on OrderKey (shutting-down records never reach here, MM:1462-1464)
-  static int compare_keys(const OrderKey &a, const OrderKey &b, int64_t churn2) {
-    if (a.shutting_down != b.shutting_down) return a.shutting_down ? 1 : -1;
-    if (a.vers != b.vers) {
-      if (a.vers > b.vers) { if (!a.full || a.lru > churn2) return -1; }
-      else if (!b.full || b.lru > churn2) return 1;
-    }
-    if (a.full != b.full) return a.full ? 1 : -1;
-    if (a.full && a.lru != b.lru) return a.lru < b.lru ? -1 : 1;
-    if (a.count != b.count) return a.count < b.count ? -1 : 1;  // counts validated to [0,1e9]: the int subtraction cannot wrap
-    if (a.rem != b.rem) return a.rem > b.rem ? -1 : 1;
-    if (!a.full && a.lru != b.lru) return a.lru < b.lru ? -1 : 1;
-    if (a.free_threads != b.free_threads) return a.free_threads > b.free_threads ? -1 : 1;
-    if (a.lip != b.lip) return a.lip < b.lip ? -1 : 1;
-    if (a.cap != b.cap) return a.cap > b.cap ? -1 : 1;
-    if (a.rpm != b.rpm) return a.rpm < b.rpm ? -1 : 1;
-    if (a.id_rank != b.id_rank) return a.id_rank < b.id_rank ? -1 : 1;
-    if (a.loc_rank != b.loc_rank) return a.loc_rank < b.loc_rank ? -1 : 1;
-    if (a.zone_rank != b.zone_rank) return a.zone_rank < b.zone_rank ? -1 : 1;
-    if (a.labels_rank != b.labels_rank) return a.labels_rank < b.labels_rank ? -1 : 1;
-    return 0;
-  }
+  // ---- PLACEMENT_ORDER as a comparator over numeric columns + dense string ranks: OrderKey / compare_keys live in
+  // place_core.cuh (shared with the device-side ranking of the fast commit path) ----
+  typedef mmp::OrderKey OrderKey;
+  static int compare_keys(const OrderKey &a, const OrderKey &b, int64_t churn2) { return mmp::compare_keys(a, b, churn2); }
 
   template <class Cmp>
   static void merge_sort(std::vector<int32_t> &v, Cmp less) {  // tolerant of a non-transitive comparator (N1)
@@ -373,6 +387,7 @@ class HostState {
     merge_sort(ord, [&](int32_t a, int32_t b) { return compare_keys(keys[a], keys[b], churn2) < 0; });
 
     s.rows.resize(n);
+    s.tie_id.resize(n); s.tie_loc.resize(n); s.tie_zone.resize(n); s.tie_lab.resize(n);
     s.rank_of.assign(NI, -1);
     s.cap_col.resize(n); s.lthreads_col.resize(n); s.linprog_col.resize(n);
     s.rs.assign(RW, 0); s.full.assign(RW, 0);
@@ -389,6 +404,7 @@ class HostState {
       row.lru = keys[k].lru; row.rem = keys[k].rem; row.count = h.row.count; row.rpm = h.row.rpm; row.idx = idx;
       row.flags = keys[k].full ? 1u : 0u;
       s.rank_of[idx] = r;
+      s.tie_id[r] = keys[k].id_rank; s.tie_loc[r] = keys[k].loc_rank; s.tie_zone[r] = keys[k].zone_rank; s.tie_lab[r] = keys[k].labels_rank;
       s.cap_col[r] = h.row.capacity; s.lthreads_col[r] = h.row.l_threads; s.linprog_col[r] = h.row.l_in_prog;
       if (keys[k].full) s.full[r >> 5] |= 1u << (r & 31);
       // MM:4769-4770: iid.length() >= 7 and first six chars name a likely-replaced replicaset
@@ -880,11 +896,12 @@ inline int32_t HostState::set_model_json(int32_t m, const char *json, int32_t si
 }
 
 inline int32_t HostState::set_types_json(const char *json) {
-  if (!json || !*json) { tc_enabled = false; tc_config.clear(); return MMP_OK; }
+  if (!json || !*json) { tc_enabled = false; tc_config.clear(); structural_dirty = true; return MMP_OK; }
   std::map<std::string, TypeConfig> cfgmap;
   std::string e;
   if (!TcJson(json).parse(cfgmap, e)) { err = "type constraints json: " + e; return MMP_E_ARG; }
   tc_enabled = true;
+  structural_dirty = true;
   tc_config.swap(cfgmap);
   for (auto &t : tc_config) intern_type(t.first);
   return MMP_OK;

@@ -20,6 +20,7 @@
 #include <thrust/iterator/counting_iterator.h>
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_place(const SnapshotView s
 // ---------------------------------------------------------------------------------------------------------------
 static constexpr int LANE_WIN = 14;     // row words copied out of the landing stage per decision: the first LANE_WIN words of the
                                         // decision's compressed word list (LaneTables::nzw); later steps read the row from L2
-static constexpr int LANE_BUDGET = 96;  // walk steps a lane may spend before handing its decision to the whole warp
+static constexpr int LANE_BUDGET = 192;  // walk steps a lane may spend before handing its decision to the whole warp
 struct LaneLayout {
   uint32_t row_bytes, stride, stage_bytes, ns, warps;
   uint32_t off_bar, off_busy, off_uses, off_warp, per_warp;
@@ -366,7 +367,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotVie
     const int i = b * 32 + lane;
     if (b >= nb || i >= n) return false;
     const int4 *dp = reinterpret_cast<const int4 *>(in + i);
-    const int4 a = __ldg(dp), c = __ldg(dp + 1);
+    int4 a, c;  // streamed once: no L1 allocation (the lane routine's tables are what should stay there)
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(dp));
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w) : "l"(dp + 1));
     d.model = a.x; d.self = a.y; d.last_used = (int64_t)(((uint64_t)(uint32_t)a.w << 32) | (uint32_t)a.z);
     d.flags = (uint32_t)c.x; d.fresh = c.y; d.extra_off = c.z; d.extra_n = c.w;
     return true;
@@ -446,7 +449,20 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotVie
     {
       uint32_t *w = win + lane * (LANE_WIN + 1);
       const uint32_t WS_ = (uint32_t)s.word_lo;
-      if (!skip) {
+      // dense front (the slot's first LANE_WIN candidate words are row words 0, 1, 2, ...: every C3-like fleet): 128-bit
+      // copies; otherwise gather the listed words one by one
+      const bool dense = WS_ == 0 && win_words == (uint32_t)LANE_WIN && wl[0] == 0x00010000u && wl[1] == 0x00030002u && wl[2] == 0x00050004u &&
+                         wl[3] == 0x00070006u && wl[4] == 0x00090008u && wl[5] == 0x000b000au && wl[6] == 0x000d000cu;
+      if (__all_sync(0xffffffffu, dense || skip)) {
+        if (!skip) {
+#pragma unroll
+          for (int j = 0; j < (LANE_WIN + 3) / 4; j++) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(my_row + j * 4);
+            w[j * 4] = q.x; w[j * 4 + 1] = q.y;
+            if (j * 4 + 2 < LANE_WIN) { w[j * 4 + 2] = q.z; w[j * 4 + 3] = q.w; }
+          }
+        }
+      } else if (!skip) {
 #pragma unroll
         for (int j = 0; j < LANE_WIN; j++) {
           const uint32_t wi = (wl[j >> 1] >> ((j & 1) * 16)) & 0xffffu;
@@ -472,7 +488,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotVie
     bool handled = true;
     const uint64_t my_id = id_base + (uint64_t)(orig_id ? (valid ? orig_id[b * 32 + lane] : 0) : b * 32 + lane);
     if ((mode & 1) == 0)
-      handled = decide_stream(s, T, c, valid && !skip, win + lane * (LANE_WIN + 1), win_words, s.excl + (size_t)m * RW, self_eword,
+      handled = decide_stream(s, T, c, valid && !skip, win + lane * (LANE_WIN + 1), win_words, wl, s.excl + (size_t)m * RW, self_eword,
                               now, seed, my_id, WarpVote(), o, budget);
     else { o.target = (int32_t)(self_eword & 1u) - 1; o.n_candidates = 0; }  // MMP_LANE_MODE=1: stream-only probe (no decisions)
     // ---- what the lane routine declined: the whole warp redoes it, reading the row from global memory (L2) ----
@@ -628,11 +644,14 @@ struct DevBuf {
   template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+#include "commit_kernels.cuh"
+
 struct DeviceSnapshot {
   DevBuf excl, cand, candx, pref, has_pref, type_slot, full, rows, rank_of, csum, lsum, models;
   DevBuf cap_col, lthreads_col, linprog_col, part_of_rank, count_col, cand_before, nzw, nz_n;
   SnapshotView view{};
   HostSnapshot host;  // kept for introspection and the small host-side parts of stats / reaper
+  bool host_stale = false;  // built on the device: the rank-space vectors of `host` are downloaded on first use (host_mirror)
   int32_t n_models = 0;
   void release() {
     for (DevBuf *b : {&excl, &cand, &candx, &pref, &has_pref, &type_slot, &full, &rows, &rank_of, &csum, &lsum, &models,
@@ -667,7 +686,15 @@ struct mmp_fleet {
   int cur = 0;
   int32_t epoch = 0;
   cudaStream_t commit_stream = nullptr;
-  DevBuf d_edge_inl, d_ovf_pairs, d_flush, d_dbg;
+  DevBuf d_flush, d_dbg;
+  ChurnState churn;             // the closed loop (churn_kernels.cuh)
+  int64_t structural_epoch = 0; // bumped by every structural commit
+  LiveState live;               // device-resident tables every non-structural commit works from (commit_kernels.cuh)
+  std::mutex mirror_mu;         // host_mirror(): lazy download of a device-built snapshot's rank-space vectors
+  int commit_host_only = 0;     // MMP_COMMIT=host: every commit takes the structural (host) path (A/B and cross-check)
+  bool device_ahead = false;    // the closed loop (churn_kernels.cuh) changed the registry on the device: host tables are behind
+  int32_t last_commit_path = 0; // 1 structural (host), 2 device
+  double last_commit_ms = 0;
   ncclComm_t comm = nullptr;    // instance-shard communicator (mmp_shard_connect)
   std::mutex comm_mu;           // collectives of one communicator are issued by one thread at a time
   std::atomic<int64_t> open_decisions{0};  // decisions that needed the row-gather pass so far
@@ -686,7 +713,7 @@ struct mmp_fleet {
   int lanes = 1;                // MMP_KERNEL=tile selects the cooperative-tile kernel (k_place) instead of k_place_lanes
   int lane_warps = 0;           // warps per block of k_place_lanes (MMP_LANE_WARPS = 8 | 10 | 12 | 14 | 16 | 20); 0 = by launch size
   // LRU store (plug point 3)
-  DevBuf lru_ts, lru_seq, lru_weight, lru_model, lru_cap, lru_wsize, lru_count, lru_seqctr;
+  DevBuf lru_ts, lru_seq, lru_weight, lru_model, lru_cap, lru_wsize, lru_count, lru_seqctr, lru_loadts;
   int32_t lru_n = 0, lru_slots = 0;
 };
 
@@ -996,6 +1023,7 @@ int32_t mmp_fleet_create(const mmp_config *cfg, mmp_fleet **out) {
   if (const char *t = getenv("MMP_LANE_WARPS")) { int v = atoi(t); if (v == 8 || v == 10 || v == 12 || v == 14 || v == 16 || v == 20) f->lane_warps = v; }
   if (const char *t = getenv("MMP_LANE_STAGES")) f->lane_stages = atoi(t);
   if (const char *t = getenv("MMP_LANE_MODE")) f->lane_mode = atoi(t);
+  if (const char *t = getenv("MMP_COMMIT")) f->commit_host_only = strcmp(t, "host") == 0;
   if (const char *t = getenv("MMP_LANE_BUDGET")) { int v = atoi(t); if (v >= 1 && v <= 4096) f->lane_budget = v; }
   if (const char *t = getenv("MMP_SHARD_CHUNKS")) f->shard_chunks = atoi(t);
   if (f->lane_mode & 2) { CK(f->d_dbg.ensure(128)); CK(cudaMemset(f->d_dbg.p, 0, 128)); }
@@ -1021,8 +1049,12 @@ void mmp_fleet_destroy(mmp_fleet *f) {
   for (auto &c : f->ctx_free) { destroy_ctx(c.get()); }
   f->ctx_free.clear();
   f->snaps[0].release(); f->snaps[1].release();
-  for (DevBuf *b : {&f->d_edge_inl, &f->d_ovf_pairs, &f->d_flush, &f->lru_ts, &f->lru_seq, &f->lru_weight, &f->lru_model,
-                    &f->lru_cap, &f->lru_wsize, &f->lru_count, &f->lru_seqctr})
+  for (DevBuf *b : {&f->live.inst_rows, &f->live.inst_tie, &f->live.inst_meta, &f->live.cand_idx, &f->live.pref_idx, &f->live.edges,
+                    &f->live.models, &f->live.ovf_pairs, &f->live.keys, &f->live.rs_words, &f->live.flags, &f->live.scratch_idx,
+                    &f->live.scratch_rows, &f->live.scratch_edges})
+    b->release();
+  for (DevBuf *b : {&f->d_flush, &f->lru_ts, &f->lru_seq, &f->lru_weight, &f->lru_model,
+                    &f->lru_cap, &f->lru_wsize, &f->lru_count, &f->lru_seqctr, &f->lru_loadts})
     b->release();
   if (f->commit_stream) cudaStreamDestroy(f->commit_stream);
   delete f;
@@ -1070,19 +1102,12 @@ int32_t mmp_models_bulk(mmp_fleet *f, int32_t first, int32_t n, const mmp_model_
   return MMP_OK;
 }
 
-int32_t mmp_fleet_commit(mmp_fleet *f) {
-  NEED(f);
-  std::lock_guard<std::mutex> g(f->ingest_mu);
-  int32_t rc = set_device(f);
-  if (rc < 0) return rc;
-  DeviceSnapshot &ds = f->snaps[1 - f->cur];
+// ---- commit: structural path (host build + upload of everything, live tables included) ----
+static int32_t commit_structural(mmp_fleet *f, DeviceSnapshot &ds, cudaStream_t st) {
   f->hs.resolve_json_models();
   if (const char *m = f->hs.build_snapshot(ds.host)) { g_err = m; return MMP_E_ARG; }
+  ds.host_stale = false;
   const HostSnapshot &h = ds.host;
-  cudaStream_t st = f->commit_stream;
-  const int RW = h.row_words;
-  const int32_t nm = f->hs.n_models_used;
-  ds.n_models = nm;
   CK(upload_vec(ds.cand, h.cand, st)); CK(upload_vec(ds.pref, h.pref, st)); CK(upload_vec(ds.has_pref, h.has_pref, st));
   CK(upload_vec(ds.type_slot, h.type_slot_hp, st)); CK(upload_vec(ds.candx, h.candx, st)); CK(upload_vec(ds.full, h.full, st));
   CK(upload_vec(ds.rows, h.rows, st)); CK(upload_vec(ds.rank_of, h.rank_of, st)); CK(upload_vec(ds.csum, h.csum, st));
@@ -1092,27 +1117,198 @@ int32_t mmp_fleet_commit(mmp_fleet *f) {
   CK(upload_vec(ds.count_col, h.count_col, st));
   CK(upload_vec(ds.cand_before, h.candx_before, st));
   CK(upload_vec(ds.nzw, h.nzw, st)); CK(upload_vec(ds.nz_n, h.nz_n, st));
-  // model rows (each snapshot keeps its own copy so in-flight readers of the other epoch are undisturbed)
+  // ---- the live tables later (non-structural) commits re-rank from ----
+  LiveState &lv = f->live;
+  const int32_t NI = f->hs.cfg.max_instances, NIW = (NI + 31) / 32, n = h.n_ranks, RW = h.row_words;
+  lv.niw = NIW;
+  std::vector<mmp_instance_row> rows((size_t)NI);
+  std::vector<uint4> tie((size_t)NI, make_uint4(0, 0, 0, 0));
+  std::vector<int2> meta((size_t)NI, make_int2(-1, 0));
+  for (int32_t i = 0; i < NI; i++) rows[i] = f->hs.inst[i].present ? f->hs.inst[i].row : mmp_instance_row{};
+  std::vector<uint32_t> cidx((size_t)h.n_slots * NIW, 0u), pidx((size_t)h.n_slots * NIW, 0u);
+  for (int32_t r = 0; r < n; r++) {
+    const int32_t i = h.rows[r].idx;
+    tie[i] = make_uint4(h.tie_id[r], h.tie_loc[r], h.tie_zone[r], h.tie_lab[r]);
+    meta[i] = make_int2(h.part_of_rank[r], 1 | (((h.rs[r >> 5] >> (r & 31)) & 1u) ? 2 : 0));
+    for (int32_t sl = 0; sl < h.n_slots; sl++) {
+      if ((h.cand[(size_t)sl * RW + (r >> 5)] >> (r & 31)) & 1u) cidx[(size_t)sl * NIW + (i >> 5)] |= 1u << (i & 31);
+      if ((h.pref[(size_t)sl * RW + (r >> 5)] >> (r & 31)) & 1u) pidx[(size_t)sl * NIW + (i >> 5)] |= 1u << (i & 31);
+    }
+  }
+  CK(upload_vec(lv.inst_rows, rows, st)); CK(upload_vec(lv.inst_tie, tie, st)); CK(upload_vec(lv.inst_meta, meta, st));
+  CK(upload_vec(lv.cand_idx, cidx, st)); CK(upload_vec(lv.pref_idx, pidx, st));
+  CK(cudaStreamSynchronize(st));  // the staging vectors above go out of scope
+  lv.tmpl = h;
+  lv.valid = true;
+  f->structural_epoch++;
+  return MMP_OK;
+}
+
+// ---- commit: device path.  Returns 1 when the fleet needs the host path after all (mixed versions, N1) ----
+static int32_t commit_device(mmp_fleet *f, DeviceSnapshot &ds, cudaStream_t st) {
+  LiveState &lv = f->live;
+  const HostSnapshot &t = lv.tmpl;
+  const int32_t NI = f->hs.cfg.max_instances, n = t.n_ranks, RW = t.row_words, NS = t.n_slots;
+  // numeric instance updates since the last commit
+  const int32_t nd = (int32_t)f->hs.dirty_inst.size();
+  if (nd) {
+    std::vector<mmp_instance_row> rows((size_t)nd);
+    for (int32_t k = 0; k < nd; k++) rows[k] = f->hs.inst[f->hs.dirty_inst[k]].row;
+    CK(upload_vec(lv.scratch_idx, f->hs.dirty_inst, st)); CK(upload_vec(lv.scratch_rows, rows, st));
+    k_scatter_inst_rows<<<(nd + 255) / 256, 256, 0, st>>>(lv.scratch_idx.as<int32_t>(), lv.scratch_rows.as<mmp_instance_row>(), nd,
+                                                          lv.inst_rows.as<mmp_instance_row>());
+    f->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));  // staging vector
+  }
+  // sizes of the snapshot's tables (the live set did not change since the template was built)
+  CK(ds.cand.ensure((size_t)NS * RW * 4)); CK(ds.pref.ensure((size_t)NS * RW * 4)); CK(ds.candx.ensure((size_t)NS * RW * 4));
+  CK(ds.full.ensure((size_t)RW * 4)); CK(ds.rows.ensure((size_t)std::max(n, 1) * sizeof(RankRow))); CK(ds.rank_of.ensure((size_t)NI * 4));
+  CK(ds.csum.ensure((size_t)RW * sizeof(WordSumI))); CK(ds.lsum.ensure((size_t)RW * sizeof(WordSumL)));
+  CK(ds.cap_col.ensure((size_t)std::max(n, 1) * 8)); CK(ds.lthreads_col.ensure((size_t)std::max(n, 1) * 4));
+  CK(ds.linprog_col.ensure((size_t)std::max(n, 1) * 4)); CK(ds.part_of_rank.ensure((size_t)std::max(n, 1) * 4));
+  CK(ds.count_col.ensure((size_t)RW * 32 * 4)); CK(ds.cand_before.ensure((size_t)NS * 4));
+  CK(ds.nzw.ensure((size_t)NS * RW * 2)); CK(ds.nz_n.ensure((size_t)NS * 4));
+  CK(upload_vec(ds.has_pref, t.has_pref, st)); CK(upload_vec(ds.type_slot, t.type_slot_hp, st));
+  CK(lv.keys.ensure((size_t)NI * sizeof(OrderKey))); CK(lv.rs_words.ensure((size_t)RW * 4)); CK(lv.flags.ensure(16));
+  CK(cudaMemsetAsync(lv.flags.p, 0, 16, st));
+  CK(cudaMemsetAsync(ds.full.p, 0, (size_t)RW * 4, st)); CK(cudaMemsetAsync(lv.rs_words.p, 0, (size_t)RW * 4, st));
+  CK(cudaMemsetAsync(ds.count_col.p, 0, (size_t)RW * 32 * 4, st));
+  const long long churn2 = (long long)((uint64_t)f->hs.cfg.min_churn_age_ms * 2u);
+  const long long vers0 = n > 0 ? (long long)f->hs.inst[t.rows[0].idx].row.vers : 0;
+  const int blocks = (NI + 127) / 128;
+  k_rank_keys<<<blocks, 128, 0, st>>>(lv.inst_rows.as<mmp_instance_row>(), lv.inst_tie.as<uint4>(), lv.inst_meta.as<int2>(), NI,
+                                     (long long)f->hs.cfg.min_space_units, lv.keys.as<OrderKey>(), vers0, lv.flags.as<int>());
+  k_rank_count<<<blocks, 128, 0, st>>>(lv.keys.as<OrderKey>(), lv.inst_meta.as<int2>(), NI, churn2, ds.rank_of.as<int32_t>());
+  k_build_rank_tables<<<blocks, 128, 0, st>>>(lv.inst_rows.as<mmp_instance_row>(), lv.inst_meta.as<int2>(), ds.rank_of.as<int32_t>(), NI,
+                                             (long long)f->hs.cfg.min_space_units, ds.rows.as<RankRow>(), ds.cap_col.as<int64_t>(),
+                                             ds.lthreads_col.as<int32_t>(), ds.linprog_col.as<int32_t>(), ds.part_of_rank.as<int32_t>(),
+                                             ds.count_col.as<int32_t>(), ds.full.as<uint32_t>(), lv.rs_words.as<uint32_t>());
+  k_word_summaries<<<(RW + 127) / 128, 128, 0, st>>>(ds.rows.as<RankRow>(), n, RW, ds.csum.as<WordSumI>(), ds.lsum.as<WordSumL>());
+  k_permute_masks<<<(NS * RW + 127) / 128, 128, 0, st>>>(lv.cand_idx.as<uint32_t>(), lv.pref_idx.as<uint32_t>(), lv.niw, ds.rows.as<RankRow>(), n,
+                                                        RW, NS, lv.rs_words.as<uint32_t>(), ds.cand.as<uint32_t>(), ds.candx.as<uint32_t>(),
+                                                        ds.pref.as<uint32_t>());
+  k_slot_lists<<<(NS + 31) / 32, 32, 0, st>>>(ds.cand.as<uint32_t>(), ds.candx.as<uint32_t>(), t.any_rs, RW, NS, t.word_lo, t.word_hi,
+                                             ds.nzw.as<uint16_t>(), ds.nz_n.as<int32_t>(), ds.cand_before.as<int32_t>());
+  f->launches += 6;
+  CK(cudaGetLastError());
+  int flags = 0;
+  CK(cudaMemcpyAsync(&flags, lv.flags.p, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (flags & 1) return 1;
+  // structural part of the host mirror; its rank-space vectors are downloaded on first use
+  ds.host = HostSnapshot();
+  ds.host.n_ranks = t.n_ranks; ds.host.row_words = t.row_words; ds.host.n_slots = t.n_slots; ds.host.any_rs = t.any_rs;
+  ds.host.tc_enabled = t.tc_enabled; ds.host.has_pref = t.has_pref; ds.host.allowed_null = t.allowed_null;
+  ds.host.type_slot = t.type_slot; ds.host.type_slot_hp = t.type_slot_hp; ds.host.word_lo = t.word_lo; ds.host.word_hi = t.word_hi;
+  ds.host.excl_stride = t.excl_stride; ds.host.part_types = t.part_types; ds.host.part_type_ids = t.part_type_ids;
+  ds.host_stale = true;
+  return MMP_OK;
+}
+
+// rank-space vectors of a device-built snapshot, downloaded on first use (introspection, the reaper's host part)
+static int32_t host_mirror(mmp_fleet *f, const DeviceSnapshot &cds, const HostSnapshot **out) {
+  DeviceSnapshot &ds = const_cast<DeviceSnapshot &>(cds);
+  std::lock_guard<std::mutex> g(f->mirror_mu);
+  if (ds.host_stale) {
+    HostSnapshot &h = ds.host;
+    const int32_t n = h.n_ranks, RW = h.row_words, NS = h.n_slots, NI = f->hs.cfg.max_instances;
+    h.rows.resize((size_t)n); h.rank_of.resize((size_t)NI); h.cand.resize((size_t)NS * RW); h.pref.resize((size_t)NS * RW);
+    h.cap_col.resize((size_t)n); h.lthreads_col.resize((size_t)n); h.linprog_col.resize((size_t)n); h.part_of_rank.resize((size_t)n);
+    if (n) {
+      CK(cudaMemcpy(h.rows.data(), ds.rows.p, (size_t)n * sizeof(RankRow), cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(h.cap_col.data(), ds.cap_col.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(h.lthreads_col.data(), ds.lthreads_col.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(h.linprog_col.data(), ds.linprog_col.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(h.part_of_rank.data(), ds.part_of_rank.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    }
+    CK(cudaMemcpy(h.rank_of.data(), ds.rank_of.p, (size_t)NI * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(h.cand.data(), ds.cand.p, (size_t)NS * RW * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(h.pref.data(), ds.pref.p, (size_t)NS * RW * 4, cudaMemcpyDeviceToHost));
+    ds.host_stale = false;
+  }
+  *out = &ds.host;
+  return MMP_OK;
+}
+
+static int32_t sync_host_from_device(mmp_fleet *f);  // churn_kernels.cuh: registry changes made on the device -> host tables
+static int32_t commit_locked(mmp_fleet *f);
+
+int32_t mmp_fleet_commit(mmp_fleet *f) {
+  NEED(f);
+  std::lock_guard<std::mutex> g(f->ingest_mu);
+  return commit_locked(f);
+}
+}  // extern "C"
+static int32_t commit_locked(mmp_fleet *f) {
+  int32_t rc = set_device(f);
+  if (rc < 0) return rc;
+  const auto t0 = std::chrono::steady_clock::now();
+  DeviceSnapshot &ds = f->snaps[1 - f->cur];
+  cudaStream_t st = f->commit_stream;
+  LiveState &lv = f->live;
+  bool structural = f->hs.structural_dirty || !lv.valid || f->commit_host_only;
+  if (structural && f->device_ahead) { rc = sync_host_from_device(f); if (rc < 0) return rc; }
+  if (!structural) {
+    rc = commit_device(f, ds, st);
+    if (rc < 0) return rc;
+    if (rc == 1) structural = true;  // mixed versions: the literal comparator needs the host's merge sort (N1)
+  }
+  if (structural) { rc = commit_structural(f, ds, st); if (rc < 0) return rc; }
+  const HostSnapshot &h = ds.host;
+  const int RW = h.row_words;
+  const int32_t nm = f->hs.n_models_used;
+  ds.n_models = nm;
+  // ---- registry: model rows + edges live on the device; a commit sends only what changed on the host ----
+  CK(lv.models.ensure((size_t)std::max(f->hs.cfg.max_models, 1) * sizeof(mmp_model_row)));
+  CK(lv.edges.ensure((size_t)std::max(f->hs.cfg.max_models, 1) * HostState::EDGE_INL * 4));
+  if (!f->device_ahead) {
+    if (structural || f->hs.all_models_dirty) {
+      if (nm) {
+        CK(cudaMemcpyAsync(lv.models.p, f->hs.models.data(), (size_t)nm * sizeof(mmp_model_row), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(lv.edges.p, f->hs.edge_inl.data(), (size_t)nm * HostState::EDGE_INL * 4, cudaMemcpyHostToDevice, st));
+      }
+    } else if (!f->hs.dirty_models.empty()) {
+      const int32_t nd = (int32_t)f->hs.dirty_models.size();
+      std::vector<mmp_model_row> rows((size_t)nd);
+      std::vector<int4> ed((size_t)nd);
+      for (int32_t k = 0; k < nd; k++) {
+        const int32_t m = f->hs.dirty_models[k];
+        rows[k] = f->hs.models[m];
+        const int32_t *e = &f->hs.edge_inl[(size_t)m * HostState::EDGE_INL];
+        ed[k] = make_int4(e[0], e[1], e[2], e[3]);
+      }
+      CK(upload_vec(lv.scratch_idx, f->hs.dirty_models, st)); CK(upload_vec(lv.scratch_rows, rows, st)); CK(upload_vec(lv.scratch_edges, ed, st));
+      k_scatter_models<<<(nd + 255) / 256, 256, 0, st>>>(lv.scratch_idx.as<int32_t>(), lv.scratch_rows.as<mmp_model_row>(),
+                                                         lv.scratch_edges.as<int4>(), nd, lv.models.as<mmp_model_row>(), lv.edges.as<int4>());
+      f->launches++;
+      CK(cudaGetLastError());
+      CK(cudaStreamSynchronize(st));  // staging vectors
+    }
+    if (structural || f->hs.ovf_dirty) {
+      std::vector<int2> pairs;
+      for (auto &kv : f->hs.edge_ovf)
+        for (int32_t e : kv.second) pairs.push_back(make_int2(kv.first, e));
+      lv.n_ovf = (int32_t)pairs.size();
+      CK(upload_vec(lv.ovf_pairs, pairs, st));
+      CK(cudaStreamSynchronize(st));
+    }
+  }
+  // each snapshot keeps its own copy of the model rows so in-flight readers of the other epoch are undisturbed
   CK(ds.models.ensure((size_t)std::max(nm, 1) * sizeof(mmp_model_row)));
-  if (nm) CK(cudaMemcpyAsync(ds.models.p, f->hs.models.data(), (size_t)nm * sizeof(mmp_model_row), cudaMemcpyHostToDevice, st));
-  // exclusion bitmap in rank space: zero, then scatter the sparse loaded/failed lists
+  if (nm) CK(cudaMemcpyAsync(ds.models.p, lv.models.p, (size_t)nm * sizeof(mmp_model_row), cudaMemcpyDeviceToDevice, st));
+  // exclusion bitmap in rank space: zero, then scatter the device-resident loaded/failed lists (one write pass)
   const int ST = h.excl_stride;  // words per stored row: the whole row, or this instance shard's block
   CK(ds.excl.ensure((size_t)std::max(nm, 1) * ST * 4));
   if (nm) {
     CK(cudaMemsetAsync(ds.excl.p, 0, (size_t)nm * ST * 4, st));
-    CK(f->d_edge_inl.ensure((size_t)nm * HostState::EDGE_INL * 4));
-    CK(cudaMemcpyAsync(f->d_edge_inl.p, f->hs.edge_inl.data(), (size_t)nm * HostState::EDGE_INL * 4, cudaMemcpyHostToDevice, st));
-    k_build_bitmap<<<(nm + 255) / 256, 256, 0, st>>>(ds.excl.as<uint32_t>(), f->d_edge_inl.as<int4>(), ds.rank_of.as<int32_t>(), nm, ST,
+    k_build_bitmap<<<(nm + 255) / 256, 256, 0, st>>>(ds.excl.as<uint32_t>(), lv.edges.as<int4>(), ds.rank_of.as<int32_t>(), nm, ST,
                                                      h.word_lo, h.word_hi);
     f->launches++;
     CK(cudaGetLastError());
-    std::vector<int2> pairs;
-    for (auto &kv : f->hs.edge_ovf)
-      for (int32_t e : kv.second) pairs.push_back(make_int2(kv.first, e));
-    if (!pairs.empty()) {
-      CK(upload_vec(f->d_ovf_pairs, pairs, st));
-      k_build_bitmap_ovf<<<((int)pairs.size() + 255) / 256, 256, 0, st>>>(ds.excl.as<uint32_t>(), f->d_ovf_pairs.as<int2>(),
-                                                                         (int)pairs.size(), ds.rank_of.as<int32_t>(), ST, h.word_lo, h.word_hi);
+    if (lv.n_ovf) {
+      k_build_bitmap_ovf<<<(lv.n_ovf + 255) / 256, 256, 0, st>>>(ds.excl.as<uint32_t>(), lv.ovf_pairs.as<int2>(), lv.n_ovf,
+                                                                 ds.rank_of.as<int32_t>(), ST, h.word_lo, h.word_hi);
       f->launches++;
       CK(cudaGetLastError());
     }
@@ -1121,7 +1317,7 @@ int32_t mmp_fleet_commit(mmp_fleet *f) {
   SnapshotView &v = ds.view;
   v.n_ranks = h.n_ranks; v.row_words = RW; v.n_models = nm; v.max_instances = f->hs.cfg.max_instances;
   v.any_rs = h.any_rs; v.n_type_ids = (int32_t)h.type_slot.size(); v.min_space = f->hs.cfg.min_space_units;
-  v.word_lo = h.word_lo; v.word_hi = h.word_hi; v.excl_stride = ST; v.n_slots = h.n_slots;
+  v.word_lo = h.word_lo; v.word_hi = h.word_hi; v.excl_stride = ST; v.n_slots = h.n_slots; v.n_extra = 0;
   v.count_col = ds.count_col.as<int32_t>(); v.cand_before = ds.cand_before.as<int32_t>();
   v.nzw = ds.nzw.as<uint16_t>(); v.nz_n = ds.nz_n.as<int32_t>();
   v.excl = ds.excl.as<uint32_t>(); v.cand = ds.cand.as<uint32_t>(); v.pref = ds.pref.as<uint32_t>();
@@ -1133,8 +1329,18 @@ int32_t mmp_fleet_commit(mmp_fleet *f) {
     f->cur = 1 - f->cur;
     f->epoch++;
   }
-  f->hs.dirty_models = false;
+  f->hs.clear_dirty();
+  f->last_commit_path = structural ? 1 : 2;
+  f->last_commit_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return f->epoch;
+}
+extern "C" {
+/* which path the last commit took (1 = structural / host, 2 = device) and how long it took on the host clock */
+int32_t mmp_commit_info(mmp_fleet *f, int32_t *path, double *ms) {
+  NEED(f);
+  if (path) *path = f->last_commit_path;
+  if (ms) *ms = f->last_commit_ms;
+  return MMP_OK;
 }
 
 static int32_t place_impl(mmp_fleet *f, const mmp_decision_in *in, int32_t n, const mmp_instance_row *fresh, int32_t n_fresh,
@@ -1375,17 +1581,23 @@ int32_t mmp_row_words(mmp_fleet *f) { NEED(f); return f->hs.row_words(); }
 int32_t mmp_live_instances(mmp_fleet *f) { NEED(f); std::shared_lock<std::shared_mutex> rd(f->snap_mu); return f->snaps[f->cur].host.n_ranks; }
 int32_t mmp_cluster_order(mmp_fleet *f, int32_t *out_idx, int32_t cap) {
   NEED(f);
+  int32_t rc0 = set_device(f); if (rc0 < 0) return rc0;
   std::shared_lock<std::shared_mutex> rd(f->snap_mu);
-  const HostSnapshot &h = f->snaps[f->cur].host;
+  const HostSnapshot *hp = nullptr;
+  rc0 = host_mirror(f, f->snaps[f->cur], &hp); if (rc0 < 0) return rc0;
+  const HostSnapshot &h = *hp;
   for (int32_t r = 0; r < h.n_ranks && r < cap; r++) out_idx[r] = h.rows[r].idx;
   return h.n_ranks;
 }
 int32_t mmp_type_sets(mmp_fleet *f, int32_t type_id, int32_t n_idx, uint8_t *allowed, int32_t *allowed_null, uint8_t *preferred,
                       int32_t *preferred_null) {
   NEED(f);
+  int32_t rc0 = set_device(f); if (rc0 < 0) return rc0;
   std::shared_lock<std::shared_mutex> rd(f->snap_mu);
-  const HostSnapshot &s = f->snaps[f->cur].host;
   if (f->epoch == 0) { g_err = "no committed snapshot"; return MMP_E_EPOCH; }
+  const HostSnapshot *hp = nullptr;
+  rc0 = host_mirror(f, f->snaps[f->cur], &hp); if (rc0 < 0) return rc0;
+  const HostSnapshot &s = *hp;
   if (type_id < 0 || type_id > 65535) { g_err = "bad type id"; return MMP_E_ARG; }
   // a name interned after this snapshot was committed had no configuration in it: it resolves like id 0
   int sl = s.type_slot[type_id < (int32_t)s.type_slot.size() ? type_id : 0];
@@ -1399,8 +1611,11 @@ int32_t mmp_type_sets(mmp_fleet *f, int32_t type_id, int32_t n_idx, uint8_t *all
 }
 int32_t mmp_instance_partition(mmp_fleet *f, int32_t idx) {
   NEED(f);
+  int32_t rc0 = set_device(f); if (rc0 < 0) return rc0;
   std::shared_lock<std::shared_mutex> rd(f->snap_mu);
-  const HostSnapshot &s = f->snaps[f->cur].host;
+  const HostSnapshot *hp = nullptr;
+  rc0 = host_mirror(f, f->snaps[f->cur], &hp); if (rc0 < 0) return rc0;
+  const HostSnapshot &s = *hp;
   if (idx < 0 || idx >= (int32_t)s.rank_of.size() || s.rank_of[idx] < 0) return -1;
   return s.part_of_rank[s.rank_of[idx]];
 }
@@ -1409,3 +1624,4 @@ int64_t mmp_kernel_launches(mmp_fleet *f) { return f ? f->launches.load() : 0; }
 }  // extern "C"
 
 #include "scan_kernels.cuh"
+#include "churn_kernels.cuh"

@@ -85,6 +85,37 @@ struct SnapshotView {  // pointers into HBM (or host vectors in the CPU harness)
   const mmp_model_row *models; // [n_models]
 };
 
+// ---- PLACEMENT_ORDER (MM:4646-4703) on numeric columns + dense string ranks.  Host: merge sort at a structural commit
+// (host_state.hpp); device: rank = number of live instances that compare less (k_rank_count, the fast commit path). ----
+struct OrderKey {
+  int64_t vers, rem, lru, cap;
+  int32_t count, free_threads, lip, rpm;
+  uint32_t id_rank, loc_rank, zone_rank, labels_rank;
+  bool full, shutting_down;
+};
+// literal restatement of MM:4646-4703 on OrderKey (shutting-down records never reach here, MM:1462-1464)
+MMP_HD int compare_keys(const OrderKey &a, const OrderKey &b, int64_t churn2) {
+  if (a.shutting_down != b.shutting_down) return a.shutting_down ? 1 : -1;
+  if (a.vers != b.vers) {
+    if (a.vers > b.vers) { if (!a.full || a.lru > churn2) return -1; }
+    else if (!b.full || b.lru > churn2) return 1;
+  }
+  if (a.full != b.full) return a.full ? 1 : -1;
+  if (a.full && a.lru != b.lru) return a.lru < b.lru ? -1 : 1;
+  if (a.count != b.count) return a.count < b.count ? -1 : 1;  // counts validated to [0,1e9]: the int subtraction cannot wrap
+  if (a.rem != b.rem) return a.rem > b.rem ? -1 : 1;
+  if (!a.full && a.lru != b.lru) return a.lru < b.lru ? -1 : 1;
+  if (a.free_threads != b.free_threads) return a.free_threads > b.free_threads ? -1 : 1;
+  if (a.lip != b.lip) return a.lip < b.lip ? -1 : 1;
+  if (a.cap != b.cap) return a.cap > b.cap ? -1 : 1;
+  if (a.rpm != b.rpm) return a.rpm < b.rpm ? -1 : 1;
+  if (a.id_rank != b.id_rank) return a.id_rank < b.id_rank ? -1 : 1;
+  if (a.loc_rank != b.loc_rank) return a.loc_rank < b.loc_rank ? -1 : 1;
+  if (a.zone_rank != b.zone_rank) return a.zone_rank < b.zone_rank ? -1 : 1;
+  if (a.labels_rank != b.labels_rank) return a.labels_rank < b.labels_rank ? -1 : 1;
+  return 0;
+}
+
 // ---- Java-semantics helpers (wrapping arithmetic, truncating division, saturating double->int) ----
 MMP_HD int64_t jsub(int64_t a, int64_t b) { return (int64_t)((uint64_t)a - (uint64_t)b); }
 MMP_HD int32_t jaddi(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
@@ -461,7 +492,23 @@ MMP_HD void prepare_ctx_a(const SnapshotView &s, const mmp_decision_in &d, CtxA 
   if (d.extra_n < 0 || d.extra_n > 16 || (d.extra_n > 0 && (d.extra_off < 0 || (int64_t)d.extra_off + d.extra_n > (int64_t)s.n_extra))) a.ok = 0;
   a.self_rank = -1;
   a.mr.last_used = 0; a.mr.size_units = 0; a.mr.rpm = 0; a.mr.type_id = 0; a.mr.copy_count = 0; a.mr.fail_count = 0; a.mr.reserved = 0;
-  if (a.ok) { a.mr = s.models[d.model]; a.self_rank = s.rank_of[d.self]; }
+  if (a.ok) {
+#if defined(__CUDA_ARCH__)
+    // the 24-byte model row is read once per decision: keep it out of L1, where the lane routine's tables live
+    const int2 *mp = reinterpret_cast<const int2 *>(s.models + d.model);
+    int2 v0, v1, v2;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(v0.x), "=r"(v0.y) : "l"(mp));
+    asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(v1.x), "=r"(v1.y) : "l"(mp + 1));
+    asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(v2.x), "=r"(v2.y) : "l"(mp + 2));
+    a.mr.last_used = (int64_t)(((uint64_t)(uint32_t)v0.y << 32) | (uint32_t)v0.x);
+    a.mr.size_units = v1.x; a.mr.rpm = v1.y;
+    a.mr.type_id = (uint16_t)((uint32_t)v2.x & 0xffffu); a.mr.copy_count = (uint8_t)(((uint32_t)v2.x >> 16) & 0xffu);
+    a.mr.fail_count = (uint8_t)((uint32_t)v2.x >> 24); a.mr.reserved = (uint32_t)v2.y;
+    a.self_rank = __ldg(s.rank_of + d.self);
+#else
+    a.mr = s.models[d.model]; a.self_rank = s.rank_of[d.self];
+#endif
+  }
 }
 MMP_HD void prepare_ctx_b(const SnapshotView &s, const mmp_decision_in &d, const CtxA &a, const FreshRow *fresh_tab, int32_t n_fresh,
                           const int32_t *extra, DecisionCtx &c) {
@@ -721,11 +768,11 @@ struct WarpVote { MMP_D bool any(bool p) const { return __any_sync(0xffffffffu, 
 // The decision's exclusion row is seen through a WINDOW: ewin[k] = row word W(k) for k < win_words (k_place_lanes copies
 // these out of the TMA landing stage so that the stage can take the next rows while the lanes compute); steps beyond the
 // window read the row itself (erow_g: global memory, word index relative to word_lo -- the row has just been streamed, so it
-// is an L2 hit), or end the lane's attempt when erow_g is null.  self_eword = the row word that holds self's bit (anywhere
+// is an L2 hit), or end the lane's attempt when erow_g is null.  first8 = entries 0..7 of the slot's word list as four u16 pairs.  self_eword = the row word that holds self's bit (anywhere
 // in the row).  Must be called by every lane of the vote group (active = false for lanes without a decision).
 template <class V>
 MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const DecisionCtx &c, bool active, const uint32_t *ewin,
-                          uint32_t win_words, const uint32_t *erow_g, uint32_t self_eword, int64_t now, uint64_t seed,
+                          uint32_t win_words, const uint32_t *first8, const uint32_t *erow_g, uint32_t self_eword, int64_t now, uint64_t seed,
                           uint64_t decision_id, const V &vote, DecideOut &o, int32_t budget) {
   o.target = MMP_TARGET_NONE; o.n_candidates = 0; o.best = -1; o.n_remaining = 0; o.pick_index = 0; o.flags = 0;
   o.cut_rank = (int32_t)NONE_RANK; o.best_rank = -1; o.first_rank = -1;
@@ -740,46 +787,53 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
   const FreshRow fr = c.fr;
   int32_t left = budget;
   const bool has_x = d.extra_n > 0;
-  // The word list and the part of the row beyond the window are read in CHUNKS of 8 steps: one 16-byte load of 8 list
-  // entries and 8 independent loads of the row words they name, issued together, so a long walk pays one L2 round trip
-  // per 8 steps instead of two dependent ones per step (C5: walks of 100+ steps over sparse candidate masks).
-  uint32_t cur_chunk = 0xffffffffu;
-  uint32_t wq[4] = {0, 0, 0, 0};                     // 8 list entries (u16 pairs) of the current chunk
-  uint32_t eq[8] = {0, 0, 0, 0, 0, 0, 0, 0};         // their row words when the chunk reaches beyond the window
-  bool reach = true;                                 // false: the chunk lies beyond the window and there is no row to read
+  // The word list and the row are seen through a CHUNK of 8 consecutive steps [base, base + 8) held in registers: the list
+  // entries (u16 pairs) and the row words they name (from the window, or -- beyond it -- from the row in global memory: 8
+  // independent loads issued together).  A chunk is refilled for ALL walking lanes whenever one of them leaves its chunk
+  // (warp vote), so the lanes of a warp refill at the same loop iterations and a long walk (C5: 100+ steps over sparse
+  // candidate masks) pays one L2 round trip per 8 steps, not two dependent ones per step.  The first chunk (steps 0..7)
+  // comes from the caller's preloaded entries `first8` and the window: the common case touches no list memory at all.
+  uint32_t base = 0;
+  uint32_t wq[4] = {first8[0], first8[1], first8[2], first8[3]};
+  uint32_t eq[8];
   auto wsel = [&](uint32_t j) -> uint32_t {          // entry j (0..7) of the chunk, without dynamic register indexing
     uint32_t q = wq[0];
     q = (j >> 1) == 1 ? wq[1] : q; q = (j >> 1) == 2 ? wq[2] : q; q = (j >> 1) == 3 ? wq[3] : q;
     return (q >> ((j & 1u) * 16u)) & 0xffffu;
   };
-  auto fetch = [&](uint32_t k) {                     // make the chunk of step k current (k < NZ)
-    const uint32_t ci = k >> 3;
-    if (ci == cur_chunk) return;
-    cur_chunk = ci;
-#if defined(__CUDA_ARCH__)
-    const uint4 q = __ldg(reinterpret_cast<const uint4 *>(T.nzw) + ci);  // list rows are row_words (a multiple of 32) entries long
-    wq[0] = q.x; wq[1] = q.y; wq[2] = q.z; wq[3] = q.w;
-#else
-    for (int j = 0; j < 4; j++) wq[j] = (uint32_t)T.nzw[ci * 8 + 2 * j] | ((uint32_t)T.nzw[ci * 8 + 2 * j + 1] << 16);
-#endif
-    reach = true;
-    if (ci * 8u + 8u > win_words) {
-      if (erow_g == nullptr) reach = false;
-      else {
+  auto fill_rows = [&]() {                           // row words of the chunk's steps
 #pragma unroll
-        for (uint32_t j = 0; j < 8; j++) {
-          const uint32_t kk = ci * 8u + j;
-          eq[j] = (kk >= win_words && kk < NZ) ? ldro(erow_g + (wsel(j) - WS)) : 0u;
-        }
+    for (uint32_t j = 0; j < 8; j++) {
+      const uint32_t kk = base + j;
+      uint32_t e = 0;
+      if (kk < NZ) {
+        if (kk < win_words) e = ewin[kk];
+        else if (erow_g != nullptr) e = ldro(erow_g + (wsel(j) - WS));
       }
+      eq[j] = e;
     }
   };
-  auto W = [&](uint32_t k) -> uint32_t { return wsel(k & 7u); };  // after fetch(k)
-  // word W(k) of the decision's exclusion row (after fetch(k)); false when it is out of reach
+  fill_rows();
+  auto refill = [&](uint32_t k) {
+    base = k;
+#pragma unroll
+    for (uint32_t j = 0; j < 4; j++) {
+      const uint32_t k0 = k + 2 * j, k1 = k0 + 1;
+      const uint32_t lo16 = k0 < NZ ? (uint32_t)ldro(T.nzw + k0) : 0xffffu, hi16 = k1 < NZ ? (uint32_t)ldro(T.nzw + k1) : 0xffffu;
+      wq[j] = lo16 | (hi16 << 16);
+    }
+    fill_rows();
+  };
+  // to be called by every lane at the top of every walk iteration
+  auto sync = [&](bool walking, uint32_t k) {
+    const bool need = walking && k < NZ && (k - base) >= 8u;
+    if (vote.any(need)) { if (walking && k < NZ) refill(k); }
+  };
+  auto W = [&](uint32_t k) -> uint32_t { return wsel(k - base); };  // step k inside the current chunk
+  // word W(k) of the decision's exclusion row; false when it is out of reach (beyond the window and no row to read)
   auto Ew = [&](uint32_t k, uint32_t, uint32_t &e) -> bool {
-    if (k < win_words) { e = ewin[k]; return true; }
-    if (!reach) return false;
-    const uint32_t j = k & 7u;
+    if (k >= win_words && erow_g == nullptr) return false;
+    const uint32_t j = k - base;
     uint32_t v = eq[0];
     v = j == 1 ? eq[1] : v; v = j == 2 ? eq[2] : v; v = j == 3 ? eq[3] : v; v = j == 4 ? eq[4] : v;
     v = j == 5 ? eq[5] : v; v = j == 6 ? eq[6] : v; v = j == 7 ? eq[7] : v;
@@ -800,10 +854,10 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
     uint32_t k = 0;
     bool search = live;
     for (;;) {
+      sync(search, k);
       if (search) {
         if (k >= NZ || left <= 0) search = false;
         else {
-          fetch(k);
           const uint32_t wi = W(k);
           uint32_t e;
           if (!Ew(k, wi, e)) search = false;
@@ -840,11 +894,11 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
     uint32_t k = kb;
     bool search = live && !simple;
     for (;;) {
+      sync(search, k);
       if (search) {
         if (k >= NZ) search = false;                         // natural end of the row
         else if (left <= 0) { search = false; live = false; }
         else {
-          fetch(k);
           const uint32_t wi = W(k);
           uint32_t e;
           if (!Ew(k, wi, e)) { search = false; live = false; }
@@ -916,8 +970,8 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
     bool search = walk, mixed = false;
     for (;;) {
       for (;;) {
+        sync(search, k);
         if (search) {
-          if (k < NZ) fetch(k);
           if (k >= NZ || (wi = W(k)) >= stop_w) {  // the walk's natural end
             search = false;
             if (lim == NONE_RANK && open_end) open = true;
@@ -1004,9 +1058,9 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
     uint32_t k = k_lo;
     bool search = sel;
     for (;;) {
+      sync(search, k);
       if (search) {
         uint32_t wi = 0, e = 0;
-        if (k < NZ) fetch(k);
         if (k >= NZ || !Ew(k, (wi = W(k)), e)) { search = false; live = false; }  // cannot happen: kth < number of survivors, all in visited words
         else {
           uint32_t x = Sw(wi, e);

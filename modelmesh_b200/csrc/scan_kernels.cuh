@@ -132,7 +132,10 @@ static int32_t reaper_impl(mmp_fleet *f, int32_t partition, int64_t now, uint8_t
   std::shared_lock<std::shared_mutex> rd(f->snap_mu);
   if (f->epoch == 0) { g_err = "no committed snapshot"; return MMP_E_EPOCH; }
   const DeviceSnapshot &ds = f->snaps[f->cur];
-  const HostSnapshot &h = ds.host;
+  const HostSnapshot *hp = nullptr;
+  rc = host_mirror(f, ds, &hp);
+  if (rc < 0) return rc;
+  const HostSnapshot &h = *hp;
   const int np = (int)h.part_types.size();
   if (partition >= np || (partition >= 0 && !h.tc_enabled)) { g_err = "no such partition"; return MMP_E_ARG; }
   StatsResult sr;
@@ -236,8 +239,39 @@ static int32_t reaper_impl(mmp_fleet *f, int32_t partition, int64_t now, uint8_t
 // ---------------------------------------------------------------------------------------------------------------
 struct LruView {
   long long *ts; long long *seq; int *weight; int *model;   // [n][slots]
+  long long *loadts;                                        // [n][slots] registration time of the copy (MR.instanceIds value), -1: not registered
   long long *cap, *wsize, *seqctr; int *count;              // [n]
   int n, slots;
+};
+
+// one event of an instance's cache, as the kernels see it
+enum { LEV_INSERT = 0, LEV_TOUCH = 1, LEV_RESIZE = 2, LEV_REMOVE = 3, LEV_SET_CAPACITY = 4, LEV_LOAD = 5, LEV_SEED = 6 };
+struct LruEv {
+  int op, model, weight, order;  // order: what an eviction reports as its cause (event index / position in the epoch's trace)
+  int dec, pad;                  // LEV_LOAD: index of the placement decision that sent the load here
+  long long last_used, t;        // t: the event's own clock (churn epochs), or the registration time of a LEV_SEED entry
+};
+struct EvictRec { int instance, model; long long last_used; int weight, order, reload, seq; };
+struct Follow { int model, exclude; long long last_used; int weight, order, seq, inst; };  // a queued ensureLoadedElsewhere (MM:2922, 6905)
+
+// per-decision outcome of a checked load (the statuses of oracle/mm_sim.inc)
+enum { CH_ACCEPTED = 0, CH_NOWHERE = 1, CH_CHURN = 2, CH_FALLTHRU = 3, CH_EARLY = 4, CH_GROW_EVICTED = 5, CH_EXISTS = 6, CH_SKIPPED = 7,
+       CH_INVALID = 8, CH_EVICTED_LATER = 9 };
+
+// What the closed loop hooks into the LRU kernel (null pointers / enabled = 0 for a plain mmp_lru_apply)
+struct ChurnHooks {
+  int enabled;
+  long long min_space, min_churn_age, load_timeout;
+  int *status;                     // [n_decisions] CH_*
+  const int *dec_target;           // [n_decisions] instance the decision resolved to
+  const int *dec_of_model;         // [n_models] this epoch's decision for the model, -1
+  const int4 *edges;               // [n_models] registered instances (first copy_count = loaded)
+  const mmp_model_row *models;
+  unsigned *rm_mask;               // [n_models] bit j: edge j is deregistered at the end of the epoch
+  const unsigned char *type_ok;    // [n_type_ids] the type set is < 95 % full (MM:2918-2920)
+  int n_type_ids;
+  Follow *next; int *n_next; int next_cap;
+  unsigned char *force_publish;    // [n_instances]
 };
 
 __device__ __forceinline__ bool key_less(long long t1, long long s1, long long t2, long long s2) { return t1 < t2 || (t1 == t2 && s1 < s2); }
@@ -276,31 +310,112 @@ __device__ int lru_find(const LruView &v, int inst, int lane, int model, int *fr
   return found;
 }
 
-__global__ void k_lru_apply(LruView v, const mmp_lru_event *__restrict__ ev, const int *__restrict__ ev_order,
-                            const int *__restrict__ inst_off, long long now, mmp_eviction *out, int out_cap, int *out_n, int *err) {
+// One warp per instance applies its events in order.  LEV_LOAD is loadLocal's admission (a11): churn guard MM:3872-3884,
+// placeholder insert (INSERTION_WEIGHT = 1, MM:5011, 5061), immediate-eviction fall-through MM:5145-5148, early reject
+// MM:5185-5190, registration, inflate to the predicted size + grow-then-check MM:2094-2106.  With hooks.enabled every eviction
+// also runs the eviction listener's bookkeeping (onEviction MM:2875-2931): deregistration mark, the reload-elsewhere rule (a12).
+__global__ void k_lru_events(LruView v, const LruEv *__restrict__ ev, const int *__restrict__ ev_order, const int *__restrict__ inst_off,
+                             long long now_param, int use_ev_time, ChurnHooks hk, EvictRec *out, int out_cap, int *out_n, int *err) {
   const int lane = threadIdx.x & 31;
   const int inst = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (inst >= v.n) return;
+  const int p0 = inst_off[inst], p1 = inst_off[inst + 1];
+  if (p0 >= p1) return;
   const size_t base = (size_t)inst * v.slots;
   long long wsize = v.wsize[inst], capacity = v.cap[inst], ctr = v.seqctr[inst];
   int count = v.count[inst];
-  for (int p = inst_off[inst]; p < inst_off[inst + 1]; p++) {
-    const int ei = ev_order[p];
-    const mmp_lru_event e = ev[ei];
-    int free_slot;
-    int slot = (e.op == MMP_LRU_SET_CAPACITY) ? -1 : lru_find(v, inst, lane, e.model, &free_slot);
-    bool do_evict = false;
-    if (e.op == MMP_LRU_SET_CAPACITY) { capacity = e.last_used; do_evict = true; }
-    else if (e.op == MMP_LRU_INSERT && slot < 0) {
-      if (free_slot < 0) { if (lane == 0) atomicExch(err, 1); continue; }
+  int evseq = 0;
+  // evict() CLHM:329-352 + the listener; returns through *self_gone whether `watch_model` was among the victims
+  auto evict_loop = [&](const LruEv &e, long long now, int watch_model, bool *self_gone) {
+    while (wsize > capacity) {
+      long long t, s;
+      const int victim = lru_min_slot(v, inst, lane, false, 0, 0, &t, &s);
+      if (victim < 0) break;
+      const int w = v.weight[base + victim], m = v.model[base + victim];
+      const long long lt = v.loadts[base + victim];
+      __syncwarp();
+      if (m == watch_model && self_gone) *self_gone = true;
       if (lane == 0) {
-        v.model[base + free_slot] = e.model; v.weight[base + free_slot] = e.weight;
+        v.model[base + victim] = -1;
+        int reload = 0;
+        if (hk.enabled) {
+          const bool in_registry = lt >= 0;
+          const bool attempt = in_registry && (now - lt) > 2 * hk.load_timeout;  // MM:2901
+          if (in_registry) {
+            const int4 ed = hk.edges[m];
+            const int cc = hk.models[m].copy_count;
+            const int es[4] = {ed.x, ed.y, ed.z, ed.w};
+            for (int j = 0; j < 4 && j < cc; j++) if (es[j] == inst) atomicOr(&hk.rm_mask[m], 1u << j);
+          }
+          const int k2 = hk.dec_of_model[m];
+          if (k2 >= 0 && hk.dec_target[k2] == inst && hk.status[k2] == CH_ACCEPTED) hk.status[k2] = CH_EVICTED_LATER;
+          const int ty = hk.models[m].type_id;
+          if (attempt && hk.type_ok[ty < hk.n_type_ids ? ty : 0]) {  // MM:2916-2922
+            reload = 1;
+            const int q = atomicAdd(hk.n_next, 1);
+            if (q < hk.next_cap) hk.next[q] = Follow{m, inst, t, w, e.order, evseq, inst};
+          }
+          hk.force_publish[inst] = 1;
+        }
+        const int pos = atomicAdd(out_n, 1);
+        if (pos < out_cap) out[pos] = EvictRec{inst, m, t, w, e.order, reload, evseq};
+      }
+      evseq++;
+      __syncwarp();
+      wsize -= (w < 0 ? -w : w); count--;
+    }
+  };
+  for (int p = p0; p < p1; p++) {
+    const LruEv e = ev[ev_order[p]];
+    const long long now = use_ev_time ? e.t : now_param;
+    int free_slot;
+    int slot = (e.op == LEV_SET_CAPACITY) ? -1 : lru_find(v, inst, lane, e.model, &free_slot);
+    if (e.op == LEV_SET_CAPACITY) { capacity = e.last_used; evict_loop(e, now, -1, nullptr); continue; }
+    if (e.op == LEV_LOAD) {
+      // limit the rate of cache churn (MM:3872-3884)
+      if (hk.min_churn_age > 0 && capacity - wsize < hk.min_space) {
+        long long t, s;
+        const int o = lru_min_slot(v, inst, lane, false, 0, 0, &t, &s);
+        if (o >= 0 && t != 0x7fffffffffffffffLL && (t == 0 ? 0 : now - t) < hk.min_churn_age) { if (lane == 0) hk.status[e.dec] = CH_CHURN; continue; }
+      }
+      if (slot >= 0) { if (lane == 0) hk.status[e.dec] = CH_EXISTS; }  // putIfAbsent found an entry: afterRead below
+    }
+    if ((e.op == LEV_INSERT || e.op == LEV_SEED || e.op == LEV_LOAD) && slot < 0) {
+      if (free_slot < 0) { if (lane == 0) atomicExch(err, 1); continue; }
+      const int w0 = e.op == LEV_LOAD ? 1 : e.weight;  // INSERTION_WEIGHT MM:5011
+      if (lane == 0) {
+        v.model[base + free_slot] = e.model; v.weight[base + free_slot] = w0;
         v.ts[base + free_slot] = e.last_used == 0 ? now : e.last_used;   // Node ctor: touch(time) (CLHM:1352-1360)
         v.seq[base + free_slot] = ++ctr;
+        v.loadts[base + free_slot] = e.op == LEV_SEED ? e.t : -1;
       } else ++ctr;
       __syncwarp();
-      wsize += e.weight; count++; do_evict = true;                       // AddTask (CLHM:601-610)
-    } else if ((e.op == MMP_LRU_INSERT || e.op == MMP_LRU_TOUCH) && slot >= 0) {
+      wsize += w0; count++;                                              // AddTask (CLHM:601-610)
+      bool gone = false;
+      evict_loop(e, now, e.model, &gone);
+      if (e.op != LEV_LOAD) continue;
+      if (lane == 0) hk.force_publish[inst] = 1;
+      if (gone) { if (lane == 0) hk.status[e.dec] = CH_FALLTHRU; continue; }  // MM:5145-5148
+      // early reject MM:5185-5190 (capacity, weightedSize, oldestTime after the placeholder went in)
+      long long ot, os;
+      const int oi = lru_min_slot(v, inst, lane, false, 0, 0, &ot, &os);
+      const long long oldest = oi < 0 ? -1 : ot;
+      const long long abs_size = e.weight < 0 ? -(long long)e.weight : (long long)e.weight;
+      if (abs_size > capacity || (e.last_used > 0 && abs_size > capacity - wsize && e.last_used < oldest)) {
+        if (lane == 0) { v.model[base + free_slot] = -1; hk.status[e.dec] = CH_EARLY; }  // ce.remove()
+        __syncwarp();
+        wsize -= 1; count--;
+        continue;
+      }
+      if (lane == 0) { v.loadts[base + free_slot] = now; hk.status[e.dec] = CH_ACCEPTED; v.weight[base + free_slot] = e.weight; }  // MM:5203, 2100
+      __syncwarp();
+      wsize += (long long)e.weight - 1;
+      gone = false;
+      evict_loop(e, now, e.model, &gone);
+      if (gone && lane == 0) hk.status[e.dec] = CH_GROW_EVICTED;          // MM:2102-2106
+      continue;
+    }
+    if ((e.op == LEV_INSERT || e.op == LEV_TOUCH || e.op == LEV_LOAD || e.op == LEV_SEED) && slot >= 0) {
       // afterRead -> touch + reposition (CLHM:383-388, 477-505; LD:243-255)
       long long old_t = v.ts[base + slot], old_s = v.seq[base + slot];
       long long lu = e.last_used > 0 ? (old_t > e.last_used ? old_t : e.last_used) : now;
@@ -322,32 +437,29 @@ __global__ void k_lru_apply(LruView v, const mmp_lru_event *__restrict__ ev, con
         }
         __syncwarp();
       }
-    } else if (e.op == MMP_LRU_RESIZE && slot >= 0) {
+    } else if (e.op == LEV_RESIZE && slot >= 0) {
       int oldw = v.weight[base + slot];
       if (lane == 0) v.weight[base + slot] = e.weight;
       __syncwarp();
-      wsize += (long long)e.weight - oldw; do_evict = true;              // UpdateTask (CLHM:643-651), quiet
-    } else if (e.op == MMP_LRU_REMOVE && slot >= 0) {
+      wsize += (long long)e.weight - oldw;                               // UpdateTask (CLHM:643-651), quiet
+      evict_loop(e, now, -1, nullptr);
+    } else if (e.op == LEV_REMOVE && slot >= 0) {
       int w = v.weight[base + slot];
-      if (lane == 0) v.model[base + slot] = -1;
+      const long long lt = v.loadts[base + slot];
+      if (lane == 0) {
+        v.model[base + slot] = -1;
+        if (hk.enabled) {
+          hk.force_publish[inst] = 1;
+          if (lt >= 0) {  // deregisterModel
+            const int4 ed = hk.edges[e.model];
+            const int cc = hk.models[e.model].copy_count;
+            const int es[4] = {ed.x, ed.y, ed.z, ed.w};
+            for (int j = 0; j < 4 && j < cc; j++) if (es[j] == inst) atomicOr(&hk.rm_mask[e.model], 1u << j);
+          }
+        }
+      }
       __syncwarp();
       wsize -= (w < 0 ? -w : w); count--;                                // RemovalTask + makeDead (CLHM:614-628, 561-570)
-    }
-    if (do_evict) {
-      while (wsize > capacity) {                                          // evict() CLHM:329-352
-        long long t, s;
-        int victim = lru_min_slot(v, inst, lane, false, 0, 0, &t, &s);
-        if (victim < 0) break;
-        int w = v.weight[base + victim], m = v.model[base + victim];
-        __syncwarp();
-        if (lane == 0) {
-          v.model[base + victim] = -1;
-          int pos = atomicAdd(out_n, 1);
-          if (pos < out_cap) out[pos] = mmp_eviction{inst, m, t, w, ei};
-        }
-        __syncwarp();
-        wsize -= (w < 0 ? -w : w); count--;
-      }
     }
   }
   if (lane == 0) { v.wsize[inst] = wsize; v.cap[inst] = capacity; v.seqctr[inst] = ctr; v.count[inst] = count; }
@@ -365,6 +477,7 @@ __global__ void k_lru_state(LruView v, long long *oldest, long long *weighted, i
 static LruView lru_view(mmp_fleet *f) {
   LruView v;
   v.ts = f->lru_ts.as<long long>(); v.seq = f->lru_seq.as<long long>(); v.weight = f->lru_weight.as<int>(); v.model = f->lru_model.as<int>();
+  v.loadts = f->lru_loadts.as<long long>();
   v.cap = f->lru_cap.as<long long>(); v.wsize = f->lru_wsize.as<long long>(); v.seqctr = f->lru_seqctr.as<long long>();
   v.count = f->lru_count.as<int>(); v.n = f->lru_n; v.slots = f->lru_slots;
   return v;
@@ -406,6 +519,8 @@ int32_t mmp_lru_init(mmp_fleet *f, int32_t n, const int64_t *capacity, int32_t s
   std::lock_guard<std::mutex> g(f->ingest_mu);
   size_t tot = (size_t)n * slots;
   CK(f->lru_ts.ensure(tot * 8)); CK(f->lru_seq.ensure(tot * 8)); CK(f->lru_weight.ensure(tot * 4)); CK(f->lru_model.ensure(tot * 4));
+  CK(f->lru_loadts.ensure(tot * 8));
+  CK(cudaMemset(f->lru_loadts.p, 0xff, tot * 8));
   CK(f->lru_cap.ensure((size_t)n * 8)); CK(f->lru_wsize.ensure((size_t)n * 8)); CK(f->lru_seqctr.ensure((size_t)n * 8)); CK(f->lru_count.ensure((size_t)n * 4));
   CK(cudaMemset(f->lru_model.p, 0xff, tot * 4));
   CK(cudaMemset(f->lru_wsize.p, 0, (size_t)n * 8)); CK(cudaMemset(f->lru_count.p, 0, (size_t)n * 4));
@@ -416,7 +531,8 @@ int32_t mmp_lru_init(mmp_fleet *f, int32_t n, const int64_t *capacity, int32_t s
   return MMP_OK;
 }
 
-int32_t mmp_lru_apply(mmp_fleet *f, const mmp_lru_event *ev, int32_t n, int64_t now_ms, mmp_eviction *out, int32_t cap) {
+static int32_t lru_apply_impl(mmp_fleet *f, const mmp_lru_event *ev, int32_t n, int64_t now_ms, mmp_eviction *out, int32_t cap,
+                              int32_t *status) {
   NEED(f);
   if (n < 0 || (n > 0 && !ev) || cap < 0 || (cap > 0 && !out)) { g_err = "bad argument"; return MMP_E_ARG; }
   if (f->lru_n == 0) { g_err = "mmp_lru_init not called"; return MMP_E_STATE; }
@@ -426,10 +542,12 @@ int32_t mmp_lru_apply(mmp_fleet *f, const mmp_lru_event *ev, int32_t n, int64_t 
   std::lock_guard<std::mutex> g(f->ingest_mu);
   // group events by instance, keeping their order (counting sort)
   std::vector<int> off((size_t)f->lru_n + 1, 0), order((size_t)n);
+  std::vector<LruEv> lev((size_t)n);
   for (int32_t i = 0; i < n; i++) {
-    if (ev[i].instance < 0 || ev[i].instance >= f->lru_n || ev[i].op < 0 || ev[i].op > MMP_LRU_SET_CAPACITY || ev[i].last_used < 0 ||
+    if (ev[i].instance < 0 || ev[i].instance >= f->lru_n || ev[i].op < 0 || ev[i].op > MMP_LRU_LOAD || ev[i].last_used < 0 ||
         (ev[i].op != MMP_LRU_SET_CAPACITY && ev[i].model < 0)) { g_err = "bad LRU event"; return MMP_E_ARG; }
     off[ev[i].instance + 1]++;
+    lev[i] = LruEv{ev[i].op, ev[i].model, ev[i].weight, i, i, 0, ev[i].last_used, now_ms};
   }
   for (int i = 0; i < f->lru_n; i++) off[i + 1] += off[i];
   { std::vector<int> pos(off.begin(), off.end() - 1); for (int32_t i = 0; i < n; i++) order[pos[ev[i].instance]++] = i; }
@@ -437,32 +555,46 @@ int32_t mmp_lru_apply(mmp_fleet *f, const mmp_lru_event *ev, int32_t n, int64_t 
   if (!c) { g_err = "cannot create CUDA stream"; return MMP_E_CUDA; }
   struct Rel { mmp_fleet *f; PlaceCtx *c; ~Rel() { release_ctx(f, c); } } rel{f, c};
   cudaStream_t s = c->stream;
-  CK(c->d_in.ensure((size_t)n * sizeof(mmp_lru_event)));
+  CK(c->d_in.ensure((size_t)n * sizeof(LruEv)));
   CK(c->d_extra.ensure((size_t)n * 4));
   CK(c->d_fresh.ensure(off.size() * 4));
-  CK(c->d_out.ensure((size_t)std::max(cap, 1) * sizeof(mmp_eviction)));
-  CK(c->d_trace.ensure(16));
-  CK(cudaMemcpyAsync(c->d_in.p, ev, (size_t)n * sizeof(mmp_lru_event), cudaMemcpyHostToDevice, s));
+  CK(c->d_out.ensure((size_t)std::max(cap, 1) * sizeof(EvictRec)));
+  CK(c->d_trace.ensure(16 + (size_t)n * 4));
+  CK(cudaMemcpyAsync(c->d_in.p, lev.data(), (size_t)n * sizeof(LruEv), cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(c->d_extra.p, order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(c->d_fresh.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice, s));
   CK(cudaMemsetAsync(c->d_trace.p, 0, 16, s));
-  int warps_per_block = 4;
-  int grid = (f->lru_n + warps_per_block - 1) / warps_per_block;
-  k_lru_apply<<<grid, warps_per_block * 32, 0, s>>>(lru_view(f), c->d_in.as<mmp_lru_event>(), c->d_extra.as<int>(), c->d_fresh.as<int>(),
-                                                   now_ms, c->d_out.as<mmp_eviction>(), cap, c->d_trace.as<int>(), c->d_trace.as<int>() + 1);
+  CK(cudaMemsetAsync(c->d_trace.as<char>() + 16, 0xff, (size_t)n * 4, s));  // status -1: not a load
+  ChurnHooks hk{};
+  hk.enabled = 0;
+  hk.min_space = f->hs.cfg.min_space_units; hk.min_churn_age = f->hs.cfg.min_churn_age_ms;
+  hk.status = c->d_trace.as<int>() + 4;
+  const int warps_per_block = 4;
+  const int grid = (f->lru_n + warps_per_block - 1) / warps_per_block;
+  k_lru_events<<<grid, warps_per_block * 32, 0, s>>>(lru_view(f), c->d_in.as<LruEv>(), c->d_extra.as<int>(), c->d_fresh.as<int>(), now_ms, 0, hk,
+                                                    c->d_out.as<EvictRec>(), cap, c->d_trace.as<int>(), c->d_trace.as<int>() + 1);
   f->launches++;
   CK(cudaGetLastError());
   int hdr[2] = {0, 0};
   CK(cudaMemcpyAsync(hdr, c->d_trace.p, 8, cudaMemcpyDeviceToHost, s));
+  if (status) CK(cudaMemcpyAsync(status, c->d_trace.as<char>() + 16, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   if (hdr[1]) { g_err = "LRU slot capacity exceeded for some instance (raise slots_per_instance)"; return MMP_E_NOMEM; }
   int got = std::min(hdr[0], cap);
-  std::vector<mmp_eviction> tmp((size_t)got);
-  if (got) CK(cudaMemcpy(tmp.data(), c->d_out.p, (size_t)got * sizeof(mmp_eviction), cudaMemcpyDeviceToHost));
-  // each instance's evictions were appended in its own order; group by instance keeping that order
-  std::stable_sort(tmp.begin(), tmp.end(), [](const mmp_eviction &a, const mmp_eviction &b) { return a.instance < b.instance; });
-  for (int i = 0; i < got; i++) out[i] = tmp[i];
+  std::vector<EvictRec> tmp((size_t)got);
+  if (got) CK(cudaMemcpy(tmp.data(), c->d_out.p, (size_t)got * sizeof(EvictRec), cudaMemcpyDeviceToHost));
+  // each instance's evictions were appended in its own order (seq); group by instance keeping that order
+  std::sort(tmp.begin(), tmp.end(), [](const EvictRec &a, const EvictRec &b) { return a.instance != b.instance ? a.instance < b.instance : a.seq < b.seq; });
+  for (int i = 0; i < got; i++) out[i] = mmp_eviction{tmp[i].instance, tmp[i].model, tmp[i].last_used, tmp[i].weight, tmp[i].order};
   return hdr[0];
+}
+
+int32_t mmp_lru_apply(mmp_fleet *f, const mmp_lru_event *ev, int32_t n, int64_t now_ms, mmp_eviction *out, int32_t cap) {
+  return lru_apply_impl(f, ev, n, now_ms, out, cap, nullptr);
+}
+int32_t mmp_lru_apply_status(mmp_fleet *f, const mmp_lru_event *ev, int32_t n, int64_t now_ms, mmp_eviction *out, int32_t cap,
+                             int32_t *status) {
+  return lru_apply_impl(f, ev, n, now_ms, out, cap, status);
 }
 
 int32_t mmp_lru_state(mmp_fleet *f, int32_t n, int64_t *oldest, int64_t *weighted, int32_t *count) {

@@ -12,8 +12,8 @@ from typing import Iterable, Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import (CLUSTER_STATS, DECISION_IN, DECISION_OUT, DECISION_TRACE, EVICTION, INSTANCE_ROW, LRU_EVENT,
-                   MODEL_ROW, MmpConfig)
+from ._lib import (CHURN_DECISION, CHURN_EVENT, CHURN_EVICTION, CLUSTER_STATS, DECISION_IN, DECISION_OUT, DECISION_TRACE, EVICTION,
+                   INSTANCE_ROW, LRU_EVENT, MODEL_ROW, ChurnConfig, ChurnReport, MmpConfig)
 
 
 class MmpError(RuntimeError):
@@ -218,6 +218,55 @@ class Fleet:
         if n > cap:
             raise MmpError(-1, f"eviction buffer too small ({n} > {cap})")
         return out[:n].copy()
+
+    def lru_apply_status(self, events: np.ndarray, now_ms: int, cap: Optional[int] = None):
+        """mmp_lru_apply + the outcome of every MMP_LRU_LOAD event (loadLocal's admission rules)."""
+        events = np.ascontiguousarray(events, dtype=LRU_EVENT)
+        cap = cap or max(16, 4 * len(events))
+        out = np.zeros(cap, dtype=EVICTION)
+        status = np.zeros(len(events), dtype=np.int32)
+        n = self._ck(self.lib.mmp_lru_apply_status(self.h, _ptr(events), len(events), now_ms, _ptr(out), cap, _ptr(status)))
+        if n > cap:
+            raise MmpError(-1, f"eviction buffer too small ({n} > {cap})")
+        return out[:n].copy(), status
+
+    # ---- the closed loop (churn) ----
+    def churn_init(self, load_timeout_ms: int, last_published_ms: int, slots_per_instance: int):
+        cfg = ChurnConfig(load_timeout_ms, last_published_ms, slots_per_instance, 0)
+        self._ck(self.lib.mmp_churn_init(self.h, C.byref(cfg)))
+        self._lru_n = self.max_instances
+
+    def churn_seed(self, instance, model, last_used, weight, load_ts, now_ms: int):
+        a = [np.ascontiguousarray(instance, dtype=np.int32), np.ascontiguousarray(model, dtype=np.int32),
+             np.ascontiguousarray(last_used, dtype=np.int64), np.ascontiguousarray(weight, dtype=np.int32),
+             np.ascontiguousarray(load_ts, dtype=np.int64)]
+        self._ck(self.lib.mmp_churn_seed(self.h, len(a[0]), _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), _ptr(a[4]), now_ms))
+
+    def churn_step(self, events: np.ndarray, now0: int, now1: int, seed: int, want_rows: bool = True):
+        ev = np.ascontiguousarray(events, dtype=CHURN_EVENT)
+        cap_d = len(ev) + 65536
+        cap_e = 4 * len(ev) + 65536
+        dec = np.zeros(cap_d, dtype=CHURN_DECISION)
+        evi = np.zeros(cap_e, dtype=CHURN_EVICTION)
+        rows = np.zeros(self.max_instances, dtype=INSTANCE_ROW) if want_rows else None
+        nd, ne = C.c_int32(), C.c_int32()
+        rep = ChurnReport()
+        self._ck(self.lib.mmp_churn_step(self.h, _ptr(ev), len(ev), now0, now1, seed, _ptr(dec), cap_d, C.byref(nd), _ptr(evi), cap_e,
+                                         C.byref(ne), _ptr(rows), C.byref(rep)))
+        if nd.value > cap_d or ne.value > cap_e:
+            raise MmpError(-1, "churn report buffers too small")
+        return dec[:nd.value].copy(), evi[:ne.value].copy(), rows, rep
+
+    def churn_model(self, model: int):
+        row = np.zeros(1, dtype=MODEL_ROW)
+        inst = np.zeros(4, dtype=np.int32)
+        self._ck(self.lib.mmp_churn_model(self.h, model, _ptr(row), _ptr(inst)))
+        return row[0], inst
+
+    def commit_info(self):
+        path, ms = C.c_int32(), C.c_double()
+        self._ck(self.lib.mmp_commit_info(self.h, C.byref(path), C.byref(ms)))
+        return int(path.value), float(ms.value)
 
     def lru_state(self):
         n = self._lru_n

@@ -432,3 +432,138 @@ def load_into_fleet(fl: SynthFleet, fleet, bulk_chunk: int = 1 << 18) -> Dict[st
         fleet.models_bulk(lo, rows[lo:hi], off, fl.edge_inst[fl.edge_off[lo]:fl.edge_off[hi]])
     fleet.commit()
     return tid
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# C4: the churn workload (BASELINE.json configs[3]): a fleet at steady state (caches filled to `fill`), then a
+# Poisson trace of requests -- cache hits on loaded models (Zipf), cache misses on unloaded ones (-> placement + load +
+# evictions), removals -- in republish windows of 2 s.
+# ---------------------------------------------------------------------------------------------------------------
+@dataclass
+class ChurnWorkload:
+    fleet: SynthFleet
+    capacity: np.ndarray          # int64[n_i] cache capacity per instance (= published capacity)
+    seed_instance: np.ndarray     # resident copies at the start: instance, model, lastUsed, weight, registration time
+    seed_model: np.ndarray
+    seed_last_used: np.ndarray
+    seed_weight: np.ndarray
+    seed_load_ts: np.ndarray
+    loaded_models: np.ndarray     # model ids with a copy at the start (hot set of the trace), hottest first
+    unloaded_models: np.ndarray
+    load_timeout_ms: int
+    window_ms: int = 2000
+
+    def events(self, epoch: int, n: int, seed: int, hit=0.70, miss=0.25):
+        """Window `epoch` of the trace: n events sorted by time.  hit / miss / (rest = remove) fractions as SURVEY.md §8d."""
+        from ._lib import CHURN_EVENT
+        rng = SplitMix((seed * 1_000_003 + epoch) ^ 0xC4C4)
+        fl = self.fleet
+        now0 = fl.now_ms + epoch * self.window_ms
+        ev = np.zeros(n, dtype=CHURN_EVENT)
+        r = rng.uniform(n)
+        kind = np.where(r < hit, 0, np.where(r < hit + miss, 1, 2))
+        nl, nu = len(self.loaded_models), len(self.unloaded_models)
+        # Zipf(1.1) over the loaded models by inverse-CDF on a precomputed table
+        if not hasattr(self, "_zipf_cdf"):
+            w = 1.0 / np.power(np.arange(1, nl + 1, dtype=np.float64), 1.1)
+            self._zipf_cdf = np.cumsum(w / w.sum())
+        hot = np.minimum(nl - 1, np.searchsorted(self._zipf_cdf, rng.uniform(n)))
+        cold = rng.randint(n, 0, max(1, nu))
+        anym = rng.randint(n, 0, fl.n_models)
+        ev["model"] = np.where(kind == 0, self.loaded_models[hot], np.where(kind == 1, self.unloaded_models[cold % max(1, nu)], anym))
+        ev["type"] = np.where(kind == 2, 1, 0)
+        live = np.nonzero(fl.inst_rows["shutting_down"] == 0)[0]
+        ev["caller"] = live[rng.randint(n, 0, len(live))]
+        ev["u"] = (rng.u64(n) >> np.uint64(33)).astype(np.uint32)
+        ev["t"] = now0 + np.sort(rng.randint(n, 0, self.window_ms))
+        return ev
+
+
+def make_churn(n_models: int, n_instances: int, seed: int, fill: float = 0.97, with_types: bool = False) -> ChurnWorkload:
+    rng = SplitMix(seed ^ 0xC4)
+    now = NOW_MS
+    ni, nm = n_instances, n_models
+    default_size = 6400
+    model_size = np.exp(np.log(256.0) + rng.uniform(nm) * (np.log(65536.0) - np.log(256.0))).astype(np.int32)
+    mean = float(model_size.mean())
+    # ~70 % of the models resident once: capacity so that `fill` of it holds an even share of them
+    cap = int(0.70 * nm * mean / ni / fill)
+    cap = max(cap, 4 * 65536)
+    min_space = max(default_size, min(default_size * 8, cap // 20))  # MM:767-769, 8 loading threads, unload manager
+    perm = np.argsort(rng.u64(nm), kind="stable").astype(np.int64)
+    # fill instance after instance with the shuffled models until `fill` of the capacity is used
+    sizes = model_size[perm].astype(np.int64)
+    csum = np.cumsum(sizes)
+    target = int(fill * cap)
+    inst_of = np.full(nm, -1, dtype=np.int64)
+    start, pos = 0, 0
+    for i in range(ni):
+        if pos >= nm:
+            break
+        base = csum[pos - 1] if pos > 0 else 0
+        end = int(np.searchsorted(csum, base + target, side="right"))
+        end = max(end, pos)
+        inst_of[pos:end] = i
+        pos = end
+    n_res = pos
+    res_models = perm[:n_res]
+    res_inst = inst_of[:n_res]
+    last_used = (now - rng.exponential(n_res, 6 * 3_600_000.0).astype(np.int64) - 1 - np.arange(n_res) % 997).astype(np.int64)
+    # 5 % of the resident models get a second copy on another instance (evicting nothing: only where it still fits)
+    used = np.bincount(res_inst, weights=model_size[res_models].astype(np.float64), minlength=ni).astype(np.int64)
+    second = np.nonzero(rng.uniform(n_res) < 0.05)[0]
+    s_inst, s_model, s_lu = [], [], []
+    other = rng.randint(len(second), 0, ni)
+    for k, j in enumerate(second):
+        m = int(res_models[j])
+        i2 = int(other[k])
+        if i2 == int(res_inst[j]) or used[i2] + model_size[m] > cap:
+            continue
+        used[i2] += model_size[m]
+        s_inst.append(i2); s_model.append(m); s_lu.append(int(last_used[j]) + 7)
+    seed_instance = np.concatenate([res_inst, np.asarray(s_inst, dtype=np.int64)]).astype(np.int32)
+    seed_model = np.concatenate([res_models, np.asarray(s_model, dtype=np.int64)]).astype(np.int32)
+    seed_lu = np.concatenate([last_used, np.asarray(s_lu, dtype=np.int64)]).astype(np.int64)
+    seed_w = model_size[seed_model].astype(np.int32)
+    load_timeout = 30_000
+    seed_lt = np.full(len(seed_model), now - 3 * 3_600_000, dtype=np.int64)
+    # registry: edges = loaded copies in seeding order per model
+    order = np.argsort(seed_model, kind="stable")
+    n_loaded = np.bincount(seed_model, minlength=nm).astype(np.int32)
+    edge_off = np.zeros(nm + 1, dtype=np.int64)
+    np.cumsum(n_loaded, out=edge_off[1:])
+    edge_inst = seed_instance[order].astype(np.int32)
+    # instance records as each pod would publish them (getFreshInstanceRecord MM:5369-5386)
+    rows = np.zeros(ni, dtype=INSTANCE_ROW)
+    rows["capacity"] = cap
+    rows["used"] = used
+    cnt = np.bincount(seed_instance, minlength=ni)
+    rows["count"] = cnt
+    oldest = np.full(ni, LONG_MAX, dtype=np.int64)
+    np.minimum.at(oldest, seed_instance, seed_lu)
+    rows["lru_time"] = oldest
+    rows["l_threads"] = 8
+    rows["rpm"] = rng.randint(ni, 0, 3000)
+    rows["start_time"] = now - rng.randint(ni, 3_600_000, 30 * 86_400_000)
+    rows["vers"] = 7
+    rows["active"] = 1
+    ids = [f"mmc4{(i * 7919) % 9973:04d}-{i:05x}" for i in range(ni)]
+    zones = [None if i % 4 == 3 else f"zone-{i % 4}" for i in range(ni)]
+    locs = [f"node-{i // 8:04d}" for i in range(ni)]
+    type_config: Optional[Dict[str, dict]] = None
+    type_names = [f"type-{t}" for t in range(4)]
+    labels: List[List[str]] = [[] for _ in range(ni)]
+    if with_types:  # a quarter of the types is pinned to half of the fleet: two partitions, subset stats in the rebalance rule
+        labels = [(["gpu"] if i % 2 == 0 else []) for i in range(ni)]
+        type_config = {"type-0": {"required": ["gpu"]}, "type-1": {"preferred": ["gpu"]}}
+    model_type = rng.randint(nm, 0, 4).astype(np.int32)
+    model_last = np.zeros(nm, dtype=np.int64)
+    model_last[seed_model] = seed_lu
+    model_last = np.where(model_last == 0, now - rng.exponential(nm, 12 * 3_600_000.0).astype(np.int64) - 1, model_last).astype(np.int64)
+    fl = SynthFleet("C4", now, min_space, 600_000, default_size, rows, ids, locs, zones, labels, type_config, type_names, model_type,
+                    model_last, model_size, np.zeros(nm, dtype=np.int32), edge_off, edge_inst, n_loaded, np.zeros(nm, dtype=np.int32), [])
+    loaded = np.nonzero(n_loaded > 0)[0]
+    hot_order = loaded[np.argsort(rng.u64(len(loaded)), kind="stable")]
+    unloaded = np.nonzero(n_loaded == 0)[0]
+    return ChurnWorkload(fl, rows["capacity"].astype(np.int64).copy(), seed_instance, seed_model, seed_lu, seed_w, seed_lt, hot_order,
+                         unloaded, load_timeout)

@@ -157,7 +157,9 @@ int32_t mmp_place_batch_trace(mmp_fleet *f, const mmp_decision_in *in, int32_t n
       const uint32_t ww = (uint32_t)std::min<int64_t>(g_lane_window, (int64_t)T.nz_n);
       std::vector<uint32_t> window(ww);
       for (uint32_t k = 0; k < ww; k++) window[k] = erow[T.nzw[k] - v.word_lo];
-      done = decide_stream(v, T, cx, true, window.data(), ww, g_lane_global ? erow : nullptr, self_eword, now_ms, seed,
+      uint32_t first8[4];
+      for (int j = 0; j < 4; j++) first8[j] = (uint32_t)T.nzw[2 * j] | ((uint32_t)T.nzw[2 * j + 1] << 16);
+      done = decide_stream(v, T, cx, true, window.data(), ww, first8, g_lane_global ? erow : nullptr, self_eword, now_ms, seed,
                            f->id_base + (uint64_t)i, SoloVote(), o, g_lane_budget);
       g_lane_decisions++;
       if (!done) g_bails++;

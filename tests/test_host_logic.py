@@ -36,7 +36,7 @@ def test_product_library_exports_every_symbol():
     lib = ctypes.CDLL(so)
     for name, _, _ in L.SYMBOLS:
         assert hasattr(lib, name), name
-    assert lib.mmp_abi_version() == 1
+    assert lib.mmp_abi_version() == 2  # MMP_ABI_VERSION (include/mmplace.h): 2 = round 2 (checked loads, closed loop, commit info)
 
 
 def test_product_has_no_cpu_fallback():
