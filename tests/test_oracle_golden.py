@@ -307,3 +307,56 @@ def test_scaleup_copies_arithmetic(oracle_lib):
     assert f(5000, 10_000, 2000, 1, 0, 10, 0, 0, 1, None) == 0                                     # a copy was loaded too recently
     assert f(5000, 10_000, 2000, 4, 2, 6, 0, 0, 0, None) == 0                                      # nowhere left to load
     assert f(5000, 10_000, 2000, 2, 0, 10, 3, 2, 0, None) == 3                                     # 10 - 2 = 8, - 2 - 3 = 3: min(15, 3) = 3, cap 10 // 3 = 3
+
+
+def test_java_golden_vectors(oracle_lib):
+    """Fixtures produced by the REFERENCE ITSELF (oracle/java/GetNextHarness.java on a box with JDK 21 + the reference's jars):
+    for every tests/golden/fleet_*.json that has a *.expected.json beside it, the oracle must reproduce the PLACEMENT_ORDER
+    order, and per decision the ordered shortlist, instReqLoad and the result up to the random draw (N4).  The input files
+    are committed (tools/golden_fleets.py); no expected file can be produced in this image (no JDK) -> "parity unpinned"."""
+    import glob
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    inputs = sorted(p for p in glob.glob(os.path.join(gdir, "fleet_*.json")) if not p.endswith(".expected.json"))
+    assert inputs, "tests/golden/fleet_*.json missing: run tools/golden_fleets.py"
+    pairs = [(p, p.replace(".json", ".expected.json")) for p in inputs if os.path.exists(p.replace(".json", ".expected.json"))]
+    for p in inputs:  # the inputs themselves must load into the oracle (format check of what the harness will be fed)
+        doc = json.load(open(p))
+        o = ob.OracleFleet(doc["minSpaceUnits"], doc["minChurnAgeMs"], 2560)
+        o.types_set(doc["typeConstraints"])
+        ids = [x["id"] for x in doc["instances"]]
+        for i, x in enumerate(doc["instances"]):
+            r = x["record"]
+            row = np.zeros(1, dtype=ob.INST)
+            row["lru_time"], row["count"], row["capacity"], row["used"] = r["lruTime"], r["count"], r["cap"], r["used"]
+            row["l_threads"], row["l_in_prog"], row["rpm"], row["shutting_down"] = r["lThreads"], r["lInProg"], r["rpm"], int(r["shutdown"])
+            row["start_time"], row["vers"], row["active"] = r["startTime"], r["vers"], int(x["active"])
+            o.instance_event(ob.ADDED, i, row[0], x["id"], r["loc"], r["zone"], r["labels"] or (), now_ms=doc["now"])
+        if doc["typeConstraints"] is not None:
+            o.tc_converge()
+        o.set_replaced_replicasets(doc["replaced"])
+        assert len(o.cluster_order()) == sum(1 for x in doc["instances"] if not x["record"]["shutdown"])
+        exp_path = p.replace(".json", ".expected.json")
+        if not os.path.exists(exp_path):
+            continue
+        exp = json.load(open(exp_path))
+        assert [ids[i] for i in o.cluster_order()] == exp["order"], p
+        types = sorted({d["type"] for d in doc["decisions"]})
+        for k, (d, e) in enumerate(zip(doc["decisions"], exp["decisions"])):
+            od = np.zeros(1, dtype=ob.DECISION)
+            od["type_idx"], od["self"], od["favour_self"], od["last_used"] = types.index(d["type"]), ids.index(d["self"]), int(d["favourSelf"]), d["lastUsed"]
+            fresh = None
+            od["fresh_idx"] = -1
+            if d["fresh"] is not None:
+                r = d["fresh"]
+                fresh = np.zeros(1, dtype=ob.INST)
+                fresh["lru_time"], fresh["count"], fresh["capacity"], fresh["used"], fresh["rpm"] = r["lruTime"], r["count"], r["cap"], r["used"], r["rpm"]
+                od["fresh_idx"] = 0
+            ex = np.asarray([ids.index(x) for x in d["excluded"]], dtype=np.int32)
+            res, coff, cidx, cload, ckeep = o.get_next_batch(od, types, np.asarray([0, len(ex)], dtype=np.int64), ex, doc["now"], 1, fresh=fresh,
+                                                            want_candidates=True)
+            assert [ids[i] for i in cidx] == e["candidates"], (p, k)
+            assert [int(x) for x in cload] == e["instReqLoad"], (p, k)
+            if e["result"] in ("null", "SELF") and len(e["candidates"]) <= 1:
+                assert int(res["target"][0]) == (ob.NONE if e["result"] == "null" else ob.SELF), (p, k)
+    if not pairs:
+        pytest.skip("parity unpinned: no tests/golden/*.expected.json (needs JDK 21 + the reference's jars, see oracle/java/README.md)")
