@@ -26,11 +26,14 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_MODELS = int(os.environ.get("BENCH_MODELS", 1_000_000))
-N_INSTANCES = int(os.environ.get("BENCH_INSTANCES", 10_000))
-CONFIG = os.environ.get("BENCH_CONFIG", "C3")
-SEED = 3
+CONFIG = os.environ.get("BENCH_CONFIG", "C3")  # C3 = the configuration BASELINE.json's metric is quoted on; C2 / C5 / C4: the others
+_DEFAULT_SIZES = {"C2": (100_000, 1_000), "C3": (1_000_000, 10_000), "C5": (1_000_000, 10_000), "C4": (500_000, 2_500)}
+N_MODELS = int(os.environ.get("BENCH_MODELS", _DEFAULT_SIZES.get(CONFIG, (1_000_000, 10_000))[0]))
+N_INSTANCES = int(os.environ.get("BENCH_INSTANCES", _DEFAULT_SIZES.get(CONFIG, (1_000_000, 10_000))[1]))
+SEED = {"C2": 2, "C3": 3, "C4": 4, "C5": 5}.get(CONFIG, 3)
 METRIC = "placement decisions/sec at 1M models x 10k instances"
+WORKLOADS = {"C2": "Zipf request rates, no type constraints", "C3": "mixed type constraints",
+             "C5": "adversarial 95%-full capacity bin-packing, heavy type-constraint masks", "C4": "churn"}
 
 
 def bytes_per_decision(row_words: int) -> int:
@@ -105,16 +108,19 @@ def measured_hbm_peak():
 
 
 def captured_traffic(batch: int):
-    """dram__bytes_read + dram__bytes_write of one k_place_lanes launch from the committed `ncu --set full` capture
-    (profiles/r01_ncu_k_place_lanes.json, written by tools/ncu_summary.py), if it was taken on this batch size."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_k_place_lanes.json")) as f:
-            d = json.load(f)
-        if int(d.get("n_decisions") or 0) == int(batch):
-            return float(d["dram_bytes_per_launch"])
-    except Exception:
-        pass
-    return None
+    """dram__bytes_read + dram__bytes_write of one k_place_lanes launch from the committed `ncu --set full` capture of this
+    configuration (profiles/r02_ncu_k_place_lanes_<config>.json, written by tools/ncu_summary.py), scaled per decision when
+    the capture was taken on another batch size (the traffic is proportional: one row per decision)."""
+    for name in (f"r02_ncu_k_place_lanes_{CONFIG.lower()}.json", "r01_ncu_k_place_lanes.json" if CONFIG == "C3" else ""):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                d = json.load(f)
+            nd = int(d.get("n_decisions") or 0)
+            if nd > 0:
+                return float(d["dram_bytes_per_launch"]) * batch / nd, f"profiles/{name.replace('.json', '.txt')}"
+        except Exception:
+            pass
+    return None, None
 
 
 def build_oracle(fl):
@@ -124,8 +130,8 @@ def build_oracle(fl):
     return helpers, helpers.oracle_from_synth(fl)
 
 
-def cpu_leg(fl, sd_all, budget_s: float, chunk: int, threads: int):
-    """Time the oracle's getNext on chunks of the same workload for about budget_s seconds."""
+def cpu_leg(fl, sd_all, budget_s: float, chunk: int, threads: int, dense: bool = False):
+    """Time the oracle's getNext on chunks of the same workload for about budget_s seconds (dense: CPU mode (ii))."""
     helpers, oracle = build_oracle(fl)
     from modelmesh_b200.synth import SynthDecisions
     done, t_total, results = 0, 0.0, []
@@ -137,7 +143,7 @@ def cpu_leg(fl, sd_all, budget_s: float, chunk: int, threads: int):
         od, off, idx = helpers.oracle_inputs_fast(fl, sd)
         od["decision_id"] = np.arange(pos, hi, dtype=np.uint64)
         t0 = time.perf_counter()
-        res = oracle.get_next_batch(od, fl.type_names, off, idx, fl.now_ms, SEED, threads=threads)
+        res = oracle.get_next_batch(od, fl.type_names, off, idx, fl.now_ms, SEED, threads=threads, dense=dense)
         t_total += time.perf_counter() - t0
         results.append((pos, hi, res))
         done += hi - pos
@@ -146,40 +152,60 @@ def cpu_leg(fl, sd_all, budget_s: float, chunk: int, threads: int):
 
 
 def run_reference(args, rank: int, world: int):
+    """The reference's own CPU path (C++ restatement: no JVM in the image) on the host cores, on the SAME step as the repo's
+    arm: one reaper-style sweep of N_MODELS getNext decisions per step, all host threads; CPU mode (ii) beside it."""
     if rank != 0:
         return
+    if CONFIG == "C4":
+        return run_reference_churn(args)
     from modelmesh_b200.synth import make_decisions, make_fleet
     fl = make_fleet(CONFIG, N_MODELS, N_INSTANCES, SEED)
     sd = make_decisions(fl, N_MODELS, SEED, sweep=True, plain=True)
     threads = host_threads()
-    chunk = min(len(sd.dec), int(os.environ.get("BENCH_REF_CHUNK", 250_000)))
     helpers, oracle = build_oracle(fl)
-    from modelmesh_b200.synth import SynthDecisions
-    times = []
+    od, off, idx = helpers.oracle_inputs_fast(fl, sd)
+    times, dense_times = [], []
     for step in range(args.warmup + args.steps):
-        lo = (step * chunk) % max(1, len(sd.dec) - chunk + 1)
-        s = SynthDecisions(sd.dec[lo:lo + chunk], sd.fresh, sd.extra)
-        od, off, idx = helpers.oracle_inputs_fast(fl, s)
         t0 = time.perf_counter()
         oracle.get_next_batch(od, fl.type_names, off, idx, fl.now_ms, SEED, threads=threads)
         dt = time.perf_counter() - t0
         if step >= args.warmup:
             times.append(dt)
+    for step in range(min(3, args.steps)):
+        t0 = time.perf_counter()
+        oracle.get_next_batch(od, fl.type_names, off, idx, fl.now_ms, SEED, threads=threads, dense=True)
+        dense_times.append(time.perf_counter() - t0)
     tot = sum(times)
-    value = chunk * len(times) / tot
+    value = N_MODELS * len(times) / tot
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "decisions/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * tot / len(times), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": f"{CONFIG} {N_MODELS} models x {N_INSTANCES} instances, mixed type constraints, "
-                               f"reaper-style sweep; each step a {chunk}-decision sample on the host cores"},
+        "config": workload_config(world=max(1, args.gpus)),
         "cpu_baseline": {"value": value, "unit": "decisions/s", "cores": threads, "kind": "port",
-                         "sample": f"{chunk} decisions/step x {len(times)} steps, C++ restatement of "
-                                   f"CacheMissForwardingLB.getNext (the Java reference cannot run: no JDK)"},
+                         "sample": f"the whole step: {N_MODELS} decisions x {len(times)} steps, C++ restatement of "
+                                   f"CacheMissForwardingLB.getNext in its reference shape (ordered set walk); the Java reference cannot run: no JDK",
+                         "dense": {"value": N_MODELS * len(dense_times) / sum(dense_times), "unit": "decisions/s", "cores": threads,
+                                   "sample": f"{len(dense_times)} steps, CPU mode (ii) of BASELINE.md: entries through a rank-ordered array"}},
         "e2e": {"value": value, "unit": "decisions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def workload_config(world: int):
+    """The `config` object of the JSON line: a pure function of the configuration and the world size, so that the repo's arm
+    and the --impl reference arm print the same one."""
+    from modelmesh_b200.sharding import shard_range
+    row_words = ((N_INSTANCES + 31) // 32 + 31) // 32 * 32
+    lo, hi = shard_range(0, world, N_MODELS)
+    gb = (hi - lo) * row_words * 4 / 1e9
+    return {"workload": f"{CONFIG} {N_MODELS} models x {N_INSTANCES} instances, {WORKLOADS.get(CONFIG, '')}, one reaper-style sweep of "
+                        f"{N_MODELS} getNext decisions per step",
+            "batch": N_MODELS,
+            "sharding": "registry sharded by model across ranks, instance table replicated" if world > 1 else "single GPU",
+            "l2": ("inputs larger than L2 (exclusion bitmap %.2f GB per rank streamed every step)" % gb if gb > 0.2 else
+                   "L2 flushed between timed steps (mmp_flush_l2): the %.1f MB bitmap would otherwise stay resident" % (gb * 1e3))}
 
 
 def main():

@@ -89,6 +89,9 @@ typedef struct {
  * The model's exclusion set (loaded ∪ failed, MM:4735-4743) and type come from the model table. */
 #define MMP_DF_FAVOUR_SELF 1u        /* CacheMissExcludeSet.favourSelf (MM:4721) */
 #define MMP_DF_MODEL_LAST_USED 2u    /* take last_used from the model row instead of this struct */
+#define MMP_DF_OWN_ID 4u             /* bits 8..31 of flags carry the decision's own id for the hash-indexed pick (N4, MM:4981)
+                                        instead of its position in the batch: the result of a decision then does not depend on
+                                        which batch it travelled in (mmp_place_submit coalesces callers this way) */
 typedef struct {
   int32_t model;        /* model index */
   int32_t self;         /* instance index of the calling pod ("instanceId", MM:4780,4808) */
@@ -191,6 +194,17 @@ int32_t mmp_place_batch_trace(mmp_fleet *, const mmp_decision_in *in, int32_t n,
  * on the equivalent 32-byte records, with 4 bytes (+1 bit) instead of 32 going to the device per decision. */
 int32_t mmp_place_sweep(mmp_fleet *, int32_t first_model, int32_t n, const int32_t *self, int32_t self_stride,
                         const uint32_t *favour_bits, mmp_decision_out *out, int64_t now_ms, uint64_t seed);
+/* Micro-batcher for plug point 1: getNext is called on arbitrary request threads (litelinks pool / gRPC
+ * pool, MM:918-925, MM:1107-1110).  mmp_place_submit blocks the calling thread while ONE submit thread drains the queue into
+ * a single mmp_place_batch against the current epoch: every `max_wait_us` or as soon as `max_batch` decisions wait.  Each
+ * decision is numbered by the batcher (MMP_DF_OWN_ID; *decision_id receives the id), so its result equals
+ * mmp_place_batch on that one record with seed = the batcher's seed -- whichever batch carried it. */
+typedef struct mmp_batcher mmp_batcher;
+int32_t mmp_batcher_create(mmp_fleet *, int32_t max_batch, int32_t max_wait_us, uint64_t seed, mmp_batcher **out);
+void mmp_batcher_destroy(mmp_batcher *);
+int32_t mmp_place_submit(mmp_batcher *, const mmp_decision_in *in, const mmp_instance_row *fresh, const int32_t *extra, int64_t now_ms,
+                         mmp_decision_out *out, uint32_t *decision_id);
+int32_t mmp_batcher_stats(mmp_batcher *, int64_t *batches, int64_t *decisions);
 /* Single decision (latency path, B = 1). */
 int32_t mmp_place_one(mmp_fleet *, const mmp_decision_in *in, const mmp_instance_row *fresh, const int32_t *extra,
                       mmp_decision_out *out, int64_t now_ms, uint64_t seed);

@@ -45,6 +45,10 @@ final class MmPlace {
     static native int placeSweep(long h, int firstModel, int n, ByteBuffer self, int selfStride, ByteBuffer favourBits, ByteBuffer out,
                                  long nowMs, long seed);
     static native int placeOne(long h, ByteBuffer in, ByteBuffer fresh, int[] extra, ByteBuffer out, long nowMs, long seed);
+    static native long batcherCreate(long h, int maxBatch, int maxWaitUs, long seed);
+    static native void batcherDestroy(long batcher);
+    static native int placeSubmit(long batcher, ByteBuffer in, ByteBuffer fresh, int[] extra, long nowMs, ByteBuffer out, int[] idOut);
+    static native int batcherStats(long batcher, long[] batchesDecisionsOut);
     static native double placeBatchDevice(long h, long dIn, int n, long dOut, long nowMs, long seed);
     static native long deviceAlloc(long h, long bytes);
     static native int deviceFree(long h, long p);

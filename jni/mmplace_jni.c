@@ -154,6 +154,36 @@ jint FN(placeOne)(JNIEnv *env, jclass c, jlong h, jobject in, jobject fresh, jin
   if (pe) (*env)->ReleasePrimitiveArrayCritical(env, extra, pe, JNI_ABORT);
   return rc;
 }
+/* micro-batcher: many request threads, one mmp_place_batch per drain (idOut[0] = the decision's own id) */
+jlong FN(batcherCreate)(JNIEnv *env, jclass c, jlong h, jint maxBatch, jint maxWaitUs, jlong seed) {
+  mmp_batcher *b = NULL;
+  (void)env; (void)c;
+  return mmp_batcher_create(H(h), maxBatch, maxWaitUs, (uint64_t)seed, &b) < 0 ? 0 : (jlong)(intptr_t)b;
+}
+void FN(batcherDestroy)(JNIEnv *env, jclass c, jlong b) { (void)env; (void)c; mmp_batcher_destroy((mmp_batcher *)(intptr_t)b); }
+jint FN(placeSubmit)(JNIEnv *env, jclass c, jlong b, jobject in, jobject fresh, jintArray extra, jlong nowMs, jobject out, jintArray idOut) {
+  jsize ne = extra ? (*env)->GetArrayLength(env, extra) : 0;
+  jint tmp[MMP_MAX_EXTRA], id;
+  uint32_t did = 0;
+  jint rc;
+  (void)c;
+  if (ne > MMP_MAX_EXTRA) ne = MMP_MAX_EXTRA;
+  if (ne) { jint *pe = (jint *)(*env)->GetPrimitiveArrayCritical(env, extra, NULL); memcpy(tmp, pe, (size_t)ne * sizeof(jint)); (*env)->ReleasePrimitiveArrayCritical(env, extra, pe, JNI_ABORT); }
+  rc = mmp_place_submit((mmp_batcher *)(intptr_t)b, (const mmp_decision_in *)BUF(in), (const mmp_instance_row *)BUF(fresh), ne ? (const int32_t *)tmp : NULL,
+                        nowMs, (mmp_decision_out *)BUF(out), &did);
+  id = (jint)did;
+  if (idOut) (*env)->SetIntArrayRegion(env, idOut, 0, 1, &id);
+  return rc;
+}
+jint FN(batcherStats)(JNIEnv *env, jclass c, jlong b, jlongArray out) {
+  int64_t v[2] = {0, 0};
+  jlong w[2];
+  jint rc = mmp_batcher_stats((mmp_batcher *)(intptr_t)b, &v[0], &v[1]);
+  (void)c;
+  w[0] = v[0]; w[1] = v[1];
+  if (out) (*env)->SetLongArrayRegion(env, out, 0, 2, w);
+  return rc;
+}
 jdouble FN(placeBatchDevice)(JNIEnv *env, jclass c, jlong h, jlong dIn, jint n, jlong dOut, jlong nowMs, jlong seed) {
   float ms = -1.0f;
   (void)env; (void)c;

@@ -61,6 +61,7 @@ class ChurnReport(C.Structure):
 
 DF_FAVOUR_SELF = 1
 DF_MODEL_LAST_USED = 2
+DF_OWN_ID = 4
 TARGET_NONE = -1
 TARGET_SELF = -2
 TARGET_INVALID = -3
@@ -126,6 +127,10 @@ SYMBOLS = [
     ("mmp_churn_step", _I32, [_P, _P, _I32, _I64, _I64, _U64, _P, _I32, C.POINTER(_I32), _P, _I32, C.POINTER(_I32), _P, C.c_void_p]),
     ("mmp_churn_model", _I32, [_P, _I32, _P, _P]),
     ("mmp_commit_info", _I32, [_P, C.POINTER(_I32), C.POINTER(C.c_double)]),
+    ("mmp_batcher_create", _I32, [_P, _I32, _I32, _U64, C.POINTER(_P)]),
+    ("mmp_batcher_destroy", None, [_P]),
+    ("mmp_place_submit", _I32, [_P, _P, _P, _P, _I64, _P, C.POINTER(C.c_uint32)]),
+    ("mmp_batcher_stats", _I32, [_P, C.POINTER(_I64), C.POINTER(_I64)]),
     ("mmp_shard_unique_id", _I32, [_P]),
     ("mmp_shard_connect", _I32, [_P, _P]),
     ("mmp_shard_words", _I32, [_P, C.POINTER(_I32), C.POINTER(_I32)]),

@@ -29,6 +29,7 @@
 #include <mutex>
 #include <shared_mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "host_state.hpp"
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_place(const SnapshotView s
         DecideOut o;
         o.target = MMP_TARGET_NONE; o.n_candidates = 0;
         bool resolved = false;
-        if (valid && whole_rows) resolved = decide_fast<false>(s, cc[j], rows_s + (size_t)slot * RW, now, seed, id_base + (uint64_t)(b * 32 + j), cot, o);
+        if (valid && whole_rows) resolved = decide_fast<false>(s, cc[j], rows_s + (size_t)slot * RW, now, seed, pick_id(cc[j].d, id_base + (uint64_t)(b * 32 + j)), cot, o);
         __syncwarp();
         {
           const uint32_t pending = __ballot_sync(0xffffffffu, valid && !resolved);
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_place(const SnapshotView s
               const int jj = jp + h;
               const uint32_t sl2 = (use + (uint32_t)h) % (uint32_t)K;
               int32_t t2, c2;
-              decide_warp(s, cc[jj], rows_s + (size_t)sl2 * RW, extra, now, seed, id_base + (uint64_t)(b * 32 + jj), &t2, &c2);
+              decide_warp(s, cc[jj], rows_s + (size_t)sl2 * RW, extra, now, seed, pick_id(cc[jj].d, id_base + (uint64_t)(b * 32 + jj)), &t2, &c2);
               if (tile == h) { o.target = t2; o.n_candidates = c2; }
             }
           }
@@ -274,8 +275,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_place(const SnapshotView s
         const uint32_t *erow = rows_s + (size_t)slot * RW;
         const int gi = b * 32 + j;
         DecideOut o;
-        if (cand || !whole_rows || !decide_fast<true>(s, cc[j], erow, now, seed, id_base + (uint64_t)gi, co, o))
-          decide_ctx(s, cc[j], erow, extra, now, seed, id_base + (uint64_t)gi, co, o, cand ? cand + (size_t)gi * 2 * s.row_words : nullptr);
+        if (cand || !whole_rows || !decide_fast<true>(s, cc[j], erow, now, seed, pick_id(cc[j].d, id_base + (uint64_t)gi), co, o))
+          decide_ctx(s, cc[j], erow, extra, now, seed, pick_id(cc[j].d, id_base + (uint64_t)gi), co, o, cand ? cand + (size_t)gi * 2 * s.row_words : nullptr);
         if (lane == j) { mine.target = o.target; mine.n_candidates = o.n_candidates; }
         if (tr && lane == 0) {
           mmp_decision_trace t;
@@ -486,7 +487,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotVie
     // ---- one decision per lane, the 32 lanes in lockstep ----
     DecideOut o;
     bool handled = true;
-    const uint64_t my_id = id_base + (uint64_t)(orig_id ? (valid ? orig_id[b * 32 + lane] : 0) : b * 32 + lane);
+    const uint64_t my_id = pick_id(d, id_base + (uint64_t)(orig_id ? (valid ? orig_id[b * 32 + lane] : 0) : b * 32 + lane));
     if ((mode & 1) == 0)
       handled = decide_stream(s, T, c, valid && !skip, win + lane * (LANE_WIN + 1), win_words, wl, s.excl + (size_t)m * RW, self_eword,
                               now, seed, my_id, WarpVote(), o, budget);
@@ -1621,6 +1622,116 @@ int32_t mmp_instance_partition(mmp_fleet *f, int32_t idx) {
 }
 int64_t mmp_kernel_launches(mmp_fleet *f) { return f ? f->launches.load() : 0; }
 
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// micro-batcher (SURVEY.md §8b plug point 1): many request threads, one submit thread, one mmp_place_batch per drain
+// ---------------------------------------------------------------------------------------------------------------
+struct mmp_batcher {
+  mmp_fleet *f = nullptr;
+  int32_t max_batch = 4096, max_wait_us = 50;
+  uint64_t seed = 0;
+  struct Req {
+    mmp_decision_in in; mmp_instance_row fresh; bool has_fresh; int32_t extra[MMP_MAX_EXTRA]; int32_t n_extra;
+    int64_t now_ms; mmp_decision_out out; int32_t rc; bool done;
+  };
+  std::mutex mu;
+  std::condition_variable cv_submit, cv_done;
+  std::vector<Req *> queue;
+  bool stop = false;
+  std::thread worker;
+  std::atomic<uint32_t> next_id{1};
+  std::atomic<int64_t> batches{0}, decisions{0};
+  std::string err;
+
+  void run() {
+    std::vector<Req *> batch;
+    std::vector<mmp_decision_in> in;
+    std::vector<mmp_decision_out> out;
+    std::vector<mmp_instance_row> fresh;
+    std::vector<int32_t> extra;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_submit.wait(lk, [&] { return stop || !queue.empty(); });
+        if (stop && queue.empty()) return;
+        if ((int32_t)queue.size() < max_batch && max_wait_us > 0)  // let concurrent callers pile up for one launch
+          cv_submit.wait_for(lk, std::chrono::microseconds(max_wait_us), [&] { return stop || (int32_t)queue.size() >= max_batch; });
+        batch.swap(queue);
+      }
+      const int32_t n = (int32_t)batch.size();
+      in.resize(n); out.resize(n); fresh.clear(); extra.clear();
+      for (int32_t i = 0; i < n; i++) {
+        Req &r = *batch[i];
+        in[i] = r.in;
+        in[i].fresh = -1;
+        if (r.has_fresh) { in[i].fresh = (int32_t)fresh.size(); fresh.push_back(r.fresh); }
+        in[i].extra_off = (int32_t)extra.size();
+        in[i].extra_n = r.n_extra;
+        extra.insert(extra.end(), r.extra, r.extra + r.n_extra);
+      }
+      const int32_t rc = mmp_place_batch(f, in.data(), n, fresh.empty() ? nullptr : fresh.data(), (int32_t)fresh.size(),
+                                         extra.empty() ? nullptr : extra.data(), (int32_t)extra.size(), out.data(), batch[0]->now_ms, seed);
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        if (rc < 0) err = mmp_last_error(f);
+        for (int32_t i = 0; i < n; i++) { batch[i]->out = out[i]; batch[i]->rc = rc; batch[i]->done = true; }
+      }
+      cv_done.notify_all();
+      batches++; decisions += n;
+      batch.clear();
+    }
+  }
+};
+
+extern "C" {
+int32_t mmp_batcher_create(mmp_fleet *f, int32_t max_batch, int32_t max_wait_us, uint64_t seed, mmp_batcher **out) {
+  NEED(f);
+  if (!out || max_batch < 1 || max_wait_us < 0) { g_err = "bad argument"; return MMP_E_ARG; }
+  auto *b = new mmp_batcher();
+  b->f = f; b->max_batch = max_batch; b->max_wait_us = max_wait_us; b->seed = seed;
+  b->worker = std::thread([b] { b->run(); });
+  *out = b;
+  return MMP_OK;
+}
+void mmp_batcher_destroy(mmp_batcher *b) {
+  if (!b) return;
+  { std::lock_guard<std::mutex> lk(b->mu); b->stop = true; }
+  b->cv_submit.notify_all();
+  if (b->worker.joinable()) b->worker.join();
+  delete b;
+}
+int32_t mmp_place_submit(mmp_batcher *b, const mmp_decision_in *in, const mmp_instance_row *fresh, const int32_t *extra, int64_t now_ms,
+                         mmp_decision_out *out, uint32_t *decision_id) {
+  if (!b || !in || !out) { g_err = "null argument"; return MMP_E_ARG; }
+  if (in->extra_n < 0 || in->extra_n > MMP_MAX_EXTRA || (in->extra_n > 0 && (!extra || in->extra_off < 0))) { g_err = "bad extra slice"; return MMP_E_ARG; }
+  mmp_batcher::Req r;
+  r.in = *in;
+  const uint32_t id = b->next_id.fetch_add(1) & 0xffffffu;
+  r.in.flags = (r.in.flags & 0xffu) | MMP_DF_OWN_ID | (id << 8);
+  r.has_fresh = fresh != nullptr && in->fresh >= 0;
+  if (r.has_fresh) r.fresh = fresh[in->fresh];
+  r.n_extra = in->extra_n;
+  for (int32_t i = 0; i < r.n_extra; i++) r.extra[i] = extra[in->extra_off + i];
+  r.now_ms = now_ms; r.done = false; r.rc = 0;
+  {
+    std::unique_lock<std::mutex> lk(b->mu);
+    if (b->stop) { g_err = "batcher is shut down"; return MMP_E_STATE; }
+    b->queue.push_back(&r);
+    if ((int32_t)b->queue.size() == 1 || (int32_t)b->queue.size() >= b->max_batch) b->cv_submit.notify_one();
+    b->cv_done.wait(lk, [&] { return r.done; });
+    if (r.rc < 0) g_err = b->err;
+  }
+  *out = r.out;
+  if (decision_id) *decision_id = id;
+  return r.rc;
+}
+int32_t mmp_batcher_stats(mmp_batcher *b, int64_t *batches, int64_t *decisions) {
+  if (!b) { g_err = "null batcher"; return MMP_E_ARG; }
+  if (batches) *batches = b->batches.load();
+  if (decisions) *decisions = b->decisions.load();
+  return MMP_OK;
+}
 }  // extern "C"
 
 #include "scan_kernels.cuh"

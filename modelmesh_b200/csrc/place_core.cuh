@@ -480,6 +480,11 @@ struct DecisionCtx {
 };
 static constexpr int LANE_MAX_EXTRA = 4;  // decisions with more extra excludes go to the cooperative general routine
 MMP_HD int ctx_slot(const DecisionCtx &c) { return c.slot & 0xffff; }
+// the id the hash-indexed pick (N4, MM:4981) is drawn with: the decision's position in the batch (+ id_base), or its own
+// 24-bit id when the caller numbers its decisions itself (MMP_DF_OWN_ID: coalesced single decisions of many threads)
+MMP_HD uint64_t pick_id(const mmp_decision_in &d, uint64_t positional) {
+  return (d.flags & MMP_DF_OWN_ID) ? (uint64_t)(d.flags >> 8) : positional;
+}
 MMP_HD bool ctx_has_pref(const DecisionCtx &c) { return (c.slot >> 16) & 1; }
 
 // The context is gathered in two steps so that a kernel can issue the first (two independent gathers that depend only on

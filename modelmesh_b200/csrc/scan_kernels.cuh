@@ -394,7 +394,7 @@ __global__ void k_lru_events(LruView v, const LruEv *__restrict__ ev, const int 
       bool gone = false;
       evict_loop(e, now, e.model, &gone);
       if (e.op != LEV_LOAD) continue;
-      if (lane == 0) hk.force_publish[inst] = 1;
+      if (lane == 0 && hk.enabled) hk.force_publish[inst] = 1;
       if (gone) { if (lane == 0) hk.status[e.dec] = CH_FALLTHRU; continue; }  // MM:5145-5148
       // early reject MM:5185-5190 (capacity, weightedSize, oldestTime after the placeholder went in)
       long long ot, os;

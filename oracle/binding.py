@@ -76,6 +76,7 @@ def lib() -> C.CDLL:
             "orc_cluster_stats": (C.c_int, [P, P]), "orc_partition_stats": (C.c_int, [P, P, P, I32]),
             "orc_instance_partition": (C.c_int, [P, I32]), "orc_type_stats": (C.c_int, [P, C.c_char_p, P]),
             "orc_get_next_batch": (I64, [P, I32, P, STRS, I32, P, I32, P, P, I64, U64, I32, P, P, P, P, P, I64]),
+            "orc_get_next_batch_dense": (I64, [P, I32, P, STRS, I32, P, I32, P, P, I64, U64, I32, P]),
             "orc_lru_create": (P, [I64]), "orc_lru_destroy": (None, [P]),
             "orc_lru_apply": (I64, [P, P, I64, I64, P, I64]), "orc_lru_oldest_time": (I64, [P]),
             "orc_lru_weighted_size": (I64, [P]), "orc_lru_size": (I64, [P]), "orc_lru_dump": (I64, [P, P, P, P, I64]),
@@ -224,13 +225,19 @@ class OracleFleet:
 
     def get_next_batch(self, dec: np.ndarray, type_names: Sequence[str], excl_off: np.ndarray, excl_idx: np.ndarray,
                        now_ms: int, seed: int, fresh: Optional[np.ndarray] = None, threads: int = 1,
-                       want_candidates: bool = False, cand_cap: Optional[int] = None):
+                       want_candidates: bool = False, cand_cap: Optional[int] = None, dense: bool = False):
         dec = np.ascontiguousarray(dec, dtype=DECISION)
         n = len(dec)
         excl_off = np.ascontiguousarray(excl_off, dtype=np.int64)
         excl_idx = np.ascontiguousarray(excl_idx, dtype=np.int32)
         fresh_a = None if fresh is None else np.ascontiguousarray(fresh, dtype=INST)
         out = np.zeros(n, dtype=RESULT)
+        if dense:  # CPU-baseline mode (ii): entries through a rank-ordered array
+            rc = self.L.orc_get_next_batch_dense(self.h, n, _ptr(dec), _strs(type_names), len(type_names), _ptr(fresh_a),
+                                                 0 if fresh_a is None else len(fresh_a), _ptr(excl_off), _ptr(excl_idx), now_ms, seed,
+                                                 threads, _ptr(out))
+            assert rc >= 0, rc
+            return out
         if not want_candidates:
             rc = self.L.orc_get_next_batch(self.h, n, _ptr(dec), _strs(type_names), len(type_names), _ptr(fresh_a),
                                            0 if fresh_a is None else len(fresh_a), _ptr(excl_off), _ptr(excl_idx),

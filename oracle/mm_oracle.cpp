@@ -869,6 +869,10 @@ struct EntIter {
   size_t li = 0;
   const Fleet *f; const OptSet *constrainTo; const ExcludeSet *exclude; bool useReplicaSets;
   const Entry *peeked = nullptr;
+  // CPU-baseline mode (ii) "dense" (BASELINE.md §4): the same filtered iteration over a rank-ordered ARRAY of the entries
+  // (built once per batch) instead of the ordered set's tree walk
+  const std::vector<const Entry *> *dense = nullptr;
+  size_t di = 0;
   bool pred(const Entry &ent) const {  // MM:4763-4770
     int32_t iid = ent.idx;
     if ((*constrainTo && !(*constrainTo)->count(iid)) || exclude->isExcluded(iid) ||
@@ -880,6 +884,13 @@ struct EntIter {
   bool hasNext() {
     if (list) return li < list->size();
     if (peeked) return true;
+    if (dense) {
+      while (di < dense->size()) {
+        const Entry *e = (*dense)[di++];
+        if (pred(*e)) { peeked = e; return true; }
+      }
+      return false;
+    }
     while (cur != end) {
       const Entry &e = *cur;
       ++cur;
@@ -902,17 +913,18 @@ static const int64_t TWELVE_MIN_MS = 12LL * 60000, ONE_DAY_MS = 86400000LL, FIVE
 inline int64_t age(int64_t t, int64_t now) { return t == 0 ? 0 : jsub(now, t); }  // MM:4162-4164
 
 void getNext(const Fleet &f, const std::string &modelType, int32_t self, const IR &fresh, bool favourSelf,
-             int64_t lastUsedTime, const ExcludeSet &exclude, int64_t now, uint64_t rnd, GetNextOut &o) {
+             int64_t lastUsedTime, const ExcludeSet &exclude, int64_t now, uint64_t rnd, GetNextOut &o,
+             const std::vector<const Entry *> *dense = nullptr) {
   const bool excludeSelf = exclude.isExcluded(self);
   static const OptSet NULLSET;
   const OptSet *constrainTo = f.haveTc ? f.tcm.getCandidateInstances(modelType) : &NULLSET;
   const bool rsEmpty = f.upgradeTracker.likelyReplacedReplicaSets.empty();
 
-  EntIter it{f.clusterState.begin(), f.clusterState.end(), nullptr, 0, &f, constrainTo, &exclude, true, nullptr};
+  EntIter it{f.clusterState.begin(), f.clusterState.end(), nullptr, 0, &f, constrainTo, &exclude, true, nullptr, dense, 0};
   if (!it.hasNext()) {
     if (rsEmpty) return;  // null
     o.flags |= 1;
-    it = EntIter{f.clusterState.begin(), f.clusterState.end(), nullptr, 0, &f, constrainTo, &exclude, false, nullptr};
+    it = EntIter{f.clusterState.begin(), f.clusterState.end(), nullptr, 0, &f, constrainTo, &exclude, false, nullptr, dense, 0};
     if (!it.hasNext()) return;
   }
   const Entry *bestEntry = it.next();
@@ -1344,12 +1356,15 @@ int orc_type_stats(orc_fleet *h, const char *type, orc_stats_t *out) {  // MM:14
   return 0;
 }
 
-int64_t orc_get_next_batch(orc_fleet *h, int32_t n, const orc_decision_t *dec, const char *const *type_names, int32_t n_types,
+static int64_t get_next_batch_impl(orc_fleet *h, int32_t n, const orc_decision_t *dec, const char *const *type_names, int32_t n_types,
                            const orc_inst_t *fresh, int32_t n_fresh, const int64_t *excl_off, const int32_t *excl_idx,
                            int64_t now_ms, uint64_t seed, int32_t threads, orc_result_t *out, int64_t *cand_off,
-                           int32_t *cand_idx, int32_t *cand_load, uint8_t *cand_keep, int64_t cand_cap) {
+                           int32_t *cand_idx, int32_t *cand_load, uint8_t *cand_keep, int64_t cand_cap, bool dense_mode) {
   if (!h || n < 0) return -1;
   const Fleet &f = h->f;
+  std::vector<const Entry *> dense_order;
+  if (dense_mode) for (const Entry &e : f.clusterState) dense_order.push_back(&e);
+  const std::vector<const Entry *> *dense = dense_mode ? &dense_order : nullptr;
   std::vector<std::string> tnames;
   for (int i = 0; i < n_types; i++) tnames.push_back(type_names[i]);
   static const std::string NOTYPE = "\x01<no-config>";
@@ -1377,7 +1392,7 @@ int64_t orc_get_next_batch(orc_fleet *h, int32_t n, const orc_decision_t *dec, c
       ExcludeSet ex{excl_idx + excl_off[i], excl_off[i + 1] - excl_off[i]};
       const std::string &type = (d.type_idx >= 0 && d.type_idx < n_types) ? tnames[d.type_idx] : NOTYPE;
       o = GetNextOut();
-      getNext(f, type, d.self, freshRec, d.favour_self != 0, d.last_used, ex, now_ms, orc_hash64(seed, d.decision_id), o);
+      getNext(f, type, d.self, freshRec, d.favour_self != 0, d.last_used, ex, now_ms, orc_hash64(seed, d.decision_id), o, dense);
       out[i].target = o.target; out[i].n_candidates = o.nCandidates; out[i].n_remaining = o.nRemaining;
       out[i].pick_index = o.pickIndex; out[i].best = o.best; out[i].flags = o.flags;
       if (wantCands) {
@@ -1403,6 +1418,21 @@ int64_t orc_get_next_batch(orc_fleet *h, int32_t n, const orc_decision_t *dec, c
   if (wantCands) cand_off[n] = candPos;
   if (bad) return -2;
   return candPos;
+}
+
+int64_t orc_get_next_batch(orc_fleet *h, int32_t n, const orc_decision_t *dec, const char *const *type_names, int32_t n_types,
+                           const orc_inst_t *fresh, int32_t n_fresh, const int64_t *excl_off, const int32_t *excl_idx,
+                           int64_t now_ms, uint64_t seed, int32_t threads, orc_result_t *out, int64_t *cand_off,
+                           int32_t *cand_idx, int32_t *cand_load, uint8_t *cand_keep, int64_t cand_cap) {
+  return get_next_batch_impl(h, n, dec, type_names, n_types, fresh, n_fresh, excl_off, excl_idx, now_ms, seed, threads, out, cand_off, cand_idx,
+                             cand_load, cand_keep, cand_cap, false);
+}
+/* CPU-baseline mode (ii) "dense" (BASELINE.md §4): same decisions, entries walked through a rank-ordered array */
+int64_t orc_get_next_batch_dense(orc_fleet *h, int32_t n, const orc_decision_t *dec, const char *const *type_names, int32_t n_types,
+                                 const orc_inst_t *fresh, int32_t n_fresh, const int64_t *excl_off, const int32_t *excl_idx,
+                                 int64_t now_ms, uint64_t seed, int32_t threads, orc_result_t *out) {
+  return get_next_batch_impl(h, n, dec, type_names, n_types, fresh, n_fresh, excl_off, excl_idx, now_ms, seed, threads, out, nullptr, nullptr,
+                             nullptr, nullptr, 0, true);
 }
 
 orc_lru *orc_lru_create(int64_t capacity) { return new orc_lru(capacity); }

@@ -129,6 +129,12 @@ int64_t orc_get_next_batch(orc_fleet *, int32_t n, const orc_decision_t *dec, co
                            orc_result_t *out, int64_t *cand_off, int32_t *cand_idx, int32_t *cand_load,
                            uint8_t *cand_keep, int64_t cand_cap);
 
+/* the same decisions with the entries walked through a rank-ordered array built once per batch instead of the ordered set
+ * (CPU-baseline mode (ii) "dense" of BASELINE.md §4) */
+int64_t orc_get_next_batch_dense(orc_fleet *, int32_t n, const orc_decision_t *dec, const char *const *type_names,
+                                 int32_t n_types, const orc_inst_t *fresh, int32_t n_fresh, const int64_t *excl_off,
+                                 const int32_t *excl_idx, int64_t now_ms, uint64_t seed, int32_t threads, orc_result_t *out);
+
 /* ---- time-ordered weighted LRU (clhm/ConcurrentLinkedHashMap + LinkedDeque) ---- */
 typedef struct orc_lru orc_lru;
 typedef struct {

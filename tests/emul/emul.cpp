@@ -160,22 +160,22 @@ int32_t mmp_place_batch_trace(mmp_fleet *f, const mmp_decision_in *in, int32_t n
       uint32_t first8[4];
       for (int j = 0; j < 4; j++) first8[j] = (uint32_t)T.nzw[2 * j] | ((uint32_t)T.nzw[2 * j + 1] << 16);
       done = decide_stream(v, T, cx, true, window.data(), ww, first8, g_lane_global ? erow : nullptr, self_eword, now_ms, seed,
-                           f->id_base + (uint64_t)i, SoloVote(), o, g_lane_budget);
+                           pick_id(in[i], f->id_base + (uint64_t)i), SoloVote(), o, g_lane_budget);
       g_lane_decisions++;
       if (!done) g_bails++;
     } else if (sharded) {
       // instance-sharded harness: only the general routine knows about rank ranges (decide_fast assumes whole rows)
     } else if (win == 1 && !cand_mask) {  // the lane-per-decision shape of k_place_lanes: budgeted walk, cooperative redo when it bails
       CoopLane cl(g_lane_budget);
-      decide_ctx<CoopLane>(v, cx, erow, extra, now_ms, seed, f->id_base + (uint64_t)i, cl, o, nullptr);
+      decide_ctx<CoopLane>(v, cx, erow, extra, now_ms, seed, pick_id(in[i], f->id_base + (uint64_t)i), cl, o, nullptr);
       g_lane_decisions++;
       done = !(o.flags & MMP_TF_BAIL);
       if (!done) g_bails++;
-    } else if (!cand_mask) done = win == 16 ? decide_fast<true>(v, cx, erow, now_ms, seed, f->id_base + (uint64_t)i, co16, o)
-                         : win == 8 ? decide_fast<true>(v, cx, erow, now_ms, seed, f->id_base + (uint64_t)i, co8, o)
-                                    : decide_fast<true>(v, cx, erow, now_ms, seed, f->id_base + (uint64_t)i, co, o);
+    } else if (!cand_mask) done = win == 16 ? decide_fast<true>(v, cx, erow, now_ms, seed, pick_id(in[i], f->id_base + (uint64_t)i), co16, o)
+                         : win == 8 ? decide_fast<true>(v, cx, erow, now_ms, seed, pick_id(in[i], f->id_base + (uint64_t)i), co8, o)
+                                    : decide_fast<true>(v, cx, erow, now_ms, seed, pick_id(in[i], f->id_base + (uint64_t)i), co, o);
     if (!done)
-      decide_ctx<Coop1>(v, cx, erow, extra, now_ms, seed, f->id_base + (uint64_t)i, co, o,
+      decide_ctx<Coop1>(v, cx, erow, extra, now_ms, seed, pick_id(in[i], f->id_base + (uint64_t)i), co, o,
                         cand_mask ? cand_mask + (size_t)i * 2 * v.row_words : nullptr);
     out[i].target = o.target; out[i].n_candidates = o.n_candidates;
     if (f->keys) f->keys[i] = shard_key(o, f->hs.cfg.shard_rank);
