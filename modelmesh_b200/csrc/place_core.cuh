@@ -758,13 +758,17 @@ struct WarpVote { MMP_D bool any(bool p) const { return __any_sync(0xffffffffu, 
 #endif
 
 // The common case of getNext for ONE DECISION PER LANE (k_place_lanes), written so that the 32 lanes of a warp stay
-// converged: every phase is a walk whose loop is left by a warp vote, bodies are predicated on a per-lane state, and the
-// scalar work between the walks is straight-line.  A walk steps through the slot's compressed word list (LaneTables::nzw):
-// step k looks at row word W(k) = nzw[k], the k-th word that holds any candidate of the decision's type.  Phases:
+// converged AND execute few instructions per step.  A walk steps through the slot's compressed word list
+// (LaneTables::nzw): step k looks at row word W(k) = nzw[k], the k-th word that holds any candidate of the decision's type.
+// Walks run in CHUNKS of 8 steps: at the start of a chunk every walking lane loads the 8 list entries from ITS OWN position
+// on (entries as four u16 pairs, their row words from the window or -- beyond it -- from the row in global memory: 8
+// independent loads), then the 8 steps run as straight-line code with compile-time register indices, each lane on its own
+// word.  One warp vote per chunk, none per step; a long walk (C5: 100+ steps over sparse candidate masks) pays one L2 round
+// trip per 8 steps.  Phases:
 //   A   first entry of F = cand & ~excl & ~extra (MM:4806)
 //   A'  non-simple (a), MM:4828-4852: the first later entry that is preferred or full
 //   B   the shortlist walk (MM:4901-4937): first member of S that fails its test; a word whose count summary is
-//       "mixed" is evaluated exactly (32 counts) by all lanes that stopped on one, in one converged step
+//       "mixed" is evaluated exactly (32 counts) by the lanes that stop on one
 //   C   the hash-indexed pick (MM:4981-4986): k-th member of the shortlist
 // Same semantics and quirks as decide_ctx (N2: the non-self test reads the caller's fresh record).  Returns false --
 // and the caller redoes the decision with the cooperative general routine -- for everything outside the common case:
@@ -773,8 +777,9 @@ struct WarpVote { MMP_D bool any(bool p) const { return __any_sync(0xffffffffu, 
 // The decision's exclusion row is seen through a WINDOW: ewin[k] = row word W(k) for k < win_words (k_place_lanes copies
 // these out of the TMA landing stage so that the stage can take the next rows while the lanes compute); steps beyond the
 // window read the row itself (erow_g: global memory, word index relative to word_lo -- the row has just been streamed, so it
-// is an L2 hit), or end the lane's attempt when erow_g is null.  first8 = entries 0..7 of the slot's word list as four u16 pairs.  self_eword = the row word that holds self's bit (anywhere
-// in the row).  Must be called by every lane of the vote group (active = false for lanes without a decision).
+// is an L2 hit), or end the lane's attempt when erow_g is null.  first8 = entries 0..7 of the slot's word list as four u16
+// pairs.  self_eword = the row word that holds self's bit (anywhere in the row).  Must be called by every lane of the vote
+// group (active = false for lanes without a decision).
 template <class V>
 MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const DecisionCtx &c, bool active, const uint32_t *ewin,
                           uint32_t win_words, const uint32_t *first8, const uint32_t *erow_g, uint32_t self_eword, int64_t now, uint64_t seed,
@@ -792,59 +797,6 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
   const FreshRow fr = c.fr;
   int32_t left = budget;
   const bool has_x = d.extra_n > 0;
-  // The word list and the row are seen through a CHUNK of 8 consecutive steps [base, base + 8) held in registers: the list
-  // entries (u16 pairs) and the row words they name (from the window, or -- beyond it -- from the row in global memory: 8
-  // independent loads issued together).  A chunk is refilled for ALL walking lanes whenever one of them leaves its chunk
-  // (warp vote), so the lanes of a warp refill at the same loop iterations and a long walk (C5: 100+ steps over sparse
-  // candidate masks) pays one L2 round trip per 8 steps, not two dependent ones per step.  The first chunk (steps 0..7)
-  // comes from the caller's preloaded entries `first8` and the window: the common case touches no list memory at all.
-  uint32_t base = 0;
-  uint32_t wq[4] = {first8[0], first8[1], first8[2], first8[3]};
-  uint32_t eq[8];
-  auto wsel = [&](uint32_t j) -> uint32_t {          // entry j (0..7) of the chunk, without dynamic register indexing
-    uint32_t q = wq[0];
-    q = (j >> 1) == 1 ? wq[1] : q; q = (j >> 1) == 2 ? wq[2] : q; q = (j >> 1) == 3 ? wq[3] : q;
-    return (q >> ((j & 1u) * 16u)) & 0xffffu;
-  };
-  auto fill_rows = [&]() {                           // row words of the chunk's steps
-#pragma unroll
-    for (uint32_t j = 0; j < 8; j++) {
-      const uint32_t kk = base + j;
-      uint32_t e = 0;
-      if (kk < NZ) {
-        if (kk < win_words) e = ewin[kk];
-        else if (erow_g != nullptr) e = ldro(erow_g + (wsel(j) - WS));
-      }
-      eq[j] = e;
-    }
-  };
-  fill_rows();
-  auto refill = [&](uint32_t k) {
-    base = k;
-#pragma unroll
-    for (uint32_t j = 0; j < 4; j++) {
-      const uint32_t k0 = k + 2 * j, k1 = k0 + 1;
-      const uint32_t lo16 = k0 < NZ ? (uint32_t)ldro(T.nzw + k0) : 0xffffu, hi16 = k1 < NZ ? (uint32_t)ldro(T.nzw + k1) : 0xffffu;
-      wq[j] = lo16 | (hi16 << 16);
-    }
-    fill_rows();
-  };
-  // to be called by every lane at the top of every walk iteration
-  auto sync = [&](bool walking, uint32_t k) {
-    const bool need = walking && k < NZ && (k - base) >= 8u;
-    if (vote.any(need)) { if (walking && k < NZ) refill(k); }
-  };
-  auto W = [&](uint32_t k) -> uint32_t { return wsel(k - base); };  // step k inside the current chunk
-  // word W(k) of the decision's exclusion row; false when it is out of reach (beyond the window and no row to read)
-  auto Ew = [&](uint32_t k, uint32_t, uint32_t &e) -> bool {
-    if (k >= win_words && erow_g == nullptr) return false;
-    const uint32_t j = k - base;
-    uint32_t v = eq[0];
-    v = j == 1 ? eq[1] : v; v = j == 2 ? eq[2] : v; v = j == 3 ? eq[3] : v; v = j == 4 ? eq[4] : v;
-    v = j == 5 ? eq[5] : v; v = j == 6 ? eq[6] : v; v = j == 7 ? eq[7] : v;
-    e = v;
-    return true;
-  };
   auto xmask = [&](uint32_t wi) -> uint32_t {  // bits of word wi taken by the extra excludes
     uint32_t m = 0;
 #pragma unroll
@@ -852,30 +804,70 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
     return m;
   };
   auto pbit = [&](uint32_t r) -> bool { return (ldro(P + (r >> 5)) >> (r & 31)) & 1u; };
+  // ---- the chunk: steps [k0, k0 + 8) of the lane's walk ----
+  uint32_t wq[4], eq[8];
+  bool reach;  // false: the chunk reaches beyond the window and there is no row to read
+  auto load_chunk = [&](uint32_t k0, bool use_first8) {
+    if (use_first8) { wq[0] = first8[0]; wq[1] = first8[1]; wq[2] = first8[2]; wq[3] = first8[3]; }
+    else {
+#pragma unroll
+      for (uint32_t j = 0; j < 4; j++) {
+        const uint32_t ka = k0 + 2 * j, kb_ = ka + 1;
+        const uint32_t lo16 = ka < NZ ? (uint32_t)ldro(T.nzw + ka) : 0xffffu, hi16 = kb_ < NZ ? (uint32_t)ldro(T.nzw + kb_) : 0xffffu;
+        wq[j] = lo16 | (hi16 << 16);
+      }
+    }
+    reach = true;
+#pragma unroll
+    for (uint32_t j = 0; j < 8; j++) {
+      const uint32_t kk = k0 + j;
+      uint32_t e = 0;
+      if (kk < NZ) {
+        if (kk < win_words) e = ewin[kk];
+        else if (erow_g != nullptr) e = ldro(erow_g + (((wq[j >> 1] >> ((j & 1u) * 16u)) & 0xffffu) - WS));
+        else reach = false;
+      }
+      eq[j] = e;
+    }
+  };
+  // Runs body(k, wi, e) on successive steps of every walking lane, from the lane's own start position, until no lane walks.
+  // body returns true to go on to the next step.  `walking` is cleared when the lane stops (body said so, the list ended:
+  // ended = true, or the budget / reach ran out: live = false).
+  // (a macro-like lambda: the 8 steps are unrolled so that eq[j] / wq[j >> 1] are compile-time register picks)
+#define MMP_WALK(K, WALKING, ENDED, BODY)                                                                                   \
+  for (;;) {                                                                                                                \
+    if (!vote.any(WALKING)) break;                                                                                          \
+    if (WALKING) {                                                                                                          \
+      if (K >= NZ) { WALKING = false; ENDED = true; }                                                                        \
+      else if (left <= 0) { WALKING = false; live = false; }                                                                 \
+      else { load_chunk(K, K == 0); left -= 8; }                                                                             \
+    }                                                                                                                       \
+    _Pragma("unroll") for (uint32_t j_ = 0; j_ < 8; j_++) {                                                                  \
+      if (WALKING) {                                                                                                        \
+        if (K >= NZ) { WALKING = false; ENDED = true; }                                                                      \
+        else if (K >= win_words && !reach) { WALKING = false; live = false; }                                                \
+        else {                                                                                                              \
+          const uint32_t wi = (wq[j_ >> 1] >> ((j_ & 1u) * 16u)) & 0xffffu, e = eq[j_];                                      \
+          bool go_;                                                                                                         \
+          BODY;                                                                                                             \
+          if (go_) K++; else WALKING = false;                                                                                \
+        }                                                                                                                   \
+      }                                                                                                                     \
+    }                                                                                                                       \
+  }
 
   // ---- A: first filtered entry ----
   uint32_t b = NONE_RANK, kb = 0;
   {
     uint32_t k = 0;
-    bool search = live;
-    for (;;) {
-      sync(search, k);
-      if (search) {
-        if (k >= NZ || left <= 0) search = false;
-        else {
-          const uint32_t wi = W(k);
-          uint32_t e;
-          if (!Ew(k, wi, e)) search = false;
-          else {
-            uint32_t x = ldro(CX + wi) & ~e;
-            if (has_x) x &= ~xmask(wi);
-            if (x) { b = wi * 32u + (uint32_t)ffs32(x); kb = k; search = false; }
-            else { k++; left--; }
-          }
-        }
-      }
-      if (!vote.any(search)) break;
-    }
+    bool walking = live, ended = false;
+    MMP_WALK(k, walking, ended, {
+      uint32_t x = ldro(CX + wi) & ~e;
+      if (has_x) x &= ~xmask(wi);
+      if (x) { b = wi * 32u + (uint32_t)ffs32(x); kb = k; }
+      go_ = x == 0;
+    })
+    (void)ended;
   }
   if (b == NONE_RANK) live = false;  // none in reach: the general routine decides (replicaset retry, null)
   RankRow rb; rb.lru = 0; rb.rem = 0; rb.count = 0; rb.rpm = 0; rb.idx = -1; rb.flags = 0;
@@ -894,30 +886,18 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
   }
   // ---- A': non-simple (a) ----
   uint32_t r1 = NONE_RANK, k1 = kb;
+  bool a_ended = false;
   {
     const uint32_t b_w = b >> 5, m_b = mask_above(b_w * 32u, b);
     uint32_t k = kb;
-    bool search = live && !simple;
-    for (;;) {
-      sync(search, k);
-      if (search) {
-        if (k >= NZ) search = false;                         // natural end of the row
-        else if (left <= 0) { search = false; live = false; }
-        else {
-          const uint32_t wi = W(k);
-          uint32_t e;
-          if (!Ew(k, wi, e)) { search = false; live = false; }
-          else {
-            uint32_t x = ldro(CX + wi) & ~e & (ldro(P + wi) | ldro(T.full + wi));
-            if (has_x) x &= ~xmask(wi);
-            if (wi == b_w) x &= m_b;
-            if (x) { r1 = wi * 32u + (uint32_t)ffs32(x); k1 = k; search = false; }
-            else { k++; left--; }
-          }
-        }
-      }
-      if (!vote.any(search)) break;
-    }
+    bool walking = live && !simple;
+    MMP_WALK(k, walking, a_ended, {
+      uint32_t x = ldro(CX + wi) & ~e & (ldro(P + wi) | ldro(T.full + wi));
+      if (has_x) x &= ~xmask(wi);
+      if (wi == b_w) x &= m_b;
+      if (x) { r1 = wi * 32u + (uint32_t)ffs32(x); k1 = k; }
+      go_ = x == 0;
+    })
   }
   bool open = false;
   if (live && !simple) {
@@ -971,58 +951,42 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
   // ---- B: first member of S' that fails its walk test, counting the members before it ----
   uint32_t cut_others = NONE_RANK, n_in = 0;
   {
-    uint32_t k = k_lo, wi = lo_w, xt = 0;
-    bool search = walk, mixed = false;
-    for (;;) {
-      for (;;) {
-        sync(search, k);
-        if (search) {
-          if (k >= NZ || (wi = W(k)) >= stop_w) {  // the walk's natural end
-            search = false;
-            if (lim == NONE_RANK && open_end) open = true;
-          } else if (left <= 0) { search = false; live = false; }  // budget exhausted before the natural end
-          else {
-            uint32_t e;
-            if (!Ew(k, wi, e)) { search = false; live = false; }
-            else {
-              const uint32_t x = Sw(wi, e);
-              int cls = 0;  // 0: no member fails, 1: every member (but a passing self) fails, 2: look at the counts
-              uint32_t v = x;
-              if (c_self) { if (wi == sw_) v &= ~sb_; cls = v ? 1 : 0; }
-              else if (x) { const WordSumI m = ldro_sum(T.csum + wi); cls = !cv(m.hi) ? 0 : (cv(m.lo) ? 1 : 2); }
-              if (cls == 0) { n_in += (uint32_t)popc32(x); k++; left--; }
-              else {
-                search = false; xt = x;
-                if (cls == 1) cut_others = wi * 32u + (uint32_t)ffs32(v);
-                else mixed = true;
-              }
-            }
-          }
-        }
-        if (!vote.any(search)) break;
-      }
-      if (!vote.any(mixed)) break;
-      if (mixed) {  // exact evaluation of a mixed word: 32 counts, zero-padded past the last rank
-        mixed = false;
-        uint32_t vm = 0;
+    uint32_t k = k_lo;
+    bool walking = walk, ended = false;
+    MMP_WALK(k, walking, ended, {
+      go_ = true;
+      if (wi >= stop_w) { ended = true; go_ = false; }  // the walk's natural end (everything at or beyond lim)
+      else {
+        const uint32_t x = Sw(wi, e);
+        int cls = 0;  // 0: no member fails, 1: every member (but a passing self) fails, 2: look at the counts
+        uint32_t v = x;
+        if (c_self) { if (wi == sw_) v &= ~sb_; cls = v ? 1 : 0; }
+        else if (x) { const WordSumI m = ldro_sum(T.csum + wi); cls = !cv(m.hi) ? 0 : (cv(m.lo) ? 1 : 2); }
+        if (cls == 2) {  // exact evaluation of a mixed word: 32 counts, zero-padded past the last rank
+          uint32_t vm = 0;
 #if defined(__CUDA_ARCH__)
-        const int4 *cc = reinterpret_cast<const int4 *>(T.count_col + (size_t)wi * 32u);
+          const int4 *cc = reinterpret_cast<const int4 *>(T.count_col + (size_t)wi * 32u);
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-          const int4 q = __ldg(cc + j);
-          vm |= ((cv(q.x) ? 1u : 0u) | (cv(q.y) ? 2u : 0u) | (cv(q.z) ? 4u : 0u) | (cv(q.w) ? 8u : 0u)) << (4 * j);
-        }
+          for (int jj = 0; jj < 8; jj++) {
+            const int4 qq = __ldg(cc + jj);
+            vm |= ((cv(qq.x) ? 1u : 0u) | (cv(qq.y) ? 2u : 0u) | (cv(qq.z) ? 4u : 0u) | (cv(qq.w) ? 8u : 0u)) << (4 * jj);
+          }
 #else
-        const int32_t *cc = T.count_col + (size_t)wi * 32u;
-        for (int j = 0; j < 32; j++) vm |= (cv(cc[j]) ? 1u : 0u) << j;
+          const int32_t *cc = T.count_col + (size_t)wi * 32u;
+          for (int jj = 0; jj < 32; jj++) vm |= (cv(cc[jj]) ? 1u : 0u) << jj;
 #endif
-        vm &= xt;
-        if (vm) cut_others = wi * 32u + (uint32_t)ffs32(vm);
-        else { n_in += (uint32_t)popc32(xt); k++; left--; search = true; }
+          v = vm & x;
+          cls = v ? 1 : 0;
+        }
+        if (cls == 0) n_in += (uint32_t)popc32(x);
+        else {
+          cut_others = wi * 32u + (uint32_t)ffs32(v);
+          n_in += (uint32_t)popc32(x & mask_below(wi * 32u, cut_others));
+          go_ = false;
+        }
       }
-      if (!vote.any(search)) break;
-    }
-    if (cut_others != NONE_RANK) n_in += (uint32_t)popc32(xt & mask_below((cut_others >> 5) * 32u, cut_others));
+    })
+    if (walk && live && ended && cut_others == NONE_RANK && lim == NONE_RANK && open_end) open = true;
   }
   walk = walk && live && !open;
   const uint32_t cut = cut_others < cut_self ? cut_others : cut_self;
@@ -1056,29 +1020,27 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
       }
     }
   }
-  // ---- C: k-th survivor in rank order (re-walks words phase B has visited: no budget is spent) ----
+  // ---- C: k-th survivor in rank order (re-walks words phase B has visited: the budget is not charged again) ----
   {
     const bool drop_self = self_in_sl && !keep_self;
     const uint32_t cut_w = cut >> 5, m_cut = mask_below(cut_w * 32u, cut);
     uint32_t k = k_lo;
-    bool search = sel;
-    for (;;) {
-      sync(search, k);
-      if (search) {
-        uint32_t wi = 0, e = 0;
-        if (k >= NZ || !Ew(k, (wi = W(k)), e)) { search = false; live = false; }  // cannot happen: kth < number of survivors, all in visited words
-        else {
-          uint32_t x = Sw(wi, e);
-          if (wi == cut_w) x &= m_cut;
-          if (drop_self && wi == sw_) x &= ~sb_;
-          const uint32_t n = (uint32_t)popc32(x);
-          if (kth < n) { chosen_rank = wi * 32u + (uint32_t)nth_bit(x, kth); search = false; }
-          else { kth -= n; k++; }
-        }
-      }
-      if (!vote.any(search)) break;
-    }
+    bool walking = sel, ended = false;
+    const int32_t left_keep = left;
+    left = 0x3fffffff;
+    MMP_WALK(k, walking, ended, {
+      uint32_t x = Sw(wi, e);
+      if (wi == cut_w) x &= m_cut;
+      if (drop_self && wi == sw_) x &= ~sb_;
+      const uint32_t n = (uint32_t)popc32(x);
+      go_ = true;
+      if (kth < n) { chosen_rank = wi * 32u + (uint32_t)nth_bit(x, kth); go_ = false; }
+      else kth -= n;
+    })
+    left = left_keep;
+    if (sel && ended) live = false;  // cannot happen: kth < number of survivors, all in visited words
   }
+#undef MMP_WALK
   if (!active) return true;
   if (!live) return false;
   o.first_rank = (int32_t)b;
