@@ -510,18 +510,25 @@ def main():
     launches = solver.kernel_launches() - launches0
     clocks = sampler.finish() if rank == 0 else None
 
-    # ---- B = 1 latency (p99 decision us) ----
+    # ---- B = 1 latency (p99 decision us): mmp_place_one round trips, three ways of launching the single decision ----
     lat = None
     if rank == 0:
         one = np.zeros(1, dtype=DECISION_OUT)
-        ts = []
-        for i in range(300 + 2000):
-            t0 = time.perf_counter()
-            lib.mmp_place_one(solver.h, dec[i % B:i % B + 1].ctypes.data_as(C.c_void_p), None, None,
-                              one.ctypes.data_as(C.c_void_p), fl.now_ms, SEED)
-            if i >= 300:
-                ts.append(1e6 * (time.perf_counter() - t0))
-        lat = {"p50_us": float(np.percentile(ts, 50)), "p99_us": float(np.percentile(ts, 99)), "n": len(ts)}
+        lat = {}
+        for mode, label in ((2, "cuda_graph"), (1, "small_kernel"), (0, "streaming_kernel")):
+            solver._ck(lib.mmp_tune(solver.h, b"one_mode", mode))
+            ts = []
+            for i in range(300 + 2000):
+                t0 = time.perf_counter()
+                lib.mmp_place_one(solver.h, dec[i % B:i % B + 1].ctypes.data_as(C.c_void_p), None, None,
+                                  one.ctypes.data_as(C.c_void_p), fl.now_ms, SEED)
+                if i >= 300:
+                    ts.append(1e6 * (time.perf_counter() - t0))
+            lat[label] = {"p50_us": float(np.percentile(ts, 50)), "p99_us": float(np.percentile(ts, 99)), "n": len(ts)}
+        solver._ck(lib.mmp_tune(solver.h, b"one_mode", 2))
+        lat.update(lat["cuda_graph"])  # the default path: k_place_small replayed as a CUDA graph, zero-copy mapped buffers
+        lat["note"] = ("host timer around mmp_place_one (launch + synchronise + 8-byte result through mapped memory); cuda_graph = one "
+                       "k_place_small node replayed, small_kernel = the same kernel as a stream launch, streaming_kernel = round 1's path")
 
     # ---- N > 1: the instance-sharded path of the north star, measured in the same run.  Every rank holds
     # a column block of the bitmap for ALL models, resolves the whole batch over its rank range, and one

@@ -339,6 +339,13 @@ int32_t mmp_churn_step(mmp_fleet *, const mmp_churn_event *ev, int32_t n, int64_
                        int32_t *n_evict, mmp_instance_row *rows_out, mmp_churn_report *report);
 /* registry state of one model as the device holds it: row + the 4 inline instance indices (first copy_count = loaded) */
 int32_t mmp_churn_model(mmp_fleet *, int32_t model, mmp_model_row *row, int32_t *instances4);
+/* tuning / measurement knobs, same meaning as the MMP_* environment variables read at mmp_fleet_create:
+ *   "one_mode"        how a batch of <= 32 decisions is launched: 0 the streaming kernel (k_place_lanes), 1 the latency kernel
+ *                     k_place_small as a stream launch, 2 (default) k_place_small as a replayed CUDA graph
+ *   "lane_budget"     walk steps a lane may spend before its decision is redone by the whole warp
+ *   "lane_warps"      warps per block of k_place_lanes (0 = default 12)
+ *   "commit_host_only" 1: every commit takes the structural (host) path */
+int32_t mmp_tune(mmp_fleet *, const char *key, int64_t value);
 /* which path the last mmp_fleet_commit took: 1 = structural (host: string ranks, type-constraint sets, sort), 2 = device
  * (numeric instance updates / model-record deltas only: scattered into the device-resident tables, re-ranked and rebuilt
  * there); and its duration on the host clock */

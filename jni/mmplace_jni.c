@@ -114,6 +114,13 @@ jint FN(modelsBulk)(JNIEnv *env, jclass c, jlong h, jint first, jint n, jobject 
   return mmp_models_bulk(H(h), first, n, (const mmp_model_row *)BUF(rows), (const int64_t *)BUF(edgeOff), (const int32_t *)BUF(edgeInst));
 }
 jint FN(commit)(JNIEnv *env, jclass c, jlong h) { (void)env; (void)c; return mmp_fleet_commit(H(h)); }
+jint FN(tune)(JNIEnv *env, jclass c, jlong h, jstring key, jlong value) {
+  const char *ck = utf(env, key);
+  jint rc = mmp_tune(H(h), ck, value);
+  (void)c;
+  unutf(env, key, ck);
+  return rc;
+}
 /* out[0] = path (1 structural, 2 device), returns the duration in ms */
 jdouble FN(commitInfo)(JNIEnv *env, jclass c, jlong h, jintArray pathOut) {
   int32_t path = 0;

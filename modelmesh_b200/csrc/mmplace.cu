@@ -528,6 +528,64 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotVie
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// k_place_small -- the latency path (B = 1 .. a few hundred decisions: one getNext on a request thread).  No landing
+// stages: a lane reads its decision's row words straight from global memory in chunks of 8 (decide_stream with an empty
+// window), so a single decision costs a handful of dependent L2 reads instead of a whole pipeline step of
+// k_place_lanes.  hdr (optional, pinned mapped memory): {now, seed, n} read by the kernel, so that a captured CUDA graph can
+// be replayed for every call without touching its node parameters.
+// ---------------------------------------------------------------------------------------------------------------
+struct SmallHdr { long long now; unsigned long long seed, id_base; int n, n_fresh, n_extra, pad; };
+__global__ void __launch_bounds__(32) k_place_small(const SnapshotView s_arg, const mmp_decision_in *__restrict__ in, int n_arg,
+                                                    const FreshRow *__restrict__ fresh, int n_fresh_arg, const int32_t *__restrict__ extra,
+                                                    mmp_decision_out *__restrict__ out, int64_t now_arg, uint64_t seed_arg, uint64_t id_base_arg,
+                                                    const volatile SmallHdr *hdr, int budget) {
+  __shared__ DecisionCtx ctx_one;
+  const int lane = threadIdx.x;
+  const int n = hdr ? hdr->n : n_arg;
+  const int n_fresh = hdr ? hdr->n_fresh : n_fresh_arg;
+  SnapshotView s = s_arg;
+  if (hdr) s.n_extra = hdr->n_extra;
+  const int64_t now = hdr ? hdr->now : now_arg;
+  const uint64_t seed = hdr ? hdr->seed : seed_arg, id_base = hdr ? hdr->id_base : id_base_arg;
+  const int i = blockIdx.x * 32 + lane;
+  const bool valid = i < n;
+  const int RW = s.excl_stride;
+  mmp_decision_in d;
+  d.model = -1; d.self = -1; d.last_used = 0; d.flags = 0; d.fresh = -1; d.extra_off = 0; d.extra_n = 0;
+  if (valid) d = in[i];
+  DecisionCtx c;
+  c.slot = -2; c.self_rank = -1; c.self_bits = 0; c.self_count = 0;
+  if (valid) prepare_ctx(s, d, fresh, n_fresh, extra, c);
+  const int m = (valid && d.model >= 0 && d.model < s.n_models) ? d.model : 0;
+  const uint32_t *row = s.excl + (size_t)m * RW;
+  const LaneTables T = lane_tables_global(s, c.slot >= 0 ? ctx_slot(c) : 0);
+  uint32_t first8[4];
+  {
+    const uint4 q = __ldg(reinterpret_cast<const uint4 *>(T.nzw));
+    first8[0] = q.x; first8[1] = q.y; first8[2] = q.z; first8[3] = q.w;
+  }
+  uint32_t self_eword = 0;
+  if (valid && c.self_rank >= 0) self_eword = __ldg(row + (c.self_rank >> 5));
+  DecideOut o;
+  const uint64_t my_id = pick_id(d, id_base + (uint64_t)i);
+  const bool handled = decide_stream(s, T, c, valid, nullptr, 0u, first8, row, self_eword, now, seed, my_id, WarpVote(), o, budget);
+  uint32_t pending = __ballot_sync(0xffffffffu, valid && !handled);
+  while (pending) {
+    const int l = __ffs((int)pending) - 1;
+    pending &= pending - 1;
+    if (lane == l) ctx_one = c;
+    const int ml = __shfl_sync(0xffffffffu, m, l);
+    const uint64_t idl = __shfl_sync(0xffffffffu, my_id, l);
+    __syncwarp();
+    int32_t t2, c2, f2, g2;
+    decide_warp(s, ctx_one, s.excl + (size_t)ml * RW, extra, now, seed, idl, &t2, &c2, &f2, &g2);
+    if (lane == l) { o.target = t2; o.n_candidates = c2; }
+    __syncwarp();
+  }
+  if (valid) out[i] = mmp_decision_out{o.target, o.n_candidates};
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // instance-sharded combine: kernels around the one collective
 // ---------------------------------------------------------------------------------------------------------------
 // keys -> results in place (both 8 bytes per decision) + a flag per decision whose winning shard left it open
@@ -675,6 +733,10 @@ struct PlaceCtx {
   // through PCIe, so a B = 1 call is one launch + one synchronise (no copy calls)
   unsigned char *mapped = nullptr;
   static constexpr size_t MAPPED_BYTES = 16384;
+  // the B = 1 path as a captured CUDA graph (one k_place_small node; now / seed / n travel through the mapped header)
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  int32_t graph_epoch = -1;
 };
 
 struct mmp_fleet {
@@ -709,6 +771,8 @@ struct mmp_fleet {
                                 // instances: 3 stages 3.5, 4 stages 4.1-4.3, 5 stages 3.8 G decisions/s (the fifth stage costs the L1
                                 // its 196 -> 228 KB carve-out step and the lane tables no longer stay resident)
   int shard_chunks = 1;         // MMP_SHARD_CHUNKS (see place_sharded)
+  int one_mode = 2;             // MMP_ONE = lanes | small | graph: how tiny batches are launched (0: the streaming kernel, 1: k_place_small
+                                // as a stream launch, 2: k_place_small as a replayed CUDA graph)
   int lane_budget = LANE_BUDGET;  // MMP_LANE_BUDGET: walk steps per lane before a decision is handed to the whole warp
   int lane_mode = 0;            // MMP_LANE_MODE=1: stream-only probe (rows staged, no decisions) -- measurement aid, results void
   int lanes = 1;                // MMP_KERNEL=tile selects the cooperative-tile kernel (k_place) instead of k_place_lanes
@@ -763,6 +827,8 @@ static void destroy_ctx(PlaceCtx *c) {
   if (c->e1) cudaEventDestroy(c->e1);
   if (c->ready) cudaEventDestroy(c->ready);
   for (int i = 0; i <= PlaceCtx::NSHARD_CHUNKS; i++) if (c->shard_ev[i]) cudaEventDestroy(c->shard_ev[i]);
+  if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+  if (c->graph) cudaGraphDestroy(c->graph);
   if (c->mapped) cudaFreeHost(c->mapped);
   for (int i = 0; i < PlaceCtx::NPIPE; i++) if (c->pipe[i]) cudaStreamDestroy(c->pipe[i]);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -1024,6 +1090,7 @@ int32_t mmp_fleet_create(const mmp_config *cfg, mmp_fleet **out) {
   if (const char *t = getenv("MMP_LANE_WARPS")) { int v = atoi(t); if (v == 8 || v == 10 || v == 12 || v == 14 || v == 16 || v == 20) f->lane_warps = v; }
   if (const char *t = getenv("MMP_LANE_STAGES")) f->lane_stages = atoi(t);
   if (const char *t = getenv("MMP_LANE_MODE")) f->lane_mode = atoi(t);
+  if (const char *t = getenv("MMP_ONE")) f->one_mode = !strcmp(t, "lanes") ? 0 : (!strcmp(t, "small") ? 1 : 2);
   if (const char *t = getenv("MMP_COMMIT")) f->commit_host_only = strcmp(t, "host") == 0;
   if (const char *t = getenv("MMP_LANE_BUDGET")) { int v = atoi(t); if (v >= 1 && v <= 4096) f->lane_budget = v; }
   if (const char *t = getenv("MMP_SHARD_CHUNKS")) f->shard_chunks = atoi(t);
@@ -1336,6 +1403,17 @@ static int32_t commit_locked(mmp_fleet *f) {
   return f->epoch;
 }
 extern "C" {
+/* tuning / measurement knobs (the MMP_* environment variables, settable on a live fleet) */
+int32_t mmp_tune(mmp_fleet *f, const char *key, int64_t value) {
+  NEED(f);
+  if (!key) { g_err = "null key"; return MMP_E_ARG; }
+  if (!strcmp(key, "one_mode") && value >= 0 && value <= 2) f->one_mode = (int)value;
+  else if (!strcmp(key, "lane_budget") && value >= 1 && value <= 4096) f->lane_budget = (int)value;
+  else if (!strcmp(key, "lane_warps") && (value == 0 || value == 8 || value == 10 || value == 12 || value == 14 || value == 16 || value == 20)) f->lane_warps = (int)value;
+  else if (!strcmp(key, "commit_host_only") && (value == 0 || value == 1)) f->commit_host_only = (int)value;
+  else { g_err = "unknown key or value out of range"; return MMP_E_ARG; }
+  return MMP_OK;
+}
 /* which path the last commit took (1 = structural / host, 2 = device) and how long it took on the host clock */
 int32_t mmp_commit_info(mmp_fleet *f, int32_t *path, double *ms) {
   NEED(f);
@@ -1397,9 +1475,48 @@ static int32_t place_impl(mmp_fleet *f, const mmp_decision_in *in, int32_t n, co
       memcpy(h + o_in, in, (size_t)n * sizeof(mmp_decision_in));
       if (n_fresh) memcpy(h + o_fr, c->fresh_host.data(), (size_t)n_fresh * sizeof(FreshRow));
       if (n_extra) memcpy(h + o_ex, extra, (size_t)n_extra * 4);
-      PlaceArgs a{vw, (const mmp_decision_in *)(dbase + o_in), n, (const FreshRow *)(dbase + o_fr), n_fresh,
-                  (const int32_t *)(dbase + o_ex), (mmp_decision_out *)(dbase + o_out), nullptr, nullptr, now_ms, seed, f->id_base.load()};
-      CK(launch_place(f, a, st));
+      if (f->one_mode == 0 || n > 512) {
+        PlaceArgs a{vw, (const mmp_decision_in *)(dbase + o_in), n, (const FreshRow *)(dbase + o_fr), n_fresh,
+                    (const int32_t *)(dbase + o_ex), (mmp_decision_out *)(dbase + o_out), nullptr, nullptr, now_ms, seed, f->id_base.load()};
+        CK(launch_place(f, a, st));
+      } else if (f->one_mode == 1 || n > 32) {
+        k_place_small<<<(n + 31) / 32, 32, 0, st>>>(vw, (const mmp_decision_in *)(dbase + o_in), n, (const FreshRow *)(dbase + o_fr), n_fresh,
+                                                  (const int32_t *)(dbase + o_ex), (mmp_decision_out *)(dbase + o_out), now_ms, seed,
+                                                  f->id_base.load(), nullptr, f->lane_budget);
+        f->launches++;
+        CK(cudaGetLastError());
+      } else {
+        // one 32-thread block as a replayed graph: the node's parameters are those of the epoch it was captured in (the
+        // snapshot view by value, the fixed offsets of this context's mapped buffer laid out for 32 decisions); what changes
+        // per call -- now, seed, id base, n -- is read from the mapped header
+        const size_t g_in = 64, g_out = g_in + 32 * sizeof(mmp_decision_in), g_fr = g_out + 32 * sizeof(mmp_decision_out),
+                     g_ex = g_fr + 32 * sizeof(FreshRow);
+        static_assert(64 + 32 * (sizeof(mmp_decision_in) + sizeof(mmp_decision_out) + sizeof(FreshRow)) + 32 * MMP_MAX_EXTRA * 4 <= PlaceCtx::MAPPED_BYTES, "mapped layout");
+        if (n_fresh > 32 || (size_t)n_extra > 32 * MMP_MAX_EXTRA) { g_err = "tiny batch with oversized side tables"; return MMP_E_ARG; }
+        SmallHdr *hd = reinterpret_cast<SmallHdr *>(h);
+        memmove(h + g_in, in, (size_t)n * sizeof(mmp_decision_in));  // (the generic layout above was filled first: move into the graph's)
+        if (n_fresh) memcpy(h + g_fr, c->fresh_host.data(), (size_t)n_fresh * sizeof(FreshRow));
+        if (n_extra) memcpy(h + g_ex, extra, (size_t)n_extra * 4);
+        hd->now = now_ms; hd->seed = seed; hd->id_base = f->id_base.load(); hd->n = n; hd->n_fresh = n_fresh; hd->n_extra = n_extra;
+        if (c->graph_epoch != f->epoch || !c->graph_exec) {
+          if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+          if (c->graph) { cudaGraphDestroy(c->graph); c->graph = nullptr; }
+          SnapshotView gv = ds.view;
+          gv.n_extra = 32 * MMP_MAX_EXTRA;
+          CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+          k_place_small<<<1, 32, 0, st>>>(gv, (const mmp_decision_in *)(dbase + g_in), 0, (const FreshRow *)(dbase + g_fr), 32,
+                                        (const int32_t *)(dbase + g_ex), (mmp_decision_out *)(dbase + g_out), 0, 0, 0,
+                                        reinterpret_cast<const volatile SmallHdr *>(dbase), f->lane_budget);
+          CK(cudaStreamEndCapture(st, &c->graph));
+          CK(cudaGraphInstantiate(&c->graph_exec, c->graph, 0));
+          c->graph_epoch = f->epoch;
+        }
+        CK(cudaGraphLaunch(c->graph_exec, st));
+        f->launches++;
+        CK(cudaStreamSynchronize(st));
+        memcpy(out, h + g_out, (size_t)n * sizeof(mmp_decision_out));
+        return MMP_OK;
+      }
       CK(cudaStreamSynchronize(st));
       memcpy(out, h + o_out, (size_t)n * sizeof(mmp_decision_out));
       return MMP_OK;

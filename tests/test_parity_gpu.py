@@ -140,3 +140,37 @@ def test_registry_sweep_entry_point(product_lib, oracle_lib):
     d2["self"] = leader
     d2["flags"] &= ~np.uint32(DF_FAVOUR_SELF)
     assert np.array_equal(s.place_sweep(0, 300_000, leader, fl.now_ms, 5), s.place_batch(d2, fl.now_ms, 5))
+
+
+@pytest.mark.parametrize("config,nm,ni,seed", [("C3", 3000, 1300, 3), ("C5", 2500, 700, 5), ("MIX", 800, 300, 14)])
+def test_latency_paths_equal_the_batch(product_lib, oracle_lib, config, nm, ni, seed):
+    """Tiny batches (B = 1 .. 32: one getNext on a request thread) through the three launch paths -- k_place_small replayed as a
+    CUDA graph (default), k_place_small as a stream launch, the streaming kernel -- give what the same decisions give inside a
+    large batch, fresh rows and extra excludes included; between commits the graph is re-captured for the new epoch."""
+    import ctypes as C
+    fl = make_fleet(config, nm, ni, seed)
+    s = solver_from_synth(fl, product_lib)
+    sd = make_decisions(fl, 700, seed)
+    fresh = sd.fresh if len(sd.fresh) else None
+    extra = sd.extra if len(sd.extra) else None
+    for rnd in range(2):
+        whole = s.place_batch(sd.dec, fl.now_ms, 11, fresh=fresh, extra=extra)
+        for mode in (2, 1, 0):
+            s._ck(product_lib.mmp_tune(s.h, b"one_mode", mode))
+            for lo, cnt in ((0, 1), (1, 1), (5, 7), (40, 32), (100, 33), (200, 300)):
+                s._ck(product_lib.mmp_fleet_set_id_base(s.h, lo))
+                got = s.place_batch(sd.dec[lo:lo + cnt], fl.now_ms, 11, fresh=fresh, extra=extra)
+                assert np.array_equal(got, whole[lo:lo + cnt]), (rnd, mode, lo, cnt)
+            s._ck(product_lib.mmp_fleet_set_id_base(s.h, 0))
+            for i in (3, 77, 311):
+                d = sd.dec[i:i + 1].copy()
+                s._ck(product_lib.mmp_fleet_set_id_base(s.h, i))
+                one = s.place_one(d, fl.now_ms, 11, fresh=fresh, extra=extra)
+                assert int(one["target"]) == int(whole["target"][i]) and int(one["n_candidates"]) == int(whole["n_candidates"][i]), (rnd, mode, i)
+            s._ck(product_lib.mmp_fleet_set_id_base(s.h, 0))
+        s._ck(product_lib.mmp_tune(s.h, b"one_mode", 2))
+        # a new epoch (numeric update -> device-path commit): the next round replays a re-captured graph
+        r = fl.inst_rows[int(np.nonzero(fl.inst_rows["shutting_down"] == 0)[0][0])].copy()
+        r["count"] = int(r["count"]) + 50
+        s.instance_update(int(np.nonzero(fl.inst_rows["shutting_down"] == 0)[0][0]), r)
+        s.commit()
