@@ -530,6 +530,40 @@ def main():
         lat["note"] = ("host timer around mmp_place_one (launch + synchronise + 8-byte result through mapped memory); cuda_graph = one "
                        "k_place_small node replayed, small_kernel = the same kernel as a stream launch, streaming_kernel = round 1's path")
 
+    # ---- the batch scans on the same fleet: ClusterStats (~50 B per instance), the reaper's registry sweep +
+    # top-K (24 B per model), each with its CUDA-event time and GB/s against the measured HBM peak ----
+    extra_kernels = None
+    if rank == 0:
+        try:
+            peak_e, _ = measured_hbm_peak()
+            ms = C.c_double()
+            for _ in range(3):
+                solver.stats()
+            solver._ck(lib.mmp_last_timing(solver.h, b"stats", C.byref(ms)))
+            stats_ms = float(ms.value)
+            taken = np.zeros(N_MODELS, dtype=np.uint8)
+            outm = np.zeros(N_MODELS, dtype=np.int32)
+            part = -1 if fl.type_config is None else 0
+            n_sel = 0
+            for _ in range(3):
+                taken[:] = 0
+                solver._ck(lib.mmp_flush_l2(solver.h))
+                n_sel = solver._ck(lib.mmp_reaper_select(solver.h, part, fl.now_ms, taken.ctypes.data_as(C.c_void_p),
+                                                         outm.ctypes.data_as(C.c_void_p), len(outm)))
+            solver._ck(lib.mmp_last_timing(solver.h, b"reaper", C.byref(ms)))
+            reaper_ms = float(ms.value)
+            live = solver.live_instances()
+            extra_kernels = [
+                {"kernel": "k_stats", "bytes": live * 52, "ms": stats_ms, "GB/s": live * 52 / (stats_ms / 1e3) / 1e9 if stats_ms > 0 else None,
+                 "frac": live * 52 / (stats_ms / 1e3) / 1e9 / peak_e if stats_ms > 0 else None,
+                 "note": "32 B row + 8 B capacity + 4 B partition + 8 B count/threads per instance; latency-bound at 10k instances"},
+                {"kernel": "k_reaper_flag + cub select/sort/select (mmp_reaper_select)", "bytes": N_MODELS * 24, "ms": reaper_ms,
+                 "GB/s": N_MODELS * 24 / (reaper_ms / 1e3) / 1e9 if reaper_ms > 0 else None,
+                 "frac": N_MODELS * 24 / (reaper_ms / 1e3) / 1e9 / peak_e if reaper_ms > 0 else None, "selected": int(n_sel),
+                 "note": "algorithmic bytes = 24 B per model (SURVEY.md 8d); the sort of the candidates is extra traffic on top"}]
+        except Exception as ex:
+            print(f"[bench] scan legs skipped: {ex}", file=sys.stderr)
+
     # ---- N > 1: the instance-sharded path of the north star, measured in the same run.  Every rank holds
     # a column block of the bitmap for ALL models, resolves the whole batch over its rank range, and one
     # ncclAllReduce(min) over 64-bit min-loc keys combines the shards (inside mmp_place_batch_device). ----
@@ -629,7 +663,7 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
             "config": workload_config(world),
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-            "latency_b1": lat, "wall_s_timed_region": wall_s,
+            "latency_b1": lat, "wall_s_timed_region": wall_s, "extra": extra_kernels,
         }
         if e2e_sweep is not None and e2e is not None:
             # the workload is a registry sweep, so the call a host makes for it is mmp_place_sweep; the

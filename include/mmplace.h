@@ -346,6 +346,9 @@ int32_t mmp_churn_model(mmp_fleet *, int32_t model, mmp_model_row *row, int32_t 
  *   "lane_warps"      warps per block of k_place_lanes (0 = default 12)
  *   "commit_host_only" 1: every commit takes the structural (host) path */
 int32_t mmp_tune(mmp_fleet *, const char *key, int64_t value);
+/* CUDA-event duration (ms) of the device part of the last mmp_stats ("stats"), mmp_reaper_select ("reaper": registry sweep +
+ * sort + select), mmp_lru_apply ("lru_apply": the event kernel) on this fleet; "commit": host-clock ms of the last commit */
+int32_t mmp_last_timing(mmp_fleet *, const char *key, double *ms);
 /* which path the last mmp_fleet_commit took: 1 = structural (host: string ranks, type-constraint sets, sort), 2 = device
  * (numeric instance updates / model-record deltas only: scattered into the device-resident tables, re-ranked and rebuilt
  * there); and its duration on the host clock */

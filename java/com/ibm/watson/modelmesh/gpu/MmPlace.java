@@ -38,6 +38,7 @@ final class MmPlace {
     static native int commit(long h);
     static native double commitInfo(long h, int[] pathOut);
     static native int tune(long h, String key, long value);
+    static native double lastTiming(long h, String key);
     // plug point 1: placement (CacheMissForwardingLB.getNext MM:4776-5004)
     static native int placeBatch(long h, ByteBuffer in, int n, ByteBuffer fresh, int nFresh, ByteBuffer extra, int nExtra, ByteBuffer out,
                                  long nowMs, long seed);

@@ -121,6 +121,14 @@ jint FN(tune)(JNIEnv *env, jclass c, jlong h, jstring key, jlong value) {
   unutf(env, key, ck);
   return rc;
 }
+jdouble FN(lastTiming)(JNIEnv *env, jclass c, jlong h, jstring key) {
+  const char *ck = utf(env, key);
+  double ms = -1.0;
+  (void)c;
+  if (mmp_last_timing(H(h), ck, &ms) < 0) ms = -1.0;
+  unutf(env, key, ck);
+  return ms;
+}
 /* out[0] = path (1 structural, 2 device), returns the duration in ms */
 jdouble FN(commitInfo)(JNIEnv *env, jclass c, jlong h, jintArray pathOut) {
   int32_t path = 0;

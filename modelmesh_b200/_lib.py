@@ -128,6 +128,7 @@ SYMBOLS = [
     ("mmp_churn_model", _I32, [_P, _I32, _P, _P]),
     ("mmp_commit_info", _I32, [_P, C.POINTER(_I32), C.POINTER(C.c_double)]),
     ("mmp_tune", _I32, [_P, C.c_char_p, _I64]),
+    ("mmp_last_timing", _I32, [_P, C.c_char_p, C.POINTER(C.c_double)]),
     ("mmp_batcher_create", _I32, [_P, _I32, _I32, _U64, C.POINTER(_P)]),
     ("mmp_batcher_destroy", None, [_P]),
     ("mmp_place_submit", _I32, [_P, _P, _P, _P, _I64, _P, C.POINTER(C.c_uint32)]),

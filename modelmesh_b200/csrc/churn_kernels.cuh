@@ -419,7 +419,7 @@ int32_t mmp_churn_step(mmp_fleet *f, const mmp_churn_event *ev, int32_t n, int64
     if (ds.host.n_ranks > 0) {
       k_stats<<<std::min(f->sm_count, (ds.host.n_ranks + 255) / 256), 256, 0, st>>>(ds.rows.as<RankRow>(), ds.cap_col.as<int64_t>(),
                                                                                   ds.part_of_rank.as<int32_t>(), ds.host.n_ranks,
-                                                                                  f->hs.cfg.min_space_units, cs.stats_acc.as<StatsAcc>(), d_min);
+                                                                                  f->hs.cfg.min_space_units, cs.stats_acc.as<StatsAcc>(), d_min, np);
       f->launches++;
     }
     k_churn_type_ok<<<(cs.n_type_ids + 127) / 128, 128, 0, st>>>(cs.stats_acc.as<StatsAcc>(), cs.type_part_off.as<int>(), cs.type_parts.as<int>(),

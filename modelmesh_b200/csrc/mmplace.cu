@@ -16,6 +16,8 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
@@ -756,6 +758,7 @@ struct mmp_fleet {
   std::mutex mirror_mu;         // host_mirror(): lazy download of a device-built snapshot's rank-space vectors
   int commit_host_only = 0;     // MMP_COMMIT=host: every commit takes the structural (host) path (A/B and cross-check)
   bool device_ahead = false;    // the closed loop (churn_kernels.cuh) changed the registry on the device: host tables are behind
+  float t_stats_ms = 0, t_reaper_ms = 0, t_lru_ms = 0;  // CUDA-event time of the device part of the last mmp_stats / mmp_reaper_select / mmp_lru_apply
   int32_t last_commit_path = 0; // 1 structural (host), 2 device
   double last_commit_ms = 0;
   ncclComm_t comm = nullptr;    // instance-shard communicator (mmp_shard_connect)
@@ -1412,6 +1415,17 @@ int32_t mmp_tune(mmp_fleet *f, const char *key, int64_t value) {
   else if (!strcmp(key, "lane_warps") && (value == 0 || value == 8 || value == 10 || value == 12 || value == 14 || value == 16 || value == 20)) f->lane_warps = (int)value;
   else if (!strcmp(key, "commit_host_only") && (value == 0 || value == 1)) f->commit_host_only = (int)value;
   else { g_err = "unknown key or value out of range"; return MMP_E_ARG; }
+  return MMP_OK;
+}
+/* CUDA-event duration (ms) of the device part of the last call of a scan: "stats", "reaper", "lru_apply", "commit" */
+int32_t mmp_last_timing(mmp_fleet *f, const char *key, double *ms) {
+  NEED(f);
+  if (!key || !ms) { g_err = "null argument"; return MMP_E_ARG; }
+  if (!strcmp(key, "stats")) *ms = f->t_stats_ms;
+  else if (!strcmp(key, "reaper")) *ms = f->t_reaper_ms;
+  else if (!strcmp(key, "lru_apply")) *ms = f->t_lru_ms;
+  else if (!strcmp(key, "commit")) *ms = f->last_commit_ms;
+  else { g_err = "unknown key"; return MMP_E_ARG; }
   return MMP_OK;
 }
 /* which path the last commit took (1 = structural / host, 2 = device) and how long it took on the host clock */

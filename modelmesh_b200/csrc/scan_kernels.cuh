@@ -8,24 +8,41 @@
 // ---------------------------------------------------------------------------------------------------------------
 struct StatsAcc { unsigned long long cap, free; int count, copies; };
 
+// One pass over the rank-ordered instance columns (~50 B per instance).  Every block accumulates into shared-memory slots
+// (one per partition + the cluster) and publishes each slot it touched with one global atomic: a handful of global atomics
+// per block instead of eight per instance.
+static constexpr int STATS_SMEM_PARTS = 511;
 __global__ void k_stats(const RankRow *__restrict__ rows, const int64_t *__restrict__ cap_col,
                         const int32_t *__restrict__ part_of_rank, int n_ranks, int64_t min_space, StatsAcc *acc,
-                        long long *min_lru) {
+                        long long *min_lru, int n_parts) {
+  __shared__ StatsAcc sacc[STATS_SMEM_PARTS + 1];
+  const bool use_smem = n_parts <= STATS_SMEM_PARTS;
+  if (use_smem)
+    for (int i = threadIdx.x; i <= n_parts; i += blockDim.x) sacc[i] = StatsAcc{0ull, 0ull, 0, 0};
+  __syncthreads();
   long long lmin = 0x7fffffffffffffffLL;
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_ranks; r += gridDim.x * blockDim.x) {
     RankRow row = rows[r];
     int p = part_of_rank[r] + 1;  // slot 0 = whole cluster
     unsigned long long cap = (unsigned long long)cap_col[r];
     unsigned long long fr = row.rem < min_space ? 0ull : (unsigned long long)row.rem;  // only non-full instances (ISST:67-71)
-    atomicAdd(&acc[0].cap, cap); atomicAdd(&acc[0].free, fr); atomicAdd(&acc[0].count, 1); atomicAdd(&acc[0].copies, row.count);
-    atomicAdd(&acc[p].cap, cap); atomicAdd(&acc[p].free, fr); atomicAdd(&acc[p].count, 1); atomicAdd(&acc[p].copies, row.count);
+    StatsAcc *dst = use_smem ? sacc : acc;
+    atomicAdd(&dst[0].cap, cap); atomicAdd(&dst[0].free, fr); atomicAdd(&dst[0].count, 1); atomicAdd(&dst[0].copies, row.count);
+    atomicAdd(&dst[p].cap, cap); atomicAdd(&dst[p].free, fr); atomicAdd(&dst[p].count, 1); atomicAdd(&dst[p].copies, row.count);
     if (row.lru > 0 && row.lru < lmin) lmin = row.lru;  // ISST.addLru (ISST:57-61)
   }
   for (int o = 16; o > 0; o >>= 1) {
     long long t = __shfl_xor_sync(0xffffffffu, lmin, o);
     if (t < lmin) lmin = t;
   }
-  if ((threadIdx.x & 31) == 0) atomicMin(min_lru, lmin);
+  if ((threadIdx.x & 31) == 0 && lmin != 0x7fffffffffffffffLL) atomicMin(min_lru, lmin);
+  if (use_smem) {
+    __syncthreads();
+    for (int i = threadIdx.x; i <= n_parts; i += blockDim.x) {
+      const StatsAcc v = sacc[i];
+      if (v.count) { atomicAdd(&acc[i].cap, v.cap); atomicAdd(&acc[i].free, v.free); atomicAdd(&acc[i].count, v.count); atomicAdd(&acc[i].copies, v.copies); }
+    }
+  }
 }
 
 struct StatsResult {
@@ -44,18 +61,21 @@ static int32_t run_stats(mmp_fleet *f, const DeviceSnapshot &ds, StatsResult &re
   long long *d_min = reinterpret_cast<long long *>(c->d_trace.as<char>() + (size_t)(np + 1) * sizeof(StatsAcc));
   const long long init = 0x7fffffffffffffffLL;
   CK(cudaMemcpyAsync(d_min, &init, 8, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaEventRecord(c->e0, c->stream));
   if (h.n_ranks > 0) {
     int grid = std::min(f->sm_count, (h.n_ranks + 255) / 256);
     k_stats<<<grid, 256, 0, c->stream>>>(ds.rows.as<RankRow>(), ds.cap_col.as<int64_t>(), ds.part_of_rank.as<int32_t>(), h.n_ranks,
-                                        f->hs.cfg.min_space_units, c->d_trace.as<StatsAcc>(), d_min);
+                                        f->hs.cfg.min_space_units, c->d_trace.as<StatsAcc>(), d_min, np);
     f->launches++;
     CK(cudaGetLastError());
   }
+  CK(cudaEventRecord(c->e1, c->stream));
   std::vector<StatsAcc> acc(np + 1);
   long long mn = 0;
   CK(cudaMemcpyAsync(acc.data(), c->d_trace.p, (size_t)(np + 1) * sizeof(StatsAcc), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaMemcpyAsync(&mn, d_min, 8, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  { float ms = 0; if (cudaEventElapsedTime(&ms, c->e0, c->e1) == cudaSuccess) f->t_stats_ms = ms; }
   res.parts.resize(np + 1);
   for (int i = 0; i <= np; i++) {
     mmp_cluster_stats &s = res.parts[i];
@@ -86,11 +106,10 @@ static std::vector<int> partition_order(const StatsResult &res) {
 // Reaper: registry sweep (MM:6536-6590 candidate rule MM:6574-6577) + bounded most-recently-used selection
 // (MM:6675-6698) as  flag/compact -> bitonic sort by (lastUsed desc, model asc) -> first-of-run.
 // ---------------------------------------------------------------------------------------------------------------
-struct SortRec { unsigned long long k; unsigned long long v; };  // k: ~biased(lastUsed) so ascending k = descending time; v: model
-
+// key: ~biased(lastUsed), so that ascending keys = descending time.  One thread per model: 24 B read, 1 + 8 B written.
 __global__ void k_reaper_flag(const mmp_model_row *__restrict__ models, int n_models, const uint8_t *__restrict__ type_excluded,
                               int n_type_ids, const uint8_t *__restrict__ taken, long long global_lru, int need_cutoff,
-                              long long cutoff, SortRec *out, int *out_n) {
+                              long long cutoff, uint8_t *__restrict__ flag, unsigned long long *__restrict__ key) {
   int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= n_models) return;
   mmp_model_row r = models[m];
@@ -98,31 +117,13 @@ __global__ void k_reaper_flag(const mmp_model_row *__restrict__ models, int n_mo
   if (ok && taken && taken[m]) ok = false;                                                           // allCandidates.set(i, null)
   if (ok && r.type_id < n_type_ids && type_excluded[r.type_id]) ok = false;                          // MM:6681-6683
   if (ok && need_cutoff && !(r.last_used > cutoff)) ok = false;                                      // MM:6685-6687
-  if (ok) {
-    int pos = atomicAdd(out_n, 1);
-    unsigned long long biased = (unsigned long long)r.last_used ^ 0x8000000000000000ull;
-    out[pos] = SortRec{~biased, (unsigned long long)(unsigned)m};
-  }
-}
-__global__ void k_fill_pad(SortRec *a, int from, int to) {
-  int i = from + blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < to) a[i] = SortRec{~0ull, ~0ull};
-}
-__device__ __forceinline__ bool rec_less(const SortRec &a, const SortRec &b) { return a.k < b.k || (a.k == b.k && a.v < b.v); }
-__global__ void k_bitonic_step(SortRec *a, int n, int j, int k) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int l = i ^ j;
-  if (l > i) {
-    SortRec x = a[i], y = a[l];
-    bool up = (i & k) == 0;
-    if (up ? rec_less(y, x) : rec_less(x, y)) { a[i] = y; a[l] = x; }
-  }
+  flag[m] = ok ? 1 : 0;
+  key[m] = ~((unsigned long long)r.last_used ^ 0x8000000000000000ull);
 }
 // keep the first record of every equal-lastUsed run (TreeSet<ModelToLoad> drops equal keys, MM:6405-6408), in order
-__global__ void k_unique_mark(const SortRec *a, int n, int *flags) {
+__global__ void k_unique_mark(const unsigned long long *__restrict__ keys, int n, uint8_t *__restrict__ flags) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) flags[i] = (i == 0 || a[i].k != a[i - 1].k) ? 1 : 0;
+  if (i < n) flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
 }
 
 static int32_t reaper_impl(mmp_fleet *f, int32_t partition, int64_t now, uint8_t *taken, int32_t *out_models, int32_t cap) {
@@ -183,46 +184,68 @@ static int32_t reaper_impl(mmp_fleet *f, int32_t partition, int64_t now, uint8_t
   if (!c) { g_err = "cannot create CUDA stream"; return MMP_E_CUDA; }
   struct Rel { mmp_fleet *f; PlaceCtx *c; ~Rel() { release_ctx(f, c); } } rel{f, c};
   cudaStream_t s = c->stream;
-  int npad = 1;
-  while (npad < nm) npad <<= 1;
-  CK(c->d_in.ensure((size_t)npad * sizeof(SortRec)));
-  CK(c->d_out.ensure((size_t)npad * 4 + 16));
+  // Registry sweep -> candidates compacted in model order (stable) -> radix sort by ~lastUsed (stable: equal times keep the
+  // lower model index first) -> first of every equal-time run (N12) -> only the first `total_count` survivors leave the device.
+  // All on the device; the host applies the emission rule (MM:6711-6719) to at most total_count records.
+  const size_t n8 = (size_t)nm * 8, n4 = (size_t)nm * 4;
+  CK(c->d_in.ensure(2 * n8 + 64));        // keys[nm], keys_sel[nm]
+  CK(c->d_out.ensure(2 * n8 + 64));       // keys_sorted[nm], keys_uniq[nm]
+  CK(c->d_trace.ensure(4 * n4 + 64));     // idx_sel, idx_sorted, idx_uniq, (spare)
+  CK(c->d_cand.ensure((size_t)nm + 64));  // flags
   CK(c->d_extra.ensure(excl.size() + 16));
   CK(c->d_fresh.ensure((size_t)nm + 16));
+  CK(c->d_n_open.ensure(16));
+  unsigned long long *keys = c->d_in.as<unsigned long long>(), *keys_sel = keys + nm;
+  unsigned long long *keys_sorted = c->d_out.as<unsigned long long>(), *keys_uniq = keys_sorted + nm;
+  int32_t *idx_sel = c->d_trace.as<int32_t>(), *idx_sorted = idx_sel + nm, *idx_uniq = idx_sorted + nm;
+  uint8_t *flags = c->d_cand.as<uint8_t>();
+  int *d_n = c->d_n_open.as<int>();
   CK(cudaMemcpyAsync(c->d_extra.p, excl.data(), excl.size(), cudaMemcpyHostToDevice, s));
   if (taken) CK(cudaMemcpyAsync(c->d_fresh.p, taken, (size_t)nm, cudaMemcpyHostToDevice, s));
-  int *d_n = c->d_out.as<int>() + npad;
-  CK(cudaMemsetAsync(d_n, 0, 4, s));
+  CK(cudaEventRecord(c->e0, s));
   k_reaper_flag<<<(nm + 255) / 256, 256, 0, s>>>(ds.models.as<mmp_model_row>(), nm, c->d_extra.as<uint8_t>(), (int)excl.size(),
-                                               taken ? c->d_fresh.as<uint8_t>() : nullptr, global_lru, free_count > 0 ? 0 : 1, cutoff,
-                                               c->d_in.as<SortRec>(), d_n);
+                                               taken ? c->d_fresh.as<uint8_t>() : nullptr, global_lru, free_count > 0 ? 0 : 1, cutoff, flags, keys);
   f->launches++;
   CK(cudaGetLastError());
+  thrust::counting_iterator<int32_t> iota(0);
+  size_t t1 = 0, t2 = 0, t3 = 0;
+  CK(cub::DeviceSelect::Flagged(nullptr, t1, keys, flags, keys_sel, d_n, nm, s));
+  CK(cub::DeviceSelect::Flagged(nullptr, t2, iota, flags, idx_sel, d_n, nm, s));
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, t3, keys_sel, keys_sorted, idx_sel, idx_sorted, nm, 0, 64, s));
+  CK(c->d_cub.ensure(std::max(t1, std::max(t2, t3)) + 64));
+  CK(cub::DeviceSelect::Flagged(c->d_cub.p, t1, keys, flags, keys_sel, d_n, nm, s));
+  CK(cub::DeviceSelect::Flagged(c->d_cub.p, t2, iota, flags, idx_sel, d_n, nm, s));
   int ncand = 0;
   CK(cudaMemcpyAsync(&ncand, d_n, 4, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  f->launches += 2;
   if (ncand == 0) return 0;
-  int n2 = 1;
-  while (n2 < ncand) n2 <<= 1;
-  if (n2 > ncand) { k_fill_pad<<<(n2 - ncand + 255) / 256, 256, 0, s>>>(c->d_in.as<SortRec>(), ncand, n2); f->launches++; }
-  for (int k = 2; k <= n2; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) { k_bitonic_step<<<(n2 + 255) / 256, 256, 0, s>>>(c->d_in.as<SortRec>(), n2, j, k); f->launches++; }
+  CK(cub::DeviceRadixSort::SortPairs(c->d_cub.p, t3, keys_sel, keys_sorted, idx_sel, idx_sorted, ncand, 0, 64, s));
+  k_unique_mark<<<(ncand + 255) / 256, 256, 0, s>>>(keys_sorted, ncand, flags);
+  CK(cub::DeviceSelect::Flagged(c->d_cub.p, t1, keys_sorted, flags, keys_uniq, d_n, ncand, s));
+  CK(cub::DeviceSelect::Flagged(c->d_cub.p, t2, idx_sorted, flags, idx_uniq, d_n, ncand, s));
+  f->launches += 4;
   CK(cudaGetLastError());
-  // distinct lastUsed values, first (lowest model index) of each: small enough to finish on the host once sorted
-  std::vector<SortRec> sorted((size_t)ncand);
-  CK(cudaMemcpyAsync(sorted.data(), c->d_in.p, (size_t)ncand * sizeof(SortRec), cudaMemcpyDeviceToHost, s));
+  CK(cudaEventRecord(c->e1, s));
+  int nuniq = 0;
+  CK(cudaMemcpyAsync(&nuniq, d_n, 4, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  { float ms = 0; if (cudaEventElapsedTime(&ms, c->e0, c->e1) == cudaSuccess) f->t_reaper_ms = ms; }
+  const int take = std::min(nuniq, total_count);
+  std::vector<unsigned long long> hk((size_t)take);
+  std::vector<int32_t> hm((size_t)take);
+  if (take) {
+    CK(cudaMemcpyAsync(hk.data(), keys_uniq, (size_t)take * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(hm.data(), idx_uniq, (size_t)take * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
   int64_t emitted = 0;
-  int32_t kept = 0, free_left = free_count;
-  unsigned long long prev_k = 0;
-  for (int i = 0; i < ncand && kept < total_count; i++) {
-    if (i > 0 && sorted[i].k == prev_k) continue;  // N12
-    prev_k = sorted[i].k;
-    kept++;
-    int64_t ts = (int64_t)((~sorted[i].k) ^ 0x8000000000000000ull);
+  int32_t free_left = free_count;
+  for (int i = 0; i < take; i++) {
+    const int64_t ts = (int64_t)((~hk[i]) ^ 0x8000000000000000ull);
     if (free_left > 0) free_left--;          // MM:6713-6714
     else if (ts < cutoff) break;             // MM:6715-6717
-    int32_t m = (int32_t)sorted[i].v;
+    const int32_t m = hm[i];
     if (taken) taken[m] = 1;
     if (emitted < cap) out_models[emitted] = m;
     emitted++;
@@ -571,14 +594,17 @@ static int32_t lru_apply_impl(mmp_fleet *f, const mmp_lru_event *ev, int32_t n, 
   hk.status = c->d_trace.as<int>() + 4;
   const int warps_per_block = 4;
   const int grid = (f->lru_n + warps_per_block - 1) / warps_per_block;
+  CK(cudaEventRecord(c->e0, s));
   k_lru_events<<<grid, warps_per_block * 32, 0, s>>>(lru_view(f), c->d_in.as<LruEv>(), c->d_extra.as<int>(), c->d_fresh.as<int>(), now_ms, 0, hk,
                                                     c->d_out.as<EvictRec>(), cap, c->d_trace.as<int>(), c->d_trace.as<int>() + 1);
+  CK(cudaEventRecord(c->e1, s));
   f->launches++;
   CK(cudaGetLastError());
   int hdr[2] = {0, 0};
   CK(cudaMemcpyAsync(hdr, c->d_trace.p, 8, cudaMemcpyDeviceToHost, s));
   if (status) CK(cudaMemcpyAsync(status, c->d_trace.as<char>() + 16, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  { float ms = 0; if (cudaEventElapsedTime(&ms, c->e0, c->e1) == cudaSuccess) f->t_lru_ms = ms; }
   if (hdr[1]) { g_err = "LRU slot capacity exceeded for some instance (raise slots_per_instance)"; return MMP_E_NOMEM; }
   int got = std::min(hdr[0], cap);
   std::vector<EvictRec> tmp((size_t)got);
