@@ -339,6 +339,51 @@ int32_t mmp_churn_step(mmp_fleet *, const mmp_churn_event *ev, int32_t n, int64_
                        int32_t *n_evict, mmp_instance_row *rows_out, mmp_churn_report *report);
 /* registry state of one model as the device holds it: row + the 4 inline instance indices (first copy_count = loaded) */
 int32_t mmp_churn_model(mmp_fleet *, int32_t model, mmp_model_row *row, int32_t *instances4);
+/* ---- registry-side batch scans ---- */
+/* MR.instanceIds / failedIn VALUES (load-start / failure times of the model's inline edges, same order as the ids given to
+ * mmp_model_upsert) and MR.lastUnloadTime ("lul").  mmp_model_upsert_json takes them from the record.  0 = unknown. */
+int32_t mmp_model_times(mmp_fleet *, int32_t model, const int64_t *edge_ts, int32_t n, int64_t last_unload_time);
+/* One cache entry of one pod, as its rate-tracking / janitor tasks see it (CacheEntry counters are pod-local): */
+typedef struct {
+  int32_t instance, model;
+  int64_t count;        /* ce.getAndResetIntervalCount(): invocations since the last run (MM:5689) */
+  int64_t last_used;    /* the entry's lastUsed in the pod's cache */
+  int64_t last_heavy;   /* ce.getLastHeavyTime() */
+  int32_t i1, i2;       /* ce.earlierUseIteration / lastUsedIteration (MM:1647-1648) */
+  int32_t weight, flags;
+} mmp_scale_in;
+typedef struct {
+  int64_t now, last_check_time;                     /* timeDelta = now - lastCheckTime (MM:5641-5642) */
+  int32_t iteration, scale_up_rpm_threshold;        /* iterationCounter, scaleUpRpmThreshold */
+  int32_t second_copy_min_age_iters, second_copy_max_age_iters;  /* MM:5621-5622 */
+  int64_t second_copy_lru_threshold_ms;             /* MM:5628 */
+  int64_t rate_check_interval_ms;                   /* RATE_CHECK_INTERVAL_MS MM:238 */
+  int64_t assume_completed_ms;                      /* loadingTimeStats(type).assumeCompletedAfterMillis() (MM:5765-5766) */
+  int64_t second_copy_remove_max_age_ms;            /* SECOND_COPY_REMOVE_MAX_AGE_MS MM:257 */
+  int32_t can_remove, reserved;                     /* the janitor's canRemove (MM:6197) */
+} mmp_scale_params;
+typedef struct {
+  int32_t action;          /* 0 nothing, 1 add a second copy (regular-usage trigger MM:5726-5758), 2 scale up by copies_to_load
+                              (MM:5760-5795), -1 the model has more registered instances than the device list holds: host path */
+  int32_t copies_to_load;
+  int64_t load_last_used;  /* lastUsed for the triggered loads: lastCheckTime (second copy) or now + 20 s (scale-up, MM:5675) */
+  int32_t rpm, i1, i2;     /* measured rate; the updated usage iterations */
+  int32_t set_heavy;       /* rpm above 3/4 of the threshold: ce.setLastHeavyTime(now) (MM:5712) */
+  int32_t remove;          /* removeModelCopies (MM:6197-6335): this pod should drop its copy */
+} mmp_scale_out;
+/* rateTrackingTask's loop body (MM:5684-5806, exclude set MM:5835-5856, loadedSince MM:5858-5870) and the janitor's
+ * removeModelCopies (MM:6197-6310, who-drops-the-copy by PLACEMENT_ORDER MM:6314-6335) for a batch of cache entries,
+ * against the committed snapshot (instance table, type-set stats) and the registry (copies, failures, load times). */
+int32_t mmp_scale_eval(mmp_fleet *, const mmp_scale_in *in, int32_t n, const mmp_scale_params *params, mmp_scale_out *out);
+/* The reaper's prune pass (pruneModelRegistry MM:6524-6609, pruneMissingInstances MM:6752-6784) over the whole registry in one
+ * sweep: registrations on instances that are not in the instance table, older than assume_gone_ms and missing for longer than
+ * assume_gone_ms (ASSUME_INSTANCE_GONE_AFTER_MS, MM:270).  missing_since (max_instances entries, in/out) is the reaper's
+ * `missings` map by instance index, 0 = absent.  Writes the models with entries to prune and, per model, the bit mask of the
+ * pruned inline edges; returns how many (the registry itself is updated by the caller through mmp_model_upsert, as the
+ * reference does through a conditional KV write). */
+int32_t mmp_registry_prune(mmp_fleet *, int32_t self, int64_t now_ms, int64_t assume_gone_ms, int64_t *missing_since, int32_t *out_models,
+                           uint8_t *out_masks, int32_t cap);
+
 /* tuning / measurement knobs, same meaning as the MMP_* environment variables read at mmp_fleet_create:
  *   "one_mode"        how a batch of <= 32 decisions is launched: 0 the streaming kernel (k_place_lanes), 1 the latency kernel
  *                     k_place_small as a stream launch, 2 (default) k_place_small as a replayed CUDA graph

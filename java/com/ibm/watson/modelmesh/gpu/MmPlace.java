@@ -37,6 +37,11 @@ final class MmPlace {
     static native int modelsBulk(long h, int first, int n, ByteBuffer rows, ByteBuffer edgeOff, ByteBuffer edgeInst);
     static native int commit(long h);
     static native double commitInfo(long h, int[] pathOut);
+    // registry-side batch scans: rate-tracking / janitor arithmetic (MM:5640-5806, 6197-6335), reaper prune pass (MM:6524-6609)
+    static native int modelTimes(long h, int model, ByteBuffer edgeTimes, int n, long lastUnloadTime);
+    static native int scaleEval(long h, ByteBuffer in, int n, ByteBuffer params, ByteBuffer out);
+    static native int registryPrune(long h, int self, long nowMs, long assumeGoneMs, ByteBuffer missingSince, ByteBuffer outModels,
+                                    ByteBuffer outMasks, int cap);
     static native int tune(long h, String key, long value);
     static native double lastTiming(long h, String key);
     // plug point 1: placement (CacheMissForwardingLB.getNext MM:4776-5004)

@@ -114,6 +114,22 @@ jint FN(modelsBulk)(JNIEnv *env, jclass c, jlong h, jint first, jint n, jobject 
   return mmp_models_bulk(H(h), first, n, (const mmp_model_row *)BUF(rows), (const int64_t *)BUF(edgeOff), (const int32_t *)BUF(edgeInst));
 }
 jint FN(commit)(JNIEnv *env, jclass c, jlong h) { (void)env; (void)c; return mmp_fleet_commit(H(h)); }
+/* ts: int64[n] direct buffer of the edges' load-start / failure times, same order as modelUpsert's ids */
+jint FN(modelTimes)(JNIEnv *env, jclass c, jlong h, jint model, jobject ts, jint n, jlong lastUnloadTime) {
+  (void)c;
+  return mmp_model_times(H(h), model, (const int64_t *)BUF(ts), n, lastUnloadTime);
+}
+/* in: n x mmp_scale_in (48 B), params: one mmp_scale_params (72 B), out: n x mmp_scale_out (40 B) -- direct buffers */
+jint FN(scaleEval)(JNIEnv *env, jclass c, jlong h, jobject in, jint n, jobject params, jobject out) {
+  (void)c;
+  return mmp_scale_eval(H(h), (const mmp_scale_in *)BUF(in), n, (const mmp_scale_params *)BUF(params), (mmp_scale_out *)BUF(out));
+}
+/* missingSince: int64[max_instances] (in/out), outModels: int32[cap], outMasks: byte[cap] -- direct buffers */
+jint FN(registryPrune)(JNIEnv *env, jclass c, jlong h, jint self, jlong nowMs, jlong assumeGoneMs, jobject missingSince, jobject outModels,
+                       jobject outMasks, jint cap) {
+  (void)c;
+  return mmp_registry_prune(H(h), self, nowMs, assumeGoneMs, (int64_t *)BUF(missingSince), (int32_t *)BUF(outModels), (uint8_t *)BUF(outMasks), cap);
+}
 jint FN(tune)(JNIEnv *env, jclass c, jlong h, jstring key, jlong value) {
   const char *ck = utf(env, key);
   jint rc = mmp_tune(H(h), ck, value);

@@ -45,6 +45,15 @@ CHURN_EVICTION = np.dtype([("instance", "<i4"), ("model", "<i4"), ("last_used", 
                            ("reload", "<i4")], align=True)
 assert LRU_EVENT.itemsize == 24 and EVICTION.itemsize == 24
 assert CHURN_EVENT.itemsize == 24 and CHURN_DECISION.itemsize == 24 and CHURN_EVICTION.itemsize == 32
+SCALE_IN = np.dtype([("instance", "<i4"), ("model", "<i4"), ("count", "<i8"), ("last_used", "<i8"), ("last_heavy", "<i8"), ("i1", "<i4"),
+                     ("i2", "<i4"), ("weight", "<i4"), ("flags", "<i4")], align=True)
+SCALE_PARAMS = np.dtype([("now", "<i8"), ("last_check_time", "<i8"), ("iteration", "<i4"), ("scale_up_rpm_threshold", "<i4"),
+                         ("second_copy_min_age_iters", "<i4"), ("second_copy_max_age_iters", "<i4"), ("second_copy_lru_threshold_ms", "<i8"),
+                         ("rate_check_interval_ms", "<i8"), ("assume_completed_ms", "<i8"), ("second_copy_remove_max_age_ms", "<i8"),
+                         ("can_remove", "<i4"), ("reserved", "<i4")], align=True)
+SCALE_OUT = np.dtype([("action", "<i4"), ("copies_to_load", "<i4"), ("load_last_used", "<i8"), ("rpm", "<i4"), ("i1", "<i4"), ("i2", "<i4"),
+                      ("set_heavy", "<i4"), ("remove", "<i4")], align=True)
+assert SCALE_IN.itemsize == 48 and SCALE_PARAMS.itemsize == 72 and SCALE_OUT.itemsize == 40
 LRU_LOAD = 5
 CHURN_REQUEST, CHURN_REMOVE = 0, 1
 
@@ -127,6 +136,9 @@ SYMBOLS = [
     ("mmp_churn_step", _I32, [_P, _P, _I32, _I64, _I64, _U64, _P, _I32, C.POINTER(_I32), _P, _I32, C.POINTER(_I32), _P, C.c_void_p]),
     ("mmp_churn_model", _I32, [_P, _I32, _P, _P]),
     ("mmp_commit_info", _I32, [_P, C.POINTER(_I32), C.POINTER(C.c_double)]),
+    ("mmp_model_times", _I32, [_P, _I32, _P, _I32, _I64]),
+    ("mmp_scale_eval", _I32, [_P, _P, _I32, _P, _P]),
+    ("mmp_registry_prune", _I32, [_P, _I32, _I64, _I64, _P, _P, _P, _I32]),
     ("mmp_tune", _I32, [_P, C.c_char_p, _I64]),
     ("mmp_last_timing", _I32, [_P, C.c_char_p, C.POINTER(C.c_double)]),
     ("mmp_batcher_create", _I32, [_P, _I32, _I32, _U64, C.POINTER(_P)]),

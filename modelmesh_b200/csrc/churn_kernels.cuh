@@ -259,6 +259,7 @@ __global__ void k_churn_type_ok(const StatsAcc *__restrict__ acc, const int *__r
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 static int32_t commit_locked(mmp_fleet *f);  // mmplace.cu: mmp_fleet_commit without taking the ingest lock
+static inline int32_t lv_n_types(mmp_fleet *f) { return f->live.n_type_ids; }
 
 static int32_t sync_host_from_device(mmp_fleet *f) {
   const int32_t nm = f->hs.n_models_used;
@@ -267,33 +268,6 @@ static int32_t sync_host_from_device(mmp_fleet *f) {
     CK(cudaMemcpy(f->hs.edge_inl.data(), f->live.edges.p, (size_t)nm * HostState::EDGE_INL * 4, cudaMemcpyDeviceToHost));
   }
   f->device_ahead = false;
-  return MMP_OK;
-}
-
-// type id -> partitions whose instances may host the type (typeSetStats MM:1432-1438; TCM:230-233, 700-716)
-static int32_t churn_type_tables(mmp_fleet *f, cudaStream_t st) {
-  ChurnState &cs = f->churn;
-  const HostSnapshot &t = f->live.tmpl;
-  const int32_t nt = (int32_t)t.type_slot.size();
-  std::vector<int> off((size_t)nt + 1, 0), parts;
-  for (int32_t ty = 0; ty < nt; ty++) {
-    off[ty] = (int)parts.size();
-    if (!t.tc_enabled || ty == 0) continue;  // no type constraints / an unconfigured name: the cluster's stats
-    const std::string &name = f->hs.type_names[ty];
-    auto it = f->hs.tc_config.find(name);
-    if (it == f->hs.tc_config.end() || it->second.required.empty()) continue;  // hasStats only with required labels (TCM:706-716)
-    const size_t before = parts.size();
-    for (size_t p = 0; p < t.part_types.size(); p++)
-      if (!std::binary_search(t.part_types[p].begin(), t.part_types[p].end(), name)) parts.push_back((int)p);
-    if (parts.size() == before) parts.push_back(-1);  // a subset without instances: empty stats
-  }
-  off[nt] = (int)parts.size();
-  if (parts.empty()) parts.push_back(-1);
-  CK(upload_vec(cs.type_part_off, off, st)); CK(upload_vec(cs.type_parts, parts, st));
-  CK(cs.type_ok.ensure((size_t)std::max(nt, 1)));
-  CK(cudaStreamSynchronize(st));
-  cs.n_type_ids = nt;
-  cs.tmpl_epoch = f->structural_epoch;
   return MMP_OK;
 }
 
@@ -327,7 +301,6 @@ int32_t mmp_churn_init(mmp_fleet *f, const mmp_churn_config *cfg) {
   CK(cudaMemsetAsync(cs.used_t.p, 0, (size_t)NM * 8, f->commit_stream));
   CK(cudaStreamSynchronize(f->commit_stream));
   cs.n_carry = 0;
-  cs.tmpl_epoch = -1;
   cs.on = true;
   return MMP_OK;
 }
@@ -386,7 +359,7 @@ int32_t mmp_churn_step(mmp_fleet *f, const mmp_churn_event *ev, int32_t n, int64
     g_err = "uncommitted ingest: call mmp_fleet_commit before mmp_churn_step"; return MMP_E_STATE;
   }
   cudaStream_t st = f->commit_stream;
-  if (cs.tmpl_epoch != f->structural_epoch) { rc = churn_type_tables(f, st); if (rc < 0) return rc; }
+  CK(cs.type_ok.ensure((size_t)std::max(lv_n_types(f), 1)));
   const DeviceSnapshot &ds = f->snaps[f->cur];  // (placement calls of other threads share it; this thread is the only writer)
   LiveState &lv = f->live;
   const int32_t NI = f->hs.cfg.max_instances, NM = f->hs.n_models_used;
@@ -422,8 +395,8 @@ int32_t mmp_churn_step(mmp_fleet *f, const mmp_churn_event *ev, int32_t n, int64
                                                                                   f->hs.cfg.min_space_units, cs.stats_acc.as<StatsAcc>(), d_min, np);
       f->launches++;
     }
-    k_churn_type_ok<<<(cs.n_type_ids + 127) / 128, 128, 0, st>>>(cs.stats_acc.as<StatsAcc>(), cs.type_part_off.as<int>(), cs.type_parts.as<int>(),
-                                                                cs.n_type_ids, cs.type_ok.as<unsigned char>());
+    k_churn_type_ok<<<(lv.n_type_ids + 127) / 128, 128, 0, st>>>(cs.stats_acc.as<StatsAcc>(), lv.type_part_off.as<int>(), lv.type_parts.as<int>(),
+                                                                lv.n_type_ids, cs.type_ok.as<unsigned char>());
     f->launches++;
     CK(cudaGetLastError());
   }
@@ -478,7 +451,7 @@ int32_t mmp_churn_step(mmp_fleet *f, const mmp_churn_event *ev, int32_t n, int64
     hk.min_space = f->hs.cfg.min_space_units; hk.min_churn_age = f->hs.cfg.min_churn_age_ms; hk.load_timeout = cs.load_timeout_ms;
     hk.status = cs.status.as<int>(); hk.dec_target = cs.dec_target.as<int>(); hk.dec_of_model = cs.dec_of_model.as<int>();
     hk.edges = lv.edges.as<int4>(); hk.models = lmodels; hk.rm_mask = cs.rm_mask.as<unsigned>();
-    hk.type_ok = cs.type_ok.as<unsigned char>(); hk.n_type_ids = cs.n_type_ids;
+    hk.type_ok = cs.type_ok.as<unsigned char>(); hk.n_type_ids = lv.n_type_ids;
     hk.next = cs.next_carry.as<Follow>(); hk.n_next = cs.counters.as<int>() + 6; hk.next_cap = ecap;
     hk.force_publish = cs.force_publish.as<unsigned char>();
     k_lru_events<<<(f->lru_n + 3) / 4, 128, 0, st>>>(lru_view(f), cs.lev.as<LruEv>(), cs.vals2.as<int>(), cs.off.as<int>(), now0, 1, hk,

@@ -6,7 +6,7 @@
 // (HostState::build_snapshot) and uploaded, together with the DEVICE-RESIDENT LIVE TABLES every later commit works from:
 //   inst_rows [NI] mmp_instance_row        the published numeric columns (IR:37-73), by instance index
 //   inst_tie  [NI] uint4                   dense ranks of id / location / zone / labels (tie-break chain MM:4697-4700)
-//   inst_meta [NI] int2                    {partition id, bit0 live | bit1 likely-replaced replicaset member}
+//   inst_meta [NI] int2                    {partition id, bit0 live | bit1 likely-replaced replicaset member | bit2 in the instance table}
 //   cand_idx / pref_idx [n_slots][NIW]     type-constraint masks over instance INDEX (allowed ∧ active / preferred)
 //   edges [NM][4], models [NM]             the registry: loaded ∪ failed instance indices (first copy_count = loaded) + rows
 // Every other commit -- numeric instance updates (the common KV event), model-record changes, the closed loop of
@@ -22,6 +22,10 @@
 struct LiveState {
   DevBuf inst_rows, inst_tie, inst_meta, cand_idx, pref_idx, edges, models, ovf_pairs, keys, rs_words, flags, scratch_idx, scratch_rows,
       scratch_edges;
+  DevBuf edge_ts, model_lul;                  // MR.instanceIds / failedIn values and MR.lastUnloadTime (registry_kernels.cuh), when given
+  bool have_times = false;
+  DevBuf type_part_off, type_parts;           // type id -> partitions whose instances may host the type (typeSetStats MM:1432-1438)
+  int32_t n_type_ids = 0;
   int32_t n_ovf = 0, niw = 0;
   bool valid = false;           // a structural commit has populated the tables
   mmp::HostSnapshot tmpl;       // the last structural snapshot: everything that does not depend on the numeric columns
@@ -31,12 +35,11 @@ struct LiveState {
 struct ChurnState {
   bool on = false;
   int64_t load_timeout_ms = 0;
-  DevBuf last_published, first_ev, dec_of_model, rm_mask, add_inst, used_t, force_publish, type_ok, type_part_off, type_parts, stats_acc;
+  DevBuf last_published, first_ev, dec_of_model, rm_mask, add_inst, used_t, force_publish, type_ok, stats_acc;
   DevBuf carry, next_carry, counters;
   DevBuf ev, is_dec, dec_pos, dec_in, dec_out, dec_meta, dec_target, extra, status, lev, keys, vals, keys2, vals2, cub_tmp, off, evict, fkeys,
       fvals, rows_changed;
-  int32_t n_carry = 0, n_type_ids = 0;
-  int64_t tmpl_epoch = -1;
+  int32_t n_carry = 0;
   // last step's phase timings (ms, CUDA events on the step's stream)
   float t_classify = 0, t_place = 0, t_route = 0, t_apply = 0, t_registry = 0, t_commit = 0, t_total = 0;
   int32_t last_lru_events = 0;

@@ -130,6 +130,11 @@ class HostState {
   static constexpr int EDGE_INL = 4;
   std::vector<mmp_model_row> models;
   std::vector<int32_t> edge_inl;
+  // MR.instanceIds / failedIn VALUES (load-start / failure time of each inline edge, MR:69,73) and MR.lastUnloadTime ("lul",
+  // MR:113): read by the scale-up / scale-down arithmetic (loadedSince MM:5858-5870, MM:6265-6272) and the registry prune sweep
+  // (MM:6752-6784).  0 = unknown.  Allocated on first use.
+  std::vector<int64_t> edge_ts, model_lul;
+  bool times_dirty = false;
   std::unordered_map<int32_t, std::vector<int32_t>> edge_ovf;
   int32_t n_models_used = 0;
   std::string err;
@@ -137,6 +142,7 @@ class HostState {
   // the ids are kept and resolved against this table at every commit, so the two KV listeners may deliver in any order.
   std::unordered_map<JStr, int32_t> id_index;
   std::unordered_map<int32_t, std::vector<JStr>> json_ids;  // model -> loaded ∪ failed ids as the record named them
+  std::unordered_map<int32_t, std::vector<int64_t>> json_ts; // their map values (load-start / failure times), same order
   uint64_t inst_gen = 1, json_resolved_gen = 0;             // id table generation / the one the JSON models were last resolved against
   // ---- what changed since the last commit (mmp_fleet_commit picks its path from these) ----
   // structural: the set of live instances, their strings / labels / siMap membership, the type configuration or the
@@ -219,6 +225,14 @@ class HostState {
     inst[idx] = HostInstance();
     return MMP_OK;
   }
+  int32_t set_model_times(int32_t m, const int64_t *ts, int32_t n, int64_t last_unload_time) {
+    if (m < 0 || m >= cfg.max_models || n < 0 || (n > 0 && !ts)) { err = "bad model index or null argument"; return MMP_E_ARG; }
+    if (edge_ts.empty()) { edge_ts.assign((size_t)cfg.max_models * EDGE_INL, 0); model_lul.assign((size_t)cfg.max_models, 0); }
+    for (int i = 0; i < EDGE_INL; i++) edge_ts[(size_t)m * EDGE_INL + i] = i < n ? ts[i] : 0;
+    model_lul[m] = last_unload_time;
+    times_dirty = true;
+    return MMP_OK;
+  }
   int32_t set_replicasets(const char *const *prefixes, int32_t n) {
     if (n < 0 || (n > 0 && !prefixes)) { err = "bad replicaset list"; return MMP_E_ARG; }
     replaced_rs.clear();
@@ -228,7 +242,7 @@ class HostState {
   }
   int32_t set_model(int32_t m, const mmp_model_row *row, const int32_t *ids, int32_t n_ids, bool from_json = false) {
     if (m < 0 || m >= cfg.max_models || !row || n_ids < 0 || (n_ids > 0 && !ids)) { err = "bad model index or null argument"; return MMP_E_ARG; }
-    if (!from_json && !json_ids.empty()) json_ids.erase(m);  // an index-based upsert replaces a record held by id
+    if (!from_json && !json_ids.empty()) { json_ids.erase(m); json_ts.erase(m); }  // an index-based upsert replaces a record held by id
     if (row->type_id >= type_names.size()) { err = "unknown type_id (use mmp_type_id)"; return MMP_E_ARG; }
     for (int32_t i = 0; i < n_ids; i++)
       if (ids[i] < 0 || ids[i] >= cfg.max_instances) { err = "model instance id out of range"; return MMP_E_ARG; }
@@ -250,14 +264,20 @@ class HostState {
   void resolve_json_models() {
     if (json_ids.empty() || json_resolved_gen == inst_gen) return;
     std::vector<int32_t> ids;
+    std::vector<int64_t> ts;
     for (auto &kv : json_ids) {
-      ids.clear();
-      for (const JStr &s : kv.second) {
-        auto it = id_index.find(s);
-        if (it != id_index.end() && std::find(ids.begin(), ids.end(), it->second) == ids.end()) ids.push_back(it->second);
+      ids.clear(); ts.clear();
+      auto tv = json_ts.find(kv.first);
+      for (size_t q = 0; q < kv.second.size(); q++) {
+        auto it = id_index.find(kv.second[q]);
+        if (it != id_index.end() && std::find(ids.begin(), ids.end(), it->second) == ids.end()) {
+          ids.push_back(it->second);
+          ts.push_back(tv != json_ts.end() && q < tv->second.size() ? tv->second[q] : 0);
+        }
       }
       const mmp_model_row row = models[kv.first];
       set_model(kv.first, &row, ids.data(), (int32_t)ids.size(), true);
+      if (!edge_ts.empty()) set_model_times(kv.first, ts.data(), (int32_t)std::min<size_t>(ts.size(), EDGE_INL), model_lul[kv.first]);
     }
     json_resolved_gen = inst_gen;
   }
@@ -757,14 +777,17 @@ class RecordJson : public TcJson {
   }
   // ModelRecord wire format (MR:61-114): type, instanceIds {iid: loadStart}, failedIn {iid: failTime}, lu; the rest is ignored
   bool model(std::string &type, std::vector<std::string> &loaded, std::vector<std::string> &failed, int64_t &last_used,
-             std::string &err) {
+             std::string &err, std::vector<int64_t> *loaded_ts = nullptr, std::vector<int64_t> *failed_ts = nullptr,
+             int64_t *last_unload = nullptr) {
     type.clear(); loaded.clear(); failed.clear(); last_used = 0;
+    if (last_unload) *last_unload = 0;
     return object([&](const std::string &k) -> bool {
       bool has;
       if (k == "type") return nullable_string(type, has);
-      if (k == "instanceIds") return key_list(loaded);
-      if (k == "failedIn") return key_list(failed);
+      if (k == "instanceIds") return key_list(loaded, loaded_ts);
+      if (k == "failedIn") return key_list(failed, failed_ts);
       if (k == "lu") return integer(last_used);
+      if (k == "lul" && last_unload) return integer(*last_unload);
       return skip();
     }, err);
   }
@@ -829,7 +852,7 @@ class RecordJson : public TcJson {
       return eat(']');
     }
   }
-  bool key_list(std::vector<std::string> &keys) {  // {"iid": 123, ...} -> the keys
+  bool key_list(std::vector<std::string> &keys, std::vector<int64_t> *vals = nullptr) {  // {"iid": 123, ...} -> the keys (and values)
     ws();
     if (!strncmp(p_, "null", 4)) { p_ += 4; return true; }
     if (!eat('{')) return false;
@@ -841,7 +864,11 @@ class RecordJson : public TcJson {
       if (!str(k)) return false;
       ws();
       if (!eat(':')) return false;
-      if (!skip_value()) return false;
+      ws();
+      int64_t v = 0;
+      const char *save = p_;
+      if (!(vals && integer(v))) { p_ = save; v = 0; if (!skip_value()) return false; }
+      if (vals) vals->push_back(v);
       keys.push_back(k);
       ws();
       if (eat(',')) continue;
@@ -868,19 +895,28 @@ inline int32_t HostState::set_model_json(int32_t m, const char *json, int32_t si
   std::string type, e;
   std::vector<std::string> loaded, failed;
   int64_t lu = 0;
-  if (!RecordJson(json).model(type, loaded, failed, lu, e)) { err = "model record json: " + e; return MMP_E_ARG; }
+  std::vector<int64_t> lts, fts;
+  int64_t lul = 0;
+  if (!RecordJson(json).model(type, loaded, failed, lu, e, &lts, &fts, &lul)) { err = "model record json: " + e; return MMP_E_ARG; }
   // the ids are kept as the record names them and resolved against the id table now AND at every commit after the table
   // changed (resolve_json_models), so a model record may arrive before the records of the instances it names
   std::vector<JStr> raw;
   std::vector<int32_t> ids;
-  for (const auto *lst : {&loaded, &failed})
-    for (const auto &s8 : *lst) {
-      JStr j = utf8_to_utf16(s8.c_str());
-      if (std::find(raw.begin(), raw.end(), j) != raw.end()) continue;
-      auto it = id_index.find(j);
-      if (it != id_index.end() && std::find(ids.begin(), ids.end(), it->second) == ids.end()) ids.push_back(it->second);
-      raw.push_back(std::move(j));
+  std::vector<int64_t> ts, raw_ts;
+  {
+    size_t li = 0;
+    for (const auto *lst : {&loaded, &failed}) {
+      const std::vector<int64_t> &tv = lst == &loaded ? lts : fts;
+      for (size_t q = 0; q < lst->size(); q++, li++) {
+        JStr j = utf8_to_utf16((*lst)[q].c_str());
+        if (std::find(raw.begin(), raw.end(), j) != raw.end()) continue;
+        auto it = id_index.find(j);
+        if (it != id_index.end() && std::find(ids.begin(), ids.end(), it->second) == ids.end()) { ids.push_back(it->second); ts.push_back(q < tv.size() ? tv[q] : 0); }
+        raw.push_back(std::move(j));
+        raw_ts.push_back(q < tv.size() ? tv[q] : 0);
+      }
     }
+  }
   mmp_model_row row{};
   row.last_used = lu;
   row.size_units = size_units;
@@ -891,7 +927,12 @@ inline int32_t HostState::set_model_json(int32_t m, const char *json, int32_t si
   row.copy_count = (uint8_t)std::min<size_t>(255, loaded.size());
   row.fail_count = (uint8_t)std::min<size_t>(255, failed.size());
   const int32_t rc = set_model(m, &row, ids.data(), (int32_t)ids.size(), true);
-  if (rc == MMP_OK) { if (raw.empty()) json_ids.erase(m); else json_ids[m] = std::move(raw); }
+  if (rc == MMP_OK) {
+    if (raw.empty()) { json_ids.erase(m); json_ts.erase(m); } else { json_ids[m] = std::move(raw); json_ts[m] = std::move(raw_ts); }
+    bool any_time = lul != 0;
+    for (int64_t t : ts) any_time = any_time || t != 0;
+    if (any_time || !edge_ts.empty()) set_model_times(m, ts.data(), (int32_t)std::min<size_t>(ts.size(), EDGE_INL), lul);
+  }
   return rc;
 }
 

@@ -319,8 +319,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_place(const SnapshotView s
 // The stages keep ~NS x 41 KB per SM in flight from HBM independently of how many warps are computing, and the
 // per-decision instruction cost is ~85 warp instructions instead of ~450 for a cooperative tile (ncu, C3 sweep).
 // ---------------------------------------------------------------------------------------------------------------
-static constexpr int LANE_WIN = 14;     // row words copied out of the landing stage per decision: the first LANE_WIN words of the
+static constexpr int LANE_WIN = 10;     // row words copied out of the landing stage per decision: the first LANE_WIN words of the
                                         // decision's compressed word list (LaneTables::nzw); later steps read the row from L2
+static constexpr int LANE_STRIDE = 17;  // words per lane in the window buffer: LANE_WIN row words, LANE_WIN / 2 list-entry pairs, padding
+                                        // to an odd stride (bank-conflict free)
 static constexpr int LANE_BUDGET = 192;  // walk steps a lane may spend before handing its decision to the whole warp
 struct LaneLayout {
   uint32_t row_bytes, stride, stage_bytes, ns, warps;
@@ -332,7 +334,7 @@ struct LaneLayout {
     ns = (uint32_t)ns_; warps = (uint32_t)warps_;
     off_bar = ns * stage_bytes; off_busy = off_bar + ns * 8u; off_uses = off_busy + ns * 4u;
     off_warp = (off_uses + ns * 4u + 127u) / 128u * 128u;
-    per_warp = 32u * (LANE_WIN + 1) * 4u + (uint32_t)((sizeof(DecisionCtx) + 15) / 16 * 16);  // window rows are LANE_WIN + 1 words apart: bank-conflict free
+    per_warp = 32u * LANE_STRIDE * 4u + (uint32_t)((sizeof(DecisionCtx) + 15) / 16 * 16);
     total = (size_t)off_warp + (size_t)warps * per_warp;
   }
 };
@@ -355,8 +357,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotVie
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + lay.off_bar);
   int *ticket = reinterpret_cast<int *>(smem_raw + lay.off_busy);               // next stage ticket of this block
   uint32_t *released = reinterpret_cast<uint32_t *>(smem_raw + lay.off_uses);  // [ns] completed uses per stage
-  uint32_t *win = reinterpret_cast<uint32_t *>(smem_raw + lay.off_warp + (size_t)wib * lay.per_warp);  // [32][LANE_WIN + 1]
-  DecisionCtx *ctx_one = reinterpret_cast<DecisionCtx *>(win + 32 * (LANE_WIN + 1));
+  uint32_t *win = reinterpret_cast<uint32_t *>(smem_raw + lay.off_warp + (size_t)wib * lay.per_warp);  // [32][LANE_STRIDE]
+  DecisionCtx *ctx_one = reinterpret_cast<DecisionCtx *>(win + 32 * LANE_STRIDE);
   if (threadIdx.x == 0) {
     for (int k = 0; k < ns; k++) { mbar_init(&bars[k], 32); released[k] = 0; }
     *ticket = 0;
@@ -437,7 +439,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotVie
     const int slot = c.slot >= 0 ? ctx_slot(c) : 0;
     const LaneTables T = lane_tables_global(s, slot);
     const uint32_t win_words = min((uint32_t)LANE_WIN, T.nz_n);
-    uint32_t wl[8];  // nzw[0..16) as 8 x 2 u16
+    uint32_t wl[8];  // nzw[0..16) as 8 x 2 u16 (the first LANE_WIN are kept)
     {
       const uint4 *np = reinterpret_cast<const uint4 *>(T.nzw);  // rows of nzw are row_words u16 = a multiple of 64 bytes
       const uint4 n0 = __ldg(np), n1 = __ldg(np + 1);
@@ -450,27 +452,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotVie
     // ---- copy the window out and hand the stage on ----
     uint32_t self_eword = 0;
     {
-      uint32_t *w = win + lane * (LANE_WIN + 1);
+      uint32_t *w = win + lane * LANE_STRIDE;
       const uint32_t WS_ = (uint32_t)s.word_lo;
-      // dense front (the slot's first LANE_WIN candidate words are row words 0, 1, 2, ...: every C3-like fleet): 128-bit
-      // copies; otherwise gather the listed words one by one
-      const bool dense = WS_ == 0 && win_words == (uint32_t)LANE_WIN && wl[0] == 0x00010000u && wl[1] == 0x00030002u && wl[2] == 0x00050004u &&
-                         wl[3] == 0x00070006u && wl[4] == 0x00090008u && wl[5] == 0x000b000au && wl[6] == 0x000d000cu;
-      if (__all_sync(0xffffffffu, dense || skip)) {
-        if (!skip) {
-#pragma unroll
-          for (int j = 0; j < (LANE_WIN + 3) / 4; j++) {
-            const uint4 q = *reinterpret_cast<const uint4 *>(my_row + j * 4);
-            w[j * 4] = q.x; w[j * 4 + 1] = q.y;
-            if (j * 4 + 2 < LANE_WIN) { w[j * 4 + 2] = q.z; w[j * 4 + 3] = q.w; }
-          }
-        }
-      } else if (!skip) {
+      if (!skip) {
 #pragma unroll
         for (int j = 0; j < LANE_WIN; j++) {
           const uint32_t wi = (wl[j >> 1] >> ((j & 1) * 16)) & 0xffffu;
           if ((uint32_t)j < win_words) w[j] = my_row[wi - WS_];
         }
+#pragma unroll
+        for (int j = 0; j < LANE_WIN / 2; j++) w[LANE_WIN + j] = wl[j];  // the window's list entries (u16 pairs)
       }
       const int sw = c.self_rank >> 5;
       if (!skip && c.self_rank >= 0 && sw >= s.word_lo && sw < s.word_hi) self_eword = my_row[sw - s.word_lo];
@@ -491,7 +482,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotVie
     bool handled = true;
     const uint64_t my_id = pick_id(d, id_base + (uint64_t)(orig_id ? (valid ? orig_id[b * 32 + lane] : 0) : b * 32 + lane));
     if ((mode & 1) == 0)
-      handled = decide_stream(s, T, c, valid && !skip, win + lane * (LANE_WIN + 1), win_words, wl, s.excl + (size_t)m * RW, self_eword,
+      handled = decide_stream(s, T, c, valid && !skip, win + lane * LANE_STRIDE, win + lane * LANE_STRIDE + LANE_WIN, win_words, s.excl + (size_t)m * RW, self_eword,
                               now, seed, my_id, WarpVote(), o, budget);
     else { o.target = (int32_t)(self_eword & 1u) - 1; o.n_candidates = 0; }  // MMP_LANE_MODE=1: stream-only probe (no decisions)
     // ---- what the lane routine declined: the whole warp redoes it, reading the row from global memory (L2) ----
@@ -561,16 +552,11 @@ __global__ void __launch_bounds__(32) k_place_small(const SnapshotView s_arg, co
   const int m = (valid && d.model >= 0 && d.model < s.n_models) ? d.model : 0;
   const uint32_t *row = s.excl + (size_t)m * RW;
   const LaneTables T = lane_tables_global(s, c.slot >= 0 ? ctx_slot(c) : 0);
-  uint32_t first8[4];
-  {
-    const uint4 q = __ldg(reinterpret_cast<const uint4 *>(T.nzw));
-    first8[0] = q.x; first8[1] = q.y; first8[2] = q.z; first8[3] = q.w;
-  }
   uint32_t self_eword = 0;
   if (valid && c.self_rank >= 0) self_eword = __ldg(row + (c.self_rank >> 5));
   DecideOut o;
   const uint64_t my_id = pick_id(d, id_base + (uint64_t)i);
-  const bool handled = decide_stream(s, T, c, valid, nullptr, 0u, first8, row, self_eword, now, seed, my_id, WarpVote(), o, budget);
+  const bool handled = decide_stream(s, T, c, valid, nullptr, nullptr, 0u, row, self_eword, now, seed, my_id, WarpVote(), o, budget);
   uint32_t pending = __ballot_sync(0xffffffffu, valid && !handled);
   while (pending) {
     const int l = __ffs((int)pending) - 1;
@@ -758,7 +744,7 @@ struct mmp_fleet {
   std::mutex mirror_mu;         // host_mirror(): lazy download of a device-built snapshot's rank-space vectors
   int commit_host_only = 0;     // MMP_COMMIT=host: every commit takes the structural (host) path (A/B and cross-check)
   bool device_ahead = false;    // the closed loop (churn_kernels.cuh) changed the registry on the device: host tables are behind
-  float t_stats_ms = 0, t_reaper_ms = 0, t_lru_ms = 0;  // CUDA-event time of the device part of the last mmp_stats / mmp_reaper_select / mmp_lru_apply
+  float t_stats_ms = 0, t_reaper_ms = 0, t_lru_ms = 0, t_prune_ms = 0;  // CUDA-event time of the device part of the last mmp_stats / mmp_reaper_select / mmp_lru_apply
   int32_t last_commit_path = 0; // 1 structural (host), 2 device
   double last_commit_ms = 0;
   ncclComm_t comm = nullptr;    // instance-shard communicator (mmp_shard_connect)
@@ -1122,7 +1108,7 @@ void mmp_fleet_destroy(mmp_fleet *f) {
   f->snaps[0].release(); f->snaps[1].release();
   for (DevBuf *b : {&f->live.inst_rows, &f->live.inst_tie, &f->live.inst_meta, &f->live.cand_idx, &f->live.pref_idx, &f->live.edges,
                     &f->live.models, &f->live.ovf_pairs, &f->live.keys, &f->live.rs_words, &f->live.flags, &f->live.scratch_idx,
-                    &f->live.scratch_rows, &f->live.scratch_edges})
+                    &f->live.scratch_rows, &f->live.scratch_edges, &f->live.edge_ts, &f->live.model_lul, &f->live.type_part_off, &f->live.type_parts})
     b->release();
   for (DevBuf *b : {&f->d_flush, &f->lru_ts, &f->lru_seq, &f->lru_weight, &f->lru_model,
                     &f->lru_cap, &f->lru_wsize, &f->lru_count, &f->lru_seqctr, &f->lru_loadts})
@@ -1156,6 +1142,10 @@ int32_t mmp_type_id(mmp_fleet *f, const char *name) {
   return id;
 }
 int32_t mmp_replicasets_set(mmp_fleet *f, const char *const *p, int32_t n) { NEED(f); FWD(f->hs.set_replicasets(p, n)); }
+int32_t mmp_model_times(mmp_fleet *f, int32_t m, const int64_t *edge_ts, int32_t n, int64_t last_unload_time) {
+  NEED(f);
+  FWD(f->hs.set_model_times(m, edge_ts, n, last_unload_time));
+}
 int32_t mmp_model_upsert(mmp_fleet *f, int32_t m, const mmp_model_row *row, const int32_t *ids, int32_t n) {
   NEED(f);
   FWD(f->hs.set_model(m, row, ids, n));
@@ -1205,6 +1195,27 @@ static int32_t commit_structural(mmp_fleet *f, DeviceSnapshot &ds, cudaStream_t 
       if ((h.cand[(size_t)sl * RW + (r >> 5)] >> (r & 31)) & 1u) cidx[(size_t)sl * NIW + (i >> 5)] |= 1u << (i & 31);
       if ((h.pref[(size_t)sl * RW + (r >> 5)] >> (r & 31)) & 1u) pidx[(size_t)sl * NIW + (i >> 5)] |= 1u << (i & 31);
     }
+  }
+  for (int32_t i = 0; i < NI; i++) if (f->hs.inst[i].present) meta[i].y |= 4;  // in the instance table (shutting-down records included)
+  {  // type id -> partitions whose instances may host the type (typeSetStats MM:1432-1438; TCM:230-233, 700-716)
+    const int32_t nt = (int32_t)h.type_slot.size();
+    std::vector<int> off((size_t)nt + 1, 0), parts;
+    for (int32_t ty = 0; ty < nt; ty++) {
+      off[ty] = (int)parts.size();
+      if (!h.tc_enabled || ty == 0) continue;  // no type constraints / an unconfigured name: the cluster's stats
+      const std::string &name = f->hs.type_names[ty];
+      auto it = f->hs.tc_config.find(name);
+      if (it == f->hs.tc_config.end() || it->second.required.empty()) continue;  // hasStats only with required labels (TCM:706-716)
+      const size_t before = parts.size();
+      for (size_t p = 0; p < h.part_types.size(); p++)
+        if (!std::binary_search(h.part_types[p].begin(), h.part_types[p].end(), name)) parts.push_back((int)p);
+      if (parts.size() == before) parts.push_back(-1);  // a subset without instances: empty stats
+    }
+    off[nt] = (int)parts.size();
+    if (parts.empty()) parts.push_back(-1);
+    CK(upload_vec(lv.type_part_off, off, st)); CK(upload_vec(lv.type_parts, parts, st));
+    CK(cudaStreamSynchronize(st));
+    lv.n_type_ids = nt;
   }
   CK(upload_vec(lv.inst_rows, rows, st)); CK(upload_vec(lv.inst_tie, tie, st)); CK(upload_vec(lv.inst_meta, meta, st));
   CK(upload_vec(lv.cand_idx, cidx, st)); CK(upload_vec(lv.pref_idx, pidx, st));
@@ -1365,6 +1376,12 @@ static int32_t commit_locked(mmp_fleet *f) {
       CK(cudaStreamSynchronize(st));
     }
   }
+  if (f->hs.times_dirty && !f->hs.edge_ts.empty()) {  // MR.instanceIds values / lastUnloadTime, when the host supplies them
+    CK(upload_vec(lv.edge_ts, f->hs.edge_ts, st)); CK(upload_vec(lv.model_lul, f->hs.model_lul, st));
+    CK(cudaStreamSynchronize(st));
+    lv.have_times = true;
+    f->hs.times_dirty = false;
+  }
   // each snapshot keeps its own copy of the model rows so in-flight readers of the other epoch are undisturbed
   CK(ds.models.ensure((size_t)std::max(nm, 1) * sizeof(mmp_model_row)));
   if (nm) CK(cudaMemcpyAsync(ds.models.p, lv.models.p, (size_t)nm * sizeof(mmp_model_row), cudaMemcpyDeviceToDevice, st));
@@ -1424,6 +1441,7 @@ int32_t mmp_last_timing(mmp_fleet *f, const char *key, double *ms) {
   if (!strcmp(key, "stats")) *ms = f->t_stats_ms;
   else if (!strcmp(key, "reaper")) *ms = f->t_reaper_ms;
   else if (!strcmp(key, "lru_apply")) *ms = f->t_lru_ms;
+  else if (!strcmp(key, "prune")) *ms = f->t_prune_ms;
   else if (!strcmp(key, "commit")) *ms = f->last_commit_ms;
   else { g_err = "unknown key"; return MMP_E_ARG; }
   return MMP_OK;
@@ -1867,3 +1885,5 @@ int32_t mmp_batcher_stats(mmp_batcher *b, int64_t *batches, int64_t *decisions) 
 
 #include "scan_kernels.cuh"
 #include "churn_kernels.cuh"
+#include "registry_kernels.cuh"
+

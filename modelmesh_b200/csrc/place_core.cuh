@@ -758,31 +758,30 @@ struct WarpVote { MMP_D bool any(bool p) const { return __any_sync(0xffffffffu, 
 #endif
 
 // The common case of getNext for ONE DECISION PER LANE (k_place_lanes), written so that the 32 lanes of a warp stay
-// converged AND execute few instructions per step.  A walk steps through the slot's compressed word list
-// (LaneTables::nzw): step k looks at row word W(k) = nzw[k], the k-th word that holds any candidate of the decision's type.
-// Walks run in CHUNKS of 8 steps: at the start of a chunk every walking lane loads the 8 list entries from ITS OWN position
-// on (entries as four u16 pairs, their row words from the window or -- beyond it -- from the row in global memory: 8
-// independent loads), then the 8 steps run as straight-line code with compile-time register indices, each lane on its own
-// word.  One warp vote per chunk, none per step; a long walk (C5: 100+ steps over sparse candidate masks) pays one L2 round
-// trip per 8 steps.  Phases:
+// converged: every phase is a walk whose loops are left by a warp vote, bodies are predicated on a per-lane state, and the
+// scalar work between the walks is straight-line.  A walk steps through the slot's compressed word list (LaneTables::nzw):
+// step k looks at row word W(k) = nzw[k], the k-th word that holds any candidate of the decision's type.  Phases:
 //   A   first entry of F = cand & ~excl & ~extra (MM:4806)
 //   A'  non-simple (a), MM:4828-4852: the first later entry that is preferred or full
 //   B   the shortlist walk (MM:4901-4937): first member of S that fails its test; a word whose count summary is
 //       "mixed" is evaluated exactly (32 counts) by the lanes that stop on one
 //   C   the hash-indexed pick (MM:4981-4986): k-th member of the shortlist
+// Every walk runs as two loops.  INSIDE THE WINDOW (steps k < win_words) a step reads its list entry and its row word from
+// the lane's window buffer (ewin[k] = row word W(k), wwin = the entries as u16 pairs: k_place_lanes fills both when it hands
+// the TMA landing stage on) -- two shared-memory loads, no bookkeeping; this is where every decision of a C3-like fleet
+// ends.  BEYOND THE WINDOW the list and the row are read from global memory (erow_g: the row has just been streamed, so it
+// is an L2 hit) in chunks of 8 steps held in registers, refilled for all walking lanes at the same iteration (one vote), so
+// that a long walk (C5: 100+ steps over sparse candidate masks) pays one L2 round trip per 8 steps; with erow_g == nullptr
+// the lane's attempt ends at the window's edge.
 // Same semantics and quirks as decide_ctx (N2: the non-self test reads the caller's fresh record).  Returns false --
 // and the caller redoes the decision with the cooperative general routine -- for everything outside the common case:
 // malformed decision, more than LANE_MAX_EXTRA extra excludes, no entry / best full (replicaset retry, non-simple (b)), or
 // a walk of more than `budget` steps.  Instance-sharded: a walk that needs ranks beyond this shard's range sets MMP_TF_OPEN.
-// The decision's exclusion row is seen through a WINDOW: ewin[k] = row word W(k) for k < win_words (k_place_lanes copies
-// these out of the TMA landing stage so that the stage can take the next rows while the lanes compute); steps beyond the
-// window read the row itself (erow_g: global memory, word index relative to word_lo -- the row has just been streamed, so it
-// is an L2 hit), or end the lane's attempt when erow_g is null.  first8 = entries 0..7 of the slot's word list as four u16
-// pairs.  self_eword = the row word that holds self's bit (anywhere in the row).  Must be called by every lane of the vote
-// group (active = false for lanes without a decision).
+// self_eword = the row word that holds self's bit (anywhere in the row).  Must be called by every lane of the vote group
+// (active = false for lanes without a decision).
 template <class V>
 MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const DecisionCtx &c, bool active, const uint32_t *ewin,
-                          uint32_t win_words, const uint32_t *first8, const uint32_t *erow_g, uint32_t self_eword, int64_t now, uint64_t seed,
+                          const uint32_t *wwin, uint32_t win_words, const uint32_t *erow_g, uint32_t self_eword, int64_t now, uint64_t seed,
                           uint64_t decision_id, const V &vote, DecideOut &o, int32_t budget) {
   o.target = MMP_TARGET_NONE; o.n_candidates = 0; o.best = -1; o.n_remaining = 0; o.pick_index = 0; o.flags = 0;
   o.cut_rank = (int32_t)NONE_RANK; o.best_rank = -1; o.first_rank = -1;
@@ -804,56 +803,65 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
     return m;
   };
   auto pbit = [&](uint32_t r) -> bool { return (ldro(P + (r >> 5)) >> (r & 31)) & 1u; };
-  // ---- the chunk: steps [k0, k0 + 8) of the lane's walk ----
-  uint32_t wq[4], eq[8];
-  bool reach;  // false: the chunk reaches beyond the window and there is no row to read
-  auto load_chunk = [&](uint32_t k0, bool use_first8) {
-    if (use_first8) { wq[0] = first8[0]; wq[1] = first8[1]; wq[2] = first8[2]; wq[3] = first8[3]; }
-    else {
-#pragma unroll
-      for (uint32_t j = 0; j < 4; j++) {
-        const uint32_t ka = k0 + 2 * j, kb_ = ka + 1;
-        const uint32_t lo16 = ka < NZ ? (uint32_t)ldro(T.nzw + ka) : 0xffffu, hi16 = kb_ < NZ ? (uint32_t)ldro(T.nzw + kb_) : 0xffffu;
-        wq[j] = lo16 | (hi16 << 16);
-      }
-    }
-    reach = true;
-#pragma unroll
-    for (uint32_t j = 0; j < 8; j++) {
-      const uint32_t kk = k0 + j;
-      uint32_t e = 0;
-      if (kk < NZ) {
-        if (kk < win_words) e = ewin[kk];
-        else if (erow_g != nullptr) e = ldro(erow_g + (((wq[j >> 1] >> ((j & 1u) * 16u)) & 0xffffu) - WS));
-        else reach = false;
-      }
-      eq[j] = e;
-    }
+  // ---- beyond the window: a chunk of 8 consecutive steps [base, base + 8) in registers ----
+  uint32_t base = 0xfffffff0u;  // no chunk loaded
+  uint32_t wq[4] = {0, 0, 0, 0};
+  uint32_t eq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  auto wsel = [&](uint32_t j) -> uint32_t {          // entry j (0..7) of the chunk, without dynamic register indexing
+    uint32_t q = wq[0];
+    q = (j >> 1) == 1 ? wq[1] : q; q = (j >> 1) == 2 ? wq[2] : q; q = (j >> 1) == 3 ? wq[3] : q;
+    return (q >> ((j & 1u) * 16u)) & 0xffffu;
   };
-  // Runs body(k, wi, e) on successive steps of every walking lane, from the lane's own start position, until no lane walks.
-  // body returns true to go on to the next step.  `walking` is cleared when the lane stops (body said so, the list ended:
-  // ended = true, or the budget / reach ran out: live = false).
-  // (a macro-like lambda: the 8 steps are unrolled so that eq[j] / wq[j >> 1] are compile-time register picks)
-#define MMP_WALK(K, WALKING, ENDED, BODY)                                                                                   \
-  for (;;) {                                                                                                                \
-    if (!vote.any(WALKING)) break;                                                                                          \
-    if (WALKING) {                                                                                                          \
-      if (K >= NZ) { WALKING = false; ENDED = true; }                                                                        \
-      else if (left <= 0) { WALKING = false; live = false; }                                                                 \
-      else { load_chunk(K, K == 0); left -= 8; }                                                                             \
-    }                                                                                                                       \
-    _Pragma("unroll") for (uint32_t j_ = 0; j_ < 8; j_++) {                                                                  \
-      if (WALKING) {                                                                                                        \
-        if (K >= NZ) { WALKING = false; ENDED = true; }                                                                      \
-        else if (K >= win_words && !reach) { WALKING = false; live = false; }                                                \
-        else {                                                                                                              \
-          const uint32_t wi = (wq[j_ >> 1] >> ((j_ & 1u) * 16u)) & 0xffffu, e = eq[j_];                                      \
-          bool go_;                                                                                                         \
-          BODY;                                                                                                             \
-          if (go_) K++; else WALKING = false;                                                                                \
-        }                                                                                                                   \
-      }                                                                                                                     \
-    }                                                                                                                       \
+  auto refill = [&](uint32_t k) {
+    base = k;
+#pragma unroll
+    for (uint32_t j = 0; j < 4; j++) {
+      const uint32_t k0 = k + 2 * j, k1 = k0 + 1;
+      const uint32_t lo16 = k0 < NZ ? (uint32_t)ldro(T.nzw + k0) : 0xffffu, hi16 = k1 < NZ ? (uint32_t)ldro(T.nzw + k1) : 0xffffu;
+      wq[j] = lo16 | (hi16 << 16);
+    }
+#pragma unroll
+    for (uint32_t j = 0; j < 8; j++) eq[j] = (k + j < NZ) ? ldro(erow_g + (wsel(j) - WS)) : 0u;
+  };
+  auto esel = [&](uint32_t j) -> uint32_t {
+    uint32_t v = eq[0];
+    v = j == 1 ? eq[1] : v; v = j == 2 ? eq[2] : v; v = j == 3 ? eq[3] : v; v = j == 4 ? eq[4] : v;
+    v = j == 5 ? eq[5] : v; v = j == 6 ? eq[6] : v; v = j == 7 ? eq[7] : v;
+    return v;
+  };
+  // One walk: BODY sees (K, wi, e) and sets go_ (true: next step).  WALKING is cleared when the lane stops: BODY said so, the
+  // list ended (ENDED = true), or the budget / the reachable part of the row ran out (live = false).  CHARGE: the steps
+  // count against the budget (phase C re-walks words phase B has paid for).
+#define MMP_WALK(K, WALKING, ENDED, CHARGE, BODY)                                                                            \
+  for (;;) { /* inside the window */                                                                                       \
+    if (WALKING && K < win_words) {                                                                                        \
+      if (CHARGE && left <= 0) { WALKING = false; live = false; }                                                          \
+      else {                                                                                                               \
+        const uint32_t wi = (wwin[K >> 1] >> ((K & 1u) * 16u)) & 0xffffu, e = ewin[K];                                     \
+        bool go_;                                                                                                          \
+        BODY;                                                                                                              \
+        if (go_) { K++; if (CHARGE) left--; } else WALKING = false;                                                        \
+      }                                                                                                                    \
+    }                                                                                                                      \
+    if (!vote.any(WALKING && K < win_words)) break;                                                                        \
+  }                                                                                                                        \
+  if (WALKING && K >= NZ) { WALKING = false; ENDED = true; }                                                               \
+  if (WALKING && erow_g == nullptr) { WALKING = false; live = false; }                                                      \
+  if (vote.any(WALKING)) {                                                                                                 \
+    for (;;) { /* beyond the window */                                                                                     \
+      { const bool need_ = WALKING && K < NZ && (K - base) >= 8u; if (vote.any(need_)) { if (WALKING && K < NZ) refill(K); } } \
+      if (WALKING) {                                                                                                       \
+        if (K >= NZ) { WALKING = false; ENDED = true; }                                                                    \
+        else if (CHARGE && left <= 0) { WALKING = false; live = false; }                                                   \
+        else {                                                                                                             \
+          const uint32_t wi = wsel(K - base), e = esel(K - base);                                                          \
+          bool go_;                                                                                                        \
+          BODY;                                                                                                            \
+          if (go_) { K++; if (CHARGE) left--; } else WALKING = false;                                                      \
+        }                                                                                                                  \
+      }                                                                                                                    \
+      if (!vote.any(WALKING)) break;                                                                                       \
+    }                                                                                                                      \
   }
 
   // ---- A: first filtered entry ----
@@ -861,7 +869,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
   {
     uint32_t k = 0;
     bool walking = live, ended = false;
-    MMP_WALK(k, walking, ended, {
+    MMP_WALK(k, walking, ended, true, {
       uint32_t x = ldro(CX + wi) & ~e;
       if (has_x) x &= ~xmask(wi);
       if (x) { b = wi * 32u + (uint32_t)ffs32(x); kb = k; }
@@ -886,18 +894,18 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
   }
   // ---- A': non-simple (a) ----
   uint32_t r1 = NONE_RANK, k1 = kb;
-  bool a_ended = false;
   {
     const uint32_t b_w = b >> 5, m_b = mask_above(b_w * 32u, b);
     uint32_t k = kb;
-    bool walking = live && !simple;
-    MMP_WALK(k, walking, a_ended, {
+    bool walking = live && !simple, ended = false;
+    MMP_WALK(k, walking, ended, true, {
       uint32_t x = ldro(CX + wi) & ~e & (ldro(P + wi) | ldro(T.full + wi));
       if (has_x) x &= ~xmask(wi);
       if (wi == b_w) x &= m_b;
       if (x) { r1 = wi * 32u + (uint32_t)ffs32(x); k1 = k; }
       go_ = x == 0;
     })
+    (void)ended;
   }
   bool open = false;
   if (live && !simple) {
@@ -953,7 +961,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
   {
     uint32_t k = k_lo;
     bool walking = walk, ended = false;
-    MMP_WALK(k, walking, ended, {
+    MMP_WALK(k, walking, ended, true, {
       go_ = true;
       if (wi >= stop_w) { ended = true; go_ = false; }  // the walk's natural end (everything at or beyond lim)
       else {
@@ -1026,9 +1034,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
     const uint32_t cut_w = cut >> 5, m_cut = mask_below(cut_w * 32u, cut);
     uint32_t k = k_lo;
     bool walking = sel, ended = false;
-    const int32_t left_keep = left;
-    left = 0x3fffffff;
-    MMP_WALK(k, walking, ended, {
+    MMP_WALK(k, walking, ended, false, {
       uint32_t x = Sw(wi, e);
       if (wi == cut_w) x &= m_cut;
       if (drop_self && wi == sw_) x &= ~sb_;
@@ -1037,7 +1043,6 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
       if (kth < n) { chosen_rank = wi * 32u + (uint32_t)nth_bit(x, kth); go_ = false; }
       else kth -= n;
     })
-    left = left_keep;
     if (sel && ended) live = false;  // cannot happen: kth < number of survivors, all in visited words
   }
 #undef MMP_WALK

@@ -35,6 +35,15 @@ SIM_EVICTION = np.dtype([("instance", "<i4"), ("model", "<i4"), ("last_used", "<
                          ("reload", "<i4")], align=True)
 assert INST.itemsize == 64 and DECISION.itemsize == 32 and RESULT.itemsize == 24 and MODEL.itemsize == 24
 assert SIM_MODEL.itemsize == 16 and SIM_EVENT.itemsize == 24 and SIM_DECISION.itemsize == 24 and SIM_EVICTION.itemsize == 32
+SCALE_IN = np.dtype([("instance", "<i4"), ("model", "<i4"), ("count", "<i8"), ("last_used", "<i8"), ("last_heavy", "<i8"), ("i1", "<i4"),
+                     ("i2", "<i4"), ("weight", "<i4"), ("flags", "<i4")], align=True)
+SCALE_PARAMS = np.dtype([("now", "<i8"), ("last_check_time", "<i8"), ("iteration", "<i4"), ("scale_up_rpm_threshold", "<i4"),
+                         ("second_copy_min_age_iters", "<i4"), ("second_copy_max_age_iters", "<i4"), ("second_copy_lru_threshold_ms", "<i8"),
+                         ("rate_check_interval_ms", "<i8"), ("assume_completed_ms", "<i8"), ("second_copy_remove_max_age_ms", "<i8"),
+                         ("can_remove", "<i4"), ("pad", "<i4")], align=True)
+SCALE_OUT = np.dtype([("action", "<i4"), ("copies_to_load", "<i4"), ("load_last_used", "<i8"), ("rpm", "<i4"), ("i1", "<i4"), ("i2", "<i4"),
+                      ("set_heavy", "<i4"), ("remove", "<i4")], align=True)
+assert SCALE_IN.itemsize == 48 and SCALE_PARAMS.itemsize == 72 and SCALE_OUT.itemsize == 40
 SIM_REQUEST, SIM_REMOVE = 0, 1
 (SIM_ACCEPTED, SIM_NOWHERE, SIM_CHURN, SIM_FALLTHRU, SIM_EARLY, SIM_GROW_EVICTED, SIM_EXISTS, SIM_SKIPPED, SIM_INVALID,
  SIM_EVICTED_LATER) = range(10)
@@ -95,6 +104,9 @@ def lib() -> C.CDLL:
             "orc_scaleup_copies": (I32, [I64, I64, I32, I32, I32, I32, I32, I32, I32, C.POINTER(I32)]),
             "orc_scaleup_exclude_set": (I32, [P, I32, I32, I32, P, I32]),
             "orc_loaded_since": (C.c_int, [P, P, I32, I64, I32]),
+            "orc_rate_task_eval": (C.c_int, [P, I32, P, P, STRS, I32, P, P, P, P, P, P]),
+            "orc_janitor_eval": (C.c_int, [P, I32, P, P, P, P, P, P, P, P]),
+            "orc_prune_missing": (I32, [P, I32, P, P, I32, I64, I64, P, P]),
             "orc_scale_down": (C.c_int, [P, I32, P, P, I32, I64, I64, I64, I64, I64, I64, I32, I64, I64]),
         }
         for name, (res, args) in sig.items():

@@ -497,6 +497,7 @@ struct Fleet {
   int changeCounter = 0;
   uint64_t nextLabelsIdentity = 1;
   std::vector<IRp> byIdx;  // test convenience: latest record by instance idx (null if absent)
+  std::vector<uint8_t> inTable;  // instanceInfo.contains(id): the KV table holds a record (a shutting-down one included)
   std::vector<JStr> keyByIdx;
 
   Fleet(int64_t minSpace, int64_t minChurn, int32_t defSize) : clusterState(EntryLess{&po}), clusterStatsTracker(nullptr, &po) {
@@ -735,6 +736,7 @@ OptSet Tcm::inferPreferredInstances(const std::map<int32_t, int32_t> &instanceSc
 // ---------------------------------------------------------------------------------------------
 void Fleet::instanceEvent(int type, int32_t idx, const JStr &key, IRp record, int64_t now) {
   enum { ENTRY_ADDED = 0, ENTRY_UPDATED = 1, ENTRY_DELETED = 2 };
+  const bool stays_in_table = type != ENTRY_DELETED && record != nullptr;
   Isst *subsetStats = nullptr;
   if (record) {
     if (record->shuttingDown) type = ENTRY_DELETED;
@@ -791,6 +793,8 @@ void Fleet::instanceEvent(int type, int32_t idx, const JStr &key, IRp record, in
   if ((changeCounter++ & 63) == 0) upgradeTracker.doHousekeeping(now);
 
   if ((size_t)idx >= byIdx.size()) { byIdx.resize(idx + 1); keyByIdx.resize(idx + 1); siActive.resize(idx + 1, 0); }
+  if ((size_t)idx >= inTable.size()) inTable.resize(idx + 1, 0);
+  inTable[idx] = stays_in_table ? 1 : 0;
   keyByIdx[idx] = key;
   if (type == ENTRY_DELETED) byIdx[idx] = nullptr; else byIdx[idx] = record;
 }

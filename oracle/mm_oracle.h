@@ -217,6 +217,22 @@ int32_t orc_scaleup_copies(int64_t count, int64_t time_delta_ms, int32_t scale_u
                            int32_t *rpm_out);
 int32_t orc_scaleup_exclude_set(orc_fleet *, int32_t self, int32_t scale_up_rpms, int32_t our_rpm, uint8_t *marks, int32_t n_idx);
 int orc_loaded_since(const int32_t *inst, const int64_t *load_ts, int32_t n, int64_t cutoff, int32_t ignore_instance);
+typedef struct { int32_t instance, model; int64_t count, last_used, last_heavy; int32_t i1, i2, weight, flags; } orc_scale_in_t;
+typedef struct {
+  int64_t now, last_check_time;
+  int32_t iteration, scale_up_rpm_threshold, second_copy_min_age_iters, second_copy_max_age_iters;
+  int64_t second_copy_lru_threshold_ms, rate_check_interval_ms, assume_completed_ms, second_copy_remove_max_age_ms;
+  int32_t can_remove, pad;
+} orc_scale_params_t;
+typedef struct { int32_t action, copies_to_load; int64_t load_last_used; int32_t rpm, i1, i2, set_heavy, remove; } orc_scale_out_t;
+int orc_rate_task_eval(orc_fleet *, int32_t n, const orc_scale_in_t *in, const orc_scale_params_t *p, const char *const *type_names,
+                       int32_t n_types, const int32_t *type_idx, const int64_t *edge_off, const int32_t *edge_inst, const int64_t *edge_ts,
+                       const int32_t *n_loaded, orc_scale_out_t *out);
+int orc_janitor_eval(orc_fleet *, int32_t n, const orc_scale_in_t *in, const orc_scale_params_t *p, const int64_t *edge_off,
+                     const int32_t *edge_inst, const int64_t *edge_ts, const int32_t *n_loaded, const int64_t *last_unload_time,
+                     orc_scale_out_t *out);
+int32_t orc_prune_missing(orc_fleet *, int32_t self, const int32_t *inst, const int64_t *ts, int32_t n, int64_t now, int64_t assume_gone_ms,
+                          int64_t *missing_since, uint8_t *pruned);
 int orc_scale_down(orc_fleet *, int32_t self, const int32_t *copies, const int64_t *load_ts, int32_t n_copies, int64_t last_used,
                    int64_t now, int64_t last_heavy_time, int64_t last_unload_time, int64_t last_check_time, int64_t interval_count,
                    int32_t scale_up_rpm_threshold, int64_t rate_check_interval_ms, int64_t second_copy_remove_max_age_ms);

@@ -30,7 +30,7 @@ static thread_local std::string g_err;
 static int g_window = 32;  // fast-path window width under test (32: warp tile, 16: half-warp tile); 1: lane-per-decision shape
 static int g_lane_budget = 48;  // CoopLane walk budget (row words) when g_window == 1
 static int g_lane_global = 1;  // decide_stream: steps beyond the window may read the row itself (the kernel's second chance: L2)
-static int g_lane_window = 14;  // decide_stream: row words available to a lane (LANE_WIN of k_place_lanes: the window copied out of the landing stage)
+static int g_lane_window = 10;  // decide_stream: row words available to a lane (LANE_WIN of k_place_lanes: the window copied out of the landing stage)
 static long g_bails = 0, g_lane_decisions = 0;
 
 extern "C" {
@@ -157,9 +157,9 @@ int32_t mmp_place_batch_trace(mmp_fleet *f, const mmp_decision_in *in, int32_t n
       const uint32_t ww = (uint32_t)std::min<int64_t>(g_lane_window, (int64_t)T.nz_n);
       std::vector<uint32_t> window(ww);
       for (uint32_t k = 0; k < ww; k++) window[k] = erow[T.nzw[k] - v.word_lo];
-      uint32_t first8[4];
-      for (int j = 0; j < 4; j++) first8[j] = (uint32_t)T.nzw[2 * j] | ((uint32_t)T.nzw[2 * j + 1] << 16);
-      done = decide_stream(v, T, cx, true, window.data(), ww, first8, g_lane_global ? erow : nullptr, self_eword, now_ms, seed,
+      std::vector<uint32_t> wwin((ww + 1) / 2 + 1, 0u);  // the window's list entries as u16 pairs (what k_place_lanes stores beside the row words)
+      for (uint32_t k = 0; k < ww; k++) wwin[k >> 1] |= (uint32_t)T.nzw[k] << ((k & 1u) * 16u);
+      done = decide_stream(v, T, cx, true, window.data(), wwin.data(), ww, g_lane_global ? erow : nullptr, self_eword, now_ms, seed,
                            pick_id(in[i], f->id_base + (uint64_t)i), SoloVote(), o, g_lane_budget);
       g_lane_decisions++;
       if (!done) g_bails++;

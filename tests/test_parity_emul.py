@@ -150,7 +150,7 @@ def test_registry_sweep_equals_the_batch_of_records(emul_lib, oracle_lib):
 
 
 @pytest.mark.parametrize("second_chance", [0, 1])
-@pytest.mark.parametrize("window", [1, 2, 5, 14])
+@pytest.mark.parametrize("window", [1, 2, 5, 10])
 @pytest.mark.parametrize("config,nm,ni,seed", [("C3", 2000, 1300, 33), ("C5", 1500, 500, 5), ("MIX", 500, 300, 14), ("MIX", 500, 700, 41)])
 def test_stream_routine_window_widths(emul_lib, oracle_lib, config, nm, ni, seed, window, second_chance):
     """decide_stream sees a window of the decision's exclusion row: the first `window` words of the type slot's compressed
@@ -179,5 +179,5 @@ def test_stream_routine_window_widths(emul_lib, oracle_lib, config, nm, ni, seed
     finally:
         emul_lib.mmp_emul_set_window(32)
         emul_lib.mmp_emul_set_lane_global(1)
-        emul_lib.mmp_emul_set_lane_window(14)
+        emul_lib.mmp_emul_set_lane_window(10)
         emul_lib.mmp_emul_set_lane_budget(48)
