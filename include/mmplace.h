@@ -350,8 +350,12 @@ typedef struct {
   int64_t last_used;    /* the entry's lastUsed in the pod's cache */
   int64_t last_heavy;   /* ce.getLastHeavyTime() */
   int32_t i1, i2;       /* ce.earlierUseIteration / lastUsedIteration (MM:1647-1648) */
-  int32_t weight, flags;
+  int32_t weight, flags; /* MMP_SCALE_NO_LOCAL_STATS */
 } mmp_scale_in;
+/* The pod's TypeConstraintManager.localInstanceSetStats is null: it is only assigned when the pod's own ADDED event created its
+ * instance set (TCM:557-583), so a pod that joined an existing set sees EMPTY_STATS (TCM:236-239) and never scales down.  The
+ * adapter passes `typeConstraints != null && typeConstraints.getLocalInstanceSetStats().totalCapacity == 0` here. */
+#define MMP_SCALE_NO_LOCAL_STATS 1
 typedef struct {
   int64_t now, last_check_time;                     /* timeDelta = now - lastCheckTime (MM:5641-5642) */
   int32_t iteration, scale_up_rpm_threshold;        /* iterationCounter, scaleUpRpmThreshold */

@@ -106,6 +106,8 @@ struct HostSnapshot {
   // mask the lane routine reads (candx when a replicaset is flagged, else cand) has any bit, ascending
   std::vector<uint16_t> nzw;          // [n_slots][row_words]
   std::vector<int32_t> nz_n;          // [n_slots]
+  std::vector<uint16_t> nzw_full;     // instance-sharded fleets: the same lists over the WHOLE row (the peer-access path decides whole rows)
+  std::vector<int32_t> nz_n_full;
   std::vector<int32_t> part_of_rank;  // [n_ranks] partition (PTS) id, 0 when no type constraints
   std::vector<std::vector<std::string>> part_types;  // prohibited type names per partition id
   std::vector<std::vector<int32_t>> part_type_ids;   // the same as type ids of THIS epoch (readers never touch the ingest-side name table)
@@ -453,6 +455,17 @@ class HostState {
       for (int32_t w = s.word_lo; w < s.word_hi; w++)
         if (cx[w]) s.nzw[(size_t)sl * RW + k++] = (uint16_t)w;
       s.nz_n[sl] = k;
+    }
+    if (cfg.shard_count > 1) {
+      s.nzw_full.assign((size_t)s.n_slots * RW, 0xffff);
+      s.nz_n_full.assign((size_t)s.n_slots, 0);
+      for (int32_t sl = 0; sl < s.n_slots; sl++) {
+        const uint32_t *cx = (s.any_rs ? s.candx.data() : s.cand.data()) + (size_t)sl * RW;
+        int32_t k = 0;
+        for (int32_t w = 0; w < RW; w++)
+          if (cx[w]) s.nzw_full[(size_t)sl * RW + k++] = (uint16_t)w;
+        s.nz_n_full[sl] = k;
+      }
     }
     s.part_type_ids.assign(s.part_types.size(), {});
     for (size_t p = 0; p < s.part_types.size(); p++)

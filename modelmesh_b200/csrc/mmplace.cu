@@ -319,6 +319,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_place(const SnapshotView s
 // The stages keep ~NS x 41 KB per SM in flight from HBM independently of how many warps are computing, and the
 // per-decision instruction cost is ~85 warp instructions instead of ~450 for a cooperative tile (ncu, C3 sweep).
 // ---------------------------------------------------------------------------------------------------------------
+static constexpr int SHARD_FRONT_WORDS = 16;  // instance-sharded fleets: row words replicated on every shard (512 ranks: where almost every walk ends)
 static constexpr int LANE_WIN = 10;     // row words copied out of the landing stage per decision: the first LANE_WIN words of the
                                         // decision's compressed word list (LaneTables::nzw); later steps read the row from L2
 static constexpr int LANE_STRIDE = 17;  // words per lane in the window buffer: LANE_WIN row words, LANE_WIN / 2 list-entry pairs, padding
@@ -482,7 +483,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotVie
     bool handled = true;
     const uint64_t my_id = pick_id(d, id_base + (uint64_t)(orig_id ? (valid ? orig_id[b * 32 + lane] : 0) : b * 32 + lane));
     if ((mode & 1) == 0)
-      handled = decide_stream(s, T, c, valid && !skip, win + lane * LANE_STRIDE, win + lane * LANE_STRIDE + LANE_WIN, win_words, s.excl + (size_t)m * RW, self_eword,
+      handled = decide_stream(s, T, c, valid && !skip, win + lane * LANE_STRIDE, win + lane * LANE_STRIDE + LANE_WIN, win_words, RowPtr{s.excl + (size_t)m * RW, (uint32_t)s.word_lo}, self_eword,
                               now, seed, my_id, WarpVote(), o, budget);
     else { o.target = (int32_t)(self_eword & 1u) - 1; o.n_candidates = 0; }  // MMP_LANE_MODE=1: stream-only probe (no decisions)
     // ---- what the lane routine declined: the whole warp redoes it, reading the row from global memory (L2) ----
@@ -556,7 +557,7 @@ __global__ void __launch_bounds__(32) k_place_small(const SnapshotView s_arg, co
   if (valid && c.self_rank >= 0) self_eword = __ldg(row + (c.self_rank >> 5));
   DecideOut o;
   const uint64_t my_id = pick_id(d, id_base + (uint64_t)i);
-  const bool handled = decide_stream(s, T, c, valid, nullptr, nullptr, 0u, row, self_eword, now, seed, my_id, WarpVote(), o, budget);
+  const bool handled = decide_stream(s, T, c, valid, nullptr, nullptr, 0u, RowPtr{row, (uint32_t)s.word_lo}, self_eword, now, seed, my_id, WarpVote(), o, budget);
   uint32_t pending = __ballot_sync(0xffffffffu, valid && !handled);
   while (pending) {
     const int l = __ffs((int)pending) - 1;
@@ -696,13 +697,14 @@ struct DevBuf {
 struct DeviceSnapshot {
   DevBuf excl, cand, candx, pref, has_pref, type_slot, full, rows, rank_of, csum, lsum, models;
   DevBuf cap_col, lthreads_col, linprog_col, part_of_rank, count_col, cand_before, nzw, nz_n;
+  DevBuf front, nzw_full, nz_n_full;  // instance-sharded fleets: replicated first words of every row; word lists over the whole row
   SnapshotView view{};
   HostSnapshot host;  // kept for introspection and the small host-side parts of stats / reaper
   bool host_stale = false;  // built on the device: the rank-space vectors of `host` are downloaded on first use (host_mirror)
   int32_t n_models = 0;
   void release() {
     for (DevBuf *b : {&excl, &cand, &candx, &pref, &has_pref, &type_slot, &full, &rows, &rank_of, &csum, &lsum, &models,
-                      &cap_col, &lthreads_col, &linprog_col, &part_of_rank, &count_col, &cand_before, &nzw, &nz_n})
+                      &cap_col, &lthreads_col, &linprog_col, &part_of_rank, &count_col, &cand_before, &nzw, &nz_n, &front, &nzw_full, &nz_n_full})
       b->release();
   }
 };
@@ -1178,6 +1180,7 @@ static int32_t commit_structural(mmp_fleet *f, DeviceSnapshot &ds, cudaStream_t 
   CK(upload_vec(ds.count_col, h.count_col, st));
   CK(upload_vec(ds.cand_before, h.candx_before, st));
   CK(upload_vec(ds.nzw, h.nzw, st)); CK(upload_vec(ds.nz_n, h.nz_n, st));
+  if (f->hs.cfg.shard_count > 1) { CK(upload_vec(ds.nzw_full, h.nzw_full, st)); CK(upload_vec(ds.nz_n_full, h.nz_n_full, st)); }
   // ---- the live tables later (non-structural) commits re-rank from ----
   LiveState &lv = f->live;
   const int32_t NI = f->hs.cfg.max_instances, NIW = (NI + 31) / 32, n = h.n_ranks, RW = h.row_words;
@@ -1252,7 +1255,7 @@ static int32_t commit_device(mmp_fleet *f, DeviceSnapshot &ds, cudaStream_t st) 
   CK(ds.count_col.ensure((size_t)RW * 32 * 4)); CK(ds.cand_before.ensure((size_t)NS * 4));
   CK(ds.nzw.ensure((size_t)NS * RW * 2)); CK(ds.nz_n.ensure((size_t)NS * 4));
   CK(upload_vec(ds.has_pref, t.has_pref, st)); CK(upload_vec(ds.type_slot, t.type_slot_hp, st));
-  CK(lv.keys.ensure((size_t)NI * sizeof(OrderKey))); CK(lv.rs_words.ensure((size_t)RW * 4)); CK(lv.flags.ensure(16));
+  CK(lv.keys.ensure((size_t)NI * sizeof(OrderKey))); CK(lv.rs_words.ensure((size_t)RW * 4)); CK(lv.flags.ensure(16 + (size_t)NS * 4));
   CK(cudaMemsetAsync(lv.flags.p, 0, 16, st));
   CK(cudaMemsetAsync(ds.full.p, 0, (size_t)RW * 4, st)); CK(cudaMemsetAsync(lv.rs_words.p, 0, (size_t)RW * 4, st));
   CK(cudaMemsetAsync(ds.count_col.p, 0, (size_t)RW * 32 * 4, st));
@@ -1272,6 +1275,12 @@ static int32_t commit_device(mmp_fleet *f, DeviceSnapshot &ds, cudaStream_t st) 
                                                         ds.pref.as<uint32_t>());
   k_slot_lists<<<(NS + 31) / 32, 32, 0, st>>>(ds.cand.as<uint32_t>(), ds.candx.as<uint32_t>(), t.any_rs, RW, NS, t.word_lo, t.word_hi,
                                              ds.nzw.as<uint16_t>(), ds.nz_n.as<int32_t>(), ds.cand_before.as<int32_t>());
+  if (f->hs.cfg.shard_count > 1) {
+    CK(ds.nzw_full.ensure((size_t)NS * RW * 2)); CK(ds.nz_n_full.ensure((size_t)NS * 4));
+    k_slot_lists<<<(NS + 31) / 32, 32, 0, st>>>(ds.cand.as<uint32_t>(), ds.candx.as<uint32_t>(), t.any_rs, RW, NS, 0, RW, ds.nzw_full.as<uint16_t>(),
+                                               ds.nz_n_full.as<int32_t>(), lv.flags.as<int32_t>() + 2 /* scratch: cand_before of a whole row = 0 */);
+    f->launches++;
+  }
   f->launches += 6;
   CK(cudaGetLastError());
   int flags = 0;
@@ -1401,6 +1410,15 @@ static int32_t commit_locked(mmp_fleet *f) {
       CK(cudaGetLastError());
     }
   }
+  if (f->hs.cfg.shard_count > 1 && nm) {  // the replicated front of every row (peer-access path: decisions are dealt across the shards)
+    const int F = std::min(SHARD_FRONT_WORDS, RW);
+    CK(ds.front.ensure((size_t)nm * F * 4));
+    CK(cudaMemsetAsync(ds.front.p, 0, (size_t)nm * F * 4, st));
+    k_build_bitmap<<<(nm + 255) / 256, 256, 0, st>>>(ds.front.as<uint32_t>(), lv.edges.as<int4>(), ds.rank_of.as<int32_t>(), nm, F, 0, F);
+    if (lv.n_ovf) k_build_bitmap_ovf<<<(lv.n_ovf + 255) / 256, 256, 0, st>>>(ds.front.as<uint32_t>(), lv.ovf_pairs.as<int2>(), lv.n_ovf, ds.rank_of.as<int32_t>(), F, 0, F);
+    f->launches += 2;
+    CK(cudaGetLastError());
+  }
   CK(cudaStreamSynchronize(st));
   SnapshotView &v = ds.view;
   v.n_ranks = h.n_ranks; v.row_words = RW; v.n_models = nm; v.max_instances = f->hs.cfg.max_instances;
@@ -1511,7 +1529,7 @@ static int32_t place_impl(mmp_fleet *f, const mmp_decision_in *in, int32_t n, co
         PlaceArgs a{vw, (const mmp_decision_in *)(dbase + o_in), n, (const FreshRow *)(dbase + o_fr), n_fresh,
                     (const int32_t *)(dbase + o_ex), (mmp_decision_out *)(dbase + o_out), nullptr, nullptr, now_ms, seed, f->id_base.load()};
         CK(launch_place(f, a, st));
-      } else if (f->one_mode == 1 || n > 32) {
+      } else if (f->one_mode == 1 || n > 32 || n_fresh > 32 || (size_t)n_extra > 32 * MMP_MAX_EXTRA) {  // (the graph's mapped layout is laid out for 32 decisions)
         k_place_small<<<(n + 31) / 32, 32, 0, st>>>(vw, (const mmp_decision_in *)(dbase + o_in), n, (const FreshRow *)(dbase + o_fr), n_fresh,
                                                   (const int32_t *)(dbase + o_ex), (mmp_decision_out *)(dbase + o_out), now_ms, seed,
                                                   f->id_base.load(), nullptr, f->lane_budget);
@@ -1524,7 +1542,6 @@ static int32_t place_impl(mmp_fleet *f, const mmp_decision_in *in, int32_t n, co
         const size_t g_in = 64, g_out = g_in + 32 * sizeof(mmp_decision_in), g_fr = g_out + 32 * sizeof(mmp_decision_out),
                      g_ex = g_fr + 32 * sizeof(FreshRow);
         static_assert(64 + 32 * (sizeof(mmp_decision_in) + sizeof(mmp_decision_out) + sizeof(FreshRow)) + 32 * MMP_MAX_EXTRA * 4 <= PlaceCtx::MAPPED_BYTES, "mapped layout");
-        if (n_fresh > 32 || (size_t)n_extra > 32 * MMP_MAX_EXTRA) { g_err = "tiny batch with oversized side tables"; return MMP_E_ARG; }
         SmallHdr *hd = reinterpret_cast<SmallHdr *>(h);
         memmove(h + g_in, in, (size_t)n * sizeof(mmp_decision_in));  // (the generic layout above was filled first: move into the graph's)
         if (n_fresh) memcpy(h + g_fr, c->fresh_host.data(), (size_t)n_fresh * sizeof(FreshRow));

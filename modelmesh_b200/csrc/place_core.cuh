@@ -751,6 +751,26 @@ MMP_HD bool shard_cannot_win(const SnapshotView &s, const DecisionCtx &c, uint32
   return (int64_t)s.cand_before[ctx_slot(c)] > (int64_t)n_row_bits + (int64_t)(c.d.extra_n > 0 ? c.d.extra_n : 0);
 }
 
+// ---- how decide_stream reaches the part of a decision's exclusion row that is not in its window ----
+// RowPtr: the stored row in this process's memory (word index relative to word_lo); p == nullptr: nothing beyond the window.
+struct RowPtr {
+  const uint32_t *p; uint32_t ws;
+  MMP_HD bool ok() const { return p != nullptr; }
+  MMP_HD uint32_t word(uint32_t wi) const { return ldro(p + (wi - ws)); }
+};
+// RowDealt (instance-sharded fleets with peer access): row words [0, front_words) are replicated on every
+// shard, word wi beyond them lives in the column block of shard wi / block_words -- this GPU's HBM or a peer's, read through
+// its NVLink-mapped pointer.
+struct RowDealt {
+  const uint32_t *front; const uint32_t *const *blocks; uint32_t front_words, block_words, stride; uint64_t model;
+  MMP_HD bool ok() const { return true; }
+  MMP_HD uint32_t word(uint32_t wi) const {
+    if (wi < front_words) return ldro(front + model * front_words + wi);
+    const uint32_t g = wi / block_words;
+    return blocks[g][model * stride + (wi - g * block_words)];
+  }
+};
+
 // ---- vote shapes for decide_stream: 32 decisions in lockstep on the GPU, one on the CPU harness ----
 struct SoloVote { MMP_HD bool any(bool p) const { return p; } };
 #if defined(__CUDACC__)
@@ -769,9 +789,9 @@ struct WarpVote { MMP_D bool any(bool p) const { return __any_sync(0xffffffffu, 
 // Every walk runs as two loops.  INSIDE THE WINDOW (steps k < win_words) a step reads its list entry and its row word from
 // the lane's window buffer (ewin[k] = row word W(k), wwin = the entries as u16 pairs: k_place_lanes fills both when it hands
 // the TMA landing stage on) -- two shared-memory loads, no bookkeeping; this is where every decision of a C3-like fleet
-// ends.  BEYOND THE WINDOW the list and the row are read from global memory (erow_g: the row has just been streamed, so it
+// ends.  BEYOND THE WINDOW the list and the row are read from global memory (row: the row has just been streamed, so it
 // is an L2 hit) in chunks of 8 steps held in registers, refilled for all walking lanes at the same iteration (one vote), so
-// that a long walk (C5: 100+ steps over sparse candidate masks) pays one L2 round trip per 8 steps; with erow_g == nullptr
+// that a long walk (C5: 100+ steps over sparse candidate masks) pays one L2 round trip per 8 steps; with !row.ok()
 // the lane's attempt ends at the window's edge.
 // Same semantics and quirks as decide_ctx (N2: the non-self test reads the caller's fresh record).  Returns false --
 // and the caller redoes the decision with the cooperative general routine -- for everything outside the common case:
@@ -779,9 +799,9 @@ struct WarpVote { MMP_D bool any(bool p) const { return __any_sync(0xffffffffu, 
 // a walk of more than `budget` steps.  Instance-sharded: a walk that needs ranks beyond this shard's range sets MMP_TF_OPEN.
 // self_eword = the row word that holds self's bit (anywhere in the row).  Must be called by every lane of the vote group
 // (active = false for lanes without a decision).
-template <class V>
+template <class V, class R>
 MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const DecisionCtx &c, bool active, const uint32_t *ewin,
-                          const uint32_t *wwin, uint32_t win_words, const uint32_t *erow_g, uint32_t self_eword, int64_t now, uint64_t seed,
+                          const uint32_t *wwin, uint32_t win_words, const R &row, uint32_t self_eword, int64_t now, uint64_t seed,
                           uint64_t decision_id, const V &vote, DecideOut &o, int32_t budget) {
   o.target = MMP_TARGET_NONE; o.n_candidates = 0; o.best = -1; o.n_remaining = 0; o.pick_index = 0; o.flags = 0;
   o.cut_rank = (int32_t)NONE_RANK; o.best_rank = -1; o.first_rank = -1;
@@ -821,7 +841,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
       wq[j] = lo16 | (hi16 << 16);
     }
 #pragma unroll
-    for (uint32_t j = 0; j < 8; j++) eq[j] = (k + j < NZ) ? ldro(erow_g + (wsel(j) - WS)) : 0u;
+    for (uint32_t j = 0; j < 8; j++) eq[j] = (k + j < NZ) ? row.word(wsel(j)) : 0u;
   };
   auto esel = [&](uint32_t j) -> uint32_t {
     uint32_t v = eq[0];
@@ -846,7 +866,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
     if (!vote.any(WALKING && K < win_words)) break;                                                                        \
   }                                                                                                                        \
   if (WALKING && K >= NZ) { WALKING = false; ENDED = true; }                                                               \
-  if (WALKING && erow_g == nullptr) { WALKING = false; live = false; }                                                      \
+  if (WALKING && !row.ok()) { WALKING = false; live = false; }                                                              \
   if (vote.any(WALKING)) {                                                                                                 \
     for (;;) { /* beyond the window */                                                                                     \
       { const bool need_ = WALKING && K < NZ && (K - base) >= 8u; if (vote.any(need_)) { if (WALKING && K < NZ) refill(K); } } \

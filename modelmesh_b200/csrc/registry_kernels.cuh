@@ -116,7 +116,7 @@ __global__ void k_scale_eval(ScaleTables T, const mmp_scale_in *__restrict__ in,
     long long cap, fr;
     const long long glru = *T.min_lru;
     if (T.tc_enabled) {
-      if (self_rank < 0) break;  // EMPTY_STATS: totalCapacity == 0
+      if (self_rank < 0 || (e.flags & MMP_SCALE_NO_LOCAL_STATS)) break;  // EMPTY_STATS: totalCapacity == 0 (quirk N13, mmplace.h)
       const StatsAcc a = T.part_acc[1 + T.part_of_rank[self_rank]];
       cap = (long long)a.cap; fr = (long long)a.free;
     } else { cap = (long long)T.part_acc[0].cap; fr = (long long)T.part_acc[0].free; }

@@ -107,7 +107,7 @@ def lib() -> C.CDLL:
             "orc_rate_task_eval": (C.c_int, [P, I32, P, P, STRS, I32, P, P, P, P, P, P]),
             "orc_janitor_eval": (C.c_int, [P, I32, P, P, P, P, P, P, P, P]),
             "orc_prune_missing": (I32, [P, I32, P, P, I32, I64, I64, P, P]),
-            "orc_scale_down": (C.c_int, [P, I32, P, P, I32, I64, I64, I64, I64, I64, I64, I32, I64, I64]),
+            "orc_scale_down": (C.c_int, [P, I32, P, P, I32, I64, I64, I64, I64, I64, I64, I32, I64, I64, I32]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)

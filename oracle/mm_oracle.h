@@ -235,7 +235,8 @@ int32_t orc_prune_missing(orc_fleet *, int32_t self, const int32_t *inst, const 
                           int64_t *missing_since, uint8_t *pruned);
 int orc_scale_down(orc_fleet *, int32_t self, const int32_t *copies, const int64_t *load_ts, int32_t n_copies, int64_t last_used,
                    int64_t now, int64_t last_heavy_time, int64_t last_unload_time, int64_t last_check_time, int64_t interval_count,
-                   int32_t scale_up_rpm_threshold, int64_t rate_check_interval_ms, int64_t second_copy_remove_max_age_ms);
+                   int32_t scale_up_rpm_threshold, int64_t rate_check_interval_ms, int64_t second_copy_remove_max_age_ms,
+                   int32_t local_stats_known);
 
 #ifdef __cplusplus
 }

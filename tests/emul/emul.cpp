@@ -159,7 +159,7 @@ int32_t mmp_place_batch_trace(mmp_fleet *f, const mmp_decision_in *in, int32_t n
       for (uint32_t k = 0; k < ww; k++) window[k] = erow[T.nzw[k] - v.word_lo];
       std::vector<uint32_t> wwin((ww + 1) / 2 + 1, 0u);  // the window's list entries as u16 pairs (what k_place_lanes stores beside the row words)
       for (uint32_t k = 0; k < ww; k++) wwin[k >> 1] |= (uint32_t)T.nzw[k] << ((k & 1u) * 16u);
-      done = decide_stream(v, T, cx, true, window.data(), wwin.data(), ww, g_lane_global ? erow : nullptr, self_eword, now_ms, seed,
+      done = decide_stream(v, T, cx, true, window.data(), wwin.data(), ww, RowPtr{g_lane_global ? erow : nullptr, (uint32_t)v.word_lo}, self_eword, now_ms, seed,
                            pick_id(in[i], f->id_base + (uint64_t)i), SoloVote(), o, g_lane_budget);
       g_lane_decisions++;
       if (!done) g_bails++;

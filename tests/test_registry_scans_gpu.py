@@ -58,6 +58,7 @@ def test_scale_eval_matches_oracle(product_lib, oracle_lib, config, nm, ni, seed
     rec["count"] = np.where(rng.uniform(size=n) < 0.5, rng.integers(0, 50, size=n), rng.integers(0, 20_000, size=n))
     rec["last_used"] = np.where(rng.uniform(size=n) < 0.05, 0, fl.now_ms - rng.integers(0, 40 * 3_600_000, size=n))
     rec["last_heavy"] = np.where(rng.uniform(size=n) < 0.4, 0, fl.now_ms - rng.integers(0, 30 * 3_600_000, size=n))
+    rec["flags"] = (rng.uniform(size=n) < 0.15).astype(np.int32)  # MMP_SCALE_NO_LOCAL_STATS (quirk N13)
     it = 5000
     rec["i1"] = it - rng.integers(0, 400, size=n)
     rec["i2"] = np.minimum(it, rec["i1"] + rng.integers(0, 300, size=n))
@@ -78,7 +79,7 @@ def test_scale_eval_matches_oracle(product_lib, oracle_lib, config, nm, ni, seed
         nl = fl.n_loaded[m64].astype(np.int32)
         tidx = fl.model_type[m64].astype(np.int32)
         orec = np.zeros(n, dtype=ob.SCALE_IN)
-        for k in ("instance", "model", "count", "last_used", "last_heavy", "i1", "i2"):
+        for k in ("instance", "model", "count", "last_used", "last_heavy", "i1", "i2", "flags"):
             orec[k] = rec[k]
         op = np.zeros(1, dtype=ob.SCALE_PARAMS)
         for k in op.dtype.names:
