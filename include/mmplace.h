@@ -235,6 +235,18 @@ int32_t mmp_shard_unique_id(void *id128);                       /* shard 0: nccl
 int32_t mmp_shard_connect(mmp_fleet *, const void *id128);      /* all shards: ncclCommInitRank(shard_count, id, shard_rank) */
 int32_t mmp_shard_words(mmp_fleet *, int32_t *word_lo, int32_t *word_hi); /* this shard's row words [lo, hi); returns the stored row stride */
 int64_t mmp_shard_open_decisions(mmp_fleet *);                  /* decisions that needed the row-gather pass so far */
+/* Peer access between the instance shards (one node, NVLink): once every shard has imported its peers' blobs, a batch is
+ * DEALT across the shards -- each decides 1/shard_count of it, reading row words beyond the replicated front from the owning
+ * shard's memory, and stores its results into every shard's result buffer.  No NCCL call and no host synchronisation on
+ * that path (mmp_shard_connect is then optional).  Each shard: export (after its first commit or before), exchange the
+ * blobs by any means, import all shard_count blobs ordered by rank.  Works across processes (CUDA IPC) and between fleets
+ * of one process (peer access).  Same contract as the collective path: every shard commits the same epochs and is given
+ * the same batches in the same order; every shard ends with the whole batch's results.  Batches of up to max_batch. */
+#define MMP_SHARD_IPC_BYTES 512
+int32_t mmp_shard_ipc_export(mmp_fleet *, int32_t max_batch, void *blob /* MMP_SHARD_IPC_BYTES */);
+int32_t mmp_shard_ipc_import(mmp_fleet *, const void *blobs /* shard_count x MMP_SHARD_IPC_BYTES, by shard rank */);
+/* out4: [0] batches taken by the peer path, [1] row words read from peers' memory, [2] result bytes stored to peers, [3] 1 = path active */
+int32_t mmp_shard_peer_stats(mmp_fleet *, int64_t *out4);
 /* Registry (model) sharding needs no exchange: each process places the decisions of its own models against the whole
  * instance table.  The only cross-shard convention is the numbering of decisions for the hash-indexed pick (N4, MM:4981):
  * decision i of a batch hashes as id_base + i, so a shard that is handed the slice [lo, hi) of a larger batch sets

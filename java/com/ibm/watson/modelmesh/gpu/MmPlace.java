@@ -69,6 +69,10 @@ final class MmPlace {
     static native int shardConnect(long h, byte[] id128);
     static native int shardWords(long h, int[] loHiOut);
     static native long shardOpenDecisions(long h);
+    static final int SHARD_IPC_BYTES = 512;
+    static native int shardIpcExport(long h, int maxBatch, byte[] blobOut);
+    static native int shardIpcImport(long h, byte[] blobsByRank);
+    static native int shardPeerStats(long h, long[] out4);
     static native int setIdBase(long h, long base);
     // introspection
     static native int rowWords(long h);

@@ -13,6 +13,7 @@
 #include <jni.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "mmplace.h"
@@ -259,6 +260,35 @@ jint FN(shardWords)(JNIEnv *env, jclass c, jlong h, jintArray out) {
   return rc;
 }
 jlong FN(shardOpenDecisions)(JNIEnv *env, jclass c, jlong h) { (void)env; (void)c; return mmp_shard_open_decisions(H(h)); }
+/* peer access between the shards: blob = byte[MMP_SHARD_IPC_BYTES]; blobs = byte[shardCount * MMP_SHARD_IPC_BYTES] by rank */
+jint FN(shardIpcExport)(JNIEnv *env, jclass c, jlong h, jint maxBatch, jbyteArray blob) {
+  unsigned char buf[MMP_SHARD_IPC_BYTES];
+  jint rc = mmp_shard_ipc_export(H(h), maxBatch, buf);
+  (void)c;
+  if (rc == 0) (*env)->SetByteArrayRegion(env, blob, 0, MMP_SHARD_IPC_BYTES, (const jbyte *)buf);
+  return rc;
+}
+jint FN(shardIpcImport)(JNIEnv *env, jclass c, jlong h, jbyteArray blobs) {
+  const jsize len = (*env)->GetArrayLength(env, blobs);
+  jbyte *p = (jbyte *)malloc(len > 0 ? (size_t)len : 1);  /* (opening IPC handles may block: no critical section here) */
+  jint rc;
+  (void)c;
+  if (!p) return MMP_E_ARG;
+  (*env)->GetByteArrayRegion(env, blobs, 0, len, p);
+  rc = mmp_shard_ipc_import(H(h), p);
+  free(p);
+  return rc;
+}
+jint FN(shardPeerStats)(JNIEnv *env, jclass c, jlong h, jlongArray out4) {
+  int64_t v[4] = {0, 0, 0, 0};
+  jlong w[4];
+  jint rc = mmp_shard_peer_stats(H(h), v);
+  int i;
+  (void)c;
+  for (i = 0; i < 4; i++) w[i] = (jlong)v[i];
+  if (rc == 0) (*env)->SetLongArrayRegion(env, out4, 0, 4, w);
+  return rc;
+}
 jint FN(setIdBase)(JNIEnv *env, jclass c, jlong h, jlong base) { (void)env; (void)c; return mmp_fleet_set_id_base(H(h), (uint64_t)base); }
 
 /* ---- introspection ---- */

@@ -149,6 +149,9 @@ SYMBOLS = [
     ("mmp_shard_connect", _I32, [_P, _P]),
     ("mmp_shard_words", _I32, [_P, C.POINTER(_I32), C.POINTER(_I32)]),
     ("mmp_shard_open_decisions", _I64, [_P]),
+    ("mmp_shard_ipc_export", _I32, [_P, _I32, _P]),
+    ("mmp_shard_ipc_import", _I32, [_P, _P]),
+    ("mmp_shard_peer_stats", _I32, [_P, _P]),
     ("mmp_fleet_set_id_base", _I32, [_P, _U64]),
 ]
 
@@ -178,6 +181,9 @@ def load(path: str, require_all: bool = True) -> C.CDLL:
 
 
 _product = None
+
+
+SHARD_IPC_BYTES = 512  # MMP_SHARD_IPC_BYTES
 
 
 def load_product() -> C.CDLL:

@@ -13,6 +13,7 @@
 //          the block's warps, lock-step voted walks), k_place<...> (cooperative tiles: traced calls / very wide rows),
 //          k_build_bitmap* (commit), k_shard_* (instance-shard combine), k_stats, k_reaper_*, k_lru_apply (scan_kernels.cuh).
 #include <cuda_runtime.h>
+#include <unistd.h>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -575,6 +576,109 @@ __global__ void __launch_bounds__(32) k_place_small(const SnapshotView s_arg, co
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// instance-sharded placement with peer access -- k_place_dealt.  The decisions of a batch are DEALT to the
+// shards by warp batch (batch wb goes to shard wb % G), so G GPUs each decide 1/G of the batch instead of all of it.  A
+// decision is resolved completely by the shard it was dealt to: the first SHARD_FRONT_WORDS words of its exclusion row are
+// replicated on every shard (DeviceSnapshot::front: where almost every walk ends), the words beyond come from the column
+// block of the shard that owns them -- this GPU's HBM or a peer's, through its NVLink-mapped pointer (RowDealt).  The
+// result (8 bytes) is stored into the result buffer of EVERY shard (peer stores over NVLink), so all shards end with the
+// whole batch's answers.  No collective call, no host synchronisation between the shards: the last block of the kernel
+// raises this shard's flag in every peer's flag array (release, system scope) and k_dealt_wait spins until all G flags of
+// the step have arrived (bounded by a timeout: a missing peer ends in an error, not a hang).
+// ---------------------------------------------------------------------------------------------------------------
+static constexpr int MAX_SHARDS = 16;
+struct DealtPeers {
+  const uint32_t *blocks[MAX_SHARDS];   // column block of every shard for the current epoch (own block: local pointer)
+  mmp_decision_out *out[MAX_SHARDS];    // result buffer of every shard for this step's parity
+  unsigned long long *flags[MAX_SHARDS];  // flag array of every shard: [G] arrival counters
+};
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_place_dealt(const SnapshotView s, const uint32_t *__restrict__ front, int front_words,
+                                                            const uint16_t *__restrict__ nzw_full, const int32_t *__restrict__ nz_n_full,
+                                                            const __grid_constant__ DealtPeers P, int G, int me, const mmp_decision_in *__restrict__ in, int n,
+                                                            const FreshRow *__restrict__ fresh, int n_fresh, const int32_t *__restrict__ extra,
+                                                            int64_t now, uint64_t seed, uint64_t id_base, int budget, unsigned long long step,
+                                                            unsigned int *__restrict__ done, unsigned long long *__restrict__ remote_words) {
+  extern __shared__ __align__(16) unsigned char dealt_smem[];
+  __shared__ DecisionCtx ctx_w[WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int RW = s.row_words;
+  uint32_t *row_s = reinterpret_cast<uint32_t *>(dealt_smem) + (size_t)warp * RW;  // whole row of a decision redone by the warp
+  const long long wb = ((long long)blockIdx.x * WARPS + warp) * G + me;             // this warp's batch of 32 decisions
+  const long long i = wb * 32 + lane;
+  const bool valid = i < n;
+  mmp_decision_in d;
+  d.model = -1; d.self = -1; d.last_used = 0; d.flags = 0; d.fresh = -1; d.extra_off = 0; d.extra_n = 0;
+  if (valid) d = in[i];
+  DecisionCtx c;
+  c.slot = -2; c.self_rank = -1; c.self_bits = 0; c.self_count = 0;
+  if (valid) prepare_ctx(s, d, fresh, n_fresh, extra, c);
+  const int m = (valid && d.model >= 0 && d.model < s.n_models) ? d.model : 0;
+  LaneTables T = lane_tables_global(s, c.slot >= 0 ? ctx_slot(c) : 0);
+  {
+    const int slot = c.slot >= 0 ? ctx_slot(c) : 0;
+    T.nzw = nzw_full + (size_t)slot * RW; T.nz_n = (uint32_t)nz_n_full[slot];
+  }
+  RowDealt row{front, P.blocks, (uint32_t)front_words, (uint32_t)s.excl_stride, (uint32_t)s.excl_stride, (uint64_t)m, (uint32_t)me, 0u};
+  uint32_t self_eword = 0;
+  if (valid && c.self_rank >= 0) self_eword = row.word((uint32_t)(c.self_rank >> 5));
+  DecideOut o;
+  o.target = MMP_TARGET_NONE; o.n_candidates = 0;
+  const uint64_t my_id = pick_id(d, id_base + (uint64_t)i);
+  const bool handled = decide_stream(s, T, c, valid, nullptr, nullptr, 0u, row, self_eword, now, seed, my_id, WarpVote(), o, budget);
+  uint32_t pending = __ballot_sync(0xffffffffu, valid && !handled);
+  while (pending) {  // the cooperative general routine over the whole row, assembled in shared memory
+    const int l = __ffs((int)pending) - 1;
+    pending &= pending - 1;
+    if (lane == l) ctx_w[warp] = c;
+    const int ml = __shfl_sync(0xffffffffu, m, l);
+    const uint64_t idl = __shfl_sync(0xffffffffu, my_id, l);
+    RowDealt rl = row;
+    rl.model = (uint64_t)ml; rl.remote = 0;
+    for (int w = lane; w < RW; w += 32) row_s[w] = rl.word((uint32_t)w);
+    row.remote += rl.remote;
+    __syncwarp();
+    int32_t t2, c2, f2, g2;
+    decide_warp(s, ctx_w[warp], row_s, extra, now, seed, idl, &t2, &c2, &f2, &g2);
+    if (lane == l) { o.target = t2; o.n_candidates = c2; }
+    __syncwarp();
+  }
+  if (valid) {
+    const mmp_decision_out r{o.target, o.n_candidates};
+    for (int g = 0; g < G; g++) P.out[g][i] = r;  // 256 contiguous bytes per warp and shard
+  }
+  // ---- arrival: every thread's peer stores are ordered before the block's count, the last block raises the flags ----
+  uint32_t rem = row.remote;
+  for (int of = 16; of > 0; of >>= 1) rem += __shfl_xor_sync(0xffffffffu, rem, of);
+  if (lane == 0 && rem) atomicAdd(remote_words, (unsigned long long)rem);
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(done, 1u);
+    if (prev == gridDim.x - 1) {
+      *done = 0;
+      __threadfence_system();
+      for (int g = 0; g < G; g++)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(P.flags[g] + me), "l"(step) : "memory");
+    }
+  }
+}
+// one warp: lane g waits for shard g's arrival at `step`; err[0] = 1 after `timeout_ns`
+__global__ void k_dealt_wait(const unsigned long long *flags, int G, unsigned long long step, unsigned long long timeout_ns, int *err) {
+  const int g = threadIdx.x;
+  if (g >= G) return;
+  unsigned long long t0, t1, v;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + g) : "memory");
+    if (v >= step) break;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > timeout_ns) { atomicExch(err, 1); break; }
+    __nanosleep(200);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // instance-sharded combine: kernels around the one collective
 // ---------------------------------------------------------------------------------------------------------------
 // keys -> results in place (both 8 bytes per decision) + a flag per decision whose winning shard left it open
@@ -750,6 +854,17 @@ struct mmp_fleet {
   int32_t last_commit_path = 0; // 1 structural (host), 2 device
   double last_commit_ms = 0;
   ncclComm_t comm = nullptr;    // instance-shard communicator (mmp_shard_connect)
+  // peer-access path of the instance-sharded layout (mmp_shard_ipc_export / _import, k_place_dealt)
+  struct Peers {
+    bool ready = false;
+    int32_t max_batch = 0;
+    DevBuf out, flags, done, err;           // out: 2 x max_batch results (step parity); flags: MAX_SHARDS arrival counters + statistics
+    void *peer_base[MAX_SHARDS][4] = {};    // what was opened from every peer: excl of snapshot 0 / 1, out, flags
+    bool opened[MAX_SHARDS][4] = {};
+    uint64_t step = 0;
+    int64_t batches = 0, result_bytes = 0;
+    int off = 0;                            // MMP_SHARD_PEERS=0 keeps the collective path although peers were imported
+  } peers;
   std::mutex comm_mu;           // collectives of one communicator are issued by one thread at a time
   std::atomic<int64_t> open_decisions{0};  // decisions that needed the row-gather pass so far
   std::atomic<uint64_t> id_base{0};        // decision i of a batch hashes as id_base + i (mmp_fleet_set_id_base)
@@ -926,6 +1041,56 @@ static cudaError_t launch_place(mmp_fleet *f, const PlaceArgs &a, cudaStream_t s
   return traced ? launch_place_t<4, 2, 2, 32, true>(f, a, st) : launch_place_t<4, 2, 2, 16, false>(f, a, st);
 }
 
+// the peer-access path of place_sharded: one k_place_dealt over this shard's deal of the batch, the arrival wait, the
+// results from this shard's result buffer into d_out.  Every shard is given the same batch in the same call sequence.
+static int32_t place_dealt(mmp_fleet *f, PlaceCtx *c, const DeviceSnapshot &ds, const mmp_decision_in *d_in, int32_t n,
+                           const FreshRow *d_fresh, int32_t n_fresh, const int32_t *d_extra, int32_t n_extra, mmp_decision_out *d_out,
+                           int64_t now_ms, uint64_t seed, cudaStream_t st) {
+  mmp_fleet::Peers &pr = f->peers;
+  const int G = f->hs.cfg.shard_count, me = f->hs.cfg.shard_rank;
+  if (n > pr.max_batch) { g_err = "batch larger than the max_batch given to mmp_shard_ipc_export"; return MMP_E_ARG; }
+  std::lock_guard<std::mutex> g(f->comm_mu);  // one dealt step at a time per fleet: the steps are numbered
+  SnapshotView vw = ds.view;
+  vw.n_extra = n_extra;
+  vw.word_lo = 0; vw.word_hi = vw.row_words;  // a dealt decision walks the whole rank range (excl_stride stays the block stride)
+  const int cur = (int)(&ds - f->snaps);
+  const uint64_t step = ++pr.step;
+  DealtPeers P;
+  for (int q = 0; q < MAX_SHARDS; q++) { P.blocks[q] = nullptr; P.out[q] = nullptr; P.flags[q] = nullptr; }
+  for (int q = 0; q < G; q++) {
+    P.blocks[q] = q == me ? ds.excl.as<uint32_t>() : reinterpret_cast<const uint32_t *>(pr.peer_base[q][cur]);
+    mmp_decision_out *ob = q == me ? pr.out.as<mmp_decision_out>() : reinterpret_cast<mmp_decision_out *>(pr.peer_base[q][2]);
+    P.out[q] = ob + (size_t)(step & 1) * pr.max_batch;
+    P.flags[q] = q == me ? pr.flags.as<unsigned long long>() : reinterpret_cast<unsigned long long *>(pr.peer_base[q][3]);
+  }
+  constexpr int WARPS = 4;
+  const long long n_wb = ((long long)n + 31) / 32;                     // warp batches of the whole batch
+  const long long mine = n_wb > me ? (n_wb - me + G - 1) / G : 0;      // ... dealt to this shard
+  const int blocks = (int)std::max<long long>(1, (mine + WARPS - 1) / WARPS);  // (an empty deal still arrives)
+  const size_t smem = (size_t)WARPS * vw.row_words * 4;
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_place_dealt<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  unsigned long long *stats = pr.flags.as<unsigned long long>() + MAX_SHARDS;
+  k_place_dealt<WARPS><<<blocks, WARPS * 32, smem, st>>>(vw, ds.front.as<uint32_t>(), std::min(SHARD_FRONT_WORDS, vw.row_words), ds.nzw_full.as<uint16_t>(),
+                                                       ds.nz_n_full.as<int32_t>(), P, G, me, d_in, n, d_fresh, n_fresh, d_extra, now_ms, seed,
+                                                       f->id_base.load(), f->lane_budget, step, pr.done.as<unsigned int>(), stats);
+  CK(cudaGetLastError());
+  k_dealt_wait<<<1, 32, 0, st>>>(pr.flags.as<unsigned long long>(), G, step, 4000000000ull, pr.err.as<int>());
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(d_out, pr.out.as<mmp_decision_out>() + (size_t)(step & 1) * pr.max_batch, (size_t)n * sizeof(mmp_decision_out),
+                     cudaMemcpyDeviceToDevice, st));
+  int err = 0;
+  CK(cudaMemcpyAsync(&err, pr.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  f->launches += 2;
+  pr.batches++;
+  {
+    const long long nb = n / 32, full = nb > me ? (nb - me + G - 1) / G : 0;
+    pr.result_bytes += (full * 32 + ((nb % G) == me ? n % 32 : 0)) * 8 * (G - 1);
+  }
+  if (err) { pr.ready = false; g_err = "instance shards: a peer did not arrive at the step within 4 s (peer path disabled)"; return MMP_E_STATE; }
+  return MMP_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // instance-sharded placement: every shard resolves the whole batch over its own rank range, ONE all-reduce(min) of the
 // 64-bit keys gives every rank the answer of the shard that holds the first entry under PLACEMENT_ORDER (min-loc), and
@@ -937,6 +1102,8 @@ static int32_t place_sharded(mmp_fleet *f, PlaceCtx *c, const DeviceSnapshot &ds
                              int64_t now_ms, uint64_t seed, cudaStream_t st) {
   SnapshotView vw = ds.view;
   vw.n_extra = n_extra;  // per call: bounds of the decisions' extra[] slices (checked on the device, prepare_ctx_a)
+  if (f->peers.ready && !f->peers.off && f->hs.cfg.shard_count > 1)
+    return place_dealt(f, c, ds, d_in, n, d_fresh, n_fresh, d_extra, n_extra, d_out, now_ms, seed, st);
   if (!f->comm) { g_err = "instance-sharded fleet is not connected (mmp_shard_connect)"; return MMP_E_STATE; }
   NcclApi &nc = nccl_api();
   std::lock_guard<std::mutex> g(f->comm_mu);
@@ -1048,6 +1215,94 @@ int32_t mmp_shard_words(mmp_fleet *f, int32_t *word_lo, int32_t *word_hi) {
   return st;
 }
 int64_t mmp_shard_open_decisions(mmp_fleet *f) { return f ? f->open_decisions.load() : 0; }
+
+// ---- peer access between the instance shards (k_place_dealt) ----
+struct ShardIpcBlob {
+  uint32_t magic, rank, count, max_batch;
+  uint64_t pid, bytes[4], ptr[4];
+  int32_t device, pad;
+  cudaIpcMemHandle_t h[4];  // excl of snapshot 0 / 1, result buffer, flag array
+};
+static_assert(sizeof(ShardIpcBlob) <= MMP_SHARD_IPC_BYTES, "blob size");
+int32_t mmp_shard_ipc_export(mmp_fleet *f, int32_t max_batch, void *blob) {
+  if (!f || !blob || max_batch <= 0) { g_err = "bad argument"; return MMP_E_ARG; }
+  const int G = f->hs.cfg.shard_count;
+  if (G < 2 || G > MAX_SHARDS) { g_err = "peer access needs 2..16 instance shards"; return MMP_E_STATE; }
+  CK(cudaSetDevice(f->device));
+  std::lock_guard<std::mutex> g(f->ingest_mu);
+  mmp_fleet::Peers &pr = f->peers;
+  int32_t lo, hi, stw;
+  HostState::shard_words(f->hs.row_words(), f->hs.cfg.shard_rank, G, lo, hi, stw);
+  // the column blocks keep their address for the fleet's lifetime: both snapshots are sized for max_models rows now
+  const size_t full = (size_t)std::max(f->hs.cfg.max_models, 1) * stw * 4;
+  for (int k = 0; k < 2; k++) {
+    DevBuf &b = f->snaps[k].excl;
+    if (b.p && b.cap < full) { g_err = "column block allocated before export is smaller than max_models rows"; return MMP_E_STATE; }
+    if (!b.p) { CK(b.ensure(full)); CK(cudaMemset(b.p, 0, full)); }
+  }
+  pr.ready = false;
+  pr.max_batch = max_batch;
+  CK(pr.out.ensure((size_t)2 * max_batch * sizeof(mmp_decision_out)));
+  CK(pr.flags.ensure((MAX_SHARDS + 8) * 8)); CK(pr.done.ensure(16)); CK(pr.err.ensure(16));
+  CK(cudaMemset(pr.flags.p, 0, (MAX_SHARDS + 8) * 8)); CK(cudaMemset(pr.done.p, 0, 16)); CK(cudaMemset(pr.err.p, 0, 16));
+  pr.step = 0;
+  ShardIpcBlob bl;
+  memset(&bl, 0, sizeof(bl));
+  bl.magic = 0x4d4d5049u; bl.rank = (uint32_t)f->hs.cfg.shard_rank; bl.count = (uint32_t)G; bl.max_batch = (uint32_t)max_batch;
+  bl.pid = (uint64_t)getpid(); bl.device = f->device;
+  void *ptrs[4] = {f->snaps[0].excl.p, f->snaps[1].excl.p, pr.out.p, pr.flags.p};
+  const size_t bytes[4] = {f->snaps[0].excl.cap, f->snaps[1].excl.cap, pr.out.cap, pr.flags.cap};
+  for (int k = 0; k < 4; k++) {
+    bl.ptr[k] = (uint64_t)(uintptr_t)ptrs[k]; bl.bytes[k] = bytes[k];
+    CK(cudaIpcGetMemHandle(&bl.h[k], ptrs[k]));
+  }
+  memset(blob, 0, MMP_SHARD_IPC_BYTES);
+  memcpy(blob, &bl, sizeof(bl));
+  return MMP_OK;
+}
+int32_t mmp_shard_ipc_import(mmp_fleet *f, const void *blobs) {
+  if (!f || !blobs) { g_err = "bad argument"; return MMP_E_ARG; }
+  const int G = f->hs.cfg.shard_count, me = f->hs.cfg.shard_rank;
+  mmp_fleet::Peers &pr = f->peers;
+  if (G < 2 || G > MAX_SHARDS || pr.max_batch <= 0) { g_err = "mmp_shard_ipc_export first"; return MMP_E_STATE; }
+  CK(cudaSetDevice(f->device));
+  std::lock_guard<std::mutex> g(f->ingest_mu);
+  for (int q = 0; q < G; q++) {
+    ShardIpcBlob bl;
+    memcpy(&bl, (const unsigned char *)blobs + (size_t)q * MMP_SHARD_IPC_BYTES, sizeof(bl));
+    if (bl.magic != 0x4d4d5049u || (int)bl.rank != q || (int)bl.count != G) { g_err = "blob of the wrong shard / fleet"; return MMP_E_ARG; }
+    if ((int32_t)bl.max_batch != pr.max_batch) { g_err = "shards exported different max_batch"; return MMP_E_ARG; }
+    if (q == me) continue;
+    if (bl.pid == (uint64_t)getpid()) {  // the peer fleet lives in this process: its pointers are valid here once peer access is on
+      int can = 0;
+      CK(cudaDeviceCanAccessPeer(&can, f->device, bl.device));
+      if (!can) { g_err = "no peer access between the shards' devices"; return MMP_E_CUDA; }
+      cudaError_t e = cudaDeviceEnablePeerAccess(bl.device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { g_err = cudaGetErrorString(e); return MMP_E_CUDA; }
+      (void)cudaGetLastError();
+      for (int k = 0; k < 4; k++) pr.peer_base[q][k] = (void *)(uintptr_t)bl.ptr[k];
+    } else {
+      for (int k = 0; k < 4; k++) {
+        if (pr.opened[q][k]) { cudaIpcCloseMemHandle(pr.peer_base[q][k]); pr.opened[q][k] = false; }
+        CK(cudaIpcOpenMemHandle(&pr.peer_base[q][k], bl.h[k], cudaIpcMemLazyEnablePeerAccess));
+        pr.opened[q][k] = true;
+      }
+    }
+  }
+  if (const char *t = getenv("MMP_SHARD_PEERS")) pr.off = atoi(t) == 0;
+  pr.ready = true;
+  return MMP_OK;
+}
+/* out[0] batches taken by the peer path, [1] row words read from peers' blocks, [2] result bytes stored to peers, [3] ready */
+int32_t mmp_shard_peer_stats(mmp_fleet *f, int64_t *out4) {
+  if (!f || !out4) { g_err = "bad argument"; return MMP_E_ARG; }
+  mmp_fleet::Peers &pr = f->peers;
+  unsigned long long words = 0;
+  if (pr.flags.p) { CK(cudaSetDevice(f->device)); CK(cudaMemcpy(&words, pr.flags.as<unsigned long long>() + MAX_SHARDS, 8, cudaMemcpyDeviceToHost)); }
+  out4[0] = pr.batches; out4[1] = (int64_t)words; out4[2] = pr.result_bytes; out4[3] = pr.ready && !pr.off ? 1 : 0;
+  return MMP_OK;
+}
+
 int32_t mmp_fleet_set_id_base(mmp_fleet *f, uint64_t id_base) {
   if (!f) { g_err = "null fleet"; return MMP_E_ARG; }
   f->id_base = id_base;
@@ -1396,7 +1651,8 @@ static int32_t commit_locked(mmp_fleet *f) {
   if (nm) CK(cudaMemcpyAsync(ds.models.p, lv.models.p, (size_t)nm * sizeof(mmp_model_row), cudaMemcpyDeviceToDevice, st));
   // exclusion bitmap in rank space: zero, then scatter the device-resident loaded/failed lists (one write pass)
   const int ST = h.excl_stride;  // words per stored row: the whole row, or this instance shard's block
-  CK(ds.excl.ensure((size_t)std::max(nm, 1) * ST * 4));
+  // (instance-sharded: sized for max_models rows from the first commit on, so that the block keeps the address its peers mapped)
+  CK(ds.excl.ensure((size_t)std::max(f->hs.cfg.shard_count > 1 ? std::max(nm, f->hs.cfg.max_models) : nm, 1) * ST * 4));
   if (nm) {
     CK(cudaMemsetAsync(ds.excl.p, 0, (size_t)nm * ST * 4, st));
     k_build_bitmap<<<(nm + 255) / 256, 256, 0, st>>>(ds.excl.as<uint32_t>(), lv.edges.as<int4>(), ds.rank_of.as<int32_t>(), nm, ST,

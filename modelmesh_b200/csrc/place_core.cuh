@@ -763,10 +763,12 @@ struct RowPtr {
 // its NVLink-mapped pointer.
 struct RowDealt {
   const uint32_t *front; const uint32_t *const *blocks; uint32_t front_words, block_words, stride; uint64_t model;
+  uint32_t me; mutable uint32_t remote;  // remote = words this lane read from a peer's block (NVLink traffic accounting)
   MMP_HD bool ok() const { return true; }
   MMP_HD uint32_t word(uint32_t wi) const {
     if (wi < front_words) return ldro(front + model * front_words + wi);
     const uint32_t g = wi / block_words;
+    if (g != me) remote++;
     return blocks[g][model * stride + (wi - g * block_words)];
   }
 };

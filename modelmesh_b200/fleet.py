@@ -164,6 +164,24 @@ class Fleet:
         stride = self._ck(self.lib.mmp_shard_words(self.h, C.byref(lo), C.byref(hi)))
         return lo.value, hi.value, stride
 
+    def shard_ipc_export(self, max_batch: int) -> bytes:
+        """This shard's blob for the peer-access path (mmp_shard_ipc_export): exchange by any means, then shard_ipc_import."""
+        buf = C.create_string_buffer(_lib.SHARD_IPC_BYTES)
+        self._ck(self.lib.mmp_shard_ipc_export(self.h, int(max_batch), buf))
+        return buf.raw
+
+    def shard_ipc_import(self, blobs: Sequence[bytes]):
+        """All shards' blobs ordered by shard rank (this shard's own included)."""
+        raw = b"".join(blobs)
+        assert len(raw) == _lib.SHARD_IPC_BYTES * len(blobs)
+        self._ck(self.lib.mmp_shard_ipc_import(self.h, C.c_char_p(raw)))
+
+    def shard_peer_stats(self):
+        """{batches, remote_row_words, result_bytes_to_peers, active} of the peer-access path."""
+        out = np.zeros(4, dtype=np.int64)
+        self._ck(self.lib.mmp_shard_peer_stats(self.h, out.ctypes.data_as(C.c_void_p)))
+        return {"batches": int(out[0]), "remote_row_words": int(out[1]), "result_bytes_to_peers": int(out[2]), "active": bool(out[3])}
+
     def shard_open_decisions(self) -> int:
         return int(self.lib.mmp_shard_open_decisions(self.h))
 

@@ -1,5 +1,7 @@
-"""Instance-sharded placement on real GPUs (one process per GPU, NCCL all-reduce(min) of the shard keys + row-gather
-pass): every shard must return exactly what the unsharded solver returns.  Needs >= 2 GPUs (gpurun --gpus 2); skipped on
+"""Instance-sharded placement on real GPUs, one process per GPU, both exchange paths: the collective one (NCCL
+all-reduce(min) of the shard keys + row-gather pass) and the peer-access one (decisions dealt across the shards, rows read
+from / results stored to peers' memory through CUDA IPC mappings, k_place_dealt): every shard must return exactly what the
+unsharded solver returns.  Needs >= 2 GPUs (gpurun --gpus 2); skipped on
 a single-GPU box.  The protocol itself is covered on CPU by test_instance_shards_cpu.py."""
 import os
 import socket
@@ -37,6 +39,25 @@ def _worker(rank, world, port, q):
                                     extra=sd.extra if len(sd.extra) else None)
                 results.append(out.copy())
             results.append(np.asarray([f.shard_open_decisions()], dtype=np.int64))
+            # ---- the peer-access path: blobs exchanged through the process group, the same batches dealt across the shards ----
+            blobs = [None] * world
+            dist.all_gather_object(blobs, f.shard_ipc_export(8192))
+            f.shard_ipc_import(blobs)
+            dist.barrier()
+            for rnd in range(2):
+                for plain in (True, False):
+                    sd = make_decisions(fl, 4000, seed, sweep=plain, plain=plain)
+                    out = f.place_batch(sd.dec, fl.now_ms, 77, fresh=sd.fresh if len(sd.fresh) else None,
+                                        extra=sd.extra if len(sd.extra) else None)
+                    results.append(out.copy())
+                if rnd == 0:  # a new epoch: the other snapshot's column blocks, through the pointers mapped at import
+                    row = fl.inst_rows[1].copy()
+                    row["used"] = row["capacity"] // 3
+                    row["count"] = 5
+                    f.instance_update(1, row)
+                    f.commit()
+            st = f.shard_peer_stats()
+            results.append(np.asarray([st["batches"], st["remote_row_words"], st["result_bytes_to_peers"], int(st["active"])], dtype=np.int64))
             dist.barrier()
             f.close()
         q.put((rank, results))
@@ -72,6 +93,7 @@ def test_sharded_matches_unsharded(product_lib, world):
         assert p.exitcode == 0
     k = 0
     total_open = 0
+    peer_words = 0
     for config, nm, ni, seed in CASES:
         fl = make_fleet(config, nm, ni, seed)
         ref_f = Fleet(fl.min_space_units, fl.min_churn_age_ms, fl.default_model_size_units, fl.n_instances, fl.n_models, lib=product_lib)
@@ -87,8 +109,30 @@ def test_sharded_matches_unsharded(product_lib, world):
             k += 1
         total_open += int(got[0][k][0])
         k += 1
+        for rnd in range(2):
+            for plain in (True, False):
+                sd = make_decisions(fl, 4000, seed, sweep=plain, plain=plain)
+                ref = ref_f.place_batch(sd.dec, fl.now_ms, 77, fresh=sd.fresh if len(sd.fresh) else None,
+                                        extra=sd.extra if len(sd.extra) else None)
+                for r in range(world):
+                    out = got[r][k]
+                    bad = np.nonzero((out["target"] != ref["target"]) | (out["n_candidates"] != ref["n_candidates"]))[0]
+                    assert len(bad) == 0, ("peers", config, rnd, plain, r, len(bad), bad[:5], out[bad[:5]], ref[bad[:5]])
+                k += 1
+            if rnd == 0:
+                row = fl.inst_rows[1].copy()
+                row["used"] = row["capacity"] // 3
+                row["count"] = 5
+                ref_f.instance_update(1, row)
+                ref_f.commit()
+        for r in range(world):
+            st = got[r][k]
+            assert st[0] == 4 and st[3] == 1, (config, r, st)  # all four batches went through the peer path
+            peer_words += int(st[1])
+        k += 1
         ref_f.close()
     assert total_open > 0  # the row-gather pass was exercised (C5 / MIX walks cross shard boundaries)
+    assert peer_words > 0  # ... and so were reads from peers' column blocks
 
 
 @pytest.mark.gpu
