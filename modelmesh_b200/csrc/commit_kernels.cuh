@@ -157,11 +157,11 @@ __global__ void k_slot_lists(const uint32_t *__restrict__ cand, const uint32_t *
   if (sl >= n_slots) return;
   const uint32_t *cx = (any_rs ? candx : cand) + (size_t)sl * row_words;
   uint16_t *out = nzw + (size_t)sl * row_words;
-  int k = 0, before = 0;
+  int k = 0, before = 0, skip = 0;
   for (int w = 0; w < word_lo; w++) before += __popc(candx[(size_t)sl * row_words + w]);
   for (int w = word_lo; w < word_hi; w++)
-    if (cx[w]) out[k++] = (uint16_t)w;
-  nz_n[sl] = k;
+    if (cx[w]) { out[k++] = (uint16_t)w; if (w < word_lo + MMP_LANE_WIN) skip++; }
+  nz_n[sl] = k | (skip << 24);
   for (; k < row_words; k++) out[k] = 0xffff;
   cand_before[sl] = before;
 }

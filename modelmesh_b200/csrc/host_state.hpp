@@ -451,10 +451,10 @@ class HostState {
     s.nz_n.assign((size_t)s.n_slots, 0);
     for (int32_t sl = 0; sl < s.n_slots; sl++) {
       const uint32_t *cx = (s.any_rs ? s.candx.data() : s.cand.data()) + (size_t)sl * RW;
-      int32_t k = 0;
+      int32_t k = 0, skip = 0;
       for (int32_t w = s.word_lo; w < s.word_hi; w++)
-        if (cx[w]) s.nzw[(size_t)sl * RW + k++] = (uint16_t)w;
-      s.nz_n[sl] = k;
+        if (cx[w]) { s.nzw[(size_t)sl * RW + k++] = (uint16_t)w; if (w < s.word_lo + MMP_LANE_WIN) skip++; }
+      s.nz_n[sl] = k | (skip << 24);  // (place_core.cuh nz_count / nz_skipped)
     }
     if (cfg.shard_count > 1) {
       s.nzw_full.assign((size_t)s.n_slots * RW, 0xffff);

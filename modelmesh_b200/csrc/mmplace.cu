@@ -321,23 +321,30 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_place(const SnapshotView s
 // per-decision instruction cost is ~85 warp instructions instead of ~450 for a cooperative tile (ncu, C3 sweep).
 // ---------------------------------------------------------------------------------------------------------------
 static constexpr int SHARD_FRONT_WORDS = 16;  // instance-sharded fleets: row words replicated on every shard (512 ranks: where almost every walk ends)
-static constexpr int LANE_WIN = 10;     // row words copied out of the landing stage per decision: the first LANE_WIN words of the
-                                        // decision's compressed word list (LaneTables::nzw); later steps read the row from L2
-static constexpr int LANE_STRIDE = 17;  // words per lane in the window buffer: LANE_WIN row words, LANE_WIN / 2 list-entry pairs, padding
-                                        // to an odd stride (bank-conflict free)
+static constexpr int LANE_WIN = MMP_LANE_WIN;  // row words copied out of the landing stage per decision: the first LANE_WIN words of the
+                                               // stored row (384 ranks); later steps go through the compressed word list and read the row from L2
+static constexpr int LANE_STRIDE = LANE_WIN + 1;  // words per lane in the window buffer (odd: bank-conflict free)
 static constexpr int LANE_BUDGET = 192;  // walk steps a lane may spend before handing its decision to the whole warp
+static constexpr int LANE_SLOTS = 64;    // type-constraint mask slots whose window words are kept in shared memory
 struct LaneLayout {
   uint32_t row_bytes, stride, stage_bytes, ns, warps;
   uint32_t off_bar, off_busy, off_uses, off_warp, per_warp;
+  uint32_t off_cx, off_p, off_full, off_csum, off_count, off_rows;  // the window part of the lane tables (LaneTables Tw)
   size_t total;
-  __host__ __device__ LaneLayout(int row_words, int ns_, int warps_) {
+  __host__ __device__ LaneLayout(int row_words, int ns_, int warps_, bool front) {
     row_bytes = (uint32_t)row_words * 4u; stride = row_bytes + 16u;  // + 16: lanes copying their windows out spread over the banks
     stage_bytes = (32u * stride + 127u) / 128u * 128u;
     ns = (uint32_t)ns_; warps = (uint32_t)warps_;
     off_bar = ns * stage_bytes; off_busy = off_bar + ns * 8u; off_uses = off_busy + ns * 4u;
     off_warp = (off_uses + ns * 4u + 127u) / 128u * 128u;
     per_warp = 32u * LANE_STRIDE * 4u + (uint32_t)((sizeof(DecisionCtx) + 15) / 16 * 16);
-    total = (size_t)off_warp + (size_t)warps * per_warp;
+    off_cx = (off_warp + warps * per_warp + 15u) / 16u * 16u;
+    off_p = off_cx + LANE_SLOTS * LANE_WIN * 4u;
+    off_full = off_p + LANE_SLOTS * LANE_WIN * 4u;
+    off_csum = off_full + ((LANE_WIN * 4u + 7u) / 8u) * 8u;
+    off_count = (off_csum + LANE_WIN * 8u + 15u) / 16u * 16u;
+    off_rows = off_count + LANE_WIN * 32u * 4u;
+    total = front ? (size_t)off_rows + (size_t)LANE_WIN * 32u * sizeof(RankRow) : (size_t)off_cx;
   }
 };
 
@@ -354,7 +361,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotVie
                                                                int emit_keys, int shard_rank, const int32_t *__restrict__ orig_id, int budget) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int RW = s.excl_stride;  // words per stored row (the whole row unless the fleet is instance-sharded)
-  const LaneLayout lay(RW, ns, WARPS);
+  const LaneLayout lay(RW, ns, WARPS, true);
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + lay.off_bar);
   int *ticket = reinterpret_cast<int *>(smem_raw + lay.off_busy);               // next stage ticket of this block
@@ -367,6 +374,38 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotVie
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   const int nb = (n + 31) >> 5;
+  // ---- the window part of the lane tables in shared memory (with the SM's shared memory given to the landing stages the
+  // L1 is too small to keep them resident: every in-window gather would be an L2 round trip) ----
+  uint32_t *f_cx = reinterpret_cast<uint32_t *>(smem_raw + lay.off_cx), *f_p = reinterpret_cast<uint32_t *>(smem_raw + lay.off_p);
+  uint32_t *f_full = reinterpret_cast<uint32_t *>(smem_raw + lay.off_full);
+  WordSumI *f_csum = reinterpret_cast<WordSumI *>(smem_raw + lay.off_csum);
+  int32_t *f_count = reinterpret_cast<int32_t *>(smem_raw + lay.off_count);
+  RankRow *f_rows = reinterpret_cast<RankRow *>(smem_raw + lay.off_rows);
+  const int WS = s.word_lo;
+  const uint32_t win_words = (uint32_t)min(LANE_WIN, s.word_hi - s.word_lo);
+  const bool front = nb >= 64;  // tiny launches read the snapshot directly
+  if (front) {
+    const int nsl = min(s.n_slots, LANE_SLOTS);
+    const uint32_t *gcx = s.any_rs ? s.candx : s.cand;
+    for (int i = threadIdx.x; i < nsl * LANE_WIN; i += blockDim.x) {
+      const int sl = i / LANE_WIN, w = i - sl * LANE_WIN;
+      const bool in = (uint32_t)w < win_words;
+      f_cx[i] = in ? gcx[(size_t)sl * s.row_words + WS + w] : 0u;
+      f_p[i] = in ? s.pref[(size_t)sl * s.row_words + WS + w] : 0u;
+    }
+    for (int w = threadIdx.x; w < LANE_WIN; w += blockDim.x) {
+      const bool in = (uint32_t)w < win_words;
+      f_full[w] = in ? s.full[WS + w] : 0u;
+      f_csum[w] = in ? s.csum[WS + w] : WordSumI{0, 0};
+    }
+    for (int i = threadIdx.x; i < LANE_WIN * 32; i += blockDim.x) {
+      const int r = WS * 32 + i;
+      const bool in = (uint32_t)(i >> 5) < win_words && r < s.n_ranks;
+      f_count[i] = in ? s.count_col[r] : 0;
+      RankRow z; z.lru = 0; z.rem = 0; z.count = 0; z.rpm = 0; z.idx = -1; z.flags = 0;
+      f_rows[i] = in ? s.rows[r] : z;
+    }
+  }
   __syncthreads();
   // batches of 32 decisions are dealt round-robin to the grid's warps (consecutive batches to the warps of one block)
   const int gw = blockIdx.x * WARPS + wib, nw = gridDim.x * WARPS;
@@ -436,17 +475,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotVie
     LANE_T(1);
     // ---- the rest of this batch's context while its rows are in flight ----
     if (s.word_lo == 0 && valid) prepare_ctx_b(s, d, ca, fresh, n_fresh, extra, c);
-    // the compressed word list of the decision's type slot: the first LANE_WIN entries (two 16-byte loads) say which row
-    // words to keep when the stage is handed on
-    const int slot = c.slot >= 0 ? ctx_slot(c) : 0;
-    const LaneTables T = lane_tables_global(s, slot);
-    const uint32_t win_words = min((uint32_t)LANE_WIN, T.nz_n);
-    uint32_t wl[8];  // nzw[0..16) as 8 x 2 u16 (the first LANE_WIN are kept)
-    {
-      const uint4 *np = reinterpret_cast<const uint4 *>(T.nzw);  // rows of nzw are row_words u16 = a multiple of 64 bytes
-      const uint4 n0 = __ldg(np), n1 = __ldg(np + 1);
-      wl[0] = n0.x; wl[1] = n0.y; wl[2] = n0.z; wl[3] = n0.w; wl[4] = n1.x; wl[5] = n1.y; wl[6] = n1.z; wl[7] = n1.w;
-    }
     if (timing && __shfl_xor_sync(0xffffffffu, c.slot ^ (int)c.self_bits, 1) == 0x7fffffff) tsum[2]++;  // consume the gathers before the timestamp
     LANE_T(2);
     while (!mbar_try_wait(&bars[st], parity)) {}
@@ -455,15 +483,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotVie
     uint32_t self_eword = 0;
     {
       uint32_t *w = win + lane * LANE_STRIDE;
-      const uint32_t WS_ = (uint32_t)s.word_lo;
       if (!skip) {
 #pragma unroll
-        for (int j = 0; j < LANE_WIN; j++) {
-          const uint32_t wi = (wl[j >> 1] >> ((j & 1) * 16)) & 0xffffu;
-          if ((uint32_t)j < win_words) w[j] = my_row[wi - WS_];
+        for (int j = 0; j < LANE_WIN / 4; j++) {
+          if ((uint32_t)(j * 4) < win_words) {  // (stored rows are a multiple of 4 words: a 16-byte read stays inside the row)
+            const uint4 q = *reinterpret_cast<const uint4 *>(my_row + j * 4);
+            w[j * 4] = q.x; w[j * 4 + 1] = q.y; w[j * 4 + 2] = q.z; w[j * 4 + 3] = q.w;
+          }
         }
-#pragma unroll
-        for (int j = 0; j < LANE_WIN / 2; j++) w[LANE_WIN + j] = wl[j];  // the window's list entries (u16 pairs)
       }
       const int sw = c.self_rank >> 5;
       if (!skip && c.self_rank >= 0 && sw >= s.word_lo && sw < s.word_hi) self_eword = my_row[sw - s.word_lo];
@@ -483,8 +510,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotVie
     DecideOut o;
     bool handled = true;
     const uint64_t my_id = pick_id(d, id_base + (uint64_t)(orig_id ? (valid ? orig_id[b * 32 + lane] : 0) : b * 32 + lane));
+    const int slot = c.slot >= 0 ? ctx_slot(c) : 0;
+    const LaneTables T = lane_tables_global(s, slot);
+    LaneTables Tw = T;
+    if (front) {  // tables indexed by absolute row word / rank: bias the shared-memory copies by the window's first word
+      if (slot < LANE_SLOTS) { Tw.cx = f_cx + slot * LANE_WIN - WS; Tw.p = f_p + slot * LANE_WIN - WS; }
+      Tw.full = f_full - WS; Tw.csum = f_csum - WS; Tw.count_col = f_count - WS * 32; Tw.rows = f_rows - WS * 32;
+    }
     if ((mode & 1) == 0)
-      handled = decide_stream(s, T, c, valid && !skip, win + lane * LANE_STRIDE, win + lane * LANE_STRIDE + LANE_WIN, win_words, RowPtr{s.excl + (size_t)m * RW, (uint32_t)s.word_lo}, self_eword,
+      handled = decide_stream(s, Tw, T, c, valid && !skip, win + lane * LANE_STRIDE, win_words, RowPtr{s.excl + (size_t)m * RW, (uint32_t)s.word_lo}, self_eword,
                               now, seed, my_id, WarpVote(), o, budget);
     else { o.target = (int32_t)(self_eword & 1u) - 1; o.n_candidates = 0; }  // MMP_LANE_MODE=1: stream-only probe (no decisions)
     // ---- what the lane routine declined: the whole warp redoes it, reading the row from global memory (L2) ----
@@ -558,7 +592,7 @@ __global__ void __launch_bounds__(32) k_place_small(const SnapshotView s_arg, co
   if (valid && c.self_rank >= 0) self_eword = __ldg(row + (c.self_rank >> 5));
   DecideOut o;
   const uint64_t my_id = pick_id(d, id_base + (uint64_t)i);
-  const bool handled = decide_stream(s, T, c, valid, nullptr, nullptr, 0u, RowPtr{row, (uint32_t)s.word_lo}, self_eword, now, seed, my_id, WarpVote(), o, budget);
+  const bool handled = decide_stream(s, T, T, c, valid, nullptr, 0u, RowPtr{row, (uint32_t)s.word_lo}, self_eword, now, seed, my_id, WarpVote(), o, budget);
   uint32_t pending = __ballot_sync(0xffffffffu, valid && !handled);
   while (pending) {
     const int l = __ffs((int)pending) - 1;
@@ -617,7 +651,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_place_dealt(const SnapshotView s
   LaneTables T = lane_tables_global(s, c.slot >= 0 ? ctx_slot(c) : 0);
   {
     const int slot = c.slot >= 0 ? ctx_slot(c) : 0;
-    T.nzw = nzw_full + (size_t)slot * RW; T.nz_n = (uint32_t)nz_n_full[slot];
+    T.nzw = nzw_full + (size_t)slot * RW; T.nz_n = nz_count(nz_n_full[slot]); T.nz_skip = 0;
   }
   RowDealt row{front, P.blocks, (uint32_t)front_words, (uint32_t)s.excl_stride, (uint32_t)s.excl_stride, (uint64_t)m, (uint32_t)me, 0u};
   uint32_t self_eword = 0;
@@ -625,7 +659,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_place_dealt(const SnapshotView s
   DecideOut o;
   o.target = MMP_TARGET_NONE; o.n_candidates = 0;
   const uint64_t my_id = pick_id(d, id_base + (uint64_t)i);
-  const bool handled = decide_stream(s, T, c, valid, nullptr, nullptr, 0u, row, self_eword, now, seed, my_id, WarpVote(), o, budget);
+  const bool handled = decide_stream(s, T, T, c, valid, nullptr, 0u, row, self_eword, now, seed, my_id, WarpVote(), o, budget);
   uint32_t pending = __ballot_sync(0xffffffffu, valid && !handled);
   while (pending) {  // the cooperative general routine over the whole row, assembled in shared memory
     const int l = __ffs((int)pending) - 1;
@@ -986,7 +1020,7 @@ static cudaError_t launch_place_t(mmp_fleet *f, const PlaceArgs &a, cudaStream_t
 // stages x warps for a stored row width: as many 32-row landing stages as fit beside the warps' window buffers
 static bool lanes_geometry(int row_words, int warps, int &ns) {
   for (ns = 8; ns >= 2; ns--)
-    if (LaneLayout(row_words, ns, warps).total <= (size_t)227 * 1024) return true;
+    if (LaneLayout(row_words, ns, warps, true).total <= (size_t)227 * 1024) return true;
   return false;
 }
 
@@ -994,7 +1028,7 @@ template <int WARPS>
 static cudaError_t launch_place_lanes(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st, int ns) {
   static std::atomic<bool> attr_set[64];  // function attributes are per device
   if (f->lane_stages >= 2 && f->lane_stages < ns) ns = f->lane_stages;
-  const LaneLayout lay(a.s.excl_stride, ns, WARPS);  // (instance-sharded rows are short: well under half an SM's shared memory)
+  const LaneLayout lay(a.s.excl_stride, ns, WARPS, true);  // (instance-sharded rows are short: well under half an SM's shared memory)
   auto kern = k_place_lanes<WARPS>;
   if (!attr_set[f->device & 63].load()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -55,6 +55,18 @@ MMP_HD RankRow load_row(const RankRow *p) {
   return *p;
 #endif
 }
+MMP_HD RankRow load_row_any(const RankRow *p) {  // generic address space (shared or global)
+#if defined(__CUDA_ARCH__)
+  const int4 a = reinterpret_cast<const int4 *>(p)[0], b = reinterpret_cast<const int4 *>(p)[1];
+  RankRow r;
+  r.lru = (int64_t)(((uint64_t)(uint32_t)a.y << 32) | (uint32_t)a.x);
+  r.rem = (int64_t)(((uint64_t)(uint32_t)a.w << 32) | (uint32_t)a.z);
+  r.count = b.x; r.rpm = b.y; r.idx = b.z; r.flags = (uint32_t)b.w;
+  return r;
+#else
+  return *p;
+#endif
+}
 struct WordSumI { int32_t lo, hi; };  // min/max count over the 32 ranks of a bitmap word
 struct WordSumL { int64_t lo, hi; };  // min/max lruTime
 struct FreshRow { int64_t lru, rem; int32_t count, rpm; };  // getFreshInstanceRecord() (MM:5369-5386), what the walk reads of it
@@ -709,6 +721,8 @@ MMP_HD bool decide_fast(const SnapshotView &s, const DecisionCtx &c, const uint3
 // the filtered set F = cand & ~excl, so every walk of decide_stream steps through the list instead of through the row:
 // on dense masks (C3: the list is 0, 1, 2, ...) nothing changes, on sparse ones (C5: a handful of candidates per type among
 // 10 000 instances) a walk that crossed 50-300 empty words becomes a few steps.
+// row words of a decision's window in k_place_lanes (shared with the commit path: nz_skip is computed for this width)
+#define MMP_LANE_WIN 12
 struct LaneTables {
   const uint32_t *cx, *p;   // this decision's candidate (replicaset filter applied) and preferred mask rows, by absolute row word
   const uint32_t *full;
@@ -717,13 +731,17 @@ struct LaneTables {
   const RankRow *rows;
   const uint16_t *nzw;      // [nz_n] ascending row-word indices with cx[w] != 0, all in [word_lo, word_hi)
   uint32_t nz_n;
+  uint32_t nz_skip;         // list entries that lie inside the caller's window (k_place_lanes: entries < word_lo + MMP_LANE_WIN)
 };
+// SnapshotView::nz_n packs both: entries in the low 24 bits, nz_skip above
+MMP_HD uint32_t nz_count(int32_t packed) { return (uint32_t)packed & 0xffffffu; }
+MMP_HD uint32_t nz_skipped(int32_t packed) { return (uint32_t)packed >> 24; }
 MMP_HD LaneTables lane_tables_global(const SnapshotView &s, int slot) {
   LaneTables t;
   const size_t so = (size_t)slot * (size_t)s.row_words;
   t.cx = (s.any_rs ? s.candx : s.cand) + so; t.p = s.pref + so; t.full = s.full; t.csum = s.csum; t.count_col = s.count_col;
   t.rows = s.rows;
-  t.nzw = s.nzw + so; t.nz_n = (uint32_t)s.nz_n[slot];
+  t.nzw = s.nzw + so; t.nz_n = nz_count(s.nz_n[slot]); t.nz_skip = nz_skipped(s.nz_n[slot]);
   return t;
 }
 // read-only table loads of the lane routine (ld.global.nc on the device)
@@ -742,6 +760,54 @@ MMP_HD WordSumI ldro_sum(const WordSumI *p) {
   return *p;
 #endif
 }
+
+// how the lane routine reads its tables: inside the window through plain loads (k_place_lanes points them at shared-memory
+// copies of the tables' window part), beyond it through the read-only path from the snapshot's own arrays
+struct TabWin {
+  const LaneTables &t;
+  MMP_HD uint32_t cx(uint32_t wi) const { return t.cx[wi]; }
+  MMP_HD uint32_t p(uint32_t wi) const { return t.p[wi]; }
+  MMP_HD uint32_t full(uint32_t wi) const { return t.full[wi]; }
+  MMP_HD WordSumI csum(uint32_t wi) const { return t.csum[wi]; }
+  MMP_HD uint32_t ge_mask(uint32_t wi, int32_t lim) const {  // bit j: count of rank wi*32 + j >= lim (32 counts, zero-padded past the last rank)
+    uint32_t vm = 0;
+#if defined(__CUDA_ARCH__)
+    const int4 *cc = reinterpret_cast<const int4 *>(t.count_col + (size_t)wi * 32u);
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) {
+      const int4 qq = cc[jj];
+      vm |= ((qq.x >= lim ? 1u : 0u) | (qq.y >= lim ? 2u : 0u) | (qq.z >= lim ? 4u : 0u) | (qq.w >= lim ? 8u : 0u)) << (4 * jj);
+    }
+#else
+    const int32_t *cc = t.count_col + (size_t)wi * 32u;
+    for (int jj = 0; jj < 32; jj++) vm |= (cc[jj] >= lim ? 1u : 0u) << jj;
+#endif
+    return vm;
+  }
+};
+struct TabGlob {
+  const LaneTables &t;
+  MMP_HD uint32_t cx(uint32_t wi) const { return ldro(t.cx + wi); }
+  MMP_HD uint32_t p(uint32_t wi) const { return ldro(t.p + wi); }
+  MMP_HD uint32_t full(uint32_t wi) const { return ldro(t.full + wi); }
+  MMP_HD WordSumI csum(uint32_t wi) const { return ldro_sum(t.csum + wi); }
+  MMP_HD uint32_t ge_mask(uint32_t wi, int32_t lim) const {
+    uint32_t vm = 0;
+#if defined(__CUDA_ARCH__)
+    const int4 *cc = reinterpret_cast<const int4 *>(t.count_col + (size_t)wi * 32u);
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) {
+      const int4 qq = __ldg(cc + jj);
+      vm |= ((qq.x >= lim ? 1u : 0u) | (qq.y >= lim ? 2u : 0u) | (qq.z >= lim ? 4u : 0u) | (qq.w >= lim ? 8u : 0u)) << (4 * jj);
+    }
+#else
+    const int32_t *cc = t.count_col + (size_t)wi * 32u;
+    for (int jj = 0; jj < 32; jj++) vm |= (cc[jj] >= lim ? 1u : 0u) << jj;
+#endif
+    return vm;
+  }
+};
+
 
 // Instance-sharded early-out: an entry of the filtered set in a LOWER shard beats anything this shard can offer
 // (min-loc under PLACEMENT_ORDER), and one must exist when the slot has more candidates below this shard's range than
@@ -781,20 +847,21 @@ struct WarpVote { MMP_D bool any(bool p) const { return __any_sync(0xffffffffu, 
 
 // The common case of getNext for ONE DECISION PER LANE (k_place_lanes), written so that the 32 lanes of a warp stay
 // converged: every phase is a walk whose loops are left by a warp vote, bodies are predicated on a per-lane state, and the
-// scalar work between the walks is straight-line.  A walk steps through the slot's compressed word list (LaneTables::nzw):
-// step k looks at row word W(k) = nzw[k], the k-th word that holds any candidate of the decision's type.  Phases:
+// scalar work between the walks is straight-line.  Phases:
 //   A   first entry of F = cand & ~excl & ~extra (MM:4806)
 //   A'  non-simple (a), MM:4828-4852: the first later entry that is preferred or full
 //   B   the shortlist walk (MM:4901-4937): first member of S that fails its test; a word whose count summary is
 //       "mixed" is evaluated exactly (32 counts) by the lanes that stop on one
 //   C   the hash-indexed pick (MM:4981-4986): k-th member of the shortlist
-// Every walk runs as two loops.  INSIDE THE WINDOW (steps k < win_words) a step reads its list entry and its row word from
-// the lane's window buffer (ewin[k] = row word W(k), wwin = the entries as u16 pairs: k_place_lanes fills both when it hands
-// the TMA landing stage on) -- two shared-memory loads, no bookkeeping; this is where every decision of a C3-like fleet
-// ends.  BEYOND THE WINDOW the list and the row are read from global memory (row: the row has just been streamed, so it
-// is an L2 hit) in chunks of 8 steps held in registers, refilled for all walking lanes at the same iteration (one vote), so
-// that a long walk (C5: 100+ steps over sparse candidate masks) pays one L2 round trip per 8 steps; with !row.ok()
-// the lane's attempt ends at the window's edge.
+// Every walk runs as two loops.  INSIDE THE WINDOW (steps k < win_words) step k is row word word_lo + k, dense: the word
+// comes from the lane's window buffer (ewin[k]: k_place_lanes copies the first MMP_LANE_WIN words of the row out of the
+// TMA landing stage when it hands the stage on) and the tables from Tw, which k_place_lanes points at shared-memory copies
+// of the tables' window part -- two shared-memory loads per step, no bookkeeping; this is where every decision of a
+// C3-like fleet ends.  BEYOND THE WINDOW a walk steps through the slot's compressed word list from its first entry past the
+// window (list entry k + koff): the list and the row are read from global memory (row: the row has just been streamed, so
+// it is an L2 hit) in chunks of 8 steps held in registers, refilled for all walking lanes at the same iteration (one vote),
+// so that a long walk (C5: 100+ steps over sparse candidate masks) pays one L2 round trip per 8 steps; with !row.ok() the
+// lane's attempt ends at the window's edge.
 // Same semantics and quirks as decide_ctx (N2: the non-self test reads the caller's fresh record).  Returns false --
 // and the caller redoes the decision with the cooperative general routine -- for everything outside the common case:
 // malformed decision, more than LANE_MAX_EXTRA extra excludes, no entry / best full (replicaset retry, non-simple (b)), or
@@ -802,8 +869,8 @@ struct WarpVote { MMP_D bool any(bool p) const { return __any_sync(0xffffffffu, 
 // self_eword = the row word that holds self's bit (anywhere in the row).  Must be called by every lane of the vote group
 // (active = false for lanes without a decision).
 template <class V, class R>
-MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const DecisionCtx &c, bool active, const uint32_t *ewin,
-                          const uint32_t *wwin, uint32_t win_words, const R &row, uint32_t self_eword, int64_t now, uint64_t seed,
+MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &Tw, const LaneTables &T, const DecisionCtx &c, bool active,
+                          const uint32_t *ewin, uint32_t win_words, const R &row, uint32_t self_eword, int64_t now, uint64_t seed,
                           uint64_t decision_id, const V &vote, DecideOut &o, int32_t budget) {
   o.target = MMP_TARGET_NONE; o.n_candidates = 0; o.best = -1; o.n_remaining = 0; o.pick_index = 0; o.flags = 0;
   o.cut_rank = (int32_t)NONE_RANK; o.best_rank = -1; o.first_rank = -1;
@@ -811,8 +878,14 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
   const bool open_end = WE < NW;
   bool live = active && c.slot >= 0 && c.d.extra_n <= LANE_MAX_EXTRA;
   const mmp_decision_in &d = c.d;
-  const uint32_t *CX = T.cx, *P = T.p;
-  const uint32_t NZ = T.nz_n;
+  // virtual step positions: k < win_words is row word WS + k (window buffer, tables Tw); k >= win_words is list entry
+  // k + koff (tables T): the list entries inside the window are skipped, the walk goes on with the first entry beyond it
+  const uint32_t kz = win_words == 0 ? 0u : T.nz_skip;  // (the caller's window is the one nz_skip was counted for)
+  const uint32_t koff = kz - win_words;                 // (mod 2^32)
+  const uint32_t NZ = win_words + (T.nz_n - kz);        // virtual length of the walk
+  const TabWin AW{Tw};
+  const TabGlob AG{T};
+  const uint32_t win_end = WS + win_words;
   const bool favour_self = (d.flags & MMP_DF_FAVOUR_SELF) != 0;
   const int32_t self_rank = c.self_rank;
   const FreshRow fr = c.fr;
@@ -824,7 +897,8 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
     for (int e = 0; e < LANE_MAX_EXTRA; e++) { const int32_t r = c.xr[e]; if (r >= 0 && ((uint32_t)r >> 5) == wi) m |= 1u << (r & 31); }
     return m;
   };
-  auto pbit = [&](uint32_t r) -> bool { return (ldro(P + (r >> 5)) >> (r & 31)) & 1u; };
+  auto pbit = [&](uint32_t r) -> bool { const uint32_t w = r >> 5; return ((w < win_end ? AW.p(w) : AG.p(w)) >> (r & 31)) & 1u; };
+  auto row_of = [&](uint32_t r) -> RankRow { return (r >> 5) < win_end ? load_row_any(Tw.rows + r) : load_row(T.rows + r); };
   // ---- beyond the window: a chunk of 8 consecutive steps [base, base + 8) in registers ----
   uint32_t base = 0xfffffff0u;  // no chunk loaded
   uint32_t wq[4] = {0, 0, 0, 0};
@@ -839,7 +913,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
 #pragma unroll
     for (uint32_t j = 0; j < 4; j++) {
       const uint32_t k0 = k + 2 * j, k1 = k0 + 1;
-      const uint32_t lo16 = k0 < NZ ? (uint32_t)ldro(T.nzw + k0) : 0xffffu, hi16 = k1 < NZ ? (uint32_t)ldro(T.nzw + k1) : 0xffffu;
+      const uint32_t lo16 = k0 < NZ ? (uint32_t)ldro(T.nzw + (k0 + koff)) : 0xffffu, hi16 = k1 < NZ ? (uint32_t)ldro(T.nzw + (k1 + koff)) : 0xffffu;
       wq[j] = lo16 | (hi16 << 16);
     }
 #pragma unroll
@@ -859,7 +933,8 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
     if (WALKING && K < win_words) {                                                                                        \
       if (CHARGE && left <= 0) { WALKING = false; live = false; }                                                          \
       else {                                                                                                               \
-        const uint32_t wi = (wwin[K >> 1] >> ((K & 1u) * 16u)) & 0xffffu, e = ewin[K];                                     \
+        const uint32_t wi = WS + K, e = ewin[K];                                                                           \
+        const TabWin &A = AW;                                                                                              \
         bool go_;                                                                                                          \
         BODY;                                                                                                              \
         if (go_) { K++; if (CHARGE) left--; } else WALKING = false;                                                        \
@@ -877,6 +952,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
         else if (CHARGE && left <= 0) { WALKING = false; live = false; }                                                   \
         else {                                                                                                             \
           const uint32_t wi = wsel(K - base), e = esel(K - base);                                                          \
+          const TabGlob &A = AG;                                                                                           \
           bool go_;                                                                                                        \
           BODY;                                                                                                            \
           if (go_) { K++; if (CHARGE) left--; } else WALKING = false;                                                      \
@@ -892,7 +968,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
     uint32_t k = 0;
     bool walking = live, ended = false;
     MMP_WALK(k, walking, ended, true, {
-      uint32_t x = ldro(CX + wi) & ~e;
+      uint32_t x = A.cx(wi) & ~e;
       if (has_x) x &= ~xmask(wi);
       if (x) { b = wi * 32u + (uint32_t)ffs32(x); kb = k; }
       go_ = x == 0;
@@ -906,7 +982,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
   int32_t best_count = 0, best_rpm = 0, best_idx = -1;
   uint32_t best_rank = b, lo = b, hi = NONE_RANK, k_lo = kb;
   if (live) {
-    rb = load_row(T.rows + b);
+    rb = row_of(b);
     us = rb.idx == d.self;
     best_rem = us ? fr.rem : rb.rem; best_count = us ? fr.count : rb.count; best_rpm = us ? fr.rpm : rb.rpm; best_idx = rb.idx;
     if (best_rem < s.min_space) live = false;  // best full (MM:4811): general routine
@@ -921,7 +997,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
     uint32_t k = kb;
     bool walking = live && !simple, ended = false;
     MMP_WALK(k, walking, ended, true, {
-      uint32_t x = ldro(CX + wi) & ~e & (ldro(P + wi) | ldro(T.full + wi));
+      uint32_t x = A.cx(wi) & ~e & (A.p(wi) | A.full(wi));
       if (has_x) x &= ~xmask(wi);
       if (wi == b_w) x &= m_b;
       if (x) { r1 = wi * 32u + (uint32_t)ffs32(x); k1 = k; }
@@ -933,7 +1009,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
   if (live && !simple) {
     if (r1 == NONE_RANK) open = open_end;  // else: neither kind follows, "no preference" logic over the whole remainder
     else if (pbit(r1)) {
-      const RankRow rp = load_row(T.rows + r1);
+      const RankRow rp = row_of(r1);
       best_rank = r1; best_idx = rp.idx; best_rem = rp.rem; best_count = rp.count; best_rpm = rp.rpm;
       us = rp.idx == d.self;
       lo = r1; k_lo = k1; use_pref = true;
@@ -971,12 +1047,12 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
   // a word of S': only the word that holds lo and the one that holds lim are cut (none beyond lim's is ever visited)
   const uint32_t lo_w = lo >> 5, m_lo = mask_above(lo_w * 32u, lo);
   const uint32_t lim_w = lim >> 5, m_lim = mask_below(lim_w * 32u, lim);  // lim == NONE_RANK: lim_w is no real word
-  auto Sw = [&](uint32_t wi, uint32_t e) -> uint32_t {
-    uint32_t m = ldro(CX + wi) & ~e;
+  auto Sw = [&](const auto &A, uint32_t wi, uint32_t e) -> uint32_t {
+    uint32_t m = A.cx(wi) & ~e;
     if (has_x) m &= ~xmask(wi);
     if (wi == lo_w) m &= m_lo;
     if (wi == lim_w) m &= m_lim;
-    return use_pref ? (m & ldro(P + wi)) : m;
+    return use_pref ? (m & A.p(wi)) : m;
   };
   // ---- B: first member of S' that fails its walk test, counting the members before it ----
   uint32_t cut_others = NONE_RANK, n_in = 0;
@@ -987,24 +1063,13 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
       go_ = true;
       if (wi >= stop_w) { ended = true; go_ = false; }  // the walk's natural end (everything at or beyond lim)
       else {
-        const uint32_t x = Sw(wi, e);
+        const uint32_t x = Sw(A, wi, e);
         int cls = 0;  // 0: no member fails, 1: every member (but a passing self) fails, 2: look at the counts
         uint32_t v = x;
         if (c_self) { if (wi == sw_) v &= ~sb_; cls = v ? 1 : 0; }
-        else if (x) { const WordSumI m = ldro_sum(T.csum + wi); cls = !cv(m.hi) ? 0 : (cv(m.lo) ? 1 : 2); }
+        else if (x) { const WordSumI m = A.csum(wi); cls = !cv(m.hi) ? 0 : (cv(m.lo) ? 1 : 2); }
         if (cls == 2) {  // exact evaluation of a mixed word: 32 counts, zero-padded past the last rank
-          uint32_t vm = 0;
-#if defined(__CUDA_ARCH__)
-          const int4 *cc = reinterpret_cast<const int4 *>(T.count_col + (size_t)wi * 32u);
-#pragma unroll
-          for (int jj = 0; jj < 8; jj++) {
-            const int4 qq = __ldg(cc + jj);
-            vm |= ((cv(qq.x) ? 1u : 0u) | (cv(qq.y) ? 2u : 0u) | (cv(qq.z) ? 4u : 0u) | (cv(qq.w) ? 8u : 0u)) << (4 * jj);
-          }
-#else
-          const int32_t *cc = T.count_col + (size_t)wi * 32u;
-          for (int jj = 0; jj < 32; jj++) vm |= (cv(cc[jj]) ? 1u : 0u) << jj;
-#endif
+          const uint32_t vm = A.ge_mask(wi, cv_min);
           v = vm & x;
           cls = v ? 1 : 0;
         }
@@ -1057,7 +1122,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
     uint32_t k = k_lo;
     bool walking = sel, ended = false;
     MMP_WALK(k, walking, ended, false, {
-      uint32_t x = Sw(wi, e);
+      uint32_t x = Sw(A, wi, e);
       if (wi == cut_w) x &= m_cut;
       if (drop_self && wi == sw_) x &= ~sb_;
       const uint32_t n = (uint32_t)popc32(x);
@@ -1074,7 +1139,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &T, const Deci
   o.best = best_idx; o.best_rank = (int32_t)best_rank;
   if (open) { o.flags = MMP_TF_OPEN; return true; }
   if (!done) {
-    const int32_t cidx = chosen_rank == best_rank ? best_idx : ((int32_t)chosen_rank == self_rank ? d.self : ldro(&T.rows[chosen_rank].idx));
+    const int32_t cidx = chosen_rank == best_rank ? best_idx : ((int32_t)chosen_rank == self_rank ? d.self : ((chosen_rank >> 5) < win_end ? Tw.rows[chosen_rank].idx : ldro(&T.rows[chosen_rank].idx)));
     o.target = (!favour_self && cidx == d.self) ? MMP_TARGET_SELF : cidx;
     o.n_candidates = ccount;
     o.n_remaining = remaining; o.pick_index = (int32_t)index;

@@ -30,7 +30,7 @@ static thread_local std::string g_err;
 static int g_window = 32;  // fast-path window width under test (32: warp tile, 16: half-warp tile); 1: lane-per-decision shape
 static int g_lane_budget = 48;  // CoopLane walk budget (row words) when g_window == 1
 static int g_lane_global = 1;  // decide_stream: steps beyond the window may read the row itself (the kernel's second chance: L2)
-static int g_lane_window = 10;  // decide_stream: row words available to a lane (LANE_WIN of k_place_lanes: the window copied out of the landing stage)
+static int g_lane_window = MMP_LANE_WIN;  // decide_stream: row words available to a lane (LANE_WIN of k_place_lanes: the window copied out of the landing stage)
 static long g_bails = 0, g_lane_decisions = 0;
 
 extern "C" {
@@ -151,15 +151,14 @@ int32_t mmp_place_batch_trace(mmp_fleet *f, const mmp_decision_in *in, int32_t n
     if (win == 2 && !cand_mask) {  // the lockstep lane routine of k_place_lanes (one decision per lane), general routine when it declines
       uint32_t self_eword = 0;
       if (cx.self_rank >= 0 && (cx.self_rank >> 5) >= v.word_lo && (cx.self_rank >> 5) < v.word_hi) self_eword = erow[(cx.self_rank >> 5) - v.word_lo];
-      // the lane sees a COPY of exactly the window (as k_place_lanes gives it): row words W(0..ww) of the slot's compressed
-      // word list; an over-read is a heap overflow under ASAN
-      const LaneTables T = lane_tables_global(v, cx.slot >= 0 ? ctx_slot(cx) : 0);
-      const uint32_t ww = (uint32_t)std::min<int64_t>(g_lane_window, (int64_t)T.nz_n);
-      std::vector<uint32_t> window(ww);
-      for (uint32_t k = 0; k < ww; k++) window[k] = erow[T.nzw[k] - v.word_lo];
-      std::vector<uint32_t> wwin((ww + 1) / 2 + 1, 0u);  // the window's list entries as u16 pairs (what k_place_lanes stores beside the row words)
-      for (uint32_t k = 0; k < ww; k++) wwin[k >> 1] |= (uint32_t)T.nzw[k] << ((k & 1u) * 16u);
-      done = decide_stream(v, T, cx, true, window.data(), wwin.data(), ww, RowPtr{g_lane_global ? erow : nullptr, (uint32_t)v.word_lo}, self_eword, now_ms, seed,
+      // the lane sees a COPY of exactly the window (as k_place_lanes gives it): the first ww words of the stored row; an
+      // over-read is a heap overflow under ASAN
+      LaneTables T = lane_tables_global(v, cx.slot >= 0 ? ctx_slot(cx) : 0);
+      const uint32_t ww = (uint32_t)std::min<int64_t>(g_lane_window, (int64_t)(v.word_hi - v.word_lo));
+      std::vector<uint32_t> window(erow, erow + ww);
+      T.nz_skip = 0;  // list entries inside THIS window (k_place_lanes uses the count stored for its MMP_LANE_WIN words)
+      while (T.nz_skip < T.nz_n && (uint32_t)T.nzw[T.nz_skip] < (uint32_t)v.word_lo + ww) T.nz_skip++;
+      done = decide_stream(v, T, T, cx, true, window.data(), ww, RowPtr{g_lane_global ? erow : nullptr, (uint32_t)v.word_lo}, self_eword, now_ms, seed,
                            pick_id(in[i], f->id_base + (uint64_t)i), SoloVote(), o, g_lane_budget);
       g_lane_decisions++;
       if (!done) g_bails++;
