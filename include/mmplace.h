@@ -403,6 +403,8 @@ int32_t mmp_registry_prune(mmp_fleet *, int32_t self, int64_t now_ms, int64_t as
 /* tuning / measurement knobs, same meaning as the MMP_* environment variables read at mmp_fleet_create:
  *   "one_mode"        how a batch of <= 32 decisions is launched: 0 the streaming kernel (k_place_lanes), 1 the latency kernel
  *                     k_place_small as a stream launch, 2 (default) k_place_small as a replayed CUDA graph
+ *   "small_max"       untraced batches of up to this many decisions run on k_place_small (one wave of 32-thread blocks, rows
+ *                     read straight from memory) instead of the streaming kernel
  *   "lane_budget"     walk steps a lane may spend before its decision is redone by the whole warp
  *   "lane_warps"      warps per block of k_place_lanes (0 = default 12)
  *   "commit_host_only" 1: every commit takes the structural (host) path */

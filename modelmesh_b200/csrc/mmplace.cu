@@ -893,7 +893,8 @@ struct mmp_fleet {
     bool ready = false;
     int32_t max_batch = 0;
     DevBuf out, flags, done, err;           // out: 2 x max_batch results (step parity); flags: MAX_SHARDS arrival counters + statistics
-    void *peer_base[MAX_SHARDS][4] = {};    // what was opened from every peer: excl of snapshot 0 / 1, out, flags
+    void *peer_base[MAX_SHARDS][4] = {};    // every peer's buffers as mapped here: excl of snapshot 0 / 1, out, flags
+    void *block_base[MAX_SHARDS][4] = {};   // ... and the allocation blocks that were opened for them
     bool opened[MAX_SHARDS][4] = {};
     uint64_t step = 0;
     int64_t batches = 0, result_bytes = 0;
@@ -913,6 +914,8 @@ struct mmp_fleet {
   int shard_chunks = 1;         // MMP_SHARD_CHUNKS (see place_sharded)
   int one_mode = 2;             // MMP_ONE = lanes | small | graph: how tiny batches are launched (0: the streaming kernel, 1: k_place_small
                                 // as a stream launch, 2: k_place_small as a replayed CUDA graph)
+  int small_max = 0;            // MMP_SMALL_MAX: untraced batches of up to this many decisions run on k_place_small (no landing stages:
+                                // one wave of 32-thread blocks), larger ones on the streaming kernel
   int lane_budget = LANE_BUDGET;  // MMP_LANE_BUDGET: walk steps per lane before a decision is handed to the whole warp
   int lane_mode = 0;            // MMP_LANE_MODE=1: stream-only probe (rows staged, no decisions) -- measurement aid, results void
   int lanes = 1;                // MMP_KERNEL=tile selects the cooperative-tile kernel (k_place) instead of k_place_lanes
@@ -1046,6 +1049,13 @@ static cudaError_t launch_place_lanes(mmp_fleet *f, const PlaceArgs &a, cudaStre
 
 static cudaError_t launch_place(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st) {
   const int rw = a.s.row_words;
+  // small launches: a batch that fits one wave of 32-decision blocks skips the landing-stage pipeline (its prologue and
+  // its one-block-per-SM shape cost more than they hide when every warp has a single step to do)
+  if (!(a.tr || a.cand) && !a.emit_keys && !a.orig_id && a.n <= f->small_max && a.s.word_lo == 0 && a.s.word_hi == a.s.row_words) {
+    k_place_small<<<(a.n + 31) / 32, 32, 0, st>>>(a.s, a.in, a.n, a.fresh, a.n_fresh, a.extra, a.out, a.now, a.seed, a.id_base, nullptr, f->lane_budget);
+    f->launches++;
+    return cudaGetLastError();
+  }
   // production path: one decision per lane (any row width of which at least two 32-row landing stages fit: ~3 KiB rows)
   if (!(a.tr || a.cand) && f->lanes) {
     int ns = 0;
@@ -1253,10 +1263,28 @@ int64_t mmp_shard_open_decisions(mmp_fleet *f) { return f ? f->open_decisions.lo
 // ---- peer access between the instance shards (k_place_dealt) ----
 struct ShardIpcBlob {
   uint32_t magic, rank, count, max_batch;
-  uint64_t pid, bytes[4], ptr[4];
+  uint64_t pid, bytes[4], ptr[4], off[4];  // off: offset of the buffer inside the allocation block its handle names
   int32_t device, pad;
   cudaIpcMemHandle_t h[4];  // excl of snapshot 0 / 1, result buffer, flag array
 };
+// cudaMalloc carves small allocations out of shared blocks and an IPC handle names the whole block: export the block's
+// handle plus the buffer's offset in it, open every distinct block once
+static int32_t ipc_block_offset(const void *p, uint64_t *off) {
+  typedef int (*GetRange)(unsigned long long *, size_t *, unsigned long long);
+  static GetRange fn = nullptr;
+  if (!fn) {
+    void *sym = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    CK(cudaGetDriverEntryPoint("cuMemGetAddressRange", &sym, cudaEnableDefault, &qr));
+    if (!sym || qr != cudaDriverEntryPointSuccess) { g_err = "cuMemGetAddressRange not available"; return MMP_E_CUDA; }
+    fn = reinterpret_cast<GetRange>(sym);
+  }
+  unsigned long long base = 0;
+  size_t size = 0;
+  if (fn(&base, &size, (unsigned long long)(uintptr_t)p) != 0) { g_err = "cuMemGetAddressRange failed"; return MMP_E_CUDA; }
+  *off = (uint64_t)(uintptr_t)p - base;
+  return MMP_OK;
+}
 static_assert(sizeof(ShardIpcBlob) <= MMP_SHARD_IPC_BYTES, "blob size");
 int32_t mmp_shard_ipc_export(mmp_fleet *f, int32_t max_batch, void *blob) {
   if (!f || !blob || max_batch <= 0) { g_err = "bad argument"; return MMP_E_ARG; }
@@ -1288,6 +1316,8 @@ int32_t mmp_shard_ipc_export(mmp_fleet *f, int32_t max_batch, void *blob) {
   const size_t bytes[4] = {f->snaps[0].excl.cap, f->snaps[1].excl.cap, pr.out.cap, pr.flags.cap};
   for (int k = 0; k < 4; k++) {
     bl.ptr[k] = (uint64_t)(uintptr_t)ptrs[k]; bl.bytes[k] = bytes[k];
+    int32_t rco = ipc_block_offset(ptrs[k], &bl.off[k]);
+    if (rco < 0) return rco;
     CK(cudaIpcGetMemHandle(&bl.h[k], ptrs[k]));
   }
   memset(blob, 0, MMP_SHARD_IPC_BYTES);
@@ -1316,10 +1346,18 @@ int32_t mmp_shard_ipc_import(mmp_fleet *f, const void *blobs) {
       (void)cudaGetLastError();
       for (int k = 0; k < 4; k++) pr.peer_base[q][k] = (void *)(uintptr_t)bl.ptr[k];
     } else {
+      for (int k = 0; k < 4; k++)
+        if (pr.opened[q][k]) { cudaIpcCloseMemHandle(pr.block_base[q][k]); pr.opened[q][k] = false; }
       for (int k = 0; k < 4; k++) {
-        if (pr.opened[q][k]) { cudaIpcCloseMemHandle(pr.peer_base[q][k]); pr.opened[q][k] = false; }
-        CK(cudaIpcOpenMemHandle(&pr.peer_base[q][k], bl.h[k], cudaIpcMemLazyEnablePeerAccess));
-        pr.opened[q][k] = true;
+        int same = -1;
+        for (int j = 0; j < k && same < 0; j++)
+          if (bl.ptr[j] - bl.off[j] == bl.ptr[k] - bl.off[k]) same = j;  // the same block in the exporting process
+        if (same >= 0) pr.block_base[q][k] = pr.block_base[q][same];
+        else {
+          CK(cudaIpcOpenMemHandle(&pr.block_base[q][k], bl.h[k], cudaIpcMemLazyEnablePeerAccess));
+          pr.opened[q][k] = true;
+        }
+        pr.peer_base[q][k] = (unsigned char *)pr.block_base[q][k] + bl.off[k];
       }
     }
   }
@@ -1372,6 +1410,7 @@ int32_t mmp_fleet_create(const mmp_config *cfg, mmp_fleet **out) {
   if (const char *t = getenv("MMP_LANE_MODE")) f->lane_mode = atoi(t);
   if (const char *t = getenv("MMP_ONE")) f->one_mode = !strcmp(t, "lanes") ? 0 : (!strcmp(t, "small") ? 1 : 2);
   if (const char *t = getenv("MMP_COMMIT")) f->commit_host_only = strcmp(t, "host") == 0;
+  if (const char *t = getenv("MMP_SMALL_MAX")) { int v = atoi(t); if (v >= 0) f->small_max = v; }
   if (const char *t = getenv("MMP_LANE_BUDGET")) { int v = atoi(t); if (v >= 1 && v <= 4096) f->lane_budget = v; }
   if (const char *t = getenv("MMP_SHARD_CHUNKS")) f->shard_chunks = atoi(t);
   if (f->lane_mode & 2) { CK(f->d_dbg.ensure(128)); CK(cudaMemset(f->d_dbg.p, 0, 128)); }
@@ -1736,6 +1775,7 @@ int32_t mmp_tune(mmp_fleet *f, const char *key, int64_t value) {
   NEED(f);
   if (!key) { g_err = "null key"; return MMP_E_ARG; }
   if (!strcmp(key, "one_mode") && value >= 0 && value <= 2) f->one_mode = (int)value;
+  else if (!strcmp(key, "small_max") && value >= 0 && value <= (1 << 24)) f->small_max = (int)value;
   else if (!strcmp(key, "lane_budget") && value >= 1 && value <= 4096) f->lane_budget = (int)value;
   else if (!strcmp(key, "lane_warps") && (value == 0 || value == 8 || value == 10 || value == 12 || value == 14 || value == 16 || value == 20)) f->lane_warps = (int)value;
   else if (!strcmp(key, "commit_host_only") && (value == 0 || value == 1)) f->commit_host_only = (int)value;

@@ -61,6 +61,10 @@ def _worker(rank, world, port, q):
             dist.barrier()
             f.close()
         q.put((rank, results))
+    except BaseException:  # the parent must not wait for a worker that died
+        import traceback
+        q.put((rank, "worker failed:\n" + traceback.format_exc()))
+        raise
     finally:
         dist.destroy_process_group()
 
@@ -87,7 +91,14 @@ def test_sharded_matches_unsharded(product_lib, world):
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    got = dict(q.get(timeout=900) for _ in range(world))
+    got = {}
+    for _ in range(world):
+        r, res = q.get(timeout=600)
+        if isinstance(res, str):
+            for p in procs:
+                p.kill()
+            pytest.fail(f"rank {r}: {res}")
+        got[r] = res
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
