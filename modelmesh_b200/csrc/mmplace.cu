@@ -892,7 +892,10 @@ struct mmp_fleet {
   struct Peers {
     bool ready = false;
     int32_t max_batch = 0;
-    DevBuf out, flags, done, err;           // out: 2 x max_batch results (step parity); flags: MAX_SHARDS arrival counters + statistics
+    DevBuf arena, done, err;                // arena (exported): 4 KB of arrival counters + statistics, then 2 x max_batch results (step parity)
+    static constexpr size_t IPC_MIN_BYTES = (size_t)8 << 20;  // exported buffers get allocation blocks of their own (an IPC handle names a block)
+    mmp_decision_out *out_buf() const { return reinterpret_cast<mmp_decision_out *>(arena.as<unsigned char>() + 4096); }
+    unsigned long long *flag_buf() const { return arena.as<unsigned long long>(); }
     void *peer_base[MAX_SHARDS][4] = {};    // every peer's buffers as mapped here: excl of snapshot 0 / 1, out, flags
     void *block_base[MAX_SHARDS][4] = {};   // ... and the allocation blocks that were opened for them
     bool opened[MAX_SHARDS][4] = {};
@@ -1103,9 +1106,9 @@ static int32_t place_dealt(mmp_fleet *f, PlaceCtx *c, const DeviceSnapshot &ds, 
   for (int q = 0; q < MAX_SHARDS; q++) { P.blocks[q] = nullptr; P.out[q] = nullptr; P.flags[q] = nullptr; }
   for (int q = 0; q < G; q++) {
     P.blocks[q] = q == me ? ds.excl.as<uint32_t>() : reinterpret_cast<const uint32_t *>(pr.peer_base[q][cur]);
-    mmp_decision_out *ob = q == me ? pr.out.as<mmp_decision_out>() : reinterpret_cast<mmp_decision_out *>(pr.peer_base[q][2]);
+    mmp_decision_out *ob = q == me ? pr.out_buf() : reinterpret_cast<mmp_decision_out *>((unsigned char *)pr.peer_base[q][2] + 4096);
     P.out[q] = ob + (size_t)(step & 1) * pr.max_batch;
-    P.flags[q] = q == me ? pr.flags.as<unsigned long long>() : reinterpret_cast<unsigned long long *>(pr.peer_base[q][3]);
+    P.flags[q] = q == me ? pr.flag_buf() : reinterpret_cast<unsigned long long *>(pr.peer_base[q][2]);
   }
   constexpr int WARPS = 4;
   const long long n_wb = ((long long)n + 31) / 32;                     // warp batches of the whole batch
@@ -1113,14 +1116,14 @@ static int32_t place_dealt(mmp_fleet *f, PlaceCtx *c, const DeviceSnapshot &ds, 
   const int blocks = (int)std::max<long long>(1, (mine + WARPS - 1) / WARPS);  // (an empty deal still arrives)
   const size_t smem = (size_t)WARPS * vw.row_words * 4;
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_place_dealt<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  unsigned long long *stats = pr.flags.as<unsigned long long>() + MAX_SHARDS;
+  unsigned long long *stats = pr.flag_buf() + MAX_SHARDS;
   k_place_dealt<WARPS><<<blocks, WARPS * 32, smem, st>>>(vw, ds.front.as<uint32_t>(), std::min(SHARD_FRONT_WORDS, vw.row_words), ds.nzw_full.as<uint16_t>(),
                                                        ds.nz_n_full.as<int32_t>(), P, G, me, d_in, n, d_fresh, n_fresh, d_extra, now_ms, seed,
                                                        f->id_base.load(), f->lane_budget, step, pr.done.as<unsigned int>(), stats);
   CK(cudaGetLastError());
-  k_dealt_wait<<<1, 32, 0, st>>>(pr.flags.as<unsigned long long>(), G, step, 4000000000ull, pr.err.as<int>());
+  k_dealt_wait<<<1, 32, 0, st>>>(pr.flag_buf(), G, step, 4000000000ull, pr.err.as<int>());
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(d_out, pr.out.as<mmp_decision_out>() + (size_t)(step & 1) * pr.max_batch, (size_t)n * sizeof(mmp_decision_out),
+  CK(cudaMemcpyAsync(d_out, pr.out_buf() + (size_t)(step & 1) * pr.max_batch, (size_t)n * sizeof(mmp_decision_out),
                      cudaMemcpyDeviceToDevice, st));
   int err = 0;
   CK(cudaMemcpyAsync(&err, pr.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1265,7 +1268,7 @@ struct ShardIpcBlob {
   uint32_t magic, rank, count, max_batch;
   uint64_t pid, bytes[4], ptr[4], off[4];  // off: offset of the buffer inside the allocation block its handle names
   int32_t device, pad;
-  cudaIpcMemHandle_t h[4];  // excl of snapshot 0 / 1, result buffer, flag array
+  cudaIpcMemHandle_t h[4];  // excl of snapshot 0 / 1, the arena (flags + result buffers)
 };
 // cudaMalloc carves small allocations out of shared blocks and an IPC handle names the whole block: export the block's
 // handle plus the buffer's offset in it, open every distinct block once
@@ -1296,25 +1299,25 @@ int32_t mmp_shard_ipc_export(mmp_fleet *f, int32_t max_batch, void *blob) {
   int32_t lo, hi, stw;
   HostState::shard_words(f->hs.row_words(), f->hs.cfg.shard_rank, G, lo, hi, stw);
   // the column blocks keep their address for the fleet's lifetime: both snapshots are sized for max_models rows now
-  const size_t full = (size_t)std::max(f->hs.cfg.max_models, 1) * stw * 4;
+  const size_t full = std::max(mmp_fleet::Peers::IPC_MIN_BYTES, (size_t)std::max(f->hs.cfg.max_models, 1) * stw * 4);
   for (int k = 0; k < 2; k++) {
     DevBuf &b = f->snaps[k].excl;
     if (b.p && b.cap < full) { g_err = "column block allocated before export is smaller than max_models rows"; return MMP_E_STATE; }
-    if (!b.p) { CK(b.ensure(full)); CK(cudaMemset(b.p, 0, full)); }
+    if (!b.p) { CK(b.ensure(full)); CK(cudaMemset(b.p, 0, b.cap)); }
   }
   pr.ready = false;
   pr.max_batch = max_batch;
-  CK(pr.out.ensure((size_t)2 * max_batch * sizeof(mmp_decision_out)));
-  CK(pr.flags.ensure((MAX_SHARDS + 8) * 8)); CK(pr.done.ensure(16)); CK(pr.err.ensure(16));
-  CK(cudaMemset(pr.flags.p, 0, (MAX_SHARDS + 8) * 8)); CK(cudaMemset(pr.done.p, 0, 16)); CK(cudaMemset(pr.err.p, 0, 16));
+  CK(pr.arena.ensure(std::max(mmp_fleet::Peers::IPC_MIN_BYTES, (size_t)4096 + (size_t)2 * max_batch * sizeof(mmp_decision_out))));
+  CK(pr.done.ensure(16)); CK(pr.err.ensure(16));
+  CK(cudaMemset(pr.arena.p, 0, 4096)); CK(cudaMemset(pr.done.p, 0, 16)); CK(cudaMemset(pr.err.p, 0, 16));
   pr.step = 0;
   ShardIpcBlob bl;
   memset(&bl, 0, sizeof(bl));
   bl.magic = 0x4d4d5049u; bl.rank = (uint32_t)f->hs.cfg.shard_rank; bl.count = (uint32_t)G; bl.max_batch = (uint32_t)max_batch;
   bl.pid = (uint64_t)getpid(); bl.device = f->device;
-  void *ptrs[4] = {f->snaps[0].excl.p, f->snaps[1].excl.p, pr.out.p, pr.flags.p};
-  const size_t bytes[4] = {f->snaps[0].excl.cap, f->snaps[1].excl.cap, pr.out.cap, pr.flags.cap};
-  for (int k = 0; k < 4; k++) {
+  void *ptrs[3] = {f->snaps[0].excl.p, f->snaps[1].excl.p, pr.arena.p};
+  const size_t bytes[3] = {f->snaps[0].excl.cap, f->snaps[1].excl.cap, pr.arena.cap};
+  for (int k = 0; k < 3; k++) {
     bl.ptr[k] = (uint64_t)(uintptr_t)ptrs[k]; bl.bytes[k] = bytes[k];
     int32_t rco = ipc_block_offset(ptrs[k], &bl.off[k]);
     if (rco < 0) return rco;
@@ -1344,11 +1347,11 @@ int32_t mmp_shard_ipc_import(mmp_fleet *f, const void *blobs) {
       cudaError_t e = cudaDeviceEnablePeerAccess(bl.device, 0);
       if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { g_err = cudaGetErrorString(e); return MMP_E_CUDA; }
       (void)cudaGetLastError();
-      for (int k = 0; k < 4; k++) pr.peer_base[q][k] = (void *)(uintptr_t)bl.ptr[k];
+      for (int k = 0; k < 3; k++) pr.peer_base[q][k] = (void *)(uintptr_t)bl.ptr[k];
     } else {
-      for (int k = 0; k < 4; k++)
+      for (int k = 0; k < 3; k++)
         if (pr.opened[q][k]) { cudaIpcCloseMemHandle(pr.block_base[q][k]); pr.opened[q][k] = false; }
-      for (int k = 0; k < 4; k++) {
+      for (int k = 0; k < 3; k++) {
         int same = -1;
         for (int j = 0; j < k && same < 0; j++)
           if (bl.ptr[j] - bl.off[j] == bl.ptr[k] - bl.off[k]) same = j;  // the same block in the exporting process
@@ -1370,7 +1373,7 @@ int32_t mmp_shard_peer_stats(mmp_fleet *f, int64_t *out4) {
   if (!f || !out4) { g_err = "bad argument"; return MMP_E_ARG; }
   mmp_fleet::Peers &pr = f->peers;
   unsigned long long words = 0;
-  if (pr.flags.p) { CK(cudaSetDevice(f->device)); CK(cudaMemcpy(&words, pr.flags.as<unsigned long long>() + MAX_SHARDS, 8, cudaMemcpyDeviceToHost)); }
+  if (pr.arena.p) { CK(cudaSetDevice(f->device)); CK(cudaMemcpy(&words, pr.flag_buf() + MAX_SHARDS, 8, cudaMemcpyDeviceToHost)); }
   out4[0] = pr.batches; out4[1] = (int64_t)words; out4[2] = pr.result_bytes; out4[3] = pr.ready && !pr.off ? 1 : 0;
   return MMP_OK;
 }
@@ -1725,7 +1728,8 @@ static int32_t commit_locked(mmp_fleet *f) {
   // exclusion bitmap in rank space: zero, then scatter the device-resident loaded/failed lists (one write pass)
   const int ST = h.excl_stride;  // words per stored row: the whole row, or this instance shard's block
   // (instance-sharded: sized for max_models rows from the first commit on, so that the block keeps the address its peers mapped)
-  CK(ds.excl.ensure((size_t)std::max(f->hs.cfg.shard_count > 1 ? std::max(nm, f->hs.cfg.max_models) : nm, 1) * ST * 4));
+  CK(ds.excl.ensure(f->hs.cfg.shard_count > 1 ? std::max(mmp_fleet::Peers::IPC_MIN_BYTES, (size_t)std::max(nm, f->hs.cfg.max_models) * ST * 4)
+                                              : (size_t)std::max(nm, 1) * ST * 4));
   if (nm) {
     CK(cudaMemsetAsync(ds.excl.p, 0, (size_t)nm * ST * 4, st));
     k_build_bitmap<<<(nm + 255) / 256, 256, 0, st>>>(ds.excl.as<uint32_t>(), lv.edges.as<int4>(), ds.rank_of.as<int32_t>(), nm, ST,
