@@ -461,10 +461,10 @@ class HostState {
       s.nz_n_full.assign((size_t)s.n_slots, 0);
       for (int32_t sl = 0; sl < s.n_slots; sl++) {
         const uint32_t *cx = (s.any_rs ? s.candx.data() : s.cand.data()) + (size_t)sl * RW;
-        int32_t k = 0;
+        int32_t k = 0, skip = 0;
         for (int32_t w = 0; w < RW; w++)
-          if (cx[w]) s.nzw_full[(size_t)sl * RW + k++] = (uint16_t)w;
-        s.nz_n_full[sl] = k;
+          if (cx[w]) { s.nzw_full[(size_t)sl * RW + k++] = (uint16_t)w; if (w < MMP_LANE_WIN) skip++; }
+        s.nz_n_full[sl] = k | (skip << 24);
       }
     }
     s.part_type_ids.assign(s.part_types.size(), {});

@@ -626,8 +626,8 @@ struct DealtPeers {
   mmp_decision_out *out[MAX_SHARDS];    // result buffer of every shard for this step's parity
   unsigned long long *flags[MAX_SHARDS];  // flag array of every shard: [G] arrival counters
 };
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) k_place_dealt(const SnapshotView s, const uint32_t *__restrict__ front, int front_words,
+template <int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) k_place_dealt(const SnapshotView s, const uint32_t *__restrict__ front, int front_words,
                                                             const uint16_t *__restrict__ nzw_full, const int32_t *__restrict__ nz_n_full,
                                                             const __grid_constant__ DealtPeers P, int G, int me, const mmp_decision_in *__restrict__ in, int n,
                                                             const FreshRow *__restrict__ fresh, int n_fresh, const int32_t *__restrict__ extra,
@@ -901,6 +901,7 @@ struct mmp_fleet {
     bool opened[MAX_SHARDS][4] = {};
     uint64_t step = 0;
     int64_t batches = 0, result_bytes = 0;
+    int minb = 4;
     int off = 0;                            // MMP_SHARD_PEERS=0 keeps the collective path although peers were imported
   } peers;
   std::mutex comm_mu;           // collectives of one communicator are issued by one thread at a time
@@ -1115,9 +1116,11 @@ static int32_t place_dealt(mmp_fleet *f, PlaceCtx *c, const DeviceSnapshot &ds, 
   const long long mine = n_wb > me ? (n_wb - me + G - 1) / G : 0;      // ... dealt to this shard
   const int blocks = (int)std::max<long long>(1, (mine + WARPS - 1) / WARPS);  // (an empty deal still arrives)
   const size_t smem = (size_t)WARPS * vw.row_words * 4;
-  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_place_dealt<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // MINB: resident blocks per SM the compiler must allow (4: no spills, 16 warps per SM; 6: 24 warps, some spills) -- MMP_DEALT_MINB
+  auto kern = pr.minb == 6 ? k_place_dealt<WARPS, 6> : k_place_dealt<WARPS, 4>;
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   unsigned long long *stats = pr.flag_buf() + MAX_SHARDS;
-  k_place_dealt<WARPS><<<blocks, WARPS * 32, smem, st>>>(vw, ds.front.as<uint32_t>(), std::min(SHARD_FRONT_WORDS, vw.row_words), ds.nzw_full.as<uint16_t>(),
+  kern<<<blocks, WARPS * 32, smem, st>>>(vw, ds.front.as<uint32_t>(), std::min(SHARD_FRONT_WORDS, vw.row_words), ds.nzw_full.as<uint16_t>(),
                                                        ds.nz_n_full.as<int32_t>(), P, G, me, d_in, n, d_fresh, n_fresh, d_extra, now_ms, seed,
                                                        f->id_base.load(), f->lane_budget, step, pr.done.as<unsigned int>(), stats);
   CK(cudaGetLastError());
@@ -1215,6 +1218,7 @@ static int32_t place_sharded(mmp_fleet *f, PlaceCtx *c, const DeviceSnapshot &ds
   SnapshotView whole = vw;
   whole.excl = c->d_rows.as<uint32_t>();
   whole.excl_stride = NW; whole.word_lo = 0; whole.word_hi = NW;
+  if (G > 1) { whole.nzw = ds.nzw_full.as<uint16_t>(); whole.nz_n = ds.nz_n_full.as<int32_t>(); }  // word lists over the whole row, not this shard's block
   PlaceArgs b{whole, c->d_in_open.as<mmp_decision_in>(), n_open, d_fresh, n_fresh, d_extra, c->d_out_open.as<mmp_decision_out>(),
               nullptr, nullptr, now_ms, seed, f->id_base.load()};
   b.orig_id = c->d_open_idx.as<int32_t>();
@@ -1365,6 +1369,7 @@ int32_t mmp_shard_ipc_import(mmp_fleet *f, const void *blobs) {
     }
   }
   if (const char *t = getenv("MMP_SHARD_PEERS")) pr.off = atoi(t) == 0;
+  if (const char *t = getenv("MMP_DEALT_MINB")) pr.minb = atoi(t) == 6 ? 6 : 4;
   pr.ready = true;
   return MMP_OK;
 }
