@@ -769,6 +769,8 @@ struct TabWin {
   MMP_HD uint32_t p(uint32_t wi) const { return t.p[wi]; }
   MMP_HD uint32_t full(uint32_t wi) const { return t.full[wi]; }
   MMP_HD WordSumI csum(uint32_t wi) const { return t.csum[wi]; }
+  // count test of a whole word against lim: 0 no rank reaches it, 1 every rank does, 2 mixed (look at the 32 counts)
+  MMP_HD int cls(uint32_t wi, int32_t lim) const { const WordSumI m = t.csum[wi]; return m.hi < lim ? 0 : (m.lo >= lim ? 1 : 2); }
   MMP_HD uint32_t ge_mask(uint32_t wi, int32_t lim) const {  // bit j: count of rank wi*32 + j >= lim (32 counts, zero-padded past the last rank)
     uint32_t vm = 0;
 #if defined(__CUDA_ARCH__)
@@ -791,6 +793,7 @@ struct TabGlob {
   MMP_HD uint32_t p(uint32_t wi) const { return ldro(t.p + wi); }
   MMP_HD uint32_t full(uint32_t wi) const { return ldro(t.full + wi); }
   MMP_HD WordSumI csum(uint32_t wi) const { return ldro_sum(t.csum + wi); }
+  MMP_HD int cls(uint32_t wi, int32_t lim) const { const WordSumI m = ldro_sum(t.csum + wi); return m.hi < lim ? 0 : (m.lo >= lim ? 1 : 2); }
   MMP_HD uint32_t ge_mask(uint32_t wi, int32_t lim) const {
     uint32_t vm = 0;
 #if defined(__CUDA_ARCH__)
@@ -806,6 +809,17 @@ struct TabGlob {
 #endif
     return vm;
   }
+};
+// a step beyond the window: its filtered word (candidates & ~exclusions), preferred word and count class were gathered
+// when the chunk of 8 steps was (re)filled -- one round of independent loads per 8 steps instead of three dependent ones
+// per step; the walk bodies see them through the same interface (cx() is the filtered word: they are handed e = 0)
+struct TabChunk {
+  uint32_t f, pw; int c; const TabGlob &g;
+  MMP_HD uint32_t cx(uint32_t) const { return f; }
+  MMP_HD uint32_t p(uint32_t) const { return pw; }
+  MMP_HD uint32_t full(uint32_t wi) const { return g.full(wi); }
+  MMP_HD int cls(uint32_t, int32_t) const { return c; }
+  MMP_HD uint32_t ge_mask(uint32_t wi, int32_t lim) const { return g.ge_mask(wi, lim); }
 };
 
 
@@ -901,8 +915,11 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &Tw, const Lan
   auto row_of = [&](uint32_t r) -> RankRow { return (r >> 5) < win_end ? load_row_any(Tw.rows + r) : load_row(T.rows + r); };
   // ---- beyond the window: a chunk of 8 consecutive steps [base, base + 8) in registers ----
   uint32_t base = 0xfffffff0u;  // no chunk loaded
-  uint32_t wq[4] = {0, 0, 0, 0};
-  uint32_t eq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint32_t wq[4] = {0, 0, 0, 0};                    // the chunk's list entries (u16 pairs)
+  uint32_t fq[8] = {0, 0, 0, 0, 0, 0, 0, 0};        // ... filtered words cx & ~row
+  uint32_t pq[8] = {0, 0, 0, 0, 0, 0, 0, 0};        // ... preferred words
+  uint32_t cq = 0;                                  // ... count classes against cls_lim (2 bits each)
+  int32_t cls_lim = 10;                             // the count limit the chunk's classes were computed for (phase B sets it and drops the chunk)
   auto wsel = [&](uint32_t j) -> uint32_t {          // entry j (0..7) of the chunk, without dynamic register indexing
     uint32_t q = wq[0];
     q = (j >> 1) == 1 ? wq[1] : q; q = (j >> 1) == 2 ? wq[2] : q; q = (j >> 1) == 3 ? wq[3] : q;
@@ -916,13 +933,22 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &Tw, const Lan
       const uint32_t lo16 = k0 < NZ ? (uint32_t)ldro(T.nzw + (k0 + koff)) : 0xffffu, hi16 = k1 < NZ ? (uint32_t)ldro(T.nzw + (k1 + koff)) : 0xffffu;
       wq[j] = lo16 | (hi16 << 16);
     }
+    cq = 0;
 #pragma unroll
-    for (uint32_t j = 0; j < 8; j++) eq[j] = (k + j < NZ) ? row.word(wsel(j)) : 0u;
+    for (uint32_t j = 0; j < 8; j++) {
+      uint32_t f = 0, pw = 0;
+      int cl = 0;
+      if (k + j < NZ) {
+        const uint32_t wi = wsel(j);
+        f = AG.cx(wi) & ~row.word(wi); pw = AG.p(wi); cl = AG.cls(wi, cls_lim);
+      }
+      fq[j] = f; pq[j] = pw; cq |= (uint32_t)cl << (2u * j);
+    }
   };
-  auto esel = [&](uint32_t j) -> uint32_t {
-    uint32_t v = eq[0];
-    v = j == 1 ? eq[1] : v; v = j == 2 ? eq[2] : v; v = j == 3 ? eq[3] : v; v = j == 4 ? eq[4] : v;
-    v = j == 5 ? eq[5] : v; v = j == 6 ? eq[6] : v; v = j == 7 ? eq[7] : v;
+  auto sel8 = [&](const uint32_t (&a)[8], uint32_t j) -> uint32_t {
+    uint32_t v = a[0];
+    v = j == 1 ? a[1] : v; v = j == 2 ? a[2] : v; v = j == 3 ? a[3] : v; v = j == 4 ? a[4] : v;
+    v = j == 5 ? a[5] : v; v = j == 6 ? a[6] : v; v = j == 7 ? a[7] : v;
     return v;
   };
   // One walk: BODY sees (K, wi, e) and sets go_ (true: next step).  WALKING is cleared when the lane stops: BODY said so, the
@@ -951,8 +977,8 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &Tw, const Lan
         if (K >= NZ) { WALKING = false; ENDED = true; }                                                                    \
         else if (CHARGE && left <= 0) { WALKING = false; live = false; }                                                   \
         else {                                                                                                             \
-          const uint32_t wi = wsel(K - base), e = esel(K - base);                                                          \
-          const TabGlob &A = AG;                                                                                           \
+          const uint32_t j_ = K - base, wi = wsel(j_), e = 0u;                                                              \
+          const TabChunk A{sel8(fq, j_), sel8(pq, j_), (int)((cq >> (2u * j_)) & 3u), AG};                                   \
           bool go_;                                                                                                        \
           BODY;                                                                                                            \
           if (go_) { K++; if (CHARGE) left--; } else WALKING = false;                                                      \
@@ -1056,6 +1082,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &Tw, const Lan
   };
   // ---- B: first member of S' that fails its walk test, counting the members before it ----
   uint32_t cut_others = NONE_RANK, n_in = 0;
+  cls_lim = cv_min; base = 0xfffffff0u;  // (a chunk gathered by an earlier phase carries classes for another limit)
   {
     uint32_t k = k_lo;
     bool walking = walk, ended = false;
@@ -1067,7 +1094,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &Tw, const Lan
         int cls = 0;  // 0: no member fails, 1: every member (but a passing self) fails, 2: look at the counts
         uint32_t v = x;
         if (c_self) { if (wi == sw_) v &= ~sb_; cls = v ? 1 : 0; }
-        else if (x) { const WordSumI m = A.csum(wi); cls = !cv(m.hi) ? 0 : (cv(m.lo) ? 1 : 2); }
+        else if (x) cls = A.cls(wi, cv_min);
         if (cls == 2) {  // exact evaluation of a mixed word: 32 counts, zero-padded past the last rank
           const uint32_t vm = A.ge_mask(wi, cv_min);
           v = vm & x;
