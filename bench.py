@@ -515,7 +515,7 @@ def main():
     if rank == 0:
         one = np.zeros(1, dtype=DECISION_OUT)
         lat = {}
-        for mode, label in ((2, "cuda_graph"), (1, "small_kernel"), (0, "streaming_kernel")):
+        for mode, label in ((3, "resident_server"), (2, "cuda_graph"), (1, "small_kernel"), (0, "streaming_kernel")):
             solver._ck(lib.mmp_tune(solver.h, b"one_mode", mode))
             ts = []
             for i in range(300 + 2000):
@@ -527,7 +527,9 @@ def main():
             lat[label] = {"p50_us": float(np.percentile(ts, 50)), "p99_us": float(np.percentile(ts, 99)), "n": len(ts)}
         solver._ck(lib.mmp_tune(solver.h, b"one_mode", 2))
         lat.update(lat["cuda_graph"])  # the default path: k_place_small replayed as a CUDA graph, zero-copy mapped buffers
-        lat["note"] = ("host timer around mmp_place_one (launch + synchronise + 8-byte result through mapped memory); cuda_graph = one "
+        lat["default_path"] = "cuda_graph"
+        lat["note"] = ("host timer around mmp_place_one (launch + synchronise + 8-byte result through mapped memory); resident_server = a request "
+                       "posted to k_place_server (a warp resident for a bounded time polling mapped memory: no launch per call, mmp_tune one_mode=3), cuda_graph = one "
                        "k_place_small node replayed, small_kernel = the same kernel as a stream launch, streaming_kernel = round 1's path")
 
     # ---- the batch scans on the same fleet: ClusterStats (~50 B per instance), the reaper's registry sweep +

@@ -563,20 +563,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_place_lanes(const SnapshotVie
 // k_place_lanes.  hdr (optional, pinned mapped memory): {now, seed, n} read by the kernel, so that a captured CUDA graph can
 // be replayed for every call without touching its node parameters.
 // ---------------------------------------------------------------------------------------------------------------
-struct SmallHdr { long long now; unsigned long long seed, id_base; int n, n_fresh, n_extra, pad; };
-__global__ void __launch_bounds__(32) k_place_small(const SnapshotView s_arg, const mmp_decision_in *__restrict__ in, int n_arg,
-                                                    const FreshRow *__restrict__ fresh, int n_fresh_arg, const int32_t *__restrict__ extra,
-                                                    mmp_decision_out *__restrict__ out, int64_t now_arg, uint64_t seed_arg, uint64_t id_base_arg,
-                                                    const volatile SmallHdr *hdr, int budget) {
-  __shared__ DecisionCtx ctx_one;
+struct SmallHdr { long long now; unsigned long long seed, id_base; int n, n_fresh, n_extra, stop; unsigned long long seq; unsigned long long pad[2]; };
+static_assert(sizeof(SmallHdr) == 64, "header is one 64-byte line");
+// one block of 32 threads resolves decisions [blk * 32, blk * 32 + 32) of a small batch
+__device__ __forceinline__ void place_small_block(const SnapshotView &s, const mmp_decision_in *in, int n, const FreshRow *fresh, int n_fresh,
+                                                  const int32_t *extra, mmp_decision_out *out, int64_t now, uint64_t seed, uint64_t id_base,
+                                                  int budget, int blk, DecisionCtx *ctx_one) {
   const int lane = threadIdx.x;
-  const int n = hdr ? hdr->n : n_arg;
-  const int n_fresh = hdr ? hdr->n_fresh : n_fresh_arg;
-  SnapshotView s = s_arg;
-  if (hdr) s.n_extra = hdr->n_extra;
-  const int64_t now = hdr ? hdr->now : now_arg;
-  const uint64_t seed = hdr ? hdr->seed : seed_arg, id_base = hdr ? hdr->id_base : id_base_arg;
-  const int i = blockIdx.x * 32 + lane;
+  const int i = blk * 32 + lane;
   const bool valid = i < n;
   const int RW = s.excl_stride;
   mmp_decision_in d;
@@ -597,16 +591,77 @@ __global__ void __launch_bounds__(32) k_place_small(const SnapshotView s_arg, co
   while (pending) {
     const int l = __ffs((int)pending) - 1;
     pending &= pending - 1;
-    if (lane == l) ctx_one = c;
+    if (lane == l) *ctx_one = c;
     const int ml = __shfl_sync(0xffffffffu, m, l);
     const uint64_t idl = __shfl_sync(0xffffffffu, my_id, l);
     __syncwarp();
     int32_t t2, c2, f2, g2;
-    decide_warp(s, ctx_one, s.excl + (size_t)ml * RW, extra, now, seed, idl, &t2, &c2, &f2, &g2);
+    decide_warp(s, *ctx_one, s.excl + (size_t)ml * RW, extra, now, seed, idl, &t2, &c2, &f2, &g2);
     if (lane == l) { o.target = t2; o.n_candidates = c2; }
     __syncwarp();
   }
   if (valid) out[i] = mmp_decision_out{o.target, o.n_candidates};
+}
+__global__ void __launch_bounds__(32) k_place_small(const SnapshotView s_arg, const mmp_decision_in *__restrict__ in, int n_arg,
+                                                    const FreshRow *__restrict__ fresh, int n_fresh_arg, const int32_t *__restrict__ extra,
+                                                    mmp_decision_out *__restrict__ out, int64_t now_arg, uint64_t seed_arg, uint64_t id_base_arg,
+                                                    const volatile SmallHdr *hdr, int budget) {
+  __shared__ DecisionCtx ctx_one;
+  SnapshotView s = s_arg;
+  if (hdr) s.n_extra = hdr->n_extra;
+  place_small_block(s, in, hdr ? hdr->n : n_arg, fresh, hdr ? hdr->n_fresh : n_fresh_arg, extra, out, hdr ? hdr->now : now_arg,
+                    hdr ? hdr->seed : seed_arg, hdr ? hdr->id_base : id_base_arg, budget, blockIdx.x, &ctx_one);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_place_server -- the B = 1 path without a launch per call.  One warp stays resident for a BOUNDED time (life_ns, or
+// idle_ns without a request), polling the sequence word of a request header in pinned mapped host memory; a request (up to
+// 32 decisions, laid out like the graph path's buffer) is resolved with the same routine as k_place_small and answered by
+// a release store of the sequence number into the response line.  The host posts a request with one store and spins on
+// the response: two PCIe round trips instead of launch + synchronise.  Bounded lifetime: anything that waits for the
+// device to drain (cudaFree inside a commit) waits at most life_ns, and a crashed host leaves no kernel behind.
+// ---------------------------------------------------------------------------------------------------------------
+struct ServerResp { unsigned long long done_seq; int alive, served; unsigned long long pad[6]; };
+static_assert(sizeof(ServerResp) == 64, "response is one 64-byte line");
+__global__ void __launch_bounds__(32) k_place_server(const SnapshotView s_arg, volatile SmallHdr *hdr, volatile ServerResp *resp,
+                                                     const mmp_decision_in *in, const FreshRow *fresh, const int32_t *extra,
+                                                     mmp_decision_out *out, unsigned long long life_ns, unsigned long long idle_ns, int budget) {
+  __shared__ DecisionCtx ctx_one;
+  const int lane = threadIdx.x;
+  unsigned long long t0, t_last, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  t_last = t0;
+  unsigned long long last = resp->done_seq;
+  int served = 0;
+  for (;;) {
+    unsigned long long seq = 0;
+    int stop = 0;
+    if (lane == 0) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seq) : "l"(&hdr->seq) : "memory");
+      stop = hdr->stop;
+    }
+    seq = __shfl_sync(0xffffffffu, seq, 0);
+    stop = __shfl_sync(0xffffffffu, stop, 0);
+    if (seq != last) {
+      SnapshotView s = s_arg;
+      s.n_extra = hdr->n_extra;
+      place_small_block(s, in, hdr->n, fresh, hdr->n_fresh, extra, out, hdr->now, hdr->seed, hdr->id_base, budget, 0, &ctx_one);
+      __threadfence_system();
+      __syncwarp();
+      if (lane == 0) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&resp->done_seq), "l"(seq) : "memory");
+      last = seq;
+      served++;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_last));
+    } else {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (stop || t - t0 > life_ns || t - t_last > idle_ns) break;
+    }
+  }
+  if (lane == 0) {
+    resp->served = served;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&resp->alive), "r"(0) : "memory");
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -916,8 +971,19 @@ struct mmp_fleet {
                                 // instances: 3 stages 3.5, 4 stages 4.1-4.3, 5 stages 3.8 G decisions/s (the fifth stage costs the L1
                                 // its 196 -> 228 KB carve-out step and the lane tables no longer stay resident)
   int shard_chunks = 1;         // MMP_SHARD_CHUNKS (see place_sharded)
-  int one_mode = 2;             // MMP_ONE = lanes | small | graph: how tiny batches are launched (0: the streaming kernel, 1: k_place_small
-                                // as a stream launch, 2: k_place_small as a replayed CUDA graph)
+  int one_mode = 2;             // MMP_ONE = lanes | small | graph | server: how tiny batches are launched (0: the streaming kernel, 1: k_place_small
+                                // as a stream launch, 2: k_place_small as a replayed CUDA graph, 3: a request to the resident k_place_server)
+  // the resident B = 1 server (one_mode 3, k_place_server)
+  struct Server {
+    std::mutex mu;                 // one request at a time; a caller that finds it taken uses the graph path
+    unsigned char *mapped = nullptr;
+    cudaStream_t stream = nullptr;
+    int32_t epoch = -1;
+    bool running = false;
+    uint64_t seq = 0;
+    int64_t launches = 0, requests = 0;
+    int64_t life_us = 2000, idle_us = 300;
+  } srv;
   int small_max = 0;            // MMP_SMALL_MAX: untraced batches of up to this many decisions run on k_place_small (no landing stages:
                                 // one wave of 32-thread blocks), larger ones on the streaming kernel
   int lane_budget = LANE_BUDGET;  // MMP_LANE_BUDGET: walk steps per lane before a decision is handed to the whole warp
@@ -1234,6 +1300,8 @@ static int32_t place_sharded(mmp_fleet *f, PlaceCtx *c, const DeviceSnapshot &ds
 // ---------------------------------------------------------------------------------------------------------------
 extern "C" {
 
+static void server_stop(mmp_fleet *f);
+
 int32_t mmp_shard_unique_id(void *id128) {
   if (!id128) { g_err = "null argument"; return MMP_E_ARG; }
   NcclApi &nc = nccl_api();
@@ -1416,7 +1484,7 @@ int32_t mmp_fleet_create(const mmp_config *cfg, mmp_fleet **out) {
   if (const char *t = getenv("MMP_LANE_WARPS")) { int v = atoi(t); if (v == 8 || v == 10 || v == 12 || v == 14 || v == 16 || v == 20) f->lane_warps = v; }
   if (const char *t = getenv("MMP_LANE_STAGES")) f->lane_stages = atoi(t);
   if (const char *t = getenv("MMP_LANE_MODE")) f->lane_mode = atoi(t);
-  if (const char *t = getenv("MMP_ONE")) f->one_mode = !strcmp(t, "lanes") ? 0 : (!strcmp(t, "small") ? 1 : 2);
+  if (const char *t = getenv("MMP_ONE")) f->one_mode = !strcmp(t, "lanes") ? 0 : (!strcmp(t, "small") ? 1 : (!strcmp(t, "server") ? 3 : 2));
   if (const char *t = getenv("MMP_COMMIT")) f->commit_host_only = strcmp(t, "host") == 0;
   if (const char *t = getenv("MMP_SMALL_MAX")) { int v = atoi(t); if (v >= 0) f->small_max = v; }
   if (const char *t = getenv("MMP_LANE_BUDGET")) { int v = atoi(t); if (v >= 1 && v <= 4096) f->lane_budget = v; }
@@ -1430,6 +1498,7 @@ int32_t mmp_fleet_create(const mmp_config *cfg, mmp_fleet **out) {
 void mmp_fleet_destroy(mmp_fleet *f) {
   if (!f) return;
   cudaSetDevice(f->device);
+  { std::lock_guard<std::mutex> lk(f->srv.mu); server_stop(f); if (f->srv.stream) cudaStreamDestroy(f->srv.stream); if (f->srv.mapped) cudaFreeHost(f->srv.mapped); f->srv.mapped = nullptr; }
   cudaDeviceSynchronize();
   if ((f->lane_mode & 2) && f->d_dbg.p) {  // MMP_LANE_MODE bit 1: print the per-phase averages of k_place_lanes
     unsigned long long h[9];
@@ -1783,7 +1852,9 @@ extern "C" {
 int32_t mmp_tune(mmp_fleet *f, const char *key, int64_t value) {
   NEED(f);
   if (!key) { g_err = "null key"; return MMP_E_ARG; }
-  if (!strcmp(key, "one_mode") && value >= 0 && value <= 2) f->one_mode = (int)value;
+  if (!strcmp(key, "one_mode") && value >= 0 && value <= 3) f->one_mode = (int)value;
+  else if (!strcmp(key, "server_life_us") && value >= 50 && value <= 1000000) f->srv.life_us = value;
+  else if (!strcmp(key, "server_idle_us") && value >= 10 && value <= 1000000) f->srv.idle_us = value;
   else if (!strcmp(key, "small_max") && value >= 0 && value <= (1 << 24)) f->small_max = (int)value;
   else if (!strcmp(key, "lane_budget") && value >= 1 && value <= 4096) f->lane_budget = (int)value;
   else if (!strcmp(key, "lane_warps") && (value == 0 || value == 8 || value == 10 || value == 12 || value == 14 || value == 16 || value == 20)) f->lane_warps = (int)value;
@@ -1808,6 +1879,73 @@ int32_t mmp_commit_info(mmp_fleet *f, int32_t *path, double *ms) {
   NEED(f);
   if (path) *path = f->last_commit_path;
   if (ms) *ms = f->last_commit_ms;
+  return MMP_OK;
+}
+
+// ---- the resident B = 1 server (k_place_server): post a request of up to 32 decisions, spin on the response ----
+static void server_stop(mmp_fleet *f) {
+  mmp_fleet::Server &sv = f->srv;
+  if (!sv.mapped || !sv.running) return;
+  volatile SmallHdr *hdr = reinterpret_cast<volatile SmallHdr *>(sv.mapped);
+  hdr->stop = 1;
+  std::atomic_thread_fence(std::memory_order_seq_cst);
+  cudaStreamSynchronize(sv.stream);
+  sv.running = false;
+}
+static int32_t place_server(mmp_fleet *f, const DeviceSnapshot &ds, const mmp_decision_in *in, int32_t n, const FreshRow *fresh, int32_t n_fresh,
+                            const int32_t *extra, int32_t n_extra, mmp_decision_out *out, int64_t now_ms, uint64_t seed) {
+  mmp_fleet::Server &sv = f->srv;
+  if (!sv.mapped) {
+    CK(cudaHostAlloc((void **)&sv.mapped, PlaceCtx::MAPPED_BYTES, cudaHostAllocMapped));
+    memset(sv.mapped, 0, PlaceCtx::MAPPED_BYTES);
+    CK(cudaStreamCreateWithFlags(&sv.stream, cudaStreamNonBlocking));
+  }
+  unsigned char *h = sv.mapped, *dbase = nullptr;
+  CK(cudaHostGetDevicePointer((void **)&dbase, h, 0));
+  const size_t g_in = 64, g_out = g_in + 32 * sizeof(mmp_decision_in), g_fr = g_out + 32 * sizeof(mmp_decision_out), g_ex = g_fr + 32 * sizeof(FreshRow),
+               g_resp = PlaceCtx::MAPPED_BYTES - 64;
+  volatile SmallHdr *hdr = reinterpret_cast<volatile SmallHdr *>(h);
+  volatile ServerResp *resp = reinterpret_cast<volatile ServerResp *>(h + g_resp);
+  if (sv.running && sv.epoch != f->epoch) server_stop(f);  // its snapshot view is another epoch's
+  memcpy(h + g_in, in, (size_t)n * sizeof(mmp_decision_in));
+  if (n_fresh) memcpy(h + g_fr, fresh, (size_t)n_fresh * sizeof(FreshRow));
+  if (n_extra) memcpy(h + g_ex, extra, (size_t)n_extra * 4);
+  hdr->now = now_ms; hdr->seed = seed; hdr->id_base = f->id_base.load(); hdr->n = n; hdr->n_fresh = n_fresh; hdr->n_extra = n_extra;
+  auto launch = [&]() -> int32_t {
+    hdr->stop = 0; resp->alive = 1;
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    SnapshotView gv = ds.view;
+    k_place_server<<<1, 32, 0, sv.stream>>>(gv, reinterpret_cast<volatile SmallHdr *>(dbase), reinterpret_cast<volatile ServerResp *>(dbase + g_resp),
+                                          (const mmp_decision_in *)(dbase + g_in), (const FreshRow *)(dbase + g_fr), (const int32_t *)(dbase + g_ex),
+                                          (mmp_decision_out *)(dbase + g_out), (unsigned long long)sv.life_us * 1000ull,
+                                          (unsigned long long)sv.idle_us * 1000ull, f->lane_budget);
+    CK(cudaGetLastError());
+    sv.running = true; sv.epoch = f->epoch; sv.launches++; f->launches++;
+    return MMP_OK;
+  };
+  if (!sv.running || resp->alive == 0) { int32_t rc = launch(); if (rc < 0) return rc; }
+  const uint64_t seq = ++sv.seq;
+  std::atomic_thread_fence(std::memory_order_seq_cst);
+  hdr->seq = seq;
+  std::atomic_thread_fence(std::memory_order_seq_cst);
+  const auto t0 = std::chrono::steady_clock::now();
+  for (uint32_t spins = 0;; spins++) {
+    if (resp->done_seq == seq) break;
+    if (resp->alive == 0) {  // the server's lifetime ended -- before or after it saw this request?
+      CK(cudaStreamSynchronize(sv.stream));
+      if (resp->done_seq == seq) break;
+      int32_t rc = launch();
+      if (rc < 0) return rc;
+    }
+    if ((spins & 0xfff) == 0xfff && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(2)) {
+      server_stop(f);
+      g_err = "the placement server did not answer within 2 s";
+      return MMP_E_CUDA;
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_seq_cst);
+  memcpy(out, h + g_out, (size_t)n * sizeof(mmp_decision_out));
+  sv.requests++;
   return MMP_OK;
 }
 
@@ -1857,6 +1995,10 @@ static int32_t place_impl(mmp_fleet *f, const mmp_decision_in *in, int32_t n, co
   {
     const size_t need = (size_t)n * (sizeof(mmp_decision_in) + sizeof(mmp_decision_out)) + (size_t)n_fresh * sizeof(FreshRow) + (size_t)n_extra * 4 + 64;
     if (!traced && need <= PlaceCtx::MAPPED_BYTES) {
+      if (f->one_mode == 3 && n <= 32 && n_fresh <= 32 && (size_t)n_extra <= 32 * MMP_MAX_EXTRA) {
+        std::unique_lock<std::mutex> lk(f->srv.mu, std::try_to_lock);
+        if (lk.owns_lock()) return place_server(f, ds, in, n, c->fresh_host.data(), n_fresh, extra, n_extra, out, now_ms, seed);
+      }  // (taken by another caller: this call goes the graph way)
       unsigned char *h = c->mapped, *dbase = nullptr;
       CK(cudaHostGetDevicePointer((void **)&dbase, h, 0));
       size_t o_in = 0, o_out = o_in + (size_t)n * sizeof(mmp_decision_in), o_fr = o_out + (size_t)n * sizeof(mmp_decision_out);

@@ -144,8 +144,8 @@ def test_registry_sweep_entry_point(product_lib, oracle_lib):
 
 @pytest.mark.parametrize("config,nm,ni,seed", [("C3", 3000, 1300, 3), ("C5", 2500, 700, 5), ("MIX", 800, 300, 14)])
 def test_latency_paths_equal_the_batch(product_lib, oracle_lib, config, nm, ni, seed):
-    """Tiny batches (B = 1 .. 32: one getNext on a request thread) through the three launch paths -- k_place_small replayed as a
-    CUDA graph (default), k_place_small as a stream launch, the streaming kernel -- give what the same decisions give inside a
+    """Tiny batches (B = 1 .. 32: one getNext on a request thread) through the four launch paths -- a request to the resident
+    k_place_server, k_place_small replayed as a CUDA graph (default), k_place_small as a stream launch, the streaming kernel -- give what the same decisions give inside a
     large batch, fresh rows and extra excludes included; between commits the graph is re-captured for the new epoch."""
     import ctypes as C
     fl = make_fleet(config, nm, ni, seed)
@@ -155,7 +155,7 @@ def test_latency_paths_equal_the_batch(product_lib, oracle_lib, config, nm, ni, 
     extra = sd.extra if len(sd.extra) else None
     for rnd in range(2):
         whole = s.place_batch(sd.dec, fl.now_ms, 11, fresh=fresh, extra=extra)
-        for mode in (2, 1, 0):
+        for mode in (3, 2, 1, 0):  # 3: requests to the resident server kernel (restarted for the new epoch in round 2)
             s._ck(product_lib.mmp_tune(s.h, b"one_mode", mode))
             for lo, cnt in ((0, 1), (1, 1), (5, 7), (40, 32), (100, 33), (200, 300)):
                 s._ck(product_lib.mmp_fleet_set_id_base(s.h, lo))

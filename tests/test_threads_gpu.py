@@ -29,7 +29,7 @@ def _oracle_answers(fl, rows, sd, seed, ids):
     return res["target"].copy(), res["n_candidates"].copy()
 
 
-@pytest.mark.parametrize("mode", ["place_one", "submit"])
+@pytest.mark.parametrize("mode", ["place_one", "place_one_server", "submit"])
 def test_concurrent_placement_with_ingest_and_commit(product_lib, oracle_lib, mode):
     lib = product_lib
     fl = make_fleet("C3", 3000, 700, 3)
@@ -47,6 +47,9 @@ def test_concurrent_placement_with_ingest_and_commit(product_lib, oracle_lib, mo
         rows_b[i]["lru_time"] = int(fl.now_ms - rng.integers(1, 5_000_000))
     s = Fleet(fl.min_space_units, fl.min_churn_age_ms, fl.default_model_size_units, fl.n_instances, fl.n_models, lib=lib)
     load_into_fleet(fl, s)
+    if mode == "place_one_server":  # the resident server answers one caller at a time, the others take the graph path; a short
+        s._ck(lib.mmp_tune(s.h, b"one_mode", 3))  # lifetime makes restarts (and restarts across commits) frequent
+        s._ck(lib.mmp_tune(s.h, b"server_life_us", 200))
     batcher = C.c_void_p()
     if mode == "submit":
         s._ck(lib.mmp_batcher_create(s.h, 256, 50, seed, C.byref(batcher)))
