@@ -614,6 +614,75 @@ __global__ void __launch_bounds__(32) k_place_small(const SnapshotView s_arg, co
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// k_place_direct -- one decision per lane WITHOUT landing stages: a lane reads the first MMP_LANE_WIN words of its
+// decision's exclusion row straight from global memory (three 16-byte loads: two 32-byte sectors of the row) into its
+// warp's window buffer, and whatever a walk needs beyond them word by word through the compressed list (decide_stream's
+// second loop).  A decision costs the sectors it looks at (~170 B at 10 k instances: record, model row, window, self's
+// word, result) instead of the whole 1 280-byte row, and without the 41 KB stages an SM holds 16-32 warps instead of 12.
+// One warp per batch of 32 decisions, no per-warp software pipeline: the other resident warps hide the gathers.
+// ---------------------------------------------------------------------------------------------------------------
+template <int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) k_place_direct(const SnapshotView s, const mmp_decision_in *__restrict__ in, int n,
+                                                                  const FreshRow *__restrict__ fresh, int n_fresh,
+                                                                  const int32_t *__restrict__ extra, mmp_decision_out *__restrict__ out,
+                                                                  int64_t now, uint64_t seed, uint64_t id_base, int budget) {
+  __shared__ uint32_t win_s[WARPS][32 * LANE_STRIDE];
+  __shared__ DecisionCtx ctx_w[WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = (blockIdx.x * WARPS + warp) * 32 + lane;
+  const bool valid = i < n;
+  const int RW = s.excl_stride;
+  mmp_decision_in d;
+  d.model = -1; d.self = -1; d.last_used = 0; d.flags = 0; d.fresh = -1; d.extra_off = 0; d.extra_n = 0;
+  if (valid) {
+    const int4 *dp = reinterpret_cast<const int4 *>(in + i);
+    int4 a, c;  // streamed once
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(dp));
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w) : "l"(dp + 1));
+    d.model = a.x; d.self = a.y; d.last_used = (int64_t)(((uint64_t)(uint32_t)a.w << 32) | (uint32_t)a.z);
+    d.flags = (uint32_t)c.x; d.fresh = c.y; d.extra_off = c.z; d.extra_n = c.w;
+  }
+  const int m = (valid && d.model >= 0 && d.model < s.n_models) ? d.model : 0;
+  const uint32_t *row = s.excl + (size_t)m * RW;
+  // the window's loads go out first: they depend on the record only
+  const uint32_t win_words = (uint32_t)min(LANE_WIN, s.word_hi - s.word_lo);
+  uint4 q[LANE_WIN / 4];
+#pragma unroll
+  for (int j = 0; j < LANE_WIN / 4; j++) {
+    q[j] = make_uint4(0u, 0u, 0u, 0u);
+    if (valid && (uint32_t)(j * 4) < win_words)
+      asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q[j].x), "=r"(q[j].y), "=r"(q[j].z), "=r"(q[j].w) : "l"(row + j * 4));
+  }
+  DecisionCtx c;
+  c.slot = -2; c.self_rank = -1; c.self_bits = 0; c.self_count = 0;
+  if (valid) prepare_ctx(s, d, fresh, n_fresh, extra, c);
+  uint32_t self_eword = 0;
+  if (valid && c.self_rank >= 0) self_eword = __ldg(row + (c.self_rank >> 5) - s.word_lo);
+  uint32_t *w = win_s[warp] + lane * LANE_STRIDE;
+#pragma unroll
+  for (int j = 0; j < LANE_WIN / 4; j++) { w[j * 4] = q[j].x; w[j * 4 + 1] = q[j].y; w[j * 4 + 2] = q[j].z; w[j * 4 + 3] = q[j].w; }
+  __syncwarp();
+  const LaneTables T = lane_tables_global(s, c.slot >= 0 ? ctx_slot(c) : 0);
+  DecideOut o;
+  const uint64_t my_id = pick_id(d, id_base + (uint64_t)i);
+  const bool handled = decide_stream(s, T, T, c, valid, w, win_words, RowPtr{row, (uint32_t)s.word_lo}, self_eword, now, seed, my_id, WarpVote(), o, budget);
+  uint32_t pending = __ballot_sync(0xffffffffu, valid && !handled);
+  while (pending) {
+    const int l = __ffs((int)pending) - 1;
+    pending &= pending - 1;
+    if (lane == l) ctx_w[warp] = c;
+    const int ml = __shfl_sync(0xffffffffu, m, l);
+    const uint64_t idl = __shfl_sync(0xffffffffu, my_id, l);
+    __syncwarp();
+    int32_t t2, c2, f2, g2;
+    decide_warp(s, ctx_w[warp], s.excl + (size_t)ml * RW, extra, now, seed, idl, &t2, &c2, &f2, &g2);
+    if (lane == l) { o.target = t2; o.n_candidates = c2; }
+    __syncwarp();
+  }
+  if (valid) out[i] = mmp_decision_out{o.target, o.n_candidates};
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // k_place_server -- the B = 1 path without a launch per call.  One warp stays resident for a BOUNDED time (life_ns, or
 // idle_ns without a request), polling the sequence word of a request header in pinned mapped host memory; a request (up to
 // 32 decisions, laid out like the graph path's buffer) is resolved with the same routine as k_place_small and answered by
@@ -984,6 +1053,7 @@ struct mmp_fleet {
     int64_t launches = 0, requests = 0;
     int64_t life_us = 2000, idle_us = 300;
   } srv;
+  int direct = 0, direct_minb = 4;  // MMP_KERNEL=direct: k_place_direct (no landing stages); MMP_DIRECT_MINB = 4 | 6 | 8 resident blocks per SM
   int small_max = 0;            // MMP_SMALL_MAX: untraced batches of up to this many decisions run on k_place_small (no landing stages:
                                 // one wave of 32-thread blocks), larger ones on the streaming kernel
   int lane_budget = LANE_BUDGET;  // MMP_LANE_BUDGET: walk steps per lane before a decision is handed to the whole warp
@@ -1119,6 +1189,14 @@ static cudaError_t launch_place_lanes(mmp_fleet *f, const PlaceArgs &a, cudaStre
 
 static cudaError_t launch_place(mmp_fleet *f, const PlaceArgs &a, cudaStream_t st) {
   const int rw = a.s.row_words;
+  // the direct kernel: rows are read straight from memory, only the words a decision looks at (MMP_KERNEL=direct | lanes)
+  if (!(a.tr || a.cand) && !a.emit_keys && !a.orig_id && f->direct && a.n > f->small_max && a.s.word_lo == 0 && a.s.word_hi == a.s.row_words) {
+    const int blocks = (a.n + 127) / 128;
+    auto kern = f->direct_minb == 8 ? k_place_direct<4, 8> : (f->direct_minb == 6 ? k_place_direct<4, 6> : k_place_direct<4, 4>);
+    kern<<<blocks, 128, 0, st>>>(a.s, a.in, a.n, a.fresh, a.n_fresh, a.extra, a.out, a.now, a.seed, a.id_base, f->lane_budget);
+    f->launches++;
+    return cudaGetLastError();
+  }
   // small launches: a batch that fits one wave of 32-decision blocks skips the landing-stage pipeline (its prologue and
   // its one-block-per-SM shape cost more than they hide when every warp has a single step to do)
   if (!(a.tr || a.cand) && !a.emit_keys && !a.orig_id && a.n <= f->small_max && a.s.word_lo == 0 && a.s.word_hi == a.s.row_words) {
@@ -1480,12 +1558,13 @@ int32_t mmp_fleet_create(const mmp_config *cfg, mmp_fleet **out) {
   CK(cudaStreamCreateWithFlags(&f->commit_stream, cudaStreamNonBlocking));
   f->hs.init(*cfg);
   if (const char *t = getenv("MMP_RING_K")) { int v = atoi(t); if (v == 2 || v == 4) f->ring_k = v; }
-  if (const char *t = getenv("MMP_KERNEL")) f->lanes = strcmp(t, "tile") != 0;
+  if (const char *t = getenv("MMP_KERNEL")) { f->lanes = strcmp(t, "tile") != 0; f->direct = !strcmp(t, "direct"); }
   if (const char *t = getenv("MMP_LANE_WARPS")) { int v = atoi(t); if (v == 8 || v == 10 || v == 12 || v == 14 || v == 16 || v == 20) f->lane_warps = v; }
   if (const char *t = getenv("MMP_LANE_STAGES")) f->lane_stages = atoi(t);
   if (const char *t = getenv("MMP_LANE_MODE")) f->lane_mode = atoi(t);
   if (const char *t = getenv("MMP_ONE")) f->one_mode = !strcmp(t, "lanes") ? 0 : (!strcmp(t, "small") ? 1 : (!strcmp(t, "server") ? 3 : 2));
   if (const char *t = getenv("MMP_COMMIT")) f->commit_host_only = strcmp(t, "host") == 0;
+  if (const char *t = getenv("MMP_DIRECT_MINB")) { int v = atoi(t); f->direct_minb = v == 8 ? 8 : (v == 6 ? 6 : 4); }
   if (const char *t = getenv("MMP_SMALL_MAX")) { int v = atoi(t); if (v >= 0) f->small_max = v; }
   if (const char *t = getenv("MMP_LANE_BUDGET")) { int v = atoi(t); if (v >= 1 && v <= 4096) f->lane_budget = v; }
   if (const char *t = getenv("MMP_SHARD_CHUNKS")) f->shard_chunks = atoi(t);
@@ -1855,6 +1934,7 @@ int32_t mmp_tune(mmp_fleet *f, const char *key, int64_t value) {
   if (!strcmp(key, "one_mode") && value >= 0 && value <= 3) f->one_mode = (int)value;
   else if (!strcmp(key, "server_life_us") && value >= 50 && value <= 1000000) f->srv.life_us = value;
   else if (!strcmp(key, "server_idle_us") && value >= 10 && value <= 1000000) f->srv.idle_us = value;
+  else if (!strcmp(key, "direct") && (value == 0 || value == 1)) f->direct = (int)value;
   else if (!strcmp(key, "small_max") && value >= 0 && value <= (1 << 24)) f->small_max = (int)value;
   else if (!strcmp(key, "lane_budget") && value >= 1 && value <= 4096) f->lane_budget = (int)value;
   else if (!strcmp(key, "lane_warps") && (value == 0 || value == 8 || value == 10 || value == 12 || value == 14 || value == 16 || value == 20)) f->lane_warps = (int)value;
