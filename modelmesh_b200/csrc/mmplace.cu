@@ -621,16 +621,41 @@ __global__ void __launch_bounds__(32) k_place_small(const SnapshotView s_arg, co
 // word, result) instead of the whole 1 280-byte row, and without the 41 KB stages an SM holds 16-32 warps instead of 12.
 // One warp per batch of 32 decisions, no per-warp software pipeline: the other resident warps hide the gathers.
 // ---------------------------------------------------------------------------------------------------------------
+// how many type slots have fewer than `few` candidates among the first `win` row words (one thread per slot)
+__global__ void k_sparse_slots(const uint32_t *__restrict__ cx, int row_words, int n_slots, int word_lo, int win, int few, int *__restrict__ out) {
+  const int sl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sl >= n_slots) return;
+  int c = 0;
+  for (int w = word_lo; w < word_lo + win && w < row_words; w++) c += __popc(cx[(size_t)sl * row_words + w]);
+  if (c < few) atomicAdd(out, 1);
+}
+// type slot of every decision of a batch (the sort key of the slot-ordered launch) and the identity permutation
+__global__ void k_slot_keys(const SnapshotView s, const mmp_decision_in *__restrict__ in, int n, uint16_t *__restrict__ keys, int32_t *__restrict__ idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int m = in[i].model;
+  uint32_t k = 0xffffu;
+  if (m >= 0 && m < s.n_models) {
+    const int ty = s.models[m].type_id;
+    k = (uint32_t)s.type_slot[(ty >= 0 && ty < s.n_type_ids) ? ty : 0] & 0x7fffu;  // (as prepare_ctx_b resolves it)
+  }
+  keys[i] = (uint16_t)k;
+  idx[i] = i;
+}
 template <int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB) k_place_direct(const SnapshotView s, const mmp_decision_in *__restrict__ in, int n,
                                                                   const FreshRow *__restrict__ fresh, int n_fresh,
                                                                   const int32_t *__restrict__ extra, mmp_decision_out *__restrict__ out,
-                                                                  int64_t now, uint64_t seed, uint64_t id_base, int budget) {
+                                                                  int64_t now, uint64_t seed, uint64_t id_base, int budget,
+                                                                  const int32_t *__restrict__ perm) {
   __shared__ uint32_t win_s[WARPS][32 * LANE_STRIDE];
   __shared__ DecisionCtx ctx_w[WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int i = (blockIdx.x * WARPS + warp) * 32 + lane;
-  const bool valid = i < n;
+  const int j_ = (blockIdx.x * WARPS + warp) * 32 + lane;
+  const bool valid = j_ < n;
+  // perm (optional): the batch in type-slot order -- decisions of one slot walk the same masks, so the 32 lanes of a warp
+  // finish their walks together instead of waiting for the longest (fleets with sparse candidate sets: C5)
+  const int i = valid ? (perm ? perm[j_] : j_) : 0;
   const int RW = s.excl_stride;
   mmp_decision_in d;
   d.model = -1; d.self = -1; d.last_used = 0; d.flags = 0; d.fresh = -1; d.extra_off = 0; d.extra_n = 0;
@@ -962,6 +987,8 @@ struct DeviceSnapshot {
   DevBuf front, nzw_full, nz_n_full;  // instance-sharded fleets: replicated first words of every row; word lists over the whole row
   SnapshotView view{};
   HostSnapshot host;  // kept for introspection and the small host-side parts of stats / reaper
+  DevBuf sparse_dev;
+  bool sparse_slots = false;  // most type slots have few candidates inside a decision's window: long walks (k_place_direct sorts big batches by slot)
   bool host_stale = false;  // built on the device: the rank-space vectors of `host` are downloaded on first use (host_mirror)
   int32_t n_models = 0;
   void release() {
@@ -979,6 +1006,7 @@ struct PlaceCtx {
   static constexpr int NSHARD_CHUNKS = 4;  // instance-sharded batches: scoring of chunk k+1 overlaps the all-reduce of chunk k
   cudaEvent_t shard_ev[NSHARD_CHUNKS + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   DevBuf d_in, d_out, d_fresh, d_extra, d_trace, d_cand;
+  DevBuf d_skey, d_skey2, d_sidx, d_sidx2, d_stmp;  // slot sort of a batch (k_slot_keys + cub radix sort -> perm)
   DevBuf d_open_flag, d_open_idx, d_n_open, d_cub, d_blocks, d_gathered, d_rows, d_in_open, d_out_open;  // instance-shard combine
   std::vector<FreshRow> fresh_host;
   // pinned, device-mapped scratch for tiny batches: the kernel reads the decisions and writes the results straight
@@ -1053,6 +1081,8 @@ struct mmp_fleet {
     int64_t launches = 0, requests = 0;
     int64_t life_us = 2000, idle_us = 300;
   } srv;
+  int sort_slots = 2;           // MMP_SORT_SLOTS = 0 never | 1 always | 2 (default) when the snapshot's candidate sets are sparse: k_place_direct
+                                // resolves a large batch in type-slot order
   int direct = 0, direct_minb = 4;  // MMP_KERNEL=direct: k_place_direct (no landing stages); MMP_DIRECT_MINB = 4 | 6 | 8 resident blocks per SM
   int small_max = 0;            // MMP_SMALL_MAX: untraced batches of up to this many decisions run on k_place_small (no landing stages:
                                 // one wave of 32-thread blocks), larger ones on the streaming kernel
@@ -1104,7 +1134,8 @@ static void release_ctx(mmp_fleet *f, PlaceCtx *c) {
 }
 static void destroy_ctx(PlaceCtx *c) {
   for (DevBuf *b : {&c->d_in, &c->d_out, &c->d_fresh, &c->d_extra, &c->d_trace, &c->d_cand, &c->d_open_flag,
-                    &c->d_open_idx, &c->d_n_open, &c->d_cub, &c->d_blocks, &c->d_gathered, &c->d_rows, &c->d_in_open, &c->d_out_open})
+                    &c->d_open_idx, &c->d_n_open, &c->d_cub, &c->d_blocks, &c->d_gathered, &c->d_rows, &c->d_in_open, &c->d_out_open,
+                    &c->d_skey, &c->d_skey2, &c->d_sidx, &c->d_sidx2, &c->d_stmp})
     b->release();
   if (c->e0) cudaEventDestroy(c->e0);
   if (c->e1) cudaEventDestroy(c->e1);
@@ -1134,6 +1165,8 @@ struct PlaceArgs {
   uint64_t seed, id_base;
   int emit_keys = 0;            // instance-sharded: write shard keys (uint64) into `out` instead of results
   const int32_t *orig_id = nullptr;  // gather pass: decision i reads row i of s.excl and hashes with id orig_id[i]
+  const int32_t *perm = nullptr;     // k_place_direct: position j of the launch resolves decision perm[j]
+  struct PlaceCtx *ctx = nullptr;    // scratch for the slot sort (the call's own context)
 };
 
 // ring depth (a power of two) / warps per block by row size: rows up to 2 KiB (16k instances) K=4 x 8 warps, up to 4 KiB K=2 x 8, beyond K=2 x 4
@@ -1192,8 +1225,22 @@ static cudaError_t launch_place(mmp_fleet *f, const PlaceArgs &a, cudaStream_t s
   // the direct kernel: rows are read straight from memory, only the words a decision looks at (MMP_KERNEL=direct | lanes)
   if (!(a.tr || a.cand) && !a.emit_keys && !a.orig_id && f->direct && a.n > f->small_max && a.s.word_lo == 0 && a.s.word_hi == a.s.row_words) {
     const int blocks = (a.n + 127) / 128;
+    const int32_t *perm = a.perm;
+    if (!perm && a.ctx && a.n >= 8192 && (f->sort_slots == 1 || (f->sort_slots == 2 && f->snaps[f->cur].sparse_slots))) {
+      PlaceCtx *c = a.ctx;  // slot order: key pass + 16-bit radix sort of the indices (a few tens of microseconds per million decisions)
+      cudaError_t e;
+      if ((e = c->d_skey.ensure((size_t)a.n * 2)) != cudaSuccess || (e = c->d_skey2.ensure((size_t)a.n * 2)) != cudaSuccess ||
+          (e = c->d_sidx.ensure((size_t)a.n * 4)) != cudaSuccess || (e = c->d_sidx2.ensure((size_t)a.n * 4)) != cudaSuccess) return e;
+      k_slot_keys<<<(a.n + 255) / 256, 256, 0, st>>>(a.s, a.in, a.n, c->d_skey.as<uint16_t>(), c->d_sidx.as<int32_t>());
+      size_t tmp = 0;
+      if ((e = cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->d_skey.as<uint16_t>(), c->d_skey2.as<uint16_t>(), c->d_sidx.as<int32_t>(), c->d_sidx2.as<int32_t>(), a.n, 0, 16, st)) != cudaSuccess) return e;
+      if ((e = c->d_stmp.ensure(tmp + 16)) != cudaSuccess) return e;
+      if ((e = cub::DeviceRadixSort::SortPairs(c->d_stmp.p, tmp, c->d_skey.as<uint16_t>(), c->d_skey2.as<uint16_t>(), c->d_sidx.as<int32_t>(), c->d_sidx2.as<int32_t>(), a.n, 0, 16, st)) != cudaSuccess) return e;
+      perm = c->d_sidx2.as<int32_t>();
+      f->launches += 2;
+    }
     auto kern = f->direct_minb == 8 ? k_place_direct<4, 8> : (f->direct_minb == 6 ? k_place_direct<4, 6> : k_place_direct<4, 4>);
-    kern<<<blocks, 128, 0, st>>>(a.s, a.in, a.n, a.fresh, a.n_fresh, a.extra, a.out, a.now, a.seed, a.id_base, f->lane_budget);
+    kern<<<blocks, 128, 0, st>>>(a.s, a.in, a.n, a.fresh, a.n_fresh, a.extra, a.out, a.now, a.seed, a.id_base, f->lane_budget, perm);
     f->launches++;
     return cudaGetLastError();
   }
@@ -1564,6 +1611,7 @@ int32_t mmp_fleet_create(const mmp_config *cfg, mmp_fleet **out) {
   if (const char *t = getenv("MMP_LANE_MODE")) f->lane_mode = atoi(t);
   if (const char *t = getenv("MMP_ONE")) f->one_mode = !strcmp(t, "lanes") ? 0 : (!strcmp(t, "small") ? 1 : (!strcmp(t, "server") ? 3 : 2));
   if (const char *t = getenv("MMP_COMMIT")) f->commit_host_only = strcmp(t, "host") == 0;
+  if (const char *t = getenv("MMP_SORT_SLOTS")) { int v = atoi(t); if (v >= 0 && v <= 2) f->sort_slots = v; }
   if (const char *t = getenv("MMP_DIRECT_MINB")) { int v = atoi(t); f->direct_minb = v == 8 ? 8 : (v == 6 ? 6 : 4); }
   if (const char *t = getenv("MMP_SMALL_MAX")) { int v = atoi(t); if (v >= 0) f->small_max = v; }
   if (const char *t = getenv("MMP_LANE_BUDGET")) { int v = atoi(t); if (v >= 1 && v <= 4096) f->lane_budget = v; }
@@ -1905,7 +1953,16 @@ static int32_t commit_locked(mmp_fleet *f) {
     f->launches += 2;
     CK(cudaGetLastError());
   }
+  int n_sparse = 0;
+  if (h.n_slots > 0) {
+    CK(ds.sparse_dev.ensure(16));
+    CK(cudaMemsetAsync(ds.sparse_dev.p, 0, 4, st));
+    k_sparse_slots<<<(h.n_slots + 63) / 64, 64, 0, st>>>((h.any_rs ? ds.candx : ds.cand).as<uint32_t>(), RW, h.n_slots, h.word_lo, LANE_WIN, 24, ds.sparse_dev.as<int>());
+    CK(cudaMemcpyAsync(&n_sparse, ds.sparse_dev.p, 4, cudaMemcpyDeviceToHost, st));
+    f->launches++;
+  }
   CK(cudaStreamSynchronize(st));
+  ds.sparse_slots = h.n_slots > 0 && 2 * n_sparse >= h.n_slots;
   SnapshotView &v = ds.view;
   v.n_ranks = h.n_ranks; v.row_words = RW; v.n_models = nm; v.max_instances = f->hs.cfg.max_instances;
   v.any_rs = h.any_rs; v.n_type_ids = (int32_t)h.type_slot.size(); v.min_space = f->hs.cfg.min_space_units;
@@ -1935,6 +1992,7 @@ int32_t mmp_tune(mmp_fleet *f, const char *key, int64_t value) {
   else if (!strcmp(key, "server_life_us") && value >= 50 && value <= 1000000) f->srv.life_us = value;
   else if (!strcmp(key, "server_idle_us") && value >= 10 && value <= 1000000) f->srv.idle_us = value;
   else if (!strcmp(key, "direct") && (value == 0 || value == 1)) f->direct = (int)value;
+  else if (!strcmp(key, "sort_slots") && value >= 0 && value <= 2) f->sort_slots = (int)value;
   else if (!strcmp(key, "small_max") && value >= 0 && value <= (1 << 24)) f->small_max = (int)value;
   else if (!strcmp(key, "lane_budget") && value >= 1 && value <= 4096) f->lane_budget = (int)value;
   else if (!strcmp(key, "lane_warps") && (value == 0 || value == 8 || value == 10 || value == 12 || value == 14 || value == 16 || value == 20)) f->lane_warps = (int)value;
@@ -2164,6 +2222,7 @@ static int32_t place_impl(mmp_fleet *f, const mmp_decision_in *in, int32_t n, co
   PlaceArgs a{vw, c->d_in.as<mmp_decision_in>(), n, c->d_fresh.as<FreshRow>(), n_fresh, c->d_extra.as<int32_t>(),
               c->d_out.as<mmp_decision_out>(), trace ? c->d_trace.as<mmp_decision_trace>() : nullptr,
               cand_mask ? c->d_cand.as<uint32_t>() : nullptr, now_ms, seed, f->id_base.load()};
+  a.ctx = c;
   CK(launch_place(f, a, st));
   CK(cudaMemcpyAsync(out, c->d_out.p, (size_t)n * sizeof(mmp_decision_out), cudaMemcpyDeviceToHost, st));
   if (trace) CK(cudaMemcpyAsync(trace, c->d_trace.p, (size_t)n * sizeof(mmp_decision_trace), cudaMemcpyDeviceToHost, st));
@@ -2257,6 +2316,7 @@ int32_t mmp_place_batch_device(mmp_fleet *f, const void *d_in, int32_t n, void *
   CK(c->d_extra.ensure(4));
   PlaceArgs a{ds.view, (const mmp_decision_in *)d_in, n, c->d_fresh.as<FreshRow>(), 0, c->d_extra.as<int32_t>(),
               (mmp_decision_out *)d_out, nullptr, nullptr, now_ms, seed, f->id_base.load()};
+  a.ctx = c;
   CK(cudaEventRecord(c->e0, c->stream));
   if (f->hs.cfg.shard_count > 1 || f->comm) {
     int32_t rcs = place_sharded(f, c, ds, (const mmp_decision_in *)d_in, n, c->d_fresh.as<FreshRow>(), 0, c->d_extra.as<int32_t>(), 0,

@@ -176,7 +176,7 @@ def test_latency_paths_equal_the_batch(product_lib, oracle_lib, config, nm, ni, 
         s.commit()
 
 
-@pytest.mark.parametrize("config,nm,ni,seed", [("C3", 20000, 10000, 3), ("C5", 6000, 5000, 5), ("MIX", 800, 300, 14), ("C2", 5000, 1000, 2)])
+@pytest.mark.parametrize("config,nm,ni,seed", [("C3", 20000, 10000, 3), ("C5", 9000, 5000, 5), ("MIX", 9000, 300, 14), ("C2", 5000, 1000, 2)])
 def test_direct_kernel_equals_the_streaming_kernel(product_lib, config, nm, ni, seed):
     """k_place_direct (rows read straight from memory: the window by three 16-byte loads, the rest through the word list) against
     k_place_lanes (whole rows through TMA landing stages) on the same batches, fresh rows / extra excludes included, and with a
@@ -187,11 +187,13 @@ def test_direct_kernel_equals_the_streaming_kernel(product_lib, config, nm, ni, 
         sd = make_decisions(fl, min(nm, 20000), seed, sweep=plain, plain=plain)
         kw = dict(fresh=sd.fresh if len(sd.fresh) else None, extra=sd.extra if len(sd.extra) else None)
         want = s.place_batch(sd.dec, fl.now_ms, 21, **kw)
-        for budget in (192, 6):
+        for budget, sort in ((192, 0), (192, 1), (6, 1), (6, 0)):  # sort 1: batches of >= 8192 decisions resolved in type-slot order
             s._ck(product_lib.mmp_tune(s.h, b"lane_budget", budget))
+            s._ck(product_lib.mmp_tune(s.h, b"sort_slots", sort))
             s._ck(product_lib.mmp_tune(s.h, b"direct", 1))
             got = s.place_batch(sd.dec, fl.now_ms, 21, **kw)
             s._ck(product_lib.mmp_tune(s.h, b"direct", 0))
-            assert np.array_equal(got, want), (plain, budget, np.nonzero(got != want)[0][:5])
+            assert np.array_equal(got, want), (plain, budget, sort, np.nonzero(got != want)[0][:5])
+        s._ck(product_lib.mmp_tune(s.h, b"sort_slots", 2))
         s._ck(product_lib.mmp_tune(s.h, b"lane_budget", 192))
     s.close()
