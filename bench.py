@@ -107,11 +107,18 @@ def measured_hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def scoring_kernel() -> str:
+    """The kernel mmp_place_batch_device launches for an untraced batch on an unsharded fleet: k_place_direct unless
+    MMP_KERNEL selects the streaming kernel (lanes) or the cooperative tiles (tile)."""
+    k = os.environ.get("MMP_KERNEL", "direct")
+    return {"lanes": "k_place_lanes", "tile": "k_place"}.get(k, "k_place_direct")
+
+
 def captured_traffic(batch: int):
-    """dram__bytes_read + dram__bytes_write of one k_place_lanes launch from the committed `ncu --set full` capture of this
-    configuration (profiles/r02_ncu_k_place_lanes_<config>.json, written by tools/ncu_summary.py), scaled per decision when
-    the capture was taken on another batch size (the traffic is proportional: one row per decision)."""
-    for name in (f"r02_ncu_k_place_lanes_{CONFIG.lower()}.json", "r01_ncu_k_place_lanes.json" if CONFIG == "C3" else ""):
+    """dram__bytes_read + dram__bytes_write of one launch of the scoring kernel from the committed `ncu --set full` capture of
+    this configuration (profiles/r02_ncu_<kernel>_<config>.json, written by tools/ncu_summary.py), scaled per decision when
+    the capture was taken on another batch size (the traffic is proportional to the number of decisions)."""
+    for name in (f"r02_ncu_{scoring_kernel()}_{CONFIG.lower()}.json",):
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
                 d = json.load(f)
@@ -656,7 +663,11 @@ def main():
         achieved = alg_bytes / k_avg_s / 1e9
         traffic, traffic_src = captured_traffic(B)
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "peak_source": peak_src, "kernel": "k_place_lanes",
+                    "traffic": traffic, "peak_source": peak_src, "kernel": scoring_kernel(),
+                    "traffic_GBps": (traffic / k_avg_s / 1e9) if traffic else None,
+                    "note": ("achieved = ALGORITHMIC bytes (whole bitmap row + model row + result per decision, SURVEY.md 8d) / kernel time. "
+                             "k_place_direct reads only the row words a decision looks at, so its DRAM traffic (`traffic`, ncu) is far below "
+                             "the algorithmic bytes and `frac` can exceed 1; traffic_GBps = traffic / kernel time is the physical HBM rate"),
                     "traffic_source": (traffic_src + " (ncu --set full, one launch; scaled per decision to this batch)") if traffic_src else None,
                     "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms_avg": 1000.0 * k_avg_s}
         cpu = None

@@ -715,41 +715,145 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_place_direct(const Snapsho
 // the response: two PCIe round trips instead of launch + synchronise.  Bounded lifetime: anything that waits for the
 // device to drain (cudaFree inside a commit) waits at most life_ns, and a crashed host leaves no kernel behind.
 // ---------------------------------------------------------------------------------------------------------------
-struct ServerResp { unsigned long long done_seq; int alive, served; unsigned long long pad[6]; };
-static_assert(sizeof(ServerResp) == 64, "response is one 64-byte line");
-__global__ void __launch_bounds__(32) k_place_server(const SnapshotView s_arg, volatile SmallHdr *hdr, volatile ServerResp *resp,
-                                                     const mmp_decision_in *in, const FreshRow *fresh, const int32_t *extra,
-                                                     mmp_decision_out *out, unsigned long long life_ns, unsigned long long idle_ns, int budget) {
+// request line 0 (one 64-byte line = one PCIe read per poll): everything a single decision without side tables needs.
+// seq: low 56 bits = request counter, top 8 bits = kind (1: one decision, its fresh row -- if any -- in line 1;
+// 2: a batch of up to 32 laid out like the graph path's buffer, sizes in line 1; 0xff: leave)
+struct SrvLine0 { unsigned long long seq; long long now; unsigned long long seed, id_base; mmp_decision_in d; };
+struct SrvLine1 { int n, n_fresh, n_extra, pad; FreshRow fr; unsigned long long pad2[3]; };
+struct ServerResp { unsigned long long done_seq; int alive, served; mmp_decision_out out0; unsigned long long pad[5]; };
+static_assert(sizeof(SrvLine0) == 64 && sizeof(SrvLine1) == 64 && sizeof(ServerResp) == 64, "one line each");
+struct SrvTabs {
+  uint32_t cx[LANE_SLOTS * LANE_WIN], p[LANE_SLOTS * LANE_WIN], full[LANE_WIN];
+  WordSumI csum[LANE_WIN];
+  __align__(16) int32_t count[LANE_WIN * 32];
+  __align__(16) RankRow rows[LANE_WIN * 32];
+};
+__global__ void __launch_bounds__(32) k_place_server(const SnapshotView s_arg, volatile SrvLine0 *l0, volatile SrvLine1 *l1, volatile ServerResp *resp,
+                                                     const mmp_decision_in *in_tab, const FreshRow *fresh_tab, const int32_t *extra,
+                                                     mmp_decision_out *out_tab, unsigned long long life_ns, unsigned long long idle_ns, int budget) {
   __shared__ DecisionCtx ctx_one;
+  __shared__ __align__(16) uint32_t line_s[16];
+  __shared__ FreshRow fresh_s;
+  __shared__ uint32_t win_s[32 * LANE_STRIDE];
+  // the window part of the lane tables, as in k_place_lanes: the in-window steps of a decision read shared memory only
+  __shared__ SrvTabs tabs;
+  uint32_t *f_cx = tabs.cx, *f_p = tabs.p, *f_full = tabs.full;
+  WordSumI *f_csum = tabs.csum;
+  int32_t *f_count = tabs.count;
+  RankRow *f_rows = tabs.rows;
   const int lane = threadIdx.x;
+  const SnapshotView &sv = s_arg;
+  const int WS = sv.word_lo;
+  const uint32_t win_words = (uint32_t)min(LANE_WIN, sv.word_hi - sv.word_lo);
+  {
+    const int nsl = min(sv.n_slots, LANE_SLOTS);
+    const uint32_t *gcx = sv.any_rs ? sv.candx : sv.cand;
+    for (int i = lane; i < nsl * LANE_WIN; i += 32) {
+      const int sl = i / LANE_WIN, w = i - sl * LANE_WIN;
+      const bool inw = (uint32_t)w < win_words;
+      f_cx[i] = inw ? gcx[(size_t)sl * sv.row_words + WS + w] : 0u;
+      f_p[i] = inw ? sv.pref[(size_t)sl * sv.row_words + WS + w] : 0u;
+    }
+    for (int w = lane; w < LANE_WIN; w += 32) {
+      const bool inw = (uint32_t)w < win_words;
+      f_full[w] = inw ? sv.full[WS + w] : 0u;
+      f_csum[w] = inw ? sv.csum[WS + w] : WordSumI{0, 0};
+    }
+    for (int i = lane; i < LANE_WIN * 32; i += 32) {
+      const int r = WS * 32 + i;
+      const bool inw = (uint32_t)(i >> 5) < win_words && r < sv.n_ranks;
+      f_count[i] = inw ? sv.count_col[r] : 0;
+      RankRow z; z.lru = 0; z.rem = 0; z.count = 0; z.rpm = 0; z.idx = -1; z.flags = 0;
+      f_rows[i] = inw ? sv.rows[r] : z;
+    }
+  }
+  __syncwarp();
   unsigned long long t0, t_last, t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   t_last = t0;
   unsigned long long last = resp->done_seq;
   int served = 0;
   for (;;) {
-    unsigned long long seq = 0;
-    int stop = 0;
-    if (lane == 0) {
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seq) : "l"(&hdr->seq) : "memory");
-      stop = hdr->stop;
-    }
-    seq = __shfl_sync(0xffffffffu, seq, 0);
-    stop = __shfl_sync(0xffffffffu, stop, 0);
-    if (seq != last) {
-      SnapshotView s = s_arg;
-      s.n_extra = hdr->n_extra;
-      place_small_block(s, in, hdr->n, fresh, hdr->n_fresh, extra, out, hdr->now, hdr->seed, hdr->id_base, budget, 0, &ctx_one);
-      __threadfence_system();
-      __syncwarp();
-      if (lane == 0) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&resp->done_seq), "l"(seq) : "memory");
-      last = seq;
-      served++;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_last));
-    } else {
+    // one poll = one 64-byte read of line 0 (lanes 0..15, four bytes each)
+    uint32_t v = 0;
+    if (lane < 16) v = reinterpret_cast<volatile uint32_t *>(l0)[lane];
+    const unsigned long long seq = (unsigned long long)__shfl_sync(0xffffffffu, v, 0) | ((unsigned long long)__shfl_sync(0xffffffffu, v, 1) << 32);
+    if (seq == last) {
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      if (stop || t - t0 > life_ns || t - t_last > idle_ns) break;
+      if (t - t0 > life_ns || t - t_last > idle_ns) break;
+      continue;
     }
+    const unsigned kind = (unsigned)(seq >> 56);
+    if (kind == 0xffu) break;
+    if (lane < 16) line_s[lane] = v;
+    __syncwarp();
+    const long long now = (long long)((unsigned long long)line_s[2] | ((unsigned long long)line_s[3] << 32));
+    const unsigned long long seed = (unsigned long long)line_s[4] | ((unsigned long long)line_s[5] << 32);
+    const unsigned long long id_base = (unsigned long long)line_s[6] | ((unsigned long long)line_s[7] << 32);
+    SnapshotView s = s_arg;
+    if (kind == 1u) {
+      // ---- one decision: record from the line, window straight from the row, tables from shared memory ----
+      const bool valid = lane == 0;
+      mmp_decision_in d;
+      d.model = -1; d.self = -1; d.last_used = 0; d.flags = 0; d.fresh = -1; d.extra_off = 0; d.extra_n = 0;
+      if (valid) d = *reinterpret_cast<const mmp_decision_in *>(line_s + 8);
+      int n_fresh = 0;
+      s.n_extra = 0;
+      if (__shfl_sync(0xffffffffu, d.fresh, 0) >= 0 || __shfl_sync(0xffffffffu, d.extra_n, 0) > 0) {  // side tables: a second read
+        if (lane == 0) { n_fresh = l1->n_fresh; s.n_extra = l1->n_extra; fresh_s.lru = l1->fr.lru; fresh_s.rem = l1->fr.rem; fresh_s.count = l1->fr.count; fresh_s.rpm = l1->fr.rpm; }
+        n_fresh = __shfl_sync(0xffffffffu, n_fresh, 0);
+        s.n_extra = __shfl_sync(0xffffffffu, s.n_extra, 0);
+        __syncwarp();
+      }
+      const int RW = s.excl_stride;
+      const int m = (valid && d.model >= 0 && d.model < s.n_models) ? d.model : 0;
+      const uint32_t *row = s.excl + (size_t)m * RW;
+      uint4 q[LANE_WIN / 4];
+#pragma unroll
+      for (int j = 0; j < LANE_WIN / 4; j++) {
+        q[j] = make_uint4(0u, 0u, 0u, 0u);
+        if (valid && (uint32_t)(j * 4) < win_words) q[j] = __ldg(reinterpret_cast<const uint4 *>(row) + j);
+      }
+      DecisionCtx c;
+      c.slot = -2; c.self_rank = -1; c.self_bits = 0; c.self_count = 0;
+      if (valid) prepare_ctx(s, d, &fresh_s, min(n_fresh, 1), extra, c);
+      uint32_t self_eword = 0;
+      if (valid && c.self_rank >= 0) self_eword = __ldg(row + (c.self_rank >> 5) - s.word_lo);
+      uint32_t *w = win_s + lane * LANE_STRIDE;
+#pragma unroll
+      for (int j = 0; j < LANE_WIN / 4; j++) { w[j * 4] = q[j].x; w[j * 4 + 1] = q[j].y; w[j * 4 + 2] = q[j].z; w[j * 4 + 3] = q[j].w; }
+      __syncwarp();
+      const int slot = c.slot >= 0 ? ctx_slot(c) : 0;
+      const LaneTables T = lane_tables_global(s, slot);
+      LaneTables Tw = T;
+      if (slot < LANE_SLOTS) { Tw.cx = f_cx + slot * LANE_WIN - WS; Tw.p = f_p + slot * LANE_WIN - WS; }
+      Tw.full = f_full - WS; Tw.csum = f_csum - WS; Tw.count_col = f_count - WS * 32; Tw.rows = f_rows - WS * 32;
+      DecideOut o;
+      const uint64_t my_id = pick_id(d, id_base);
+      const bool handled = decide_stream(s, Tw, T, c, valid, w, win_words, RowPtr{row, (uint32_t)s.word_lo}, self_eword, now, seed, my_id, WarpVote(), o, budget);
+      if (__shfl_sync(0xffffffffu, (int)(!handled), 0)) {
+        if (lane == 0) ctx_one = c;
+        __syncwarp();
+        int32_t t2, c2, f2, g2;
+        decide_warp(s, ctx_one, s.excl + (size_t)__shfl_sync(0xffffffffu, m, 0) * RW, extra, now, seed, __shfl_sync(0xffffffffu, my_id, 0), &t2, &c2, &f2, &g2);
+        if (lane == 0) { o.target = t2; o.n_candidates = c2; }
+        __syncwarp();
+      }
+      if (lane == 0) { resp->out0.target = o.target; resp->out0.n_candidates = o.n_candidates; }
+    } else {
+      // ---- a batch of up to 32 through the mapped tables (sizes in line 1) ----
+      int n = 0, n_fresh = 0, n_extra = 0;
+      if (lane == 0) { n = l1->n; n_fresh = l1->n_fresh; n_extra = l1->n_extra; }
+      n = __shfl_sync(0xffffffffu, n, 0); n_fresh = __shfl_sync(0xffffffffu, n_fresh, 0); n_extra = __shfl_sync(0xffffffffu, n_extra, 0);
+      s.n_extra = n_extra;
+      place_small_block(s, in_tab, n, fresh_tab, n_fresh, extra, out_tab, now, seed, id_base, budget, 0, &ctx_one);
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&resp->done_seq), "l"(seq) : "memory");
+    last = seq;
+    served++;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_last));
   }
   if (lane == 0) {
     resp->served = served;
@@ -784,6 +888,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_place_dealt(const Snapshot
                                                             unsigned int *__restrict__ done, unsigned long long *__restrict__ remote_words) {
   extern __shared__ __align__(16) unsigned char dealt_smem[];
   __shared__ DecisionCtx ctx_w[WARPS];
+  __shared__ uint32_t win_d[WARPS][32 * LANE_STRIDE];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int RW = s.row_words;
   uint32_t *row_s = reinterpret_cast<uint32_t *>(dealt_smem) + (size_t)warp * RW;  // whole row of a decision redone by the warp
@@ -800,15 +905,22 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_place_dealt(const Snapshot
   LaneTables T = lane_tables_global(s, c.slot >= 0 ? ctx_slot(c) : 0);
   {
     const int slot = c.slot >= 0 ? ctx_slot(c) : 0;
-    T.nzw = nzw_full + (size_t)slot * RW; T.nz_n = nz_count(nz_n_full[slot]); T.nz_skip = 0;
+    T.nzw = nzw_full + (size_t)slot * RW; T.nz_n = nz_count(nz_n_full[slot]); T.nz_skip = nz_skipped(nz_n_full[slot]);
   }
   RowDealt row{front, P.blocks, (uint32_t)front_words, (uint32_t)s.excl_stride, (uint32_t)s.excl_stride, (uint64_t)m, (uint32_t)me, 0u};
   uint32_t self_eword = 0;
   if (valid && c.self_rank >= 0) self_eword = row.word((uint32_t)(c.self_rank >> 5));
+  // the window: the first MMP_LANE_WIN words of the row, from the replicated front (local memory on every shard)
+  const uint32_t win_words = (uint32_t)min(min(LANE_WIN, front_words), RW);
+  uint32_t *w = win_d[warp] + lane * LANE_STRIDE;
+#pragma unroll
+  for (int j = 0; j < LANE_WIN; j++) w[j] = (valid && (uint32_t)j < win_words) ? __ldg(front + (size_t)m * front_words + j) : 0u;
+  __syncwarp();
+  if (win_words < (uint32_t)LANE_WIN) T.nz_skip = 0;  // (a front shorter than the window: no window at all)
   DecideOut o;
   o.target = MMP_TARGET_NONE; o.n_candidates = 0;
   const uint64_t my_id = pick_id(d, id_base + (uint64_t)i);
-  const bool handled = decide_stream(s, T, T, c, valid, nullptr, 0u, row, self_eword, now, seed, my_id, WarpVote(), o, budget);
+  const bool handled = decide_stream(s, T, T, c, valid, w, win_words < (uint32_t)LANE_WIN ? 0u : win_words, row, self_eword, now, seed, my_id, WarpVote(), o, budget);
   uint32_t pending = __ballot_sync(0xffffffffu, valid && !handled);
   while (pending) {  // the cooperative general routine over the whole row, assembled in shared memory
     const int l = __ffs((int)pending) - 1;
@@ -1053,7 +1165,7 @@ struct mmp_fleet {
     bool opened[MAX_SHARDS][4] = {};
     uint64_t step = 0;
     int64_t batches = 0, result_bytes = 0;
-    int minb = 4;
+    int minb = 6;
     int off = 0;                            // MMP_SHARD_PEERS=0 keeps the collective path although peers were imported
   } peers;
   std::mutex comm_mu;           // collectives of one communicator are issued by one thread at a time
@@ -1083,7 +1195,7 @@ struct mmp_fleet {
   } srv;
   int sort_slots = 2;           // MMP_SORT_SLOTS = 0 never | 1 always | 2 (default) when the snapshot's candidate sets are sparse: k_place_direct
                                 // resolves a large batch in type-slot order
-  int direct = 0, direct_minb = 4;  // MMP_KERNEL=direct: k_place_direct (no landing stages); MMP_DIRECT_MINB = 4 | 6 | 8 resident blocks per SM
+  int direct = 1, direct_minb = 6;  // MMP_KERNEL=direct: k_place_direct (no landing stages); MMP_DIRECT_MINB = 4 | 6 | 8 resident blocks per SM
   int small_max = 0;            // MMP_SMALL_MAX: untraced batches of up to this many decisions run on k_place_small (no landing stages:
                                 // one wave of 32-thread blocks), larger ones on the streaming kernel
   int lane_budget = LANE_BUDGET;  // MMP_LANE_BUDGET: walk steps per lane before a decision is handed to the whole warp
@@ -1562,7 +1674,7 @@ int32_t mmp_shard_ipc_import(mmp_fleet *f, const void *blobs) {
     }
   }
   if (const char *t = getenv("MMP_SHARD_PEERS")) pr.off = atoi(t) == 0;
-  if (const char *t = getenv("MMP_DEALT_MINB")) pr.minb = atoi(t) == 6 ? 6 : 4;
+  if (const char *t = getenv("MMP_DEALT_MINB")) pr.minb = atoi(t) == 4 ? 4 : 6;
   pr.ready = true;
   return MMP_OK;
 }
@@ -1605,7 +1717,7 @@ int32_t mmp_fleet_create(const mmp_config *cfg, mmp_fleet **out) {
   CK(cudaStreamCreateWithFlags(&f->commit_stream, cudaStreamNonBlocking));
   f->hs.init(*cfg);
   if (const char *t = getenv("MMP_RING_K")) { int v = atoi(t); if (v == 2 || v == 4) f->ring_k = v; }
-  if (const char *t = getenv("MMP_KERNEL")) { f->lanes = strcmp(t, "tile") != 0; f->direct = !strcmp(t, "direct"); }
+  if (const char *t = getenv("MMP_KERNEL")) { f->lanes = strcmp(t, "tile") != 0; f->direct = strcmp(t, "lanes") != 0 && strcmp(t, "tile") != 0; }
   if (const char *t = getenv("MMP_LANE_WARPS")) { int v = atoi(t); if (v == 8 || v == 10 || v == 12 || v == 14 || v == 16 || v == 20) f->lane_warps = v; }
   if (const char *t = getenv("MMP_LANE_STAGES")) f->lane_stages = atoi(t);
   if (const char *t = getenv("MMP_LANE_MODE")) f->lane_mode = atoi(t);
@@ -2024,12 +2136,14 @@ int32_t mmp_commit_info(mmp_fleet *f, int32_t *path, double *ms) {
 static void server_stop(mmp_fleet *f) {
   mmp_fleet::Server &sv = f->srv;
   if (!sv.mapped || !sv.running) return;
-  volatile SmallHdr *hdr = reinterpret_cast<volatile SmallHdr *>(sv.mapped);
-  hdr->stop = 1;
+  volatile SrvLine0 *l0 = reinterpret_cast<volatile SrvLine0 *>(sv.mapped);
+  sv.seq++;
+  l0->seq = (sv.seq & 0x00ffffffffffffffull) | (0xffull << 56);  // kind 0xff: leave
   std::atomic_thread_fence(std::memory_order_seq_cst);
   cudaStreamSynchronize(sv.stream);
   sv.running = false;
 }
+// mapped buffer: [line 0][line 1][32 decisions][32 results][32 fresh rows][32 x MMP_MAX_EXTRA extras] ... [response line]
 static int32_t place_server(mmp_fleet *f, const DeviceSnapshot &ds, const mmp_decision_in *in, int32_t n, const FreshRow *fresh, int32_t n_fresh,
                             const int32_t *extra, int32_t n_extra, mmp_decision_out *out, int64_t now_ms, uint64_t seed) {
   mmp_fleet::Server &sv = f->srv;
@@ -2040,31 +2154,44 @@ static int32_t place_server(mmp_fleet *f, const DeviceSnapshot &ds, const mmp_de
   }
   unsigned char *h = sv.mapped, *dbase = nullptr;
   CK(cudaHostGetDevicePointer((void **)&dbase, h, 0));
-  const size_t g_in = 64, g_out = g_in + 32 * sizeof(mmp_decision_in), g_fr = g_out + 32 * sizeof(mmp_decision_out), g_ex = g_fr + 32 * sizeof(FreshRow),
+  const size_t g_in = 128, g_out = g_in + 32 * sizeof(mmp_decision_in), g_fr = g_out + 32 * sizeof(mmp_decision_out), g_ex = g_fr + 32 * sizeof(FreshRow),
                g_resp = PlaceCtx::MAPPED_BYTES - 64;
-  volatile SmallHdr *hdr = reinterpret_cast<volatile SmallHdr *>(h);
+  static_assert(128 + 32 * (sizeof(mmp_decision_in) + sizeof(mmp_decision_out) + sizeof(FreshRow)) + 32 * MMP_MAX_EXTRA * 4 + 64 <= PlaceCtx::MAPPED_BYTES, "mapped layout");
+  volatile SrvLine0 *l0 = reinterpret_cast<volatile SrvLine0 *>(h);
+  volatile SrvLine1 *l1 = reinterpret_cast<volatile SrvLine1 *>(h + 64);
   volatile ServerResp *resp = reinterpret_cast<volatile ServerResp *>(h + g_resp);
   if (sv.running && sv.epoch != f->epoch) server_stop(f);  // its snapshot view is another epoch's
-  memcpy(h + g_in, in, (size_t)n * sizeof(mmp_decision_in));
-  if (n_fresh) memcpy(h + g_fr, fresh, (size_t)n_fresh * sizeof(FreshRow));
-  if (n_extra) memcpy(h + g_ex, extra, (size_t)n_extra * 4);
-  hdr->now = now_ms; hdr->seed = seed; hdr->id_base = f->id_base.load(); hdr->n = n; hdr->n_fresh = n_fresh; hdr->n_extra = n_extra;
+  // kind 1: one decision whose side tables are at most its own fresh row (the shape of getNext on a request thread)
+  const bool single = n == 1 && n_extra == 0 && (in[0].fresh < 0 || in[0].fresh == 0) && n_fresh <= 1;
+  if (single) {
+    mmp_decision_in d = in[0];
+    if (n_fresh) { FreshRow fr = fresh[0]; memcpy((void *)&l1->fr, &fr, sizeof(fr)); }
+    l1->n = 1; l1->n_fresh = n_fresh; l1->n_extra = 0;
+    memcpy((void *)&l0->d, &d, sizeof(d));
+  } else {
+    memcpy(h + g_in, in, (size_t)n * sizeof(mmp_decision_in));
+    if (n_fresh) memcpy(h + g_fr, fresh, (size_t)n_fresh * sizeof(FreshRow));
+    if (n_extra) memcpy(h + g_ex, extra, (size_t)n_extra * 4);
+    l1->n = n; l1->n_fresh = n_fresh; l1->n_extra = n_extra;
+  }
+  l0->now = now_ms; l0->seed = seed; l0->id_base = f->id_base.load();
   auto launch = [&]() -> int32_t {
-    hdr->stop = 0; resp->alive = 1;
+    if ((l0->seq >> 56) == 0xffull) l0->seq = resp->done_seq;  // (a "leave" left behind by server_stop is not for the new server)
+    resp->alive = 1;
     std::atomic_thread_fence(std::memory_order_seq_cst);
-    SnapshotView gv = ds.view;
-    k_place_server<<<1, 32, 0, sv.stream>>>(gv, reinterpret_cast<volatile SmallHdr *>(dbase), reinterpret_cast<volatile ServerResp *>(dbase + g_resp),
-                                          (const mmp_decision_in *)(dbase + g_in), (const FreshRow *)(dbase + g_fr), (const int32_t *)(dbase + g_ex),
-                                          (mmp_decision_out *)(dbase + g_out), (unsigned long long)sv.life_us * 1000ull,
-                                          (unsigned long long)sv.idle_us * 1000ull, f->lane_budget);
+    k_place_server<<<1, 32, 0, sv.stream>>>(ds.view, reinterpret_cast<volatile SrvLine0 *>(dbase), reinterpret_cast<volatile SrvLine1 *>(dbase + 64),
+                                          reinterpret_cast<volatile ServerResp *>(dbase + g_resp), (const mmp_decision_in *)(dbase + g_in),
+                                          (const FreshRow *)(dbase + g_fr), (const int32_t *)(dbase + g_ex), (mmp_decision_out *)(dbase + g_out),
+                                          (unsigned long long)sv.life_us * 1000ull, (unsigned long long)sv.idle_us * 1000ull, f->lane_budget);
     CK(cudaGetLastError());
     sv.running = true; sv.epoch = f->epoch; sv.launches++; f->launches++;
     return MMP_OK;
   };
   if (!sv.running || resp->alive == 0) { int32_t rc = launch(); if (rc < 0) return rc; }
-  const uint64_t seq = ++sv.seq;
+  sv.seq++;
+  const uint64_t seq = (sv.seq & 0x00ffffffffffffffull) | ((uint64_t)(single ? 1 : 2) << 56);
   std::atomic_thread_fence(std::memory_order_seq_cst);
-  hdr->seq = seq;
+  l0->seq = seq;  // (the last store into line 0: a reader that sees it sees the request)
   std::atomic_thread_fence(std::memory_order_seq_cst);
   const auto t0 = std::chrono::steady_clock::now();
   for (uint32_t spins = 0;; spins++) {
@@ -2082,7 +2209,8 @@ static int32_t place_server(mmp_fleet *f, const DeviceSnapshot &ds, const mmp_de
     }
   }
   std::atomic_thread_fence(std::memory_order_seq_cst);
-  memcpy(out, h + g_out, (size_t)n * sizeof(mmp_decision_out));
+  if (single) { out[0].target = resp->out0.target; out[0].n_candidates = resp->out0.n_candidates; }
+  else memcpy(out, h + g_out, (size_t)n * sizeof(mmp_decision_out));
   sv.requests++;
   return MMP_OK;
 }

@@ -186,6 +186,7 @@ def test_direct_kernel_equals_the_streaming_kernel(product_lib, config, nm, ni, 
     for plain in (True, False):
         sd = make_decisions(fl, min(nm, 20000), seed, sweep=plain, plain=plain)
         kw = dict(fresh=sd.fresh if len(sd.fresh) else None, extra=sd.extra if len(sd.extra) else None)
+        s._ck(product_lib.mmp_tune(s.h, b"direct", 0))
         want = s.place_batch(sd.dec, fl.now_ms, 21, **kw)
         for budget, sort in ((192, 0), (192, 1), (6, 1), (6, 0)):  # sort 1: batches of >= 8192 decisions resolved in type-slot order
             s._ck(product_lib.mmp_tune(s.h, b"lane_budget", budget))
@@ -195,5 +196,6 @@ def test_direct_kernel_equals_the_streaming_kernel(product_lib, config, nm, ni, 
             s._ck(product_lib.mmp_tune(s.h, b"direct", 0))
             assert np.array_equal(got, want), (plain, budget, sort, np.nonzero(got != want)[0][:5])
         s._ck(product_lib.mmp_tune(s.h, b"sort_slots", 2))
+        s._ck(product_lib.mmp_tune(s.h, b"direct", 1))
         s._ck(product_lib.mmp_tune(s.h, b"lane_budget", 192))
     s.close()
