@@ -536,9 +536,9 @@ def main():
                 if i >= 300:
                     ts.append(1e6 * (time.perf_counter() - t0))
             lat[label] = {"p50_us": float(np.percentile(ts, 50)), "p99_us": float(np.percentile(ts, 99)), "n": len(ts)}
-        solver._ck(lib.mmp_tune(solver.h, b"one_mode", 2))
-        lat.update(lat["cuda_graph"])  # the default path: k_place_small replayed as a CUDA graph, zero-copy mapped buffers
-        lat["default_path"] = "cuda_graph"
+        solver._ck(lib.mmp_tune(solver.h, b"one_mode", 3))
+        lat.update(lat["resident_server"])  # the default path: a request posted to the resident k_place_server
+        lat["default_path"] = "resident_server"
         lat["note"] = ("host timer around mmp_place_one (launch + synchronise + 8-byte result through mapped memory); resident_server = a request "
                        "posted to k_place_server (a warp resident for a bounded time polling mapped memory: no launch per call, mmp_tune one_mode=3), cuda_graph = one "
                        "k_place_small node replayed, small_kernel = the same kernel as a stream launch, streaming_kernel = round 1's path")

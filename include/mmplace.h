@@ -402,7 +402,7 @@ int32_t mmp_registry_prune(mmp_fleet *, int32_t self, int64_t now_ms, int64_t as
 
 /* tuning / measurement knobs, same meaning as the MMP_* environment variables read at mmp_fleet_create:
  *   "one_mode"        how a batch of <= 32 decisions is launched: 0 the streaming kernel (k_place_lanes), 1 the latency kernel
- *                     k_place_small as a stream launch, 2 (default) k_place_small as a replayed CUDA graph, 3 a request to the
+ *                     k_place_small as a stream launch, 2 k_place_small as a replayed CUDA graph, 3 (default) a request to the
  *                     resident server kernel k_place_server (no launch per call: the host posts the request into mapped memory
  *                     and spins on the answer; one caller at a time, concurrent callers take the graph path)
  *   "server_life_us"  longest residence of one k_place_server launch (default 2000): bounds how long a device-wide wait

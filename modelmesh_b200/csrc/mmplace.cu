@@ -586,7 +586,9 @@ __device__ __forceinline__ void place_small_block(const SnapshotView &s, const m
   if (valid && c.self_rank >= 0) self_eword = __ldg(row + (c.self_rank >> 5));
   DecideOut o;
   const uint64_t my_id = pick_id(d, id_base + (uint64_t)i);
-  const bool handled = decide_stream(s, T, T, c, valid, nullptr, 0u, RowPtr{row, (uint32_t)s.word_lo}, self_eword, now, seed, my_id, WarpVote(), o, budget);
+  __shared__ uint32_t chunk_b[32 * MMP_CHUNK_WORDS];  // (callers are one-warp blocks)
+  const bool handled = decide_stream(s, T, T, c, valid, nullptr, 0u, RowPtr{row, (uint32_t)s.word_lo}, self_eword, now, seed, my_id, WarpVote(), o, budget,
+                                     chunk_b + lane * MMP_CHUNK_WORDS);
   uint32_t pending = __ballot_sync(0xffffffffu, valid && !handled);
   while (pending) {
     const int l = __ffs((int)pending) - 1;
@@ -649,6 +651,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_place_direct(const Snapsho
                                                                   int64_t now, uint64_t seed, uint64_t id_base, int budget,
                                                                   const int32_t *__restrict__ perm) {
   __shared__ uint32_t win_s[WARPS][32 * LANE_STRIDE];
+  __shared__ uint32_t chunk_s[WARPS][32 * MMP_CHUNK_WORDS];
   __shared__ DecisionCtx ctx_w[WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int j_ = (blockIdx.x * WARPS + warp) * 32 + lane;
@@ -690,7 +693,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_place_direct(const Snapsho
   const LaneTables T = lane_tables_global(s, c.slot >= 0 ? ctx_slot(c) : 0);
   DecideOut o;
   const uint64_t my_id = pick_id(d, id_base + (uint64_t)i);
-  const bool handled = decide_stream(s, T, T, c, valid, w, win_words, RowPtr{row, (uint32_t)s.word_lo}, self_eword, now, seed, my_id, WarpVote(), o, budget);
+  const bool handled = decide_stream(s, T, T, c, valid, w, win_words, RowPtr{row, (uint32_t)s.word_lo}, self_eword, now, seed, my_id, WarpVote(), o, budget,
+                                     chunk_s[warp] + lane * MMP_CHUNK_WORDS);
   uint32_t pending = __ballot_sync(0xffffffffu, valid && !handled);
   while (pending) {
     const int l = __ffs((int)pending) - 1;
@@ -735,6 +739,7 @@ __global__ void __launch_bounds__(32) k_place_server(const SnapshotView s_arg, v
   __shared__ __align__(16) uint32_t line_s[16];
   __shared__ FreshRow fresh_s;
   __shared__ uint32_t win_s[32 * LANE_STRIDE];
+  __shared__ uint32_t chunk_v[32 * MMP_CHUNK_WORDS];
   // the window part of the lane tables, as in k_place_lanes: the in-window steps of a decision read shared memory only
   __shared__ SrvTabs tabs;
   uint32_t *f_cx = tabs.cx, *f_p = tabs.p, *f_full = tabs.full;
@@ -830,7 +835,8 @@ __global__ void __launch_bounds__(32) k_place_server(const SnapshotView s_arg, v
       Tw.full = f_full - WS; Tw.csum = f_csum - WS; Tw.count_col = f_count - WS * 32; Tw.rows = f_rows - WS * 32;
       DecideOut o;
       const uint64_t my_id = pick_id(d, id_base);
-      const bool handled = decide_stream(s, Tw, T, c, valid, w, win_words, RowPtr{row, (uint32_t)s.word_lo}, self_eword, now, seed, my_id, WarpVote(), o, budget);
+      const bool handled = decide_stream(s, Tw, T, c, valid, w, win_words, RowPtr{row, (uint32_t)s.word_lo}, self_eword, now, seed, my_id, WarpVote(), o, budget,
+                                         chunk_v + lane * MMP_CHUNK_WORDS);
       if (__shfl_sync(0xffffffffu, (int)(!handled), 0)) {
         if (lane == 0) ctx_one = c;
         __syncwarp();
@@ -889,6 +895,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_place_dealt(const Snapshot
   extern __shared__ __align__(16) unsigned char dealt_smem[];
   __shared__ DecisionCtx ctx_w[WARPS];
   __shared__ uint32_t win_d[WARPS][32 * LANE_STRIDE];
+  __shared__ uint32_t chunk_d[WARPS][32 * MMP_CHUNK_WORDS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int RW = s.row_words;
   uint32_t *row_s = reinterpret_cast<uint32_t *>(dealt_smem) + (size_t)warp * RW;  // whole row of a decision redone by the warp
@@ -920,7 +927,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_place_dealt(const Snapshot
   DecideOut o;
   o.target = MMP_TARGET_NONE; o.n_candidates = 0;
   const uint64_t my_id = pick_id(d, id_base + (uint64_t)i);
-  const bool handled = decide_stream(s, T, T, c, valid, w, win_words < (uint32_t)LANE_WIN ? 0u : win_words, row, self_eword, now, seed, my_id, WarpVote(), o, budget);
+  const bool handled = decide_stream(s, T, T, c, valid, w, win_words < (uint32_t)LANE_WIN ? 0u : win_words, row, self_eword, now, seed, my_id, WarpVote(), o, budget,
+                                     chunk_d[warp] + lane * MMP_CHUNK_WORDS);
   uint32_t pending = __ballot_sync(0xffffffffu, valid && !handled);
   while (pending) {  // the cooperative general routine over the whole row, assembled in shared memory
     const int l = __ffs((int)pending) - 1;
@@ -1180,7 +1188,7 @@ struct mmp_fleet {
                                 // instances: 3 stages 3.5, 4 stages 4.1-4.3, 5 stages 3.8 G decisions/s (the fifth stage costs the L1
                                 // its 196 -> 228 KB carve-out step and the lane tables no longer stay resident)
   int shard_chunks = 1;         // MMP_SHARD_CHUNKS (see place_sharded)
-  int one_mode = 2;             // MMP_ONE = lanes | small | graph | server: how tiny batches are launched (0: the streaming kernel, 1: k_place_small
+  int one_mode = 3;             // MMP_ONE = lanes | small | graph | server: how tiny batches are launched (0: the streaming kernel, 1: k_place_small
                                 // as a stream launch, 2: k_place_small as a replayed CUDA graph, 3: a request to the resident k_place_server)
   // the resident B = 1 server (one_mode 3, k_place_server)
   struct Server {

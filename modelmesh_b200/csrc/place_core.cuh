@@ -723,6 +723,7 @@ MMP_HD bool decide_fast(const SnapshotView &s, const DecisionCtx &c, const uint3
 // 10 000 instances) a walk that crossed 50-300 empty words becomes a few steps.
 // row words of a decision's window in k_place_lanes (shared with the commit path: nz_skip is computed for this width)
 #define MMP_LANE_WIN 12
+#define MMP_CHUNK_WORDS 21  // decide_stream's per-lane chunk of 8 steps beyond the window (odd: conflict-free lane stride in shared memory)
 struct LaneTables {
   const uint32_t *cx, *p;   // this decision's candidate (replicaset filter applied) and preferred mask rows, by absolute row word
   const uint32_t *full;
@@ -885,7 +886,7 @@ struct WarpVote { MMP_D bool any(bool p) const { return __any_sync(0xffffffffu, 
 template <class V, class R>
 MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &Tw, const LaneTables &T, const DecisionCtx &c, bool active,
                           const uint32_t *ewin, uint32_t win_words, const R &row, uint32_t self_eword, int64_t now, uint64_t seed,
-                          uint64_t decision_id, const V &vote, DecideOut &o, int32_t budget) {
+                          uint64_t decision_id, const V &vote, DecideOut &o, int32_t budget, uint32_t *chunk = nullptr) {
   o.target = MMP_TARGET_NONE; o.n_candidates = 0; o.best = -1; o.n_remaining = 0; o.pick_index = 0; o.flags = 0;
   o.cut_rank = (int32_t)NONE_RANK; o.best_rank = -1; o.first_rank = -1;
   const uint32_t NW = (uint32_t)s.row_words, WS = (uint32_t)s.word_lo, WE = (uint32_t)s.word_hi;
@@ -915,25 +916,22 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &Tw, const Lan
   auto row_of = [&](uint32_t r) -> RankRow { return (r >> 5) < win_end ? load_row_any(Tw.rows + r) : load_row(T.rows + r); };
   // ---- beyond the window: a chunk of 8 consecutive steps [base, base + 8) in registers ----
   uint32_t base = 0xfffffff0u;  // no chunk loaded
-  uint32_t wq[4] = {0, 0, 0, 0};                    // the chunk's list entries (u16 pairs)
-  uint32_t fq[8] = {0, 0, 0, 0, 0, 0, 0, 0};        // ... filtered words cx & ~row
-  uint32_t pq[8] = {0, 0, 0, 0, 0, 0, 0, 0};        // ... preferred words
-  uint32_t cq = 0;                                  // ... count classes against cls_lim (2 bits each)
+  // chunk storage, MMP_CHUNK_WORDS words per lane: [0,4) the list entries (u16 pairs), [4,12) filtered words cx & ~row,
+  // [12,20) preferred words, [20] count classes against cls_lim (2 bits each).  The caller hands a shared-memory slice
+  // (dynamic indexing is one load); without one the array lives in local memory.
+  uint32_t chunk_local[MMP_CHUNK_WORDS];
+  uint32_t *ch = chunk ? chunk : chunk_local;
   int32_t cls_lim = 10;                             // the count limit the chunk's classes were computed for (phase B sets it and drops the chunk)
-  auto wsel = [&](uint32_t j) -> uint32_t {          // entry j (0..7) of the chunk, without dynamic register indexing
-    uint32_t q = wq[0];
-    q = (j >> 1) == 1 ? wq[1] : q; q = (j >> 1) == 2 ? wq[2] : q; q = (j >> 1) == 3 ? wq[3] : q;
-    return (q >> ((j & 1u) * 16u)) & 0xffffu;
-  };
+  auto wsel = [&](uint32_t j) -> uint32_t { return (ch[j >> 1] >> ((j & 1u) * 16u)) & 0xffffu; };
   auto refill = [&](uint32_t k) {
     base = k;
 #pragma unroll
     for (uint32_t j = 0; j < 4; j++) {
       const uint32_t k0 = k + 2 * j, k1 = k0 + 1;
       const uint32_t lo16 = k0 < NZ ? (uint32_t)ldro(T.nzw + (k0 + koff)) : 0xffffu, hi16 = k1 < NZ ? (uint32_t)ldro(T.nzw + (k1 + koff)) : 0xffffu;
-      wq[j] = lo16 | (hi16 << 16);
+      ch[j] = lo16 | (hi16 << 16);
     }
-    cq = 0;
+    uint32_t cq = 0;
 #pragma unroll
     for (uint32_t j = 0; j < 8; j++) {
       uint32_t f = 0, pw = 0;
@@ -942,14 +940,9 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &Tw, const Lan
         const uint32_t wi = wsel(j);
         f = AG.cx(wi) & ~row.word(wi); pw = AG.p(wi); cl = AG.cls(wi, cls_lim);
       }
-      fq[j] = f; pq[j] = pw; cq |= (uint32_t)cl << (2u * j);
+      ch[4 + j] = f; ch[12 + j] = pw; cq |= (uint32_t)cl << (2u * j);
     }
-  };
-  auto sel8 = [&](const uint32_t (&a)[8], uint32_t j) -> uint32_t {
-    uint32_t v = a[0];
-    v = j == 1 ? a[1] : v; v = j == 2 ? a[2] : v; v = j == 3 ? a[3] : v; v = j == 4 ? a[4] : v;
-    v = j == 5 ? a[5] : v; v = j == 6 ? a[6] : v; v = j == 7 ? a[7] : v;
-    return v;
+    ch[20] = cq;
   };
   // One walk: BODY sees (K, wi, e) and sets go_ (true: next step).  WALKING is cleared when the lane stops: BODY said so, the
   // list ended (ENDED = true), or the budget / the reachable part of the row ran out (live = false).  CHARGE: the steps
@@ -978,7 +971,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &Tw, const Lan
         else if (CHARGE && left <= 0) { WALKING = false; live = false; }                                                   \
         else {                                                                                                             \
           const uint32_t j_ = K - base, wi = wsel(j_), e = 0u;                                                              \
-          const TabChunk A{sel8(fq, j_), sel8(pq, j_), (int)((cq >> (2u * j_)) & 3u), AG};                                   \
+          const TabChunk A{ch[4u + j_], ch[12u + j_], (int)((ch[20] >> (2u * j_)) & 3u), AG};                                 \
           bool go_;                                                                                                        \
           BODY;                                                                                                            \
           if (go_) { K++; if (CHARGE) left--; } else WALKING = false;                                                      \

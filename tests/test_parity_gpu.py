@@ -168,7 +168,7 @@ def test_latency_paths_equal_the_batch(product_lib, oracle_lib, config, nm, ni, 
                 one = s.place_one(d, fl.now_ms, 11, fresh=fresh, extra=extra)
                 assert int(one["target"]) == int(whole["target"][i]) and int(one["n_candidates"]) == int(whole["n_candidates"][i]), (rnd, mode, i)
             s._ck(product_lib.mmp_fleet_set_id_base(s.h, 0))
-        s._ck(product_lib.mmp_tune(s.h, b"one_mode", 2))
+        s._ck(product_lib.mmp_tune(s.h, b"one_mode", 3))
         # a new epoch (numeric update -> device-path commit): the next round replays a re-captured graph
         r = fl.inst_rows[int(np.nonzero(fl.inst_rows["shutting_down"] == 0)[0][0])].copy()
         r["count"] = int(r["count"]) + 50
