@@ -629,6 +629,8 @@ def main():
             barrier()
             ms_peer, ok_peer = timed_leg()
             st = sh.shard_peer_stats()
+            tk, tw = C.c_double(), C.c_double()
+            lib.mmp_last_timing(sh.h, b"dealt_kernel", C.byref(tk)); lib.mmp_last_timing(sh.h, b"dealt_wait", C.byref(tw))
             tot = torch.tensor([float(st["remote_row_words"]) * 4.0, float(st["result_bytes_to_peers"])], dtype=torch.float64, device="cuda")
             dist.all_reduce(tot, op=dist.ReduceOp.SUM)
             n_dec = float(N_MODELS) * max(st["batches"], 1)
@@ -637,7 +639,8 @@ def main():
                 "exchange": "k_place_dealt: decisions dealt by warp batch, peer loads of row words beyond the %d-word replicated front, "
                             "8-byte results stored to all %d shards, flag arrival + k_dealt_wait (no NCCL, no host sync)" % (16, world),
                 "nvlink_bytes_per_decision": {"row_words_read": float(tot[0]) / n_dec, "results_written": float(tot[1]) / n_dec},
-                "batches_on_peer_path": st["batches"], "matches_registry_sharded": ok_peer}
+                "batches_on_peer_path": st["batches"], "matches_registry_sharded": ok_peer,
+                "rank0_last_step_ms": {"k_place_dealt": tk.value, "k_dealt_wait": tw.value}}
         except Exception as ex:  # (the collective figure above stands on its own)
             print(f"[bench] peer-access leg skipped: {ex}", file=sys.stderr)
         sh.close()

@@ -414,7 +414,8 @@ int32_t mmp_registry_prune(mmp_fleet *, int32_t self, int64_t now_ms, int64_t as
  *   "commit_host_only" 1: every commit takes the structural (host) path */
 int32_t mmp_tune(mmp_fleet *, const char *key, int64_t value);
 /* CUDA-event duration (ms) of the device part of the last mmp_stats ("stats"), mmp_reaper_select ("reaper": registry sweep +
- * sort + select), mmp_lru_apply ("lru_apply": the event kernel) on this fleet; "commit": host-clock ms of the last commit */
+ * sort + select), mmp_lru_apply ("lru_apply": the event kernel) on this fleet; "commit": host-clock ms of the last commit; "prune": mmp_registry_prune;
+ * "dealt_kernel" / "dealt_wait": k_place_dealt and the arrival wait of the last peer-access step of an instance-sharded fleet */
 int32_t mmp_last_timing(mmp_fleet *, const char *key, double *ms);
 /* which path the last mmp_fleet_commit took: 1 = structural (host: string ranks, type-constraint sets, sort), 2 = device
  * (numeric instance updates / model-record deltas only: scattered into the device-resident tables, re-ranked and rebuilt

@@ -1174,6 +1174,8 @@ struct mmp_fleet {
     uint64_t step = 0;
     int64_t batches = 0, result_bytes = 0;
     int minb = 6;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // around k_place_dealt and k_dealt_wait of the last step
+    float t_kernel_ms = 0, t_wait_ms = 0;
     int off = 0;                            // MMP_SHARD_PEERS=0 keeps the collective path although peers were imported
   } peers;
   std::mutex comm_mu;           // collectives of one communicator are issued by one thread at a time
@@ -1431,18 +1433,24 @@ static int32_t place_dealt(mmp_fleet *f, PlaceCtx *c, const DeviceSnapshot &ds, 
   auto kern = pr.minb == 6 ? k_place_dealt<WARPS, 6> : k_place_dealt<WARPS, 4>;
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   unsigned long long *stats = pr.flag_buf() + MAX_SHARDS;
+  if (!pr.ev[0]) for (int k = 0; k < 3; k++) CK(cudaEventCreate(&pr.ev[k]));
+  CK(cudaEventRecord(pr.ev[0], st));
   kern<<<blocks, WARPS * 32, smem, st>>>(vw, ds.front.as<uint32_t>(), std::min(SHARD_FRONT_WORDS, vw.row_words), ds.nzw_full.as<uint16_t>(),
                                                        ds.nz_n_full.as<int32_t>(), P, G, me, d_in, n, d_fresh, n_fresh, d_extra, now_ms, seed,
                                                        f->id_base.load(), f->lane_budget, step, pr.done.as<unsigned int>(), stats);
   CK(cudaGetLastError());
+  CK(cudaEventRecord(pr.ev[1], st));
   k_dealt_wait<<<1, 32, 0, st>>>(pr.flag_buf(), G, step, 4000000000ull, pr.err.as<int>());
   CK(cudaGetLastError());
+  CK(cudaEventRecord(pr.ev[2], st));
   CK(cudaMemcpyAsync(d_out, pr.out_buf() + (size_t)(step & 1) * pr.max_batch, (size_t)n * sizeof(mmp_decision_out),
                      cudaMemcpyDeviceToDevice, st));
   int err = 0;
   CK(cudaMemcpyAsync(&err, pr.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   f->launches += 2;
+  cudaEventElapsedTime(&pr.t_kernel_ms, pr.ev[0], pr.ev[1]);
+  cudaEventElapsedTime(&pr.t_wait_ms, pr.ev[1], pr.ev[2]);
   pr.batches++;
   {
     const long long nb = n / 32, full = nb > me ? (nb - me + G - 1) / G : 0;
@@ -2129,6 +2137,8 @@ int32_t mmp_last_timing(mmp_fleet *f, const char *key, double *ms) {
   else if (!strcmp(key, "lru_apply")) *ms = f->t_lru_ms;
   else if (!strcmp(key, "prune")) *ms = f->t_prune_ms;
   else if (!strcmp(key, "commit")) *ms = f->last_commit_ms;
+  else if (!strcmp(key, "dealt_kernel")) *ms = f->peers.t_kernel_ms;
+  else if (!strcmp(key, "dealt_wait")) *ms = f->peers.t_wait_ms;
   else { g_err = "unknown key"; return MMP_E_ARG; }
   return MMP_OK;
 }

@@ -879,7 +879,8 @@ struct WarpVote { MMP_D bool any(bool p) const { return __any_sync(0xffffffffu, 
 // lane's attempt ends at the window's edge.
 // Same semantics and quirks as decide_ctx (N2: the non-self test reads the caller's fresh record).  Returns false --
 // and the caller redoes the decision with the cooperative general routine -- for everything outside the common case:
-// malformed decision, more than LANE_MAX_EXTRA extra excludes, no entry / best full (replicaset retry, non-simple (b)), or
+// malformed decision, more than LANE_MAX_EXTRA extra excludes, no entry (replicaset retry), a full best whose type has
+// preferred instances it is not one of (non-simple (b)), or
 // a walk of more than `budget` steps.  Instance-sharded: a walk that needs ranks beyond this shard's range sets MMP_TF_OPEN.
 // self_eword = the row word that holds self's bit (anywhere in the row).  Must be called by every lane of the vote group
 // (active = false for lanes without a decision).
@@ -997,17 +998,20 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &Tw, const Lan
   if (b == NONE_RANK) live = false;  // none in reach: the general routine decides (replicaset retry, null)
   RankRow rb; rb.lru = 0; rb.rem = 0; rb.count = 0; rb.rpm = 0; rb.idx = -1; rb.flags = 0;
   bool us = false, simple = true, use_pref = false;
-  int64_t best_rem = 0;
+  int64_t best_rem = 0, best_lru = 0;
+  bool best_full = false;
   int32_t best_count = 0, best_rpm = 0, best_idx = -1;
   uint32_t best_rank = b, lo = b, hi = NONE_RANK, k_lo = kb;
   if (live) {
     rb = row_of(b);
     us = rb.idx == d.self;
     best_rem = us ? fr.rem : rb.rem; best_count = us ? fr.count : rb.count; best_rpm = us ? fr.rpm : rb.rpm; best_idx = rb.idx;
-    if (best_rem < s.min_space) live = false;  // best full (MM:4811): general routine
+    best_lru = us ? fr.lru : rb.lru;
+    best_full = best_rem < s.min_space;  // MM:4811
     const bool has_pref = ctx_has_pref(c);
     simple = !has_pref || pbit(b);
     use_pref = has_pref && simple;  // best is preferred: preference is treated as required (MM:4905-4907)
+    if (best_full && !simple) live = false;  // non-simple (b), MM:4853-4887: general routine
   }
   // ---- A': non-simple (a) ----
   uint32_t r1 = NONE_RANK, k1 = kb;
@@ -1035,7 +1039,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &Tw, const Lan
     } else hi = r1;
   }
   bool done = false;
-  int32_t fl = MMP_TF_SIMPLE | MMP_TF_FAST;
+  int32_t fl = MMP_TF_SIMPLE | MMP_TF_FAST | (best_full ? MMP_TF_BEST_FULL : 0);
   if (live && !open && us && favour_self) { o.target = MMP_TARGET_SELF; fl |= MMP_TF_FAVOUR_EXIT; done = true; }
   // ---- the walk's per-decision constants ----
   bool walk = live && !open && !done;
@@ -1051,12 +1055,19 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &Tw, const Lan
       if (in && has_x) in = (xmask(w) & bit) == 0;  // an explicitly excluded self never passes the filter (MM:4780-4781)
       if (in) { self_in_s = true; sw_ = w; sb_ = bit; }
     }
-    const int64_t q = best_rem >> 2;
-    c_self = fr.rem < s.min_space || fr.rem < q;
-    self_viol = rb.rem < s.min_space || rb.rem < q;
+    if (best_full) {  // a full best: the distance test is on lruTime (MM:4862-4866), N2: the caller's record for every non-self member
+      const int64_t a10 = age_of(best_lru, now) / 10;
+      const int64_t df = jsub(fr.lru, best_lru), ds = jsub(rb.lru, best_lru);
+      c_self = df > 45000 && df > a10;
+      self_viol = ds > 45000 && ds > a10;
+    } else {
+      const int64_t q = best_rem >> 2;
+      c_self = fr.rem < s.min_space || fr.rem < q;
+      self_viol = rb.rem < s.min_space || rb.rem < q;
+    }
     const int32_t thr = jaddi(best_count, best_count >> 2);
     cv_min = thr >= 9 ? thr + 1 : 10;
-    if (self_in_s && cv(c.self_count)) self_viol = true;
+    if (!best_full && self_in_s && cv(c.self_count)) self_viol = true;
   }
   const uint32_t cut_self = (self_in_s && self_viol) ? (uint32_t)self_rank : NONE_RANK;
   // S' = F restricted to (lo, lim), lim = min(hi, cut_self): nothing at or beyond a failing self can be a candidate
@@ -1087,7 +1098,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &Tw, const Lan
         int cls = 0;  // 0: no member fails, 1: every member (but a passing self) fails, 2: look at the counts
         uint32_t v = x;
         if (c_self) { if (wi == sw_) v &= ~sb_; cls = v ? 1 : 0; }
-        else if (x) cls = A.cls(wi, cv_min);
+        else if (x && !best_full) cls = A.cls(wi, cv_min);  // (a full best: no count test, the walk runs to the end of S)
         if (cls == 2) {  // exact evaluation of a mixed word: 32 counts, zero-padded past the last rank
           const uint32_t vm = A.ge_mask(wi, cv_min);
           v = vm & x;
