@@ -920,8 +920,17 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_place_dealt(const Snapshot
   // the window: the first MMP_LANE_WIN words of the row, from the replicated front (local memory on every shard)
   const uint32_t win_words = (uint32_t)min(min(LANE_WIN, front_words), RW);
   uint32_t *w = win_d[warp] + lane * LANE_STRIDE;
+  if ((front_words & 3) == 0) {  // (front rows are 16-byte aligned then: three vector loads)
 #pragma unroll
-  for (int j = 0; j < LANE_WIN; j++) w[j] = (valid && (uint32_t)j < win_words) ? __ldg(front + (size_t)m * front_words + j) : 0u;
+    for (int j = 0; j < LANE_WIN / 4; j++) {
+      uint4 q = make_uint4(0u, 0u, 0u, 0u);
+      if (valid && (uint32_t)(j * 4) < win_words) q = __ldg(reinterpret_cast<const uint4 *>(front + (size_t)m * front_words) + j);
+      w[j * 4] = q.x; w[j * 4 + 1] = q.y; w[j * 4 + 2] = q.z; w[j * 4 + 3] = q.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < LANE_WIN; j++) w[j] = (valid && (uint32_t)j < win_words) ? __ldg(front + (size_t)m * front_words + j) : 0u;
+  }
   __syncwarp();
   if (win_words < (uint32_t)LANE_WIN) T.nz_skip = 0;  // (a front shorter than the window: no window at all)
   DecideOut o;
@@ -954,9 +963,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_place_dealt(const Snapshot
   uint32_t rem = row.remote;
   for (int of = 16; of > 0; of >>= 1) rem += __shfl_xor_sync(0xffffffffu, rem, of);
   if (lane == 0 && rem) atomicAdd(remote_words, (unsigned long long)rem);
-  __threadfence_system();
-  __syncthreads();
+  __syncthreads();  // the block's peer stores are ordered before thread 0's fence (cumulative, system scope), the fence before the count
   if (threadIdx.x == 0) {
+    __threadfence_system();
     const unsigned int prev = atomicAdd(done, 1u);
     if (prev == gridDim.x - 1) {
       *done = 0;
