@@ -875,8 +875,8 @@ __global__ void __launch_bounds__(32) k_place_server(const SnapshotView s_arg, v
 // replicated on every shard (DeviceSnapshot::front: where almost every walk ends), the words beyond come from the column
 // block of the shard that owns them -- this GPU's HBM or a peer's, through its NVLink-mapped pointer (RowDealt).  The
 // result (8 bytes) is stored into the result buffer of EVERY shard (peer stores over NVLink), so all shards end with the
-// whole batch's answers.  No collective call, no host synchronisation between the shards: the last block of the kernel
-// raises this shard's flag in every peer's flag array (release, system scope) and k_dealt_wait spins until all G flags of
+// whole batch's answers.  No collective call, no host synchronisation between the shards: k_dealt_wait, the next kernel on
+// the stream, raises this shard's flag in every peer's flag array (release, system scope) and spins until all G flags of
 // the step have arrived (bounded by a timeout: a missing peer ends in an error, not a hang).
 // ---------------------------------------------------------------------------------------------------------------
 static constexpr int MAX_SHARDS = 16;
@@ -959,26 +959,21 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_place_dealt(const Snapshot
     const mmp_decision_out r{o.target, o.n_candidates};
     for (int g = 0; g < G; g++) P.out[g][i] = r;  // 256 contiguous bytes per warp and shard
   }
-  // ---- arrival: every thread's peer stores are ordered before the block's count, the last block raises the flags ----
   uint32_t rem = row.remote;
   for (int of = 16; of > 0; of >>= 1) rem += __shfl_xor_sync(0xffffffffu, rem, of);
   if (lane == 0 && rem) atomicAdd(remote_words, (unsigned long long)rem);
-  __syncthreads();  // the block's peer stores are ordered before thread 0's fence (cumulative, system scope), the fence before the count
-  if (threadIdx.x == 0) {
-    __threadfence_system();
-    const unsigned int prev = atomicAdd(done, 1u);
-    if (prev == gridDim.x - 1) {
-      *done = 0;
-      __threadfence_system();
-      for (int g = 0; g < G; g++)
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(P.flags[g] + me), "l"(step) : "memory");
-    }
-  }
+  // (arrival is signalled by k_dealt_wait, the next kernel on this stream: a kernel boundary orders this kernel's stores --
+  // peer stores included -- before it, which spares every block a system-scope fence over NVLink)
 }
-// one warp: lane g waits for shard g's arrival at `step`; err[0] = 1 after `timeout_ns`
-__global__ void k_dealt_wait(const unsigned long long *flags, int G, unsigned long long step, unsigned long long timeout_ns, int *err) {
+// one warp, launched behind k_place_dealt on the same stream: lane g raises this shard's flag in shard g's flag array
+// (release, system scope: ordered after everything the dealt kernel stored) and then waits for shard g's arrival at `step`;
+// err[0] = 1 after `timeout_ns`
+__global__ void k_dealt_wait(const __grid_constant__ DealtPeers P, int G, int me, unsigned long long step, unsigned long long timeout_ns, int *err) {
   const int g = threadIdx.x;
   if (g >= G) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(P.flags[g] + me), "l"(step) : "memory");
+  const unsigned long long *flags = P.flags[me];
   unsigned long long t0, t1, v;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   for (;;) {
@@ -989,7 +984,6 @@ __global__ void k_dealt_wait(const unsigned long long *flags, int G, unsigned lo
     __nanosleep(200);
   }
 }
-
 // ---------------------------------------------------------------------------------------------------------------
 // instance-sharded combine: kernels around the one collective
 // ---------------------------------------------------------------------------------------------------------------
@@ -1449,7 +1443,7 @@ static int32_t place_dealt(mmp_fleet *f, PlaceCtx *c, const DeviceSnapshot &ds, 
                                                        f->id_base.load(), f->lane_budget, step, pr.done.as<unsigned int>(), stats);
   CK(cudaGetLastError());
   CK(cudaEventRecord(pr.ev[1], st));
-  k_dealt_wait<<<1, 32, 0, st>>>(pr.flag_buf(), G, step, 4000000000ull, pr.err.as<int>());
+  k_dealt_wait<<<1, 32, 0, st>>>(P, G, me, step, 4000000000ull, pr.err.as<int>());
   CK(cudaGetLastError());
   CK(cudaEventRecord(pr.ev[2], st));
   CK(cudaMemcpyAsync(d_out, pr.out_buf() + (size_t)(step & 1) * pr.max_batch, (size_t)n * sizeof(mmp_decision_out),
