@@ -1,0 +1,9 @@
+#!/bin/bash
+# round 2, step o: best-full in the lane routine; whole GPU suite; C5 / C3 benches
+cd "$GRAFT_REPO_ROOT"
+timeout 1500 python -m pytest tests -m gpu -q --deselect tests/test_churn_gpu.py::test_closed_loop_c4_full_size > gpurun_out/r02_o_pytest.log 2>&1; tail -4 gpurun_out/r02_o_pytest.log
+run() { name=$1; shift; env "$@" timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu --no-e2e > gpurun_out/r02_o_$name.json 2> gpurun_out/r02_o_$name.err; python -c "
+import json; d=json.load(open('gpurun_out/r02_o_$name.json')); print('$name value %.3f G/s frac %.3f ms %.4f lat %s' % (d['value']/1e9, d['roofline']['frac'], d['ms_per_step'], {k: (round(v['p50_us'],1), round(v['p99_us'],1)) for k, v in d['latency_b1'].items() if isinstance(v, dict)}))"; tail -2 gpurun_out/r02_o_$name.err | cut -c1-300; }
+run c5 BENCH_CONFIG=C5
+run c3
+run c5_lanes BENCH_CONFIG=C5 MMP_KERNEL=lanes MMP_LANE_MODE=2
