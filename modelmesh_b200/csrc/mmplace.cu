@@ -860,6 +860,7 @@ __global__ void __launch_bounds__(32) k_place_server(const SnapshotView s_arg, v
     last = seq;
     served++;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_last));
+    if (t_last - t0 > life_ns) break;  // (a busy server leaves too: the host restarts it with its next request)
   }
   if (lane == 0) {
     resp->served = served;
