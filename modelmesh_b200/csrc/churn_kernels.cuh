@@ -333,8 +333,10 @@ int32_t mmp_churn_seed(mmp_fleet *f, int32_t n, const int32_t *instance, const i
   ChurnHooks hk{};
   hk.min_space = f->hs.cfg.min_space_units; hk.min_churn_age = f->hs.cfg.min_churn_age_ms;
   const int grid = (f->lru_n + 3) / 4;
-  k_lru_events<<<grid, 128, 0, st>>>(lru_view(f), cs.lev.as<LruEv>(), cs.vals.as<int>(), cs.off.as<int>(), now_ms, 0, hk, cs.evict.as<EvictRec>(),
-                                    16, cs.counters.as<int>() + 4, cs.counters.as<int>() + 5);
+  size_t lsm = 0;
+  const int lst = lru_stage_slots(f, &lsm);
+  k_lru_events<<<grid, 128, lsm, st>>>(lru_view(f), cs.lev.as<LruEv>(), cs.vals.as<int>(), cs.off.as<int>(), now_ms, 0, hk, cs.evict.as<EvictRec>(),
+                                      16, cs.counters.as<int>() + 4, cs.counters.as<int>() + 5, lst);
   f->launches++;
   CK(cudaGetLastError());
   int hdr[8];
@@ -454,8 +456,10 @@ int32_t mmp_churn_step(mmp_fleet *f, const mmp_churn_event *ev, int32_t n, int64
     hk.type_ok = cs.type_ok.as<unsigned char>(); hk.n_type_ids = lv.n_type_ids;
     hk.next = cs.next_carry.as<Follow>(); hk.n_next = cs.counters.as<int>() + 6; hk.next_cap = ecap;
     hk.force_publish = cs.force_publish.as<unsigned char>();
-    k_lru_events<<<(f->lru_n + 3) / 4, 128, 0, st>>>(lru_view(f), cs.lev.as<LruEv>(), cs.vals2.as<int>(), cs.off.as<int>(), now0, 1, hk,
-                                                    cs.evict.as<EvictRec>(), ecap, cs.counters.as<int>() + 4, cs.counters.as<int>() + 5);
+    size_t lsm = 0;
+    const int lst = lru_stage_slots(f, &lsm);
+    k_lru_events<<<(f->lru_n + 3) / 4, 128, lsm, st>>>(lru_view(f), cs.lev.as<LruEv>(), cs.vals2.as<int>(), cs.off.as<int>(), now0, 1, hk,
+                                                      cs.evict.as<EvictRec>(), ecap, cs.counters.as<int>() + 4, cs.counters.as<int>() + 5, lst);
     f->launches++;
     CK(cudaGetLastError());
     CK(cudaEventRecord(evs[4], st));

@@ -9,9 +9,18 @@
 //   rows      [n_ranks] RankRow 32 B      per-rank instance columns the walk reads (lru, remaining, count, rpm, idx)
 //   csum/lsum [row_words]                 per-32-rank min/max of count / lruTime (threshold searches skip whole words)
 //   rank_of   [max_instances] i32, models [n_models] mmp_model_row 24 B, type_slot [n_type_ids] u16
-// Kernels: k_place_lanes<WARPS> (the production scoring kernel: one decision per lane, 32-row TMA landing stages shared by
-//          the block's warps, lock-step voted walks), k_place<...> (cooperative tiles: traced calls / very wide rows),
-//          k_build_bitmap* (commit), k_shard_* (instance-shard combine), k_stats, k_reaper_*, k_lru_apply (scan_kernels.cuh).
+//   nzw/nz_n  [n_slots][row_words] u16    compressed word lists: the row words that hold any candidate of the slot (walks beyond the window)
+//   front     [n_models][16] u32          instance-sharded fleets: the first row words, replicated on every shard
+// Kernels:
+//   k_place_direct<4, MINB>  the scoring kernel (default): one decision per lane, the row's window read straight from memory,
+//                            longer walks through the word lists; optional slot-sorted batches (k_slot_keys + cub radix sort)
+//   k_place_lanes<WARPS>     round 1's streaming kernel (whole rows through TMA landing stages): MMP_KERNEL=lanes and the
+//                            collective instance-shard path
+//   k_place_small            tiny batches as a stream launch / replayed CUDA graph;  k_place_server: the resident B = 1 server
+//   k_place_dealt, k_dealt_wait   instance shards over peer memory;  k_shard_*: the kernels around the NCCL all-reduce
+//   k_place<...>             cooperative tiles: traced calls / very wide rows
+//   k_build_bitmap*, k_sparse_slots + commit_kernels.cuh (device-path commit), scan_kernels.cuh (k_stats, k_reaper_flag,
+//   k_lru_events), churn_kernels.cuh (the closed loop), registry_kernels.cuh (k_scale_eval, k_registry_prune)
 #include <cuda_runtime.h>
 #include <unistd.h>
 #include <dlfcn.h>

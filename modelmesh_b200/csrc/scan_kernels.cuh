@@ -338,13 +338,31 @@ __device__ int lru_find(const LruView &v, int inst, int lane, int model, int *fr
 // MM:5185-5190, registration, inflate to the predicted size + grow-then-check MM:2094-2106.  With hooks.enabled every eviction
 // also runs the eviction listener's bookkeeping (onEviction MM:2875-2931): deregistration mark, the reload-elsewhere rule (a12).
 __global__ void k_lru_events(LruView v, const LruEv *__restrict__ ev, const int *__restrict__ ev_order, const int *__restrict__ inst_off,
-                             long long now_param, int use_ev_time, ChurnHooks hk, EvictRec *out, int out_cap, int *out_n, int *err) {
+                             long long now_param, int use_ev_time, ChurnHooks hk, EvictRec *out, int out_cap, int *out_n, int *err, int stage_slots) {
   const int lane = threadIdx.x & 31;
   const int inst = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (inst >= v.n) return;
   const int p0 = inst_off[inst], p1 = inst_off[inst + 1];
   if (p0 >= p1) return;
-  const size_t base = (size_t)inst * v.slots;
+  // An instance with many events (the pod that holds a hot model: its touches are serial) works on a copy of its slot arrays
+  // in shared memory -- every event scans the slots twice (find the model, find the successor / the oldest) -- and writes
+  // them back at the end.  stage_slots = slots the block's dynamic shared memory has room for per warp (0: no staging).
+  extern __shared__ __align__(16) unsigned char lru_smem[];
+  LruView sv = v;
+  int hi = inst;                 // the instance index the helpers see (0 on the staged copy)
+  size_t base = (size_t)inst * v.slots;
+  const bool staged = stage_slots >= v.slots && (p1 - p0) >= 12;
+  if (staged) {
+    unsigned char *mine = lru_smem + (size_t)(threadIdx.x >> 5) * (size_t)stage_slots * 32u;
+    long long *s_ts = reinterpret_cast<long long *>(mine), *s_seq = s_ts + stage_slots, *s_lt = s_seq + stage_slots;
+    int *s_w = reinterpret_cast<int *>(s_lt + stage_slots), *s_m = s_w + stage_slots;
+    for (int i = lane; i < v.slots; i += 32) {
+      s_ts[i] = sv.ts[base + i]; s_seq[i] = sv.seq[base + i]; s_lt[i] = sv.loadts[base + i]; s_w[i] = sv.weight[base + i]; s_m[i] = sv.model[base + i];
+    }
+    __syncwarp();
+    sv.ts = s_ts; sv.seq = s_seq; sv.loadts = s_lt; sv.weight = s_w; sv.model = s_m;
+    hi = 0; base = 0;
+  }
   long long wsize = v.wsize[inst], capacity = v.cap[inst], ctr = v.seqctr[inst];
   int count = v.count[inst];
   int evseq = 0;
@@ -352,14 +370,14 @@ __global__ void k_lru_events(LruView v, const LruEv *__restrict__ ev, const int 
   auto evict_loop = [&](const LruEv &e, long long now, int watch_model, bool *self_gone) {
     while (wsize > capacity) {
       long long t, s;
-      const int victim = lru_min_slot(v, inst, lane, false, 0, 0, &t, &s);
+      const int victim = lru_min_slot(sv, hi, lane, false, 0, 0, &t, &s);
       if (victim < 0) break;
-      const int w = v.weight[base + victim], m = v.model[base + victim];
-      const long long lt = v.loadts[base + victim];
+      const int w = sv.weight[base + victim], m = sv.model[base + victim];
+      const long long lt = sv.loadts[base + victim];
       __syncwarp();
       if (m == watch_model && self_gone) *self_gone = true;
       if (lane == 0) {
-        v.model[base + victim] = -1;
+        sv.model[base + victim] = -1;
         int reload = 0;
         if (hk.enabled) {
           const bool in_registry = lt >= 0;
@@ -392,13 +410,13 @@ __global__ void k_lru_events(LruView v, const LruEv *__restrict__ ev, const int 
     const LruEv e = ev[ev_order[p]];
     const long long now = use_ev_time ? e.t : now_param;
     int free_slot;
-    int slot = (e.op == LEV_SET_CAPACITY) ? -1 : lru_find(v, inst, lane, e.model, &free_slot);
+    int slot = (e.op == LEV_SET_CAPACITY) ? -1 : lru_find(sv, hi, lane, e.model, &free_slot);
     if (e.op == LEV_SET_CAPACITY) { capacity = e.last_used; evict_loop(e, now, -1, nullptr); continue; }
     if (e.op == LEV_LOAD) {
       // limit the rate of cache churn (MM:3872-3884)
       if (hk.min_churn_age > 0 && capacity - wsize < hk.min_space) {
         long long t, s;
-        const int o = lru_min_slot(v, inst, lane, false, 0, 0, &t, &s);
+        const int o = lru_min_slot(sv, hi, lane, false, 0, 0, &t, &s);
         if (o >= 0 && t != 0x7fffffffffffffffLL && (t == 0 ? 0 : now - t) < hk.min_churn_age) { if (lane == 0) hk.status[e.dec] = CH_CHURN; continue; }
       }
       if (slot >= 0) { if (lane == 0) hk.status[e.dec] = CH_EXISTS; }  // putIfAbsent found an entry: afterRead below
@@ -407,10 +425,10 @@ __global__ void k_lru_events(LruView v, const LruEv *__restrict__ ev, const int 
       if (free_slot < 0) { if (lane == 0) atomicExch(err, 1); continue; }
       const int w0 = e.op == LEV_LOAD ? 1 : e.weight;  // INSERTION_WEIGHT MM:5011
       if (lane == 0) {
-        v.model[base + free_slot] = e.model; v.weight[base + free_slot] = w0;
-        v.ts[base + free_slot] = e.last_used == 0 ? now : e.last_used;   // Node ctor: touch(time) (CLHM:1352-1360)
-        v.seq[base + free_slot] = ++ctr;
-        v.loadts[base + free_slot] = e.op == LEV_SEED ? e.t : -1;
+        sv.model[base + free_slot] = e.model; sv.weight[base + free_slot] = w0;
+        sv.ts[base + free_slot] = e.last_used == 0 ? now : e.last_used;   // Node ctor: touch(time) (CLHM:1352-1360)
+        sv.seq[base + free_slot] = ++ctr;
+        sv.loadts[base + free_slot] = e.op == LEV_SEED ? e.t : -1;
       } else ++ctr;
       __syncwarp();
       wsize += w0; count++;                                              // AddTask (CLHM:601-610)
@@ -421,16 +439,16 @@ __global__ void k_lru_events(LruView v, const LruEv *__restrict__ ev, const int 
       if (gone) { if (lane == 0) hk.status[e.dec] = CH_FALLTHRU; continue; }  // MM:5145-5148
       // early reject MM:5185-5190 (capacity, weightedSize, oldestTime after the placeholder went in)
       long long ot, os;
-      const int oi = lru_min_slot(v, inst, lane, false, 0, 0, &ot, &os);
+      const int oi = lru_min_slot(sv, hi, lane, false, 0, 0, &ot, &os);
       const long long oldest = oi < 0 ? -1 : ot;
       const long long abs_size = e.weight < 0 ? -(long long)e.weight : (long long)e.weight;
       if (abs_size > capacity || (e.last_used > 0 && abs_size > capacity - wsize && e.last_used < oldest)) {
-        if (lane == 0) { v.model[base + free_slot] = -1; hk.status[e.dec] = CH_EARLY; }  // ce.remove()
+        if (lane == 0) { sv.model[base + free_slot] = -1; hk.status[e.dec] = CH_EARLY; }  // ce.remove()
         __syncwarp();
         wsize -= 1; count--;
         continue;
       }
-      if (lane == 0) { v.loadts[base + free_slot] = now; hk.status[e.dec] = CH_ACCEPTED; v.weight[base + free_slot] = e.weight; }  // MM:5203, 2100
+      if (lane == 0) { sv.loadts[base + free_slot] = now; hk.status[e.dec] = CH_ACCEPTED; sv.weight[base + free_slot] = e.weight; }  // MM:5203, 2100
       __syncwarp();
       wsize += (long long)e.weight - 1;
       gone = false;
@@ -440,37 +458,37 @@ __global__ void k_lru_events(LruView v, const LruEv *__restrict__ ev, const int 
     }
     if ((e.op == LEV_INSERT || e.op == LEV_TOUCH || e.op == LEV_LOAD || e.op == LEV_SEED) && slot >= 0) {
       // afterRead -> touch + reposition (CLHM:383-388, 477-505; LD:243-255)
-      long long old_t = v.ts[base + slot], old_s = v.seq[base + slot];
+      long long old_t = sv.ts[base + slot], old_s = sv.seq[base + slot];
       long long lu = e.last_used > 0 ? (old_t > e.last_used ? old_t : e.last_used) : now;
       if (lu != old_t) {
         long long nt, ns;
         // (times only move forward through max(); a smaller "now" than the entry's time can move it backwards)
         bool moved_back = lu < old_t;
-        int nx = moved_back ? -1 : lru_min_slot(v, inst, lane, true, old_t, old_s, &nt, &ns);
+        int nx = moved_back ? -1 : lru_min_slot(sv, hi, lane, true, old_t, old_s, &nt, &ns);
         bool stay = !moved_back && (nx < 0 || nt >= lu);
         if (moved_back) {
           // prev.lastUsed <= lu fails in general: unlink + insert (LD:253-254)
-          if (lane == 0) { v.ts[base + slot] = lu; v.seq[base + slot] = ctr + 1; }
+          if (lane == 0) { sv.ts[base + slot] = lu; sv.seq[base + slot] = ctr + 1; }
           ++ctr;
         } else if (stay) {
-          if (lane == 0) { v.ts[base + slot] = lu; if (nx >= 0 && nt == lu) v.seq[base + slot] = ns - 1; }
+          if (lane == 0) { sv.ts[base + slot] = lu; if (nx >= 0 && nt == lu) sv.seq[base + slot] = ns - 1; }
         } else {
-          if (lane == 0) { v.ts[base + slot] = lu; v.seq[base + slot] = ctr + 1; }
+          if (lane == 0) { sv.ts[base + slot] = lu; sv.seq[base + slot] = ctr + 1; }
           ++ctr;
         }
         __syncwarp();
       }
     } else if (e.op == LEV_RESIZE && slot >= 0) {
-      int oldw = v.weight[base + slot];
-      if (lane == 0) v.weight[base + slot] = e.weight;
+      int oldw = sv.weight[base + slot];
+      if (lane == 0) sv.weight[base + slot] = e.weight;
       __syncwarp();
       wsize += (long long)e.weight - oldw;                               // UpdateTask (CLHM:643-651), quiet
       evict_loop(e, now, -1, nullptr);
     } else if (e.op == LEV_REMOVE && slot >= 0) {
-      int w = v.weight[base + slot];
-      const long long lt = v.loadts[base + slot];
+      int w = sv.weight[base + slot];
+      const long long lt = sv.loadts[base + slot];
       if (lane == 0) {
-        v.model[base + slot] = -1;
+        sv.model[base + slot] = -1;
         if (hk.enabled) {
           hk.force_publish[inst] = 1;
           if (lt >= 0) {  // deregisterModel
@@ -485,6 +503,13 @@ __global__ void k_lru_events(LruView v, const LruEv *__restrict__ ev, const int 
       wsize -= (w < 0 ? -w : w); count--;                                // RemovalTask + makeDead (CLHM:614-628, 561-570)
     }
   }
+  if (staged) {
+    __syncwarp();
+    const size_t gb = (size_t)inst * v.slots;
+    for (int i = lane; i < v.slots; i += 32) {
+      v.ts[gb + i] = sv.ts[i]; v.seq[gb + i] = sv.seq[i]; v.loadts[gb + i] = sv.loadts[i]; v.weight[gb + i] = sv.weight[i]; v.model[gb + i] = sv.model[i];
+    }
+  }
   if (lane == 0) { v.wsize[inst] = wsize; v.cap[inst] = capacity; v.seqctr[inst] = ctr; v.count[inst] = count; }
 }
 
@@ -497,6 +522,20 @@ __global__ void k_lru_state(LruView v, long long *oldest, long long *weighted, i
   if (lane == 0) { oldest[inst] = slot < 0 ? -1 : t; weighted[inst] = v.wsize[inst]; count[inst] = v.count[inst]; }
 }
 
+// dynamic shared memory of a k_lru_events launch with 4 warps per block: room for every warp's staged slot arrays (32 B per
+// slot), or none when the instance caches are too large for it
+static int lru_stage_slots(mmp_fleet *f, size_t *smem) {
+  static std::atomic<bool> attr_set[64];
+  const size_t tot = (size_t)f->lru_slots * 32u * 4u;
+  *smem = 0;
+  if (f->lru_slots <= 0 || tot > (size_t)200 * 1024) return 0;
+  if (!attr_set[f->device & 63].load()) {
+    if (cudaFuncSetAttribute(k_lru_events, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    attr_set[f->device & 63] = true;
+  }
+  *smem = tot;
+  return f->lru_slots;
+}
 static LruView lru_view(mmp_fleet *f) {
   LruView v;
   v.ts = f->lru_ts.as<long long>(); v.seq = f->lru_seq.as<long long>(); v.weight = f->lru_weight.as<int>(); v.model = f->lru_model.as<int>();
@@ -594,9 +633,11 @@ static int32_t lru_apply_impl(mmp_fleet *f, const mmp_lru_event *ev, int32_t n, 
   hk.status = c->d_trace.as<int>() + 4;
   const int warps_per_block = 4;
   const int grid = (f->lru_n + warps_per_block - 1) / warps_per_block;
+  size_t lsm = 0;
+  const int lst = lru_stage_slots(f, &lsm);
   CK(cudaEventRecord(c->e0, s));
-  k_lru_events<<<grid, warps_per_block * 32, 0, s>>>(lru_view(f), c->d_in.as<LruEv>(), c->d_extra.as<int>(), c->d_fresh.as<int>(), now_ms, 0, hk,
-                                                    c->d_out.as<EvictRec>(), cap, c->d_trace.as<int>(), c->d_trace.as<int>() + 1);
+  k_lru_events<<<grid, warps_per_block * 32, lsm, s>>>(lru_view(f), c->d_in.as<LruEv>(), c->d_extra.as<int>(), c->d_fresh.as<int>(), now_ms, 0, hk,
+                                                      c->d_out.as<EvictRec>(), cap, c->d_trace.as<int>(), c->d_trace.as<int>() + 1, lst);
   CK(cudaEventRecord(c->e1, s));
   f->launches++;
   CK(cudaGetLastError());
