@@ -945,10 +945,12 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &Tw, const Lan
     }
     ch[20] = cq;
   };
+  auto chunk_empty = [&]() -> bool { return (ch[4] | ch[5] | ch[6] | ch[7] | ch[8] | ch[9] | ch[10] | ch[11]) == 0u; };
   // One walk: BODY sees (K, wi, e) and sets go_ (true: next step).  WALKING is cleared when the lane stops: BODY said so, the
   // list ended (ENDED = true), or the budget / the reachable part of the row ran out (live = false).  CHARGE: the steps
-  // count against the budget (phase C re-walks words phase B has paid for).
-#define MMP_WALK(K, WALKING, ENDED, CHARGE, BODY)                                                                            \
+  // count against the budget (phase C re-walks words phase B has paid for).  BULK (beyond the window only): an expression
+  // that tries to take a freshly gathered chunk of 8 steps at once -- true: the 8 steps are done (its side effects are theirs).
+#define MMP_WALK(K, WALKING, ENDED, CHARGE, BULK, BODY)                                                                          \
   for (;;) { /* inside the window */                                                                                       \
     if (WALKING && K < win_words) {                                                                                        \
       if (CHARGE && left <= 0) { WALKING = false; live = false; }                                                          \
@@ -970,6 +972,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &Tw, const Lan
       if (WALKING) {                                                                                                       \
         if (K >= NZ) { WALKING = false; ENDED = true; }                                                                    \
         else if (CHARGE && left <= 0) { WALKING = false; live = false; }                                                   \
+        else if (K == base && K + 8u <= NZ && (!CHARGE || left >= 8) && (BULK)) { K += 8u; if (CHARGE) left -= 8; }          \
         else {                                                                                                             \
           const uint32_t j_ = K - base, wi = wsel(j_), e = 0u;                                                              \
           const TabChunk A{ch[4u + j_], ch[12u + j_], (int)((ch[20] >> (2u * j_)) & 3u), AG};                                 \
@@ -987,7 +990,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &Tw, const Lan
   {
     uint32_t k = 0;
     bool walking = live, ended = false;
-    MMP_WALK(k, walking, ended, true, {
+    MMP_WALK(k, walking, ended, true, (!has_x && chunk_empty()), {
       uint32_t x = A.cx(wi) & ~e;
       if (has_x) x &= ~xmask(wi);
       if (x) { b = wi * 32u + (uint32_t)ffs32(x); kb = k; }
@@ -1019,7 +1022,7 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &Tw, const Lan
     const uint32_t b_w = b >> 5, m_b = mask_above(b_w * 32u, b);
     uint32_t k = kb;
     bool walking = live && !simple, ended = false;
-    MMP_WALK(k, walking, ended, true, {
+    MMP_WALK(k, walking, ended, true, false, {
       uint32_t x = A.cx(wi) & ~e & (A.p(wi) | A.full(wi));
       if (has_x) x &= ~xmask(wi);
       if (wi == b_w) x &= m_b;
@@ -1084,13 +1087,28 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &Tw, const Lan
     if (wi == lim_w) m &= m_lim;
     return use_pref ? (m & A.p(wi)) : m;
   };
+  // a gathered chunk whose 8 words need none of the special masks: strictly between lo's word and lim's, self's word not among them
+  auto chunk_plain = [&]() -> bool { const uint32_t w0 = wsel(0), w7 = wsel(7); return w0 > lo_w && w7 < lim_w && (sw_ < w0 || sw_ > w7); };
+  auto chunk_members = [&]() -> uint32_t {  // members of S' in such a chunk
+    uint32_t n = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) n += (uint32_t)popc32(use_pref ? (ch[4 + j] & ch[12 + j]) : ch[4 + j]);
+    return n;
+  };
   // ---- B: first member of S' that fails its walk test, counting the members before it ----
   uint32_t cut_others = NONE_RANK, n_in = 0;
   cls_lim = cv_min; base = 0xfffffff0u;  // (a chunk gathered by an earlier phase carries classes for another limit)
+  auto bulk_b = [&]() -> bool {  // no member of the chunk can fail: count them all at once
+    const uint32_t n = chunk_members();
+    if (c_self) return n == 0;                    // (every non-self member fails: only an empty chunk passes)
+    if (!best_full && ch[20] != 0u) return false;  // a word whose counts may reach the limit: step by step
+    n_in += n;
+    return true;
+  };
   {
     uint32_t k = k_lo;
     bool walking = walk, ended = false;
-    MMP_WALK(k, walking, ended, true, {
+    MMP_WALK(k, walking, ended, true, (!has_x && chunk_plain() && bulk_b()), {
       go_ = true;
       if (wi >= stop_w) { ended = true; go_ = false; }  // the walk's natural end (everything at or beyond lim)
       else {
@@ -1152,7 +1170,8 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &Tw, const Lan
     const uint32_t cut_w = cut >> 5, m_cut = mask_below(cut_w * 32u, cut);
     uint32_t k = k_lo;
     bool walking = sel, ended = false;
-    MMP_WALK(k, walking, ended, false, {
+    auto bulk_c = [&]() -> bool { const uint32_t n = chunk_members(); if (kth < n) return false; kth -= n; return true; };
+    MMP_WALK(k, walking, ended, false, (!has_x && chunk_plain() && wsel(7) < cut_w && bulk_c()), {
       uint32_t x = Sw(A, wi, e);
       if (wi == cut_w) x &= m_cut;
       if (drop_self && wi == sw_) x &= ~sb_;
