@@ -10,3 +10,8 @@ print('c4', d['value'], d['unit'], d['ms_per_step'], d['phases_ms'], d['cpu_base
 PY
 tail -3 gpurun_out/r02_r_bench_c4_churn.err | cut -c1-300
 python -c "import __graft_entry__ as g; g.smoke()"
+run() { name=$1; shift; env "$@" timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu --no-e2e > gpurun_out/r02_r_$name.json 2> gpurun_out/r02_r_$name.err; python -c "
+import json; d=json.load(open('gpurun_out/r02_r_$name.json')); print('$name value %.3f G/s frac %.3f ms %.4f' % (d['value']/1e9, d['roofline']['frac'], d['ms_per_step']))"; tail -2 gpurun_out/r02_r_$name.err | cut -c1-300; }
+run c5 BENCH_CONFIG=C5
+run c3
+run c2 BENCH_CONFIG=C2
