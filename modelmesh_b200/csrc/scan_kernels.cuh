@@ -406,8 +406,10 @@ __global__ void k_lru_events(LruView v, const LruEv *__restrict__ ev, const int 
       wsize -= (w < 0 ? -w : w); count--;
     }
   };
+  LruEv e_next = ev[ev_order[p0]];
   for (int p = p0; p < p1; p++) {
-    const LruEv e = ev[ev_order[p]];
+    const LruEv e = e_next;
+    if (p + 1 < p1) e_next = ev[ev_order[p + 1]];  // (the next event's two dependent loads fly while this one is applied)
     const long long now = use_ev_time ? e.t : now_param;
     int free_slot;
     int slot = (e.op == LEV_SET_CAPACITY) ? -1 : lru_find(sv, hi, lane, e.model, &free_slot);
