@@ -407,6 +407,10 @@ int32_t mmp_registry_prune(mmp_fleet *, int32_t self, int64_t now_ms, int64_t as
  *                     and spins on the answer; one caller at a time, concurrent callers take the graph path)
  *   "server_life_us"  longest residence of one k_place_server launch (default 2000): bounds how long a device-wide wait
  *                     (cudaFree inside a commit) can be held up; "server_idle_us" (default 300): it leaves earlier when idle
+ *   "direct"          1 (default): batches are resolved by k_place_direct (rows read straight from memory); 0: by the streaming
+ *                     kernel k_place_lanes (whole rows through TMA landing stages) -- MMP_KERNEL=direct | lanes | tile
+ *   "sort_slots"      k_place_direct resolves a batch of >= 8192 decisions in type-slot order: 0 never, 1 always, 2 (default) when
+ *                     the committed snapshot's candidate sets are sparse (long walks: lanes of a warp then finish together)
  *   "small_max"       untraced batches of up to this many decisions run on k_place_small (one wave of 32-thread blocks, rows
  *                     read straight from memory) instead of the streaming kernel
  *   "lane_budget"     walk steps a lane may spend before its decision is redone by the whole warp
