@@ -1374,7 +1374,9 @@ static cudaError_t launch_place(mmp_fleet *f, const PlaceArgs &a, cudaStream_t s
       perm = c->d_sidx2.as<int32_t>();
       f->launches += 2;
     }
-    auto kern = f->direct_minb == 8 ? k_place_direct<4, 8> : (f->direct_minb == 6 ? k_place_direct<4, 6> : k_place_direct<4, 4>);
+    int minb = f->direct_minb;
+    if (minb == 6 && blocks > f->sm_count * 6 && blocks <= f->sm_count * 8) minb = 8;  // a launch of 1.0 .. 1.33 waves at 6 blocks per SM fits ONE wave at 8
+    auto kern = minb == 8 ? k_place_direct<4, 8> : (minb == 6 ? k_place_direct<4, 6> : k_place_direct<4, 4>);
     kern<<<blocks, 128, 0, st>>>(a.s, a.in, a.n, a.fresh, a.n_fresh, a.extra, a.out, a.now, a.seed, a.id_base, f->lane_budget, perm);
     f->launches++;
     return cudaGetLastError();
