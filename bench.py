@@ -702,13 +702,32 @@ def main():
                    "sample": f"{done} decisions of the same sweep, {threads} threads, C++ restatement of the reference's "
                              f"sorted-set walk (CacheMissForwardingLB.getNext); the Java reference cannot run here",
                    "parity_mismatches_vs_gpu": mism}
+        commit_fig = None
+        if world == 1:
+            try:  # mmp_fleet_commit after a publish window's worth of numeric instance updates (the device path), this fleet's size
+                rng_c = np.random.default_rng(7)
+                rows2 = fl.inst_rows.copy()
+                ts_c, paths = [], []
+                for _ in range(6):
+                    for i in rng_c.choice(fl.n_instances, size=min(fl.n_instances, 1000), replace=False):
+                        rows2[i]["rpm"] = int(rng_c.integers(0, 3000))
+                        solver.instance_update(int(i), rows2[i])
+                    t0 = time.perf_counter()
+                    solver.commit()
+                    ts_c.append(1000.0 * (time.perf_counter() - t0))
+                    paths.append(int(solver.commit_info()[0]))
+                commit_fig = {"p50_ms": float(np.percentile(ts_c[1:], 50)), "max_ms": float(np.max(ts_c[1:])), "n": len(ts_c) - 1,
+                              "paths": paths, "note": "host clock around mmp_fleet_commit after 1 000 numeric instance updates; path 2 = rebuilt on the "
+                              "device (re-rank by counting, rank tables, masks, bitmap from the device-resident edges), 1 = host"}
+            except Exception as ex:
+                print(f"[bench] commit leg skipped: {ex}", file=sys.stderr)
         line = {
             "metric": METRIC, "value": value, "unit": "decisions/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
             "config": workload_config(world),
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-            "latency_b1": lat, "wall_s_timed_region": wall_s, "extra": extra_kernels,
+            "latency_b1": lat, "wall_s_timed_region": wall_s, "extra": extra_kernels, "commit": commit_fig,
         }
         if e2e_sweep is not None and e2e is not None:
             # the workload is a registry sweep, so the call a host makes for it is mmp_place_sweep; the

@@ -65,7 +65,13 @@ __global__ void k_rank_keys(const mmp_instance_row *__restrict__ rows, const uin
   if ((meta[i].y & 1) && r.vers != vers0) atomicOr(flags, 1);  // mixed versions: the comparator may be non-transitive (N1): host path
 }
 
-// rank_of[i] = #{ live j : compare_keys(j, i) < 0 }, keys tiled through shared memory
+// rank_of[i] = #{ live j : compare_keys(j, i) < 0 }, keys tiled through shared memory.  The j range is cut into gridDim.y
+// slices (N threads alone would leave most SMs idle: 79 blocks at 10 k instances); rank_of must hold 0 for live and -1 for
+// other indices on entry (k_rank_init), every slice adds its count
+__global__ void k_rank_init(const int2 *__restrict__ meta, int n_idx, int32_t *__restrict__ rank_of) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_idx) rank_of[i] = (meta[i].y & 1) ? 0 : -1;
+}
 __global__ void __launch_bounds__(128) k_rank_count(const OrderKey *__restrict__ keys, const int2 *__restrict__ meta, int n_idx,
                                                     long long churn2, int32_t *__restrict__ rank_of) {
   __shared__ OrderKey tile[128];
@@ -74,20 +80,22 @@ __global__ void __launch_bounds__(128) k_rank_count(const OrderKey *__restrict__
   const bool mine = i < n_idx && (meta[i].y & 1);
   OrderKey me;
   if (i < n_idx) me = keys[i];
+  const int per = ((n_idx + (int)gridDim.y - 1) / (int)gridDim.y + 127) / 128 * 128;
+  const int j0 = (int)blockIdx.y * per, j1 = min(n_idx, j0 + per);
   int cnt = 0;
-  for (int base = 0; base < n_idx; base += 128) {
+  for (int base = j0; base < j1; base += 128) {
     const int j = base + threadIdx.x;
-    live_t[threadIdx.x] = (j < n_idx) ? (meta[j].y & 1) : 0;
-    if (j < n_idx) tile[threadIdx.x] = keys[j];
+    live_t[threadIdx.x] = (j < j1) ? (meta[j].y & 1) : 0;
+    if (j < j1) tile[threadIdx.x] = keys[j];
     __syncthreads();
     if (mine) {
-      const int lim = min(128, n_idx - base);
+      const int lim = min(128, j1 - base);
       for (int t = 0; t < lim; t++)
         if (live_t[t] && compare_keys(tile[t], me, churn2) < 0) cnt++;
     }
     __syncthreads();
   }
-  if (i < n_idx) rank_of[i] = mine ? cnt : -1;
+  if (mine && cnt) atomicAdd(&rank_of[i], cnt);
 }
 
 __global__ void k_build_rank_tables(const mmp_instance_row *__restrict__ rows_in, const int2 *__restrict__ meta,

@@ -1939,7 +1939,12 @@ static int32_t commit_device(mmp_fleet *f, DeviceSnapshot &ds, cudaStream_t st) 
   const int blocks = (NI + 127) / 128;
   k_rank_keys<<<blocks, 128, 0, st>>>(lv.inst_rows.as<mmp_instance_row>(), lv.inst_tie.as<uint4>(), lv.inst_meta.as<int2>(), NI,
                                      (long long)f->hs.cfg.min_space_units, lv.keys.as<OrderKey>(), vers0, lv.flags.as<int>());
-  k_rank_count<<<blocks, 128, 0, st>>>(lv.keys.as<OrderKey>(), lv.inst_meta.as<int2>(), NI, churn2, ds.rank_of.as<int32_t>());
+  k_rank_init<<<blocks, 128, 0, st>>>(lv.inst_meta.as<int2>(), NI, ds.rank_of.as<int32_t>());
+  {  // enough (i-block, j-slice) pairs to fill the SMs a few times over
+    const int slices = std::max(1, std::min((NI + 127) / 128, (f->sm_count * 8 + blocks - 1) / blocks));
+    k_rank_count<<<dim3((unsigned)blocks, (unsigned)slices), 128, 0, st>>>(lv.keys.as<OrderKey>(), lv.inst_meta.as<int2>(), NI, churn2, ds.rank_of.as<int32_t>());
+  }
+  f->launches++;
   k_build_rank_tables<<<blocks, 128, 0, st>>>(lv.inst_rows.as<mmp_instance_row>(), lv.inst_meta.as<int2>(), ds.rank_of.as<int32_t>(), NI,
                                              (long long)f->hs.cfg.min_space_units, ds.rows.as<RankRow>(), ds.cap_col.as<int64_t>(),
                                              ds.lthreads_col.as<int32_t>(), ds.linprog_col.as<int32_t>(), ds.part_of_rank.as<int32_t>(),
