@@ -50,8 +50,33 @@ class ClockSampler(threading.Thread):
         self.samples = []
         self.stop_flag = threading.Event()
         self.proc = None
+        self.t_mark = None  # samples taken before mark() (warm-up) are dropped
+        self.stamps = []
+
+    def mark(self):
+        self.t_mark = time.perf_counter()
 
     def run(self):
+        # NVML in-process (a query takes tens of microseconds: the timed region of this bench is a few milliseconds, which the
+        # 100 ms period of `nvidia-smi -lms` cannot sample); nvidia-smi as the fall-back
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            names = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+            while not self.stop_flag.is_set():
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                try:
+                    r = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                except Exception:
+                    r = 0
+                self.samples.append([str(sm), str(mx), "0"] + ["Active" if r & bit else "Not Active" for _, bit in names])
+                self.stamps.append(time.perf_counter())
+                time.sleep(0.001)
+            return
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -65,6 +90,7 @@ class ClockSampler(threading.Thread):
                 parts = [p.strip() for p in line.split(",")]
                 if len(parts) >= 7:
                     self.samples.append(parts)
+                    self.stamps.append(time.perf_counter())
         except Exception:
             pass
 
@@ -76,7 +102,9 @@ class ClockSampler(threading.Thread):
             except Exception:
                 pass
         sm, mx, reasons = [], [], set()
-        for p in self.samples:
+        for p, ts in zip(list(self.samples), list(self.stamps)):
+            if self.t_mark is not None and ts < self.t_mark:
+                continue
             try:
                 sm.append(float(p[0]))
                 mx.append(float(p[1]))
@@ -297,10 +325,12 @@ def run_churn(args, rank: int, world: int, local_rank: int):
     dev_ms, wall_ms, phases, mism, cpu_s = [], [], [], 0, []
     n_dec = n_evict = n_lru = n_pub = 0
     for ep in range(args.warmup + args.steps):
+        if ep == 0:
+            sampler.start()
+            time.sleep(0.05)
         if ep == args.warmup:
             launches0 = s.kernel_launches()
-            sampler.start()
-            time.sleep(0.25)
+            sampler.mark()
         ev = w.events(ep, CHURN_EVENTS, SEED)
         now0 = fl.now_ms + ep * w.window_ms
         s._ck(lib.mmp_flush_l2(s.h))
@@ -447,15 +477,16 @@ def main():
 
     # inputs smaller than L2 (C2: a 12.8 MB bitmap): write a buffer larger than L2 before every timed step
     flush = (lambda: solver._ck(lib.mmp_flush_l2(solver.h))) if B * row_words * 4 < 200e6 else (lambda: None)
-    for _ in range(args.warmup):
-        solver._ck(lib.mmp_place_batch_device(solver.h, d_in, B, d_out, fl.now_ms, SEED, C.byref(kms)))
-    launches0 = solver.kernel_launches()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.25)
+        time.sleep(0.05)
+    for _ in range(args.warmup):
+        solver._ck(lib.mmp_place_batch_device(solver.h, d_in, B, d_out, fl.now_ms, SEED, C.byref(kms)))
+    launches0 = solver.kernel_launches()
     barrier()
     kernel_ms = []
+    sampler.mark()
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
         flush()
