@@ -153,8 +153,8 @@ def test_registry_sweep_equals_the_batch_of_records(emul_lib, oracle_lib):
 @pytest.mark.parametrize("window", [1, 2, 5, 10])
 @pytest.mark.parametrize("config,nm,ni,seed", [("C3", 2000, 1300, 33), ("C5", 1500, 500, 5), ("MIX", 500, 300, 14), ("MIX", 500, 700, 41)])
 def test_stream_routine_window_widths(emul_lib, oracle_lib, config, nm, ni, seed, window, second_chance):
-    """decide_stream sees a window of the decision's exclusion row: the first `window` words of the type slot's compressed
-    word list (k_place_lanes copies 14 out of the landing stage).  second_chance = 0: a walk that leaves the window must be
+    """decide_stream sees a window of the decision's exclusion row: its first `window` words (the kernels copy MMP_LANE_WIN = 12);
+    beyond it a walk steps through the type slot's compressed word list.  second_chance = 0: a walk that leaves the window must be
     declined, never answered from partial information; 1: it goes on reading the row itself (the kernel reads it from L2)."""
     import ctypes as C
     emul_lib.mmp_emul_lane_bails.restype = C.c_long
@@ -179,5 +179,34 @@ def test_stream_routine_window_widths(emul_lib, oracle_lib, config, nm, ni, seed
     finally:
         emul_lib.mmp_emul_set_window(32)
         emul_lib.mmp_emul_set_lane_global(1)
-        emul_lib.mmp_emul_set_lane_window(10)
+        emul_lib.mmp_emul_set_lane_window(12)
+        emul_lib.mmp_emul_set_lane_budget(48)
+
+
+@pytest.mark.parametrize("window,budget", [(12, 192), (0, 1000), (3, 400)])
+@pytest.mark.parametrize("config,nm,ni,seed", [("C5", 900, 10000, 5), ("C5", 900, 5000, 6), ("C3", 900, 10000, 3)])
+def test_long_walks_match_oracle(emul_lib, oracle_lib, config, nm, ni, seed, window, budget):
+    """Rows of 160-320 words with the budgets the kernels run with: walks of a hundred and more steps beyond the window go
+    through the chunk machinery of decide_stream (8 list entries gathered at a time; a chunk none of whose steps can stop the
+    walk is taken at once), a full best instance is handled by the lane routine (simple case).  window 0 = k_place_small."""
+    import ctypes as C
+    emul_lib.mmp_emul_lane_bails.restype = C.c_long
+    emul_lib.mmp_emul_set_window(2)
+    emul_lib.mmp_emul_set_lane_window(window)
+    emul_lib.mmp_emul_set_lane_global(1)
+    emul_lib.mmp_emul_set_lane_budget(budget)
+    try:
+        fl = make_fleet(config, nm, ni, seed)
+        o = oracle_from_synth(fl)
+        s = solver_from_synth(fl, emul_lib)
+        emul_lib.mmp_emul_lane_bails(None)
+        for plain in (True, False):
+            sd = make_decisions(fl, 900, seed, sweep=plain, plain=plain)
+            compare_decisions(fl, sd, o, s, seed=seed + 5, full_lists=False)
+        n = C.c_long()
+        bails = emul_lib.mmp_emul_lane_bails(C.byref(n))
+        assert n.value > 0 and bails < n.value // 4  # the lane routine itself answers (almost) all of them
+    finally:
+        emul_lib.mmp_emul_set_window(32)
+        emul_lib.mmp_emul_set_lane_window(12)
         emul_lib.mmp_emul_set_lane_budget(48)
