@@ -225,7 +225,7 @@ def run_reference(args, rank: int, world: int):
         "e2e": {"value": value, "unit": "decisions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=OUT, flush=True)
 
 
 def workload_config(world: int):
@@ -292,7 +292,7 @@ def run_reference_churn(args):
         "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": churn_config(),
         "cpu_baseline": {"value": value, "unit": "events/s", "cores": 1, "kind": "port",
                          "sample": f"{len(times)} windows of {CHURN_EVENTS} events, the oracle's closed loop (oracle/mm_sim.inc), one thread"},
-        "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+        "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), file=OUT, flush=True)
 
 
 def run_churn(args, rank: int, world: int, local_rank: int):
@@ -409,7 +409,7 @@ def run_churn(args, rank: int, world: int, local_rank: int):
                           "parity_mismatching_windows": mism} if check else None),
         "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=OUT, flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
@@ -768,11 +768,26 @@ def main():
             line["e2e"] = e2e_sweep
         if inst is not None:
             line["instance_sharded"] = inst
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+def _only_the_json_line_on_stdout():
+    """Libraries print to the process's stdout behind Python's back (NCCL's version banner with NCCL_DEBUG=VERSION, ...): route
+    file descriptor 1 to stderr for the whole run and keep the original for the one JSON line."""
+    global OUT
+    try:
+        sys.stdout.flush()
+        OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    except Exception:
+        OUT = sys.stdout
+
+
+OUT = sys.stdout
+
 if __name__ == "__main__":
+    _only_the_json_line_on_stdout()
     main()
