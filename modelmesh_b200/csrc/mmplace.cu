@@ -2437,12 +2437,12 @@ int32_t mmp_place_sweep(mmp_fleet *f, int32_t first_model, int32_t n, const int3
   CK(c->d_trace.ensure(n_self * 4 + n_fav * 4 + 16));  // scratch: self[] then favour bits
   int32_t *d_self = c->d_trace.as<int32_t>();
   uint32_t *d_fav = n_fav ? reinterpret_cast<uint32_t *>(d_self + n_self) : nullptr;
+  CK(cudaMemcpyAsync(d_self, self, n_self * 4, cudaMemcpyHostToDevice, st));
+  if (n_fav) CK(cudaMemcpyAsync(d_fav, favour_bits, n_fav * 4, cudaMemcpyHostToDevice, st));
+  k_expand_sweep<<<(n + 255) / 256, 256, 0, st>>>(c->d_in.as<mmp_decision_in>(), n, first_model, d_self, self_stride, d_fav);
+  f->launches++;
+  CK(cudaGetLastError());
   if (f->hs.cfg.shard_count > 1 || f->comm) {
-    CK(cudaMemcpyAsync(d_self, self, n_self * 4, cudaMemcpyHostToDevice, st));
-    if (n_fav) CK(cudaMemcpyAsync(d_fav, favour_bits, n_fav * 4, cudaMemcpyHostToDevice, st));
-    k_expand_sweep<<<(n + 255) / 256, 256, 0, st>>>(c->d_in.as<mmp_decision_in>(), n, first_model, d_self, self_stride, d_fav);
-    f->launches++;
-    CK(cudaGetLastError());
     int32_t rcs = place_sharded(f, c, ds, c->d_in.as<mmp_decision_in>(), n, c->d_fresh.as<FreshRow>(), 0, c->d_extra.as<int32_t>(), 0,
                                 c->d_out.as<mmp_decision_out>(), now_ms, seed, st);
     if (rcs < 0) return rcs;
@@ -2450,22 +2450,14 @@ int32_t mmp_place_sweep(mmp_fleet *f, int32_t first_model, int32_t n, const int3
     CK(cudaStreamSynchronize(st));
     return MMP_OK;
   }
-  // chunks through NPIPE streams: the inputs of chunk k + 1 travel to the device and the results of chunk k - 1 to the host
-  // (PCIe is full duplex) while chunk k is expanded and scored
-  const int32_t CHUNK = 1 << 17;  // a multiple of 32: favour bits of a chunk start on a word
-  if (!self_stride) CK(cudaMemcpyAsync(d_self, self, 4, cudaMemcpyHostToDevice, st));
+  // chunks: the results of chunk k travel to the host while chunk k + 1 is scored
+  const int32_t CHUNK = 1 << 18;
   CK(cudaEventRecord(c->ready, st));
   for (int i = 0; i < PlaceCtx::NPIPE; i++) CK(cudaStreamWaitEvent(c->pipe[i], c->ready, 0));
   int ci = 0;
   for (int32_t lo = 0; lo < n; lo += CHUNK, ci++) {
     const int32_t cnt = std::min(CHUNK, n - lo);
     cudaStream_t ps = c->pipe[ci % PlaceCtx::NPIPE];
-    if (self_stride) CK(cudaMemcpyAsync(d_self + lo, self + lo, (size_t)cnt * 4, cudaMemcpyHostToDevice, ps));
-    if (n_fav) CK(cudaMemcpyAsync(d_fav + lo / 32, favour_bits + lo / 32, (size_t)((cnt + 31) / 32) * 4, cudaMemcpyHostToDevice, ps));
-    k_expand_sweep<<<(cnt + 255) / 256, 256, 0, ps>>>(c->d_in.as<mmp_decision_in>() + lo, cnt, first_model + lo, self_stride ? d_self + lo : d_self,
-                                                     self_stride, n_fav ? d_fav + lo / 32 : nullptr);
-    f->launches++;
-    CK(cudaGetLastError());
     PlaceArgs a{ds.view, c->d_in.as<mmp_decision_in>() + lo, cnt, c->d_fresh.as<FreshRow>(), 0, c->d_extra.as<int32_t>(),
                 c->d_out.as<mmp_decision_out>() + lo, nullptr, nullptr, now_ms, seed, f->id_base.load() + (uint64_t)lo};
     CK(launch_place(f, a, ps));
