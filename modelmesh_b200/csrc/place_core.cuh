@@ -879,8 +879,8 @@ struct WarpVote { MMP_D bool any(bool p) const { return __any_sync(0xffffffffu, 
 // lane's attempt ends at the window's edge.
 // Same semantics and quirks as decide_ctx (N2: the non-self test reads the caller's fresh record).  Returns false --
 // and the caller redoes the decision with the cooperative general routine -- for everything outside the common case:
-// malformed decision, more than LANE_MAX_EXTRA extra excludes, no entry (replicaset retry), a full best whose type has
-// preferred instances it is not one of (non-simple (b)), or
+// malformed decision, more than LANE_MAX_EXTRA extra excludes, no entry (replicaset retry), a full best followed by preferred
+// entries within its lruTime distance (non-simple (b) with preferred candidates), or
 // a walk of more than `budget` steps.  Instance-sharded: a walk that needs ranks beyond this shard's range sets MMP_TF_OPEN.
 // self_eword = the row word that holds self's bit (anywhere in the row).  Must be called by every lane of the vote group
 // (active = false for lanes without a decision).
@@ -1014,14 +1014,13 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &Tw, const Lan
     const bool has_pref = ctx_has_pref(c);
     simple = !has_pref || pbit(b);
     use_pref = has_pref && simple;  // best is preferred: preference is treated as required (MM:4905-4907)
-    if (best_full && !simple) live = false;  // non-simple (b), MM:4853-4887: general routine
   }
   // ---- A': non-simple (a) ----
   uint32_t r1 = NONE_RANK, k1 = kb;
   {
     const uint32_t b_w = b >> 5, m_b = mask_above(b_w * 32u, b);
     uint32_t k = kb;
-    bool walking = live && !simple, ended = false;
+    bool walking = live && !simple && !best_full, ended = false;
     MMP_WALK(k, walking, ended, true, false, {
       uint32_t x = A.cx(wi) & ~e & (A.p(wi) | A.full(wi));
       if (has_x) x &= ~xmask(wi);
@@ -1032,7 +1031,44 @@ MMP_HD bool decide_stream(const SnapshotView &s, const LaneTables &Tw, const Lan
     (void)ended;
   }
   bool open = false;
-  if (live && !simple) {
+  // ---- A'': non-simple (b), MM:4853-4887 -- a full best that is not one of its type's preferred instances.  kb = the first
+  // later entry whose lruTime is "far" from the best's (more than 2 min and more than a quarter of the best's age; each entry
+  // tested on its OWN published lruTime); a preferred entry before kb makes the preferred ones the candidates (the general
+  // routine takes those decisions), none means "no preference" logic over the entries before kb ----
+  {
+    const int64_t a4 = age_of(best_lru, now) / 4;
+    auto far = [&](int64_t l) { const int64_t diff = jsub(l, best_lru); return diff > 120000 && diff > a4; };
+    const uint32_t b_w = b >> 5, m_b = mask_above(b_w * 32u, b);
+    uint32_t k = kb, kb_rank = NONE_RANK;
+    bool pref_before = false;
+    const bool case_b = live && !simple && best_full;
+    bool walking = case_b, ended = false;
+    MMP_WALK(k, walking, ended, true, false, {
+      uint32_t x = A.cx(wi) & ~e;
+      if (has_x) x &= ~xmask(wi);
+      if (wi == b_w) x &= m_b;
+      go_ = true;
+      if (x) {
+        const int64_t l_lo = ldro(&s.lsum[wi].lo);
+        const int64_t l_hi = ldro(&s.lsum[wi].hi);
+        uint32_t v = 0;  // the members of x that are far
+        if (far(l_hi)) {
+          if (far(l_lo)) v = x;
+          else for (uint32_t t = x; t; t &= t - 1) { const uint32_t bt = (uint32_t)ffs32(t); if (far(ldro(&T.rows[wi * 32u + bt].lru))) v |= 1u << bt; }
+        }
+        const uint32_t near_ = v ? (x & mask_below(wi * 32u, wi * 32u + (uint32_t)ffs32(v))) : x;  // members before the first far one
+        if (near_ & A.p(wi)) { pref_before = true; go_ = false; }
+        else if (v) { kb_rank = wi * 32u + (uint32_t)ffs32(v); go_ = false; }
+      }
+    })
+    if (case_b && live) {
+      if (pref_before) live = false;                      // the preferred entries within the distance are the candidates: general routine
+      else if (kb_rank == NONE_RANK && open_end) open = true;  // the deciding entry is in a later shard
+      else hi = kb_rank;                                  // no preferred one in range: rewind, "no preference" logic (use_pref stays false)
+    }
+    (void)ended;
+  }
+  if (live && !simple && !best_full) {
     if (r1 == NONE_RANK) open = open_end;  // else: neither kind follows, "no preference" logic over the whole remainder
     else if (pbit(r1)) {
       const RankRow rp = row_of(r1);
