@@ -1139,7 +1139,9 @@ struct PlaceCtx {
   static constexpr int NSHARD_CHUNKS = 4;  // instance-sharded batches: scoring of chunk k+1 overlaps the all-reduce of chunk k
   cudaEvent_t shard_ev[NSHARD_CHUNKS + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   DevBuf d_in, d_out, d_fresh, d_extra, d_trace, d_cand;
-  DevBuf d_skey, d_skey2, d_sidx, d_sidx2, d_stmp;  // slot sort of a batch (k_slot_keys + cub radix sort -> perm)
+  // slot sort of a batch (k_slot_keys + cub radix sort -> perm): set 0 for single launches, 1 + pipe for the chunks of a pipelined call
+  static constexpr int NSORT = 4;
+  DevBuf d_skey[NSORT], d_skey2[NSORT], d_sidx[NSORT], d_sidx2[NSORT], d_stmp[NSORT];
   DevBuf d_open_flag, d_open_idx, d_n_open, d_cub, d_blocks, d_gathered, d_rows, d_in_open, d_out_open;  // instance-shard combine
   std::vector<FreshRow> fresh_host;
   // pinned, device-mapped scratch for tiny batches: the kernel reads the decisions and writes the results straight
@@ -1269,9 +1271,9 @@ static void release_ctx(mmp_fleet *f, PlaceCtx *c) {
 }
 static void destroy_ctx(PlaceCtx *c) {
   for (DevBuf *b : {&c->d_in, &c->d_out, &c->d_fresh, &c->d_extra, &c->d_trace, &c->d_cand, &c->d_open_flag,
-                    &c->d_open_idx, &c->d_n_open, &c->d_cub, &c->d_blocks, &c->d_gathered, &c->d_rows, &c->d_in_open, &c->d_out_open,
-                    &c->d_skey, &c->d_skey2, &c->d_sidx, &c->d_sidx2, &c->d_stmp})
+                    &c->d_open_idx, &c->d_n_open, &c->d_cub, &c->d_blocks, &c->d_gathered, &c->d_rows, &c->d_in_open, &c->d_out_open})
     b->release();
+  for (int k = 0; k < PlaceCtx::NSORT; k++) { c->d_skey[k].release(); c->d_skey2[k].release(); c->d_sidx[k].release(); c->d_sidx2[k].release(); c->d_stmp[k].release(); }
   if (c->e0) cudaEventDestroy(c->e0);
   if (c->e1) cudaEventDestroy(c->e1);
   if (c->ready) cudaEventDestroy(c->ready);
@@ -1302,6 +1304,7 @@ struct PlaceArgs {
   const int32_t *orig_id = nullptr;  // gather pass: decision i reads row i of s.excl and hashes with id orig_id[i]
   const int32_t *perm = nullptr;     // k_place_direct: position j of the launch resolves decision perm[j]
   struct PlaceCtx *ctx = nullptr;    // scratch for the slot sort (the call's own context)
+  int sort_slot = 0;                 // ... which of its scratch sets (chunks in flight on different streams use different ones)
 };
 
 // ring depth (a power of two) / warps per block by row size: rows up to 2 KiB (16k instances) K=4 x 8 warps, up to 4 KiB K=2 x 8, beyond K=2 x 4
@@ -1363,15 +1366,16 @@ static cudaError_t launch_place(mmp_fleet *f, const PlaceArgs &a, cudaStream_t s
     const int32_t *perm = a.perm;
     if (!perm && a.ctx && a.n >= 8192 && (f->sort_slots == 1 || (f->sort_slots == 2 && f->snaps[f->cur].sparse_slots))) {
       PlaceCtx *c = a.ctx;  // slot order: key pass + 16-bit radix sort of the indices (a few tens of microseconds per million decisions)
+      const int ss = a.sort_slot >= 0 && a.sort_slot < PlaceCtx::NSORT ? a.sort_slot : 0;
       cudaError_t e;
-      if ((e = c->d_skey.ensure((size_t)a.n * 2)) != cudaSuccess || (e = c->d_skey2.ensure((size_t)a.n * 2)) != cudaSuccess ||
-          (e = c->d_sidx.ensure((size_t)a.n * 4)) != cudaSuccess || (e = c->d_sidx2.ensure((size_t)a.n * 4)) != cudaSuccess) return e;
-      k_slot_keys<<<(a.n + 255) / 256, 256, 0, st>>>(a.s, a.in, a.n, c->d_skey.as<uint16_t>(), c->d_sidx.as<int32_t>());
+      if ((e = c->d_skey[ss].ensure((size_t)a.n * 2)) != cudaSuccess || (e = c->d_skey2[ss].ensure((size_t)a.n * 2)) != cudaSuccess ||
+          (e = c->d_sidx[ss].ensure((size_t)a.n * 4)) != cudaSuccess || (e = c->d_sidx2[ss].ensure((size_t)a.n * 4)) != cudaSuccess) return e;
+      k_slot_keys<<<(a.n + 255) / 256, 256, 0, st>>>(a.s, a.in, a.n, c->d_skey[ss].as<uint16_t>(), c->d_sidx[ss].as<int32_t>());
       size_t tmp = 0;
-      if ((e = cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->d_skey.as<uint16_t>(), c->d_skey2.as<uint16_t>(), c->d_sidx.as<int32_t>(), c->d_sidx2.as<int32_t>(), a.n, 0, 16, st)) != cudaSuccess) return e;
-      if ((e = c->d_stmp.ensure(tmp + 16)) != cudaSuccess) return e;
-      if ((e = cub::DeviceRadixSort::SortPairs(c->d_stmp.p, tmp, c->d_skey.as<uint16_t>(), c->d_skey2.as<uint16_t>(), c->d_sidx.as<int32_t>(), c->d_sidx2.as<int32_t>(), a.n, 0, 16, st)) != cudaSuccess) return e;
-      perm = c->d_sidx2.as<int32_t>();
+      if ((e = cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->d_skey[ss].as<uint16_t>(), c->d_skey2[ss].as<uint16_t>(), c->d_sidx[ss].as<int32_t>(), c->d_sidx2[ss].as<int32_t>(), a.n, 0, 16, st)) != cudaSuccess) return e;
+      if ((e = c->d_stmp[ss].ensure(tmp + 16)) != cudaSuccess) return e;
+      if ((e = cub::DeviceRadixSort::SortPairs(c->d_stmp[ss].p, tmp, c->d_skey[ss].as<uint16_t>(), c->d_skey2[ss].as<uint16_t>(), c->d_sidx[ss].as<int32_t>(), c->d_sidx2[ss].as<int32_t>(), a.n, 0, 16, st)) != cudaSuccess) return e;
+      perm = c->d_sidx2[ss].as<int32_t>();
       f->launches += 2;
     }
     int minb = f->direct_minb;
@@ -2377,6 +2381,7 @@ static int32_t place_impl(mmp_fleet *f, const mmp_decision_in *in, int32_t n, co
       CK(cudaMemcpyAsync(c->d_in.as<mmp_decision_in>() + lo, in + lo, (size_t)cnt * sizeof(mmp_decision_in), cudaMemcpyHostToDevice, ps));
       PlaceArgs a{vw, c->d_in.as<mmp_decision_in>() + lo, cnt, c->d_fresh.as<FreshRow>(), n_fresh, c->d_extra.as<int32_t>(),
                   c->d_out.as<mmp_decision_out>() + lo, nullptr, nullptr, now_ms, seed, f->id_base.load() + (uint64_t)lo};
+      a.ctx = c; a.sort_slot = 1 + ci % PlaceCtx::NPIPE;
       CK(launch_place(f, a, ps));
       CK(cudaMemcpyAsync(out + lo, c->d_out.as<mmp_decision_out>() + lo, (size_t)cnt * sizeof(mmp_decision_out), cudaMemcpyDeviceToHost, ps));
     }
@@ -2460,6 +2465,7 @@ int32_t mmp_place_sweep(mmp_fleet *f, int32_t first_model, int32_t n, const int3
     cudaStream_t ps = c->pipe[ci % PlaceCtx::NPIPE];
     PlaceArgs a{ds.view, c->d_in.as<mmp_decision_in>() + lo, cnt, c->d_fresh.as<FreshRow>(), 0, c->d_extra.as<int32_t>(),
                 c->d_out.as<mmp_decision_out>() + lo, nullptr, nullptr, now_ms, seed, f->id_base.load() + (uint64_t)lo};
+    a.ctx = c; a.sort_slot = 1 + ci % PlaceCtx::NPIPE;
     CK(launch_place(f, a, ps));
     CK(cudaMemcpyAsync(out + lo, c->d_out.as<mmp_decision_out>() + lo, (size_t)cnt * sizeof(mmp_decision_out), cudaMemcpyDeviceToHost, ps));
   }

@@ -1,0 +1,13 @@
+#!/bin/bash
+# round 2, run x: slot-sorted chunks in the pipelined end-to-end paths: GPU suite, C5 and C3 default bench lines
+cd "$GRAFT_REPO_ROOT"
+O=gpurun_out
+timeout 1200 python -m pytest tests -m gpu -q > $O/r02_x_pytest_gpu.log 2>&1; tail -3 $O/r02_x_pytest_gpu.log
+BENCH_CONFIG=C5 timeout 600 python bench.py > $O/r02_x_bench_c5_n1.json 2> $O/r02_x_bench_c5_n1.err
+timeout 600 python bench.py > $O/r02_x_bench_c3_n1.json 2> $O/r02_x_bench_c3_n1.err
+python - <<'PY'
+import json
+for f in ('gpurun_out/r02_x_bench_c5_n1.json', 'gpurun_out/r02_x_bench_c3_n1.json'):
+    d = json.loads([l for l in open(f) if l.startswith('{')][-1])
+    print(f, d['value'], d['ms_per_step'], d['clocks'], (d.get('latency_b1') or {}).get('p50_us'), d.get('e2e'), (d.get('e2e_records') or {}).get('value'), (d.get('cpu_baseline') or {}).get('parity_mismatches_vs_gpu'))
+PY
