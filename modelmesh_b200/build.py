@@ -10,7 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(CSRC, "libmmplace.so")
 SOURCES = ["mmplace.cu"]
-DEPS = ["mmplace.cu", "place_core.cuh", "host_state.hpp", "scan_kernels.cuh", os.path.join("..", "..", "include", "mmplace.h")]
+DEPS = ["mmplace.cu", "place_core.cuh", "host_state.hpp", "scan_kernels.cuh", "commit_kernels.cuh", "churn_kernels.cuh",
+        "registry_kernels.cuh", os.path.join("..", "..", "include", "mmplace.h")]
 
 
 def nvcc_path() -> str:
