@@ -4,6 +4,7 @@ the Java text, structured differently from oracle/mm_oracle.cpp (lists and dicts
 shortlist as a sorted-prefix enumeration), must give the same ordered shortlist, rpm-filter survivors and pick.
 
   * shortlist == brute-force filter -> sort -> prefix (MM:4760-4771, 4806-4811, 4889-4937, N2/N3 literal)
+  * the same with type constraints and preferences: constrainTo, non-simple (a) and (b) (MM:4788-4790, 4816-4887), N8
   * rpm filter == independent re-derivation (MM:4957-4980)
   * PLACEMENT_ORDER is a strict weak order on uniform-`vers` fleets and the cluster order is sorted under it (MM:4646-4703)
 """
@@ -212,3 +213,184 @@ def test_rpm_filter_thresholds_independent_rederivation(oracle_lib):
                 return ((ago < -1000 and rpm > int(1.1 * mn)) or (ago < 5000 and rpm > int(1.5 * mn)) or (ago < 720_000 and rpm > 3 * mn)
                         or (ago < 86_400_000 and rpm > 4 * mn))
             assert [bool(k) for k in ckeep[:3]] == [not drop(r) for r in loads], (fresh_rpm, ago)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The same brute force for types WITH constraints: constrainTo (required labels), prefer (preferred labels), the two
+# non-simple cases.  Written from the Java text (MM:4776-5004) as an iterator over a materialised list, the way the Java
+# reads -- `it`, `clusterStateReplay`, `prefer = null` -- and not the way the oracle or the kernels are structured.
+# The candidate / preferred sets themselves come from the oracle's TypeConstraintManager restatement (this test pins
+# getNext's use of them, test_type_masks_* pin the sets).
+# ---------------------------------------------------------------------------------------------------------------
+def _select(cands, loads, last_used, now, rnd, self_idx, favour_self):
+    keep = [True] * len(cands)
+    remaining, index = len(cands), 0
+    if len(cands) > 1:
+        ago = _age(last_used, now)
+        if ago < 5 * 86_400_000:
+            mn = max(100, min(loads))
+            m11, m15 = _java_int(1.1 * mn), _java_int(1.5 * mn)
+            for k, rpm in enumerate(loads):
+                if rpm >= 100 and ((ago < -1000 and rpm > m11) or (ago < 5000 and rpm > m15) or (ago < 720_000 and rpm > mn * 3)
+                                   or (ago < 86_400_000 and rpm > mn * 4)):
+                    keep[k] = False
+                    remaining -= 1
+                    if remaining == 1:
+                        break
+        index = 0 if remaining == 1 else (((rnd >> 32) * remaining) >> 32)
+    chosen = [c for c, k in zip(cands, keep) if k][index]
+    target = ob.SELF if (not favour_self and chosen == self_idx) else chosen
+    return dict(target=target, cands=cands, keep=keep, n_remaining=remaining, pick=index)
+
+
+def brute_get_next_tc(order, rows, ids, active, replaced, min_space, self_idx, fresh, favour_self, last_used, excluded, now, rnd,
+                      constrain_to, prefer):
+    def passes(i, use_rs):
+        if constrain_to is not None and i not in constrain_to:
+            return False
+        if i in excluded or not active[i]:
+            return False
+        if use_rs and replaced and len(ids[i]) >= 7 and ids[i][:6] in replaced:
+            return False
+        return True
+    flt = [i for i in order if passes(i, True)]
+    if not flt and replaced:
+        flt = [i for i in order if passes(i, False)]
+    if not flt:
+        return dict(target=ob.NONE, cands=[], keep=[], n_remaining=0, pick=0)
+    exclude_self = self_idx in excluded
+    it = iter(flt)
+    best_entry = next(it)                                               # bestEntry: never reassigned
+    best_iid = best_entry
+    us = (not exclude_self) and best_iid == self_idx
+    best_inst = fresh if us else rows[best_iid]
+    best_is_full = _rem(best_inst) < min_space                          # final: keeps the FIRST entry's verdict
+    cands, loads = [], []
+    case = "simple"
+    simple = prefer is None or best_iid in prefer
+    if not simple:
+        replay = []
+        if not best_is_full:                                            # (a) MM:4828-4852
+            found = False
+            for ent in it:
+                if ent in prefer:
+                    found = True
+                    best_iid = ent
+                    best_inst = rows[ent]                               # ent.getValue(): the published record, even for self
+                    us = (not us) and (not exclude_self) and ent == self_idx
+                    break
+                if _rem(rows[ent]) < min_space:
+                    break
+                replay.append(ent)
+            case = "a_found" if found else "a_rewind"
+            if not found:
+                it = iter(replay)
+                prefer = None
+            simple = True
+        else:                                                           # (b) MM:4853-4887
+            oldest = int(best_inst["lru_time"])
+            for ent in it:
+                diff = _i64(int(rows[ent]["lru_time"]) - oldest)
+                if diff > 120_000 and diff > int(_age(oldest, now) / 4):
+                    break
+                if ent in prefer:
+                    us = (not us) and (not exclude_self) and ent == self_idx
+                    if us and favour_self:
+                        return dict(target=ob.NONE, cands=[], keep=[], n_remaining=0, pick=0, early=True)  # N8: null
+                    replay = None
+                    cands.append(ent)
+                    loads.append(int(rows[ent]["rpm"]))
+                elif replay is not None:
+                    replay.append(ent)
+            case = "b_pref" if replay is None else "b_rewind"
+            if replay is not None:
+                it = iter(replay)
+                prefer = None
+                simple = True
+    if simple:
+        if us and favour_self:
+            return dict(target=ob.SELF, cands=[], keep=[], n_remaining=0, pick=0, early=True)
+        cands.append(best_iid)
+        loads.append(int(best_inst["rpm"]))
+        oldest = int(best_inst["lru_time"])
+        for ent in it:
+            if prefer is not None and ent not in prefer:
+                continue
+            us = (not us) and (not exclude_self) and ent == self_idx
+            cur = rows[best_entry] if us else fresh                     # N2 / N3, literal
+            if best_is_full:
+                diff = _i64(int(cur["lru_time"]) - oldest)
+                if diff > 45_000 and diff > int(_age(oldest, now) / 10):
+                    break
+            else:
+                rem = _rem(cur)
+                if rem < min_space or rem < (_rem(best_inst) >> 2):
+                    break
+                cnt, first = int(rows[ent]["count"]), int(best_inst["count"])
+                if cnt >= 10 and cnt > first + (first >> 2):
+                    break
+            if us and favour_self:
+                return dict(target=ob.SELF, cands=cands, keep=[], n_remaining=0, pick=0, early=True)
+            cands.append(ent)
+            loads.append(int(cur["rpm"]))
+    if not cands:
+        return dict(target=ob.NONE, cands=[], keep=[], n_remaining=0, pick=0)
+    out = _select(cands, loads, last_used, now, rnd, self_idx, favour_self)
+    out["case"] = case
+    return out
+
+
+@pytest.mark.parametrize("config,nm,ni,seed", [("C3", 1500, 400, 3), ("C3", 1500, 97, 4), ("C5", 1500, 500, 5), ("C5", 1500, 300, 7),
+                                               ("MIX", 500, 160, 5), ("MIX", 500, 300, 8), ("MIX", 500, 97, 14), ("MIX", 500, 200, 21),
+                                               ("MIX", 500, 250, 41), ("MIX", 500, 120, 3), ("MIX", 500, 64, 10), ("MIX", 500, 180, 11)])
+def test_constrained_types_and_preferences_parity_unpinned_by_reference_tests(oracle_lib, config, nm, ni, seed):
+    fl = make_fleet(config, nm, ni, seed)
+    if fl.type_config is None:
+        pytest.skip("this seed draws no type constraints (covered by the test above)")
+    o = oracle_from_synth(fl)
+    sd = make_decisions(fl, 1200, seed)
+    od, off, idx = oracle_inputs(fl, sd)
+    fresh = sd.fresh if len(sd.fresh) else None
+    res, coff, cidx, cload, ckeep = o.get_next_batch(od, fl.type_names, off, idx, fl.now_ms, seed * 7, fresh=fresh, want_candidates=True)
+    order = [int(x) for x in o.cluster_order()]
+    rows = fl.inst_rows
+    active = [bool(a) and not bool(s) for a, s in zip(rows["active"], rows["shutting_down"])]
+    replaced = set(fl.replaced_replicasets)
+    sets = {}
+    for t, name in enumerate(fl.type_names):
+        a, p = o.type_sets(name, fl.n_instances)
+        sets[t] = (None if a is None else set(int(x) for x in np.nonzero(a)[0]), None if p is None else set(int(x) for x in np.nonzero(p)[0]))
+    seen = dict(simple=0, a_found=0, a_rewind=0, b_pref=0, b_rewind=0, constrained=0)
+    for i in range(len(od)):
+        d = sd.dec[i]
+        self_idx = int(d["self"])
+        if d["fresh"] >= 0:
+            fr = sd.fresh[int(d["fresh"])]
+        else:
+            fr = rows[self_idx].copy()
+            fr["rpm"] = 0                                               # N7
+        cto, prf = sets[int(od["type_idx"][i])]
+        b = brute_get_next_tc(order, rows, fl.inst_ids, active, replaced, fl.min_space_units, self_idx, fr,
+                              bool(d["flags"] & L.DF_FAVOUR_SELF), int(od["last_used"][i]), set(int(x) for x in idx[off[i]:off[i + 1]]),
+                              fl.now_ms, _hash64(seed * 7, i), cto, prf)
+        assert b["target"] == int(res["target"][i]), (i, b, res[i])
+        if b.get("early") or not b["cands"]:
+            continue
+        want = [int(x) for x in cidx[coff[i]:coff[i + 1]]]
+        assert b["cands"] == want, (i, b["cands"][:6], want[:6])
+        assert b["keep"] == [bool(k) for k in ckeep[coff[i]:coff[i + 1]]], i
+        assert b["n_remaining"] == int(res["n_remaining"][i]) and b["pick"] == int(res["pick_index"][i]), i
+        seen["constrained"] += cto is not None
+        seen[b["case"]] = seen.get(b["case"], 0) + 1
+    acc = getattr(test_constrained_types_and_preferences_parity_unpinned_by_reference_tests, "seen", {})
+    for k, v in seen.items():
+        acc[k] = acc.get(k, 0) + v
+    test_constrained_types_and_preferences_parity_unpinned_by_reference_tests.seen = acc
+
+
+def test_constrained_brute_force_reached_every_case():
+    seen = getattr(test_constrained_types_and_preferences_parity_unpinned_by_reference_tests, "seen", None)
+    if seen is None:
+        pytest.skip("runs after the constrained brute-force cases")
+    # every branch of MM:4822-4887 was exercised: (a) with and without a preferred entry, (b) with preferred candidates and rewound
+    assert seen["constrained"] > 500 and seen["a_found"] > 100 and seen["a_rewind"] > 20 and seen["b_pref"] > 20 and seen["b_rewind"] > 20, seen
