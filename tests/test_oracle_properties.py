@@ -5,6 +5,7 @@ shortlist as a sorted-prefix enumeration), must give the same ordered shortlist,
 
   * shortlist == brute-force filter -> sort -> prefix (MM:4760-4771, 4806-4811, 4889-4937, N2/N3 literal)
   * the same with type constraints and preferences: constrainTo, non-simple (a) and (b) (MM:4788-4790, 4816-4887), N8
+  * the reaper's proactive-load selection (MM:6455-6462, 6574-6577, 6616-6735, N12) as plain Python arithmetic and a sorted list
   * rpm filter == independent re-derivation (MM:4957-4980)
   * PLACEMENT_ORDER is a strict weak order on uniform-`vers` fleets and the cluster order is sorted under it (MM:4646-4703)
 """
@@ -394,3 +395,115 @@ def test_constrained_brute_force_reached_every_case():
         pytest.skip("runs after the constrained brute-force cases")
     # every branch of MM:4822-4887 was exercised: (a) with and without a preferred entry, (b) with preferred candidates and rewound
     assert seen["constrained"] > 500 and seen["a_found"] > 100 and seen["a_rewind"] > 20 and seen["b_pref"] > 20 and seen["b_rewind"] > 20, seen
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The reaper's proactive-load selection (MM:6455-6462 candidate rule inputs, MM:6574-6577, MM:6616-6735), naive form:
+# plain Python ints for the Java arithmetic, a sorted list for the TreeSet<ModelToLoad> (whose compareTo looks at lastUsed
+# only: two candidates with the same lastUsed are ONE element -- N12), partitions visited in getPartitionStats() order with
+# the selected models nulled out of the shared candidate list.
+# ---------------------------------------------------------------------------------------------------------------
+def _trunc_div(a, b):  # Java integer division truncates toward zero
+    q = abs(a) // abs(b)
+    return q if (a >= 0) == (b >= 0) else -q
+
+
+def brute_reaper(stats, global_stats, insts_of_subset, rows, models, type_prohibited, default_size, now, taken):
+    """stats / global_stats: ClusterStats dicts; insts_of_subset: instance indices the subset's loop visits (cluster order);
+    models: list of (last_used, type_idx, n_loaded, n_failed); type_prohibited(type_idx) -> bool for this subset."""
+    if not global_stats["total_capacity"] > 0:
+        return []
+    global_lru = 0 if global_stats["total_free"] > 0 else global_stats["global_lru"]
+    cands = [m for m, (lu, t, nl, nf) in enumerate(models) if nl == 0 and nf < 2 and (global_lru == 0 or lu > global_lru)]
+    free_count = total_count = 0
+    if stats["total_capacity"] > 0 and stats["total_free"] > 0:
+        if stats["model_copy_count"] < 3:
+            size_est = default_size
+        else:
+            used = stats["total_capacity"] - stats["total_free"]
+            used32 = ((used + (1 << 31)) % (1 << 32)) - (1 << 31)       # (int) of a long
+            avg = _trunc_div(used32, stats["model_copy_count"])
+            size_est = avg if stats["model_copy_count"] > 10 else _trunc_div(avg + default_size, 2)
+        space = 0
+        for i in insts_of_subset:
+            r = rows[i]
+            max_loads = int(r["l_threads"]) * 50 - int(r["l_in_prog"])
+            if max_loads <= 0:
+                continue
+            avail = _rem(r) - int(r["capacity"]) // 8
+            if avail > 0:
+                space += min(avail, max_loads * size_est)
+        space = _trunc_div(space, 2)
+        free_count = _trunc_div(space, size_est)
+        total_count = max(free_count, _trunc_div(stats["total_capacity"], 20 * size_est))
+    cutoff = 0 if stats["global_lru"] == LONG_MAX else stats["global_lru"] + max(_trunc_div(_age(stats["global_lru"], now), 3), 1_200_000)
+    to_load = []                                                        # [(lastUsed, model)], lastUsed descending, unique lastUsed
+    for m in cands:
+        if taken[m]:
+            continue
+        lu, t, _, _ = models[m]
+        if type_prohibited(t):
+            continue
+        if total_count > 0 and (free_count > 0 or lu > cutoff):
+            if len(to_load) < total_count or to_load[-1][0] < lu:
+                if all(x[0] != lu for x in to_load):                    # TreeSet.add: equal under compareTo -> not added
+                    to_load.append((lu, m))
+                    to_load.sort(key=lambda x: -x[0])
+                if len(to_load) > total_count:
+                    to_load.pop()
+    out = []
+    for lu, m in to_load:
+        if free_count > 0:
+            free_count -= 1
+        elif lu < cutoff:
+            break
+        taken[m] = 1
+        out.append(m)
+    return out
+
+
+@pytest.mark.parametrize("config,nm,ni,seed", [("C2", 3000, 300, 2), ("C3", 3000, 400, 3), ("C5", 3000, 400, 5), ("MIX", 1500, 160, 5),
+                                               ("MIX", 1500, 300, 8), ("MIX", 1500, 97, 14), ("MIX", 1500, 200, 2), ("MIX", 1500, 120, 29)])
+def test_reaper_selection_parity_unpinned_by_reference_tests(oracle_lib, config, nm, ni, seed):
+    fl = make_fleet(config, nm, ni, seed)
+    if config == "C5":  # leave some room so that the free-space branch is taken too
+        fl.inst_rows["used"][::3] = fl.inst_rows["capacity"][::3] // 2
+    o = oracle_from_synth(fl)
+    om = np.zeros(nm, dtype=ob.MODEL)
+    om["last_used"], om["type_idx"], om["n_loaded"], om["n_failed"] = fl.model_last_used, fl.model_type, fl.n_loaded, fl.n_failed
+    models = [(int(a), int(b), int(c), int(d)) for a, b, c, d in zip(om["last_used"], om["type_idx"], om["n_loaded"], om["n_failed"])]
+    names = ("total_capacity", "total_free", "global_lru", "instance_count", "model_copy_count")
+    as_dict = lambda s: {k: int(s[k]) for k in names}
+    gstats = as_dict(o.cluster_stats())
+    order = [int(x) for x in o.cluster_order()]
+    rows = fl.inst_rows
+    total = 0
+    if fl.type_config is None:
+        want = o.reaper_select(om, fl.type_names, -1, fl.now_ms)
+        got = brute_reaper(gstats, gstats, order, rows, models, lambda t: False, fl.default_model_size_units, fl.now_ms, np.zeros(nm, np.uint8))
+        assert got == [int(x) for x in want], (got[:5], want[:5])
+        total = len(got)
+    else:
+        pstats, pids = o.partition_stats()
+        part_of = {i: o.instance_partition(i) for i in order}
+        cand_sets = [o.type_sets(name, fl.n_instances)[0] for name in fl.type_names]
+        taken_o, taken_b = np.zeros(nm, np.uint8), np.zeros(nm, np.uint8)
+        for st, pid in zip(pstats, pids):                               # getPartitionStats() order (MM:6476-6489)
+            members = [i for i in order if part_of[i] == int(pid)]
+            rep = members[0]
+            # a type is prohibited for the subset iff its candidate set exists and excludes the subset's instances (TCM:557-575)
+            prohibited = lambda t, rep=rep: 0 <= t < len(cand_sets) and cand_sets[t] is not None and not bool(cand_sets[t][rep])
+            want = o.reaper_select(om, fl.type_names, int(pid), fl.now_ms, taken=taken_o)
+            got = brute_reaper(as_dict(st), gstats, members, rows, models, prohibited, fl.default_model_size_units, fl.now_ms, taken_b)
+            assert got == [int(x) for x in want], (int(pid), got[:5], [int(x) for x in want[:5]])
+            assert np.array_equal(taken_o, taken_b)
+            total += len(got)
+    acc = getattr(test_reaper_selection_parity_unpinned_by_reference_tests, "total", 0) + total
+    test_reaper_selection_parity_unpinned_by_reference_tests.total = acc
+
+
+def test_reaper_brute_force_selected_something():
+    total = getattr(test_reaper_selection_parity_unpinned_by_reference_tests, "total", None)
+    if total is None:
+        pytest.skip("runs after the reaper brute-force cases")
+    assert total > 200, total
