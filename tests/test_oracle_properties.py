@@ -507,3 +507,39 @@ def test_reaper_brute_force_selected_something():
     if total is None:
         pytest.skip("runs after the reaper brute-force cases")
     assert total > 200, total
+
+
+@pytest.mark.parametrize("config,nm,ni,seed", [("C2", 500, 300, 2), ("C3", 500, 400, 3), ("C5", 500, 400, 5), ("MIX", 300, 160, 5), ("MIX", 300, 97, 14)])
+def test_cluster_and_partition_stats_are_plain_sums(oracle_lib, config, nm, ni, seed):
+    """ClusterStats (MM:1570-1591) / InstanceSetStatsTracker (ISST:63-92) against sums over the instance table: capacity, free space of
+    the non-full instances only (ISST:67-71), instance and model-copy counts, the oldest positive lruTime (ISST:57-61); per partition
+    the same over its members, with the LRU as quirk N10 leaves it."""
+    fl = make_fleet(config, nm, ni, seed)
+    o = oracle_from_synth(fl, bulk=False)
+    rows = fl.inst_rows
+    live = [int(x) for x in o.cluster_order()]                          # the instances in the cluster state (shutting-down ones are not)
+    def sums(members):
+        cap = sum(int(rows["capacity"][i]) for i in members)
+        free = sum(_rem(rows[i]) for i in members if _rem(rows[i]) >= fl.min_space_units)
+        copies = sum(int(rows["count"][i]) for i in members)
+        return cap, free, len(members), copies
+    lrus = [int(rows["lru_time"][i]) for i in live if int(rows["lru_time"][i]) > 0]
+    glru = min(lrus) if lrus else LONG_MAX
+    g = o.cluster_stats()
+    assert (int(g["total_capacity"]), int(g["total_free"]), int(g["instance_count"]), int(g["model_copy_count"])) == sums(live)
+    assert int(g["global_lru"]) == glru
+    if fl.type_config is not None:
+        pstats, pids = o.partition_stats()
+        part_of = {i: o.instance_partition(i) for i in live}
+        assert sorted(set(part_of.values())) == sorted(int(p) for p in pids)
+        for st, pid in zip(pstats, pids):
+            members = [i for i in live if part_of[i] == int(pid)]
+            assert (int(st["total_capacity"]), int(st["total_free"]), int(st["instance_count"]), int(st["model_copy_count"])) == sums(members)
+            # N10, literal: an instance event recomputes ITS subset's LRU over all instances known at that moment (MM:1519-1541);
+            # the fleet was fed as ADDED events in index order, so a subset's LRU dates from its highest-index member's event
+            upto = max(members)
+            seen_l = [int(rows["lru_time"][i]) for i in live if i <= upto and int(rows["lru_time"][i]) > 0]
+            assert int(st["global_lru"]) == (min(seen_l) if seen_l else LONG_MAX)
+        # PARTITION_STATS_COMP (TCM:264-271): free desc, lru asc, capacity desc
+        keys = [(-int(s["total_free"]), int(s["global_lru"]), -int(s["total_capacity"])) for s in pstats]
+        assert keys == sorted(keys)
