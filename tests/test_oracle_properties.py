@@ -6,6 +6,8 @@ shortlist as a sorted-prefix enumeration), must give the same ordered shortlist,
   * shortlist == brute-force filter -> sort -> prefix (MM:4760-4771, 4806-4811, 4889-4937, N2/N3 literal)
   * the same with type constraints and preferences: constrainTo, non-simple (a) and (b) (MM:4788-4790, 4816-4887), N8
   * the reaper's proactive-load selection (MM:6455-6462, 6574-6577, 6616-6735, N12) as plain Python arithmetic and a sorted list
+  * a14: the rate-tracking loop body and the janitor's removeModelCopies / removeSecondModelCopy (MM:5684-5870, 6197-6335, N13)
+  * ClusterStats / partition stats as plain sums (N10 literal)
   * rpm filter == independent re-derivation (MM:4957-4980)
   * PLACEMENT_ORDER is a strict weak order on uniform-`vers` fleets and the cluster order is sorted under it (MM:4646-4703)
 """
@@ -543,3 +545,209 @@ def test_cluster_and_partition_stats_are_plain_sums(oracle_lib, config, nm, ni, 
         # PARTITION_STATS_COMP (TCM:264-271): free desc, lru asc, capacity desc
         keys = [(-int(s["total_free"]), int(s["global_lru"]), -int(s["total_capacity"])) for s in pstats]
         assert keys == sorted(keys)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a14: the rate-tracking task's loop body (MM:5684-5806, getExcludeSet MM:5835-5856, loadedSince MM:5858-5870) and the janitor's
+# removeModelCopies / removeSecondModelCopy (MM:6197-6335), per cache entry, as plain Python over dicts -- against
+# orc_rate_task_eval / orc_janitor_eval.  Inputs the Java reads from elsewhere (typeSetStats, instanceSetStats, PLACEMENT_ORDER)
+# are taken from the oracle's own restatements of those, which other tests pin; what is re-derived here is the arithmetic.
+# ---------------------------------------------------------------------------------------------------------------
+def brute_rate_entry(e, p, inst_count, have_tc, tstats, loaded, failed, rows, order, order_set):
+    """e: cache-entry dict; loaded / failed: [(instance, load time)]; returns the entry's outcome as a dict."""
+    o = dict(action=0, copies_to_load=0, load_last_used=0, rpm=0, i1=e["i1"], i2=e["i2"], set_heavy=0)
+    if inst_count < 2:
+        return o
+    time_delta = p["now"] - p["last_check_time"]
+    lower, upper = p["iteration"] - p["second_copy_max_age_iters"], p["iteration"] - p["second_copy_min_age_iters"]
+    suitable = inst_count
+    if have_tc:
+        suitable = tstats["instance_count"]
+        if suitable < 2:
+            return o
+    thr = p["scale_up_rpm_threshold"]
+    heavy = _trunc_div(thr * 3, 4)
+    rpm = _trunc_div(e["count"] * 60_000, time_delta)
+    o["rpm"] = rpm
+    if rpm > heavy:
+        o["set_heavy"] = 1
+    if not loaded:
+        return o
+    cand = suitable - (len(loaded) + len(failed))
+    if cand <= 0:
+        return o
+    if len(loaded) == 1:
+        i1, i2 = e["i1"], e["i2"]
+        in1 = in2 = False
+        if i2 >= lower and i1 <= upper:
+            in1, in2 = i1 >= lower, i2 <= upper
+        if in2 or not in1:
+            o["i1"] = i2
+        o["i2"] = p["iteration"]
+        if in1 or in2:
+            if tstats["total_capacity"] == 0:
+                return o                                                # ArithmeticException, caught at MM:5797
+            if _trunc_div(10 * tstats["total_free"], tstats["total_capacity"]) >= 1 or \
+                    (p["now"] - tstats["global_lru"]) > p["second_copy_lru_threshold_ms"]:
+                o.update(action=1, copies_to_load=1, load_last_used=p["last_check_time"])
+                return o
+    if rpm < thr:
+        return o
+    cutoff = p["now"] - (time_delta + p["rate_check_interval_ms"] + 2 * p["assume_completed_ms"])
+    if any(i != e["instance"] and ts > cutoff for i, ts in loaded):     # loadedSince(mr, cutoff, instanceId)
+        return o
+    # invokeCounter.getBusyness(): the pod's own request rate; the oracle and the product take the pod's PUBLISHED rpm for it
+    # (0 for a pod that is not in the cluster state, e.g. shutting down)
+    our_rpm = int(rows[e["instance"]]["rpm"]) if e["instance"] in order_set else 0
+    max_rpm = max(thr * 4, our_rpm - 2 * thr)
+    exclude = [i for i in order if i != e["instance"] and int(rows[i]["rpm"]) > max_rpm]
+    if exclude:
+        holders = {i for i, _ in loaded} | {i for i, _ in failed}
+        cand -= sum(1 for i in exclude if i not in holders)
+        cand -= len(exclude)                                            # (sic: subtracted again, MM:5767)
+        if cand <= 0:
+            return o
+    copies = min(_trunc_div(rpm, thr), cand)
+    if copies > 2:
+        copies = min(copies, suitable // 3)
+    o.update(action=2, copies_to_load=copies, load_last_used=p["now"] + 20_000)
+    return o
+
+
+def brute_janitor_entry(e, p, have_tc, local_stats, loaded, lul, ids, shutting_down, pos):
+    """removeModelCopies for the entry's pod; local_stats: instanceSetStats() of that pod (None: EMPTY_STATS, quirk N13)."""
+    if not p["can_remove"] or e["last_used"] == 0 or len(loaded) < 2:
+        return 0
+    st = local_stats if local_stats is not None else dict(total_capacity=0, total_free=0, global_lru=LONG_MAX)
+    if st["total_capacity"] == 0 or _trunc_div(st["total_free"] * 100, st["total_capacity"]) > 5:
+        return 0
+    other = None
+    for i, _ in sorted(loaded, key=lambda x: ids[x[0]]):                # TreeMap key order
+        if i != e["instance"] and not shutting_down[i]:
+            other = i
+            break
+    if other is None:
+        return 0
+    now = p["now"]
+    if len(loaded) == 2:
+        cache_age = now - st["global_lru"]
+        down_age = _trunc_div(cache_age, 10)
+        if e["last_heavy"] == 0 or (now - e["last_heavy"]) < _trunc_div(cache_age, 5):
+            down_age = min(p["second_copy_remove_max_age_ms"], down_age)
+        if (now - e["last_used"]) > down_age:
+            if shutting_down[e["instance"]]:
+                return 0
+            return 0 if pos[other] > pos[e["instance"]] else 1         # PLACEMENT_ORDER.compare(other, this) > 0: the other pod flushes
+        return 0
+    if lul > 0 and now - lul < 8 * p["rate_check_interval_ms"]:
+        return 0
+    if any(ts > now - 1_800_000 for _, ts in loaded):
+        return 0
+    min_age = _trunc_div(3 * st["global_lru"] + 10_400_000, 100)
+    min_age = 600_000 if min_age < 600_000 else (18_000_000 if min_age > 18_000_000 else min_age)
+    if now - e["last_heavy"] < min_age:
+        return 0
+    since = now - p["last_check_time"]
+    if since < p["rate_check_interval_ms"] // 10:
+        return 0
+    if _trunc_div(e["count"] * 60_000, since) > _trunc_div(p["scale_up_rpm_threshold"] * 2, 3):
+        return 0
+    return 1
+
+
+@pytest.mark.parametrize("config,nm,ni,seed", [("C2", 3000, 300, 2), ("C3", 3000, 400, 3), ("C5", 3000, 400, 5), ("MIX", 1500, 160, 14),
+                                               ("MIX", 1500, 200, 8)])
+def test_scale_arithmetic_parity_unpinned_by_reference_tests(oracle_lib, config, nm, ni, seed):
+    import ctypes as C
+    rng = np.random.default_rng(seed)
+    fl = make_fleet(config, nm, ni, seed)
+    keep = np.minimum(fl.edge_off[1:] - fl.edge_off[:-1], 4)
+    off = np.zeros(nm + 1, dtype=np.int64)
+    np.cumsum(keep, out=off[1:])
+    inst = np.concatenate([fl.edge_inst[fl.edge_off[m]:fl.edge_off[m] + keep[m]] for m in range(nm)]).astype(np.int32)
+    n_loaded = np.minimum(fl.n_loaded, keep).astype(np.int32)
+    ts = np.where(rng.uniform(size=len(inst)) < 0.3, fl.now_ms - rng.integers(0, 120_000, size=len(inst)),
+                  fl.now_ms - rng.integers(0, 4 * 3_600_000, size=len(inst))).astype(np.int64)
+    lul = np.where(rng.uniform(size=nm) < 0.3, fl.now_ms - rng.integers(0, 200_000, size=nm), 0).astype(np.int64)
+    o = oracle_from_synth(fl)
+    n = 4000
+    rec = np.zeros(n, dtype=ob.SCALE_IN)
+    models = rng.integers(0, nm, size=n)
+    rec["model"] = models
+    for r in range(n):
+        m = int(models[r]); k = int(n_loaded[m])
+        rec["instance"][r] = int(inst[off[m] + rng.integers(0, k)]) if k and rng.uniform() < 0.9 else int(rng.integers(0, ni))
+    rec["count"] = np.where(rng.uniform(size=n) < 0.5, rng.integers(0, 50, size=n), rng.integers(0, 20_000, size=n))
+    rec["last_used"] = np.where(rng.uniform(size=n) < 0.05, 0, fl.now_ms - rng.integers(0, 40 * 3_600_000, size=n))
+    rec["last_heavy"] = np.where(rng.uniform(size=n) < 0.4, 0, fl.now_ms - rng.integers(0, 30 * 3_600_000, size=n))
+    rec["flags"] = (rng.uniform(size=n) < 0.15).astype(np.int32)
+    it = 5000
+    rec["i1"] = it - rng.integers(0, 400, size=n)
+    rec["i2"] = np.minimum(it, rec["i1"] + rng.integers(0, 300, size=n))
+    m64 = models.astype(np.int64)
+    deg = (off[m64 + 1] - off[m64]).astype(np.int64)
+    eoff = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(deg, out=eoff[1:])
+    einst = np.concatenate([inst[off[m]:off[m + 1]] for m in m64]).astype(np.int32)
+    ets = np.concatenate([ts[off[m]:off[m + 1]] for m in m64]).astype(np.int64)
+    nl = n_loaded[m64].astype(np.int32)
+    tidx = fl.model_type[m64].astype(np.int32)
+    lulr = lul[m64].astype(np.int64)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    names = (C.c_char_p * len(fl.type_names))(*[t.encode() for t in fl.type_names])
+    # what the brute force reads
+    stat_names = ("total_capacity", "total_free", "global_lru", "instance_count", "model_copy_count")
+    as_dict = lambda s: {k: int(s[k]) for k in stat_names}
+    gst = as_dict(o.cluster_stats())
+    have_tc = fl.type_config is not None
+    tst = {t: as_dict(o.type_stats(name)) for t, name in enumerate(fl.type_names)}
+    order = [int(x) for x in o.cluster_order()]
+    order_set = set(order)
+    pos = {i: k for k, i in enumerate(order)}
+    rows = fl.inst_rows
+    sd = [bool(x) for x in rows["shutting_down"]]
+    for i in range(ni):
+        pos.setdefault(i, 1 << 30)
+    pst = {}
+    if have_tc:
+        ps, pids = o.partition_stats()
+        pst = {int(pid): as_dict(s) for s, pid in zip(ps, pids)}
+    seen = dict(second=0, scale=0, remove=0)
+    for thr, can_remove, lru_thr in ((2000, 1, 6 * 3_600_000), (300, 1, 1000), (5, 0, 6 * 3_600_000)):
+        p = np.zeros(1, dtype=ob.SCALE_PARAMS)
+        p["now"], p["last_check_time"], p["iteration"], p["scale_up_rpm_threshold"] = fl.now_ms, fl.now_ms - 10_000, it, thr
+        p["second_copy_min_age_iters"], p["second_copy_max_age_iters"], p["second_copy_lru_threshold_ms"] = 42, 240, lru_thr
+        p["rate_check_interval_ms"], p["assume_completed_ms"], p["second_copy_remove_max_age_ms"], p["can_remove"] = 10_000, 30_000, 36_000_000, can_remove
+        pd = {k: int(p[k][0]) for k in p.dtype.names if k != "pad"}
+        up, down = np.zeros(n, dtype=ob.SCALE_OUT), np.zeros(n, dtype=ob.SCALE_OUT)
+        assert oracle_lib.orc_rate_task_eval(o.h, n, vp(rec), vp(p), names, len(fl.type_names), vp(tidx), vp(eoff), vp(einst), vp(ets), vp(nl), vp(up)) == 0
+        assert oracle_lib.orc_janitor_eval(o.h, n, vp(rec), vp(p), vp(eoff), vp(einst), vp(ets), vp(nl), vp(lulr), vp(down)) == 0
+        for r in range(n):
+            e = {k: int(rec[k][r]) for k in ("instance", "model", "count", "last_used", "last_heavy", "i1", "i2", "flags")}
+            edges = [(int(einst[q]), int(ets[q])) for q in range(eoff[r], eoff[r + 1])]
+            loaded, failed = edges[:int(nl[r])], edges[int(nl[r]):]
+            ty = int(tidx[r])
+            b = brute_rate_entry(e, pd, gst["instance_count"], have_tc, tst[ty] if have_tc else gst, loaded, failed, rows, order, order_set)
+            for k in ("action", "copies_to_load", "load_last_used", "rpm", "i1", "i2", "set_heavy"):
+                assert b[k] == int(up[k][r]), str((thr, r, k, b, [int(up[x][r]) for x in up.dtype.names], ty, len(loaded), len(failed), e))
+            if have_tc:
+                part = o.instance_partition(e["instance"])
+                local = None if (e["flags"] & 1) or part not in pst else pst[part]
+            else:
+                local = gst
+            rm = brute_janitor_entry(e, pd, have_tc, local, loaded, int(lulr[r]), fl.inst_ids, sd, pos)
+            assert rm == int(down["remove"][r]), (thr, r, rm, down[r], e)
+            seen["second"] += b["action"] == 1
+            seen["scale"] += b["action"] == 2
+            seen["remove"] += rm
+    acc = getattr(test_scale_arithmetic_parity_unpinned_by_reference_tests, "seen", dict(second=0, scale=0, remove=0))
+    for k in seen:
+        acc[k] += seen[k]
+    test_scale_arithmetic_parity_unpinned_by_reference_tests.seen = acc
+
+
+def test_scale_brute_force_reached_every_outcome():
+    seen = getattr(test_scale_arithmetic_parity_unpinned_by_reference_tests, "seen", None)
+    if seen is None:
+        pytest.skip("runs after the scale brute-force cases")
+    assert seen["second"] > 50 and seen["scale"] > 50 and seen["remove"] > 20, seen
