@@ -751,3 +751,44 @@ def test_scale_brute_force_reached_every_outcome():
     if seen is None:
         pytest.skip("runs after the scale brute-force cases")
     assert seen["second"] > 50 and seen["scale"] > 50 and seen["remove"] > 20, seen
+
+
+@pytest.mark.parametrize("with_types,fill,seed", [(False, 0.95, 4), (True, 0.90, 5), (False, 0.99, 6)])
+def test_closed_loop_oracle_conserves_copies_and_capacity(oracle_lib, with_types, fill, seed):
+    """Invariants of the closed loop (oracle/mm_sim.inc) after every publish window of a churn trace: the registry holds
+    exactly the copies that are resident in the per-instance caches (every admitted load registers, every eviction and removal
+    deregisters: MM:5203, 2875-2931), no cache is over its capacity (CLHM:329-352), every eviction names a model that was
+    admitted or seeded, and an accepted decision never targets an instance the model already held at the window's start."""
+    from modelmesh_b200.synth import make_churn
+    w = make_churn(8000, 60, seed, fill=fill, with_types=with_types)
+    fl = w.fleet
+    o = oracle_from_synth(fl, bulk=False)
+    models = np.zeros(fl.n_models, dtype=ob.SIM_MODEL)
+    models["last_used"], models["type_idx"], models["size_units"] = fl.model_last_used, fl.model_type, fl.model_size
+    sim = ob.OracleSim(o, models, fl.type_names, fl.edge_off, fl.edge_inst, fl.n_loaded, w.capacity, w.load_timeout_ms, fl.now_ms - 60_000)
+    order = np.argsort(w.seed_instance, kind="stable")
+    bounds = np.searchsorted(w.seed_instance[order], np.arange(fl.n_instances + 1))
+    for i in range(fl.n_instances):
+        sel = order[bounds[i]:bounds[i + 1]]
+        if len(sel):
+            sim.seed(i, w.seed_model[sel], w.seed_last_used[sel], w.seed_weight[sel], w.seed_load_ts[sel], fl.now_ms)
+    accepted = evicted = 0
+    for ep in range(6):
+        before = {m: set(int(x) for x in sim.model_copies(m)[0]) for m in range(fl.n_models)} if ep == 0 else after
+        ev = w.events(ep, 1200, seed)
+        now0 = fl.now_ms + ep * w.window_ms
+        dec, evi, rows, npub, carry = sim.step(ev, now0, now0 + w.window_ms, 400 + ep)
+        after = {m: set(int(x) for x in sim.model_copies(m)[0]) for m in range(fl.n_models)}
+        resident = sum(sim.lru_state(i)[2] for i in range(fl.n_instances))
+        assert resident == sum(len(v) for v in after.values()), ep
+        for i in range(fl.n_instances):
+            assert sim.lru_state(i)[1] <= int(w.capacity[i]), (ep, i)
+            assert 0 <= int(rows["used"][i]) <= int(rows["capacity"][i]) + int(w.capacity[i])
+        ok = dec[dec["status"] == ob.SIM_ACCEPTED]
+        for d in ok:
+            t = int(d["self"]) if int(d["target"]) == ob.SELF else int(d["target"])
+            assert 0 <= t < fl.n_instances and t not in before[int(d["model"])], (ep, d)
+        for e in evi:
+            assert 0 <= int(e["model"]) < fl.n_models and 0 <= int(e["instance"]) < fl.n_instances and int(e["weight"]) != 0
+        accepted += len(ok); evicted += len(evi)
+    assert accepted > 100 and evicted > 50, (accepted, evicted)
