@@ -32,5 +32,15 @@ for cfg, nm, ni in (("MIX", 400, 300), ("C5", 800, 700), ("C3", 800, 1300)):
             sd = make_decisions(fl, 800, 3)
             f.place_batch(sd.dec, fl.now_ms, 5, fresh=sd.fresh, extra=sd.extra)
         f.close()
+# long rows: the chunk machinery of decide_stream (8-step gathers, chunks taken at once), a full best, non-simple (b)
+for cfg, nm, ni in (("C5", 600, 10000), ("C5", 600, 5000), ("C3", 600, 10000)):
+    fl = make_fleet(cfg, nm, ni, 5)
+    s = solver_from_synth(fl, lib)
+    for win, budget in ((12, 192), (0, 1000), (3, 400), (12, 7)):
+        lib.mmp_emul_set_window(2); lib.mmp_emul_set_lane_window(win); lib.mmp_emul_set_lane_budget(budget)
+        for plain in (True, False):
+            sd = make_decisions(fl, 600, 5, sweep=plain, plain=plain)
+            s.place_batch(sd.dec, fl.now_ms, 5, fresh=sd.fresh if len(sd.fresh) else None, extra=sd.extra if len(sd.extra) else None)
+    s.close()
 print("asan/ubsan: clean")
 PY
