@@ -8,6 +8,8 @@ shortlist as a sorted-prefix enumeration), must give the same ordered shortlist,
   * the reaper's proactive-load selection (MM:6455-6462, 6574-6577, 6616-6735, N12) as plain Python arithmetic and a sorted list
   * a14: the rate-tracking loop body and the janitor's removeModelCopies / removeSecondModelCopy (MM:5684-5870, 6197-6335, N13)
   * ClusterStats / partition stats as plain sums (N10 literal)
+  * a6: the converged per-type instance sets of TypeConstraintManager as set comprehensions (TCM:92-95, 455-486, 680-747, N11)
+  * invariants of the closed loop (registry == caches, capacities) after every window
   * rpm filter == independent re-derivation (MM:4957-4980)
   * PLACEMENT_ORDER is a strict weak order on uniform-`vers` fleets and the cluster order is sorted under it (MM:4646-4703)
 """
@@ -792,3 +794,65 @@ def test_closed_loop_oracle_conserves_copies_and_capacity(oracle_lib, with_types
             assert 0 <= int(e["model"]) < fl.n_models and 0 <= int(e["instance"]) < fl.n_instances and int(e["weight"]) != 0
         accepted += len(ok); evicted += len(evi)
     assert accepted > 100 and evicted > 50, (accepted, evicted)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a6: the converged per-type instance sets of TypeConstraintManager as set comprehensions -- membership as updateInstance
+# computes it (TCM:455-486: required = ALL labels, preferred = ANY label, independently), then one refreshPerTypeInstanceSets
+# (TCM:680-747): instance scores = 4 x prohibited types - configured preferences, the default preferred set = the top-scoring
+# instances (none when all scores are equal), N11: a type WITHOUT required labels gets the default preferred set even when it
+# configures preferred labels; a type with required labels and no configured preference gets the top-scoring allowed ones.
+# ---------------------------------------------------------------------------------------------------------------
+def brute_type_sets(type_config, type_names, labels, live):
+    def matches(inst, tl, all_):
+        if not labels[inst] or not tl:
+            return False
+        return all(l in labels[inst] for l in tl) if all_ else any(l in labels[inst] for l in tl)
+    # ConfigTypeConstraints (TCM:92-95): both lists sorted and de-duplicated, preferred labels that are also required dropped
+    cfg = {t: (sorted(set(c.get("required", []))), sorted(set(c.get("preferred", [])) - set(c.get("required", [])))) for t, c in (type_config or {}).items()}
+    allowed = {t: (None if not req else {i for i in live if matches(i, req, True)}) for t, (req, _) in cfg.items()}
+    conf_pref = {}
+    for t, (_, prf) in cfg.items():
+        s = {i for i in live if matches(i, prf, False)}
+        conf_pref[t] = s if s else None
+    scores = {i: 4 * sum(1 for t in cfg if allowed[t] is not None and i not in allowed[t]) - sum(1 for t in cfg if conf_pref[t] and i in conf_pref[t])
+              for i in live}
+    def infer(include):
+        pool = [i for i in live if include is None or i in include]
+        if not pool:
+            return None
+        mn, mx = min(scores[i] for i in pool), max(max(scores[i] for i in pool), 0)
+        top = {i for i in pool if scores[i] >= mx} if any(scores[i] >= mx for i in pool) else set()
+        return top if mn < mx and top else None
+    default_pref = infer(None)
+    out = {}
+    for t in type_names:
+        if t not in cfg:
+            out[t] = (None, default_pref)
+        elif allowed[t] is None:
+            out[t] = (None, default_pref)                              # N11
+        else:
+            pref = conf_pref[t] if (conf_pref[t] is not None or not allowed[t]) else infer(allowed[t])
+            out[t] = (allowed[t], pref)
+    return out
+
+
+@pytest.mark.parametrize("config,nm,ni,seed", [("C3", 200, 400, 3), ("C3", 200, 97, 4), ("C5", 200, 500, 5), ("C5", 200, 64, 7),
+                                               ("MIX", 200, 160, 5), ("MIX", 200, 300, 8), ("MIX", 200, 97, 14), ("MIX", 200, 200, 21)])
+def test_type_sets_parity_unpinned_by_reference_tests(oracle_lib, config, nm, ni, seed):
+    fl = make_fleet(config, nm, ni, seed)
+    if fl.type_config is None:
+        pytest.skip("no type constraints drawn")
+    o = oracle_from_synth(fl, bulk=False)
+    live = [int(x) for x in o.cluster_order()]
+    want = brute_type_sets(fl.type_config, fl.type_names, [set(l) for l in fl.inst_labels], live)
+    checked = 0
+    for name in fl.type_names:
+        a, p = o.type_sets(name, fl.n_instances)
+        wa, wp = want[name]
+        got_a = None if a is None else {int(x) for x in np.nonzero(a)[0]} & set(live)
+        got_p = None if p is None else {int(x) for x in np.nonzero(p)[0]} & set(live)
+        assert got_a == wa, (name, sorted(got_a or [])[:8], sorted(wa or [])[:8])
+        assert (got_p or None) == (wp or None), (name, sorted(got_p or [])[:8], sorted(wp or [])[:8])
+        checked += 1
+    assert checked == len(fl.type_names)
