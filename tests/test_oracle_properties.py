@@ -11,7 +11,8 @@ shortlist as a sorted-prefix enumeration), must give the same ordered shortlist,
   * a6: the converged per-type instance sets of TypeConstraintManager as set comprehensions (TCM:92-95, 455-486, 680-747, N11)
   * invariants of the closed loop (registry == caches, capacities) after every window
   * rpm filter == independent re-derivation (MM:4957-4980)
-  * PLACEMENT_ORDER is a strict weak order on uniform-`vers` fleets and the cluster order is sorted under it (MM:4646-4703)
+  * PLACEMENT_ORDER is a strict weak order on uniform-`vers` fleets and the cluster order is sorted under it (MM:4646-4703);
+    the comparator itself re-derived and compared on sampled pairs, mixed versions (N1) included
 """
 import numpy as np
 import pytest
@@ -856,3 +857,83 @@ def test_type_sets_parity_unpinned_by_reference_tests(oracle_lib, config, nm, ni
         assert (got_p or None) == (wp or None), (name, sorted(got_p or [])[:8], sorted(wp or [])[:8])
         checked += 1
     assert checked == len(fl.type_names)
+
+
+def brute_compare(r1, id1, loc1, zone1, lab1, r2, id2, loc2, zone2, lab2, min_space, min_churn_age):
+    """PLACEMENT_ORDER.compare (MM:4646-4703) for two DIFFERENT records, from the Java text; returns the sign."""
+    sgn = lambda a, b: (a > b) - (a < b)
+    def nulls_last(a, b):
+        if a is None or b is None:
+            return 0 if a is b else (1 if a is None else -1)
+        return sgn(a, b)
+    sd1, sd2 = bool(r1["shutting_down"]), bool(r2["shutting_down"])
+    if sd1 != sd2:
+        return 1 if sd1 else -1
+    v1, v2 = int(r1["vers"]), int(r2["vers"])
+    rem1, rem2 = _rem(r1), _rem(r2)
+    full1, full2 = rem1 < min_space, rem2 < min_space
+    if v1 != v2:                                                         # N1: "prefer newer version unless it's saturated"
+        if v1 > v2:
+            if not full1 or int(r1["lru_time"]) > min_churn_age * 2:
+                return -1
+        elif not full2 or int(r2["lru_time"]) > min_churn_age * 2:
+            return 1
+    if full1 != full2:
+        return 1 if full1 else -1
+    if full1:
+        d = sgn(int(r1["lru_time"]), int(r2["lru_time"]))
+        if d:
+            return d
+    d = sgn(int(r1["count"]) - int(r2["count"]), 0)
+    if d:
+        return d
+    d = sgn(rem2, rem1)
+    if d:
+        return d
+    if not full1:
+        d = sgn(int(r1["lru_time"]), int(r2["lru_time"]))
+        if d:
+            return d
+    lip1, lip2 = int(r1["l_in_prog"]), int(r2["l_in_prog"])
+    for d in (sgn(int(r2["l_threads"]) - lip2, int(r1["l_threads"]) - lip1), sgn(lip1, lip2), sgn(int(r2["capacity"]), int(r1["capacity"])),
+              sgn(int(r1["rpm"]), int(r2["rpm"])), sgn(id1, id2), nulls_last(loc1, loc2), nulls_last(zone1, zone2)):
+        if d:
+            return d
+    l1, l2 = list(lab1 or []), list(lab2 or [])
+    if len(l1) != len(l2):
+        return sgn(len(l1), len(l2))
+    for a, b in zip(l1, l2):
+        if a != b:
+            return sgn(a, b)
+    return 0
+
+
+@pytest.mark.parametrize("mixed_vers", [False, True])
+@pytest.mark.parametrize("config,ni,seed", [("C2", 300, 2), ("C3", 400, 3), ("C5", 400, 5), ("MIX", 200, 8), ("MIX", 160, 14), ("MIX", 120, 21)])
+def test_placement_order_comparator_parity_unpinned_by_reference_tests(oracle_lib, config, ni, seed, mixed_vers):
+    """The oracle's comparator against the Java text re-derived in Python on sampled pairs, with uniform and with mixed
+    instance versions (N1's corner: newer-but-saturated instances), equal-key instances included (MIX draws them)."""
+    fl = make_fleet(config, 50, ni, seed)
+    rng = np.random.default_rng(seed)
+    if mixed_vers:
+        fl.inst_rows["vers"] = np.where(rng.uniform(size=ni) < 0.4, 8, 7)
+    o = oracle_from_synth(fl)
+    live = [int(x) for x in o.cluster_order()]
+    rows = fl.inst_rows
+    seen_tie = 0
+    for _ in range(6000):
+        a, b = (live[int(k)] for k in rng.integers(0, len(live), 2))
+        if a == b:
+            continue
+        want = brute_compare(rows[a], fl.inst_ids[a], fl.inst_locs[a], fl.inst_zones[a], fl.inst_labels[a],
+                             rows[b], fl.inst_ids[b], fl.inst_locs[b], fl.inst_zones[b], fl.inst_labels[b],
+                             fl.min_space_units, fl.min_churn_age_ms)
+        got = o.compare(a, b)
+        assert (got > 0) - (got < 0) == want, (a, b, got, want, rows[a], rows[b])
+        ra, rb = rows[a], rows[b]
+        seen_tie += all(int(ra[k]) == int(rb[k]) for k in ("count", "capacity", "used", "lru_time", "rpm", "l_in_prog", "l_threads"))
+    if not mixed_vers:  # a uniform-vers cluster state is sorted under the re-derived comparator too
+        for a, b in zip(live[:-1], live[1:]):
+            assert brute_compare(rows[a], fl.inst_ids[a], fl.inst_locs[a], fl.inst_zones[a], fl.inst_labels[a],
+                                 rows[b], fl.inst_ids[b], fl.inst_locs[b], fl.inst_zones[b], fl.inst_labels[b],
+                                 fl.min_space_units, fl.min_churn_age_ms) < 0
