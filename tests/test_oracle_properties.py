@@ -10,6 +10,7 @@ shortlist as a sorted-prefix enumeration), must give the same ordered shortlist,
   * ClusterStats / partition stats as plain sums (N10 literal)
   * a6: the converged per-type instance sets of TypeConstraintManager as set comprehensions (TCM:92-95, 455-486, 680-747, N11)
   * invariants of the closed loop (registry == caches, capacities) after every window
+  * a10: the time-ordered weighted LRU as a plain Python list (CLHM / LinkedDeque)
   * rpm filter == independent re-derivation (MM:4957-4980)
   * PLACEMENT_ORDER is a strict weak order on uniform-`vers` fleets and the cluster order is sorted under it (MM:4646-4703);
     the comparator itself re-derived and compared on sampled pairs, mixed versions (N1) included
@@ -937,3 +938,119 @@ def test_placement_order_comparator_parity_unpinned_by_reference_tests(oracle_li
             assert brute_compare(rows[a], fl.inst_ids[a], fl.inst_locs[a], fl.inst_zones[a], fl.inst_labels[a],
                                  rows[b], fl.inst_ids[b], fl.inst_locs[b], fl.inst_zones[b], fl.inst_labels[b],
                                  fl.min_space_units, fl.min_churn_age_ms) < 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a10: the time-ordered weighted LRU (clhm/ConcurrentLinkedHashMap + LinkedDeque, single-threaded reading: every read is
+# drained at once) as a plain Python list, from the Java text: put / putIfAbsent (CLHM:821-858, AddTask 590-610), get
+# (731-738 -> touch 1357-1360 -> LinkedDeque.reposition / insert LD:243-288), replaceQuietly (963-984, UpdateTask 631-652),
+# remove (860-871), setCapacity (305-316: evict, notify, oldestTime NOT refreshed), forceSetLastUsedTime (756-768: no
+# reposition), evict from the head while weightedSize > capacity with |weight| on makeDead (329-352), oldestTime (1129-1133).
+# ---------------------------------------------------------------------------------------------------------------
+class BruteLru:
+    def __init__(self, capacity):
+        self.cap, self.wsize, self.oldest = capacity, 0, -1
+        self.deque = []          # [key, weight, lastUsed], oldest first
+        self.pending = []
+
+    def _find(self, key):
+        for n in self.deque:
+            if n[0] == key:
+                return n
+        return None
+
+    def _insert(self, node):    # LD:258-288: after the last element whose lastUsed <= ts, scanning from the tail
+        pos = len(self.deque)
+        while pos > 0 and self.deque[pos - 1][2] > node[2]:
+            pos -= 1
+        self.deque.insert(pos, node)
+
+    def _reposition(self, node):  # LD:243-255
+        i = next(k for k, n in enumerate(self.deque) if n is node)
+        lu = node[2]
+        if i == 0 or self.deque[i - 1][2] <= lu:
+            if i == len(self.deque) - 1 or self.deque[i + 1][2] >= lu:
+                return
+        del self.deque[i]
+        self._insert(node)
+
+    def _evict(self, ev_index):
+        while self.wsize > self.cap and self.deque:
+            k, w, lu = self.deque.pop(0)
+            self.wsize -= abs(w)
+            self.pending.append((k, ev_index, lu, w))
+
+    def _oldest(self):
+        self.oldest = self.deque[0][2] if self.deque else -1
+
+    def _after_read(self, node, last_used, now):
+        t = last_used if last_used > 0 else 0
+        node[2] = now if t == 0 else max(node[2], t)
+        self._reposition(node)
+        self._oldest()
+
+    def apply(self, op, key, weight, last_used, ev_index, now, out):
+        node = self._find(key)
+        if op == 0:
+            if node is None:
+                n = [key, weight, now if last_used == 0 else max(0, last_used)]
+                self.wsize += weight
+                self._insert(n)
+                self._evict(ev_index)
+                self._oldest()
+                out.extend(self.pending); self.pending = []
+            else:
+                self._after_read(node, last_used, now)
+        elif op == 1:
+            if node is not None:
+                self._after_read(node, last_used, now)
+        elif op == 2:
+            if node is not None:
+                diff = weight - node[1]
+                node[1] = weight
+                if diff != 0:
+                    self.wsize += diff
+                    self._evict(ev_index)
+                    self._oldest()
+                    if diff > 0:
+                        out.extend(self.pending); self.pending = []
+        elif op == 3:
+            if node is not None:
+                self.wsize -= abs(node[1])
+                self.deque.remove(node)
+                self._oldest()
+        elif op == 4:
+            self.cap = weight
+            self._evict(ev_index)
+            out.extend(self.pending); self.pending = []
+        elif op == 5:
+            if node is not None:
+                node[2] = last_used
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_time_ordered_lru_matches_a_plain_list(oracle_lib, seed):
+    rng = np.random.default_rng(100 + seed)
+    cap = int(rng.integers(20_000, 60_000))
+    o, b = ob.OracleLru(cap), BruteLru(cap)
+    now = 1_000_000
+    evictions = 0
+    for batch in range(10):
+        n = 400
+        ev = np.zeros(n, dtype=ob.LRU_EVENT)
+        r = rng.uniform(size=n)
+        ev["op"] = np.where(r < 0.45, 0, np.where(r < 0.72, 1, np.where(r < 0.85, 2, np.where(r < 0.94, 3, np.where(r < 0.97, 4, 5)))))
+        ev["key"] = rng.integers(0, 120, size=n)
+        ev["weight"] = np.where(ev["op"] == 4, rng.integers(15_000, 60_000, size=n), rng.integers(1, 6000, size=n))
+        ev["last_used"] = np.where(rng.uniform(size=n) < 0.3, 0, now - rng.integers(0, 500_000, size=n))
+        want = o.apply(ev, now)
+        got = []
+        for i in range(n):
+            b.apply(int(ev["op"][i]), int(ev["key"][i]), int(ev["weight"][i]), int(ev["last_used"][i]), i, now, got)
+        assert [(int(e["key"]), int(e["event"]), int(e["last_used"]), int(e["weight"])) for e in want] == got, batch
+        k, t, w = o.dump()
+        assert [list(x) for x in zip(k.tolist(), w.tolist(), t.tolist())] == b.deque, batch
+        assert o.weighted_size() == b.wsize and o.oldest_time() == b.oldest and o.size() == len(b.deque), batch
+        evictions += len(got)
+        now += int(rng.integers(1, 200_000))
+    assert evictions > 20
